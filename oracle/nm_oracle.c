@@ -1,0 +1,1407 @@
+/* nm_oracle.c — CPU oracle, plain C, fp64.  TEST INFRASTRUCTURE ONLY (see nm_oracle.h).
+ *
+ * Restates, stage by stage, what the reference executes for one environment step:
+ *   env layer : /root/reference/envs/nightmare_v3_env.py:145-371,399-497
+ *   physics   : MuJoCo 3.1.2 mj_step (called at envs/nightmare_v3_env.py:200), published pipeline
+ *               (SURVEY.md §3.2 and Appendix A).  MuJoCo is a third-party dependency that is absent
+ *               from /root/reference and not installable here -> PARITY UNPINNED against real MuJoCo.
+ * Written for clarity, not speed: dense matrices, generic kinematic tree (free/hinge/slide joints).
+ */
+#include "nm_oracle.h"
+
+#include <math.h>
+#include <pthread.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define MINVAL 1e-15
+#define MAXVAL 1e10
+#define TOLPLANEMESH 0.3 /* extra plane-mesh contacts must be this fraction of rbound apart (Appendix A.2) */
+
+enum { JNT_FREE = 0, JNT_BALL = 1, JNT_SLIDE = 2, JNT_HINGE = 3 };
+enum { GEOM_PLANE = 0, GEOM_SPHERE = 2, GEOM_MESH = 7 };
+enum { INT_EULER = 0, INT_RK4 = 1, INT_IMPLICIT = 2, INT_IMPLICITFAST = 3 };
+
+/* ------------------------------------------------------------------------------------------ model */
+struct nmo_model {
+  unsigned char* raw;
+  int nq, nv, nu, nbody, njnt, ngeom, nsite, nsensor, nhv, nhn;
+  int integrator, solver, cone, iterations, noslip_iterations, eulerdamp;
+  double timestep, gravity[3], tolerance, noslip_tolerance, impratio, meaninertia;
+  const double *qpos0, *body_pos, *body_quat, *body_ipos, *body_iquat, *body_mass, *body_inertia, *body_invweight0;
+  const int *body_parent, *body_rootid, *body_jntadr, *body_jntnum, *body_dofadr, *body_dofnum;
+  const int *jnt_type, *jnt_body, *jnt_qposadr, *jnt_dofadr;
+  const double *jnt_pos, *jnt_axis;
+  const int *dof_body, *dof_jnt, *dof_parent;
+  const double *dof_damping, *dof_armature;
+  const int *act_dof, *act_ctrllimited, *act_forcelimited;
+  const double *act_gain, *act_bias, *act_gear, *act_ctrlrange, *act_forcerange;
+  const int *geom_type, *geom_body, *geom_condim, *geom_priority, *geom_plane, *geom_hull_adr, *geom_hull_num;
+  const double *geom_pos, *geom_quat, *geom_size, *geom_friction, *geom_solref, *geom_solimp, *geom_margin, *geom_gap, *geom_rbound;
+  const float* hull_vert;
+  const int *hull_nbr_adr, *hull_nbr;
+  const int *site_body, *sensor_site;
+  const double *site_pos, *site_size;
+};
+
+static const void* nmb_find(const unsigned char* raw, const char* name, int* code, long long* count) {
+  unsigned cnt;
+  memcpy(&cnt, raw + 4, 4);
+  size_t off = 8;
+  for (unsigned i = 0; i < cnt; i++) {
+    const char* nm = (const char*)(raw + off);
+    unsigned c, nd;
+    long long dims[4], nbytes;
+    memcpy(&c, raw + off + 32, 4);
+    memcpy(&nd, raw + off + 36, 4);
+    memcpy(dims, raw + off + 40, 32);
+    memcpy(&nbytes, raw + off + 72, 8);
+    off += 80;
+    if (strncmp(nm, name, 32) == 0) {
+      if (code) *code = (int)c;
+      long long n = 1;
+      for (unsigned k = 0; k < nd; k++) n *= dims[k];
+      if (count) *count = n;
+      return raw + off;
+    }
+    off += (size_t)nbytes + (size_t)((8 - nbytes % 8) % 8);
+  }
+  return NULL;
+}
+
+#define GETP(field, type)                                                     \
+  do {                                                                        \
+    m->field = (const type*)nmb_find(m->raw, #field, NULL, NULL);             \
+    if (!m->field) {                                                          \
+      snprintf(err, errlen, "nmb: missing array '%s'", #field);               \
+      nmo_model_free(m);                                                      \
+      return NULL;                                                            \
+    }                                                                         \
+  } while (0)
+
+nmo_model* nmo_model_load(const char* path, char* err, int errlen) {
+  char dummy[8];
+  if (!err) { err = dummy; errlen = 8; }
+  FILE* f = fopen(path, "rb");
+  if (!f) { snprintf(err, errlen, "cannot open %s", path); return NULL; }
+  fseek(f, 0, SEEK_END);
+  long sz = ftell(f);
+  fseek(f, 0, SEEK_SET);
+  nmo_model* m = (nmo_model*)calloc(1, sizeof(nmo_model));
+  m->raw = (unsigned char*)malloc((size_t)sz + 8);
+  if (fread(m->raw, 1, (size_t)sz, f) != (size_t)sz || memcmp(m->raw, "NMB1", 4) != 0) {
+    fclose(f);
+    snprintf(err, errlen, "%s is not an NMB1 file", path);
+    nmo_model_free(m);
+    return NULL;
+  }
+  fclose(f);
+  const int* sizes = (const int*)nmb_find(m->raw, "sizes", NULL, NULL);
+  const int* oi = (const int*)nmb_find(m->raw, "opt_int", NULL, NULL);
+  const double* orl = (const double*)nmb_find(m->raw, "opt_real", NULL, NULL);
+  if (!sizes || !oi || !orl) { snprintf(err, errlen, "nmb: missing header arrays"); nmo_model_free(m); return NULL; }
+  m->nq = sizes[0]; m->nv = sizes[1]; m->nu = sizes[2]; m->nbody = sizes[3]; m->njnt = sizes[4];
+  m->ngeom = sizes[5]; m->nsite = sizes[6]; m->nsensor = sizes[7]; m->nhv = sizes[8]; m->nhn = sizes[9];
+  m->integrator = oi[0]; m->solver = oi[1]; m->cone = oi[2]; m->iterations = oi[3];
+  m->noslip_iterations = oi[4]; m->eulerdamp = oi[5];
+  m->timestep = orl[0]; m->gravity[0] = orl[1]; m->gravity[1] = orl[2]; m->gravity[2] = orl[3];
+  m->tolerance = orl[4]; m->noslip_tolerance = orl[5]; m->impratio = orl[6]; m->meaninertia = orl[7];
+  GETP(qpos0, double); GETP(body_pos, double); GETP(body_quat, double); GETP(body_ipos, double);
+  GETP(body_iquat, double); GETP(body_mass, double); GETP(body_inertia, double); GETP(body_invweight0, double);
+  GETP(body_parent, int); GETP(body_rootid, int); GETP(body_jntadr, int); GETP(body_jntnum, int);
+  GETP(body_dofadr, int); GETP(body_dofnum, int);
+  GETP(jnt_type, int); GETP(jnt_body, int); GETP(jnt_qposadr, int); GETP(jnt_dofadr, int);
+  GETP(jnt_pos, double); GETP(jnt_axis, double);
+  GETP(dof_body, int); GETP(dof_jnt, int); GETP(dof_parent, int); GETP(dof_damping, double); GETP(dof_armature, double);
+  GETP(act_dof, int); GETP(act_ctrllimited, int); GETP(act_forcelimited, int);
+  GETP(act_gain, double); GETP(act_bias, double); GETP(act_gear, double); GETP(act_ctrlrange, double); GETP(act_forcerange, double);
+  GETP(geom_type, int); GETP(geom_body, int); GETP(geom_condim, int); GETP(geom_priority, int); GETP(geom_plane, int);
+  GETP(geom_hull_adr, int); GETP(geom_hull_num, int);
+  GETP(geom_pos, double); GETP(geom_quat, double); GETP(geom_size, double); GETP(geom_friction, double);
+  GETP(geom_solref, double); GETP(geom_solimp, double); GETP(geom_margin, double); GETP(geom_gap, double); GETP(geom_rbound, double);
+  GETP(hull_vert, float); GETP(hull_nbr_adr, int); GETP(hull_nbr, int);
+  GETP(site_body, int); GETP(sensor_site, int); GETP(site_pos, double); GETP(site_size, double);
+  return m;
+}
+
+void nmo_model_free(nmo_model* m) {
+  if (!m) return;
+  free(m->raw);
+  free(m);
+}
+
+int nmo_model_size(const nmo_model* m, const char* w) {
+  if (!strcmp(w, "nq")) return m->nq;
+  if (!strcmp(w, "nv")) return m->nv;
+  if (!strcmp(w, "nu")) return m->nu;
+  if (!strcmp(w, "nbody")) return m->nbody;
+  if (!strcmp(w, "njnt")) return m->njnt;
+  if (!strcmp(w, "ngeom")) return m->ngeom;
+  if (!strcmp(w, "nsite")) return m->nsite;
+  if (!strcmp(w, "nsensor")) return m->nsensor;
+  return -1;
+}
+
+/* ------------------------------------------------------------------------------------------ small math */
+static inline double dot3(const double* a, const double* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+static inline void cross3(double* r, const double* a, const double* b) {
+  double x = a[1] * b[2] - a[2] * b[1], y = a[2] * b[0] - a[0] * b[2], z = a[0] * b[1] - a[1] * b[0];
+  r[0] = x; r[1] = y; r[2] = z;
+}
+static inline double normalize3(double* v) {
+  double n = sqrt(dot3(v, v));
+  if (n < MINVAL) { v[0] = 1; v[1] = 0; v[2] = 0; return 0; }
+  v[0] /= n; v[1] /= n; v[2] /= n;
+  return n;
+}
+static inline void normalize4(double* q) {
+  double n = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+  if (n < MINVAL) { q[0] = 1; q[1] = q[2] = q[3] = 0; return; }
+  q[0] /= n; q[1] /= n; q[2] /= n; q[3] /= n;
+}
+static inline void mul_quat(double* r, const double* a, const double* b) {
+  double w = a[0] * b[0] - a[1] * b[1] - a[2] * b[2] - a[3] * b[3];
+  double x = a[0] * b[1] + a[1] * b[0] + a[2] * b[3] - a[3] * b[2];
+  double y = a[0] * b[2] - a[1] * b[3] + a[2] * b[0] + a[3] * b[1];
+  double z = a[0] * b[3] + a[1] * b[2] - a[2] * b[1] + a[3] * b[0];
+  r[0] = w; r[1] = x; r[2] = y; r[3] = z;
+}
+static inline void quat2mat(double* m, const double* q) {
+  double w = q[0], x = q[1], y = q[2], z = q[3];
+  m[0] = w * w + x * x - y * y - z * z; m[1] = 2 * (x * y - w * z); m[2] = 2 * (x * z + w * y);
+  m[3] = 2 * (x * y + w * z); m[4] = w * w - x * x + y * y - z * z; m[5] = 2 * (y * z - w * x);
+  m[6] = 2 * (x * z - w * y); m[7] = 2 * (y * z + w * x); m[8] = w * w - x * x - y * y + z * z;
+}
+static inline void mat_vec3(double* r, const double* m, const double* v) {
+  double x = m[0] * v[0] + m[1] * v[1] + m[2] * v[2];
+  double y = m[3] * v[0] + m[4] * v[1] + m[5] * v[2];
+  double z = m[6] * v[0] + m[7] * v[1] + m[8] * v[2];
+  r[0] = x; r[1] = y; r[2] = z;
+}
+static inline void axisangle2quat(double* q, const double* axis, double angle) {
+  double s = sin(0.5 * angle);
+  q[0] = cos(0.5 * angle); q[1] = axis[0] * s; q[2] = axis[1] * s; q[3] = axis[2] * s;
+}
+/* rotate vector by quaternion (≙ mju_rotVecQuat, env.py:217-219) */
+static inline void rot_vec_quat(double* r, const double* v, const double* q) {
+  double m[9];
+  quat2mat(m, q);
+  mat_vec3(r, m, v);
+}
+/* spatial inertia (10 numbers: Ixx Iyy Izz Ixy Ixz Iyz, m*r(3), m) times motion vector [w; v] */
+static void mul_inert_vec(double* res, const double* i, const double* v) {
+  res[0] = i[0] * v[0] + i[3] * v[1] + i[4] * v[2] - i[8] * v[4] + i[7] * v[5];
+  res[1] = i[3] * v[0] + i[1] * v[1] + i[5] * v[2] + i[8] * v[3] - i[6] * v[5];
+  res[2] = i[4] * v[0] + i[5] * v[1] + i[2] * v[2] - i[7] * v[3] + i[6] * v[4];
+  res[3] = i[8] * v[1] - i[7] * v[2] + i[9] * v[3];
+  res[4] = i[6] * v[2] - i[8] * v[0] + i[9] * v[4];
+  res[5] = i[7] * v[0] - i[6] * v[1] + i[9] * v[5];
+}
+/* motion x motion */
+static void cross_motion(double* r, const double* vel, const double* v) {
+  double a[3], b[3], c[3];
+  cross3(a, vel, v);          /* w x v_ang */
+  cross3(b, vel, v + 3);      /* w x v_lin */
+  cross3(c, vel + 3, v);      /* vlin x v_ang */
+  r[0] = a[0]; r[1] = a[1]; r[2] = a[2];
+  r[3] = b[0] + c[0]; r[4] = b[1] + c[1]; r[5] = b[2] + c[2];
+}
+/* motion x* force */
+static void cross_force(double* r, const double* vel, const double* f) {
+  double a[3], b[3], c[3];
+  cross3(a, vel, f);          /* w x f_ang */
+  cross3(b, vel + 3, f + 3);  /* v x f_lin */
+  cross3(c, vel, f + 3);      /* w x f_lin */
+  r[0] = a[0] + b[0]; r[1] = a[1] + b[1]; r[2] = a[2] + b[2];
+  r[3] = c[0]; r[4] = c[1]; r[5] = c[2];
+}
+
+/* ------------------------------------------------------------------------------------------ per-env data */
+typedef struct {
+  double dist, pos[3], frame[9], mu, solref[2], solimp[5], margin;
+  int geom1, geom2, body1, body2, vert, efc_address, dim;
+} contact_t;
+
+typedef struct {
+  /* state */
+  double *qpos, *qvel, *qacc_warmstart, *ctrl, time;
+  /* position-dependent */
+  double *xpos, *xquat, *xmat, *xipos, *ximat, *xanchor, *xaxis, *site_xpos, *subtree_com, *cinert, *crb, *cdof;
+  double *M, *L;               /* dense mass matrix and its Cholesky factor (lower) */
+  /* velocity-dependent */
+  double *cvel, *cdof_dot, *qfrc_bias, *qfrc_passive, *qfrc_actuator, *qfrc_smooth, *qacc_smooth;
+  double *qfrc_constraint, *qacc, *act_force;
+  /* contacts / constraints */
+  int ncon, nefc;
+  contact_t con[NMO_MAXCON];
+  double *efc_J, *efc_pos, *efc_margin, *efc_diagApprox, *efc_R, *efc_D, *efc_aref, *efc_vel, *efc_b, *efc_force, *efc_AR;
+  int solver_niter, noslip_niter, warm_used, nwarn;
+  double* sensordata;
+  double* scratch;   /* >= 8*nv + MAXEFC*nv */
+} data_t;
+
+#define MAXEFC (4 * NMO_MAXCON)
+
+/* env layer carry state (envs/nightmare_v3_env.py:56-97) */
+typedef struct {
+  double actions[18], prev_actions[18], dof_pos[18], dof_vel[18], commands[3];
+  double base_lin_vel[3], base_ang_vel[3], projected_gravity[3], base_height;
+  double tibia_f[6], feet_f[6], body_f, dof_acc[18];
+  double feet_air_time[6];
+  int last_contacts[6], last_contacts_filt[6];
+  double episode_sums[NMO_NREW], sums_at_reset[NMO_NREW];
+  int64_t ep_len;
+  int reset_buf, time_out;
+} envstate_t;
+
+struct nmo_batch {
+  const nmo_model* m;
+  int n;
+  uint64_t seed;
+  nmo_envcfg cfg;
+  data_t* d;
+  envstate_t* e;
+  int64_t step_counter;
+};
+
+static double* dalloc(size_t n) { return (double*)calloc(n ? n : 1, sizeof(double)); }
+
+static void data_init(const nmo_model* m, data_t* d) {
+  int nv = m->nv, nb = m->nbody;
+  memset(d, 0, sizeof(*d));
+  d->qpos = dalloc(m->nq); d->qvel = dalloc(nv); d->qacc_warmstart = dalloc(nv); d->ctrl = dalloc(m->nu);
+  d->xpos = dalloc(3 * nb); d->xquat = dalloc(4 * nb); d->xmat = dalloc(9 * nb); d->xipos = dalloc(3 * nb);
+  d->ximat = dalloc(9 * nb); d->xanchor = dalloc(3 * m->njnt); d->xaxis = dalloc(3 * m->njnt);
+  d->site_xpos = dalloc(3 * m->nsite); d->subtree_com = dalloc(3 * nb); d->cinert = dalloc(10 * nb);
+  d->crb = dalloc(10 * nb); d->cdof = dalloc(6 * nv); d->M = dalloc(nv * nv); d->L = dalloc(nv * nv);
+  d->cvel = dalloc(6 * nb); d->cdof_dot = dalloc(6 * nv); d->qfrc_bias = dalloc(nv); d->qfrc_passive = dalloc(nv);
+  d->qfrc_actuator = dalloc(nv); d->qfrc_smooth = dalloc(nv); d->qacc_smooth = dalloc(nv);
+  d->qfrc_constraint = dalloc(nv); d->qacc = dalloc(nv); d->act_force = dalloc(m->nu);
+  d->efc_J = dalloc(MAXEFC * nv); d->efc_pos = dalloc(MAXEFC); d->efc_margin = dalloc(MAXEFC);
+  d->efc_diagApprox = dalloc(MAXEFC); d->efc_R = dalloc(MAXEFC); d->efc_D = dalloc(MAXEFC);
+  d->efc_aref = dalloc(MAXEFC); d->efc_vel = dalloc(MAXEFC); d->efc_b = dalloc(MAXEFC);
+  d->efc_force = dalloc(MAXEFC); d->efc_AR = dalloc((size_t)MAXEFC * MAXEFC);
+  d->sensordata = dalloc(m->nsensor);
+  d->scratch = dalloc(16 * nv + (size_t)MAXEFC * nv + 16 * nb);
+  memcpy(d->qpos, m->qpos0, sizeof(double) * m->nq);
+}
+
+static void data_free(data_t* d) {
+  double** p[] = {&d->qpos, &d->qvel, &d->qacc_warmstart, &d->ctrl, &d->xpos, &d->xquat, &d->xmat, &d->xipos, &d->ximat,
+                  &d->xanchor, &d->xaxis, &d->site_xpos, &d->subtree_com, &d->cinert, &d->crb, &d->cdof, &d->M, &d->L,
+                  &d->cvel, &d->cdof_dot, &d->qfrc_bias, &d->qfrc_passive, &d->qfrc_actuator, &d->qfrc_smooth,
+                  &d->qacc_smooth, &d->qfrc_constraint, &d->qacc, &d->act_force, &d->efc_J, &d->efc_pos, &d->efc_margin,
+                  &d->efc_diagApprox, &d->efc_R, &d->efc_D, &d->efc_aref, &d->efc_vel, &d->efc_b, &d->efc_force,
+                  &d->efc_AR, &d->sensordata, &d->scratch};
+  for (size_t i = 0; i < sizeof(p) / sizeof(p[0]); i++) free(*p[i]);
+}
+
+/* ------------------------------------------------------------------------------------------ P1 kinematics */
+static void kinematics(const nmo_model* m, data_t* d) {
+  double* xpos = d->xpos; double* xquat = d->xquat; double* xmat = d->xmat;
+  xpos[0] = xpos[1] = xpos[2] = 0;
+  xquat[0] = 1; xquat[1] = xquat[2] = xquat[3] = 0;
+  quat2mat(xmat, xquat);
+  memset(d->xipos, 0, 3 * sizeof(double));
+  quat2mat(d->ximat, xquat);
+  for (int i = 1; i < m->nbody; i++) {
+    int pid = m->body_parent[i], ja = m->body_jntadr[i], jn = m->body_jntnum[i];
+    double pos[3], quat[4];
+    if (jn == 1 && m->jnt_type[ja] == JNT_FREE) {
+      int qa = m->jnt_qposadr[ja];
+      memcpy(pos, d->qpos + qa, 3 * sizeof(double));
+      memcpy(quat, d->qpos + qa + 3, 4 * sizeof(double));
+      normalize4(quat);
+      memcpy(d->xanchor + 3 * ja, pos, 3 * sizeof(double));
+      d->xaxis[3 * ja] = 0; d->xaxis[3 * ja + 1] = 0; d->xaxis[3 * ja + 2] = 1;
+    } else {
+      double t[3];
+      mat_vec3(t, xmat + 9 * pid, m->body_pos + 3 * i);
+      for (int k = 0; k < 3; k++) pos[k] = xpos[3 * pid + k] + t[k];
+      mul_quat(quat, xquat + 4 * pid, m->body_quat + 4 * i);
+      for (int j = ja; j < ja + jn; j++) {
+        double mat[9], anchor[3], axis[3];
+        quat2mat(mat, quat);
+        mat_vec3(anchor, mat, m->jnt_pos + 3 * j);
+        for (int k = 0; k < 3; k++) anchor[k] += pos[k];
+        mat_vec3(axis, mat, m->jnt_axis + 3 * j);
+        memcpy(d->xanchor + 3 * j, anchor, sizeof(anchor));
+        memcpy(d->xaxis + 3 * j, axis, sizeof(axis));
+        double q = d->qpos[m->jnt_qposadr[j]] - m->qpos0[m->jnt_qposadr[j]];
+        if (m->jnt_type[j] == JNT_HINGE) {
+          double qloc[4], qn[4], off[3];
+          axisangle2quat(qloc, m->jnt_axis + 3 * j, q);
+          mul_quat(qn, quat, qloc);
+          memcpy(quat, qn, sizeof(qn));
+          quat2mat(mat, quat);
+          mat_vec3(off, mat, m->jnt_pos + 3 * j);      /* off-centre rotation correction */
+          for (int k = 0; k < 3; k++) pos[k] = anchor[k] - off[k];
+        } else if (m->jnt_type[j] == JNT_SLIDE) {
+          for (int k = 0; k < 3; k++) pos[k] += axis[k] * q;
+        }
+      }
+    }
+    normalize4(quat);
+    memcpy(xpos + 3 * i, pos, sizeof(pos));
+    memcpy(xquat + 4 * i, quat, sizeof(quat));
+    quat2mat(xmat + 9 * i, quat);
+    double t[3], qi[4];
+    mat_vec3(t, xmat + 9 * i, m->body_ipos + 3 * i);
+    for (int k = 0; k < 3; k++) d->xipos[3 * i + k] = pos[k] + t[k];
+    mul_quat(qi, quat, m->body_iquat + 4 * i);
+    quat2mat(d->ximat + 9 * i, qi);
+  }
+  for (int s = 0; s < m->nsite; s++) {
+    int b = m->site_body[s];
+    double t[3];
+    mat_vec3(t, xmat + 9 * b, m->site_pos + 3 * s);
+    for (int k = 0; k < 3; k++) d->site_xpos[3 * s + k] = xpos[3 * b + k] + t[k];
+  }
+}
+
+/* ------------------------------------------------------------------------------------------ P2 comPos */
+static void com_pos(const nmo_model* m, data_t* d) {
+  int nb = m->nbody;
+  double* smass = d->scratch;
+  for (int i = 0; i < nb; i++) {
+    smass[i] = m->body_mass[i];
+    for (int k = 0; k < 3; k++) d->subtree_com[3 * i + k] = m->body_mass[i] * d->xipos[3 * i + k];
+  }
+  for (int i = nb - 1; i > 0; i--) {
+    int p = m->body_parent[i];
+    smass[p] += smass[i];
+    for (int k = 0; k < 3; k++) d->subtree_com[3 * p + k] += d->subtree_com[3 * i + k];
+  }
+  for (int i = 0; i < nb; i++) {
+    if (smass[i] < MINVAL) memcpy(d->subtree_com + 3 * i, d->xipos + 3 * i, 3 * sizeof(double));
+    else for (int k = 0; k < 3; k++) d->subtree_com[3 * i + k] /= smass[i];
+  }
+  for (int i = 1; i < nb; i++) {
+    const double* R = d->ximat + 9 * i;
+    const double* I = m->body_inertia + 3 * i;
+    const double* c = d->subtree_com + 3 * m->body_rootid[i];
+    double mass = m->body_mass[i], r[3];
+    for (int k = 0; k < 3; k++) r[k] = d->xipos[3 * i + k] - c[k];
+    double* ci = d->cinert + 10 * i;
+    /* R diag(I) R^T */
+    ci[0] = R[0] * R[0] * I[0] + R[1] * R[1] * I[1] + R[2] * R[2] * I[2];
+    ci[1] = R[3] * R[3] * I[0] + R[4] * R[4] * I[1] + R[5] * R[5] * I[2];
+    ci[2] = R[6] * R[6] * I[0] + R[7] * R[7] * I[1] + R[8] * R[8] * I[2];
+    ci[3] = R[0] * R[3] * I[0] + R[1] * R[4] * I[1] + R[2] * R[5] * I[2];
+    ci[4] = R[0] * R[6] * I[0] + R[1] * R[7] * I[1] + R[2] * R[8] * I[2];
+    ci[5] = R[3] * R[6] * I[0] + R[4] * R[7] * I[1] + R[5] * R[8] * I[2];
+    /* parallel axis */
+    ci[0] += mass * (r[1] * r[1] + r[2] * r[2]);
+    ci[1] += mass * (r[0] * r[0] + r[2] * r[2]);
+    ci[2] += mass * (r[0] * r[0] + r[1] * r[1]);
+    ci[3] -= mass * r[0] * r[1];
+    ci[4] -= mass * r[0] * r[2];
+    ci[5] -= mass * r[1] * r[2];
+    ci[6] = mass * r[0]; ci[7] = mass * r[1]; ci[8] = mass * r[2];
+    ci[9] = mass;
+  }
+  memset(d->cinert, 0, 10 * sizeof(double));
+  for (int j = 0; j < m->njnt; j++) {
+    int b = m->jnt_body[j], da = m->jnt_dofadr[j];
+    const double* c = d->subtree_com + 3 * m->body_rootid[b];
+    double off[3];
+    for (int k = 0; k < 3; k++) off[k] = c[k] - d->xanchor[3 * j + k];
+    if (m->jnt_type[j] == JNT_FREE) {
+      for (int k = 0; k < 3; k++) {
+        double* cd = d->cdof + 6 * (da + k);
+        memset(cd, 0, 6 * sizeof(double));
+        cd[3 + k] = 1;
+      }
+      for (int k = 0; k < 3; k++) {
+        double* cd = d->cdof + 6 * (da + 3 + k);
+        double ax[3] = {d->xmat[9 * b + k], d->xmat[9 * b + 3 + k], d->xmat[9 * b + 6 + k]};
+        memcpy(cd, ax, sizeof(ax));
+        cross3(cd + 3, ax, off);
+      }
+    } else if (m->jnt_type[j] == JNT_HINGE) {
+      double* cd = d->cdof + 6 * da;
+      memcpy(cd, d->xaxis + 3 * j, 3 * sizeof(double));
+      cross3(cd + 3, d->xaxis + 3 * j, off);
+    } else { /* slide */
+      double* cd = d->cdof + 6 * da;
+      cd[0] = cd[1] = cd[2] = 0;
+      memcpy(cd + 3, d->xaxis + 3 * j, 3 * sizeof(double));
+    }
+  }
+}
+
+/* ------------------------------------------------------------------------------------------ P3 CRBA + factor */
+static int cholesky(double* L, const double* A, int n) {
+  memcpy(L, A, sizeof(double) * n * n);
+  for (int j = 0; j < n; j++) {
+    double s = L[j * n + j];
+    for (int k = 0; k < j; k++) s -= L[j * n + k] * L[j * n + k];
+    if (s < MINVAL) return -1;
+    s = sqrt(s);
+    L[j * n + j] = s;
+    for (int i = j + 1; i < n; i++) {
+      double t = L[i * n + j];
+      for (int k = 0; k < j; k++) t -= L[i * n + k] * L[j * n + k];
+      L[i * n + j] = t / s;
+    }
+    for (int k = j + 1; k < n; k++) L[j * n + k] = 0;
+  }
+  return 0;
+}
+static void chol_solve(const double* L, int n, double* x) {
+  for (int i = 0; i < n; i++) {
+    double s = x[i];
+    for (int k = 0; k < i; k++) s -= L[i * n + k] * x[k];
+    x[i] = s / L[i * n + i];
+  }
+  for (int i = n - 1; i >= 0; i--) {
+    double s = x[i];
+    for (int k = i + 1; k < n; k++) s -= L[k * n + i] * x[k];
+    x[i] = s / L[i * n + i];
+  }
+}
+
+static void crb(const nmo_model* m, data_t* d) {
+  int nv = m->nv, nb = m->nbody;
+  memcpy(d->crb, d->cinert, sizeof(double) * 10 * nb);
+  for (int i = nb - 1; i > 0; i--) {
+    int p = m->body_parent[i];
+    if (p > 0) for (int k = 0; k < 10; k++) d->crb[10 * p + k] += d->crb[10 * i + k];
+  }
+  memset(d->M, 0, sizeof(double) * nv * nv);
+  for (int i = 0; i < nv; i++) {
+    double buf[6];
+    mul_inert_vec(buf, d->crb + 10 * m->dof_body[i], d->cdof + 6 * i);
+    for (int j = i; j >= 0; j = m->dof_parent[j]) {
+      double s = 0;
+      for (int k = 0; k < 6; k++) s += d->cdof[6 * j + k] * buf[k];
+      d->M[i * nv + j] = d->M[j * nv + i] = s;
+    }
+    d->M[i * nv + i] += m->dof_armature[i];
+  }
+  if (cholesky(d->L, d->M, nv) != 0) d->nwarn++;
+}
+
+/* ------------------------------------------------------------------------------------------ P4 collision */
+static void make_frame(double* f) {
+  /* f[0:3] = normal; build tangents (≙ mju_makeFrame) */
+  normalize3(f);
+  double* y = f + 3;
+  y[0] = 0; y[1] = 0; y[2] = 0;
+  if (f[1] < 0.5 && f[1] > -0.5) y[1] = 1; else y[2] = 1;
+  double dd = dot3(f, y);
+  for (int k = 0; k < 3; k++) y[k] -= dd * f[k];
+  normalize3(y);
+  cross3(f + 6, f, y);
+}
+
+static void mix_params(const nmo_model* m, int g1, int g2, contact_t* c) {
+  int p1 = m->geom_priority[g1], p2 = m->geom_priority[g2];
+  const double *f1 = m->geom_friction + 3 * g1, *f2 = m->geom_friction + 3 * g2;
+  if (p1 == p2) {
+    c->mu = f1[0] > f2[0] ? f1[0] : f2[0];
+    c->dim = m->geom_condim[g1] > m->geom_condim[g2] ? m->geom_condim[g1] : m->geom_condim[g2];
+    for (int k = 0; k < 2; k++) c->solref[k] = 0.5 * (m->geom_solref[2 * g1 + k] + m->geom_solref[2 * g2 + k]);
+    for (int k = 0; k < 5; k++) c->solimp[k] = 0.5 * (m->geom_solimp[5 * g1 + k] + m->geom_solimp[5 * g2 + k]);
+  } else {
+    int g = p1 > p2 ? g1 : g2;
+    c->mu = m->geom_friction[3 * g];
+    c->dim = m->geom_condim[g];
+    memcpy(c->solref, m->geom_solref + 2 * g, 2 * sizeof(double));
+    memcpy(c->solimp, m->geom_solimp + 5 * g, 5 * sizeof(double));
+  }
+  c->margin = (m->geom_margin[g1] > m->geom_margin[g2] ? m->geom_margin[g1] : m->geom_margin[g2]) -
+              (m->geom_gap[g1] > m->geom_gap[g2] ? m->geom_gap[g1] : m->geom_gap[g2]);
+}
+
+static void collision(const nmo_model* m, data_t* d) {
+  d->ncon = 0;
+  for (int g = 0; g < m->ngeom; g++) {
+    int pg = m->geom_plane[g];
+    if (pg < 0) continue;
+    int pb = m->geom_body[pg], b = m->geom_body[g];
+    /* plane frame in world */
+    double pq[4], pm[9], ppos[3], t[3];
+    mul_quat(pq, d->xquat + 4 * pb, m->geom_quat + 4 * pg);
+    quat2mat(pm, pq);
+    mat_vec3(t, d->xmat + 9 * pb, m->geom_pos + 3 * pg);
+    for (int k = 0; k < 3; k++) ppos[k] = d->xpos[3 * pb + k] + t[k];
+    double n[3] = {pm[2], pm[5], pm[8]};
+    double margin = m->geom_margin[g] > m->geom_margin[pg] ? m->geom_margin[g] : m->geom_margin[pg];
+    const double* R = d->xmat + 9 * b;
+    const double* p = d->xpos + 3 * b;
+    if (m->geom_type[g] == GEOM_MESH) {
+      int adr = m->geom_hull_adr[g], num = m->geom_hull_num[g];
+      /* support vertex along -n: exhaustive argmin of n.(v - ppos), lowest index wins ties
+         (MuJoCo hill-climbs the hull graph; identical on a convex hull except for exact ties) */
+      int best = -1;
+      double bestd = 0, bestw[3] = {0, 0, 0};
+      for (int v = 0; v < num; v++) {
+        double lv[3] = {m->hull_vert[3 * (adr + v)], m->hull_vert[3 * (adr + v) + 1], m->hull_vert[3 * (adr + v) + 2]};
+        double w[3];
+        mat_vec3(w, R, lv);
+        for (int k = 0; k < 3; k++) w[k] += p[k];
+        double dist = (w[0] - ppos[0]) * n[0] + (w[1] - ppos[1]) * n[1] + (w[2] - ppos[2]) * n[2];
+        if (best < 0 || dist < bestd) { best = v; bestd = dist; memcpy(bestw, w, sizeof(w)); }
+      }
+      if (best < 0 || bestd > margin) continue;
+      int first = d->ncon, cnt = 0;
+      for (int pass = 0; pass < 2; pass++) {
+        /* pass 0: the support vertex.  pass 1: its hull-graph neighbours (up to 3 more contacts) */
+        int lo = pass == 0 ? 0 : m->hull_nbr_adr[adr + best];
+        int hi = pass == 0 ? 1 : m->hull_nbr_adr[adr + best + 1];
+        for (int e = lo; e < hi && cnt < 4 && d->ncon < NMO_MAXCON; e++) {
+          int v = pass == 0 ? best : m->hull_nbr[e];
+          double w[3], dist;
+          if (pass == 0) { memcpy(w, bestw, sizeof(w)); dist = bestd; }
+          else {
+            double lv[3] = {m->hull_vert[3 * (adr + v)], m->hull_vert[3 * (adr + v) + 1], m->hull_vert[3 * (adr + v) + 2]};
+            mat_vec3(w, R, lv);
+            for (int k = 0; k < 3; k++) w[k] += p[k];
+            dist = (w[0] - ppos[0]) * n[0] + (w[1] - ppos[1]) * n[1] + (w[2] - ppos[2]) * n[2];
+            if (dist > margin) continue;
+          }
+          double cp[3];
+          for (int k = 0; k < 3; k++) cp[k] = w[k] - 0.5 * dist * n[k];
+          int tooclose = 0;
+          for (int c = first; c < first + cnt; c++) {
+            double dx = d->con[c].pos[0] - cp[0], dy = d->con[c].pos[1] - cp[1], dz = d->con[c].pos[2] - cp[2];
+            if (sqrt(dx * dx + dy * dy + dz * dz) < TOLPLANEMESH * m->geom_rbound[g]) tooclose = 1;
+          }
+          if (tooclose) continue;
+          contact_t* c = d->con + d->ncon++;
+          cnt++;
+          c->dist = dist;
+          memcpy(c->pos, cp, sizeof(cp));
+          memcpy(c->frame, n, sizeof(n));
+          make_frame(c->frame);
+          c->geom1 = pg; c->geom2 = g; c->body1 = pb; c->body2 = b; c->vert = v;
+          mix_params(m, pg, g, c);
+        }
+      }
+    } else if (m->geom_type[g] == GEOM_SPHERE) {
+      double gc[3];
+      mat_vec3(gc, R, m->geom_pos + 3 * g);
+      for (int k = 0; k < 3; k++) gc[k] += p[k];
+      double dist = (gc[0] - ppos[0]) * n[0] + (gc[1] - ppos[1]) * n[1] + (gc[2] - ppos[2]) * n[2] - m->geom_size[3 * g];
+      if (dist > margin || d->ncon >= NMO_MAXCON) continue;
+      contact_t* c = d->con + d->ncon++;
+      c->dist = dist;
+      for (int k = 0; k < 3; k++) c->pos[k] = gc[k] - n[k] * (m->geom_size[3 * g] + 0.5 * dist);
+      memcpy(c->frame, n, sizeof(n));
+      make_frame(c->frame);
+      c->geom1 = pg; c->geom2 = g; c->body1 = pb; c->body2 = b; c->vert = -1;
+      mix_params(m, pg, g, c);
+    }
+  }
+}
+
+/* ------------------------------------------------------------------------------------------ P5 constraints */
+static void jac_point(const nmo_model* m, const data_t* d, int body, const double* point, double* jacp /*3 x nv*/) {
+  int nv = m->nv;
+  memset(jacp, 0, sizeof(double) * 3 * nv);
+  if (body <= 0) return;
+  double off[3];
+  const double* c = d->subtree_com + 3 * m->body_rootid[body];
+  for (int k = 0; k < 3; k++) off[k] = point[k] - c[k];
+  int b = body;
+  while (b > 0 && m->body_dofnum[b] == 0) b = m->body_parent[b];
+  if (b <= 0) return;
+  for (int i = m->body_dofadr[b] + m->body_dofnum[b] - 1; i >= 0; i = m->dof_parent[i]) {
+    double t[3];
+    cross3(t, d->cdof + 6 * i, off);
+    for (int k = 0; k < 3; k++) jacp[k * nv + i] = d->cdof[6 * i + 3 + k] + t[k];
+  }
+}
+
+static double impedance(const double* solimp, double pos, double margin) {
+  double dmin = solimp[0], dmax = solimp[1], width = solimp[2], mid = solimp[3], power = solimp[4];
+  if (dmin < 0.0001) dmin = 0.0001; if (dmin > 0.9999) dmin = 0.9999;
+  if (dmax < 0.0001) dmax = 0.0001; if (dmax > 0.9999) dmax = 0.9999;
+  if (mid < 0.0001) mid = 0.0001; if (mid > 0.9999) mid = 0.9999;
+  if (power < 1) power = 1;
+  if (dmin == dmax || width <= MINVAL) return 0.5 * (dmin + dmax);
+  double x = fabs((pos - margin) / width);
+  if (x >= 1) return dmax;
+  if (x <= 0) return dmin;
+  double y;
+  if (power == 1) y = x;
+  else if (x <= mid) y = pow(x, power) / pow(mid, power - 1);
+  else y = 1 - pow(1 - x, power) / pow(1 - mid, power - 1);
+  return dmin + y * (dmax - dmin);
+}
+
+static void make_constraint(const nmo_model* m, data_t* d) {
+  int nv = m->nv;
+  d->nefc = 0;
+  double* jac1 = d->scratch;            /* 3 x nv */
+  double* jac2 = d->scratch + 3 * nv;   /* 3 x nv */
+  for (int ci = 0; ci < d->ncon; ci++) {
+    contact_t* c = d->con + ci;
+    c->efc_address = -1;
+    if (c->dim != 3 || d->nefc + 4 > MAXEFC) { d->nwarn++; continue; }   /* oracle scope: condim 3, pyramidal */
+    c->efc_address = d->nefc;
+    jac_point(m, d, c->body1, c->pos, jac1);
+    jac_point(m, d, c->body2, c->pos, jac2);
+    double Jc[3][64];   /* rows in contact frame; nv <= 64 */
+    for (int r = 0; r < 3; r++)
+      for (int i = 0; i < nv; i++) {
+        double s = 0;
+        for (int k = 0; k < 3; k++) s += c->frame[3 * r + k] * (jac2[k * nv + i] - jac1[k * nv + i]);
+        Jc[r][i] = s;
+      }
+    double tran = m->body_invweight0[2 * c->body1] + m->body_invweight0[2 * c->body2];
+    for (int r = 0; r < 4; r++) {
+      int e = d->nefc++;
+      int t = 1 + r / 2;
+      double sgn = (r % 2 == 0) ? 1.0 : -1.0;
+      for (int i = 0; i < nv; i++) d->efc_J[e * nv + i] = Jc[0][i] + sgn * c->mu * Jc[t][i];
+      d->efc_pos[e] = c->dist;
+      d->efc_margin[e] = c->margin;
+      d->efc_diagApprox[e] = tran + c->mu * c->mu * tran;
+    }
+  }
+  /* impedance, R, D, reference acceleration */
+  for (int ci = 0; ci < d->ncon; ci++) {
+    contact_t* c = d->con + ci;
+    if (c->efc_address < 0) continue;
+    int e0 = c->efc_address;
+    double tc = c->solref[0], dr = c->solref[1], dmax = c->solimp[1];
+    if (dmax < 0.0001) dmax = 0.0001; if (dmax > 0.9999) dmax = 0.9999;
+    double K, B;
+    if (tc > 0) {
+      if (tc < 2 * m->timestep) tc = 2 * m->timestep;   /* refsafe */
+      K = 1.0 / (dmax * dmax * tc * tc * dr * dr);
+      B = 2.0 / (dmax * tc);
+    } else {
+      K = -tc / (dmax * dmax);
+      B = -dr / dmax;
+    }
+    for (int r = 0; r < 4; r++) {
+      int e = e0 + r;
+      double imp = impedance(c->solimp, d->efc_pos[e], d->efc_margin[e]);
+      double R = (1 - imp) * d->efc_diagApprox[e] / imp;
+      if (R < MINVAL) R = MINVAL;
+      d->efc_R[e] = R;
+      double vel = 0;
+      for (int i = 0; i < nv; i++) vel += d->efc_J[e * nv + i] * d->qvel[i];
+      d->efc_vel[e] = vel;
+      d->efc_aref[e] = -B * vel - K * imp * (d->efc_pos[e] - d->efc_margin[e]);
+    }
+    /* pyramidal cone: all edges share R = 2 mu^2 R[first]  (mu regularised by impratio) */
+    double mureg = c->mu / sqrt(m->impratio > MINVAL ? m->impratio : 1.0);
+    double Rpy = 2 * mureg * mureg * d->efc_R[e0];
+    if (Rpy < MINVAL) Rpy = MINVAL;
+    for (int r = 0; r < 4; r++) { d->efc_R[e0 + r] = Rpy; d->efc_D[e0 + r] = 1.0 / Rpy; }
+  }
+}
+
+/* ------------------------------------------------------------------------------------------ P6 projectConstraint */
+static void project_constraint(const nmo_model* m, data_t* d) {
+  int nv = m->nv, ne = d->nefc;
+  double* X = d->scratch + 16 * nv;  /* ne x nv : rows = M^-1 J_e^T */
+  for (int e = 0; e < ne; e++) {
+    memcpy(X + e * nv, d->efc_J + e * nv, sizeof(double) * nv);
+    chol_solve(d->L, nv, X + e * nv);
+  }
+  for (int a = 0; a < ne; a++)
+    for (int b = 0; b < ne; b++) {
+      double s = 0;
+      for (int i = 0; i < nv; i++) s += d->efc_J[a * nv + i] * X[b * nv + i];
+      d->efc_AR[a * ne + b] = s + (a == b ? d->efc_R[a] : 0);
+    }
+}
+
+/* ------------------------------------------------------------------------------------------ P7 comVel + rne */
+static void com_vel(const nmo_model* m, data_t* d) {
+  memset(d->cvel, 0, 6 * sizeof(double));
+  for (int i = 1; i < m->nbody; i++) {
+    double cvel[6];
+    memcpy(cvel, d->cvel + 6 * m->body_parent[i], sizeof(cvel));
+    int bda = m->body_dofadr[i];
+    for (int j = m->body_jntadr[i]; j >= 0 && j < m->body_jntadr[i] + m->body_jntnum[i]; j++) {
+      if (m->jnt_type[j] == JNT_FREE) {
+        for (int k = 0; k < 3; k++) {
+          memset(d->cdof_dot + 6 * (bda + k), 0, 6 * sizeof(double));
+          for (int c = 0; c < 6; c++) cvel[c] += d->cdof[6 * (bda + k) + c] * d->qvel[bda + k];
+        }
+        bda += 3;
+        for (int k = 0; k < 3; k++) cross_motion(d->cdof_dot + 6 * (bda + k), cvel, d->cdof + 6 * (bda + k));
+        for (int k = 0; k < 3; k++)
+          for (int c = 0; c < 6; c++) cvel[c] += d->cdof[6 * (bda + k) + c] * d->qvel[bda + k];
+        bda += 3;
+      } else {
+        cross_motion(d->cdof_dot + 6 * bda, cvel, d->cdof + 6 * bda);
+        for (int c = 0; c < 6; c++) cvel[c] += d->cdof[6 * bda + c] * d->qvel[bda];
+        bda++;
+      }
+    }
+    memcpy(d->cvel + 6 * i, cvel, sizeof(cvel));
+  }
+}
+
+static void rne(const nmo_model* m, data_t* d, double* result) {
+  int nb = m->nbody, nv = m->nv;
+  double* cacc = d->scratch;            /* 6 x nb */
+  double* cfrc = d->scratch + 6 * nb;   /* 6 x nb */
+  memset(cacc, 0, 6 * sizeof(double));
+  for (int k = 0; k < 3; k++) cacc[3 + k] = -m->gravity[k];
+  memset(cfrc, 0, 6 * sizeof(double));
+  for (int i = 1; i < nb; i++) {
+    double tmp[6], tmp1[6];
+    memcpy(cacc + 6 * i, cacc + 6 * m->body_parent[i], 6 * sizeof(double));
+    for (int j = 0; j < m->body_dofnum[i]; j++) {
+      int dd = m->body_dofadr[i] + j;
+      for (int c = 0; c < 6; c++) cacc[6 * i + c] += d->cdof_dot[6 * dd + c] * d->qvel[dd];
+    }
+    mul_inert_vec(cfrc + 6 * i, d->cinert + 10 * i, cacc + 6 * i);
+    mul_inert_vec(tmp, d->cinert + 10 * i, d->cvel + 6 * i);
+    cross_force(tmp1, d->cvel + 6 * i, tmp);
+    for (int c = 0; c < 6; c++) cfrc[6 * i + c] += tmp1[c];
+  }
+  for (int i = nb - 1; i > 0; i--) {
+    int p = m->body_parent[i];
+    if (p > 0) for (int c = 0; c < 6; c++) cfrc[6 * p + c] += cfrc[6 * i + c];
+  }
+  for (int i = 0; i < nv; i++) {
+    double s = 0;
+    for (int c = 0; c < 6; c++) s += d->cdof[6 * i + c] * cfrc[6 * m->dof_body[i] + c];
+    result[i] = s;
+  }
+}
+
+/* ------------------------------------------------------------------------------------------ P8 actuation / acceleration */
+static void fwd_velocity_actuation_acceleration(const nmo_model* m, data_t* d) {
+  int nv = m->nv;
+  com_vel(m, d);
+  for (int i = 0; i < nv; i++) d->qfrc_passive[i] = -m->dof_damping[i] * d->qvel[i];
+  rne(m, d, d->qfrc_bias);
+  memset(d->qfrc_actuator, 0, sizeof(double) * nv);
+  for (int a = 0; a < m->nu; a++) {
+    double ctrl = d->ctrl[a];
+    if (m->act_ctrllimited[a]) {
+      if (ctrl < m->act_ctrlrange[2 * a]) ctrl = m->act_ctrlrange[2 * a];
+      if (ctrl > m->act_ctrlrange[2 * a + 1]) ctrl = m->act_ctrlrange[2 * a + 1];
+    }
+    int dof = m->act_dof[a], jid = m->dof_jnt[dof];
+    double gear = m->act_gear[a];
+    double length = d->qpos[m->jnt_qposadr[jid]] * gear, velocity = d->qvel[dof] * gear;
+    double f = m->act_gain[3 * a] * ctrl + m->act_bias[3 * a] + m->act_bias[3 * a + 1] * length + m->act_bias[3 * a + 2] * velocity;
+    if (m->act_forcelimited[a]) {
+      if (f < m->act_forcerange[2 * a]) f = m->act_forcerange[2 * a];
+      if (f > m->act_forcerange[2 * a + 1]) f = m->act_forcerange[2 * a + 1];
+    }
+    d->act_force[a] = f;
+    d->qfrc_actuator[dof] += gear * f;
+  }
+  for (int i = 0; i < nv; i++) {
+    d->qfrc_smooth[i] = d->qfrc_passive[i] - d->qfrc_bias[i] + d->qfrc_actuator[i];
+    d->qacc_smooth[i] = d->qfrc_smooth[i];
+  }
+  chol_solve(d->L, nv, d->qacc_smooth);
+}
+
+/* ------------------------------------------------------------------------------------------ P9 constraint solve */
+static void dual_finish(const nmo_model* m, data_t* d) {
+  int nv = m->nv, ne = d->nefc;
+  for (int i = 0; i < nv; i++) {
+    double s = 0;
+    for (int e = 0; e < ne; e++) s += d->efc_J[e * nv + i] * d->efc_force[e];
+    d->qfrc_constraint[i] = s;
+    d->qacc[i] = s;
+  }
+  chol_solve(d->L, nv, d->qacc);
+  for (int i = 0; i < nv; i++) d->qacc[i] += d->qacc_smooth[i];
+}
+
+static void fwd_constraint(const nmo_model* m, data_t* d) {
+  int nv = m->nv, ne = d->nefc;
+  d->solver_niter = d->noslip_niter = 0;
+  d->warm_used = 0;
+  if (ne == 0) {
+    memcpy(d->qacc, d->qacc_smooth, sizeof(double) * nv);
+    memcpy(d->qacc_warmstart, d->qacc_smooth, sizeof(double) * nv);
+    memset(d->qfrc_constraint, 0, sizeof(double) * nv);
+    return;
+  }
+  const double* AR = d->efc_AR;
+  double* f = d->efc_force;
+  /* b = J qacc_smooth - aref */
+  for (int e = 0; e < ne; e++) {
+    double s = 0;
+    for (int i = 0; i < nv; i++) s += d->efc_J[e * nv + i] * d->qacc_smooth[i];
+    d->efc_b[e] = s - d->efc_aref[e];
+  }
+  /* warm start: forces implied by qacc_warmstart, kept only if their dual cost beats f = 0 */
+  for (int e = 0; e < ne; e++) {
+    double jar = -d->efc_aref[e];
+    for (int i = 0; i < nv; i++) jar += d->efc_J[e * nv + i] * d->qacc_warmstart[i];
+    f[e] = jar < 0 ? -d->efc_D[e] * jar : 0;
+  }
+  double cost = 0;
+  for (int a = 0; a < ne; a++) {
+    double s = 0;
+    for (int b = 0; b < ne; b++) s += AR[a * ne + b] * f[b];
+    cost += 0.5 * f[a] * s + f[a] * d->efc_b[a];
+  }
+  if (cost > 0) memset(f, 0, sizeof(double) * ne); else d->warm_used = 1;
+
+  double scale = 1.0 / (m->meaninertia * (nv > 1 ? nv : 1));
+  /* PGS (pyramidal rows are scalar inequality constraints) */
+  for (int it = 0; it < m->iterations; it++) {
+    double improvement = 0;
+    for (int e = 0; e < ne; e++) {
+      double res = d->efc_b[e];
+      for (int b = 0; b < ne; b++) res += AR[e * ne + b] * f[b];
+      double old = f[e];
+      f[e] -= res / AR[e * ne + e];
+      if (f[e] < 0) f[e] = 0;
+      double delta = f[e] - old;
+      double change = 0.5 * delta * delta * AR[e * ne + e] + delta * res;
+      if (change > 1e-10) { f[e] = old; change = 0; }
+      improvement -= change;
+    }
+    d->solver_niter++;
+    if (improvement * scale < m->tolerance) break;
+  }
+  dual_finish(m, d);
+  memcpy(d->qacc_warmstart, d->qacc, sizeof(double) * nv);   /* saved BEFORE noslip */
+
+  /* noslip post-processing: friction dimensions re-solved without regularisation */
+  if (m->noslip_iterations > 0) {
+    for (int it = 0; it < m->noslip_iterations; it++) {
+      double improvement = 0;
+      for (int ci = 0; ci < d->ncon; ci++) {
+        int e0 = d->con[ci].efc_address;
+        if (e0 < 0) continue;
+        for (int j = e0; j < e0 + 4; j += 2) {
+          double res[2], old[2] = {f[j], f[j + 1]};
+          for (int k = 0; k < 2; k++) {
+            double s = d->efc_b[j + k];
+            for (int b = 0; b < ne; b++) s += AR[(j + k) * ne + b] * f[b];
+            res[k] = s - d->efc_R[j + k] * f[j + k];
+          }
+          double Ac[4] = {AR[j * ne + j] - d->efc_R[j], AR[j * ne + j + 1], AR[(j + 1) * ne + j], AR[(j + 1) * ne + j + 1] - d->efc_R[j + 1]};
+          double bc[2] = {res[0] - Ac[0] * old[0] - Ac[1] * old[1], res[1] - Ac[2] * old[0] - Ac[3] * old[1]};
+          double mid = 0.5 * (old[0] + old[1]);
+          double K1 = Ac[0] + Ac[3] - Ac[1] - Ac[2];
+          double K0 = mid * (Ac[0] - Ac[3]) + bc[0] - bc[1];
+          if (K1 < MINVAL) { f[j] = f[j + 1] = mid; }
+          else {
+            double x = -K0 / K1;
+            if (x < -mid) { f[j] = 0; f[j + 1] = 2 * mid; }
+            else if (x > mid) { f[j] = 2 * mid; f[j + 1] = 0; }
+            else { f[j] = mid + x; f[j + 1] = mid - x; }
+          }
+          double dl[2] = {f[j] - old[0], f[j + 1] - old[1]};
+          double change = 0.5 * (dl[0] * (Ac[0] * dl[0] + Ac[1] * dl[1]) + dl[1] * (Ac[2] * dl[0] + Ac[3] * dl[1])) + dl[0] * res[0] + dl[1] * res[1];
+          if (change > 1e-10) { f[j] = old[0]; f[j + 1] = old[1]; change = 0; }
+          improvement -= change;
+        }
+      }
+      d->noslip_niter++;
+      if (improvement * scale < m->noslip_tolerance) break;
+    }
+    dual_finish(m, d);
+  }
+}
+
+/* ------------------------------------------------------------------------------------------ P10 touch sensors */
+static double ray_sphere(const double* center, double radius, const double* pnt, const double* vec) {
+  double dif[3] = {pnt[0] - center[0], pnt[1] - center[1], pnt[2] - center[2]};
+  double a = dot3(vec, vec), b = dot3(vec, dif), c = dot3(dif, dif) - radius * radius;
+  double det = b * b - a * c;
+  if (det < MINVAL || a < MINVAL) return -1;
+  det = sqrt(det);
+  double x0 = (-b - det) / a, x1 = (-b + det) / a;
+  if (x0 >= 0) return x0;
+  if (x1 >= 0) return x1;
+  return -1;
+}
+
+static void sensor_touch(const nmo_model* m, data_t* d) {
+  for (int s = 0; s < m->nsensor; s++) {
+    int site = m->sensor_site[s], body = m->site_body[site];
+    double sum = 0;
+    for (int ci = 0; ci < d->ncon; ci++) {
+      const contact_t* c = d->con + ci;
+      if (c->efc_address < 0 || (c->body1 != body && c->body2 != body)) continue;
+      double fn = 0;
+      for (int r = 0; r < 4; r++) fn += d->efc_force[c->efc_address + r];
+      if (fn <= 0) continue;
+      double ray[3] = {c->frame[0] * fn, c->frame[1] * fn, c->frame[2] * fn};
+      normalize3(ray);
+      if (c->body2 == body) { ray[0] = -ray[0]; ray[1] = -ray[1]; ray[2] = -ray[2]; }
+      if (ray_sphere(d->site_xpos + 3 * site, m->site_size[site], c->pos, ray) >= 0) sum += fn;
+    }
+    d->sensordata[s] = sum;
+  }
+}
+
+/* ------------------------------------------------------------------------------------------ forward + integrate */
+static void forward(const nmo_model* m, data_t* d) {
+  kinematics(m, d);
+  com_pos(m, d);
+  crb(m, d);
+  collision(m, d);
+  make_constraint(m, d);
+  project_constraint(m, d);
+  fwd_velocity_actuation_acceleration(m, d);
+  fwd_constraint(m, d);
+  sensor_touch(m, d);
+}
+
+static void integrate_pos(const nmo_model* m, double* qpos, const double* qvel, double h) {
+  for (int j = 0; j < m->njnt; j++) {
+    int qa = m->jnt_qposadr[j], da = m->jnt_dofadr[j];
+    if (m->jnt_type[j] == JNT_FREE) {
+      for (int k = 0; k < 3; k++) qpos[qa + k] += h * qvel[da + k];
+      double w[3] = {qvel[da + 3], qvel[da + 4], qvel[da + 5]}, qr[4], qn[4];
+      double angle = h * normalize3(w);
+      axisangle2quat(qr, w, angle);
+      normalize4(qpos + qa + 3);
+      mul_quat(qn, qpos + qa + 3, qr);
+      memcpy(qpos + qa + 3, qn, sizeof(qn));
+    } else {
+      qpos[qa] += h * qvel[da];
+    }
+  }
+}
+
+static int bad_state(const nmo_model* m, const data_t* d) {
+  for (int i = 0; i < m->nq; i++) if (!(fabs(d->qpos[i]) < MAXVAL)) return 1;
+  for (int i = 0; i < m->nv; i++) if (!(fabs(d->qvel[i]) < MAXVAL)) return 1;
+  return 0;
+}
+
+static void reset_data(const nmo_model* m, data_t* d) {
+  memcpy(d->qpos, m->qpos0, sizeof(double) * m->nq);
+  memset(d->qvel, 0, sizeof(double) * m->nv);
+  memset(d->qacc_warmstart, 0, sizeof(double) * m->nv);
+  d->time = 0;
+  d->nwarn++;
+}
+
+static void step1(const nmo_model* m, data_t* d) {
+  int nv = m->nv;
+  double h = m->timestep;
+  if (bad_state(m, d)) reset_data(m, d);      /* ≙ mj_checkPos / mj_checkVel */
+  forward(m, d);
+  for (int i = 0; i < nv; i++)
+    if (!(fabs(d->qacc[i]) < MAXVAL)) { reset_data(m, d); forward(m, d); break; }   /* ≙ mj_checkAcc */
+  double* qacc = d->scratch;
+  if (m->integrator == INT_IMPLICITFAST || m->integrator == INT_IMPLICIT) {
+    /* implicitfast: qDeriv = d(qfrc_smooth)/d(qvel) restricted to actuator + passive terms (diagonal here) */
+    double* A = d->efc_AR;  /* borrow: nv*nv <= MAXEFC^2 */
+    double* L = A + nv * nv;
+    memcpy(A, d->M, sizeof(double) * nv * nv);
+    for (int i = 0; i < nv; i++) A[i * nv + i] += h * m->dof_damping[i];
+    for (int a = 0; a < m->nu; a++) {
+      int dof = m->act_dof[a];
+      double g = m->act_gear[a];
+      A[dof * nv + dof] -= h * m->act_bias[3 * a + 2] * g * g;
+    }
+    cholesky(L, A, nv);
+    for (int i = 0; i < nv; i++) qacc[i] = d->qfrc_smooth[i] + d->qfrc_constraint[i];
+    chol_solve(L, nv, qacc);
+  } else { /* Euler (with implicit joint damping when eulerdamp is enabled) */
+    int any = 0;
+    for (int i = 0; i < nv; i++) if (m->dof_damping[i] > 0) any = 1;
+    if (any && m->eulerdamp) {
+      double* A = d->efc_AR;
+      double* L = A + nv * nv;
+      memcpy(A, d->M, sizeof(double) * nv * nv);
+      for (int i = 0; i < nv; i++) A[i * nv + i] += h * m->dof_damping[i];
+      cholesky(L, A, nv);
+      for (int i = 0; i < nv; i++) qacc[i] = d->qfrc_smooth[i] + d->qfrc_constraint[i];
+      chol_solve(L, nv, qacc);
+    } else {
+      memcpy(qacc, d->qacc, sizeof(double) * nv);
+    }
+  }
+  for (int i = 0; i < nv; i++) d->qvel[i] += h * qacc[i];
+  integrate_pos(m, d->qpos, d->qvel, h);
+  d->time += h;
+}
+
+/* ------------------------------------------------------------------------------------------ Philox4x32-10 */
+void nmo_philox4x32(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t out[4]) {
+  for (int r = 0; r < 10; r++) {
+    uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+    uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n1 = (uint32_t)p1;
+    uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1, n3 = (uint32_t)p0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+static inline double u01(uint32_t x) { return (double)(x >> 8) * (1.0 / 16777216.0); }
+
+/* ------------------------------------------------------------------------------------------ batch */
+nmo_batch* nmo_batch_create(const nmo_model* m, int n, uint64_t seed, const nmo_envcfg* cfg) {
+  if (m->nv > 64) return NULL;
+  nmo_batch* b = (nmo_batch*)calloc(1, sizeof(nmo_batch));
+  b->m = m; b->n = n; b->seed = seed;
+  if (cfg) b->cfg = *cfg;
+  b->d = (data_t*)calloc(n, sizeof(data_t));
+  b->e = (envstate_t*)calloc(n, sizeof(envstate_t));
+  for (int i = 0; i < n; i++) { data_init(m, b->d + i); b->e[i].reset_buf = 1; }
+  return b;
+}
+void nmo_batch_free(nmo_batch* b) {
+  if (!b) return;
+  for (int i = 0; i < b->n; i++) data_free(b->d + i);
+  free(b->d); free(b->e); free(b);
+}
+void nmo_set_state(nmo_batch* b, const double* qpos, const double* qvel, const double* warm) {
+  for (int i = 0; i < b->n; i++) {
+    if (qpos) memcpy(b->d[i].qpos, qpos + (size_t)i * b->m->nq, sizeof(double) * b->m->nq);
+    if (qvel) memcpy(b->d[i].qvel, qvel + (size_t)i * b->m->nv, sizeof(double) * b->m->nv);
+    if (warm) memcpy(b->d[i].qacc_warmstart, warm + (size_t)i * b->m->nv, sizeof(double) * b->m->nv);
+  }
+}
+void nmo_get_state(const nmo_batch* b, double* qpos, double* qvel, double* warm) {
+  for (int i = 0; i < b->n; i++) {
+    if (qpos) memcpy(qpos + (size_t)i * b->m->nq, b->d[i].qpos, sizeof(double) * b->m->nq);
+    if (qvel) memcpy(qvel + (size_t)i * b->m->nv, b->d[i].qvel, sizeof(double) * b->m->nv);
+    if (warm) memcpy(warm + (size_t)i * b->m->nv, b->d[i].qacc_warmstart, sizeof(double) * b->m->nv);
+  }
+}
+
+/* contiguous env slices per thread, last thread takes the remainder (env.py:195-204) */
+typedef struct { nmo_batch* b; int lo, hi, nstep, mode; const float* actions; int act_stride; float* obs; float* rew; int64_t* done; } job_t;
+
+static void env_step_one(nmo_batch* b, int i, const float* act, float* obs, float* rew, int64_t* done);
+
+static void* worker(void* arg) {
+  job_t* j = (job_t*)arg;
+  for (int i = j->lo; i < j->hi; i++) {
+    if (j->mode == 0) for (int s = 0; s < j->nstep; s++) step1(j->b->m, j->b->d + i);
+    else if (j->mode == 1) forward(j->b->m, j->b->d + i);
+    else env_step_one(j->b, i, j->actions + (size_t)i * j->act_stride, j->obs + (size_t)i * 66, j->rew + i, j->done + i);
+  }
+  return NULL;
+}
+
+static void run_parallel(job_t proto, int nthreads) {
+  int n = proto.b->n;
+  if (nthreads < 1) nthreads = 1;
+  if (nthreads > n) nthreads = n;
+  if (nthreads == 1) { proto.lo = 0; proto.hi = n; worker(&proto); return; }
+  pthread_t* th = (pthread_t*)malloc(sizeof(pthread_t) * nthreads);
+  job_t* jobs = (job_t*)malloc(sizeof(job_t) * nthreads);
+  int chunk = n / nthreads;
+  for (int t = 0; t < nthreads; t++) {
+    jobs[t] = proto;
+    jobs[t].lo = t * chunk;
+    jobs[t].hi = (t == nthreads - 1) ? n : (t + 1) * chunk;
+    pthread_create(th + t, NULL, worker, jobs + t);
+  }
+  for (int t = 0; t < nthreads; t++) pthread_join(th[t], NULL);
+  free(th); free(jobs);
+}
+
+void nmo_physics_step(nmo_batch* b, const double* ctrl, int nstep, int nthreads) {
+  if (ctrl) for (int i = 0; i < b->n; i++) memcpy(b->d[i].ctrl, ctrl + (size_t)i * b->m->nu, sizeof(double) * b->m->nu);
+  job_t j; memset(&j, 0, sizeof(j));
+  j.b = b; j.nstep = nstep; j.mode = 0;
+  run_parallel(j, nthreads);
+}
+void nmo_forward(nmo_batch* b, const double* ctrl, int nthreads) {
+  if (ctrl) for (int i = 0; i < b->n; i++) memcpy(b->d[i].ctrl, ctrl + (size_t)i * b->m->nu, sizeof(double) * b->m->nu);
+  job_t j; memset(&j, 0, sizeof(j));
+  j.b = b; j.mode = 1;
+  run_parallel(j, nthreads);
+}
+
+#define RET(name_, ptr_, cnt_)                                                         \
+  if (!strcmp(name, name_)) {                                                          \
+    int c_ = (cnt_);                                                                   \
+    if (c_ > cap) c_ = cap;                                                            \
+    for (int k_ = 0; k_ < c_; k_++) out[k_] = (double)(ptr_)[k_];                       \
+    return (cnt_);                                                                     \
+  }
+
+int nmo_get_array(const nmo_batch* b, int env, const char* name, double* out, int cap) {
+  const nmo_model* m = b->m;
+  const data_t* d = b->d + env;
+  int nv = m->nv, nb = m->nbody;
+  RET("qpos", d->qpos, m->nq) RET("qvel", d->qvel, nv) RET("qacc_warmstart", d->qacc_warmstart, nv) RET("ctrl", d->ctrl, m->nu)
+  RET("xpos", d->xpos, 3 * nb) RET("xquat", d->xquat, 4 * nb) RET("xmat", d->xmat, 9 * nb) RET("xipos", d->xipos, 3 * nb)
+  RET("ximat", d->ximat, 9 * nb) RET("xanchor", d->xanchor, 3 * m->njnt) RET("xaxis", d->xaxis, 3 * m->njnt)
+  RET("site_xpos", d->site_xpos, 3 * m->nsite) RET("subtree_com", d->subtree_com, 3 * nb) RET("cinert", d->cinert, 10 * nb)
+  RET("cdof", d->cdof, 6 * nv) RET("M", d->M, nv * nv) RET("cvel", d->cvel, 6 * nb) RET("cdof_dot", d->cdof_dot, 6 * nv)
+  RET("qfrc_bias", d->qfrc_bias, nv) RET("qfrc_actuator", d->qfrc_actuator, nv) RET("qfrc_smooth", d->qfrc_smooth, nv)
+  RET("qacc_smooth", d->qacc_smooth, nv) RET("qfrc_constraint", d->qfrc_constraint, nv) RET("qacc", d->qacc, nv)
+  RET("sensordata", d->sensordata, m->nsensor)
+  RET("efc_J", d->efc_J, d->nefc * nv) RET("efc_pos", d->efc_pos, d->nefc) RET("efc_R", d->efc_R, d->nefc)
+  RET("efc_aref", d->efc_aref, d->nefc) RET("efc_b", d->efc_b, d->nefc) RET("efc_force", d->efc_force, d->nefc)
+  RET("efc_AR", d->efc_AR, d->nefc * d->nefc) RET("efc_vel", d->efc_vel, d->nefc)
+  if (!strcmp(name, "ncon")) { if (cap > 0) out[0] = d->ncon; return 1; }
+  if (!strcmp(name, "nefc")) { if (cap > 0) out[0] = d->nefc; return 1; }
+  if (!strcmp(name, "time")) { if (cap > 0) out[0] = d->time; return 1; }
+  if (!strcmp(name, "solver_niter")) { if (cap > 0) out[0] = d->solver_niter; if (cap > 1) out[1] = d->noslip_niter; if (cap > 2) out[2] = d->warm_used; return 3; }
+  if (!strcmp(name, "nwarn")) { if (cap > 0) out[0] = d->nwarn; return 1; }
+  if (!strcmp(name, "contact")) {   /* per contact: geom1 geom2 vert dist pos(3) */
+    int c_ = d->ncon * 7;
+    for (int c = 0; c < d->ncon && 7 * c + 6 < cap; c++) {
+      out[7 * c] = d->con[c].geom1; out[7 * c + 1] = d->con[c].geom2; out[7 * c + 2] = d->con[c].vert;
+      out[7 * c + 3] = d->con[c].dist; out[7 * c + 4] = d->con[c].pos[0]; out[7 * c + 5] = d->con[c].pos[1]; out[7 * c + 6] = d->con[c].pos[2];
+    }
+    return c_;
+  }
+  return -1;
+}
+
+/* ------------------------------------------------------------------------------------------ env layer */
+enum { RW_ACTION_RATE = 0, RW_ANG_VEL_XY, RW_BASE_HEIGHT, RW_BODY_CONTACT_FORCES, RW_COLLISION, RW_DEFAULT_POSITION,
+       RW_DOF_ACC, RW_DOF_VEL, RW_FEET_AIR_TIME, RW_FEET_CONTACT_FORCES, RW_FEET_STUMBLE, RW_LIN_VEL_Z, RW_ORIENTATION,
+       RW_STAND_STILL, RW_TERMINATION, RW_TORQUES, RW_TRACKING_ANG_VEL, RW_TRACKING_LIN_VEL };
+
+/* ≙ _resample_commands (env.py:321-333) with the counter-based RNG this project defines
+   (the reference uses the unseeded global numpy MT19937, which cannot be reproduced) */
+static void resample_commands(nmo_batch* b, int i, int phase) {
+  const nmo_envcfg* c = &b->cfg;
+  envstate_t* e = b->e + i;
+  uint32_t r[4];
+  nmo_philox4x32((uint32_t)b->seed, (uint32_t)i, (uint32_t)b->step_counter, (uint32_t)((uint64_t)b->step_counter >> 32), (uint32_t)phase,
+                 (uint32_t)(b->seed >> 32), r);
+  e->commands[0] = u01(r[0]) * 2 * c->max_lin_vel_x - c->max_lin_vel_x;
+  e->commands[1] = 0;
+  e->commands[2] = u01(r[1]) * 2 * c->max_ang_vel - c->max_ang_vel;
+  double nrm = sqrt(e->commands[0] * e->commands[0] + e->commands[1] * e->commands[1]);
+  double keep = nrm > 0.02 ? 1.0 : 0.0;
+  e->commands[0] *= keep; e->commands[1] *= keep;
+}
+
+static void reset_one(nmo_batch* b, int i) {
+  /* env.py:348-361: only qpos/qvel are restored; warm start, time and ctrl survive (quirk Q3) */
+  const nmo_model* m = b->m;
+  data_t* d = b->d + i;
+  envstate_t* e = b->e + i;
+  memcpy(d->qpos, m->qpos0, sizeof(double) * m->nq);
+  memset(d->qvel, 0, sizeof(double) * m->nv);
+  resample_commands(b, i, 1);
+  memset(e->feet_air_time, 0, sizeof(e->feet_air_time));
+  e->ep_len = 0;
+  e->reset_buf = 1;
+}
+
+static double reward_term(nmo_batch* b, envstate_t* e, int k) {
+  const nmo_envcfg* c = &b->cfg;
+  double s = 0;
+  switch (k) {
+    case RW_ACTION_RATE: for (int j = 0; j < 18; j++) { double x = e->prev_actions[j] - e->actions[j]; s += x * x; } return s;
+    case RW_ANG_VEL_XY: return e->base_ang_vel[0] * e->base_ang_vel[0] + e->base_ang_vel[1] * e->base_ang_vel[1];
+    case RW_BASE_HEIGHT: { double x = e->base_height - c->base_height_target; return x * x; }
+    case RW_BODY_CONTACT_FORCES:
+      if (c->tibia_contact_mode == 1) for (int j = 0; j < 6; j++) s += e->tibia_f[j];
+      if (c->body_contact_mode == 1) s += e->body_f;
+      return s;
+    case RW_DEFAULT_POSITION: for (int j = 0; j < 18; j++) { double x = e->dof_pos[j] - c->default_pos[j]; s += x * x; } return s;
+    case RW_DOF_ACC: for (int j = 0; j < 18; j++) s += e->dof_acc[j] * e->dof_acc[j]; return s;
+    case RW_DOF_VEL: for (int j = 0; j < 18; j++) s += e->dof_vel[j] * e->dof_vel[j]; return s;
+    case RW_FEET_AIR_TIME: {   /* stateful, env.py:447-477 */
+      for (int j = 0; j < 6; j++) {
+        int contact = e->feet_f[j] > 1.0;
+        int filt = contact || e->last_contacts[j];
+        e->feet_air_time[j] += c->dt;
+        e->feet_air_time[j] *= (filt == e->last_contacts_filt[j]) ? 1.0 : 0.0;
+        e->last_contacts[j] = contact;
+        e->last_contacts_filt[j] = filt;
+        double t = e->feet_air_time[j];
+        double r = (t > 1.0 ? (t - 1.0) : 0.0) + (t < 0.5 ? (0.5 - t) : 0.0);
+        s += r * r;
+      }
+      return s;
+    }
+    case RW_FEET_CONTACT_FORCES:
+      for (int j = 0; j < 6; j++) { double x = (e->feet_f[j] - c->max_contact_force) * (e->feet_f[j] > c->max_contact_force ? 1.0 : 0.0); s += x * x; }
+      return s;
+    case RW_LIN_VEL_Z: return e->base_lin_vel[2] * e->base_lin_vel[2];
+    case RW_ORIENTATION: return e->projected_gravity[0] * e->projected_gravity[0] + e->projected_gravity[1] * e->projected_gravity[1];
+    case RW_STAND_STILL: {
+      for (int j = 0; j < 18; j++) s += fabs(e->dof_pos[j] - c->default_pos[j]);
+      double nrm = sqrt(e->commands[0] * e->commands[0] + e->commands[1] * e->commands[1]);
+      return s * (nrm < 0.01 ? 1.0 : 0.0);
+    }
+    case RW_TORQUES: return 0.0;   /* qfrc_applied is never written (quirk Q7) */
+    case RW_TRACKING_ANG_VEL: { double x = e->commands[2] - e->base_ang_vel[2]; return exp(-x * x / c->tracking_sigma); }
+    case RW_TRACKING_LIN_VEL: {
+      double x = e->commands[0] - e->base_lin_vel[0], y = e->commands[1] - e->base_lin_vel[1];
+      return exp(-(x * x + y * y) / c->tracking_sigma);
+    }
+    default: return 0.0;   /* collision / feet_stumble have no function in the reference */
+  }
+}
+
+static void env_step_one(nmo_batch* b, int i, const float* act, float* obs, float* rew, int64_t* done) {
+  const nmo_model* m = b->m;
+  const nmo_envcfg* c = &b->cfg;
+  data_t* d = b->d + i;
+  envstate_t* e = b->e + i;
+  /* E1 */
+  double prev_dof_vel[18];
+  for (int j = 0; j < 18; j++) {
+    e->prev_actions[j] = e->actions[j];
+    double a = (double)act[j] * c->action_scale;
+    e->actions[j] = a < -c->clip_actions ? -c->clip_actions : (a > c->clip_actions ? c->clip_actions : a);
+    prev_dof_vel[j] = e->dof_vel[j];
+  }
+  /* E3/E4: PD law from the carried (possibly stale) dof_pos */
+  for (int j = 0; j < 18; j++) d->ctrl[j] = ((e->actions[j] - c->default_pos[j]) - e->dof_pos[j]) * c->p_gain;
+  /* E5 */
+  for (int s = 0; s < c->decimation; s++) step1(m, d);
+  /* E6 */
+  e->ep_len += 1;
+  /* E7: base frame quantities; cvel/xipos/sensordata are one substep stale (quirk Q4) */
+  int fj = -1;
+  for (int j = 0; j < m->njnt; j++) if (m->jnt_type[j] == JNT_FREE) { fj = j; break; }
+  int bb = m->jnt_body[fj], qa = m->jnt_qposadr[fj];
+  double bq[4] = {d->qpos[qa + 3], -d->qpos[qa + 4], -d->qpos[qa + 5], -d->qpos[qa + 6]};
+  double grav[3] = {0, 0, -9.81};
+  rot_vec_quat(e->base_lin_vel, d->cvel + 6 * bb + 3, bq);
+  rot_vec_quat(e->base_ang_vel, d->cvel + 6 * bb, bq);
+  rot_vec_quat(e->projected_gravity, grav, bq);
+  /* E8 */
+  for (int j = 0; j < 18; j++) { e->dof_pos[j] = d->qpos[m->nq - 18 + j]; e->dof_vel[j] = d->qvel[m->nv - 18 + j]; }
+  e->base_height = d->xipos[3 * bb + 2];
+  for (int j = 0; j < 6; j++) { e->tibia_f[j] = d->sensordata[j]; e->feet_f[j] = d->sensordata[6 + j]; }
+  e->body_f = d->sensordata[12];
+  /* E9 */
+  for (int j = 0; j < 18; j++) e->dof_acc[j] = (e->dof_vel[j] - prev_dof_vel[j]) / c->dt;
+  for (int j = 0; j < 6; j++) e->tibia_f[j] *= (e->feet_f[j] == 0) ? 1.0 : 0.0;
+  /* E10 */
+  if (c->resample_period > 0 && e->ep_len % c->resample_period == 0) resample_commands(b, i, 0);
+  /* E11 */
+  e->time_out = (double)e->ep_len > c->max_episode_length;
+  int reset = e->time_out;
+  double fmax = e->feet_f[0], tmax = e->tibia_f[0];
+  for (int j = 1; j < 6; j++) { if (e->feet_f[j] > fmax) fmax = e->feet_f[j]; if (e->tibia_f[j] > tmax) tmax = e->tibia_f[j]; }
+  reset |= fmax > c->termination_contact_force;
+  if (c->tibia_contact_mode == 2) reset |= tmax > c->tibia_max_contact_force;
+  if (c->body_contact_mode == 2) reset |= e->body_f > c->body_max_contact_force;
+  {
+    const double* pg = e->projected_gravity;
+    double nrm = sqrt(pg[0] * pg[0] + pg[1] * pg[1] + pg[2] * pg[2]);
+    reset |= acos(-pg[2] / nrm) > 60.0 * M_PI / 180.0;
+  }
+  e->reset_buf = reset;
+  /* E13: reset_idx runs BEFORE this step's rewards are accumulated (env.py:274 precedes :277-288), so the
+     logged episode sums exclude the terminal step and that step's reward opens the next episode's sum */
+  if (reset) {
+    reset_one(b, i);
+    memcpy(e->sums_at_reset, e->episode_sums, sizeof(e->episode_sums));
+    memset(e->episode_sums, 0, sizeof(e->episode_sums));
+  }
+  /* E14: rewards from pre-reset buffers, post-reset commands (quirk Q1) */
+  double total = 0;
+  for (int k = 0; k < NMO_NREW; k++) {
+    if (k == RW_TERMINATION || c->rew_scale[k] == 0) continue;
+    double r = reward_term(b, e, k) * c->rew_scale[k];
+    total += r;
+    e->episode_sums[k] += r;
+  }
+  if (c->rew_scale[RW_TERMINATION] != 0) {
+    double r = (double)(e->reset_buf * (e->time_out ? 0 : 1)) * c->rew_scale[RW_TERMINATION];
+    total += r;
+    e->episode_sums[RW_TERMINATION] += r;
+  }
+  /* E15 */
+  double o[66];
+  for (int k = 0; k < 3; k++) {
+    o[k] = e->base_lin_vel[k] * c->obs_lin_vel;
+    o[3 + k] = e->base_ang_vel[k] * c->obs_ang_vel;
+    o[6 + k] = e->projected_gravity[k];
+  }
+  o[9] = e->commands[0] * c->obs_lin_vel; o[10] = e->commands[1] * c->obs_lin_vel; o[11] = e->commands[2] * c->obs_ang_vel;
+  for (int j = 0; j < 18; j++) {
+    o[12 + j] = (e->dof_pos[j] - c->default_pos[j]) * c->obs_dof_pos;
+    o[30 + j] = e->dof_vel[j] * c->obs_dof_vel;
+    o[48 + j] = e->actions[j];
+  }
+  if (c->add_noise) {
+    for (int k = 0; k < 66; k += 4) {
+      uint32_t r[4];
+      nmo_philox4x32((uint32_t)b->seed, (uint32_t)i, (uint32_t)b->step_counter, (uint32_t)((uint64_t)b->step_counter >> 32),
+                     (uint32_t)(2 + k / 4), (uint32_t)(b->seed >> 32), r);
+      for (int q = 0; q < 4 && k + q < 66; q++) o[k + q] += (2 * u01(r[q]) - 1) * c->noise_vec[k + q];
+    }
+  }
+  for (int k = 0; k < 66; k++) {
+    double v = o[k] < -c->clip_obs ? -c->clip_obs : (o[k] > c->clip_obs ? c->clip_obs : o[k]);
+    obs[k] = (float)v;
+  }
+  *rew = (float)total;
+  *done = e->reset_buf;
+}
+
+void nmo_env_step(nmo_batch* b, const float* actions, int act_stride, float* obs, float* rew, int64_t* done,
+                  float* time_outs, double* ep_sum_means, int* num_reset, int nthreads) {
+  b->step_counter += 1;      /* E6: common_step_counter (used as the RNG counter of this step) */
+  /* episode sums of envs that reset this step must be captured before they are zeroed: do the
+     per-env work first, then the cross-env reduction (env.py:363-367) */
+  job_t j; memset(&j, 0, sizeof(j));
+  j.b = b; j.mode = 2; j.actions = actions; j.act_stride = act_stride; j.obs = obs; j.rew = rew; j.done = done;
+  run_parallel(j, nthreads);
+  int nres = 0;
+  double acc[NMO_NREW];
+  memset(acc, 0, sizeof(acc));
+  for (int i = 0; i < b->n; i++) {
+    if (time_outs) time_outs[i] = b->e[i].time_out ? 1.0f : 0.0f;
+    if (b->e[i].reset_buf) {
+      nres++;
+      for (int k = 0; k < NMO_NREW; k++) acc[k] += b->e[i].sums_at_reset[k];
+    }
+  }
+  /* extras["episode"]["rew_k"] = mean over reset envs / max_episode_length_s (env.py:366) */
+  if (ep_sum_means)
+    for (int k = 0; k < NMO_NREW; k++) ep_sum_means[k] = nres ? acc[k] / nres / b->cfg.max_episode_length_s : 0.0;
+  if (num_reset) *num_reset = nres;
+}
+
+void nmo_env_reset_idx(nmo_batch* b, const int64_t* ids, int n) {
+  for (int k = 0; k < n; k++) {
+    int i = (int)ids[k];
+    reset_one(b, i);
+    memset(b->e[i].episode_sums, 0, sizeof(b->e[i].episode_sums));
+  }
+}
+
+int nmo_env_get(const nmo_batch* b, const char* name, double* out, int cap) {
+  int n = b->n;
+#define EGET(nm, expr, per)                                                     \
+  if (!strcmp(name, nm)) {                                                      \
+    for (int i = 0; i < n; i++)                                                 \
+      for (int k = 0; k < (per); k++)                                           \
+        if (i * (per) + k < cap) out[i * (per) + k] = (double)(expr);           \
+    return n * (per);                                                           \
+  }
+  EGET("ep_len", b->e[i].ep_len, 1) EGET("commands", b->e[i].commands[k], 3) EGET("actions", b->e[i].actions[k], 18)
+  EGET("dof_pos", b->e[i].dof_pos[k], 18) EGET("dof_vel", b->e[i].dof_vel[k], 18)
+  EGET("episode_sums", b->e[i].episode_sums[k], NMO_NREW) EGET("feet_air_time", b->e[i].feet_air_time[k], 6)
+  EGET("last_contacts", b->e[i].last_contacts[k], 6) EGET("last_contacts_filt", b->e[i].last_contacts_filt[k], 6)
+  EGET("reset_buf", b->e[i].reset_buf, 1) EGET("time_out", b->e[i].time_out, 1)
+  EGET("tibia_f", b->e[i].tibia_f[k], 6) EGET("feet_f", b->e[i].feet_f[k], 6) EGET("body_f", b->e[i].body_f, 1)
+  EGET("base_lin_vel", b->e[i].base_lin_vel[k], 3) EGET("base_ang_vel", b->e[i].base_ang_vel[k], 3)
+  EGET("projected_gravity", b->e[i].projected_gravity[k], 3)
+  if (!strcmp(name, "step_counter")) { if (cap > 0) out[0] = (double)b->step_counter; return 1; }
+  return -1;
+}
+
+int nmo_env_set(nmo_batch* b, const char* name, const double* in, int count) {
+  int n = b->n;
+#define ESET(nm, lhs, type, per)                                                \
+  if (!strcmp(name, nm)) {                                                      \
+    if (count != n * (per)) return -2;                                          \
+    for (int i = 0; i < n; i++)                                                 \
+      for (int k = 0; k < (per); k++) lhs = (type)in[i * (per) + k];            \
+    return 0;                                                                   \
+  }
+  ESET("ep_len", b->e[i].ep_len, int64_t, 1) ESET("commands", b->e[i].commands[k], double, 3)
+  ESET("actions", b->e[i].actions[k], double, 18) ESET("dof_pos", b->e[i].dof_pos[k], double, 18)
+  ESET("dof_vel", b->e[i].dof_vel[k], double, 18) ESET("episode_sums", b->e[i].episode_sums[k], double, NMO_NREW)
+  if (!strcmp(name, "step_counter")) { b->step_counter = (int64_t)in[0]; return 0; }
+  return -1;
+}
