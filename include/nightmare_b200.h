@@ -1,0 +1,137 @@
+/* nightmare_b200.h — C ABI of the B200-native batched Nightmare-v3 environment step.
+ *
+ * The reference has no native boundary of its own: its env layer (Python) drives MuJoCo 3.1.2
+ * through pybind11.  Each entry point below names the reference call site(s) it replaces
+ * (paths relative to /root/reference).  All pointers in nm_buffers are DEVICE pointers owned by the
+ * caller (torch tensors in the Python host layer); the library never synchronises the stream.
+ *
+ * Error convention: functions return 0 on success or a negative nm_status; nm_last_error() gives
+ * the message of the last failure on the calling thread.  No exceptions cross this boundary.
+ */
+#ifndef NIGHTMARE_B200_H
+#define NIGHTMARE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NM_NDOF 18        /* actuated hinge dofs  (envs/nightmare_v3_env.py:40  num_dof = nv - 6) */
+#define NM_NQ 25          /* models/nightmare_v3/mjmodel.xml: free joint (7) + 18 hinges */
+#define NM_NV 24
+#define NM_NOBS 66        /* envs/nightmare_v3_config.py:11 */
+#define NM_NSENSOR 13     /* mjmodel.xml:156-170 */
+#define NM_NREW 18        /* reward terms in alphabetical order (envs/helpers.py:7) */
+#define NM_MAXCON_GEOM 4  /* plane-mesh: support vertex + up to 3 more */
+#define NM_DBG_STRIDE 160 /* floats per env in the optional debug buffer */
+
+typedef enum {
+  NM_OK = 0,
+  NM_ERR_IO = -1,          /* file missing / unreadable                         */
+  NM_ERR_FORMAT = -2,      /* not an NMB1 compiled model / missing arrays       */
+  NM_ERR_UNSUPPORTED = -3, /* model topology/options outside the kernel's scope */
+  NM_ERR_ARG = -4,
+  NM_ERR_CUDA = -5,
+  NM_ERR_NAME = -6
+} nm_status;
+
+typedef struct nm_model nm_model;
+typedef struct nm_batch nm_batch;
+typedef void* nm_stream;   /* cudaStream_t */
+
+/* Scalars of NightmareV3Config the step reads (envs/nightmare_v3_config.py:4-100), pre-digested
+ * the way NightmareV3Env.__init__ does it (envs/nightmare_v3_env.py:99-137).  Same layout as the
+ * oracle's nmo_envcfg. */
+typedef struct {
+  int32_t decimation, num_actions, tibia_contact_mode, body_contact_mode, add_noise, resample_period, strict_reference, pad0;
+  double action_scale, clip_actions, p_gain, clip_obs;
+  double default_pos[NM_NDOF];
+  double obs_lin_vel, obs_ang_vel, obs_dof_pos, obs_dof_vel;
+  double max_lin_vel_x, max_ang_vel;
+  double max_episode_length, max_episode_length_s;
+  double termination_contact_force, tibia_max_contact_force, body_max_contact_force;
+  double tracking_sigma, base_height_target, max_contact_force;
+  double dt;
+  double rew_scale[NM_NREW];
+  double noise_vec[NM_NOBS];
+} nm_envcfg;
+
+/* Caller-owned device buffers, row-major [num_envs, K]. */
+typedef struct {
+  /* physics state  (≙ MjData.qpos / qvel / qacc_warmstart, envs/nightmare_v3_env.py:38) */
+  float* qpos;           /* [N,25] */
+  float* qvel;           /* [N,24] */
+  float* warm;           /* [N,24] */
+  /* env carry state (≙ buffers of envs/nightmare_v3_env.py:56-97) */
+  float* actions;        /* [N,18] clipped actions of the previous step */
+  float* dof_pos;        /* [N,18] */
+  float* dof_vel;        /* [N,18] */
+  float* commands;       /* [N,3]  */
+  int64_t* episode_length; /* [N] (episode_length_buf, int64 like the reference :88) */
+  float* episode_sums;   /* [N,18] indexed by reward-term id */
+  float* feet_air_time;  /* [N,6]  */
+  int32_t* contact_bits; /* [N] bits 0-5 last_contacts, 8-13 last_contacts_filt */
+  /* step outputs (≙ return tuple of step(), envs/nightmare_v3_env.py:311) */
+  float* obs;            /* [N,66] */
+  float* rew;            /* [N]    */
+  int64_t* done;         /* [N]    reset_buf */
+  float* time_outs;      /* [N]    */
+  float* sensordata;     /* [N,13] touch sensors of the last substep */
+  float* episode_acc;    /* [NM_NREW+1] sum over envs reset this step of their episode sums, then the count
+                            (zeroed by nm_step before the kernel runs) */
+  float* debug;          /* [N,NM_DBG_STRIDE] or NULL */
+} nm_buffers;
+
+const char* nm_last_error(void);
+
+/* ≙ mj.MjModel.from_xml_path(cfg.env.model_path)           envs/nightmare_v3_env.py:37
+ * The MJCF is compiled by the host layer (nightmare_rl_b200/mjcf.py) into an .nmb file / buffer. */
+int  nm_model_load(const char* nmb_path, nm_model** out);
+int  nm_model_from_buffer(const void* data, size_t nbytes, nm_model** out);
+void nm_model_destroy(nm_model*);
+/* ≙ model.nq / nv / nu / nbody ...  ("nq","nv","nu","nbody","ngeom","nsensor","nleg")   env.py:40-41 */
+int  nm_model_size(const nm_model*, const char* what);
+/* ≙ model.opt.timestep                                     envs/nightmare_v3_env.py:99 */
+double nm_model_timestep(const nm_model*);
+/* ≙ mj.mj_name2id(model, objtype, name) (mjtObj numbering)  envs/nightmare_v3_env.py:48 */
+int  nm_name2id(const nm_model*, int objtype, const char* name);
+/* ≙ model.qpos0                                            envs/nightmare_v3_env.py:349 */
+int  nm_model_qpos0(const nm_model*, float* out, int cap);
+
+/* ≙ [mj.MjData(model) for _ in range(num_envs)]             envs/nightmare_v3_env.py:38 */
+int  nm_batch_create(const nm_model*, int num_envs, int device, uint64_t seed, const nm_envcfg* cfg,
+                     const nm_buffers* bufs, nm_batch** out);
+void nm_batch_destroy(nm_batch*);
+/* global env id of local env 0 (multi-GPU sharding keeps RNG streams keyed by GLOBAL env id) */
+int  nm_batch_set_env_offset(nm_batch*, int64_t first_global_env);
+
+/* ≙ NightmareV3Env.step(actions)                            envs/nightmare_v3_env.py:145-311
+ * actions: device float32 [N, act_stride], first 18 columns used (:156).  step_counter is the
+ * value of common_step_counter AFTER this step's increment (:213); it is the RNG counter. */
+int  nm_step(nm_batch*, const float* actions, int act_stride, int64_t step_counter, nm_stream stream);
+/* ≙ for i: data[i].ctrl = ctrl[i]; mj.mj_step(model, data[i], nstep)   envs/nightmare_v3_env.py:191-200
+ * Raw physics (parity harness): ctrl device float32 [N,18]. */
+int  nm_physics_step(nm_batch*, const float* ctrl, int nstep, nm_stream stream);
+/* ≙ reset_idx(env_ids) state part: data[i].qpos = qpos0; data[i].qvel = 0      envs/nightmare_v3_env.py:348-361
+ * env_ids: device int64 [n]. Also resamples commands (phase 1 of step_counter), zeroes feet_air_time,
+ * episode_length and episode_sums, sets done=1. */
+int  nm_reset_idx(nm_batch*, const int64_t* env_ids, int n, int64_t step_counter, nm_stream stream);
+
+/* Same as nm_step but with HOST buffers: copies actions H2D, runs the step and copies
+ * obs/rew/done back D2H on `stream`, then synchronises the stream (end-to-end entry point). */
+int  nm_step_host(nm_batch*, const float* h_actions, int act_stride, int64_t step_counter,
+                  float* h_obs, float* h_rew, int64_t* h_done, nm_stream stream);
+
+/* number of kernel launches issued by this batch so far (bench.py "gpu_launches") */
+int64_t nm_batch_launches(const nm_batch*);
+
+/* Measurement utility (no reference counterpart): FFMA micro-benchmark on the current device, returns
+ * TFLOP/s (2 flops per FMA).  bench.py uses it as the FP32-pipe roofline denominator. */
+double nm_measure_fp32_peak(nm_stream stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

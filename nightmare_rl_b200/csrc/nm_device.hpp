@@ -1,0 +1,89 @@
+// nm_device.hpp — constant tables shared by the host ABI (nm_abi.cu) and the step kernels (nm_kernels.cu).
+//
+// Topology the kernels are specialised for ("legged-star"): one free-floating base body plus up to six
+// serial chains of three single-hinge links (coxa, femur, tibia), joint anchors at the link origins;
+// one convex collision hull on every last link and one on the base, colliding with a static plane;
+// touch sites on the last links and on the base.  That is exactly models/nightmare_v3/mjmodel.xml:32-170
+// of the reference.  nm_batch_create() verifies the compiled model against it and fails loudly otherwise.
+#pragma once
+#include <cstdint>
+
+#define NM_OCT 8            // lanes per environment: 6 leg lanes + base-geom lane + spare
+#define NM_MAXC 4           // contacts per collision geom
+#define NM_BLOCK 64         // threads per CTA = 8 environments
+
+struct NmGeom {
+  int has;                  // lane owns a collision geom
+  int hull_adr, hull_num, start;
+  float rbound, margin, mu;
+  float rfac;               // R = rfac * (1-imp)/imp   (pyramidal: 2 mu_reg^2 * (1+mu^2) * invweight)
+  float K, B;               // reference-acceleration spring/damper from solref
+  float dmin, dmax, width, mid, power;
+};
+
+struct NmLeg {
+  float pos[3][3];          // link origin in parent frame
+  float rc[3][9];           // constant rotation of the link frame (body quat)
+  int   rc_ident[3];
+  float axis[3][3];         // hinge axis, link frame
+  float ipos[3][3];         // link COM, link frame
+  float iloc[3][6];         // link inertia about its COM in the link frame: xx yy zz xy xz yz
+  float mass[3];
+  float qref[3];
+  float gain0[3], bias0[3], bias1[3], bias2[3], gear[3];
+  float clo[3], chi[3], flo[3], fhi[3];
+  float damping[3], armature[3];
+  float site_pos[2][3];     // touch sites on the last link: slot 0 ("tibia"/"base"), slot 1 ("foot")
+  float site_r[2];          // < 0: absent
+  float isleg;              // 1 for real legs, 0 for the base-geom / spare lanes
+  NmGeom geom;
+};
+
+struct NmDevModel {
+  NmLeg leg[NM_OCT];
+  float b_ipos[3], b_iloc[6], b_mass, total_mass;
+  float plane_n[3], plane_d, frame[9];
+  float gravity[3];
+  float timestep, tolerance, noslip_tolerance, solver_scale;
+  int iterations, noslip_iterations, nleg, integrator;
+  float imp_damp, imp_act;  // which velocity derivatives enter the implicit velocity update (implicitfast: both; Euler+eulerdamp: damping)
+  float qpos0[32];
+};
+
+// env-layer scalars in fp32 (from nm_envcfg)
+struct NmDevCfg {
+  int decimation, tibia_mode, body_mode, add_noise, resample_period, pad[3];
+  float action_scale, clip_actions, p_gain, clip_obs;
+  float default_pos[18];
+  float obs_lin_vel, obs_ang_vel, obs_dof_pos, obs_dof_vel;
+  float max_lin_vel_x, max_ang_vel, max_episode_length, inv_episode_length_s;
+  float term_force, tibia_max_force, body_max_force;
+  float inv_tracking_sigma, base_height_target, max_contact_force, dt, inv_dt;
+  float rew_scale[18];
+  float noise_vec[66];
+};
+
+struct NmKernelArgs {
+  const NmDevModel* model;
+  const NmDevCfg* cfg;
+  const float4* hull_vert;
+  const int* hull_nbr_adr;
+  const int* hull_nbr;
+  int num_envs;
+  int nstep;
+  long long step_counter;
+  long long env_offset;
+  unsigned long long seed;
+  // state
+  float* qpos; float* qvel; float* warm;
+  float* actions; float* dof_pos; float* dof_vel; float* commands;
+  long long* episode_length; float* episode_sums; float* feet_air_time; int* contact_bits;
+  float* obs; float* rew; long long* done; float* time_outs; float* sensordata; float* episode_acc; float* debug;
+  // inputs
+  const float* in_actions; int act_stride;   // env mode
+  const float* in_ctrl;                       // physics-only mode
+};
+
+void nm_launch_step(const NmKernelArgs& a, bool env_mode, void* stream);
+void nm_launch_reset(const NmKernelArgs& a, const long long* env_ids, int n, void* stream);
+double nm_run_ffma_peak(void* stream);

@@ -1,0 +1,1193 @@
+// nm_kernels.cu — the whole environment step of the Nightmare-v3 hexapod in ONE kernel launch (sm_100a).
+//
+// Replaces, per environment and per call of NightmareV3Env.step (reference envs/nightmare_v3_env.py:145-311):
+//   action scaling/clipping + PD law (:152-188), `decimation` x mj_step (:200; MuJoCo 3.1.2 pipeline:
+//   kinematics, comPos, CRBA, factorisation, plane/hull collision, pyramidal contact rows, RNE, velocity
+//   actuators, PGS + noslip, touch sensors, implicitfast), state extraction (:216-232), command
+//   resampling (:235,:321-333), termination (:239-258), reset (:335-361), rewards (:277-288,:399-497)
+//   and observations (:291-309).
+//
+// Work decomposition (design, not a port): one environment per 8-lane group ("octet") of a warp,
+// four environments per warp.  Lanes 0..5 each own one leg (3 hinges, 3 links, the tibia hull and
+// its contacts); lane 6 owns the base hull and its contacts; lane 7 is a spare.  Everything that
+// belongs to the floating base (pose, 6x6 Schur complement, base accelerations) is computed
+// redundantly by all eight lanes from bit-identical inputs, so it never has to be communicated; sums
+// over legs are xor-butterfly shuffles inside the octet.  The mass matrix is never formed: with the
+// legs eliminated first, M^-1 splits into six private 3x3 Cholesky factors G_k, six 3x6 couplings
+// E_k = M_k^-1 C_k and one replicated 6x6 factor G_S of S = M_bb - sum_k C_k^T E_k.  Contact rows are
+// whitened by those factors (Y = J~ G_S^-T in base space, Z = J_k G_k^-T in leg space), which turns
+// the dual PGS / noslip sweeps into updates of a 6-vector u (shared) and a 3-vector w_k (private):
+// A = J M^-1 J^T + R is never materialised either.
+//
+// All state lives in registers for the whole step (both substeps); HBM is touched once on the way
+// in and once on the way out.  Shared memory only holds the per-CTA copy of the model constants.
+#include <cuda_runtime.h>
+#include <math_constants.h>
+
+#include "nm_device.hpp"
+
+#define FULL 0xffffffffu
+#define NM_MINVAL 1e-15f
+#define NM_TINY 1e-30f
+
+// ---------------------------------------------------------------------------------------------- small algebra
+struct V3 { float x, y, z; };
+struct M3 { float a[9]; };          // row-major
+struct SV { V3 w, v; };             // spatial motion [angular; linear] or force [torque; force]
+struct In { float xx, yy, zz, xy, xz, yz; V3 h; float m; };   // spatial inertia about the c-frame origin
+
+__device__ __forceinline__ V3 mk(float x, float y, float z) { V3 r; r.x = x; r.y = y; r.z = z; return r; }
+__device__ __forceinline__ V3 ld3(const float* p) { return mk(p[0], p[1], p[2]); }
+__device__ __forceinline__ V3 operator+(V3 a, V3 b) { return mk(a.x + b.x, a.y + b.y, a.z + b.z); }
+__device__ __forceinline__ V3 operator-(V3 a, V3 b) { return mk(a.x - b.x, a.y - b.y, a.z - b.z); }
+__device__ __forceinline__ V3 operator*(float s, V3 a) { return mk(s * a.x, s * a.y, s * a.z); }
+__device__ __forceinline__ float dot(V3 a, V3 b) { return fmaf(a.x, b.x, fmaf(a.y, b.y, a.z * b.z)); }
+__device__ __forceinline__ V3 cross(V3 a, V3 b) { return mk(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
+__device__ __forceinline__ V3 fma3(float s, V3 a, V3 b) { return mk(fmaf(s, a.x, b.x), fmaf(s, a.y, b.y), fmaf(s, a.z, b.z)); }
+__device__ __forceinline__ V3 mul(const M3& m, V3 v) {
+  return mk(fmaf(m.a[0], v.x, fmaf(m.a[1], v.y, m.a[2] * v.z)), fmaf(m.a[3], v.x, fmaf(m.a[4], v.y, m.a[5] * v.z)),
+            fmaf(m.a[6], v.x, fmaf(m.a[7], v.y, m.a[8] * v.z)));
+}
+__device__ __forceinline__ V3 mulT(const M3& m, V3 v) {
+  return mk(fmaf(m.a[0], v.x, fmaf(m.a[3], v.y, m.a[6] * v.z)), fmaf(m.a[1], v.x, fmaf(m.a[4], v.y, m.a[7] * v.z)),
+            fmaf(m.a[2], v.x, fmaf(m.a[5], v.y, m.a[8] * v.z)));
+}
+__device__ __forceinline__ V3 col(const M3& m, int i) { return mk(m.a[i], m.a[3 + i], m.a[6 + i]); }
+__device__ __forceinline__ M3 matmul(const M3& A, const M3& B) {
+  M3 C;
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++) C.a[3 * i + j] = fmaf(A.a[3 * i], B.a[j], fmaf(A.a[3 * i + 1], B.a[3 + j], A.a[3 * i + 2] * B.a[6 + j]));
+  return C;
+}
+__device__ __forceinline__ M3 quat2mat(float w, float x, float y, float z) {
+  M3 m;
+  m.a[0] = w * w + x * x - y * y - z * z; m.a[1] = 2.f * (x * y - w * z); m.a[2] = 2.f * (x * z + w * y);
+  m.a[3] = 2.f * (x * y + w * z); m.a[4] = w * w - x * x + y * y - z * z; m.a[5] = 2.f * (y * z - w * x);
+  m.a[6] = 2.f * (x * z - w * y); m.a[7] = 2.f * (y * z + w * x); m.a[8] = w * w - x * x - y * y + z * z;
+  return m;
+}
+// rotation by `angle` about unit `ax` (Rodrigues)
+__device__ __forceinline__ M3 axis_rot(V3 ax, float angle) {
+  float s, c;
+  sincosf(angle, &s, &c);
+  float t = 1.f - c;
+  M3 m;
+  m.a[0] = fmaf(t * ax.x, ax.x, c); m.a[1] = fmaf(t * ax.x, ax.y, -s * ax.z); m.a[2] = fmaf(t * ax.x, ax.z, s * ax.y);
+  m.a[3] = fmaf(t * ax.x, ax.y, s * ax.z); m.a[4] = fmaf(t * ax.y, ax.y, c); m.a[5] = fmaf(t * ax.y, ax.z, -s * ax.x);
+  m.a[6] = fmaf(t * ax.x, ax.z, -s * ax.y); m.a[7] = fmaf(t * ax.y, ax.z, s * ax.x); m.a[8] = fmaf(t * ax.z, ax.z, c);
+  return m;
+}
+// X * Iloc * X^T for symmetric Iloc = (xx yy zz xy xz yz)
+__device__ __forceinline__ void rot_inertia(const M3& X, const float* I, float* o) {
+  float T[9];
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    float a = X.a[3 * i], b = X.a[3 * i + 1], c = X.a[3 * i + 2];
+    T[3 * i] = fmaf(a, I[0], fmaf(b, I[3], c * I[4]));
+    T[3 * i + 1] = fmaf(a, I[3], fmaf(b, I[1], c * I[5]));
+    T[3 * i + 2] = fmaf(a, I[4], fmaf(b, I[5], c * I[2]));
+  }
+  o[0] = fmaf(T[0], X.a[0], fmaf(T[1], X.a[1], T[2] * X.a[2]));
+  o[1] = fmaf(T[3], X.a[3], fmaf(T[4], X.a[4], T[5] * X.a[5]));
+  o[2] = fmaf(T[6], X.a[6], fmaf(T[7], X.a[7], T[8] * X.a[8]));
+  o[3] = fmaf(T[0], X.a[3], fmaf(T[1], X.a[4], T[2] * X.a[5]));
+  o[4] = fmaf(T[0], X.a[6], fmaf(T[1], X.a[7], T[2] * X.a[8]));
+  o[5] = fmaf(T[3], X.a[6], fmaf(T[4], X.a[7], T[5] * X.a[8]));
+}
+__device__ __forceinline__ In make_inertia(const float* Iw, float m, V3 r) {
+  In c;
+  c.xx = fmaf(m, r.y * r.y + r.z * r.z, Iw[0]);
+  c.yy = fmaf(m, r.x * r.x + r.z * r.z, Iw[1]);
+  c.zz = fmaf(m, r.x * r.x + r.y * r.y, Iw[2]);
+  c.xy = fmaf(-m, r.x * r.y, Iw[3]);
+  c.xz = fmaf(-m, r.x * r.z, Iw[4]);
+  c.yz = fmaf(-m, r.y * r.z, Iw[5]);
+  c.h = m * r;
+  c.m = m;
+  return c;
+}
+__device__ __forceinline__ In operator+(const In& a, const In& b) {
+  In c;
+  c.xx = a.xx + b.xx; c.yy = a.yy + b.yy; c.zz = a.zz + b.zz; c.xy = a.xy + b.xy; c.xz = a.xz + b.xz; c.yz = a.yz + b.yz;
+  c.h = a.h + b.h; c.m = a.m + b.m;
+  return c;
+}
+__device__ __forceinline__ SV imul(const In& i, const SV& s) {   // spatial inertia times motion
+  SV r;
+  r.w.x = fmaf(i.xx, s.w.x, fmaf(i.xy, s.w.y, i.xz * s.w.z)) + (i.h.y * s.v.z - i.h.z * s.v.y);
+  r.w.y = fmaf(i.xy, s.w.x, fmaf(i.yy, s.w.y, i.yz * s.w.z)) + (i.h.z * s.v.x - i.h.x * s.v.z);
+  r.w.z = fmaf(i.xz, s.w.x, fmaf(i.yz, s.w.y, i.zz * s.w.z)) + (i.h.x * s.v.y - i.h.y * s.v.x);
+  r.v = fma3(i.m, s.v, cross(s.w, i.h));
+  return r;
+}
+__device__ __forceinline__ SV cross_motion(const SV& vel, const SV& s) { SV r; r.w = cross(vel.w, s.w); r.v = cross(vel.w, s.v) + cross(vel.v, s.w); return r; }
+__device__ __forceinline__ SV cross_force(const SV& vel, const SV& f) { SV r; r.w = cross(vel.w, f.w) + cross(vel.v, f.v); r.v = cross(vel.w, f.v); return r; }
+__device__ __forceinline__ float sdot(const SV& a, const SV& b) { return dot(a.w, b.w) + dot(a.v, b.v); }
+__device__ __forceinline__ SV operator+(const SV& a, const SV& b) { SV r; r.w = a.w + b.w; r.v = a.v + b.v; return r; }
+__device__ __forceinline__ SV sfma(float s, const SV& a, const SV& b) { SV r; r.w = fma3(s, a.w, b.w); r.v = fma3(s, a.v, b.v); return r; }
+
+// ---------------------------------------------------------------------------------------------- octet collectives
+__device__ __forceinline__ float oct_sum(float v) {
+  v += __shfl_xor_sync(FULL, v, 1);
+  v += __shfl_xor_sync(FULL, v, 2);
+  v += __shfl_xor_sync(FULL, v, 4);
+  return v;
+}
+__device__ __forceinline__ float oct_max(float v) {
+  v = fmaxf(v, __shfl_xor_sync(FULL, v, 1));
+  v = fmaxf(v, __shfl_xor_sync(FULL, v, 2));
+  v = fmaxf(v, __shfl_xor_sync(FULL, v, 4));
+  return v;
+}
+__device__ __forceinline__ int oct_sumi(int v) {
+  v += __shfl_xor_sync(FULL, v, 1);
+  v += __shfl_xor_sync(FULL, v, 2);
+  v += __shfl_xor_sync(FULL, v, 4);
+  return v;
+}
+__device__ __forceinline__ V3 oct_sum3(V3 v) { return mk(oct_sum(v.x), oct_sum(v.y), oct_sum(v.z)); }
+__device__ __forceinline__ float oct_bcast(float v, int src_lane) { return __shfl_sync(FULL, v, src_lane); }
+
+// ---------------------------------------------------------------------------------------------- factorisations
+// 3x3 Cholesky of (m00 m10 m11 m20 m21 m22): g = (l00 l10 l11 l20 l21 l22), gi = inverse diagonal
+__device__ __forceinline__ void chol3(const float* m, float* g, float* gi) {
+  gi[0] = rsqrtf(fmaxf(m[0], NM_TINY)); g[0] = m[0] * gi[0];
+  g[1] = m[1] * gi[0];
+  float d1 = fmaxf(fmaf(-g[1], g[1], m[2]), NM_TINY);
+  gi[1] = rsqrtf(d1); g[2] = d1 * gi[1];
+  g[3] = m[3] * gi[0];
+  g[4] = fmaf(-g[3], g[1], m[4]) * gi[1];
+  float d2 = fmaxf(fmaf(-g[4], g[4], fmaf(-g[3], g[3], m[5])), NM_TINY);
+  gi[2] = rsqrtf(d2); g[5] = d2 * gi[2];
+}
+__device__ __forceinline__ void fwd3(const float* g, const float* gi, const float* b, float* y) {
+  y[0] = b[0] * gi[0];
+  y[1] = fmaf(-g[1], y[0], b[1]) * gi[1];
+  y[2] = fmaf(-g[4], y[1], fmaf(-g[3], y[0], b[2])) * gi[2];
+}
+__device__ __forceinline__ void bwd3(const float* g, const float* gi, const float* y, float* x) {
+  x[2] = y[2] * gi[2];
+  x[1] = fmaf(-g[4], x[2], y[1]) * gi[1];
+  x[0] = fmaf(-g[3], x[2], fmaf(-g[1], x[1], y[0])) * gi[0];
+}
+// 6x6 lower-triangular packed row-wise: index(i,j) = i(i+1)/2 + j
+#define TRI(i, j) ((i) * ((i) + 1) / 2 + (j))
+__device__ __forceinline__ void chol6(float* s, float* si) {   // in place
+#pragma unroll
+  for (int j = 0; j < 6; j++) {
+    float d = s[TRI(j, j)];
+#pragma unroll
+    for (int k = 0; k < j; k++) d = fmaf(-s[TRI(j, k)], s[TRI(j, k)], d);
+    d = fmaxf(d, NM_TINY);
+    si[j] = rsqrtf(d);
+    s[TRI(j, j)] = d * si[j];
+#pragma unroll
+    for (int i = j + 1; i < 6; i++) {
+      float t = s[TRI(i, j)];
+#pragma unroll
+      for (int k = 0; k < j; k++) t = fmaf(-s[TRI(i, k)], s[TRI(j, k)], t);
+      s[TRI(i, j)] = t * si[j];
+    }
+  }
+}
+__device__ __forceinline__ void fwd6(const float* s, const float* si, const float* b, float* y) {
+#pragma unroll
+  for (int i = 0; i < 6; i++) {
+    float t = b[i];
+#pragma unroll
+    for (int k = 0; k < i; k++) t = fmaf(-s[TRI(i, k)], y[k], t);
+    y[i] = t * si[i];
+  }
+}
+__device__ __forceinline__ void bwd6(const float* s, const float* si, const float* y, float* x) {
+#pragma unroll
+  for (int i = 5; i >= 0; i--) {
+    float t = y[i];
+#pragma unroll
+    for (int k = i + 1; k < 6; k++) t = fmaf(-s[TRI(k, i)], x[k], t);
+    x[i] = t * si[i];
+  }
+}
+
+// Block elimination of the legs: G_k, E_k = M_k^-1 C_k, G_S = chol(M_bb - sum_k C_k^T E_k)
+struct Factor { float g[6], gi[3], E[3][6], S[21], Si[6]; };
+__device__ __forceinline__ void factor_system(const float* Mk, const float (*C)[6], const float* Mbb, const float* dadd, Factor& F) {
+  float m[6] = {Mk[0] + dadd[0], Mk[1], Mk[2] + dadd[1], Mk[3], Mk[4], Mk[5] + dadd[2]};
+  chol3(m, F.g, F.gi);
+#pragma unroll
+  for (int c = 0; c < 6; c++) {
+    float b[3] = {C[0][c], C[1][c], C[2][c]}, y[3], x[3];
+    fwd3(F.g, F.gi, b, y);
+    bwd3(F.g, F.gi, y, x);
+    F.E[0][c] = x[0]; F.E[1][c] = x[1]; F.E[2][c] = x[2];
+  }
+#pragma unroll
+  for (int a = 0; a < 6; a++)
+#pragma unroll
+    for (int b = 0; b <= a; b++) {
+      float t = fmaf(C[0][a], F.E[0][b], fmaf(C[1][a], F.E[1][b], C[2][a] * F.E[2][b]));
+      F.S[TRI(a, b)] = Mbb[TRI(a, b)] - oct_sum(t);
+    }
+  chol6(F.S, F.Si);
+}
+// x = M^-1 [rb; rk]  (rb replicated across the octet, rk private)
+__device__ __forceinline__ void solve_system(const Factor& F, const float* rb, const float* rk, float* xb, float* xk) {
+  float y[3], yk[3];
+  fwd3(F.g, F.gi, rk, y);
+  bwd3(F.g, F.gi, y, yk);
+  float rt[6], t6[6];
+#pragma unroll
+  for (int a = 0; a < 6; a++) {
+    float t = fmaf(F.E[0][a], rk[0], fmaf(F.E[1][a], rk[1], F.E[2][a] * rk[2]));
+    rt[a] = rb[a] - oct_sum(t);
+  }
+  fwd6(F.S, F.Si, rt, t6);
+  bwd6(F.S, F.Si, t6, xb);
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    float t = yk[i];
+#pragma unroll
+    for (int a = 0; a < 6; a++) t = fmaf(-F.E[i][a], xb[a], t);
+    xk[i] = t;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- misc
+__device__ __forceinline__ float impedance(const NmGeom& g, float pos) {
+  if (g.dmin == g.dmax || g.width <= NM_MINVAL) return 0.5f * (g.dmin + g.dmax);
+  float x = fabsf(pos / g.width);
+  if (x >= 1.f) return g.dmax;
+  if (x <= 0.f) return g.dmin;
+  float y;
+  if (g.power == 1.f) y = x;
+  else if (g.power == 2.f) y = (x <= g.mid) ? x * x / g.mid : 1.f - (1.f - x) * (1.f - x) / (1.f - g.mid);
+  else y = (x <= g.mid) ? powf(x, g.power) / powf(g.mid, g.power - 1.f) : 1.f - powf(1.f - x, g.power) / powf(1.f - g.mid, g.power - 1.f);
+  return fmaf(y, g.dmax - g.dmin, g.dmin);
+}
+
+__device__ __forceinline__ float ray_sphere(V3 center, float radius, V3 pnt, V3 vec) {
+  V3 dif = pnt - center;
+  float a = dot(vec, vec), b = dot(vec, dif), c = dot(dif, dif) - radius * radius;
+  float det = b * b - a * c;
+  if (det < NM_MINVAL || a < NM_MINVAL) return -1.f;
+  det = sqrtf(det);
+  float x0 = (-b - det) / a, x1 = (-b + det) / a;
+  if (x0 >= 0.f) return x0;
+  if (x1 >= 0.f) return x1;
+  return -1.f;
+}
+
+__device__ __forceinline__ void philox4x32(unsigned k0, unsigned k1, unsigned c0, unsigned c1, unsigned c2, unsigned c3, unsigned* out) {
+#pragma unroll
+  for (int r = 0; r < 10; r++) {
+    unsigned hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    unsigned hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    unsigned n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+__device__ __forceinline__ float u01(unsigned x) { return (float)(x >> 8) * (1.0f / 16777216.0f); }
+
+// ≙ _resample_commands (env.py:321-333); RNG keyed by (seed, GLOBAL env id), counter (step, phase)
+__device__ __forceinline__ void resample_commands(const NmDevCfg& c, unsigned long long seed, long long genv, long long step, int phase, float* cmd) {
+  unsigned r[4];
+  philox4x32((unsigned)seed, (unsigned)genv, (unsigned)step, (unsigned)((unsigned long long)step >> 32), (unsigned)phase, (unsigned)(seed >> 32), r);
+  float cx = u01(r[0]) * 2.f * c.max_lin_vel_x - c.max_lin_vel_x;
+  float cy = 0.f;
+  float cw = u01(r[1]) * 2.f * c.max_ang_vel - c.max_ang_vel;
+  float keep = sqrtf(cx * cx + cy * cy) > 0.02f ? 1.f : 0.f;
+  cmd[0] = cx * keep; cmd[1] = cy * keep; cmd[2] = cw;
+}
+
+// per-lane contact rows (whitened), kept in local memory (L1-resident)
+struct ConRows {
+  float y[NM_MAXC][4][6];
+  float z[NM_MAXC][4][3];
+  float b[NM_MAXC][4], ad[NM_MAXC][4], adi[NM_MAXC][4], f[NM_MAXC][4];
+  float R[NM_MAXC];
+  V3 pos[NM_MAXC];
+};
+
+enum { RW_ACTION_RATE = 0, RW_ANG_VEL_XY, RW_BASE_HEIGHT, RW_BODY_CONTACT_FORCES, RW_COLLISION, RW_DEFAULT_POSITION,
+       RW_DOF_ACC, RW_DOF_VEL, RW_FEET_AIR_TIME, RW_FEET_CONTACT_FORCES, RW_FEET_STUMBLE, RW_LIN_VEL_Z, RW_ORIENTATION,
+       RW_STAND_STILL, RW_TERMINATION, RW_TORQUES, RW_TRACKING_ANG_VEL, RW_TRACKING_LIN_VEL };
+
+// ================================================================================================ the step kernel
+template <bool ENV>
+__global__ void __launch_bounds__(NM_BLOCK) nm_step_kernel(const NmKernelArgs A) {
+  __shared__ NmDevModel sm;
+  __shared__ NmDevCfg scfg;
+  {
+    const int* src = reinterpret_cast<const int*>(A.model);
+    int* dst = reinterpret_cast<int*>(&sm);
+    for (int i = threadIdx.x; i < (int)(sizeof(NmDevModel) / 4); i += blockDim.x) dst[i] = src[i];
+    if (ENV) {
+      const int* s2 = reinterpret_cast<const int*>(A.cfg);
+      int* d2 = reinterpret_cast<int*>(&scfg);
+      for (int i = threadIdx.x; i < (int)(sizeof(NmDevCfg) / 4); i += blockDim.x) d2[i] = s2[i];
+    }
+  }
+  __syncthreads();
+
+  const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int env_raw = gtid >> 3;
+  const bool valid = env_raw < A.num_envs;
+  const int env = valid ? env_raw : A.num_envs - 1;
+  const int l = threadIdx.x & 7;                 // lane inside the octet
+  const int lane = threadIdx.x & 31;
+  const int obase = lane & 24;                   // first warp lane of this octet
+  const NmLeg& L = sm.leg[l];
+  const NmGeom& G = L.geom;
+  const float isleg = L.isleg;
+  const bool leg = l < sm.nleg;
+  const float h = sm.timestep;
+
+  // ------------------------------------------------------------------ load state (registers for the whole step)
+  const float* qp = A.qpos + (size_t)env * 25;
+  const float* qv = A.qvel + (size_t)env * 24;
+  const float* qw = A.warm + (size_t)env * 24;
+  V3 p = ld3(qp);
+  float q0 = qp[3], q1 = qp[4], q2 = qp[5], q3 = qp[6];
+  V3 vlin = ld3(qv), wloc = ld3(qv + 3);
+  float awb[6], awk[3], th[3], thd[3], ctrl[3];
+#pragma unroll
+  for (int i = 0; i < 6; i++) awb[i] = qw[i];
+  const int jo = leg ? 3 * l : 0;
+#pragma unroll
+  for (int j = 0; j < 3; j++) {
+    th[j] = leg ? qp[7 + jo + j] : 0.f;
+    thd[j] = leg ? qv[6 + jo + j] : 0.f;
+    awk[j] = leg ? qw[6 + jo + j] : 0.f;
+  }
+
+  // ------------------------------------------------------------------ E1/E3: actions -> ctrl   (env.py:152-188)
+  float act[3] = {0.f, 0.f, 0.f}, prev_act[3] = {0.f, 0.f, 0.f}, prev_dof_vel[3] = {0.f, 0.f, 0.f};
+  if (ENV) {
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+      if (leg) {
+        prev_act[j] = A.actions[(size_t)env * 18 + jo + j];
+        float a = A.in_actions[(size_t)env * A.act_stride + jo + j] * scfg.action_scale;
+        act[j] = fminf(fmaxf(a, -scfg.clip_actions), scfg.clip_actions);
+        prev_dof_vel[j] = A.dof_vel[(size_t)env * 18 + jo + j];
+        float dpos = A.dof_pos[(size_t)env * 18 + jo + j];          // carried buffer, stale after a reset (quirk Q2)
+        ctrl[j] = ((act[j] - scfg.default_pos[jo + j]) - dpos) * scfg.p_gain;
+      } else ctrl[j] = 0.f;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 3; j++) ctrl[j] = leg ? A.in_ctrl[(size_t)env * 18 + jo + j] : 0.f;
+  }
+
+  // outputs of the LAST substep's forward pass that the env layer reads (stale by one substep, quirk Q4)
+  SV cvel_b; cvel_b.w = mk(0, 0, 0); cvel_b.v = mk(0, 0, 0);
+  float sens0 = 0.f, sens1 = 0.f, base_height = 0.f;
+  int bad = 0;
+  ConRows cr;
+
+#pragma unroll 1
+  for (int sub = 0; sub < A.nstep; sub++) {
+    // ================================================================ P1 kinematics
+    {
+      float n2 = q0 * q0 + q1 * q1 + q2 * q2 + q3 * q3;
+      if (n2 < NM_MINVAL) { q0 = 1.f; q1 = q2 = q3 = 0.f; }
+      else { float inv = rsqrtf(n2); q0 *= inv; q1 *= inv; q2 *= inv; q3 *= inv; }
+    }
+    const M3 Rb = quat2mat(q0, q1, q2, q3);
+    M3 X = Rb;
+    V3 pj = p;
+    V3 axw[3], anc[3], xip[3];
+    float Iw[3][6];
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+      pj = pj + mul(X, ld3(L.pos[j]));
+      M3 Rj = axis_rot(ld3(L.axis[j]), th[j] - L.qref[j]);
+      if (!L.rc_ident[j]) { M3 Rc;
+#pragma unroll
+        for (int k = 0; k < 9; k++) Rc.a[k] = L.rc[j][k];
+        Rj = matmul(Rc, Rj); }
+      X = matmul(X, Rj);
+      axw[j] = mul(X, ld3(L.axis[j]));
+      anc[j] = pj;
+      xip[j] = pj + mul(X, ld3(L.ipos[j]));
+      rot_inertia(X, L.iloc[j], Iw[j]);
+    }
+    const M3 Xg = X;          // frame of the lane's collision geom (tibia; base for the pseudo-legs)
+    const V3 pg = pj;
+    const V3 xip_b = p + mul(Rb, ld3(sm.b_ipos));
+    float Iwb[6];
+    rot_inertia(Rb, sm.b_iloc, Iwb);
+
+    // ================================================================ P2 comPos: subtree COM, c-frame inertias and dofs
+    V3 msum = fma3(L.mass[0], xip[0], fma3(L.mass[1], xip[1], L.mass[2] * xip[2]));
+    msum = oct_sum3(msum);
+    const V3 com = (1.f / sm.total_mass) * fma3(sm.b_mass, xip_b, msum);
+    In ci[3];
+    SV cd[3];
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+      ci[j] = make_inertia(Iw[j], L.mass[j], xip[j] - com);
+      cd[j].w = axw[j];
+      cd[j].v = cross(axw[j], com - anc[j]);
+    }
+    const In cib = make_inertia(Iwb, sm.b_mass, xip_b - com);
+    const V3 offb = com - p;
+    SV cdr[3];                 // base rotational dofs (body-frame axes); translational dofs are [0; e_i]
+#pragma unroll
+    for (int i = 0; i < 3; i++) { cdr[i].w = col(Rb, i); cdr[i].v = cross(cdr[i].w, offb); }
+
+    // ================================================================ P7 comVel + RNE bias forces
+    const V3 omega = mul(Rb, wloc);
+    SV cvb; cvb.w = omega; cvb.v = vlin + cross(omega, offb);
+    SV cab; cab.w = mk(0, 0, 0); cab.v = cross(vlin, omega) - ld3(sm.gravity);
+    float bias_k[3], bias_b[6];
+    {
+      SV fb = imul(cib, cab) + cross_force(cvb, imul(cib, cvb));
+      SV cv = cvb, ca = cab, f[3];
+#pragma unroll
+      for (int j = 0; j < 3; j++) {
+        SV cdd = cross_motion(cv, cd[j]);
+        ca = sfma(thd[j], cdd, ca);
+        cv = sfma(thd[j], cd[j], cv);
+        f[j] = imul(ci[j], ca) + cross_force(cv, imul(ci[j], cv));
+      }
+      f[1] = f[1] + f[2];
+      f[0] = f[0] + f[1];
+      bias_k[2] = sdot(cd[2], f[2]); bias_k[1] = sdot(cd[1], f[1]); bias_k[0] = sdot(cd[0], f[0]);
+      SV Fb;
+      Fb.w = fb.w + oct_sum3(f[0].w);
+      Fb.v = fb.v + oct_sum3(f[0].v);
+      bias_b[0] = Fb.v.x; bias_b[1] = Fb.v.y; bias_b[2] = Fb.v.z;
+#pragma unroll
+      for (int i = 0; i < 3; i++) bias_b[3 + i] = sdot(cdr[i], Fb);
+    }
+
+    // ================================================================ P3 CRBA in block form
+    float Mk[6], C[3][6], Mbb[21];
+    {
+      In crb2 = ci[2], crb1 = ci[1] + crb2, crb0 = ci[0] + crb1;
+      In s = crb0;
+      In cb;
+      cb.xx = cib.xx + oct_sum(s.xx); cb.yy = cib.yy + oct_sum(s.yy); cb.zz = cib.zz + oct_sum(s.zz);
+      cb.xy = cib.xy + oct_sum(s.xy); cb.xz = cib.xz + oct_sum(s.xz); cb.yz = cib.yz + oct_sum(s.yz);
+      cb.h = cib.h + oct_sum3(s.h); cb.m = cib.m + oct_sum(s.m);
+      SV b0 = imul(crb0, cd[0]), b1 = imul(crb1, cd[1]), b2 = imul(crb2, cd[2]);
+      Mk[0] = sdot(cd[0], b0) + L.armature[0];
+      Mk[1] = sdot(cd[0], b1); Mk[2] = sdot(cd[1], b1) + L.armature[1];
+      Mk[3] = sdot(cd[0], b2); Mk[4] = sdot(cd[1], b2); Mk[5] = sdot(cd[2], b2) + L.armature[2];
+      const SV bb[3] = {b0, b1, b2};
+#pragma unroll
+      for (int i = 0; i < 3; i++) {
+        C[i][0] = bb[i].v.x * isleg; C[i][1] = bb[i].v.y * isleg; C[i][2] = bb[i].v.z * isleg;
+#pragma unroll
+        for (int r = 0; r < 3; r++) C[i][3 + r] = sdot(cdr[r], bb[i]) * isleg;
+      }
+      // pseudo-legs carry no mass: make their private block the identity so the factorisation is well defined
+      Mk[0] = fmaf(Mk[0], isleg, 1.f - isleg); Mk[2] = fmaf(Mk[2], isleg, 1.f - isleg); Mk[5] = fmaf(Mk[5], isleg, 1.f - isleg);
+      Mk[1] *= isleg; Mk[3] *= isleg; Mk[4] *= isleg;
+#pragma unroll
+      for (int i = 0; i < 21; i++) Mbb[i] = 0.f;
+      Mbb[TRI(0, 0)] = cb.m; Mbb[TRI(1, 1)] = cb.m; Mbb[TRI(2, 2)] = cb.m;
+#pragma unroll
+      for (int r = 0; r < 3; r++) {
+        SV br = imul(cb, cdr[r]);
+        Mbb[TRI(3 + r, 0)] = br.v.x; Mbb[TRI(3 + r, 1)] = br.v.y; Mbb[TRI(3 + r, 2)] = br.v.z;
+#pragma unroll
+        for (int s2 = 0; s2 <= r; s2++) Mbb[TRI(3 + r, 3 + s2)] = sdot(cdr[s2], br);
+      }
+    }
+
+    // ================================================================ P8 actuation + smooth acceleration
+    float rk[3], rb[6], hD[3];
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+      float c = fminf(fmaxf(ctrl[j], L.clo[j]), L.chi[j]);
+      float g = L.gear[j];
+      float frc = fmaf(L.gain0[j], c, L.bias0[j]) + L.bias1[j] * (th[j] * g) + L.bias2[j] * (thd[j] * g);
+      frc = fminf(fmaxf(frc, L.flo[j]), L.fhi[j]);
+      rk[j] = (g * frc - L.damping[j] * thd[j] - bias_k[j]) * isleg;
+      hD[j] = h * (sm.imp_damp * L.damping[j] - sm.imp_act * L.bias2[j] * g * g) * isleg;   // -h * d(qfrc_smooth)/d(qvel), diagonal
+    }
+#pragma unroll
+    for (int i = 0; i < 6; i++) rb[i] = -bias_b[i];
+    Factor F, FH;
+    {
+      const float zero3[3] = {0.f, 0.f, 0.f};
+      factor_system(Mk, C, Mbb, zero3, F);
+      factor_system(Mk, C, Mbb, hD, FH);      // (M - h*qDeriv) for the implicit velocity update
+    }
+    float xsb[6], xsk[3];                      // qacc_smooth
+    solve_system(F, rb, rk, xsb, xsk);
+
+    // ================================================================ P4 collision: convex hull vs plane
+    const V3 pn = ld3(sm.plane_n);
+    int nc = 0;
+    float cdist[NM_MAXC];
+    int cvert[NM_MAXC];
+    if (G.has) {
+      const V3 dl = mulT(Xg, pn);                        // plane normal in the geom frame; minimise dl . v
+      const float4* hv = A.hull_vert + G.hull_adr;
+      const int* nadr = A.hull_nbr_adr + G.hull_adr;
+      int best = G.start;
+      float4 v4 = __ldg(hv + best);
+      float bval = fmaf(dl.x, v4.x, fmaf(dl.y, v4.y, dl.z * v4.z));
+      for (;;) {                                          // hill-climb on the hull graph (convex => global minimum)
+        int e0 = __ldg(nadr + best), e1 = __ldg(nadr + best + 1);
+        int nb = best;
+        for (int e = e0; e < e1; e++) {
+          int u = __ldg(A.hull_nbr + e);
+          float4 w4 = __ldg(hv + u);
+          float val = fmaf(dl.x, w4.x, fmaf(dl.y, w4.y, dl.z * w4.z));
+          if (val < bval) { bval = val; nb = u; }
+        }
+        if (nb == best) break;
+        best = nb;
+      }
+      v4 = __ldg(hv + best);
+      V3 wv = pg + mul(Xg, mk(v4.x, v4.y, v4.z));
+      float dist = dot(pn, wv) - sm.plane_d;
+      if (dist <= G.margin) {
+        cdist[0] = dist; cvert[0] = best; cr.pos[0] = fma3(-0.5f * dist, pn, wv); nc = 1;
+        const float thr2 = (0.3f * G.rbound) * (0.3f * G.rbound);
+        int e0 = __ldg(nadr + best), e1 = __ldg(nadr + best + 1);
+        for (int e = e0; e < e1 && nc < NM_MAXC; e++) {   // up to 3 more among the support vertex's neighbours
+          int u = __ldg(A.hull_nbr + e);
+          float4 w4 = __ldg(hv + u);
+          V3 wu = pg + mul(Xg, mk(w4.x, w4.y, w4.z));
+          float du = dot(pn, wu) - sm.plane_d;
+          if (du > G.margin) continue;
+          V3 cp = fma3(-0.5f * du, pn, wu);
+          bool close = false;
+          for (int k = 0; k < nc; k++) { V3 d3 = cr.pos[k] - cp; close |= dot(d3, d3) < thr2; }
+          if (close) continue;
+          cdist[nc] = du; cvert[nc] = u; cr.pos[nc] = cp; nc++;
+        }
+      }
+    }
+    const int ncon_env = oct_sumi(nc);
+    const bool any_contact = __any_sync(FULL, ncon_env > 0);
+
+    float xb[6], xk[3];          // constraint-induced acceleration M^-1 J^T f (after noslip)
+#pragma unroll
+    for (int i = 0; i < 6; i++) xb[i] = 0.f;
+#pragma unroll
+    for (int i = 0; i < 3; i++) xk[i] = 0.f;
+    float wsb[6], wsk[3];        // qacc to store as next warm start (after PGS, before noslip)
+#pragma unroll
+    for (int i = 0; i < 6; i++) wsb[i] = xsb[i];
+#pragma unroll
+    for (int i = 0; i < 3; i++) wsk[i] = xsk[i];
+    float fn_slot0 = 0.f, fn_slot1 = 0.f;
+    int dbg_pgs = 0, dbg_noslip = 0, dbg_warm = 0;
+
+    if (any_contact) {
+      // ============================================================== P5 contact rows, whitened
+      const V3 fr0 = ld3(sm.frame), fr1 = ld3(sm.frame + 3), fr2 = ld3(sm.frame + 6);
+      for (int c = 0; c < nc; c++) {
+        const V3 r = cr.pos[c] - com;
+        V3 colb[6], colk[3];
+        colb[0] = mk(1, 0, 0); colb[1] = mk(0, 1, 0); colb[2] = mk(0, 0, 1);
+#pragma unroll
+        for (int i = 0; i < 3; i++) colb[3 + i] = cdr[i].v + cross(cdr[i].w, r);
+#pragma unroll
+        for (int j = 0; j < 3; j++) colk[j] = isleg * (cd[j].v + cross(cd[j].w, r));
+        float Y[3][6], Z[3][3], vb[3], as[3], aw[3];
+        const V3 frm[3] = {fr0, fr1, fr2};
+#pragma unroll
+        for (int f = 0; f < 3; f++) {
+          float Jb[6], Jk[3], Jt[6];
+#pragma unroll
+          for (int a = 0; a < 6; a++) Jb[a] = dot(frm[f], colb[a]);
+#pragma unroll
+          for (int j = 0; j < 3; j++) Jk[j] = dot(frm[f], colk[j]);
+#pragma unroll
+          for (int a = 0; a < 6; a++) Jt[a] = Jb[a] - fmaf(Jk[0], F.E[0][a], fmaf(Jk[1], F.E[1][a], Jk[2] * F.E[2][a]));
+          fwd6(F.S, F.Si, Jt, Y[f]);
+          fwd3(F.g, F.gi, Jk, Z[f]);
+          vb[f] = Jb[0] * vlin.x + Jb[1] * vlin.y + Jb[2] * vlin.z + Jb[3] * wloc.x + Jb[4] * wloc.y + Jb[5] * wloc.z +
+                  Jk[0] * thd[0] + Jk[1] * thd[1] + Jk[2] * thd[2];
+          float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+          for (int a = 0; a < 6; a++) { s1 = fmaf(Jb[a], xsb[a], s1); s2 = fmaf(Jb[a], awb[a], s2); }
+#pragma unroll
+          for (int j = 0; j < 3; j++) { s1 = fmaf(Jk[j], xsk[j], s1); s2 = fmaf(Jk[j], awk[j], s2); }
+          as[f] = s1; aw[f] = s2;
+        }
+        const float pos = cdist[c] - G.margin;
+        const float imp = impedance(G, pos);
+        const float R = fmaxf(G.rfac * (1.f - imp) / imp, NM_MINVAL);
+        cr.R[c] = R;
+        const float kd = G.K * imp * pos;
+#pragma unroll
+        for (int rr = 0; rr < 4; rr++) {
+          const int t = 1 + (rr >> 1);
+          const float sm_ = (rr & 1) ? -G.mu : G.mu;
+          float ad = R;
+#pragma unroll
+          for (int a = 0; a < 6; a++) { float y = fmaf(sm_, Y[t][a], Y[0][a]); cr.y[c][rr][a] = y; ad = fmaf(y, y, ad); }
+#pragma unroll
+          for (int j = 0; j < 3; j++) { float z = fmaf(sm_, Z[t][j], Z[0][j]); cr.z[c][rr][j] = z; ad = fmaf(z, z, ad); }
+          cr.ad[c][rr] = ad;
+          cr.adi[c][rr] = 1.f / ad;
+          const float aref = -G.B * fmaf(sm_, vb[t], vb[0]) - kd;
+          cr.b[c][rr] = fmaf(sm_, as[t], as[0]) - aref;
+          const float jar = fmaf(sm_, aw[t], aw[0]) - aref;       // warm start: forces implied by qacc_warmstart
+          cr.f[c][rr] = jar < 0.f ? -jar / R : 0.f;
+        }
+      }
+
+      // ============================================================== P9 warm start, PGS, noslip
+      float u[6], wv[3];
+#pragma unroll
+      for (int a = 0; a < 6; a++) u[a] = 0.f;
+#pragma unroll
+      for (int j = 0; j < 3; j++) wv[j] = 0.f;
+      float cl = 0.f;
+      for (int c = 0; c < nc; c++)
+#pragma unroll
+        for (int rr = 0; rr < 4; rr++) {
+          float f = cr.f[c][rr];
+#pragma unroll
+          for (int a = 0; a < 6; a++) u[a] = fmaf(cr.y[c][rr][a], f, u[a]);
+#pragma unroll
+          for (int j = 0; j < 3; j++) wv[j] = fmaf(cr.z[c][rr][j], f, wv[j]);
+          cl += f * fmaf(0.5f * cr.R[c], f, cr.b[c][rr]);
+        }
+      float uu = 0.f;
+#pragma unroll
+      for (int a = 0; a < 6; a++) { u[a] = oct_sum(u[a]); uu = fmaf(u[a], u[a], uu); }
+      cl += 0.5f * (wv[0] * wv[0] + wv[1] * wv[1] + wv[2] * wv[2]);
+      const float cost = fmaf(0.5f, uu, oct_sum(cl));
+      if (cost > 0.f) {        // f = 0 is cheaper than the warm start
+        for (int c = 0; c < nc; c++)
+#pragma unroll
+          for (int rr = 0; rr < 4; rr++) cr.f[c][rr] = 0.f;
+#pragma unroll
+        for (int a = 0; a < 6; a++) u[a] = 0.f;
+#pragma unroll
+        for (int j = 0; j < 3; j++) wv[j] = 0.f;
+      } else dbg_warm = ncon_env > 0 ? 1 : 0;
+
+      // ---- PGS sweeps: rows in contact order (base geom first, then legs 1..6), Gauss-Seidel through u
+      bool active = ncon_env > 0;
+      for (int it = 0; it < sm.iterations; it++) {
+        if (!__any_sync(FULL, active)) break;
+        float improvement = 0.f;
+#pragma unroll 1
+        for (int ph = 0; ph < 7; ph++) {
+          const int owner = ph == 0 ? 6 : ph - 1;
+          const bool mine = active && (l == owner) && nc > 0;
+          if (!__any_sync(FULL, mine)) continue;
+          if (mine) {
+            for (int c = 0; c < nc; c++)
+#pragma unroll
+              for (int rr = 0; rr < 4; rr++) {
+                float res = cr.b[c][rr];
+#pragma unroll
+                for (int a = 0; a < 6; a++) res = fmaf(cr.y[c][rr][a], u[a], res);
+#pragma unroll
+                for (int j = 0; j < 3; j++) res = fmaf(cr.z[c][rr][j], wv[j], res);
+                const float old = cr.f[c][rr];
+                res = fmaf(cr.R[c], old, res);
+                float fnew = fmaxf(0.f, fmaf(-res, cr.adi[c][rr], old));
+                float delta = fnew - old;
+                float change = delta * fmaf(0.5f * delta, cr.ad[c][rr], res);
+                if (change > 1e-10f) { delta = 0.f; fnew = old; change = 0.f; }
+                improvement -= change;
+                cr.f[c][rr] = fnew;
+#pragma unroll
+                for (int a = 0; a < 6; a++) u[a] = fmaf(cr.y[c][rr][a], delta, u[a]);
+#pragma unroll
+                for (int j = 0; j < 3; j++) wv[j] = fmaf(cr.z[c][rr][j], delta, wv[j]);
+              }
+          }
+#pragma unroll
+          for (int a = 0; a < 6; a++) u[a] = oct_bcast(u[a], obase | owner);
+        }
+        improvement = oct_sum(improvement);
+        if (active) dbg_pgs++;
+        if (improvement * sm.solver_scale < sm.tolerance) active = false;
+      }
+      // qacc after PGS -> next step's warm start (saved BEFORE noslip)
+      {
+        float tb[6], tk[3];
+        bwd6(F.S, F.Si, u, tb);
+        float y3[3];
+        bwd3(F.g, F.gi, wv, y3);
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+          float t = y3[i];
+#pragma unroll
+          for (int a = 0; a < 6; a++) t = fmaf(-F.E[i][a], tb[a], t);
+          tk[i] = t;
+        }
+        if (ncon_env > 0) {
+#pragma unroll
+          for (int i = 0; i < 6; i++) wsb[i] = xsb[i] + tb[i];
+#pragma unroll
+          for (int i = 0; i < 3; i++) wsk[i] = xsk[i] + tk[i];
+        }
+      }
+      // ---- noslip: opposing pyramid edges re-solved without R, their sum kept fixed
+      active = ncon_env > 0;
+      for (int it = 0; it < sm.noslip_iterations; it++) {
+        if (!__any_sync(FULL, active)) break;
+        float improvement = 0.f;
+#pragma unroll 1
+        for (int ph = 0; ph < 7; ph++) {
+          const int owner = ph == 0 ? 6 : ph - 1;
+          const bool mine = active && (l == owner) && nc > 0;
+          if (!__any_sync(FULL, mine)) continue;
+          if (mine) {
+            for (int c = 0; c < nc; c++)
+#pragma unroll
+              for (int pr = 0; pr < 4; pr += 2) {
+                float res0 = cr.b[c][pr], res1 = cr.b[c][pr + 1], a00 = 0.f, a11 = 0.f, a01 = 0.f;
+#pragma unroll
+                for (int a = 0; a < 6; a++) {
+                  float y0 = cr.y[c][pr][a], y1 = cr.y[c][pr + 1][a];
+                  res0 = fmaf(y0, u[a], res0); res1 = fmaf(y1, u[a], res1);
+                  a00 = fmaf(y0, y0, a00); a11 = fmaf(y1, y1, a11); a01 = fmaf(y0, y1, a01);
+                }
+#pragma unroll
+                for (int j = 0; j < 3; j++) {
+                  float z0 = cr.z[c][pr][j], z1 = cr.z[c][pr + 1][j];
+                  res0 = fmaf(z0, wv[j], res0); res1 = fmaf(z1, wv[j], res1);
+                  a00 = fmaf(z0, z0, a00); a11 = fmaf(z1, z1, a11); a01 = fmaf(z0, z1, a01);
+                }
+                const float o0 = cr.f[c][pr], o1 = cr.f[c][pr + 1];
+                const float bc0 = res0 - a00 * o0 - a01 * o1, bc1 = res1 - a01 * o0 - a11 * o1;
+                const float mid = 0.5f * (o0 + o1);
+                const float K1 = a00 + a11 - 2.f * a01;
+                const float K0 = mid * (a00 - a11) + bc0 - bc1;
+                float f0, f1;
+                if (K1 < NM_MINVAL) { f0 = mid; f1 = mid; }
+                else {
+                  float x = -K0 / K1;
+                  if (x < -mid) { f0 = 0.f; f1 = 2.f * mid; }
+                  else if (x > mid) { f0 = 2.f * mid; f1 = 0.f; }
+                  else { f0 = mid + x; f1 = mid - x; }
+                }
+                float d0 = f0 - o0, d1 = f1 - o1;
+                float change = 0.5f * (d0 * (a00 * d0 + a01 * d1) + d1 * (a01 * d0 + a11 * d1)) + d0 * res0 + d1 * res1;
+                if (change > 1e-10f) { f0 = o0; f1 = o1; d0 = 0.f; d1 = 0.f; change = 0.f; }
+                improvement -= change;
+                cr.f[c][pr] = f0; cr.f[c][pr + 1] = f1;
+#pragma unroll
+                for (int a = 0; a < 6; a++) u[a] = fmaf(cr.y[c][pr][a], d0, fmaf(cr.y[c][pr + 1][a], d1, u[a]));
+#pragma unroll
+                for (int j = 0; j < 3; j++) wv[j] = fmaf(cr.z[c][pr][j], d0, fmaf(cr.z[c][pr + 1][j], d1, wv[j]));
+              }
+          }
+#pragma unroll
+          for (int a = 0; a < 6; a++) u[a] = oct_bcast(u[a], obase | owner);
+        }
+        improvement = oct_sum(improvement);
+        if (active) dbg_noslip++;
+        if (improvement * sm.solver_scale < sm.noslip_tolerance) active = false;
+      }
+      // final constraint acceleration x = M^-1 J^T f
+      {
+        bwd6(F.S, F.Si, u, xb);
+        float y3[3];
+        bwd3(F.g, F.gi, wv, y3);
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+          float t = y3[i];
+#pragma unroll
+          for (int a = 0; a < 6; a++) t = fmaf(-F.E[i][a], xb[a], t);
+          xk[i] = t;
+        }
+        if (ncon_env == 0) {
+#pragma unroll
+          for (int i = 0; i < 6; i++) xb[i] = 0.f;
+#pragma unroll
+          for (int i = 0; i < 3; i++) xk[i] = 0.f;
+        }
+      }
+      // ============================================================== P10 touch sensors (sum of pyramid-edge forces)
+      for (int c = 0; c < nc; c++) {
+        float fn = cr.f[c][0] + cr.f[c][1] + cr.f[c][2] + cr.f[c][3];
+        if (fn <= 0.f) continue;
+        const V3 ray = mk(-pn.x, -pn.y, -pn.z);          // normal points plane -> body; sensor is on the body
+        if (L.site_r[0] >= 0.f && ray_sphere(pg + mul(Xg, ld3(L.site_pos[0])), L.site_r[0], cr.pos[c], ray) >= 0.f) fn_slot0 += fn;
+        if (L.site_r[1] >= 0.f && ray_sphere(pg + mul(Xg, ld3(L.site_pos[1])), L.site_r[1], cr.pos[c], ray) >= 0.f) fn_slot1 += fn;
+      }
+    }
+    sens0 = fn_slot0; sens1 = fn_slot1;
+    cvel_b = cvb;
+    base_height = xip_b.z;
+
+    // ================================================================ optional debug record (parity harness)
+    if (A.debug != nullptr && valid && sub == A.nstep - 1) {
+      float* dbg = A.debug + (size_t)env * 160;
+      if (l == 0) {
+        dbg[0] = (float)ncon_env; dbg[1] = (float)dbg_pgs; dbg[2] = (float)dbg_noslip; dbg[3] = (float)dbg_warm;
+#pragma unroll
+        for (int i = 0; i < 6; i++) { dbg[96 + i] = xsb[i]; dbg[128 + i] = xsb[i] + xb[i]; }
+      }
+      if (l < 7) {
+        float* g = dbg + 8 + l * 12;
+        g[0] = (float)nc;
+        for (int c = 0; c < NM_MAXC; c++) { g[1 + 2 * c] = c < nc ? (float)cvert[c] : -1.f; g[2 + 2 * c] = c < nc ? cdist[c] : 0.f; }
+      }
+      if (leg) {
+#pragma unroll
+        for (int j = 0; j < 3; j++) { dbg[102 + jo + j] = xsk[j]; dbg[134 + jo + j] = xsk[j] + xk[j]; }
+      }
+    }
+
+    // ================================================================ P11 implicitfast velocity update + position integration
+    {
+      // (M + hD) qdd = M qacc  =>  qdd = qacc - (M + hD)^-1 [0; hD qacc_k]
+      float qab[6], qak[3], zb[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, rkk[3], cb6[6], ck3[3];
+#pragma unroll
+      for (int i = 0; i < 6; i++) qab[i] = xsb[i] + xb[i];
+#pragma unroll
+      for (int j = 0; j < 3; j++) { qak[j] = xsk[j] + xk[j]; rkk[j] = hD[j] * qak[j]; }
+      solve_system(FH, zb, rkk, cb6, ck3);
+#pragma unroll
+      for (int i = 0; i < 6; i++) qab[i] -= cb6[i];
+#pragma unroll
+      for (int j = 0; j < 3; j++) qak[j] -= ck3[j];
+      vlin = fma3(h, mk(qab[0], qab[1], qab[2]), vlin);
+      wloc = fma3(h, mk(qab[3], qab[4], qab[5]), wloc);
+#pragma unroll
+      for (int j = 0; j < 3; j++) { thd[j] = fmaf(h, qak[j], thd[j]); th[j] = fmaf(h, thd[j], th[j]); }
+      p = fma3(h, vlin, p);
+      // quaternion integration with the body-frame angular velocity
+      float wn = sqrtf(dot(wloc, wloc));
+      if (wn >= NM_MINVAL) {
+        float s, c;
+        sincosf(0.5f * h * wn, &s, &c);
+        float k = s / wn;
+        float rx = wloc.x * k, ry = wloc.y * k, rz = wloc.z * k;
+        float nw = q0 * c - q1 * rx - q2 * ry - q3 * rz;
+        float nx = q0 * rx + q1 * c + q2 * rz - q3 * ry;
+        float ny = q0 * ry - q1 * rz + q2 * c + q3 * rx;
+        float nz = q0 * rz + q1 * ry - q2 * rx + q3 * c;
+        q0 = nw; q1 = nx; q2 = ny; q3 = nz;
+      }
+#pragma unroll
+      for (int i = 0; i < 6; i++) awb[i] = wsb[i];
+#pragma unroll
+      for (int j = 0; j < 3; j++) awk[j] = wsk[j];
+    }
+    // divergence guard (≙ mj_checkPos / mj_checkVel auto-reset): non-finite or huge state resets the env
+    {
+      float mx = fmaxf(fmaxf(fabsf(p.x), fabsf(p.y)), fabsf(p.z));
+      mx = fmaxf(mx, fmaxf(fmaxf(fabsf(vlin.x), fabsf(vlin.y)), fabsf(vlin.z)));
+      mx = fmaxf(mx, fmaxf(fmaxf(fabsf(wloc.x), fabsf(wloc.y)), fabsf(wloc.z)));
+#pragma unroll
+      for (int j = 0; j < 3; j++) mx = fmaxf(mx, fmaxf(fabsf(th[j]), fabsf(thd[j])));
+      int b = !(mx < 1e10f);                                  // catches NaN too
+      b = oct_sumi(b);
+      if (b) {
+        bad = 1;
+        p = ld3(sm.qpos0); q0 = sm.qpos0[3]; q1 = sm.qpos0[4]; q2 = sm.qpos0[5]; q3 = sm.qpos0[6];
+        vlin = mk(0, 0, 0); wloc = mk(0, 0, 0);
+#pragma unroll
+        for (int j = 0; j < 3; j++) { th[j] = leg ? sm.qpos0[7 + jo + j] : 0.f; thd[j] = 0.f; awk[j] = 0.f; }
+#pragma unroll
+        for (int i = 0; i < 6; i++) awb[i] = 0.f;
+      }
+    }
+  }  // substeps
+
+  // ==================================================================== physics-only mode: write state and leave
+  if (!ENV) {
+    if (valid) {
+      float* qpo = A.qpos + (size_t)env * 25;
+      float* qvo = A.qvel + (size_t)env * 24;
+      float* qwo = A.warm + (size_t)env * 24;
+      if (l == 7) {
+        qpo[0] = p.x; qpo[1] = p.y; qpo[2] = p.z; qpo[3] = q0; qpo[4] = q1; qpo[5] = q2; qpo[6] = q3;
+        qvo[0] = vlin.x; qvo[1] = vlin.y; qvo[2] = vlin.z; qvo[3] = wloc.x; qvo[4] = wloc.y; qvo[5] = wloc.z;
+#pragma unroll
+        for (int i = 0; i < 6; i++) qwo[i] = awb[i];
+      }
+      if (leg) {
+#pragma unroll
+        for (int j = 0; j < 3; j++) { qpo[7 + jo + j] = th[j]; qvo[6 + jo + j] = thd[j]; qwo[6 + jo + j] = awk[j]; }
+        A.sensordata[(size_t)env * 13 + l] = sens0;
+        A.sensordata[(size_t)env * 13 + 6 + l] = sens1;
+      }
+      if (l == 6) A.sensordata[(size_t)env * 13 + 12] = sens0;
+    }
+    return;
+  }
+
+  // ==================================================================== env epilogue (env.py:212-309)
+  const NmDevCfg& c = scfg;
+  long long ep_len = A.episode_length[env] + 1;                              // E6
+  // E7: base-frame velocities / gravity with the POST-integration quaternion, cvel from the last forward pass
+  M3 Rq;
+  {
+    float n2 = q0 * q0 + q1 * q1 + q2 * q2 + q3 * q3;   // conj(q) rotates world -> body; mju_rotVecQuat does not normalise
+    (void)n2;
+    Rq = quat2mat(q0, q1, q2, q3);
+  }
+  const V3 blin = mulT(Rq, cvel_b.v), bang = mulT(Rq, cvel_b.w), pgrav = mulT(Rq, mk(0.f, 0.f, -9.81f));
+  // E8/E9 per-leg buffers
+  float dacc2 = 0.f, arate2 = 0.f, dpos2 = 0.f, dvel2 = 0.f, dposabs = 0.f;
+  float tib = 0.f, foot = 0.f, bodyf = 0.f;
+  if (leg) {
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+      float da = (thd[j] - prev_dof_vel[j]) * c.inv_dt;
+      dacc2 = fmaf(da, da, dacc2);
+      float ar = prev_act[j] - act[j];
+      arate2 = fmaf(ar, ar, arate2);
+      float dp = th[j] - c.default_pos[jo + j];
+      dpos2 = fmaf(dp, dp, dpos2);
+      dposabs += fabsf(dp);
+      dvel2 = fmaf(thd[j], thd[j], dvel2);
+    }
+    foot = sens1;
+    tib = (foot == 0.f) ? sens0 : 0.f;                                         // env.py:232
+  }
+  if (l == 6) bodyf = sens0;
+  const float tib_sum = oct_sum(tib), tib_max = oct_max(leg ? tib : -CUDART_INF_F);
+  const float foot_max = oct_max(leg ? foot : -CUDART_INF_F);
+  const float body_f = oct_sum(bodyf);
+  dacc2 = oct_sum(dacc2); arate2 = oct_sum(arate2); dpos2 = oct_sum(dpos2); dvel2 = oct_sum(dvel2); dposabs = oct_sum(dposabs);
+  float fcf = 0.f;
+  if (leg && foot > c.max_contact_force) { float x = foot - c.max_contact_force; fcf = x * x; }
+  fcf = oct_sum(fcf);
+
+  // E10 command resampling
+  float cmd[3] = {A.commands[(size_t)env * 3], A.commands[(size_t)env * 3 + 1], A.commands[(size_t)env * 3 + 2]};
+  const long long genv = A.env_offset + env;
+  if (c.resample_period > 0 && ep_len % c.resample_period == 0) resample_commands(c, A.seed, genv, A.step_counter, 0, cmd);
+  // E11 termination
+  const bool time_out = (float)ep_len > c.max_episode_length;
+  bool reset = time_out | (foot_max > c.term_force) | (bad != 0);
+  if (c.tibia_mode == 2) reset |= tib_max > c.tibia_max_force;
+  if (c.body_mode == 2) reset |= body_f > c.body_max_force;
+  {
+    float nrm = sqrtf(dot(pgrav, pgrav));
+    reset |= (-pgrav.z) < 0.5f * nrm;                                          // acos(-pg_z/|pg|) > 60 deg
+  }
+  // E13 reset
+  float esum[18];
+  const bool w7 = valid && l == 7;
+  if (reset) {
+    resample_commands(c, A.seed, genv, A.step_counter, 1, cmd);
+    ep_len = 0;
+  }
+  // E14 rewards (alphabetical accumulation, termination last)
+  float fat_term = 0.f;
+  if (c.rew_scale[RW_FEET_AIR_TIME] != 0.f) {                                   // stateful term (env.py:447-477)
+    int bits = A.contact_bits[env];
+    float t = 0.f;
+    int nb_last = 0, nb_filt = 0;
+    if (leg) {
+      float air = reset ? 0.f : A.feet_air_time[(size_t)env * 6 + l];
+      int last = (bits >> l) & 1, lastf = (bits >> (8 + l)) & 1;
+      int contact = foot > 1.0f, filt = contact | last;
+      air += c.dt;
+      air = (filt == lastf) ? air : 0.f;
+      float r = (air > 1.f ? air - 1.f : 0.f) + (air < 0.5f ? 0.5f - air : 0.f);
+      t = r * r;
+      nb_last = contact << l; nb_filt = filt << (8 + l);
+      if (valid) A.feet_air_time[(size_t)env * 6 + l] = air;
+    }
+    fat_term = oct_sum(t);
+    int nbits = oct_sumi(nb_last | nb_filt);
+    if (w7) A.contact_bits[env] = nbits;
+  } else if (reset && leg && valid) A.feet_air_time[(size_t)env * 6 + l] = 0.f;
+
+  float total = 0.f;
+  {
+    float term[18];
+    term[RW_ACTION_RATE] = arate2;
+    term[RW_ANG_VEL_XY] = bang.x * bang.x + bang.y * bang.y;
+    { float x = base_height - c.base_height_target; term[RW_BASE_HEIGHT] = x * x; }
+    term[RW_BODY_CONTACT_FORCES] = (c.tibia_mode == 1 ? tib_sum : 0.f) + (c.body_mode == 1 ? body_f : 0.f);
+    term[RW_COLLISION] = 0.f;
+    term[RW_DEFAULT_POSITION] = dpos2;
+    term[RW_DOF_ACC] = dacc2;
+    term[RW_DOF_VEL] = dvel2;
+    term[RW_FEET_AIR_TIME] = fat_term;
+    term[RW_FEET_CONTACT_FORCES] = fcf;
+    term[RW_FEET_STUMBLE] = 0.f;
+    term[RW_LIN_VEL_Z] = blin.z * blin.z;
+    term[RW_ORIENTATION] = pgrav.x * pgrav.x + pgrav.y * pgrav.y;
+    term[RW_STAND_STILL] = dposabs * (sqrtf(cmd[0] * cmd[0] + cmd[1] * cmd[1]) < 0.01f ? 1.f : 0.f);
+    term[RW_TERMINATION] = 0.f;
+    term[RW_TORQUES] = 0.f;
+    { float x = cmd[2] - bang.z; term[RW_TRACKING_ANG_VEL] = expf(-x * x * c.inv_tracking_sigma); }
+    { float x = cmd[0] - blin.x, y = cmd[1] - blin.y; term[RW_TRACKING_LIN_VEL] = expf(-(x * x + y * y) * c.inv_tracking_sigma); }
+#pragma unroll
+    for (int k = 0; k < 18; k++) {
+      float prev = reset ? 0.f : A.episode_sums[(size_t)env * 18 + k];
+      float r = 0.f;
+      if (k != RW_TERMINATION && c.rew_scale[k] != 0.f) { r = term[k] * c.rew_scale[k]; total += r; }
+      esum[k] = prev + r;
+    }
+    if (c.rew_scale[RW_TERMINATION] != 0.f) {
+      float r = ((reset && !time_out) ? 1.f : 0.f) * c.rew_scale[RW_TERMINATION];
+      total += r;
+      esum[RW_TERMINATION] += r;
+    }
+  }
+  // episode statistics of envs that reset this step (sums BEFORE this step's rewards, env.py:363-367)
+  if (w7 && reset) {
+#pragma unroll
+    for (int k = 0; k < 18; k++) {
+      float s = A.episode_sums[(size_t)env * 18 + k];
+      if (c.rew_scale[k] != 0.f) atomicAdd(A.episode_acc + k, s);
+    }
+    atomicAdd(A.episode_acc + 18, 1.f);
+  }
+
+  // ------------------------------------------------------------------ write back
+  if (valid) {
+    float* qpo = A.qpos + (size_t)env * 25;
+    float* qvo = A.qvel + (size_t)env * 24;
+    float* qwo = A.warm + (size_t)env * 24;
+    float* ob = A.obs + (size_t)env * 66;
+    const float co = c.clip_obs;
+    unsigned nz[4];
+    if (leg) {
+#pragma unroll
+      for (int j = 0; j < 3; j++) {
+        qpo[7 + jo + j] = reset ? sm.qpos0[7 + jo + j] : th[j];
+        qvo[6 + jo + j] = reset ? 0.f : thd[j];
+        qwo[6 + jo + j] = awk[j];                                               // warm start survives resets (quirk Q3)
+        A.actions[(size_t)env * 18 + jo + j] = act[j];
+        A.dof_pos[(size_t)env * 18 + jo + j] = th[j];                           // terminal pose stays in the buffer (quirk Q2)
+        A.dof_vel[(size_t)env * 18 + jo + j] = thd[j];
+        float o0 = (th[j] - c.default_pos[jo + j]) * c.obs_dof_pos, o1 = thd[j] * c.obs_dof_vel, o2 = act[j];
+        if (c.add_noise) {
+          int k0 = 12 + jo + j, k1 = 30 + jo + j, k2 = 48 + jo + j;
+          philox4x32((unsigned)A.seed, (unsigned)genv, (unsigned)A.step_counter, (unsigned)((unsigned long long)A.step_counter >> 32), 2 + (k0 >> 2), (unsigned)(A.seed >> 32), nz);
+          o0 = fmaf(2.f * u01(nz[k0 & 3]) - 1.f, c.noise_vec[k0], o0);
+          philox4x32((unsigned)A.seed, (unsigned)genv, (unsigned)A.step_counter, (unsigned)((unsigned long long)A.step_counter >> 32), 2 + (k1 >> 2), (unsigned)(A.seed >> 32), nz);
+          o1 = fmaf(2.f * u01(nz[k1 & 3]) - 1.f, c.noise_vec[k1], o1);
+          philox4x32((unsigned)A.seed, (unsigned)genv, (unsigned)A.step_counter, (unsigned)((unsigned long long)A.step_counter >> 32), 2 + (k2 >> 2), (unsigned)(A.seed >> 32), nz);
+          o2 = fmaf(2.f * u01(nz[k2 & 3]) - 1.f, c.noise_vec[k2], o2);
+        }
+        ob[12 + jo + j] = fminf(fmaxf(o0, -co), co);
+        ob[30 + jo + j] = fminf(fmaxf(o1, -co), co);
+        ob[48 + jo + j] = fminf(fmaxf(o2, -co), co);
+      }
+      A.sensordata[(size_t)env * 13 + l] = sens0;
+      A.sensordata[(size_t)env * 13 + 6 + l] = sens1;
+    }
+    if (l == 6) {
+      A.sensordata[(size_t)env * 13 + 12] = sens0;
+      float o[12] = {blin.x * c.obs_lin_vel, blin.y * c.obs_lin_vel, blin.z * c.obs_lin_vel, bang.x * c.obs_ang_vel, bang.y * c.obs_ang_vel,
+                     bang.z * c.obs_ang_vel, pgrav.x, pgrav.y, pgrav.z, cmd[0] * c.obs_lin_vel, cmd[1] * c.obs_lin_vel, cmd[2] * c.obs_ang_vel};
+#pragma unroll
+      for (int k = 0; k < 12; k++) {
+        float v = o[k];
+        if (c.add_noise) {
+          philox4x32((unsigned)A.seed, (unsigned)genv, (unsigned)A.step_counter, (unsigned)((unsigned long long)A.step_counter >> 32), 2 + (k >> 2), (unsigned)(A.seed >> 32), nz);
+          v = fmaf(2.f * u01(nz[k & 3]) - 1.f, c.noise_vec[k], v);
+        }
+        ob[k] = fminf(fmaxf(v, -co), co);
+      }
+    }
+    if (l == 7) {
+      if (reset) {
+#pragma unroll
+        for (int i = 0; i < 7; i++) qpo[i] = sm.qpos0[i];
+#pragma unroll
+        for (int i = 0; i < 6; i++) qvo[i] = 0.f;
+      } else {
+        qpo[0] = p.x; qpo[1] = p.y; qpo[2] = p.z; qpo[3] = q0; qpo[4] = q1; qpo[5] = q2; qpo[6] = q3;
+        qvo[0] = vlin.x; qvo[1] = vlin.y; qvo[2] = vlin.z; qvo[3] = wloc.x; qvo[4] = wloc.y; qvo[5] = wloc.z;
+      }
+#pragma unroll
+      for (int i = 0; i < 6; i++) qwo[i] = awb[i];
+      A.commands[(size_t)env * 3] = cmd[0]; A.commands[(size_t)env * 3 + 1] = cmd[1]; A.commands[(size_t)env * 3 + 2] = cmd[2];
+      A.episode_length[env] = ep_len;
+#pragma unroll
+      for (int k = 0; k < 18; k++) A.episode_sums[(size_t)env * 18 + k] = esum[k];
+      A.rew[env] = total;
+      A.done[env] = reset ? 1 : 0;
+      A.time_outs[env] = time_out ? 1.f : 0.f;
+    }
+  }
+}
+
+// ================================================================================================ reset_idx kernel
+// ≙ reset_idx (env.py:335-361) for an explicit id list: qpos<-qpos0, qvel<-0, commands resampled (phase 1),
+// feet_air_time/episode_length/episode_sums zeroed, reset_buf<-1.  One thread per listed env.
+__global__ void nm_reset_kernel(const NmKernelArgs A, const long long* ids, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  long long e = ids[i];
+  if (e < 0 || e >= A.num_envs) return;
+  const NmDevModel& m = *A.model;
+  for (int k = 0; k < 25; k++) A.qpos[e * 25 + k] = m.qpos0[k];
+  for (int k = 0; k < 24; k++) A.qvel[e * 24 + k] = 0.f;
+  float cmd[3];
+  resample_commands(*A.cfg, A.seed, A.env_offset + e, A.step_counter, 1, cmd);
+  for (int k = 0; k < 3; k++) A.commands[e * 3 + k] = cmd[k];
+  for (int k = 0; k < 6; k++) A.feet_air_time[e * 6 + k] = 0.f;
+  for (int k = 0; k < 18; k++) A.episode_sums[e * 18 + k] = 0.f;
+  A.episode_length[e] = 0;
+  A.done[e] = 1;
+}
+
+void nm_launch_step(const NmKernelArgs& a, bool env_mode, void* stream) {
+  const int threads = a.num_envs * NM_OCT;
+  const int blocks = (threads + NM_BLOCK - 1) / NM_BLOCK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (env_mode) nm_step_kernel<true><<<blocks, NM_BLOCK, 0, st>>>(a);
+  else nm_step_kernel<false><<<blocks, NM_BLOCK, 0, st>>>(a);
+}
+
+void nm_launch_reset(const NmKernelArgs& a, const long long* env_ids, int n, void* stream) {
+  if (n <= 0) return;
+  nm_reset_kernel<<<(n + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(a, env_ids, n);
+}
+
+// ================================================================================================ FP32 pipe peak
+// FFMA micro-benchmark used as the roofline denominator of the step kernel (MEASURED_PEAKS.json has no
+// CUDA-core FP32 figure): 8 independent FMA chains per thread, 2 flops per FFMA.
+__global__ void nm_ffma_kernel(float* out, int iters) {
+  float a0 = threadIdx.x * 1e-3f, a1 = a0 + 1.f, a2 = a0 + 2.f, a3 = a0 + 3.f, a4 = a0 + 4.f, a5 = a0 + 5.f, a6 = a0 + 6.f, a7 = a0 + 7.f;
+  const float b = 1.0000001f, c = 1e-7f;
+#pragma unroll 1
+  for (int i = 0; i < iters; i++) {
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+      a0 = fmaf(a0, b, c); a1 = fmaf(a1, b, c); a2 = fmaf(a2, b, c); a3 = fmaf(a3, b, c);
+      a4 = fmaf(a4, b, c); a5 = fmaf(a5, b, c); a6 = fmaf(a6, b, c); a7 = fmaf(a7, b, c);
+    }
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+double nm_run_ffma_peak(void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int blocks = sms * 8, threads = 256, iters = 4096;
+  float* buf = nullptr;
+  if (cudaMalloc(&buf, sizeof(float) * blocks * threads) != cudaSuccess) return -1.0;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  double best = 0.0;
+  for (int rep = 0; rep < 5; rep++) {
+    cudaEventRecord(e0, st);
+    nm_ffma_kernel<<<blocks, threads, 0, st>>>(buf, iters);
+    cudaEventRecord(e1, st);
+    cudaEventSynchronize(e1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    double tf = 2.0 * 8 * 16 * (double)iters * blocks * threads / (ms * 1e-3) / 1e12;
+    if (rep > 0 && tf > best) best = tf;
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  cudaFree(buf);
+  return best;
+}

@@ -1,0 +1,225 @@
+"""``NightmareV3Env`` — GPU-resident drop-in for the reference's vectorised hexapod environment.
+
+Same constructor, attributes and ``reset/step/get_observations`` contract as the reference class
+(``envs/nightmare_v3_env.py:26-396``), so ``train.py`` and rsl_rl's ``OnPolicyRunner`` run on it
+unchanged.  Where the reference loops over ``num_envs`` CPU ``MjData`` objects and a dozen pybind
+calls per env per step (``:191-226``), this class makes ONE C-ABI call per step
+(``nm_step`` in ``include/nightmare_b200.h``) that launches one fused sm_100a kernel; actions,
+state, observations, rewards and resets never leave HBM.
+
+Deliberate differences (also listed in DESIGN.md):
+* tensors returned by ``step`` are views of persistent device buffers (the reference allocates new
+  CPU tensors every call, ``:311``); pass ``copy_outputs=True`` to get fresh copies;
+* command resampling uses a counter-based Philox stream keyed by ``(seed, env id, step)`` instead
+  of the unseeded global numpy RNG (``:327-330``), which cannot be reproduced;
+* ``cfg.viewer.render`` is ignored with a warning (no GUI on a GPU box).
+"""
+from __future__ import annotations
+
+import os
+import pickle
+import time
+import warnings
+
+import numpy as np
+import torch
+
+from .. import _lib, mjcf
+from ..batch import Batch
+from ..envcfg import REWARD_TERMS, build_envcfg, reward_table
+from .nightmare_v3_config import NightmareV3Config
+
+
+class NightmareV3Env:
+    def __init__(self, cfg: NightmareV3Config, log_dir="/tmp/nightmare_v3/logs", num_threads=1, *,
+                 device=None, seed: int = 0, env_offset: int = 0, copy_outputs: bool = False, debug: bool = False):
+        self.cfg = cfg
+        self.log_dir = log_dir
+        self.thread_num = num_threads            # accepted for API compatibility; the GPU needs no host threads
+
+        self.num_envs = self.cfg.env.num_envs
+        self.num_obs = self.cfg.env.num_obs
+        self.num_privileged_obs = self.num_obs   # reference quirk: not None although privileged obs are None (:34)
+        self.num_actions = self.cfg.env.num_actions
+
+        if device is None:
+            device = f"cuda:{int(os.environ.get('LOCAL_RANK', 0))}"
+        self.device = torch.device(device)
+        if self.device.type != "cuda" or not torch.cuda.is_available():
+            raise _lib.NightmareLibError("NightmareV3Env needs a CUDA device: the environment step has no CPU path")
+
+        # ≙ mj.MjModel.from_xml_path (:37): host compile (or load of the pre-compiled .nmb), then upload
+        self.model = mjcf.load_model(self.cfg.env.model_path)
+        self._dev_model = _lib.Model(self.model.to_bytes())
+        self.num_dof = self.model.nv - 6
+        self.num_geoms = self.model.ngeom
+        self.num_oscillators = self.num_actions - self.num_dof
+        self.gravity_vec = np.array([0.0, 0.0, -9.81])
+        self.body_index = self.model.name2id(mjcf.OBJ_BODY, self.cfg.env.body_name)
+        assert self.body_index != -1
+        if self.body_index != 1:
+            raise _lib.NightmareLibError("cfg.env.body_name must name the floating base (body 1)")
+        if self.num_obs != 66 or self.num_dof != 18:
+            raise _lib.NightmareLibError("the step kernel assembles the 66-entry observation of the 18-dof hexapod")
+
+        if self.cfg.viewer.render:
+            warnings.warn("cfg.viewer.render is ignored: the GPU environment has no interactive viewer")
+        self.recorded_states = []
+
+        self.reward_scales, self.reward_names, self._sum_keys = None, None, None
+        self.dt = self.model.opt_real[0] * self.cfg.control.decimation
+        table, order, keys = reward_table(self.cfg, self.dt)
+        self.reward_scales = {k: float(table[REWARD_TERMS.index(k)]) for k in keys}
+        self.reward_names = order
+        self._sum_keys = keys
+        self.command_ranges = self.cfg.commands.ranges
+        self.obs_scales = self.cfg.normalization.obs_scales
+        self.max_episode_length_s = self.cfg.env.episode_length_s
+        self.max_episode_length = np.ceil(self.max_episode_length_s / self.dt)
+        self.default_dof_pos = np.array(self.cfg.control.default_pos, dtype=np.float64)
+        self.add_noise = self.cfg.noise.add_noise
+        self.common_step_counter = 0
+        self.extras = {}
+        self._copy = copy_outputs
+
+        self._envcfg = build_envcfg(self.cfg, float(self.model.opt_real[0]))
+        self._batch = Batch(self._dev_model, self.num_envs, self.device, seed=seed, envcfg=self._envcfg,
+                            debug=debug, env_offset=env_offset)
+        b = self._batch
+        # public buffers (device tensors; the reference keeps numpy arrays of the same names, :56-97)
+        self.obs_buf, self.rew_buf, self.reset_buf = b.obs, b.rew, b.done
+        self.privileged_obs_buf = None
+        self.time_out_buf = b.time_outs
+        self.commands, self.actions = b.commands, b.actions
+        self.dof_pos, self.dof_vel = b.dof_pos, b.dof_vel
+        self.feet_air_time = b.feet_air_time
+        self.episode_sums = {k: b.episode_sums[:, REWARD_TERMS.index(k)] for k in keys}
+        self._key_idx = torch.tensor([REWARD_TERMS.index(k) for k in keys], device=self.device)
+        self._ep_means = torch.zeros(len(REWARD_TERMS), device=self.device)
+        self._time_outs_latched = torch.zeros(self.num_envs, device=self.device)
+        self._rec = None
+        if self.cfg.viewer.record_states:
+            self._rec = _StateRecorder(self, self.log_dir)
+
+    # ------------------------------------------------------------------ episode_length_buf: the runner REBINDS it
+    @property
+    def episode_length_buf(self):
+        return self._batch.episode_length
+
+    @episode_length_buf.setter
+    def episode_length_buf(self, value):
+        # rsl_rl: env.episode_length_buf = torch.randint_like(env.episode_length_buf, high=...) (train.py:54)
+        self._batch.episode_length.copy_(torch.as_tensor(value).to(device=self.device, dtype=torch.int64))
+
+    # ------------------------------------------------------------------ step
+    def step(self, actions):
+        """Apply actions, advance ``decimation`` physics substeps, return ``(obs, None, rew, dones, extras)``
+        exactly like the reference (:145-311); every tensor is on ``self.device``."""
+        self.render()
+        self.common_step_counter += 1
+        self._batch.step(actions, self.common_step_counter)
+        self._refresh_extras()
+        if self._rec is not None:
+            self._rec.after_step()
+        if self._copy:
+            return self.obs_buf.clone(), None, self.rew_buf.clone(), self.reset_buf.clone(), self.extras
+        return self.obs_buf, None, self.rew_buf, self.reset_buf, self.extras
+
+    def _refresh_extras(self):
+        # extras are only refreshed on steps where at least one env reset (reference quirk Q10, :344,:363-371);
+        # evaluated on the device, without a host sync
+        acc = self._batch.episode_acc
+        cnt = acc[-1]
+        has = cnt > 0
+        means = acc[:-1] / torch.clamp(cnt, min=1.0) / self.max_episode_length_s
+        self._ep_means = torch.where(has, means, self._ep_means)
+        self.extras["episode"] = {"rew_" + k: self._ep_means[REWARD_TERMS.index(k)] for k in self._sum_keys}
+        if self.cfg.env.send_timeouts:
+            self._time_outs_latched = torch.where(has, self._batch.time_outs, self._time_outs_latched)
+            self.extras["time_outs"] = self._time_outs_latched
+
+    def get_observations(self):
+        return self.obs_buf.clone() if self._copy else self.obs_buf
+
+    def get_privileged_observations(self):
+        return None
+
+    # ------------------------------------------------------------------ reset
+    def reset_idx(self, env_ids):
+        """≙ reference ``reset_idx`` (:335-371) for an explicit list of env ids."""
+        ids = torch.as_tensor(np.asarray(env_ids) if not torch.is_tensor(env_ids) else env_ids, device=self.device).to(torch.int64).flatten()
+        if ids.numel() == 0:
+            return
+        sums = self._batch.episode_sums[ids].mean(dim=0) / self.max_episode_length_s
+        self._ep_means = sums.clone()
+        self._batch.reset_idx(ids, self.common_step_counter)
+        self.extras["episode"] = {"rew_" + k: self._ep_means[REWARD_TERMS.index(k)] for k in self._sum_keys}
+        if self.cfg.env.send_timeouts:
+            self._time_outs_latched = self._batch.time_outs.clone()
+            self.extras["time_outs"] = self._time_outs_latched
+
+    def reset(self):
+        """Reset all robots, then take one zero-action step (:392-396)."""
+        self.reset_idx(torch.arange(self.num_envs, device=self.device))
+        obs, privileged_obs, _, _, _ = self.step(torch.zeros((self.num_envs, self.num_actions), device=self.device))
+        return obs, privileged_obs
+
+    def render(self):
+        return None
+
+    # ------------------------------------------------------------------ raw state access (parity harness, checkpoints)
+    def get_state(self):
+        b = self._batch
+        return b.qpos, b.qvel, b.warm
+
+    def set_state(self, qpos=None, qvel=None, warm=None):
+        b = self._batch
+        for dst, src in ((b.qpos, qpos), (b.qvel, qvel), (b.warm, warm)):
+            if src is not None:
+                dst.copy_(torch.as_tensor(src, dtype=torch.float32).to(self.device))
+
+    @property
+    def gpu_launches(self) -> int:
+        return self._batch.launches
+
+
+class _StateRecorder:
+    """Env-0 trajectory recorder (reference :261-272, replayed by ``open_custom_play.py:50-66``).
+
+    The reference appends ``(time, qpos, qvel, act)`` of env 0 every step and pickles the list whenever
+    env 0 resets.  Doing that literally would force a device->host sync per step; instead rows are
+    staged in a device ring buffer and flushed every ``flush_every`` steps (one small D2H copy), which
+    produces the same files with the same contents (file names carry the flush time)."""
+
+    def __init__(self, env: "NightmareV3Env", log_dir: str, flush_every: int = 256):
+        self.env, self.log_dir, self.k = env, log_dir, flush_every
+        self.ring = torch.zeros(flush_every, 1 + 25 + 24 + 1, device=env.device)
+        self.fill = 0
+        self.rows: list = []
+        self.sim_time = 0.0
+
+    def after_step(self):
+        e = self.env
+        b = e._batch
+        row = self.ring[self.fill]
+        row[1:26] = b.qpos[0]
+        row[26:50] = b.qvel[0]
+        row[50] = b.done[0].to(torch.float32)
+        self.fill += 1
+        if self.fill == self.k:
+            self.flush()
+
+    def flush(self):
+        if self.fill == 0:
+            return
+        host = self.ring[: self.fill].cpu().numpy().astype(np.float64)
+        self.fill = 0
+        for r in host:
+            self.sim_time += self.env.dt          # data.time is never reset by reset_idx (quirk Q3)
+            if r[50] != 0:
+                os.makedirs(self.log_dir, exist_ok=True)
+                with open(f"{self.log_dir}/{int(time.time())}.pkl", "wb") as fh:
+                    pickle.dump(self.rows, fh)
+                self.rows = []
+            self.rows.append((self.sim_time, r[1:26].copy(), r[26:50].copy(), np.zeros(0)))
+        self.env.recorded_states = self.rows

@@ -229,6 +229,7 @@ typedef struct {
   /* position-dependent */
   double *xpos, *xquat, *xmat, *xipos, *ximat, *xanchor, *xaxis, *site_xpos, *subtree_com, *cinert, *crb, *cdof;
   double *M, *L;               /* dense mass matrix and its Cholesky factor (lower) */
+  double *MH, *LH;             /* M - h*qDeriv of the implicit velocity update and its factor */
   /* velocity-dependent */
   double *cvel, *cdof_dot, *qfrc_bias, *qfrc_passive, *qfrc_actuator, *qfrc_smooth, *qacc_smooth;
   double *qfrc_constraint, *qacc, *act_force;
@@ -274,7 +275,7 @@ static void data_init(const nmo_model* m, data_t* d) {
   d->xpos = dalloc(3 * nb); d->xquat = dalloc(4 * nb); d->xmat = dalloc(9 * nb); d->xipos = dalloc(3 * nb);
   d->ximat = dalloc(9 * nb); d->xanchor = dalloc(3 * m->njnt); d->xaxis = dalloc(3 * m->njnt);
   d->site_xpos = dalloc(3 * m->nsite); d->subtree_com = dalloc(3 * nb); d->cinert = dalloc(10 * nb);
-  d->crb = dalloc(10 * nb); d->cdof = dalloc(6 * nv); d->M = dalloc(nv * nv); d->L = dalloc(nv * nv);
+  d->crb = dalloc(10 * nb); d->cdof = dalloc(6 * nv); d->M = dalloc(nv * nv); d->L = dalloc(nv * nv); d->MH = dalloc(nv * nv); d->LH = dalloc(nv * nv);
   d->cvel = dalloc(6 * nb); d->cdof_dot = dalloc(6 * nv); d->qfrc_bias = dalloc(nv); d->qfrc_passive = dalloc(nv);
   d->qfrc_actuator = dalloc(nv); d->qfrc_smooth = dalloc(nv); d->qacc_smooth = dalloc(nv);
   d->qfrc_constraint = dalloc(nv); d->qacc = dalloc(nv); d->act_force = dalloc(m->nu);
@@ -289,7 +290,7 @@ static void data_init(const nmo_model* m, data_t* d) {
 
 static void data_free(data_t* d) {
   double** p[] = {&d->qpos, &d->qvel, &d->qacc_warmstart, &d->ctrl, &d->xpos, &d->xquat, &d->xmat, &d->xipos, &d->ximat,
-                  &d->xanchor, &d->xaxis, &d->site_xpos, &d->subtree_com, &d->cinert, &d->crb, &d->cdof, &d->M, &d->L,
+                  &d->xanchor, &d->xaxis, &d->site_xpos, &d->subtree_com, &d->cinert, &d->crb, &d->cdof, &d->M, &d->L, &d->MH, &d->LH,
                   &d->cvel, &d->cdof_dot, &d->qfrc_bias, &d->qfrc_passive, &d->qfrc_actuator, &d->qfrc_smooth,
                   &d->qacc_smooth, &d->qfrc_constraint, &d->qacc, &d->act_force, &d->efc_J, &d->efc_pos, &d->efc_margin,
                   &d->efc_diagApprox, &d->efc_R, &d->efc_D, &d->efc_aref, &d->efc_vel, &d->efc_b, &d->efc_force,
@@ -993,8 +994,8 @@ static void step1(const nmo_model* m, data_t* d) {
   double* qacc = d->scratch;
   if (m->integrator == INT_IMPLICITFAST || m->integrator == INT_IMPLICIT) {
     /* implicitfast: qDeriv = d(qfrc_smooth)/d(qvel) restricted to actuator + passive terms (diagonal here) */
-    double* A = d->efc_AR;  /* borrow: nv*nv <= MAXEFC^2 */
-    double* L = A + nv * nv;
+    double* A = d->MH;
+    double* L = d->LH;
     memcpy(A, d->M, sizeof(double) * nv * nv);
     for (int i = 0; i < nv; i++) A[i * nv + i] += h * m->dof_damping[i];
     for (int a = 0; a < m->nu; a++) {
@@ -1009,8 +1010,8 @@ static void step1(const nmo_model* m, data_t* d) {
     int any = 0;
     for (int i = 0; i < nv; i++) if (m->dof_damping[i] > 0) any = 1;
     if (any && m->eulerdamp) {
-      double* A = d->efc_AR;
-      double* L = A + nv * nv;
+      double* A = d->MH;
+      double* L = d->LH;
       memcpy(A, d->M, sizeof(double) * nv * nv);
       for (int i = 0; i < nv; i++) A[i * nv + i] += h * m->dof_damping[i];
       cholesky(L, A, nv);

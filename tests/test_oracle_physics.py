@@ -1,0 +1,235 @@
+"""Physical invariants of the CPU oracle (oracle/nm_oracle.c).  The reference pins nothing for this
+path (no tests, no golden vectors; MuJoCo itself is not installable here), so the oracle is anchored on
+first principles instead — SURVEY.md §4b."""
+import numpy as np
+import pytest
+
+from nightmare_rl_b200 import mjcf
+from oracle import oracle as O
+
+
+def _variant(compiled_model, tmp_path, timestep=None, integrator=None, no_actuators=False):
+    cm = mjcf.CompiledModel(dict((k, v.copy()) for k, v in compiled_model.arrays.items()), compiled_model.names)
+    if no_actuators:
+        cm.arrays["act_gain"][:] = 0
+        cm.arrays["act_bias"][:] = 0
+    if timestep is not None:
+        cm.arrays["opt_real"][0] = timestep
+    if integrator is not None:
+        cm.arrays["opt_int"][0] = integrator
+    p = str(tmp_path / f"v_{timestep}_{integrator}_{no_actuators}.nmb")
+    cm.save(p)
+    return cm, O.OracleModel(p)
+
+
+def _mul_inert(i, v):
+    r = np.zeros(6)
+    r[0] = i[0] * v[0] + i[3] * v[1] + i[4] * v[2] - i[8] * v[4] + i[7] * v[5]
+    r[1] = i[3] * v[0] + i[1] * v[1] + i[5] * v[2] + i[8] * v[3] - i[6] * v[5]
+    r[2] = i[4] * v[0] + i[5] * v[1] + i[2] * v[2] - i[7] * v[3] + i[6] * v[4]
+    r[3] = i[8] * v[1] - i[7] * v[2] + i[9] * v[3]
+    r[4] = i[6] * v[2] - i[8] * v[0] + i[9] * v[4]
+    r[5] = i[7] * v[0] - i[6] * v[1] + i[9] * v[5]
+    return r
+
+
+def _random_flying_state(cm, rng):
+    qpos = cm.qpos0.copy()
+    qpos[2] = 5.0
+    qpos[3:7] = rng.normal(size=4)
+    qpos[3:7] /= np.linalg.norm(qpos[3:7])
+    qpos[7:] = rng.uniform(-0.5, 0.5, 18)
+    qvel = rng.normal(size=24) * np.r_[np.ones(3) * 0.5, np.ones(3) * 2, np.ones(18) * 3]
+    return qpos, qvel
+
+
+def test_free_fall_law(oracle_model):
+    """Contact-free, ctrl=0: v_n = -g h n and z_n = z0 - g h^2 n(n+1)/2 (semi-implicit), joints stay at rest."""
+    b = O.OracleBatch(oracle_model, 1)
+    h, g = 0.008, 9.81
+    for n in range(1, 19):
+        b.physics_step(np.zeros((1, 18)), 1)
+        q, v, _ = b.get_state()
+        assert b.get(0, "ncon")[0] == 0
+        assert abs(v[0, 2] + g * h * n) < 1e-12
+        assert abs(q[0, 2] - (0.15 - 0.5 * g * h * h * n * (n + 1))) < 1e-12
+        assert np.abs(q[0, 7:]).max() < 1e-12 and np.abs(q[0, 3:7] - [1, 0, 0, 0]).max() < 1e-12
+    b.physics_step(np.zeros((1, 18)), 3)     # ncon belongs to the forward pass at the START of a substep
+    assert b.get(0, "ncon")[0] >= 1          # first touch-down ~0.16 s after release
+
+
+def test_mass_matrix_matches_kinetic_energy(compiled_model, oracle_model):
+    """q'Mq/2 equals the sum of body kinetic energies computed from the c-frame velocities."""
+    rng = np.random.default_rng(1)
+    b = O.OracleBatch(oracle_model, 1)
+    qpos, qvel = _random_flying_state(compiled_model, rng)
+    b.set_state(qpos[None], qvel[None], np.zeros((1, 24)))
+    b.forward(np.zeros((1, 18)))
+    M = b.get(0, "M").reshape(24, 24)
+    ci, cv = b.get(0, "cinert").reshape(-1, 10), b.get(0, "cvel").reshape(-1, 6)
+    T = sum(0.5 * cv[i] @ _mul_inert(ci[i], cv[i]) for i in range(1, 20))
+    assert abs(0.5 * qvel @ M @ qvel - T) < 1e-10 * max(1.0, T)
+    assert np.allclose(M, M.T, atol=1e-14) and np.linalg.eigvalsh(M).min() > 0
+
+
+def test_forward_inverse_roundtrip(compiled_model, oracle_model):
+    """M qacc_smooth + bias = actuator force."""
+    rng = np.random.default_rng(2)
+    b = O.OracleBatch(oracle_model, 1)
+    qpos, qvel = _random_flying_state(compiled_model, rng)
+    ctrl = rng.uniform(-10, 10, 18)
+    b.set_state(qpos[None], qvel[None], np.zeros((1, 24)))
+    b.forward(ctrl[None])
+    M = b.get(0, "M").reshape(24, 24)
+    res = M @ b.get(0, "qacc_smooth") + b.get(0, "qfrc_bias") - b.get(0, "qfrc_actuator")
+    assert np.abs(res).max() < 1e-9
+    tau = 0.8 * (np.clip(ctrl, -8, 8) - qvel[6:])                  # kv (clamp(ctrl) - qvel), mjmodel.xml:136
+    assert np.allclose(b.get(0, "qfrc_actuator")[6:], tau, atol=1e-12)
+    assert np.abs(b.get(0, "qfrc_actuator")[:6]).max() == 0
+
+
+@pytest.mark.parametrize("h", [1e-4, 5e-5])
+def test_energy_and_momentum_conservation(compiled_model, tmp_path, h):
+    """Torque-free flight: energy drift is O(h) (halves with h), linear momentum follows m g t, angular
+    momentum about the COM is conserved.  Exercises CRBA, RNE (incl. free-joint quasi-velocities) and
+    the quaternion integrator together."""
+    cm, om = _variant(compiled_model, tmp_path, timestep=h, integrator=mjcf.INT_EULER, no_actuators=True)
+    rng = np.random.default_rng(0)
+    b = O.OracleBatch(om, 1)
+    qpos, qvel = _random_flying_state(cm, rng)
+    b.set_state(qpos[None], qvel[None], np.zeros((1, 24)))
+
+    def diag():
+        b.forward(np.zeros((1, 18)))
+        M = b.get(0, "M").reshape(24, 24)
+        qv = b.get(0, "qvel")
+        xipos = b.get(0, "xipos").reshape(-1, 3)
+        ci, cv = b.get(0, "cinert").reshape(-1, 10), b.get(0, "cvel").reshape(-1, 6)
+        mom = sum(_mul_inert(ci[i], cv[i]) for i in range(1, 20))
+        return 0.5 * qv @ M @ qv + 9.81 * (cm.body_mass * xipos[:, 2]).sum(), mom
+
+    e0, m0 = diag()
+    T = 0.05
+    b.physics_step(np.zeros((1, 18)), int(round(T / h)))
+    e1, m1 = diag()
+    assert abs(e1 - e0) < 8.0 * h * abs(e0)          # first-order drift, ~-1.4e-3 J at h=1e-4 on 147 J
+    assert np.abs(m1[:3] - m0[:3]).max() < 0.2 * h * 1e3 * 1e-2 + 1e-5
+    assert np.abs(m1[3:] - m0[3:] - np.array([0, 0, -3.0 * 9.81 * T])).max() < 1e-4
+
+
+def test_energy_drift_is_first_order(compiled_model, tmp_path):
+    drift = []
+    for h in (1e-4, 5e-5):
+        cm, om = _variant(compiled_model, tmp_path, timestep=h, integrator=mjcf.INT_EULER, no_actuators=True)
+        rng = np.random.default_rng(0)
+        b = O.OracleBatch(om, 1)
+        qpos, qvel = _random_flying_state(cm, rng)
+        b.set_state(qpos[None], qvel[None], np.zeros((1, 24)))
+
+        def energy():
+            b.forward(np.zeros((1, 18)))
+            M = b.get(0, "M").reshape(24, 24)
+            qv = b.get(0, "qvel")
+            return 0.5 * qv @ M @ qv + 9.81 * (cm.body_mass * b.get(0, "xipos").reshape(-1, 3)[:, 2]).sum()
+
+        e0 = energy()
+        b.physics_step(np.zeros((1, 18)), int(round(0.05 / h)))
+        drift.append(energy() - e0)
+    assert abs(drift[0] / drift[1] - 2.0) < 0.05
+
+
+def _settle(oracle_model, n_sub=120, seed=0, ctrl_scale=0.0):
+    rng = np.random.default_rng(seed)
+    b = O.OracleBatch(oracle_model, 1)
+    for t in range(n_sub):
+        b.physics_step(rng.uniform(-1, 1, (1, 18)) * ctrl_scale, 1)
+    return b
+
+
+def test_contact_solver_invariants(oracle_model):
+    """A = J M^-1 J' + R is symmetric PSD, pyramid forces are >= 0, touch sensors add up to the normal forces."""
+    seen = 0
+    for seed, scale in ((0, 0.0), (1, 4.0), (2, 8.0)):
+        b = _settle(oracle_model, 60 + 20 * seed, seed, scale)
+        for _ in range(30):
+            b.physics_step(np.zeros((1, 18)), 1)
+            ne = int(b.get(0, "nefc")[0])
+            if ne == 0:
+                continue
+            seen += 1
+            A = b.get(0, "efc_AR").reshape(ne, ne)
+            assert np.allclose(A, A.T, atol=1e-9 * np.abs(A).max())
+            assert np.linalg.eigvalsh(0.5 * (A + A.T)).min() > 0
+            f = b.get(0, "efc_force")
+            assert (f >= 0).all()
+            con = b.get(0, "contact").reshape(-1, 7)
+            fn = f.reshape(-1, 4).sum(axis=1)
+            sd = b.get(0, "sensordata")
+            geoms = con[:, 1].astype(int)
+            for k in range(6):                       # tibia sites have a 10 m radius: every contact of that body counts
+                assert abs(sd[k] - fn[geoms == 2 + k].sum()) < 1e-9
+            assert abs(sd[12] - fn[geoms == 1].sum()) < 1e-9
+            assert (sd[6:12] <= sd[:6] + 1e-12).all()        # foot sphere lies inside the tibia sphere
+            # qacc is consistent with the forces: M (qacc - qacc_smooth) = J' f
+            M = b.get(0, "M").reshape(24, 24)
+            J = b.get(0, "efc_J").reshape(ne, 24)
+            assert np.abs(M @ (b.get(0, "qacc") - b.get(0, "qacc_smooth")) - J.T @ f).max() < 1e-8
+            assert (con[:, 3] <= 0).all()            # active contacts penetrate (margin 0)
+    assert seen > 20
+
+
+def test_contact_rows_are_pyramidal(oracle_model):
+    b = _settle(oracle_model, 40)
+    ne = int(b.get(0, "nefc")[0])
+    assert ne > 0 and ne % 4 == 0
+    J = b.get(0, "efc_J").reshape(ne, 24)
+    for c in range(ne // 4):
+        r = J[4 * c:4 * c + 4]
+        # opposite edges share the normal row: (r0 + r1)/2 == (r2 + r3)/2 == J_normal; mu = 1
+        assert np.allclose(r[0] + r[1], r[2] + r[3], atol=1e-12)
+        jn = 0.5 * (r[0] + r[1])
+        assert np.allclose(jn[:3], [0, 0, 1], atol=1e-12)           # flat floor: normal = +z on the base translation dofs
+        R = b.get(0, "efc_R")[4 * c:4 * c + 4]
+        assert np.allclose(R, R[0]) and R[0] > 0
+
+
+def test_rest_pose_is_stable(oracle_model):
+    """Zero actions for 3 s: the robot settles on the floor (belly or feet) and stops moving."""
+    b = O.OracleBatch(oracle_model, 1)
+    b.physics_step(np.zeros((1, 18)), 375)
+    q, v, _ = b.get_state()
+    assert np.isfinite(q).all() and np.abs(v).max() < 0.2      # 3-sweep PGS leaves a small residual jitter
+    assert 0.0 < q[0, 2] < 0.1
+    sd = b.get(0, "sensordata")
+    assert abs(sd[:6].sum() + sd[12] - 3.0 * 9.81) < 0.5            # contact forces carry the weight
+
+
+def test_divergence_guard(compiled_model, oracle_model):
+    b = O.OracleBatch(oracle_model, 1)
+    qpos = compiled_model.qpos0.copy()
+    qpos[0] = np.nan
+    b.set_state(qpos[None], None, None)
+    b.physics_step(np.zeros((1, 18)), 1)
+    q, v, _ = b.get_state()
+    assert np.isfinite(q).all() and b.get(0, "nwarn")[0] >= 1
+
+
+def test_philox_known_answers():
+    """Philox4x32-10 known-answer vectors (Random123 kat_vectors): the RNG that replaces numpy's MT19937."""
+    assert [hex(x) for x in O.philox4x32(0, 0, 0, 0, 0, 0)] == ["0x6627e8d5", "0xe169c58d", "0xbc57ac4c", "0x9b00dbd8"]
+    f = 0xFFFFFFFF
+    assert [hex(x) for x in O.philox4x32(f, f, f, f, f, f)] == ["0x408f276d", "0x41c83b0e", "0xa20bc7c6", "0x6d5451fd"]
+    assert [hex(x) for x in O.philox4x32(0xA4093822, 0x299F31D0, 0x243F6A88, 0x85A308D3, 0x13198A2E, 0x03707344)] == \
+        ["0xd16cfe09", "0x94fdcceb", "0x5001e420", "0x24126ea1"]
+
+
+def test_threads_do_not_change_results(oracle_model):
+    rng = np.random.default_rng(4)
+    ctrl = rng.uniform(-8, 8, (16, 18))
+    out = []
+    for th in (1, 4):
+        b = O.OracleBatch(oracle_model, 16)
+        b.physics_step(ctrl, 40, th)
+        out.append(b.get_state())
+    for a, c in zip(*out):
+        assert np.array_equal(a, c)
