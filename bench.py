@@ -224,6 +224,35 @@ def run_ours(args):
         dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
     e2e_val = world * E * Ke / (float(e2e_ms.item()) * 1e-3)
 
+    # ---- batch-size sweep (metric is quoted on 4096-131072 envs): device-timed, state resident, rank 0 of a 1-GPU run only
+    sweep = None
+    if world == 1 and not args.no_sweep:
+        sweep = []
+        for En in (16384, 65536, 131072):
+            c2 = NightmareV3Config()
+            c2.env.num_envs = En
+            c2.env.model_path = NMB
+            c2.viewer.render = False
+            c2.viewer.record_states = False
+            e2 = NightmareV3Env(c2, seed=1, device=dev)
+            e2.reset()
+            e2.episode_length_buf = torch.randint(0, 1250, (En,), device=dev, generator=gen)
+            acts = torch.randn(4, En, 18, device=dev, generator=gen)
+            for i in range(5):
+                e2._batch.step(acts[i % 4], 100 + i)
+            torch.cuda.synchronize()
+            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            Ks = 30
+            s0.record()
+            for i in range(Ks):
+                e2._batch.step(acts[i % 4], 200 + i)
+            s1.record()
+            torch.cuda.synchronize()
+            ms = s0.elapsed_time(s1) / Ks
+            sweep.append({"envs": En, "ms_per_step": ms, "env_steps_per_s": En / (ms * 1e-3)})
+            del e2, acts
+            torch.cuda.empty_cache()
+
     if rank == 0:
         peaks = {}
         try:
@@ -248,13 +277,15 @@ def run_ours(args):
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": E * 18 * 4, "d2h_bytes_per_step": E * (66 * 4 + 4 + 8), "steps": Ke},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak, "traffic": None,
-                         "peak_source": which, "kernel": "nm_step_kernel<true>", "kernel_ms": kern_ms,
+                         "peak_source": which, "kernel": "nm_step_kernel<true> (+ the 2 us nm_finalize_kernel inside the same event pair)", "kernel_ms": kern_ms,
                          "note": "kernel is FP32-pipe/latency bound, not HBM bound; see roofline_fp32"},
             "roofline_fp32": {"bound": "fp32", "achieved": tfs, "peak": fp32_peak, "unit": "TFLOP/s", "frac": tfs / fp32_peak if fp32_peak > 0 else None,
                               "flops_per_env_step": FLOPS_PER_ENV_STEP, "peak_source": "FFMA micro-benchmark in this run"},
             "cpu_baseline": {"value": cpu_val, "unit": UNIT, "cores": cores, "kind": "port",
                              "sample": f"{E} envs x {cpu_steps} env-steps, fp64 C restatement (oracle/), {cores} pthreads"},
         }
+        if sweep is not None:
+            line["sweep"] = {"note": "same step at larger batches on 1 GPU, back-to-back launches, no L2 flush", "points": sweep}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -267,6 +298,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--envs-per-gpu", type=int, default=4096)
+    ap.add_argument("--no-sweep", action="store_true", help="skip the 16384/65536/131072-env sweep of the 1-GPU run")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

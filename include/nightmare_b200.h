@@ -79,9 +79,11 @@ typedef struct {
   int64_t* done;         /* [N]    reset_buf */
   float* time_outs;      /* [N]    */
   float* sensordata;     /* [N,13] touch sensors of the last substep */
-  float* episode_acc;    /* [NM_NREW+1] sum over envs reset this step of their episode sums, then the count
-                            (zeroed by nm_step before the kernel runs) */
+  float* episode_acc;    /* [NM_NREW+1] sum over the envs reset THIS step of their episode sums, then their count */
   float* debug;          /* [N,NM_DBG_STRIDE] or NULL */
+  /* extras (≙ self.extras, envs/nightmare_v3_env.py:363-371): refreshed only on steps where >= 1 env reset */
+  float* ep_means;       /* [NM_NREW] mean episode sum of the envs that reset / max_episode_length_s   (:366) */
+  float* time_outs_latched; /* [N] time_out_buf as of the last step that reset an env                  (:371) */
 } nm_buffers;
 
 const char* nm_last_error(void);

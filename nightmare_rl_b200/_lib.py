@@ -17,7 +17,8 @@ _vp, _ci, _i64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64
 class NmBuffers(ctypes.Structure):
     _fields_ = [(n, _vp) for n in (
         "qpos", "qvel", "warm", "actions", "dof_pos", "dof_vel", "commands", "episode_length", "episode_sums",
-        "feet_air_time", "contact_bits", "obs", "rew", "done", "time_outs", "sensordata", "episode_acc", "debug")]
+        "feet_air_time", "contact_bits", "obs", "rew", "done", "time_outs", "sensordata", "episode_acc", "debug",
+        "ep_means", "time_outs_latched")]
 
 
 class NightmareLibError(RuntimeError):

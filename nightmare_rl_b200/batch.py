@@ -35,6 +35,7 @@ class Batch:
         self.time_outs = z(num_envs)
         self.sensordata = z(num_envs, 13)
         self.episode_acc = z(NREW + 1)
+        self.ep_means, self.time_outs_latched = z(NREW), z(num_envs)
         self.debug = z(num_envs, _lib.NM_DBG_STRIDE) if debug else None
         b = _lib.NmBuffers()
         for name, _ in _lib.NmBuffers._fields_:

@@ -374,6 +374,9 @@ struct nm_batch {
   float4* d_hull;
   int* d_nbr_adr;
   int* d_nbr;
+  int* d_hint;
+  float* d_acc;          // [2][19] double-buffered episode accumulators
+  int parity;
   float* d_stage_actions;
   size_t stage_cap;
   int64_t launches;
@@ -403,7 +406,7 @@ extern "C" int nm_batch_create(const nm_model* m, int num_envs, int device, uint
     return fail(NM_ERR_UNSUPPORTED, "the env-step kernel is laid out for the 6-leg / 18-dof Nightmare topology");
   if (!bufs->qpos || !bufs->qvel || !bufs->warm || !bufs->sensordata) return fail(NM_ERR_ARG, "physics buffers must be non-null");
   if (cfg && (!bufs->actions || !bufs->dof_pos || !bufs->dof_vel || !bufs->commands || !bufs->episode_length || !bufs->episode_sums ||
-              !bufs->feet_air_time || !bufs->contact_bits || !bufs->obs || !bufs->rew || !bufs->done || !bufs->time_outs || !bufs->episode_acc))
+              !bufs->feet_air_time || !bufs->contact_bits || !bufs->obs || !bufs->rew || !bufs->done || !bufs->time_outs || !bufs->episode_acc || !bufs->ep_means || !bufs->time_outs_latched))
     return fail(NM_ERR_ARG, "env buffers must be non-null when an env config is given");
   if (cfg && (cfg->decimation < 1 || cfg->num_actions < NM_NDOF)) return fail(NM_ERR_ARG, "env config: decimation>=1 and num_actions>=18 required");
   int ndev = 0;
@@ -425,7 +428,13 @@ extern "C" int nm_batch_create(const nm_model* m, int num_envs, int device, uint
   CUDA_OK(cudaMemcpy(b->d_nbr_adr, m->nbr_adr.data(), sizeof(int) * m->nbr_adr.size(), cudaMemcpyHostToDevice));
   CUDA_OK(cudaMalloc(&b->d_nbr, sizeof(int) * (m->nbr.size() + 1)));
   CUDA_OK(cudaMemcpy(b->d_nbr, m->nbr.data(), sizeof(int) * m->nbr.size(), cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMalloc(&b->d_hint, sizeof(int) * (size_t)num_envs * NM_OCT));
+  CUDA_OK(cudaMemset(b->d_hint, 0, sizeof(int) * (size_t)num_envs * NM_OCT));
+  CUDA_OK(cudaMalloc(&b->d_acc, sizeof(float) * 2 * (NM_NREW + 1)));
+  CUDA_OK(cudaMemset(b->d_acc, 0, sizeof(float) * 2 * (NM_NREW + 1)));
   NmKernelArgs& a = b->args;
+  a.hull_hint = b->d_hint;
+  a.ep_means = bufs->ep_means; a.time_outs_latched = bufs->time_outs_latched;
   a.model = b->d_model; a.cfg = b->d_cfg; a.hull_vert = b->d_hull; a.hull_nbr_adr = b->d_nbr_adr; a.hull_nbr = b->d_nbr;
   a.num_envs = num_envs; a.nstep = cfg ? cfg->decimation : 1; a.step_counter = 0; a.env_offset = 0; a.seed = seed;
   a.qpos = bufs->qpos; a.qvel = bufs->qvel; a.warm = bufs->warm; a.actions = bufs->actions; a.dof_pos = bufs->dof_pos;
@@ -440,7 +449,7 @@ extern "C" int nm_batch_create(const nm_model* m, int num_envs, int device, uint
 
 extern "C" void nm_batch_destroy(nm_batch* b) {
   if (!b) return;
-  cudaFree(b->d_model); cudaFree(b->d_cfg); cudaFree(b->d_hull); cudaFree(b->d_nbr_adr); cudaFree(b->d_nbr);
+  cudaFree(b->d_model); cudaFree(b->d_cfg); cudaFree(b->d_hull); cudaFree(b->d_nbr_adr); cudaFree(b->d_nbr); cudaFree(b->d_hint); cudaFree(b->d_acc);
   if (b->d_stage_actions) cudaFree(b->d_stage_actions);
   delete b;
 }
@@ -457,9 +466,12 @@ extern "C" int nm_step(nm_batch* b, const float* actions, int act_stride, int64_
   if (act_stride < NM_NDOF) return fail(NM_ERR_ARG, "nm_step: actions need at least 18 columns");
   NmKernelArgs a = b->args;
   a.in_actions = actions; a.act_stride = act_stride; a.step_counter = step_counter;
-  CUDA_OK(cudaMemsetAsync(a.episode_acc, 0, sizeof(float) * (NM_NREW + 1), static_cast<cudaStream_t>(stream)));
+  a.acc_cur = b->d_acc + (NM_NREW + 1) * b->parity;
+  a.acc_next = b->d_acc + (NM_NREW + 1) * (b->parity ^ 1);
+  b->parity ^= 1;
   nm_launch_step(a, true, stream);
-  b->launches++;
+  nm_launch_finalize(a, stream);
+  b->launches += 2;
   CUDA_OK(cudaGetLastError());
   return NM_OK;
 }

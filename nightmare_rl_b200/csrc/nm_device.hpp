@@ -39,7 +39,7 @@ struct NmLeg {
   NmGeom geom;
 };
 
-struct NmDevModel {
+struct alignas(16) NmDevModel {
   NmLeg leg[NM_OCT];
   float b_ipos[3], b_iloc[6], b_mass, total_mass;
   float plane_n[3], plane_d, frame[9];
@@ -51,7 +51,7 @@ struct NmDevModel {
 };
 
 // env-layer scalars in fp32 (from nm_envcfg)
-struct NmDevCfg {
+struct alignas(16) NmDevCfg {
   int decimation, tibia_mode, body_mode, add_noise, resample_period, pad[3];
   float action_scale, clip_actions, p_gain, clip_obs;
   float default_pos[18];
@@ -69,6 +69,7 @@ struct NmKernelArgs {
   const float4* hull_vert;
   const int* hull_nbr_adr;
   const int* hull_nbr;
+  int* hull_hint;            // [N, NM_OCT] last support vertex per collision hull (library-owned scratch)
   int num_envs;
   int nstep;
   long long step_counter;
@@ -79,11 +80,14 @@ struct NmKernelArgs {
   float* actions; float* dof_pos; float* dof_vel; float* commands;
   long long* episode_length; float* episode_sums; float* feet_air_time; int* contact_bits;
   float* obs; float* rew; long long* done; float* time_outs; float* sensordata; float* episode_acc; float* debug;
+  float* ep_means; float* time_outs_latched;   // extras, refreshed only on steps where >= 1 env reset (env.py:363-371)
+  float* acc_cur; float* acc_next;             // library-owned double-buffered accumulators behind episode_acc
   // inputs
   const float* in_actions; int act_stride;   // env mode
   const float* in_ctrl;                       // physics-only mode
 };
 
 void nm_launch_step(const NmKernelArgs& a, bool env_mode, void* stream);
+void nm_launch_finalize(const NmKernelArgs& a, void* stream);
 void nm_launch_reset(const NmKernelArgs& a, const long long* env_ids, int n, void* stream);
 double nm_run_ffma_peak(void* stream);

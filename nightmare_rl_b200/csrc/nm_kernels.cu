@@ -255,6 +255,9 @@ __device__ __forceinline__ void solve_system(const Factor& F, const float* rb, c
 }
 
 // ---------------------------------------------------------------------------------------------- misc
+__device__ __noinline__ float impedance_pow(float x, float mid, float power) {   // general solimp power: cold path, kept out of line
+  return (x <= mid) ? powf(x, power) / powf(mid, power - 1.f) : 1.f - powf(1.f - x, power) / powf(1.f - mid, power - 1.f);
+}
 __device__ __forceinline__ float impedance(const NmGeom& g, float pos) {
   if (g.dmin == g.dmax || g.width <= NM_MINVAL) return 0.5f * (g.dmin + g.dmax);
   float x = fabsf(pos / g.width);
@@ -263,7 +266,7 @@ __device__ __forceinline__ float impedance(const NmGeom& g, float pos) {
   float y;
   if (g.power == 1.f) y = x;
   else if (g.power == 2.f) y = (x <= g.mid) ? x * x / g.mid : 1.f - (1.f - x) * (1.f - x) / (1.f - g.mid);
-  else y = (x <= g.mid) ? powf(x, g.power) / powf(g.mid, g.power - 1.f) : 1.f - powf(1.f - x, g.power) / powf(1.f - g.mid, g.power - 1.f);
+  else y = impedance_pow(x, g.mid, g.power);
   return fmaf(y, g.dmax - g.dmin, g.dmin);
 }
 
@@ -279,7 +282,7 @@ __device__ __forceinline__ float ray_sphere(V3 center, float radius, V3 pnt, V3 
   return -1.f;
 }
 
-__device__ __forceinline__ void philox4x32(unsigned k0, unsigned k1, unsigned c0, unsigned c1, unsigned c2, unsigned c3, unsigned* out) {
+__device__ __noinline__ void philox4x32(unsigned k0, unsigned k1, unsigned c0, unsigned c1, unsigned c2, unsigned c3, unsigned* out) {
 #pragma unroll
   for (int r = 0; r < 10; r++) {
     unsigned hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
@@ -291,6 +294,12 @@ __device__ __forceinline__ void philox4x32(unsigned k0, unsigned k1, unsigned c0
   out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 __device__ __forceinline__ float u01(unsigned x) { return (float)(x >> 8) * (1.0f / 16777216.0f); }
+// uniform noise in [-1,1) for observation entry k: Philox block (phase 2 + k/4), word k%4 (same definition as the oracle)
+__device__ __noinline__ float obs_noise(unsigned long long seed, long long genv, long long step, int k) {
+  unsigned nz[4];
+  philox4x32((unsigned)seed, (unsigned)genv, (unsigned)step, (unsigned)((unsigned long long)step >> 32), (unsigned)(2 + (k >> 2)), (unsigned)(seed >> 32), nz);
+  return 2.f * u01(nz[k & 3]) - 1.f;
+}
 
 // ≙ _resample_commands (env.py:321-333); RNG keyed by (seed, GLOBAL env id), counter (step, phase)
 __device__ __forceinline__ void resample_commands(const NmDevCfg& c, unsigned long long seed, long long genv, long long step, int phase, float* cmd) {
@@ -303,11 +312,13 @@ __device__ __forceinline__ void resample_commands(const NmDevCfg& c, unsigned lo
   cmd[0] = cx * keep; cmd[1] = cy * keep; cmd[2] = cw;
 }
 
-// per-lane contact rows (whitened), kept in local memory (L1-resident)
-struct ConRows {
-  float y[NM_MAXC][4][6];
-  float z[NM_MAXC][4][3];
-  float b[NM_MAXC][4], ad[NM_MAXC][4], adi[NM_MAXC][4], f[NM_MAXC][4];
+// per-lane contact blocks in contact space (local memory, L1-resident): 42 floats per contact
+struct ConBlk {
+  float Y[NM_MAXC][3][6];   // whitened base-space image of the contact-frame rows (normal, tangent 1, tangent 2)
+  float Z[NM_MAXC][3][3];   // whitened leg-space image
+  float Gm[NM_MAXC][6];     // Gram matrix of the three whitened rows: 00 01 02 11 12 22
+  float beta[NM_MAXC][3];   // J qacc_smooth - aref, split per frame axis
+  float f[NM_MAXC][4];      // pyramid-edge forces
   float R[NM_MAXC];
   V3 pos[NM_MAXC];
 };
@@ -322,13 +333,14 @@ __global__ void __launch_bounds__(NM_BLOCK) nm_step_kernel(const NmKernelArgs A)
   __shared__ NmDevModel sm;
   __shared__ NmDevCfg scfg;
   {
-    const int* src = reinterpret_cast<const int*>(A.model);
-    int* dst = reinterpret_cast<int*>(&sm);
-    for (int i = threadIdx.x; i < (int)(sizeof(NmDevModel) / 4); i += blockDim.x) dst[i] = src[i];
+    static_assert(sizeof(NmDevModel) % 16 == 0 && sizeof(NmDevCfg) % 16 == 0, "constant tables are copied as int4");
+    const int4* src = reinterpret_cast<const int4*>(A.model);
+    int4* dst = reinterpret_cast<int4*>(&sm);
+    for (int i = threadIdx.x; i < (int)(sizeof(NmDevModel) / 16); i += blockDim.x) dst[i] = __ldg(src + i);
     if (ENV) {
-      const int* s2 = reinterpret_cast<const int*>(A.cfg);
-      int* d2 = reinterpret_cast<int*>(&scfg);
-      for (int i = threadIdx.x; i < (int)(sizeof(NmDevCfg) / 4); i += blockDim.x) d2[i] = s2[i];
+      const int4* s2 = reinterpret_cast<const int4*>(A.cfg);
+      int4* d2 = reinterpret_cast<int4*>(&scfg);
+      for (int i = threadIdx.x; i < (int)(sizeof(NmDevCfg) / 16); i += blockDim.x) d2[i] = __ldg(s2 + i);
     }
   }
   __syncthreads();
@@ -387,7 +399,10 @@ __global__ void __launch_bounds__(NM_BLOCK) nm_step_kernel(const NmKernelArgs A)
   SV cvel_b; cvel_b.w = mk(0, 0, 0); cvel_b.v = mk(0, 0, 0);
   float sens0 = 0.f, sens1 = 0.f, base_height = 0.f;
   int bad = 0;
-  ConRows cr;
+  ConBlk cb;
+  // support-vertex hint of this lane's hull (pure accelerator: any start vertex gives the same support vertex up to exact ties)
+  int hint = G.has ? A.hull_hint[(size_t)env * NM_OCT + l] : 0;
+  hint = (hint >= 0 && hint < G.hull_num) ? hint : 0;
 
 #pragma unroll 1
   for (int sub = 0; sub < A.nstep; sub++) {
@@ -524,6 +539,9 @@ __global__ void __launch_bounds__(NM_BLOCK) nm_step_kernel(const NmKernelArgs A)
     solve_system(F, rb, rk, xsb, xsk);
 
     // ================================================================ P4 collision: convex hull vs plane
+    // Support vertex by hill-climbing the hull graph (a local minimum of a linear function on a convex hull
+    // is the global one), warm-started from the previous substep's / step's support vertex (A.hull_hint):
+    // the walk is then usually a single round over ~6 neighbours instead of ~6 rounds / ~40 vertices.
     const V3 pn = ld3(sm.plane_n);
     int nc = 0;
     float cdist[NM_MAXC];
@@ -532,44 +550,55 @@ __global__ void __launch_bounds__(NM_BLOCK) nm_step_kernel(const NmKernelArgs A)
       const V3 dl = mulT(Xg, pn);                        // plane normal in the geom frame; minimise dl . v
       const float4* hv = A.hull_vert + G.hull_adr;
       const int* nadr = A.hull_nbr_adr + G.hull_adr;
-      int best = G.start;
+      int best = hint;
       float4 v4 = __ldg(hv + best);
       float bval = fmaf(dl.x, v4.x, fmaf(dl.y, v4.y, dl.z * v4.z));
-      for (;;) {                                          // hill-climb on the hull graph (convex => global minimum)
-        int e0 = __ldg(nadr + best), e1 = __ldg(nadr + best + 1);
+      int e0, e1;
+      for (;;) {
+        e0 = __ldg(nadr + best); e1 = __ldg(nadr + best + 1);
         int nb = best;
-        for (int e = e0; e < e1; e++) {
-          int u = __ldg(A.hull_nbr + e);
-          float4 w4 = __ldg(hv + u);
-          float val = fmaf(dl.x, w4.x, fmaf(dl.y, w4.y, dl.z * w4.z));
-          if (val < bval) { bval = val; nb = u; }
+        for (int e = e0; e < e1; e += 4) {                // 4 neighbours per trip: loads issued together, compared in list order
+          const int el = e1 - 1;
+          const int u0 = __ldg(A.hull_nbr + e), u1 = __ldg(A.hull_nbr + min(e + 1, el)), u2 = __ldg(A.hull_nbr + min(e + 2, el)),
+                    u3 = __ldg(A.hull_nbr + min(e + 3, el));
+          const float4 w0 = __ldg(hv + u0), w1 = __ldg(hv + u1), w2 = __ldg(hv + u2), w3 = __ldg(hv + u3);
+          const float a0 = fmaf(dl.x, w0.x, fmaf(dl.y, w0.y, dl.z * w0.z)), a1 = fmaf(dl.x, w1.x, fmaf(dl.y, w1.y, dl.z * w1.z));
+          const float a2 = fmaf(dl.x, w2.x, fmaf(dl.y, w2.y, dl.z * w2.z)), a3 = fmaf(dl.x, w3.x, fmaf(dl.y, w3.y, dl.z * w3.z));
+          if (a0 < bval) { bval = a0; nb = u0; }
+          if (a1 < bval) { bval = a1; nb = u1; }
+          if (a2 < bval) { bval = a2; nb = u2; }
+          if (a3 < bval) { bval = a3; nb = u3; }
         }
         if (nb == best) break;
         best = nb;
       }
+      hint = best;
       v4 = __ldg(hv + best);
       V3 wv = pg + mul(Xg, mk(v4.x, v4.y, v4.z));
       float dist = dot(pn, wv) - sm.plane_d;
       if (dist <= G.margin) {
-        cdist[0] = dist; cvert[0] = best; cr.pos[0] = fma3(-0.5f * dist, pn, wv); nc = 1;
+        cdist[0] = dist; cvert[0] = best; cb.pos[0] = fma3(-0.5f * dist, pn, wv); nc = 1;
         const float thr2 = (0.3f * G.rbound) * (0.3f * G.rbound);
-        int e0 = __ldg(nadr + best), e1 = __ldg(nadr + best + 1);
+        const float dpl = dot(pn, pg) - sm.plane_d;       // cheap pre-test in the geom frame: dist(u) ~= dl.v_u + dpl
         for (int e = e0; e < e1 && nc < NM_MAXC; e++) {   // up to 3 more among the support vertex's neighbours
           int u = __ldg(A.hull_nbr + e);
           float4 w4 = __ldg(hv + u);
+          if (fmaf(dl.x, w4.x, fmaf(dl.y, w4.y, dl.z * w4.z)) + dpl > G.margin + 1e-4f) continue;
           V3 wu = pg + mul(Xg, mk(w4.x, w4.y, w4.z));
           float du = dot(pn, wu) - sm.plane_d;
           if (du > G.margin) continue;
           V3 cp = fma3(-0.5f * du, pn, wu);
           bool close = false;
-          for (int k = 0; k < nc; k++) { V3 d3 = cr.pos[k] - cp; close |= dot(d3, d3) < thr2; }
+          for (int k = 0; k < nc; k++) { V3 d3 = cb.pos[k] - cp; close |= dot(d3, d3) < thr2; }
           if (close) continue;
-          cdist[nc] = du; cvert[nc] = u; cr.pos[nc] = cp; nc++;
+          cdist[nc] = du; cvert[nc] = u; cb.pos[nc] = cp; nc++;
         }
       }
     }
     const int ncon_env = oct_sumi(nc);
-    const bool any_contact = __any_sync(FULL, ncon_env > 0);
+    const unsigned has_bal = __ballot_sync(FULL, nc > 0);
+    const unsigned owner_mask = (has_bal | (has_bal >> 8) | (has_bal >> 16) | (has_bal >> 24)) & 0x7fu;   // octet lanes owning contacts, any env of the warp
+    const bool any_contact = owner_mask != 0u;
 
     float xb[6], xk[3];          // constraint-induced acceleration M^-1 J^T f (after noslip)
 #pragma unroll
@@ -585,10 +614,15 @@ __global__ void __launch_bounds__(NM_BLOCK) nm_step_kernel(const NmKernelArgs A)
     int dbg_pgs = 0, dbg_noslip = 0, dbg_warm = 0;
 
     if (any_contact) {
-      // ============================================================== P5 contact rows, whitened
+      // ============================================================== P5 contact blocks, whitened
+      // Per contact: the three contact-frame Jacobian rows (normal, tangent 1, tangent 2) whitened by the block
+      // factors (Y = J~ G_S^-T, Z = J_k G_k^-T), their 3x3 Gram matrix Gm = J M^-1 J^T restricted to the contact,
+      // and the affine term split as beta0 + s*beta_t.  The four pyramid edges are Jn +- mu*Jt: every edge
+      // quantity (diagonal, residual, coupling) is a +-mu combination of these, so edges are never materialised.
       const V3 fr0 = ld3(sm.frame), fr1 = ld3(sm.frame + 3), fr2 = ld3(sm.frame + 6);
+      const float mu = G.mu;
       for (int c = 0; c < nc; c++) {
-        const V3 r = cr.pos[c] - com;
+        const V3 r = cb.pos[c] - com;
         V3 colb[6], colk[3];
         colb[0] = mk(1, 0, 0); colb[1] = mk(0, 1, 0); colb[2] = mk(0, 0, 1);
 #pragma unroll
@@ -616,47 +650,62 @@ __global__ void __launch_bounds__(NM_BLOCK) nm_step_kernel(const NmKernelArgs A)
 #pragma unroll
           for (int j = 0; j < 3; j++) { s1 = fmaf(Jk[j], xsk[j], s1); s2 = fmaf(Jk[j], awk[j], s2); }
           as[f] = s1; aw[f] = s2;
+#pragma unroll
+          for (int a = 0; a < 6; a++) cb.Y[c][f][a] = Y[f][a];
+#pragma unroll
+          for (int j = 0; j < 3; j++) cb.Z[c][f][j] = Z[f][j];
+        }
+        {
+          int gi_ = 0;
+#pragma unroll
+          for (int f = 0; f < 3; f++)
+#pragma unroll
+            for (int g = f; g < 3; g++) {
+              float t = 0.f;
+#pragma unroll
+              for (int a = 0; a < 6; a++) t = fmaf(Y[f][a], Y[g][a], t);
+#pragma unroll
+              for (int j = 0; j < 3; j++) t = fmaf(Z[f][j], Z[g][j], t);
+              cb.Gm[c][gi_++] = t;                          // 00 01 02 11 12 22
+            }
         }
         const float pos = cdist[c] - G.margin;
         const float imp = impedance(G, pos);
         const float R = fmaxf(G.rfac * (1.f - imp) / imp, NM_MINVAL);
-        cr.R[c] = R;
+        cb.R[c] = R;
         const float kd = G.K * imp * pos;
+        // b_edge = J_edge qacc_smooth - aref_edge,  aref_edge = -B (J_edge qvel) - K imp pos
+        const float be0 = fmaf(G.B, vb[0], as[0]) + kd, be1 = fmaf(G.B, vb[1], as[1]), be2 = fmaf(G.B, vb[2], as[2]);
+        cb.beta[c][0] = be0; cb.beta[c][1] = be1; cb.beta[c][2] = be2;
+        // warm start: edge forces implied by qacc_warmstart
+        const float ja0 = fmaf(G.B, vb[0], aw[0]) + kd, ja1 = fmaf(G.B, vb[1], aw[1]), ja2 = fmaf(G.B, vb[2], aw[2]);
+        const float rinv = 1.f / R;
 #pragma unroll
         for (int rr = 0; rr < 4; rr++) {
-          const int t = 1 + (rr >> 1);
-          const float sm_ = (rr & 1) ? -G.mu : G.mu;
-          float ad = R;
-#pragma unroll
-          for (int a = 0; a < 6; a++) { float y = fmaf(sm_, Y[t][a], Y[0][a]); cr.y[c][rr][a] = y; ad = fmaf(y, y, ad); }
-#pragma unroll
-          for (int j = 0; j < 3; j++) { float z = fmaf(sm_, Z[t][j], Z[0][j]); cr.z[c][rr][j] = z; ad = fmaf(z, z, ad); }
-          cr.ad[c][rr] = ad;
-          cr.adi[c][rr] = 1.f / ad;
-          const float aref = -G.B * fmaf(sm_, vb[t], vb[0]) - kd;
-          cr.b[c][rr] = fmaf(sm_, as[t], as[0]) - aref;
-          const float jar = fmaf(sm_, aw[t], aw[0]) - aref;       // warm start: forces implied by qacc_warmstart
-          cr.f[c][rr] = jar < 0.f ? -jar / R : 0.f;
+          const float sg = (rr & 1) ? -mu : mu;
+          const float jar = fmaf(sg, (rr >> 1) ? ja2 : ja1, ja0);
+          cb.f[c][rr] = jar < 0.f ? -jar * rinv : 0.f;
         }
       }
 
       // ============================================================== P9 warm start, PGS, noslip
+      // Dual state: u = G_S^-1 (base part of J^T f), replicated across the octet; wv = G_k^-1 (leg part), private.
       float u[6], wv[3];
 #pragma unroll
       for (int a = 0; a < 6; a++) u[a] = 0.f;
 #pragma unroll
       for (int j = 0; j < 3; j++) wv[j] = 0.f;
       float cl = 0.f;
-      for (int c = 0; c < nc; c++)
+      for (int c = 0; c < nc; c++) {
+        const float f0 = cb.f[c][0], f1 = cb.f[c][1], f2 = cb.f[c][2], f3 = cb.f[c][3];
+        const float c0 = (f0 + f1) + (f2 + f3), c1 = mu * (f0 - f1), c2 = mu * (f2 - f3);
 #pragma unroll
-        for (int rr = 0; rr < 4; rr++) {
-          float f = cr.f[c][rr];
+        for (int a = 0; a < 6; a++) u[a] = fmaf(cb.Y[c][0][a], c0, fmaf(cb.Y[c][1][a], c1, fmaf(cb.Y[c][2][a], c2, u[a])));
 #pragma unroll
-          for (int a = 0; a < 6; a++) u[a] = fmaf(cr.y[c][rr][a], f, u[a]);
-#pragma unroll
-          for (int j = 0; j < 3; j++) wv[j] = fmaf(cr.z[c][rr][j], f, wv[j]);
-          cl += f * fmaf(0.5f * cr.R[c], f, cr.b[c][rr]);
-        }
+        for (int j = 0; j < 3; j++) wv[j] = fmaf(cb.Z[c][0][j], c0, fmaf(cb.Z[c][1][j], c1, fmaf(cb.Z[c][2][j], c2, wv[j])));
+        const float hR = 0.5f * cb.R[c], b0 = cb.beta[c][0], b1 = mu * cb.beta[c][1], b2 = mu * cb.beta[c][2];
+        cl += f0 * fmaf(hR, f0, b0 + b1) + f1 * fmaf(hR, f1, b0 - b1) + f2 * fmaf(hR, f2, b0 + b2) + f3 * fmaf(hR, f3, b0 - b2);
+      }
       float uu = 0.f;
 #pragma unroll
       for (int a = 0; a < 6; a++) { u[a] = oct_sum(u[a]); uu = fmaf(u[a], u[a], uu); }
@@ -665,130 +714,124 @@ __global__ void __launch_bounds__(NM_BLOCK) nm_step_kernel(const NmKernelArgs A)
       if (cost > 0.f) {        // f = 0 is cheaper than the warm start
         for (int c = 0; c < nc; c++)
 #pragma unroll
-          for (int rr = 0; rr < 4; rr++) cr.f[c][rr] = 0.f;
+          for (int rr = 0; rr < 4; rr++) cb.f[c][rr] = 0.f;
 #pragma unroll
         for (int a = 0; a < 6; a++) u[a] = 0.f;
 #pragma unroll
         for (int j = 0; j < 3; j++) wv[j] = 0.f;
       } else dbg_warm = ncon_env > 0 ? 1 : 0;
 
-      // ---- PGS sweeps: rows in contact order (base geom first, then legs 1..6), Gauss-Seidel through u
+      // ---- sweeps: rows in contact order (base geom first, then legs 1..6), Gauss-Seidel through u.
+      // sweep 0..iterations-1: PGS on single edges (with R); then noslip on opposing edge pairs (without R, sum fixed).
+      const int npgs = sm.iterations, nsweep = sm.iterations + sm.noslip_iterations;
       bool active = ncon_env > 0;
-      for (int it = 0; it < sm.iterations; it++) {
-        if (!__any_sync(FULL, active)) break;
+      bool in_noslip = false;
+#pragma unroll 1
+      for (int sweep = 0; sweep <= nsweep; sweep++) {
+        if (sweep == npgs) {
+          // qacc after PGS -> next step's warm start (saved BEFORE noslip)
+          float tb[6], tk[3], y3[3];
+          bwd6(F.S, F.Si, u, tb);
+          bwd3(F.g, F.gi, wv, y3);
+#pragma unroll
+          for (int i = 0; i < 3; i++) {
+            float t = y3[i];
+#pragma unroll
+            for (int a = 0; a < 6; a++) t = fmaf(-F.E[i][a], tb[a], t);
+            tk[i] = t;
+          }
+          if (ncon_env > 0) {
+#pragma unroll
+            for (int i = 0; i < 6; i++) wsb[i] = xsb[i] + tb[i];
+#pragma unroll
+            for (int i = 0; i < 3; i++) wsk[i] = xsk[i] + tk[i];
+          }
+          active = ncon_env > 0;
+          in_noslip = true;
+        }
+        if (sweep == nsweep) break;
+        if (!__any_sync(FULL, active)) continue;
         float improvement = 0.f;
 #pragma unroll 1
-        for (int ph = 0; ph < 7; ph++) {
-          const int owner = ph == 0 ? 6 : ph - 1;
-          const bool mine = active && (l == owner) && nc > 0;
-          if (!__any_sync(FULL, mine)) continue;
-          if (mine) {
-            for (int c = 0; c < nc; c++)
+        for (unsigned pm = owner_mask; pm != 0u;) {
+          // phase order: lane 6 (base geom) first, then legs 0..5
+          const int owner = (pm & 0x40u) ? 6 : (__ffs(pm) - 1);
+          pm &= ~(1u << owner);
+          if (active && l == owner) {
+            for (int c = 0; c < nc; c++) {
+              float p0 = 0.f, p1 = 0.f, p2 = 0.f;        // J_contact . (current constraint acceleration)
 #pragma unroll
-              for (int rr = 0; rr < 4; rr++) {
-                float res = cr.b[c][rr];
+              for (int a = 0; a < 6; a++) { const float ua = u[a]; p0 = fmaf(cb.Y[c][0][a], ua, p0); p1 = fmaf(cb.Y[c][1][a], ua, p1); p2 = fmaf(cb.Y[c][2][a], ua, p2); }
 #pragma unroll
-                for (int a = 0; a < 6; a++) res = fmaf(cr.y[c][rr][a], u[a], res);
+              for (int j = 0; j < 3; j++) { const float wj = wv[j]; p0 = fmaf(cb.Z[c][0][j], wj, p0); p1 = fmaf(cb.Z[c][1][j], wj, p1); p2 = fmaf(cb.Z[c][2][j], wj, p2); }
+              const float g00 = cb.Gm[c][0], g01 = cb.Gm[c][1], g02 = cb.Gm[c][2], g11 = cb.Gm[c][3], g12 = cb.Gm[c][4], g22 = cb.Gm[c][5];
+              const float be0 = cb.beta[c][0], be1 = cb.beta[c][1], be2 = cb.beta[c][2];
+              float c0 = 0.f, c1 = 0.f, c2 = 0.f;
+              if (!in_noslip) {
+                const float R = cb.R[c];
 #pragma unroll
-                for (int j = 0; j < 3; j++) res = fmaf(cr.z[c][rr][j], wv[j], res);
-                const float old = cr.f[c][rr];
-                res = fmaf(cr.R[c], old, res);
-                float fnew = fmaxf(0.f, fmaf(-res, cr.adi[c][rr], old));
-                float delta = fnew - old;
-                float change = delta * fmaf(0.5f * delta, cr.ad[c][rr], res);
-                if (change > 1e-10f) { delta = 0.f; fnew = old; change = 0.f; }
-                improvement -= change;
-                cr.f[c][rr] = fnew;
+                for (int rr = 0; rr < 4; rr++) {
+                  const bool t2 = rr >> 1;
+                  const float sg = (rr & 1) ? -mu : mu;
+                  const float g0t = t2 ? g02 : g01, gtt = t2 ? g22 : g11, g1t = t2 ? g12 : g11, g2t = t2 ? g22 : g12;
+                  const float ad = R + fmaf(sg, fmaf(sg, gtt, 2.f * g0t), g00);
+                  const float old = cb.f[c][rr];
+                  const float res = fmaf(R, old, fmaf(sg, (t2 ? be2 : be1) + (t2 ? p2 : p1), be0 + p0));
+                  float fnew = fmaxf(0.f, old - res / ad);
+                  float delta = fnew - old;
+                  float change = delta * fmaf(0.5f * delta, ad, res);
+                  if (change > 1e-10f) { delta = 0.f; fnew = old; change = 0.f; }
+                  improvement -= change;
+                  cb.f[c][rr] = fnew;
+                  p0 = fmaf(delta, fmaf(sg, g0t, g00), p0); p1 = fmaf(delta, fmaf(sg, g1t, g01), p1); p2 = fmaf(delta, fmaf(sg, g2t, g02), p2);
+                  c0 += delta;
+                  if (t2) c2 = fmaf(sg, delta, c2); else c1 = fmaf(sg, delta, c1);
+                }
+              } else {
 #pragma unroll
-                for (int a = 0; a < 6; a++) u[a] = fmaf(cr.y[c][rr][a], delta, u[a]);
-#pragma unroll
-                for (int j = 0; j < 3; j++) wv[j] = fmaf(cr.z[c][rr][j], delta, wv[j]);
+                for (int pr = 0; pr < 2; pr++) {
+                  const bool t2 = pr;
+                  const float g0t = t2 ? g02 : g01, gtt = t2 ? g22 : g11, g1t = t2 ? g12 : g11, g2t = t2 ? g22 : g12;
+                  const float mg = mu * mu * gtt;
+                  const float a00 = fmaf(2.f * mu, g0t, g00) + mg, a11 = fmaf(-2.f * mu, g0t, g00) + mg, a01 = g00 - mg;
+                  const float bt = mu * ((t2 ? be2 : be1) + (t2 ? p2 : p1));
+                  const float res0 = (be0 + p0) + bt, res1 = (be0 + p0) - bt;
+                  const float o0 = cb.f[c][2 * pr], o1 = cb.f[c][2 * pr + 1];
+                  const float bc0 = res0 - a00 * o0 - a01 * o1, bc1 = res1 - a01 * o0 - a11 * o1;
+                  const float mid = 0.5f * (o0 + o1);
+                  const float K1 = a00 + a11 - 2.f * a01;
+                  const float K0 = mid * (a00 - a11) + bc0 - bc1;
+                  float f0, f1;
+                  if (K1 < NM_MINVAL) { f0 = mid; f1 = mid; }
+                  else {
+                    float x = -K0 / K1;
+                    if (x < -mid) { f0 = 0.f; f1 = 2.f * mid; }
+                    else if (x > mid) { f0 = 2.f * mid; f1 = 0.f; }
+                    else { f0 = mid + x; f1 = mid - x; }
+                  }
+                  float d0 = f0 - o0, d1 = f1 - o1;
+                  float change = 0.5f * (d0 * (a00 * d0 + a01 * d1) + d1 * (a01 * d0 + a11 * d1)) + d0 * res0 + d1 * res1;
+                  if (change > 1e-10f) { f0 = o0; f1 = o1; d0 = 0.f; d1 = 0.f; change = 0.f; }
+                  improvement -= change;
+                  cb.f[c][2 * pr] = f0; cb.f[c][2 * pr + 1] = f1;
+                  const float ds = d0 + d1, dd = mu * (d0 - d1);
+                  p0 = fmaf(ds, g00, fmaf(dd, g0t, p0)); p1 = fmaf(ds, g01, fmaf(dd, g1t, p1)); p2 = fmaf(ds, g02, fmaf(dd, g2t, p2));
+                  c0 += ds;
+                  if (t2) c2 += dd; else c1 += dd;
+                }
               }
+#pragma unroll
+              for (int a = 0; a < 6; a++) u[a] = fmaf(cb.Y[c][0][a], c0, fmaf(cb.Y[c][1][a], c1, fmaf(cb.Y[c][2][a], c2, u[a])));
+#pragma unroll
+              for (int j = 0; j < 3; j++) wv[j] = fmaf(cb.Z[c][0][j], c0, fmaf(cb.Z[c][1][j], c1, fmaf(cb.Z[c][2][j], c2, wv[j])));
+            }
           }
 #pragma unroll
           for (int a = 0; a < 6; a++) u[a] = oct_bcast(u[a], obase | owner);
         }
         improvement = oct_sum(improvement);
-        if (active) dbg_pgs++;
-        if (improvement * sm.solver_scale < sm.tolerance) active = false;
-      }
-      // qacc after PGS -> next step's warm start (saved BEFORE noslip)
-      {
-        float tb[6], tk[3];
-        bwd6(F.S, F.Si, u, tb);
-        float y3[3];
-        bwd3(F.g, F.gi, wv, y3);
-#pragma unroll
-        for (int i = 0; i < 3; i++) {
-          float t = y3[i];
-#pragma unroll
-          for (int a = 0; a < 6; a++) t = fmaf(-F.E[i][a], tb[a], t);
-          tk[i] = t;
-        }
-        if (ncon_env > 0) {
-#pragma unroll
-          for (int i = 0; i < 6; i++) wsb[i] = xsb[i] + tb[i];
-#pragma unroll
-          for (int i = 0; i < 3; i++) wsk[i] = xsk[i] + tk[i];
-        }
-      }
-      // ---- noslip: opposing pyramid edges re-solved without R, their sum kept fixed
-      active = ncon_env > 0;
-      for (int it = 0; it < sm.noslip_iterations; it++) {
-        if (!__any_sync(FULL, active)) break;
-        float improvement = 0.f;
-#pragma unroll 1
-        for (int ph = 0; ph < 7; ph++) {
-          const int owner = ph == 0 ? 6 : ph - 1;
-          const bool mine = active && (l == owner) && nc > 0;
-          if (!__any_sync(FULL, mine)) continue;
-          if (mine) {
-            for (int c = 0; c < nc; c++)
-#pragma unroll
-              for (int pr = 0; pr < 4; pr += 2) {
-                float res0 = cr.b[c][pr], res1 = cr.b[c][pr + 1], a00 = 0.f, a11 = 0.f, a01 = 0.f;
-#pragma unroll
-                for (int a = 0; a < 6; a++) {
-                  float y0 = cr.y[c][pr][a], y1 = cr.y[c][pr + 1][a];
-                  res0 = fmaf(y0, u[a], res0); res1 = fmaf(y1, u[a], res1);
-                  a00 = fmaf(y0, y0, a00); a11 = fmaf(y1, y1, a11); a01 = fmaf(y0, y1, a01);
-                }
-#pragma unroll
-                for (int j = 0; j < 3; j++) {
-                  float z0 = cr.z[c][pr][j], z1 = cr.z[c][pr + 1][j];
-                  res0 = fmaf(z0, wv[j], res0); res1 = fmaf(z1, wv[j], res1);
-                  a00 = fmaf(z0, z0, a00); a11 = fmaf(z1, z1, a11); a01 = fmaf(z0, z1, a01);
-                }
-                const float o0 = cr.f[c][pr], o1 = cr.f[c][pr + 1];
-                const float bc0 = res0 - a00 * o0 - a01 * o1, bc1 = res1 - a01 * o0 - a11 * o1;
-                const float mid = 0.5f * (o0 + o1);
-                const float K1 = a00 + a11 - 2.f * a01;
-                const float K0 = mid * (a00 - a11) + bc0 - bc1;
-                float f0, f1;
-                if (K1 < NM_MINVAL) { f0 = mid; f1 = mid; }
-                else {
-                  float x = -K0 / K1;
-                  if (x < -mid) { f0 = 0.f; f1 = 2.f * mid; }
-                  else if (x > mid) { f0 = 2.f * mid; f1 = 0.f; }
-                  else { f0 = mid + x; f1 = mid - x; }
-                }
-                float d0 = f0 - o0, d1 = f1 - o1;
-                float change = 0.5f * (d0 * (a00 * d0 + a01 * d1) + d1 * (a01 * d0 + a11 * d1)) + d0 * res0 + d1 * res1;
-                if (change > 1e-10f) { f0 = o0; f1 = o1; d0 = 0.f; d1 = 0.f; change = 0.f; }
-                improvement -= change;
-                cr.f[c][pr] = f0; cr.f[c][pr + 1] = f1;
-#pragma unroll
-                for (int a = 0; a < 6; a++) u[a] = fmaf(cr.y[c][pr][a], d0, fmaf(cr.y[c][pr + 1][a], d1, u[a]));
-#pragma unroll
-                for (int j = 0; j < 3; j++) wv[j] = fmaf(cr.z[c][pr][j], d0, fmaf(cr.z[c][pr + 1][j], d1, wv[j]));
-              }
-          }
-#pragma unroll
-          for (int a = 0; a < 6; a++) u[a] = oct_bcast(u[a], obase | owner);
-        }
-        improvement = oct_sum(improvement);
-        if (active) dbg_noslip++;
-        if (improvement * sm.solver_scale < sm.noslip_tolerance) active = false;
+        if (active) { if (in_noslip) dbg_noslip++; else dbg_pgs++; }
+        if (improvement * sm.solver_scale < (in_noslip ? sm.noslip_tolerance : sm.tolerance)) active = false;
       }
       // final constraint acceleration x = M^-1 J^T f
       {
@@ -811,11 +854,11 @@ __global__ void __launch_bounds__(NM_BLOCK) nm_step_kernel(const NmKernelArgs A)
       }
       // ============================================================== P10 touch sensors (sum of pyramid-edge forces)
       for (int c = 0; c < nc; c++) {
-        float fn = cr.f[c][0] + cr.f[c][1] + cr.f[c][2] + cr.f[c][3];
+        float fn = cb.f[c][0] + cb.f[c][1] + cb.f[c][2] + cb.f[c][3];
         if (fn <= 0.f) continue;
         const V3 ray = mk(-pn.x, -pn.y, -pn.z);          // normal points plane -> body; sensor is on the body
-        if (L.site_r[0] >= 0.f && ray_sphere(pg + mul(Xg, ld3(L.site_pos[0])), L.site_r[0], cr.pos[c], ray) >= 0.f) fn_slot0 += fn;
-        if (L.site_r[1] >= 0.f && ray_sphere(pg + mul(Xg, ld3(L.site_pos[1])), L.site_r[1], cr.pos[c], ray) >= 0.f) fn_slot1 += fn;
+        if (L.site_r[0] >= 0.f && ray_sphere(pg + mul(Xg, ld3(L.site_pos[0])), L.site_r[0], cb.pos[c], ray) >= 0.f) fn_slot0 += fn;
+        if (L.site_r[1] >= 0.f && ray_sphere(pg + mul(Xg, ld3(L.site_pos[1])), L.site_r[1], cb.pos[c], ray) >= 0.f) fn_slot1 += fn;
       }
     }
     sens0 = fn_slot0; sens1 = fn_slot1;
@@ -901,6 +944,7 @@ __global__ void __launch_bounds__(NM_BLOCK) nm_step_kernel(const NmKernelArgs A)
   // ==================================================================== physics-only mode: write state and leave
   if (!ENV) {
     if (valid) {
+      if (G.has) A.hull_hint[(size_t)env * NM_OCT + l] = hint;
       float* qpo = A.qpos + (size_t)env * 25;
       float* qvo = A.qvel + (size_t)env * 24;
       float* qwo = A.warm + (size_t)env * 24;
@@ -1040,9 +1084,9 @@ __global__ void __launch_bounds__(NM_BLOCK) nm_step_kernel(const NmKernelArgs A)
 #pragma unroll
     for (int k = 0; k < 18; k++) {
       float s = A.episode_sums[(size_t)env * 18 + k];
-      if (c.rew_scale[k] != 0.f) atomicAdd(A.episode_acc + k, s);
+      if (c.rew_scale[k] != 0.f) atomicAdd(A.acc_cur + k, s);
     }
-    atomicAdd(A.episode_acc + 18, 1.f);
+    atomicAdd(A.acc_cur + 18, 1.f);
   }
 
   // ------------------------------------------------------------------ write back
@@ -1052,7 +1096,7 @@ __global__ void __launch_bounds__(NM_BLOCK) nm_step_kernel(const NmKernelArgs A)
     float* qwo = A.warm + (size_t)env * 24;
     float* ob = A.obs + (size_t)env * 66;
     const float co = c.clip_obs;
-    unsigned nz[4];
+    if (G.has) A.hull_hint[(size_t)env * NM_OCT + l] = hint;
     if (leg) {
 #pragma unroll
       for (int j = 0; j < 3; j++) {
@@ -1064,13 +1108,10 @@ __global__ void __launch_bounds__(NM_BLOCK) nm_step_kernel(const NmKernelArgs A)
         A.dof_vel[(size_t)env * 18 + jo + j] = thd[j];
         float o0 = (th[j] - c.default_pos[jo + j]) * c.obs_dof_pos, o1 = thd[j] * c.obs_dof_vel, o2 = act[j];
         if (c.add_noise) {
-          int k0 = 12 + jo + j, k1 = 30 + jo + j, k2 = 48 + jo + j;
-          philox4x32((unsigned)A.seed, (unsigned)genv, (unsigned)A.step_counter, (unsigned)((unsigned long long)A.step_counter >> 32), 2 + (k0 >> 2), (unsigned)(A.seed >> 32), nz);
-          o0 = fmaf(2.f * u01(nz[k0 & 3]) - 1.f, c.noise_vec[k0], o0);
-          philox4x32((unsigned)A.seed, (unsigned)genv, (unsigned)A.step_counter, (unsigned)((unsigned long long)A.step_counter >> 32), 2 + (k1 >> 2), (unsigned)(A.seed >> 32), nz);
-          o1 = fmaf(2.f * u01(nz[k1 & 3]) - 1.f, c.noise_vec[k1], o1);
-          philox4x32((unsigned)A.seed, (unsigned)genv, (unsigned)A.step_counter, (unsigned)((unsigned long long)A.step_counter >> 32), 2 + (k2 >> 2), (unsigned)(A.seed >> 32), nz);
-          o2 = fmaf(2.f * u01(nz[k2 & 3]) - 1.f, c.noise_vec[k2], o2);
+          const int k0 = 12 + jo + j, k1 = 30 + jo + j, k2 = 48 + jo + j;
+          o0 = fmaf(obs_noise(A.seed, genv, A.step_counter, k0), c.noise_vec[k0], o0);
+          o1 = fmaf(obs_noise(A.seed, genv, A.step_counter, k1), c.noise_vec[k1], o1);
+          o2 = fmaf(obs_noise(A.seed, genv, A.step_counter, k2), c.noise_vec[k2], o2);
         }
         ob[12 + jo + j] = fminf(fmaxf(o0, -co), co);
         ob[30 + jo + j] = fminf(fmaxf(o1, -co), co);
@@ -1086,10 +1127,7 @@ __global__ void __launch_bounds__(NM_BLOCK) nm_step_kernel(const NmKernelArgs A)
 #pragma unroll
       for (int k = 0; k < 12; k++) {
         float v = o[k];
-        if (c.add_noise) {
-          philox4x32((unsigned)A.seed, (unsigned)genv, (unsigned)A.step_counter, (unsigned)((unsigned long long)A.step_counter >> 32), 2 + (k >> 2), (unsigned)(A.seed >> 32), nz);
-          v = fmaf(2.f * u01(nz[k & 3]) - 1.f, c.noise_vec[k], v);
-        }
+        if (c.add_noise) v = fmaf(obs_noise(A.seed, genv, A.step_counter, k), c.noise_vec[k], v);
         ob[k] = fminf(fmaxf(v, -co), co);
       }
     }
@@ -1134,6 +1172,27 @@ __global__ void nm_reset_kernel(const NmKernelArgs A, const long long* ids, int 
   for (int k = 0; k < 18; k++) A.episode_sums[e * 18 + k] = 0.f;
   A.episode_length[e] = 0;
   A.done[e] = 1;
+}
+
+// ================================================================================================ extras kernel
+// Second (tiny) launch of every env step: publishes this step's episode accumulators (episode_acc), and -- only when
+// at least one env reset, which is how the reference behaves (env.py:344,:363-371, quirk Q10) -- refreshes the
+// mean episode sums / episode_length_s and latches time_outs.  Also clears the accumulator half the NEXT step
+// will add into, so no memset is needed between steps.
+__global__ void nm_finalize_kernel(const NmKernelArgs A) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const float cnt = A.acc_cur[18];
+  if (i < 19) {
+    const float v = A.acc_cur[i];
+    A.episode_acc[i] = v;
+    A.acc_next[i] = 0.f;
+    if (i < 18 && cnt > 0.f) A.ep_means[i] = v / cnt * A.cfg->inv_episode_length_s;
+  }
+  if (cnt > 0.f && i < A.num_envs) A.time_outs_latched[i] = A.time_outs[i];
+}
+
+void nm_launch_finalize(const NmKernelArgs& a, void* stream) {
+  nm_finalize_kernel<<<(a.num_envs + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
 }
 
 void nm_launch_step(const NmKernelArgs& a, bool env_mode, void* stream) {

@@ -94,9 +94,7 @@ class NightmareV3Env:
         self.dof_pos, self.dof_vel = b.dof_pos, b.dof_vel
         self.feet_air_time = b.feet_air_time
         self.episode_sums = {k: b.episode_sums[:, REWARD_TERMS.index(k)] for k in keys}
-        self._key_idx = torch.tensor([REWARD_TERMS.index(k) for k in keys], device=self.device)
-        self._ep_means = torch.zeros(len(REWARD_TERMS), device=self.device)
-        self._time_outs_latched = torch.zeros(self.num_envs, device=self.device)
+        self._extras_keys = [("rew_" + k, REWARD_TERMS.index(k)) for k in keys]
         self._rec = None
         if self.cfg.viewer.record_states:
             self._rec = _StateRecorder(self, self.log_dir)
@@ -126,17 +124,13 @@ class NightmareV3Env:
         return self.obs_buf, None, self.rew_buf, self.reset_buf, self.extras
 
     def _refresh_extras(self):
-        # extras are only refreshed on steps where at least one env reset (reference quirk Q10, :344,:363-371);
-        # evaluated on the device, without a host sync
-        acc = self._batch.episode_acc
-        cnt = acc[-1]
-        has = cnt > 0
-        means = acc[:-1] / torch.clamp(cnt, min=1.0) / self.max_episode_length_s
-        self._ep_means = torch.where(has, means, self._ep_means)
-        self.extras["episode"] = {"rew_" + k: self._ep_means[REWARD_TERMS.index(k)] for k in self._sum_keys}
+        # extras are only refreshed on steps where at least one env reset (reference quirk Q10, :344,:363-371).
+        # The latching happens on the device (nm_finalize_kernel, second launch of nm_step): no host sync, and
+        # one small clone here so that dicts stored by the runner keep the values of THEIR step.
+        means = self._batch.ep_means.clone().unbind(0)
+        self.extras["episode"] = {name: means[i] for name, i in self._extras_keys}
         if self.cfg.env.send_timeouts:
-            self._time_outs_latched = torch.where(has, self._batch.time_outs, self._time_outs_latched)
-            self.extras["time_outs"] = self._time_outs_latched
+            self.extras["time_outs"] = self._batch.time_outs_latched
 
     def get_observations(self):
         return self.obs_buf.clone() if self._copy else self.obs_buf
@@ -150,13 +144,11 @@ class NightmareV3Env:
         ids = torch.as_tensor(np.asarray(env_ids) if not torch.is_tensor(env_ids) else env_ids, device=self.device).to(torch.int64).flatten()
         if ids.numel() == 0:
             return
-        sums = self._batch.episode_sums[ids].mean(dim=0) / self.max_episode_length_s
-        self._ep_means = sums.clone()
-        self._batch.reset_idx(ids, self.common_step_counter)
-        self.extras["episode"] = {"rew_" + k: self._ep_means[REWARD_TERMS.index(k)] for k in self._sum_keys}
-        if self.cfg.env.send_timeouts:
-            self._time_outs_latched = self._batch.time_outs.clone()
-            self.extras["time_outs"] = self._time_outs_latched
+        b = self._batch
+        b.ep_means.copy_(b.episode_sums[ids].mean(dim=0) / self.max_episode_length_s)
+        b.reset_idx(ids, self.common_step_counter)
+        b.time_outs_latched.copy_(b.time_outs)
+        self._refresh_extras()
 
     def reset(self):
         """Reset all robots, then take one zero-action step (:392-396)."""

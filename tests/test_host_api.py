@@ -24,7 +24,7 @@ def test_struct_layouts_agree():
     n_i32, n_f64 = 8, 4 + 18 + 4 + 2 + 2 + 3 + 3 + 1 + 18 + 66
     assert ctypes.sizeof(EnvCfgStruct) == 4 * n_i32 + 8 * n_f64
     from nightmare_rl_b200 import _lib
-    assert ctypes.sizeof(_lib.NmBuffers) == 18 * ctypes.sizeof(ctypes.c_void_p)
+    assert ctypes.sizeof(_lib.NmBuffers) == 20 * ctypes.sizeof(ctypes.c_void_p)      # pointer fields of nm_buffers
 
 
 def test_model_through_abi(compiled_model):
