@@ -37,7 +37,9 @@ UNIT = "env-steps/s"
 # restated pipeline (2 substeps).  The FLOP figure is the executed FP32 count per env-step measured with
 # ncu on this kernel (profiles/), not an estimate of MuJoCo's own count.
 BYTES_PER_ENV_STEP = 1464
-FLOPS_PER_ENV_STEP = 80_000
+FLOPS_PER_ENV_STEP = 71_800
+# dram__bytes_read.sum + dram__bytes_write.sum of nm_step_kernel<true> per 4096-env launch (ncu --set full, profiles/r01_notes.md)
+NCU_DRAM_BYTES_PER_LAUNCH_4096 = 4_588_288
 
 
 def _workload(envs_per_gpu, decimation=2):
@@ -56,7 +58,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                                           "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
@@ -276,7 +278,8 @@ def run_ours(args):
             "clocks": clocks,
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": E * 18 * 4, "d2h_bytes_per_step": E * (66 * 4 + 4 + 8), "steps": Ke},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak, "traffic": None,
+            "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak, "traffic": NCU_DRAM_BYTES_PER_LAUNCH_4096 if E == 4096 else None,
+                         "algorithmic_bytes": BYTES_PER_ENV_STEP * E,
                          "peak_source": which, "kernel": "nm_step_kernel<true> (+ the 2 us nm_finalize_kernel inside the same event pair)", "kernel_ms": kern_ms,
                          "note": "kernel is FP32-pipe/latency bound, not HBM bound; see roofline_fp32"},
             "roofline_fp32": {"bound": "fp32", "achieved": tfs, "peak": fp32_peak, "unit": "TFLOP/s", "frac": tfs / fp32_peak if fp32_peak > 0 else None,

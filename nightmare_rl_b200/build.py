@@ -7,7 +7,8 @@ import subprocess
 
 PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
-LIB_PATH = os.path.join(PKG, "libnightmare_b200.so")
+# NIGHTMARE_B200_LIB lets experiments load an alternative build of the same ABI (tools/quick_bench.py)
+LIB_PATH = os.environ.get("NIGHTMARE_B200_LIB") or os.path.join(PKG, "libnightmare_b200.so")
 SOURCES = ["nm_kernels.cu", "nm_abi.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--use_fast_math=false"]

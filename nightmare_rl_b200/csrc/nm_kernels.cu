@@ -312,12 +312,15 @@ __device__ __forceinline__ void resample_commands(const NmDevCfg& c, unsigned lo
   cmd[0] = cx * keep; cmd[1] = cy * keep; cmd[2] = cw;
 }
 
-// per-lane contact blocks in contact space (local memory, L1-resident): 42 floats per contact
+// per-lane contact blocks (local memory, L1-resident): 49 floats per contact.  Only the three whitened
+// contact-frame rows are stored; the four pyramid edges Jn +- mu*Jt are formed on the fly from them.
 struct ConBlk {
   float Y[NM_MAXC][3][6];   // whitened base-space image of the contact-frame rows (normal, tangent 1, tangent 2)
   float Z[NM_MAXC][3][3];   // whitened leg-space image
-  float Gm[NM_MAXC][6];     // Gram matrix of the three whitened rows: 00 01 02 11 12 22
-  float beta[NM_MAXC][3];   // J qacc_smooth - aref, split per frame axis
+  float b[NM_MAXC][4];      // J_edge qacc_smooth - aref_edge
+  float ad[NM_MAXC][4];     // |edge|^2  (diagonal of A = J M^-1 J^T)
+  float adi[NM_MAXC][4];    // 1 / (|edge|^2 + R)
+  float a01[NM_MAXC][2];    // edge(2t) . edge(2t+1): off-diagonal of the opposing pair (noslip)
   float f[NM_MAXC][4];      // pyramid-edge forces
   float R[NM_MAXC];
   V3 pos[NM_MAXC];
@@ -329,7 +332,10 @@ enum { RW_ACTION_RATE = 0, RW_ANG_VEL_XY, RW_BASE_HEIGHT, RW_BODY_CONTACT_FORCES
 
 // ================================================================================================ the step kernel
 template <bool ENV>
-__global__ void __launch_bounds__(NM_BLOCK) nm_step_kernel(const NmKernelArgs A) {
+#ifndef NM_MIN_BLOCKS
+#define NM_MIN_BLOCKS 4        // CTAs of 64 threads per SM the register allocation must allow (4 -> 255 regs, 8 -> 128 regs)
+#endif
+__global__ void __launch_bounds__(NM_BLOCK, NM_MIN_BLOCKS) nm_step_kernel(const NmKernelArgs A) {
   __shared__ NmDevModel sm;
   __shared__ NmDevCfg scfg;
   {
@@ -655,36 +661,36 @@ __global__ void __launch_bounds__(NM_BLOCK) nm_step_kernel(const NmKernelArgs A)
 #pragma unroll
           for (int j = 0; j < 3; j++) cb.Z[c][f][j] = Z[f][j];
         }
-        {
-          int gi_ = 0;
-#pragma unroll
-          for (int f = 0; f < 3; f++)
-#pragma unroll
-            for (int g = f; g < 3; g++) {
-              float t = 0.f;
-#pragma unroll
-              for (int a = 0; a < 6; a++) t = fmaf(Y[f][a], Y[g][a], t);
-#pragma unroll
-              for (int j = 0; j < 3; j++) t = fmaf(Z[f][j], Z[g][j], t);
-              cb.Gm[c][gi_++] = t;                          // 00 01 02 11 12 22
-            }
-        }
         const float pos = cdist[c] - G.margin;
         const float imp = impedance(G, pos);
         const float R = fmaxf(G.rfac * (1.f - imp) / imp, NM_MINVAL);
         cb.R[c] = R;
         const float kd = G.K * imp * pos;
-        // b_edge = J_edge qacc_smooth - aref_edge,  aref_edge = -B (J_edge qvel) - K imp pos
-        const float be0 = fmaf(G.B, vb[0], as[0]) + kd, be1 = fmaf(G.B, vb[1], as[1]), be2 = fmaf(G.B, vb[2], as[2]);
-        cb.beta[c][0] = be0; cb.beta[c][1] = be1; cb.beta[c][2] = be2;
-        // warm start: edge forces implied by qacc_warmstart
-        const float ja0 = fmaf(G.B, vb[0], aw[0]) + kd, ja1 = fmaf(G.B, vb[1], aw[1]), ja2 = fmaf(G.B, vb[2], aw[2]);
         const float rinv = 1.f / R;
 #pragma unroll
-        for (int rr = 0; rr < 4; rr++) {
-          const float sg = (rr & 1) ? -mu : mu;
-          const float jar = fmaf(sg, (rr >> 1) ? ja2 : ja1, ja0);
-          cb.f[c][rr] = jar < 0.f ? -jar * rinv : 0.f;
+        for (int t = 0; t < 2; t++) {
+          float a00 = 0.f, a11 = 0.f, a01 = 0.f;
+#pragma unroll
+          for (int a = 0; a < 6; a++) {
+            const float y0 = fmaf(mu, Y[1 + t][a], Y[0][a]), y1 = fmaf(-mu, Y[1 + t][a], Y[0][a]);
+            a00 = fmaf(y0, y0, a00); a11 = fmaf(y1, y1, a11); a01 = fmaf(y0, y1, a01);
+          }
+#pragma unroll
+          for (int j = 0; j < 3; j++) {
+            const float z0 = fmaf(mu, Z[1 + t][j], Z[0][j]), z1 = fmaf(-mu, Z[1 + t][j], Z[0][j]);
+            a00 = fmaf(z0, z0, a00); a11 = fmaf(z1, z1, a11); a01 = fmaf(z0, z1, a01);
+          }
+          cb.ad[c][2 * t] = a00; cb.ad[c][2 * t + 1] = a11;
+          cb.adi[c][2 * t] = 1.f / (a00 + R); cb.adi[c][2 * t + 1] = 1.f / (a11 + R);
+          cb.a01[c][t] = a01;
+#pragma unroll
+          for (int e = 0; e < 2; e++) {
+            const float sg = e ? -mu : mu;
+            const float aref = -G.B * fmaf(sg, vb[1 + t], vb[0]) - kd;
+            cb.b[c][2 * t + e] = fmaf(sg, as[1 + t], as[0]) - aref;
+            const float jar = fmaf(sg, aw[1 + t], aw[0]) - aref;     // warm start: edge forces implied by qacc_warmstart
+            cb.f[c][2 * t + e] = jar < 0.f ? -jar * rinv : 0.f;
+          }
         }
       }
 
@@ -703,8 +709,8 @@ __global__ void __launch_bounds__(NM_BLOCK) nm_step_kernel(const NmKernelArgs A)
         for (int a = 0; a < 6; a++) u[a] = fmaf(cb.Y[c][0][a], c0, fmaf(cb.Y[c][1][a], c1, fmaf(cb.Y[c][2][a], c2, u[a])));
 #pragma unroll
         for (int j = 0; j < 3; j++) wv[j] = fmaf(cb.Z[c][0][j], c0, fmaf(cb.Z[c][1][j], c1, fmaf(cb.Z[c][2][j], c2, wv[j])));
-        const float hR = 0.5f * cb.R[c], b0 = cb.beta[c][0], b1 = mu * cb.beta[c][1], b2 = mu * cb.beta[c][2];
-        cl += f0 * fmaf(hR, f0, b0 + b1) + f1 * fmaf(hR, f1, b0 - b1) + f2 * fmaf(hR, f2, b0 + b2) + f3 * fmaf(hR, f3, b0 - b2);
+        const float hR = 0.5f * cb.R[c];
+        cl += f0 * fmaf(hR, f0, cb.b[c][0]) + f1 * fmaf(hR, f1, cb.b[c][1]) + f2 * fmaf(hR, f2, cb.b[c][2]) + f3 * fmaf(hR, f3, cb.b[c][3]);
       }
       float uu = 0.f;
 #pragma unroll
@@ -759,44 +765,66 @@ __global__ void __launch_bounds__(NM_BLOCK) nm_step_kernel(const NmKernelArgs A)
           pm &= ~(1u << owner);
           if (active && l == owner) {
             for (int c = 0; c < nc; c++) {
-              float p0 = 0.f, p1 = 0.f, p2 = 0.f;        // J_contact . (current constraint acceleration)
+              float Yc[3][6], Zc[3][3];
 #pragma unroll
-              for (int a = 0; a < 6; a++) { const float ua = u[a]; p0 = fmaf(cb.Y[c][0][a], ua, p0); p1 = fmaf(cb.Y[c][1][a], ua, p1); p2 = fmaf(cb.Y[c][2][a], ua, p2); }
+              for (int f = 0; f < 3; f++) {
 #pragma unroll
-              for (int j = 0; j < 3; j++) { const float wj = wv[j]; p0 = fmaf(cb.Z[c][0][j], wj, p0); p1 = fmaf(cb.Z[c][1][j], wj, p1); p2 = fmaf(cb.Z[c][2][j], wj, p2); }
-              const float g00 = cb.Gm[c][0], g01 = cb.Gm[c][1], g02 = cb.Gm[c][2], g11 = cb.Gm[c][3], g12 = cb.Gm[c][4], g22 = cb.Gm[c][5];
-              const float be0 = cb.beta[c][0], be1 = cb.beta[c][1], be2 = cb.beta[c][2];
-              float c0 = 0.f, c1 = 0.f, c2 = 0.f;
-              if (!in_noslip) {
-                const float R = cb.R[c];
+                for (int a = 0; a < 6; a++) Yc[f][a] = cb.Y[c][f][a];
 #pragma unroll
-                for (int rr = 0; rr < 4; rr++) {
-                  const bool t2 = rr >> 1;
-                  const float sg = (rr & 1) ? -mu : mu;
-                  const float g0t = t2 ? g02 : g01, gtt = t2 ? g22 : g11, g1t = t2 ? g12 : g11, g2t = t2 ? g22 : g12;
-                  const float ad = R + fmaf(sg, fmaf(sg, gtt, 2.f * g0t), g00);
-                  const float old = cb.f[c][rr];
-                  const float res = fmaf(R, old, fmaf(sg, (t2 ? be2 : be1) + (t2 ? p2 : p1), be0 + p0));
-                  float fnew = fmaxf(0.f, old - res / ad);
-                  float delta = fnew - old;
-                  float change = delta * fmaf(0.5f * delta, ad, res);
-                  if (change > 1e-10f) { delta = 0.f; fnew = old; change = 0.f; }
+                for (int j = 0; j < 3; j++) Zc[f][j] = cb.Z[c][f][j];
+              }
+              const float R = cb.R[c];
+#pragma unroll
+              for (int t = 0; t < 2; t++) {
+                float y0[6], y1[6], z0[3], z1[3];               // the opposing edge pair Jn +- mu*Jt of tangent t
+#pragma unroll
+                for (int a = 0; a < 6; a++) { y0[a] = fmaf(mu, Yc[1 + t][a], Yc[0][a]); y1[a] = fmaf(-mu, Yc[1 + t][a], Yc[0][a]); }
+#pragma unroll
+                for (int j = 0; j < 3; j++) { z0[j] = fmaf(mu, Zc[1 + t][j], Zc[0][j]); z1[j] = fmaf(-mu, Zc[1 + t][j], Zc[0][j]); }
+                const float o0 = cb.f[c][2 * t], o1 = cb.f[c][2 * t + 1];
+                float d0, d1;
+                if (!in_noslip) {
+                  // PGS: the two edges one after the other (Gauss-Seidel), each with its regulariser R
+                  float res = cb.b[c][2 * t];
+#pragma unroll
+                  for (int a = 0; a < 6; a++) res = fmaf(y0[a], u[a], res);
+#pragma unroll
+                  for (int j = 0; j < 3; j++) res = fmaf(z0[j], wv[j], res);
+                  res = fmaf(R, o0, res);
+                  float fnew = fmaxf(0.f, fmaf(-res, cb.adi[c][2 * t], o0));
+                  d0 = fnew - o0;
+                  float change = d0 * fmaf(0.5f * d0, cb.ad[c][2 * t] + R, res);
+                  if (change > 1e-10f) { d0 = 0.f; fnew = o0; change = 0.f; }
                   improvement -= change;
-                  cb.f[c][rr] = fnew;
-                  p0 = fmaf(delta, fmaf(sg, g0t, g00), p0); p1 = fmaf(delta, fmaf(sg, g1t, g01), p1); p2 = fmaf(delta, fmaf(sg, g2t, g02), p2);
-                  c0 += delta;
-                  if (t2) c2 = fmaf(sg, delta, c2); else c1 = fmaf(sg, delta, c1);
-                }
-              } else {
+                  cb.f[c][2 * t] = fnew;
 #pragma unroll
-                for (int pr = 0; pr < 2; pr++) {
-                  const bool t2 = pr;
-                  const float g0t = t2 ? g02 : g01, gtt = t2 ? g22 : g11, g1t = t2 ? g12 : g11, g2t = t2 ? g22 : g12;
-                  const float mg = mu * mu * gtt;
-                  const float a00 = fmaf(2.f * mu, g0t, g00) + mg, a11 = fmaf(-2.f * mu, g0t, g00) + mg, a01 = g00 - mg;
-                  const float bt = mu * ((t2 ? be2 : be1) + (t2 ? p2 : p1));
-                  const float res0 = (be0 + p0) + bt, res1 = (be0 + p0) - bt;
-                  const float o0 = cb.f[c][2 * pr], o1 = cb.f[c][2 * pr + 1];
+                  for (int a = 0; a < 6; a++) u[a] = fmaf(y0[a], d0, u[a]);
+#pragma unroll
+                  for (int j = 0; j < 3; j++) wv[j] = fmaf(z0[j], d0, wv[j]);
+                  res = cb.b[c][2 * t + 1];
+#pragma unroll
+                  for (int a = 0; a < 6; a++) res = fmaf(y1[a], u[a], res);
+#pragma unroll
+                  for (int j = 0; j < 3; j++) res = fmaf(z1[j], wv[j], res);
+                  res = fmaf(R, o1, res);
+                  fnew = fmaxf(0.f, fmaf(-res, cb.adi[c][2 * t + 1], o1));
+                  d1 = fnew - o1;
+                  change = d1 * fmaf(0.5f * d1, cb.ad[c][2 * t + 1] + R, res);
+                  if (change > 1e-10f) { d1 = 0.f; fnew = o1; change = 0.f; }
+                  improvement -= change;
+                  cb.f[c][2 * t + 1] = fnew;
+#pragma unroll
+                  for (int a = 0; a < 6; a++) u[a] = fmaf(y1[a], d1, u[a]);
+#pragma unroll
+                  for (int j = 0; j < 3; j++) wv[j] = fmaf(z1[j], d1, wv[j]);
+                } else {
+                  // noslip: the pair re-solved jointly without R, its sum kept fixed
+                  float res0 = cb.b[c][2 * t], res1 = cb.b[c][2 * t + 1];
+#pragma unroll
+                  for (int a = 0; a < 6; a++) { res0 = fmaf(y0[a], u[a], res0); res1 = fmaf(y1[a], u[a], res1); }
+#pragma unroll
+                  for (int j = 0; j < 3; j++) { res0 = fmaf(z0[j], wv[j], res0); res1 = fmaf(z1[j], wv[j], res1); }
+                  const float a00 = cb.ad[c][2 * t], a11 = cb.ad[c][2 * t + 1], a01 = cb.a01[c][t];
                   const float bc0 = res0 - a00 * o0 - a01 * o1, bc1 = res1 - a01 * o0 - a11 * o1;
                   const float mid = 0.5f * (o0 + o1);
                   const float K1 = a00 + a11 - 2.f * a01;
@@ -809,21 +837,17 @@ __global__ void __launch_bounds__(NM_BLOCK) nm_step_kernel(const NmKernelArgs A)
                     else if (x > mid) { f0 = 2.f * mid; f1 = 0.f; }
                     else { f0 = mid + x; f1 = mid - x; }
                   }
-                  float d0 = f0 - o0, d1 = f1 - o1;
+                  d0 = f0 - o0; d1 = f1 - o1;
                   float change = 0.5f * (d0 * (a00 * d0 + a01 * d1) + d1 * (a01 * d0 + a11 * d1)) + d0 * res0 + d1 * res1;
                   if (change > 1e-10f) { f0 = o0; f1 = o1; d0 = 0.f; d1 = 0.f; change = 0.f; }
                   improvement -= change;
-                  cb.f[c][2 * pr] = f0; cb.f[c][2 * pr + 1] = f1;
-                  const float ds = d0 + d1, dd = mu * (d0 - d1);
-                  p0 = fmaf(ds, g00, fmaf(dd, g0t, p0)); p1 = fmaf(ds, g01, fmaf(dd, g1t, p1)); p2 = fmaf(ds, g02, fmaf(dd, g2t, p2));
-                  c0 += ds;
-                  if (t2) c2 += dd; else c1 += dd;
+                  cb.f[c][2 * t] = f0; cb.f[c][2 * t + 1] = f1;
+#pragma unroll
+                  for (int a = 0; a < 6; a++) u[a] = fmaf(y0[a], d0, fmaf(y1[a], d1, u[a]));
+#pragma unroll
+                  for (int j = 0; j < 3; j++) wv[j] = fmaf(z0[j], d0, fmaf(z1[j], d1, wv[j]));
                 }
               }
-#pragma unroll
-              for (int a = 0; a < 6; a++) u[a] = fmaf(cb.Y[c][0][a], c0, fmaf(cb.Y[c][1][a], c1, fmaf(cb.Y[c][2][a], c2, u[a])));
-#pragma unroll
-              for (int j = 0; j < 3; j++) wv[j] = fmaf(cb.Z[c][0][j], c0, fmaf(cb.Z[c][1][j], c1, fmaf(cb.Z[c][2][j], c2, wv[j])));
             }
           }
 #pragma unroll
