@@ -10,7 +10,9 @@
 
 #define NM_OCT 8            // lanes per environment: 6 leg lanes + base-geom lane + spare
 #define NM_MAXC 4           // contacts per collision geom
+#ifndef NM_BLOCK
 #define NM_BLOCK 64         // threads per CTA = 8 environments
+#endif
 
 struct NmGeom {
   int has;                  // lane owns a collision geom
