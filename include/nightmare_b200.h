@@ -126,6 +126,29 @@ int  nm_reset_idx(nm_batch*, const int64_t* env_ids, int n, int64_t step_counter
 int  nm_step_host(nm_batch*, const float* h_actions, int act_stride, int64_t step_counter,
                   float* h_obs, float* h_rew, int64_t* h_done, nm_stream stream);
 
+/* ---- PPO policy forward (≙ rsl_rl v1.0.2 PPO.act: actor_critic.act / evaluate / get_actions_log_prob, reached from
+ * train.py:54 runner.learn and play.py:122 `nn.act(obs)`; network shape from envs/nightmare_v3_config.py:105-109).
+ * One launch computes, for n observations: mean = actor(obs), value = critic(obs), actions = mean + std*eps with
+ * eps ~ N(0,1) from Philox keyed by (seed, env_offset + row, step), and log_prob = sum log N(actions; mean, std).
+ * TF32 tensor-core MMAs with fp32 accumulation; ELU hidden activations. */
+typedef struct nm_policy nm_policy;
+typedef struct {
+  int32_t num_layers;    /* linear layers, 1..6 */
+  int32_t dims[7];       /* dims[0] = inputs, dims[i] = width after layer i (<= 128 each) */
+} nm_mlp_shape;
+int  nm_policy_create(const nm_mlp_shape* actor, const nm_mlp_shape* critic, int device, nm_policy** out);
+void nm_policy_destroy(nm_policy*);
+/* which: 0 actor, 1 critic (floats of the flat parameter vector), 2 number of actions */
+int  nm_policy_param_count(const nm_policy*, int which);
+/* actor_params / critic_params: DEVICE float32, the module's parameters flattened in PyTorch order
+ * (layer0.weight [out][in], layer0.bias, layer1.weight, ...); std: DEVICE float32 [num_actions]. */
+int  nm_policy_load_weights(nm_policy*, const float* actor_params, const float* critic_params, const float* std, nm_stream stream);
+/* obs: DEVICE float32 [n, obs_stride]; outputs DEVICE float32: actions [n,A], mean [n,A], value [n], logp [n].
+ * deterministic != 0: actions = mean (≙ act_inference, play scripts). */
+int  nm_policy_act(nm_policy*, const float* obs, int obs_stride, int n, uint64_t seed, int64_t step, int64_t env_offset,
+                   int deterministic, float* actions, float* mean, float* value, float* logp, nm_stream stream);
+int64_t nm_policy_launches(const nm_policy*);
+
 /* number of kernel launches issued by this batch so far (bench.py "gpu_launches") */
 int64_t nm_batch_launches(const nm_batch*);
 

@@ -51,6 +51,13 @@ def _load() -> ctypes.CDLL:
     L.nm_batch_launches.restype = _i64
     L.nm_measure_fp32_peak.argtypes = [_vp]
     L.nm_measure_fp32_peak.restype = ctypes.c_double
+    L.nm_policy_create.argtypes = [_vp, _vp, _ci, ctypes.POINTER(_vp)]
+    L.nm_policy_destroy.argtypes = [_vp]
+    L.nm_policy_param_count.argtypes = [_vp, _ci]
+    L.nm_policy_load_weights.argtypes = [_vp, _vp, _vp, _vp, _vp]
+    L.nm_policy_act.argtypes = [_vp, _vp, _ci, _ci, ctypes.c_uint64, _i64, _i64, _ci, _vp, _vp, _vp, _vp, _vp]
+    L.nm_policy_launches.argtypes = [_vp]
+    L.nm_policy_launches.restype = _i64
     return L
 
 
@@ -58,7 +65,9 @@ lib = _load()
 
 EXPORTS = ("nm_last_error", "nm_model_load", "nm_model_from_buffer", "nm_model_destroy", "nm_model_size", "nm_model_timestep",
            "nm_name2id", "nm_model_qpos0", "nm_batch_create", "nm_batch_destroy", "nm_batch_set_env_offset", "nm_step",
-           "nm_physics_step", "nm_reset_idx", "nm_step_host", "nm_batch_launches", "nm_measure_fp32_peak")
+           "nm_physics_step", "nm_reset_idx", "nm_step_host", "nm_batch_launches", "nm_measure_fp32_peak",
+           "nm_policy_create", "nm_policy_destroy", "nm_policy_param_count", "nm_policy_load_weights", "nm_policy_act",
+           "nm_policy_launches")
 
 
 def check(rc: int) -> None:

@@ -18,6 +18,7 @@
 
 static thread_local std::string g_err;
 static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+int nm_fail(int code, const std::string& msg) { return fail(code, msg); }   // shared with nm_policy.cu
 extern "C" const char* nm_last_error(void) { return g_err.c_str(); }
 
 #define CUDA_OK(expr)                                                                                   \

@@ -36,6 +36,7 @@ class NightmareV3Env:
         self.cfg = cfg
         self.log_dir = log_dir
         self.thread_num = num_threads            # accepted for API compatibility; the GPU needs no host threads
+        self.env_offset = int(env_offset)        # global id of local env 0 (multi-GPU sharding)
 
         self.num_envs = self.cfg.env.num_envs
         self.num_obs = self.cfg.env.num_obs

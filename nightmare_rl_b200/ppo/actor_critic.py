@@ -1,0 +1,93 @@
+"""Actor-critic MLP pair with rsl_rl v1.0.2's interface and ``state_dict`` keys
+(``std``, ``actor.{0,2,4,...}.{weight,bias}``, ``critic.{0,2,4,...}.{weight,bias}``; consumed by the reference at
+``play.py:65-72``).  Network sizes come from ``NightmareV3ConfigPPO.policy`` (``envs/nightmare_v3_config.py:105-109``)."""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+from torch.distributions import Normal
+
+_ACTIVATIONS = {
+    "elu": nn.ELU, "selu": nn.SELU, "relu": nn.ReLU, "lrelu": nn.LeakyReLU, "tanh": nn.Tanh, "sigmoid": nn.Sigmoid,
+}
+
+
+def _activation(name: str) -> nn.Module:
+    try:
+        return _ACTIVATIONS[name]()
+    except KeyError:
+        raise ValueError(f"unknown activation '{name}' (one of {sorted(_ACTIVATIONS)})") from None
+
+
+def _mlp(n_in: int, hidden, n_out: int, act: str) -> nn.Sequential:
+    dims = [n_in, *hidden, n_out]
+    layers = []
+    for i in range(len(dims) - 1):
+        layers.append(nn.Linear(dims[i], dims[i + 1]))
+        if i < len(dims) - 2:
+            layers.append(_activation(act))
+    return nn.Sequential(*layers)
+
+
+class ActorCritic(nn.Module):
+    is_recurrent = False
+
+    def __init__(self, num_actor_obs, num_critic_obs, num_actions, actor_hidden_dims=(256, 256, 256),
+                 critic_hidden_dims=(256, 256, 256), activation="elu", init_noise_std=1.0, **kwargs):
+        if kwargs:
+            print("ActorCritic.__init__ got unexpected arguments, which will be ignored: " + str(list(kwargs.keys())))
+        super().__init__()
+        self.activation_name = activation
+        self.actor = _mlp(num_actor_obs, list(actor_hidden_dims), num_actions, activation)
+        self.critic = _mlp(num_critic_obs, list(critic_hidden_dims), 1, activation)
+        self.std = nn.Parameter(init_noise_std * torch.ones(num_actions))
+        self.distribution = None
+        Normal.set_default_validate_args = False
+
+    # rsl_rl API -----------------------------------------------------------------------------------
+    def reset(self, dones=None):
+        pass
+
+    def forward(self):
+        raise NotImplementedError
+
+    @property
+    def action_mean(self):
+        return self.distribution.mean
+
+    @property
+    def action_std(self):
+        return self.distribution.stddev
+
+    @property
+    def entropy(self):
+        return self.distribution.entropy().sum(dim=-1)
+
+    def update_distribution(self, observations):
+        mean = self.actor(observations)
+        self.distribution = Normal(mean, mean * 0.0 + self.std)
+
+    def act(self, observations, **kwargs):
+        self.update_distribution(observations)
+        return self.distribution.sample()
+
+    def get_actions_log_prob(self, actions):
+        return self.distribution.log_prob(actions).sum(dim=-1)
+
+    def act_inference(self, observations):
+        return self.actor(observations)
+
+    def evaluate(self, critic_observations, **kwargs):
+        return self.critic(critic_observations)
+
+    # helpers for the fused rollout kernel ----------------------------------------------------------
+    def layer_dims(self):
+        a = [m for m in self.actor if isinstance(m, nn.Linear)]
+        c = [m for m in self.critic if isinstance(m, nn.Linear)]
+        return ([a[0].in_features] + [m.out_features for m in a], [c[0].in_features] + [m.out_features for m in c])
+
+    def flat_params(self):
+        """(actor, critic) parameters flattened in module order: weight [out,in] then bias, layer by layer."""
+        fa = torch.cat([p.detach().reshape(-1) for m in self.actor if isinstance(m, nn.Linear) for p in (m.weight, m.bias)])
+        fc = torch.cat([p.detach().reshape(-1) for m in self.critic if isinstance(m, nn.Linear) for p in (m.weight, m.bias)])
+        return fa.float().contiguous(), fc.float().contiguous()

@@ -1,0 +1,81 @@
+"""ctypes wrapper of the fused policy forward (``nm_policy_*`` in include/nightmare_b200.h, csrc/nm_policy.cu)."""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+
+from .. import _lib
+
+
+class MlpShape(ctypes.Structure):
+    _fields_ = [("num_layers", ctypes.c_int32), ("dims", ctypes.c_int32 * 7)]
+
+
+def _shape(dims):
+    s = MlpShape()
+    s.num_layers = len(dims) - 1
+    for i, d in enumerate(dims):
+        s.dims[i] = int(d)
+    return s
+
+
+class FusedPolicy:
+    """mean/value/actions/log-prob of an ``ActorCritic`` for a whole batch of observations in one kernel launch."""
+
+    def __init__(self, actor_critic, device: torch.device, seed: int = 0, env_offset: int = 0):
+        if device.type != "cuda":
+            raise _lib.NightmareLibError("the fused policy kernel only runs on CUDA devices")
+        if getattr(actor_critic, "activation_name", "elu") != "elu":
+            raise _lib.NightmareLibError("the fused policy kernel implements ELU hidden activations only")
+        adims, cdims = actor_critic.layer_dims()
+        self.device, self.seed, self.env_offset = device, int(seed), int(env_offset)
+        self.num_actions = adims[-1]
+        self._h = ctypes.c_void_p()
+        a, c = _shape(adims), _shape(cdims)
+        with torch.cuda.device(device):
+            _lib.check(_lib.lib.nm_policy_create(ctypes.byref(a), ctypes.byref(c), device.index or 0, ctypes.byref(self._h)))
+        self._out = {}
+        self.load(actor_critic)
+
+    def _stream(self):
+        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def load(self, actor_critic):
+        """Re-pack the module's current parameters (call after every optimiser step that precedes a rollout)."""
+        fa, fc = actor_critic.flat_params()
+        std = actor_critic.std.detach().float().contiguous()
+        _lib.check(_lib.lib.nm_policy_load_weights(self._h, fa.data_ptr(), fc.data_ptr(), std.data_ptr(), self._stream()))
+        self._std = std.clone()
+        self._keep = (fa, fc, std)
+
+    def act(self, obs: torch.Tensor, step: int, deterministic: bool = False):
+        """→ (actions [n,A], mean [n,A], value [n], log_prob [n]); fresh tensors every call."""
+        if obs.device != self.device or obs.dtype != torch.float32:
+            obs = obs.to(device=self.device, dtype=torch.float32)
+        if obs.dim() != 2 or obs.stride(1) != 1:
+            obs = obs.reshape(obs.shape[0], -1).contiguous()
+        n = obs.shape[0]
+        A = self.num_actions
+        actions = torch.empty(n, A, device=self.device)
+        mean = torch.empty(n, A, device=self.device)
+        value = torch.empty(n, device=self.device)
+        logp = torch.empty(n, device=self.device)
+        _lib.check(_lib.lib.nm_policy_act(self._h, obs.data_ptr(), obs.stride(0), n, ctypes.c_uint64(self.seed), ctypes.c_int64(step),
+                                          ctypes.c_int64(self.env_offset), 1 if deterministic else 0, actions.data_ptr(), mean.data_ptr(),
+                                          value.data_ptr(), logp.data_ptr(), self._stream()))
+        self._keep_obs = obs
+        return actions, mean, value, logp
+
+    @property
+    def std(self):
+        return self._std
+
+    @property
+    def launches(self) -> int:
+        return int(_lib.lib.nm_policy_launches(self._h))
+
+    def __del__(self):
+        if getattr(self, "_h", None) and getattr(_lib, "lib", None) is not None:
+            _lib.lib.nm_policy_destroy(self._h)
+            self._h = None

@@ -1,0 +1,173 @@
+"""Proximal Policy Optimisation with rsl_rl v1.0.2's interface and update rule (hyper-parameters:
+``NightmareV3ConfigPPO.algorithm``, reference ``envs/nightmare_v3_config.py:117-131``): clipped surrogate, clipped value
+loss, entropy bonus, gradient-norm clipping, KL-adaptive learning rate, ``num_learning_epochs x num_mini_batches`` shuffled
+mini-batches, time-out bootstrapping of the reward.
+
+Multi-GPU: when ``torch.distributed`` is initialised each rank owns a shard of the environments; the gradients of every
+optimiser step are averaged with ONE all-reduce of a flat buffer (15 043 parameters here), the mean KL is all-reduced so
+every rank takes the same learning-rate decision, and advantages are normalised with global moments."""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+import torch.optim as optim
+
+from .storage import RolloutStorage
+
+
+def _world():
+    return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+
+
+class PPO:
+    def __init__(self, actor_critic, num_learning_epochs=1, num_mini_batches=1, clip_param=0.2, gamma=0.998, lam=0.95,
+                 value_loss_coef=1.0, entropy_coef=0.0, learning_rate=1e-3, max_grad_norm=1.0, use_clipped_value_loss=True,
+                 schedule="fixed", desired_kl=0.01, device="cpu", fused_rollout=None, seed=0, env_offset=0):
+        self.device = torch.device(device)
+        if self.device.type == "cuda" and self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        self.desired_kl, self.schedule, self.learning_rate = desired_kl, schedule, learning_rate
+        self.actor_critic = actor_critic.to(self.device)
+        self.storage = None
+        self.optimizer = optim.Adam(self.actor_critic.parameters(), lr=learning_rate)
+        self.transition = RolloutStorage.Transition()
+        self.clip_param, self.num_learning_epochs, self.num_mini_batches = clip_param, num_learning_epochs, num_mini_batches
+        self.value_loss_coef, self.entropy_coef, self.gamma, self.lam = value_loss_coef, entropy_coef, gamma, lam
+        self.max_grad_norm, self.use_clipped_value_loss = max_grad_norm, use_clipped_value_loss
+        self.world = _world()
+        if self.world > 1:                                  # identical initial weights on every rank
+            for p in self.actor_critic.parameters():
+                dist.broadcast(p.data, src=0)
+        # fused tensor-core rollout forward (CUDA only; the PyTorch modules remain the differentiable path for update())
+        if fused_rollout is None:
+            fused_rollout = self.device.type == "cuda"
+        self.fused = None
+        self._seed, self._env_offset = seed, env_offset
+        if fused_rollout:
+            from .policy_kernel import FusedPolicy
+            self.fused = FusedPolicy(self.actor_critic, self.device, seed=seed, env_offset=env_offset)
+        self._weights_dirty = False
+        self._act_calls = 0
+        self._flat_grad = None
+
+    def init_storage(self, num_envs, num_transitions_per_env, actor_obs_shape, critic_obs_shape, action_shape):
+        self.storage = RolloutStorage(num_envs, num_transitions_per_env, actor_obs_shape, critic_obs_shape, action_shape, self.device)
+
+    def test_mode(self):
+        self.actor_critic.eval()
+
+    def train_mode(self):
+        self.actor_critic.train()
+
+    def weights_changed(self):
+        """Call after loading a checkpoint: the packed copy the fused kernel reads is refreshed before the next act()."""
+        self._weights_dirty = True
+
+    # ------------------------------------------------------------------ rollout
+    def act(self, obs, critic_obs):
+        t = self.transition
+        self._act_calls += 1
+        if self.fused is not None:
+            if self._weights_dirty:
+                self.fused.load(self.actor_critic)
+                self._weights_dirty = False
+            actions, mean, value, logp = self.fused.act(obs, self._act_calls)
+            t.actions, t.values, t.actions_log_prob, t.action_mean = actions, value.unsqueeze(1), logp, mean
+            t.action_sigma = self.fused.std.unsqueeze(0).expand_as(mean)
+        else:
+            t.actions = self.actor_critic.act(obs).detach()
+            t.values = self.actor_critic.evaluate(critic_obs).detach()
+            t.actions_log_prob = self.actor_critic.get_actions_log_prob(t.actions).detach()
+            t.action_mean = self.actor_critic.action_mean.detach()
+            t.action_sigma = self.actor_critic.action_std.detach()
+        t.observations, t.critic_observations = obs, critic_obs
+        return t.actions
+
+    def process_env_step(self, rewards, dones, infos):
+        t = self.transition
+        t.rewards = rewards.clone()
+        t.dones = dones
+        if "time_outs" in infos:                            # bootstrap the value of episodes cut by the time limit
+            t.rewards += self.gamma * torch.squeeze(t.values * infos["time_outs"].unsqueeze(1).to(self.device), 1)
+        self.storage.add_transitions(t)
+        t.clear()
+        self.actor_critic.reset(dones)
+
+    def compute_returns(self, last_critic_obs):
+        last_values = self.actor_critic.evaluate(last_critic_obs).detach()
+        self.storage.compute_returns(last_values, self.gamma, self.lam, self._reduce_moments if self.world > 1 else None)
+
+    # ------------------------------------------------------------------ collectives
+    @staticmethod
+    def _reduce_moments(s, ss, n):
+        buf = torch.stack([s, ss, n])
+        dist.all_reduce(buf)
+        return buf[0], buf[1], buf[2]
+
+    def _allreduce_grads(self):
+        params = [p for p in self.actor_critic.parameters() if p.grad is not None]
+        total = sum(p.numel() for p in params)
+        if self._flat_grad is None or self._flat_grad.numel() != total:
+            self._flat_grad = torch.empty(total, device=self.device)
+        torch.cat([p.grad.reshape(-1) for p in params], out=self._flat_grad)
+        dist.all_reduce(self._flat_grad)
+        self._flat_grad.div_(self.world)
+        off = 0
+        for p in params:
+            p.grad.copy_(self._flat_grad[off:off + p.numel()].view_as(p.grad))
+            off += p.numel()
+
+    # ------------------------------------------------------------------ update
+    def update(self):
+        mean_value_loss = torch.zeros((), device=self.device)
+        mean_surrogate_loss = torch.zeros((), device=self.device)
+        ac = self.actor_critic
+        gen = self.storage.mini_batch_generator(self.num_mini_batches, self.num_learning_epochs)
+        for (obs_b, cobs_b, act_b, tgt_val_b, adv_b, ret_b, old_logp_b, old_mu_b, old_sigma_b, _hid, _mask) in gen:
+            ac.act(obs_b)
+            logp_b = ac.get_actions_log_prob(act_b)
+            value_b = ac.evaluate(cobs_b)
+            mu_b, sigma_b, entropy_b = ac.action_mean, ac.action_std, ac.entropy
+
+            if self.desired_kl is not None and self.schedule == "adaptive":
+                with torch.inference_mode():
+                    kl = torch.sum(torch.log(sigma_b / old_sigma_b + 1.0e-5)
+                                   + (torch.square(old_sigma_b) + torch.square(old_mu_b - mu_b)) / (2.0 * torch.square(sigma_b)) - 0.5, axis=-1)
+                    kl_mean = torch.mean(kl)
+                    if self.world > 1:
+                        dist.all_reduce(kl_mean)
+                        kl_mean /= self.world
+                    kl_val = float(kl_mean)                # one host read per mini-batch, as in rsl_rl
+                    if kl_val > self.desired_kl * 2.0:
+                        self.learning_rate = max(1e-5, self.learning_rate / 1.5)
+                    elif 0.0 < kl_val < self.desired_kl / 2.0:
+                        self.learning_rate = min(1e-2, self.learning_rate * 1.5)
+                    for g in self.optimizer.param_groups:
+                        g["lr"] = self.learning_rate
+
+            ratio = torch.exp(logp_b - torch.squeeze(old_logp_b))
+            adv = torch.squeeze(adv_b)
+            surrogate = -adv * ratio
+            surrogate_clipped = -adv * torch.clamp(ratio, 1.0 - self.clip_param, 1.0 + self.clip_param)
+            surrogate_loss = torch.max(surrogate, surrogate_clipped).mean()
+            if self.use_clipped_value_loss:
+                value_clipped = tgt_val_b + (value_b - tgt_val_b).clamp(-self.clip_param, self.clip_param)
+                value_loss = torch.max((value_b - ret_b).pow(2), (value_clipped - ret_b).pow(2)).mean()
+            else:
+                value_loss = (ret_b - value_b).pow(2).mean()
+            loss = surrogate_loss + self.value_loss_coef * value_loss - self.entropy_coef * entropy_b.mean()
+
+            self.optimizer.zero_grad()
+            loss.backward()
+            if self.world > 1:
+                self._allreduce_grads()
+            nn.utils.clip_grad_norm_(ac.parameters(), self.max_grad_norm)
+            self.optimizer.step()
+            mean_value_loss += value_loss.detach()
+            mean_surrogate_loss += surrogate_loss.detach()
+
+        n_upd = self.num_learning_epochs * self.num_mini_batches
+        self.storage.clear()
+        self._weights_dirty = True
+        return float(mean_value_loss / n_upd), float(mean_surrogate_loss / n_upd)
