@@ -211,14 +211,13 @@ def run_ours(args):
     h_obs, h_rew, h_done = torch.empty(E, 66).pin_memory(), torch.empty(E).pin_memory(), torch.empty(E, dtype=torch.int64).pin_memory()
     Ke = min(K, 200)
     for i in range(3):
-        obs, _, rew, done, _ = env.step(h_act[i % 16])
+        env.step_host(h_act[i % 16], h_obs, h_rew, h_done)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(Ke):
-        obs, _, rew, done, _ = env.step(h_act[i % 16].to(dev, non_blocking=True))
-        h_obs.copy_(obs, non_blocking=True); h_rew.copy_(rew, non_blocking=True); h_done.copy_(done, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+        # public host-side call: pinned actions H2D, step, obs/rew/dones D2H, stream sync -- every step
+        obs, _, rew, done, _ = env.step_host(h_act[i % 16], h_obs, h_rew, h_done)
     e1.record()
     barrier()
     e2e_ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)

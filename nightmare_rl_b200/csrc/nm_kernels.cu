@@ -31,6 +31,14 @@
 // warp are reused by the others: the hot code (~120 KB) is ~4x the 32 KB L1.5 I-cache, and unsynchronised warps
 // each stream it from L2 on their own (measured: 42 -> 83 M env-steps/s at 131072 envs; profiles/r01_notes.md).
 #define PHASE_SYNC() __syncthreads()
+// Experiment builds (-DNM_TIMING): every warp records clock64() at the phase boundaries into a global buffer
+// (tools/phase_timing.py); compiled out of the product library.
+#ifdef NM_TIMING
+__device__ long long* nm_timing_buf = nullptr;
+#define TSTAMP(k) do { if (nm_timing_buf && (threadIdx.x & 31) == 0) nm_timing_buf[(size_t)(gtid >> 5) * 32 + (k)] = clock64(); } while (0)
+#else
+#define TSTAMP(k)
+#endif
 #define NM_MINVAL 1e-15f
 #define NM_TINY 1e-30f
 
@@ -316,15 +324,16 @@ __device__ __forceinline__ void resample_commands(const NmDevCfg& c, unsigned lo
   cmd[0] = cx * keep; cmd[1] = cy * keep; cmd[2] = cw;
 }
 
-// per-lane contact blocks (local memory, L1-resident): 49 floats per contact.  Only the three whitened
-// contact-frame rows are stored; the four pyramid edges Jn +- mu*Jt are formed on the fly from them.
+// per-lane contact blocks (local memory, L1-resident): 53 floats per contact.  The three whitened contact-frame
+// rows couple a contact to the rest of the system; the 4x4 Gram matrix of its own pyramid edges Jn +- mu*Jt
+// (computed from the edge vectors themselves, no cancellation) carries the coupling among its four rows.
 struct ConBlk {
   float Y[NM_MAXC][3][6];   // whitened base-space image of the contact-frame rows (normal, tangent 1, tangent 2)
   float Z[NM_MAXC][3][3];   // whitened leg-space image
   float b[NM_MAXC][4];      // J_edge qacc_smooth - aref_edge
-  float ad[NM_MAXC][4];     // |edge|^2  (diagonal of A = J M^-1 J^T)
   float adi[NM_MAXC][4];    // 1 / (|edge|^2 + R)
-  float a01[NM_MAXC][2];    // edge(2t) . edge(2t+1): off-diagonal of the opposing pair (noslip)
+  float G[NM_MAXC][10];     // Gram matrix of the 4 pyramid edges (= A restricted to this contact, without R):
+                            //   00 11 22 33 | 01 23 (opposing pairs) | 02 03 12 13 (across the two tangents)
   float f[NM_MAXC][4];      // pyramid-edge forces
   float R[NM_MAXC];
   V3 pos[NM_MAXC];
@@ -360,6 +369,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) nm_step_kernel(const NmKernelArgs
   __syncthreads();
 
   const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
+  TSTAMP(0);
   const int env_raw = gtid >> 3;
   const bool valid = env_raw < A.num_envs;
   const int env = valid ? env_raw : A.num_envs - 1;
@@ -420,7 +430,9 @@ __global__ void __launch_bounds__(BLOCK, MINB) nm_step_kernel(const NmKernelArgs
 
 #pragma unroll 1
   for (int sub = 0; sub < A.nstep; sub++) {
+    TSTAMP(1 + 10 * sub);
     PHASE_SYNC();
+    TSTAMP(2 + 10 * sub);
     // ================================================================ P1 kinematics
     {
       float n2 = q0 * q0 + q1 * q1 + q2 * q2 + q3 * q3;
@@ -496,6 +508,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) nm_step_kernel(const NmKernelArgs
       for (int i = 0; i < 3; i++) bias_b[3 + i] = sdot(cdr[i], Fb);
     }
 
+    TSTAMP(3 + 10 * sub);
     PHASE_SYNC();
     // ================================================================ P3 CRBA in block form
     float Mk[6], C[3][6], Mbb[21];
@@ -532,6 +545,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) nm_step_kernel(const NmKernelArgs
       }
     }
 
+    TSTAMP(4 + 10 * sub);
     PHASE_SYNC();
     // ================================================================ P8 actuation + smooth acceleration
     float rk[3], rb[6], hD[3];
@@ -555,6 +569,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) nm_step_kernel(const NmKernelArgs
     float xsb[6], xsk[3];                      // qacc_smooth
     solve_system(F, rb, rk, xsb, xsk);
 
+    TSTAMP(5 + 10 * sub);
     PHASE_SYNC();
     // ================================================================ P4 collision: convex hull vs plane
     // Support vertex by hill-climbing the hull graph (a local minimum of a linear function on a convex hull
@@ -598,26 +613,61 @@ __global__ void __launch_bounds__(BLOCK, MINB) nm_step_kernel(const NmKernelArgs
         cdist[0] = dist; cvert[0] = best; cb.pos[0] = fma3(-0.5f * dist, pn, wv); nc = 1;
         const float thr2 = (0.3f * G.rbound) * (0.3f * G.rbound);
         const float dpl = dot(pn, pg) - sm.plane_d;       // cheap pre-test in the geom frame: dist(u) ~= dl.v_u + dpl
-        for (int e = e0; e < e1 && nc < NM_MAXC; e++) {   // up to 3 more among the support vertex's neighbours
-          int u = __ldg(A.hull_nbr + e);
-          float4 w4 = __ldg(hv + u);
-          if (fmaf(dl.x, w4.x, fmaf(dl.y, w4.y, dl.z * w4.z)) + dpl > G.margin + 1e-4f) continue;
-          V3 wu = pg + mul(Xg, mk(w4.x, w4.y, w4.z));
-          float du = dot(pn, wu) - sm.plane_d;
-          if (du > G.margin) continue;
-          V3 cp = fma3(-0.5f * du, pn, wu);
-          bool close = false;
-          for (int k = 0; k < nc; k++) { V3 d3 = cb.pos[k] - cp; close |= dot(d3, d3) < thr2; }
-          if (close) continue;
-          cdist[nc] = du; cvert[nc] = u; cb.pos[nc] = cp; nc++;
+        for (int e = e0; e < e1 && nc < NM_MAXC; e += 4) {   // up to 3 more among the support vertex's neighbours
+          // four neighbours per trip (loads issued together); almost all fail the cheap depth pre-test
+          const int el = e1 - 1;
+          int uu[4];
+          float dd[4];
+#pragma unroll
+          for (int k = 0; k < 4; k++) uu[k] = __ldg(A.hull_nbr + min(e + k, el));
+#pragma unroll
+          for (int k = 0; k < 4; k++) {
+            const float4 w4 = __ldg(hv + uu[k]);
+            dd[k] = fmaf(dl.x, w4.x, fmaf(dl.y, w4.y, dl.z * w4.z)) + dpl;
+          }
+#pragma unroll
+          for (int k = 0; k < 4; k++) {
+            if (e + k > el || nc >= NM_MAXC || dd[k] > G.margin + 1e-4f) continue;
+            const int u = uu[k];
+            const float4 w4 = __ldg(hv + u);
+            V3 wu = pg + mul(Xg, mk(w4.x, w4.y, w4.z));
+            float du = dot(pn, wu) - sm.plane_d;
+            if (du > G.margin) continue;
+            V3 cp = fma3(-0.5f * du, pn, wu);
+            bool close = false;
+            for (int q = 0; q < nc; q++) { V3 d3 = cb.pos[q] - cp; close |= dot(d3, d3) < thr2; }
+            if (close) continue;
+            cdist[nc] = du; cvert[nc] = u; cb.pos[nc] = cp; nc++;
+          }
         }
       }
     }
     const int ncon_env = oct_sumi(nc);
+    // Sweep order inside an env is MuJoCo's row order: base geom (lane 6) first, then legs 0..5.  Each octet walks ITS
+    // OWN list of contact-owning lanes: in slot k of a sweep the k-th owner of every octet works, so a sweep costs
+    // max(#owners per env) slots for the warp, not |union of owner lanes over its 4 envs|.
     const unsigned has_bal = __ballot_sync(FULL, nc > 0);
-    const unsigned owner_mask = (has_bal | (has_bal >> 8) | (has_bal >> 16) | (has_bal >> 24)) & 0x7fu;   // octet lanes owning contacts, any env of the warp
-    const bool any_contact = owner_mask != 0u;
+    const unsigned m8 = (has_bal >> obase) & 0x7fu;
+    const unsigned ord = ((m8 >> 6) & 1u) | ((m8 & 0x3fu) << 1);          // bit 0 = lane 6, bit 1+k = lane k
+    const int my_bit = l == 6 ? 0 : l + 1;
+    const int my_slot = __popc(ord & ((1u << my_bit) - 1u));               // my position among this octet's owners
+    int nslot = __popc(ord);
+    nslot = max(nslot, __shfl_xor_sync(FULL, nslot, 8));
+    nslot = max(nslot, __shfl_xor_sync(FULL, nslot, 16));                   // warp-uniform: slots per sweep
+    const bool any_contact = nslot > 0;
+    unsigned owner_tab = 0u;                                              // 4 bits per slot: owning lane of this octet (0 if none)
+    {
+      unsigned t = ord;
+#pragma unroll
+      for (int k = 0; k < 7; k++) {
+        const int b = __ffs(t) - 1;                                       // -1 when exhausted
+        const unsigned ln = b < 0 ? 0u : (b == 0 ? 6u : (unsigned)(b - 1));
+        owner_tab |= ln << (4 * k);
+        t &= t - 1u;
+      }
+    }
 
+    TSTAMP(6 + 10 * sub);
     PHASE_SYNC();
     float xb[6], xk[3];          // constraint-induced acceleration M^-1 J^T f (after noslip)
 #pragma unroll
@@ -680,33 +730,40 @@ __global__ void __launch_bounds__(BLOCK, MINB) nm_step_kernel(const NmKernelArgs
         cb.R[c] = R;
         const float kd = G.K * imp * pos;
         const float rinv = 1.f / R;
+        {
+          float ey[4][6], ez[4][3];                         // the four edges: Jn + mu*Jt1, Jn - mu*Jt1, Jn + mu*Jt2, Jn - mu*Jt2
 #pragma unroll
-        for (int t = 0; t < 2; t++) {
-          float a00 = 0.f, a11 = 0.f, a01 = 0.f;
+          for (int e = 0; e < 4; e++) {
+            const float sg = (e & 1) ? -mu : mu;
 #pragma unroll
-          for (int a = 0; a < 6; a++) {
-            const float y0 = fmaf(mu, Y[1 + t][a], Y[0][a]), y1 = fmaf(-mu, Y[1 + t][a], Y[0][a]);
-            a00 = fmaf(y0, y0, a00); a11 = fmaf(y1, y1, a11); a01 = fmaf(y0, y1, a01);
+            for (int a = 0; a < 6; a++) ey[e][a] = fmaf(sg, Y[1 + (e >> 1)][a], Y[0][a]);
+#pragma unroll
+            for (int j = 0; j < 3; j++) ez[e][j] = fmaf(sg, Z[1 + (e >> 1)][j], Z[0][j]);
+          }
+          const int gi_[10] = {0, 1, 2, 3, 0, 2, 0, 0, 1, 1}, gj_[10] = {0, 1, 2, 3, 1, 3, 2, 3, 2, 3};
+#pragma unroll
+          for (int k = 0; k < 10; k++) {
+            float t = 0.f;
+#pragma unroll
+            for (int a = 0; a < 6; a++) t = fmaf(ey[gi_[k]][a], ey[gj_[k]][a], t);
+#pragma unroll
+            for (int j = 0; j < 3; j++) t = fmaf(ez[gi_[k]][j], ez[gj_[k]][j], t);
+            cb.G[c][k] = t;
+            if (k < 4) cb.adi[c][k] = 1.f / (t + R);
           }
 #pragma unroll
-          for (int j = 0; j < 3; j++) {
-            const float z0 = fmaf(mu, Z[1 + t][j], Z[0][j]), z1 = fmaf(-mu, Z[1 + t][j], Z[0][j]);
-            a00 = fmaf(z0, z0, a00); a11 = fmaf(z1, z1, a11); a01 = fmaf(z0, z1, a01);
-          }
-          cb.ad[c][2 * t] = a00; cb.ad[c][2 * t + 1] = a11;
-          cb.adi[c][2 * t] = 1.f / (a00 + R); cb.adi[c][2 * t + 1] = 1.f / (a11 + R);
-          cb.a01[c][t] = a01;
-#pragma unroll
-          for (int e = 0; e < 2; e++) {
-            const float sg = e ? -mu : mu;
-            const float aref = -G.B * fmaf(sg, vb[1 + t], vb[0]) - kd;
-            cb.b[c][2 * t + e] = fmaf(sg, as[1 + t], as[0]) - aref;
-            const float jar = fmaf(sg, aw[1 + t], aw[0]) - aref;     // warm start: edge forces implied by qacc_warmstart
-            cb.f[c][2 * t + e] = jar < 0.f ? -jar * rinv : 0.f;
+          for (int e = 0; e < 4; e++) {
+            const float sg = (e & 1) ? -mu : mu;
+            const int t = 1 + (e >> 1);
+            const float aref = -G.B * fmaf(sg, vb[t], vb[0]) - kd;
+            cb.b[c][e] = fmaf(sg, as[t], as[0]) - aref;
+            const float jar = fmaf(sg, aw[t], aw[0]) - aref;        // warm start: edge forces implied by qacc_warmstart
+            cb.f[c][e] = jar < 0.f ? -jar * rinv : 0.f;
           }
         }
       }
 
+      TSTAMP(7 + 10 * sub);
       // ============================================================== P9 warm start, PGS, noslip
       // Dual state: u = G_S^-1 (base part of J^T f), replicated across the octet; wv = G_k^-1 (leg part), private.
       float u[6], wv[3];
@@ -772,72 +829,47 @@ __global__ void __launch_bounds__(BLOCK, MINB) nm_step_kernel(const NmKernelArgs
         if (!__any_sync(FULL, active)) continue;
         float improvement = 0.f;
 #pragma unroll 1
-        for (unsigned pm = owner_mask; pm != 0u;) {
-          // phase order: lane 6 (base geom) first, then legs 0..5
-          const int owner = (pm & 0x40u) ? 6 : (__ffs(pm) - 1);
-          pm &= ~(1u << owner);
-          if (active && l == owner) {
+        for (int slot = 0; slot < nslot; slot++) {
+          // lane of this octet that owns slot `slot` (none: broadcast from lane 0, u is unchanged there)
+          const int owner = (owner_tab >> (4 * slot)) & 0xf;
+          if (active && nc > 0 && my_slot == slot) {
             for (int c = 0; c < nc; c++) {
-              float Yc[3][6], Zc[3][3];
+              // residuals of the 4 edges against the CURRENT dual state, all at once: r_e = b_e + (p0 +- mu*p_t),
+              // p_a = Y_a.u + Z_a.w (three independent dot products); the Gauss-Seidel coupling among the 4 rows of
+              // this contact is then applied through its edge Gram matrix instead of re-walking u after every row.
+              float p0 = 0.f, p1 = 0.f, p2 = 0.f;
 #pragma unroll
-              for (int f = 0; f < 3; f++) {
+              for (int a = 0; a < 6; a++) { const float ua = u[a]; p0 = fmaf(cb.Y[c][0][a], ua, p0); p1 = fmaf(cb.Y[c][1][a], ua, p1); p2 = fmaf(cb.Y[c][2][a], ua, p2); }
 #pragma unroll
-                for (int a = 0; a < 6; a++) Yc[f][a] = cb.Y[c][f][a];
+              for (int j = 0; j < 3; j++) { const float wj = wv[j]; p0 = fmaf(cb.Z[c][0][j], wj, p0); p1 = fmaf(cb.Z[c][1][j], wj, p1); p2 = fmaf(cb.Z[c][2][j], wj, p2); }
+              float r[4] = {cb.b[c][0] + fmaf(mu, p1, p0), cb.b[c][1] + fmaf(-mu, p1, p0), cb.b[c][2] + fmaf(mu, p2, p0), cb.b[c][3] + fmaf(-mu, p2, p0)};
+              float o[4] = {cb.f[c][0], cb.f[c][1], cb.f[c][2], cb.f[c][3]};
+              float d[4];
+              const float g00 = cb.G[c][0], g11 = cb.G[c][1], g22 = cb.G[c][2], g33 = cb.G[c][3], g01 = cb.G[c][4], g23 = cb.G[c][5];
+              const float g02 = cb.G[c][6], g03 = cb.G[c][7], g12 = cb.G[c][8], g13 = cb.G[c][9];
+              if (!in_noslip) {
+                // PGS: edges one after the other, each with its regulariser R
+                const float R = cb.R[c];
+                const float gd[4] = {g00, g11, g22, g33};
 #pragma unroll
-                for (int j = 0; j < 3; j++) Zc[f][j] = cb.Z[c][f][j];
-              }
-              const float R = cb.R[c];
-#pragma unroll
-              for (int t = 0; t < 2; t++) {
-                float y0[6], y1[6], z0[3], z1[3];               // the opposing edge pair Jn +- mu*Jt of tangent t
-#pragma unroll
-                for (int a = 0; a < 6; a++) { y0[a] = fmaf(mu, Yc[1 + t][a], Yc[0][a]); y1[a] = fmaf(-mu, Yc[1 + t][a], Yc[0][a]); }
-#pragma unroll
-                for (int j = 0; j < 3; j++) { z0[j] = fmaf(mu, Zc[1 + t][j], Zc[0][j]); z1[j] = fmaf(-mu, Zc[1 + t][j], Zc[0][j]); }
-                const float o0 = cb.f[c][2 * t], o1 = cb.f[c][2 * t + 1];
-                float d0, d1;
-                if (!in_noslip) {
-                  // PGS: the two edges one after the other (Gauss-Seidel), each with its regulariser R
-                  float res = cb.b[c][2 * t];
-#pragma unroll
-                  for (int a = 0; a < 6; a++) res = fmaf(y0[a], u[a], res);
-#pragma unroll
-                  for (int j = 0; j < 3; j++) res = fmaf(z0[j], wv[j], res);
-                  res = fmaf(R, o0, res);
-                  float fnew = fmaxf(0.f, fmaf(-res, cb.adi[c][2 * t], o0));
-                  d0 = fnew - o0;
-                  float change = d0 * fmaf(0.5f * d0, cb.ad[c][2 * t] + R, res);
-                  if (change > 1e-10f) { d0 = 0.f; fnew = o0; change = 0.f; }
+                for (int e = 0; e < 4; e++) {
+                  const float res = fmaf(R, o[e], r[e]);
+                  float fnew = fmaxf(0.f, fmaf(-res, cb.adi[c][e], o[e]));
+                  float de = fnew - o[e];
+                  float change = de * fmaf(0.5f * de, gd[e] + R, res);
+                  if (change > 1e-10f) { de = 0.f; fnew = o[e]; change = 0.f; }
                   improvement -= change;
-                  cb.f[c][2 * t] = fnew;
+                  o[e] = fnew; d[e] = de;
+                  if (e == 0) { r[1] = fmaf(de, g01, r[1]); r[2] = fmaf(de, g02, r[2]); r[3] = fmaf(de, g03, r[3]); }
+                  if (e == 1) { r[2] = fmaf(de, g12, r[2]); r[3] = fmaf(de, g13, r[3]); }
+                  if (e == 2) { r[3] = fmaf(de, g23, r[3]); }
+                }
+              } else {
+                // noslip: each opposing pair re-solved jointly without R, its sum kept fixed
 #pragma unroll
-                  for (int a = 0; a < 6; a++) u[a] = fmaf(y0[a], d0, u[a]);
-#pragma unroll
-                  for (int j = 0; j < 3; j++) wv[j] = fmaf(z0[j], d0, wv[j]);
-                  res = cb.b[c][2 * t + 1];
-#pragma unroll
-                  for (int a = 0; a < 6; a++) res = fmaf(y1[a], u[a], res);
-#pragma unroll
-                  for (int j = 0; j < 3; j++) res = fmaf(z1[j], wv[j], res);
-                  res = fmaf(R, o1, res);
-                  fnew = fmaxf(0.f, fmaf(-res, cb.adi[c][2 * t + 1], o1));
-                  d1 = fnew - o1;
-                  change = d1 * fmaf(0.5f * d1, cb.ad[c][2 * t + 1] + R, res);
-                  if (change > 1e-10f) { d1 = 0.f; fnew = o1; change = 0.f; }
-                  improvement -= change;
-                  cb.f[c][2 * t + 1] = fnew;
-#pragma unroll
-                  for (int a = 0; a < 6; a++) u[a] = fmaf(y1[a], d1, u[a]);
-#pragma unroll
-                  for (int j = 0; j < 3; j++) wv[j] = fmaf(z1[j], d1, wv[j]);
-                } else {
-                  // noslip: the pair re-solved jointly without R, its sum kept fixed
-                  float res0 = cb.b[c][2 * t], res1 = cb.b[c][2 * t + 1];
-#pragma unroll
-                  for (int a = 0; a < 6; a++) { res0 = fmaf(y0[a], u[a], res0); res1 = fmaf(y1[a], u[a], res1); }
-#pragma unroll
-                  for (int j = 0; j < 3; j++) { res0 = fmaf(z0[j], wv[j], res0); res1 = fmaf(z1[j], wv[j], res1); }
-                  const float a00 = cb.ad[c][2 * t], a11 = cb.ad[c][2 * t + 1], a01 = cb.a01[c][t];
+                for (int t = 0; t < 2; t++) {
+                  const float a00 = t ? g22 : g00, a11 = t ? g33 : g11, a01 = t ? g23 : g01;
+                  const float o0 = o[2 * t], o1 = o[2 * t + 1], res0 = r[2 * t], res1 = r[2 * t + 1];
                   const float bc0 = res0 - a00 * o0 - a01 * o1, bc1 = res1 - a01 * o0 - a11 * o1;
                   const float mid = 0.5f * (o0 + o1);
                   const float K1 = a00 + a11 - 2.f * a01;
@@ -850,17 +882,20 @@ __global__ void __launch_bounds__(BLOCK, MINB) nm_step_kernel(const NmKernelArgs
                     else if (x > mid) { f0 = 2.f * mid; f1 = 0.f; }
                     else { f0 = mid + x; f1 = mid - x; }
                   }
-                  d0 = f0 - o0; d1 = f1 - o1;
+                  float d0 = f0 - o0, d1 = f1 - o1;
                   float change = 0.5f * (d0 * (a00 * d0 + a01 * d1) + d1 * (a01 * d0 + a11 * d1)) + d0 * res0 + d1 * res1;
                   if (change > 1e-10f) { f0 = o0; f1 = o1; d0 = 0.f; d1 = 0.f; change = 0.f; }
                   improvement -= change;
-                  cb.f[c][2 * t] = f0; cb.f[c][2 * t + 1] = f1;
-#pragma unroll
-                  for (int a = 0; a < 6; a++) u[a] = fmaf(y0[a], d0, fmaf(y1[a], d1, u[a]));
-#pragma unroll
-                  for (int j = 0; j < 3; j++) wv[j] = fmaf(z0[j], d0, fmaf(z1[j], d1, wv[j]));
+                  o[2 * t] = f0; o[2 * t + 1] = f1; d[2 * t] = d0; d[2 * t + 1] = d1;
+                  if (t == 0) { r[2] = fmaf(d0, g02, fmaf(d1, g12, r[2])); r[3] = fmaf(d0, g03, fmaf(d1, g13, r[3])); }
                 }
               }
+              cb.f[c][0] = o[0]; cb.f[c][1] = o[1]; cb.f[c][2] = o[2]; cb.f[c][3] = o[3];
+              const float c0 = (d[0] + d[1]) + (d[2] + d[3]), c1 = mu * (d[0] - d[1]), c2 = mu * (d[2] - d[3]);
+#pragma unroll
+              for (int a = 0; a < 6; a++) u[a] = fmaf(cb.Y[c][0][a], c0, fmaf(cb.Y[c][1][a], c1, fmaf(cb.Y[c][2][a], c2, u[a])));
+#pragma unroll
+              for (int j = 0; j < 3; j++) wv[j] = fmaf(cb.Z[c][0][j], c0, fmaf(cb.Z[c][1][j], c1, fmaf(cb.Z[c][2][j], c2, wv[j])));
             }
           }
 #pragma unroll
@@ -898,7 +933,9 @@ __global__ void __launch_bounds__(BLOCK, MINB) nm_step_kernel(const NmKernelArgs
         if (L.site_r[1] >= 0.f && ray_sphere(pg + mul(Xg, ld3(L.site_pos[1])), L.site_r[1], cb.pos[c], ray) >= 0.f) fn_slot1 += fn;
       }
     }
+    TSTAMP(8 + 10 * sub);
     PHASE_SYNC();
+    TSTAMP(9 + 10 * sub);
     sens0 = fn_slot0; sens1 = fn_slot1;
     cvel_b = cvb;
     base_height = xip_b.z;
@@ -979,6 +1016,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) nm_step_kernel(const NmKernelArgs
     }
   }  // substeps
 
+  TSTAMP(21);
   // ==================================================================== physics-only mode: write state and leave
   if (!ENV) {
     if (valid) {
@@ -1190,7 +1228,12 @@ __global__ void __launch_bounds__(BLOCK, MINB) nm_step_kernel(const NmKernelArgs
       A.time_outs[env] = time_out ? 1.f : 0.f;
     }
   }
+  TSTAMP(22);
 }
+
+#ifdef NM_TIMING
+extern "C" int nm_debug_set_timing_buffer(long long* dev_ptr) { return (int)cudaMemcpyToSymbol(nm_timing_buf, &dev_ptr, sizeof(dev_ptr)); }
+#endif
 
 // ================================================================================================ reset_idx kernel
 // ≙ reset_idx (env.py:335-361) for an explicit id list: qpos<-qpos0, qvel<-0, commands resampled (phase 1),

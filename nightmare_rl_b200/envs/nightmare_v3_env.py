@@ -82,6 +82,7 @@ class NightmareV3Env:
         self.common_step_counter = 0
         self.extras = {}
         self._copy = copy_outputs
+        self._host = None
 
         self._envcfg = build_envcfg(self.cfg, float(self.model.opt_real[0]))
         self._batch = Batch(self._dev_model, self.num_envs, self.device, seed=seed, envcfg=self._envcfg,
@@ -96,6 +97,8 @@ class NightmareV3Env:
         self.feet_air_time = b.feet_air_time
         self.episode_sums = {k: b.episode_sums[:, REWARD_TERMS.index(k)] for k in keys}
         self._extras_keys = [("rew_" + k, REWARD_TERMS.index(k)) for k in keys]
+        _views = b.ep_means.unbind(0)
+        self._extras_views = {name: _views[i] for name, i in self._extras_keys}
         self._rec = None
         if self.cfg.viewer.record_states:
             self._rec = _StateRecorder(self, self.log_dir)
@@ -124,12 +127,40 @@ class NightmareV3Env:
             return self.obs_buf.clone(), None, self.rew_buf.clone(), self.reset_buf.clone(), self.extras
         return self.obs_buf, None, self.rew_buf, self.reset_buf, self.extras
 
-    def _refresh_extras(self):
+    def step_host(self, actions, obs_out=None, rew_out=None, done_out=None):
+        """``step`` for HOST-resident callers, the way the reference is used (CPU action tensor in, CPU tensors out,
+        ``envs/nightmare_v3_env.py:155,311``): one C-ABI call (``nm_step_host``) enqueues the host->device copy of the
+        actions, the step, and the device->host copies of obs / rew / dones on the current stream and waits for them.
+        ``actions`` should be a pinned CPU float32 tensor ``[num_envs, >=18]``; outputs are written into the given
+        (pinned) tensors or into buffers owned by the env, which are overwritten by the next call."""
+        if self._host is None:
+            pin = lambda *s, **k: torch.empty(*s, **k).pin_memory()
+            self._host = (pin(self.num_envs, 66), pin(self.num_envs), pin(self.num_envs, dtype=torch.int64))
+        obs_out = self._host[0] if obs_out is None else obs_out
+        rew_out = self._host[1] if rew_out is None else rew_out
+        done_out = self._host[2] if done_out is None else done_out
+        a = actions
+        if not torch.is_tensor(a) or a.device.type != "cpu" or a.dtype != torch.float32 or not a.is_contiguous():
+            a = torch.as_tensor(a).detach().to("cpu", torch.float32).contiguous()
+        if a.dim() != 2 or a.shape[0] != self.num_envs or a.shape[1] < 18:
+            raise ValueError(f"actions must be [num_envs, >=18], got {tuple(a.shape)}")
+        self.common_step_counter += 1
+        self._batch.step_host(a, self.common_step_counter, obs_out, rew_out, done_out)
+        self._refresh_extras(fresh=False)                  # views of the device-side latches (valid until the next step)
+        if self._rec is not None:
+            self._rec.after_step()
+        return obs_out, None, rew_out, done_out, self.extras
+
+    def _refresh_extras(self, fresh=True):
         # extras are only refreshed on steps where at least one env reset (reference quirk Q10, :344,:363-371).
-        # The latching happens on the device (nm_finalize_kernel, second launch of nm_step): no host sync, and
-        # one small clone here so that dicts stored by the runner keep the values of THEIR step.
-        means = self._batch.ep_means.clone().unbind(0)
-        self.extras["episode"] = {name: means[i] for name, i in self._extras_keys}
+        # The latching happens on the device (nm_finalize_kernel, second launch of nm_step): no host sync.  With
+        # ``fresh`` one small clone gives the dict its own storage, so dicts a runner keeps (rsl_rl appends
+        # infos['episode'] every step) retain the values of THEIR step, like the reference's fresh tensors.
+        if fresh:
+            means = self._batch.ep_means.clone().unbind(0)
+            self.extras["episode"] = {name: means[i] for name, i in self._extras_keys}
+        else:
+            self.extras["episode"] = self._extras_views
         if self.cfg.env.send_timeouts:
             self.extras["time_outs"] = self._batch.time_outs_latched
 

@@ -212,6 +212,29 @@ def test_step_host_matches_device_path():
         assert torch.equal(x, y)
 
 
+def test_env_step_host_public_api():
+    """NightmareV3Env.step_host (CPU tensors in / out, like the reference's step :155,:311) == step on the device."""
+    from nightmare_rl_b200.envs.nightmare_v3_config import NightmareV3Config
+    from nightmare_rl_b200.envs.nightmare_v3_env import NightmareV3Env
+    envs = []
+    for _ in range(2):
+        cfg = NightmareV3Config()
+        cfg.env.num_envs = 200
+        cfg.env.model_path = NMB
+        cfg.viewer.render = cfg.viewer.record_states = False
+        e = NightmareV3Env(cfg, seed=4)
+        e.reset()
+        envs.append(e)
+    g = torch.Generator().manual_seed(0)
+    for t in range(20):
+        a = torch.randn(200, 18, generator=g).pin_memory()
+        o1, p1, r1, d1, x1 = envs[0].step(a)
+        o2, p2, r2, d2, x2 = envs[1].step_host(a)
+        assert p2 is None and o2.device.type == "cpu" and d2.dtype == torch.int64
+        assert torch.equal(o1.cpu(), o2) and torch.equal(r1.cpu(), r2) and torch.equal(d1.cpu(), d2)
+        assert torch.equal(x1["time_outs"].cpu(), x2["time_outs"].cpu())
+
+
 def test_full_size_properties():
     """BASELINE configs[1] size (4096 envs): 200 random-action steps stay finite, counters behave, resets re-arm."""
     from nightmare_rl_b200.envs.nightmare_v3_config import NightmareV3Config
