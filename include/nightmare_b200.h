@@ -121,8 +121,10 @@ int  nm_physics_step(nm_batch*, const float* ctrl, int nstep, nm_stream stream);
  * episode_length and episode_sums, sets done=1. */
 int  nm_reset_idx(nm_batch*, const int64_t* env_ids, int n, int64_t step_counter, nm_stream stream);
 
-/* Same as nm_step but with HOST buffers: copies actions H2D, runs the step and copies
- * obs/rew/done back D2H on `stream`, then synchronises the stream (end-to-end entry point). */
+/* Same as nm_step but with HOST buffers (the way the reference's step is called: CPU tensor in, CPU tensors out,
+ * envs/nightmare_v3_env.py:155,:311), then synchronises the stream.  Pinned (page-locked) buffers are accessed zero-copy:
+ * the kernel reads the actions and writes obs/rew/done through their device aliases, no copy-engine transfer is issued
+ * (the device-resident obs/rew/done buffers are updated as well).  Pageable buffers are staged with async copies. */
 int  nm_step_host(nm_batch*, const float* h_actions, int act_stride, int64_t step_counter,
                   float* h_obs, float* h_rew, int64_t* h_done, nm_stream stream);
 

@@ -444,6 +444,7 @@ extern "C" int nm_batch_create(const nm_model* m, int num_envs, int device, uint
   a.obs = bufs->obs; a.rew = bufs->rew; a.done = reinterpret_cast<long long*>(bufs->done); a.time_outs = bufs->time_outs;
   a.sensordata = bufs->sensordata; a.episode_acc = bufs->episode_acc; a.debug = bufs->debug;
   a.in_actions = nullptr; a.act_stride = 0; a.in_ctrl = nullptr;
+  a.host_obs = nullptr; a.host_rew = nullptr; a.host_done = nullptr;
   *out = b;
   return NM_OK;
 }
@@ -499,10 +500,38 @@ extern "C" int nm_reset_idx(nm_batch* b, const int64_t* env_ids, int n, int64_t 
   return NM_OK;
 }
 
+// pinned (page-locked) host memory is mapped into the device address space under UVA: returns its device alias or null
+static void* mapped_alias(const void* host_ptr) {
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, host_ptr) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  if (at.type != cudaMemoryTypeHost || at.devicePointer == nullptr) return nullptr;
+  return at.devicePointer;
+}
+
 extern "C" int nm_step_host(nm_batch* b, const float* h_actions, int act_stride, int64_t step_counter, float* h_obs, float* h_rew,
                             int64_t* h_done, nm_stream stream) {
   if (!b || !h_actions || !h_obs || !h_rew || !h_done) return fail(NM_ERR_ARG, "nm_step_host: null argument");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // Zero-copy path: when all four host buffers are pinned the kernel reads the actions and writes obs / rew / dones
+  // directly through their device aliases (coalesced rows over PCIe), so the step needs no copy-engine transfers at all.
+  void *ma = mapped_alias(h_actions), *mo = mapped_alias(h_obs), *mr = mapped_alias(h_rew), *md = mapped_alias(h_done);
+  if (ma && mo && mr && md) {
+    if (!b->args.obs) return fail(NM_ERR_ARG, "nm_step_host: batch was created without env buffers");
+    if (act_stride < NM_NDOF) return fail(NM_ERR_ARG, "nm_step_host: actions need at least 18 columns");
+    NmKernelArgs a = b->args;
+    a.in_actions = static_cast<const float*>(ma); a.act_stride = act_stride; a.step_counter = step_counter;
+    a.host_obs = static_cast<float*>(mo); a.host_rew = static_cast<float*>(mr); a.host_done = static_cast<long long*>(md);
+    a.acc_cur = b->d_acc + (NM_NREW + 1) * b->parity;
+    a.acc_next = b->d_acc + (NM_NREW + 1) * (b->parity ^ 1);
+    b->parity ^= 1;
+    nm_launch_step(a, true, stream);
+    nm_launch_finalize(a, stream);
+    b->launches += 2;
+    CUDA_OK(cudaGetLastError());
+    CUDA_OK(cudaStreamSynchronize(st));
+    return NM_OK;
+  }
+  // Pageable host memory: staged copies on the same stream
   const size_t need = (size_t)b->n * act_stride * sizeof(float);
   if (need > b->stage_cap) {
     if (b->d_stage_actions) cudaFree(b->d_stage_actions);

@@ -10,6 +10,7 @@
 
 #define NM_OCT 8            // lanes per environment: 6 leg lanes + base-geom lane + spare
 #define NM_MAXC 4           // contacts per collision geom
+#define NM_NOBS_DEV 66      // observation entries per env (envs/nightmare_v3_config.py:11)
 #ifndef NM_BLOCK
 #define NM_BLOCK 64         // threads per CTA = 8 environments
 #endif
@@ -84,6 +85,8 @@ struct NmKernelArgs {
   float* obs; float* rew; long long* done; float* time_outs; float* sensordata; float* episode_acc; float* debug;
   float* ep_means; float* time_outs_latched;   // extras, refreshed only on steps where >= 1 env reset (env.py:363-371)
   float* acc_cur; float* acc_next;             // library-owned double-buffered accumulators behind episode_acc
+  // host-resident callers (nm_step_host, zero-copy): pinned host memory mapped into the device address space, or null
+  float* host_obs; float* host_rew; long long* host_done;
   // inputs
   const float* in_actions; int act_stride;   // env mode
   const float* in_ctrl;                       // physics-only mode

@@ -355,6 +355,9 @@ template <bool ENV, int BLOCK, int MINB>
 __global__ void __launch_bounds__(BLOCK, MINB) nm_step_kernel(const NmKernelArgs A) {
   __shared__ NmDevModel sm;
   __shared__ NmDevCfg scfg;
+  // observations of the CTA's environments, staged so that they leave the SM as fully coalesced rows (to HBM and,
+  // for host-resident callers, straight to pinned host memory over PCIe)
+  __shared__ __align__(16) float obs_tile[ENV ? (BLOCK / NM_OCT) * NM_NOBS_DEV : 4];
   {
     static_assert(sizeof(NmDevModel) % 16 == 0 && sizeof(NmDevCfg) % 16 == 0, "constant tables are copied as int4");
     const int4* src = reinterpret_cast<const int4*>(A.model);
@@ -1170,7 +1173,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) nm_step_kernel(const NmKernelArgs
     float* qpo = A.qpos + (size_t)env * 25;
     float* qvo = A.qvel + (size_t)env * 24;
     float* qwo = A.warm + (size_t)env * 24;
-    float* ob = A.obs + (size_t)env * 66;
+    float* ob = obs_tile + (threadIdx.x >> 3) * NM_NOBS_DEV;
     const float co = c.clip_obs;
     if (G.has) A.hull_hint[(size_t)env * NM_OCT + l] = hint;
     if (leg) {
@@ -1226,6 +1229,19 @@ __global__ void __launch_bounds__(BLOCK, MINB) nm_step_kernel(const NmKernelArgs
       A.rew[env] = total;
       A.done[env] = reset ? 1 : 0;
       A.time_outs[env] = time_out ? 1.f : 0.f;
+      if (A.host_obs != nullptr) { A.host_rew[env] = total; A.host_done[env] = reset ? 1 : 0; }
+    }
+  }
+  __syncthreads();
+  {
+    const int env0 = blockIdx.x * (BLOCK / NM_OCT);
+    const int nrow = min(BLOCK / NM_OCT, A.num_envs - env0);
+    const int nflt = nrow * NM_NOBS_DEV;
+    float* dst = A.obs + (size_t)env0 * NM_NOBS_DEV;
+    for (int i = threadIdx.x; i < nflt; i += BLOCK) dst[i] = obs_tile[i];
+    if (A.host_obs != nullptr) {
+      float* hdst = A.host_obs + (size_t)env0 * NM_NOBS_DEV;
+      for (int i = threadIdx.x; i < nflt; i += BLOCK) hdst[i] = obs_tile[i];
     }
   }
   TSTAMP(22);
