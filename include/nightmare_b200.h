@@ -109,6 +109,12 @@ void nm_batch_destroy(nm_batch*);
 /* global env id of local env 0 (multi-GPU sharding keeps RNG streams keyed by GLOBAL env id) */
 int  nm_batch_set_env_offset(nm_batch*, int64_t first_global_env);
 
+/* Domain randomisation — NOT in the reference (BASELINE config 3 asks for it).  dr: DEVICE float32 [N,4] =
+ * (contact-friction scale, actuator-kv scale, base-mass scale, unused), caller-owned; NULL switches it off (default).
+ * ranges = {mu_lo, mu_hi, kv_lo, kv_hi, mass_lo, mass_hi}: when resample_on_reset != 0 an env that resets inside nm_step
+ * draws new scales uniformly from them (Philox phase 3).  With all scales 1 the step is bit-identical to DR off. */
+int  nm_batch_set_domain_randomization(nm_batch*, float* dr, const float* ranges, int resample_on_reset);
+
 /* ≙ NightmareV3Env.step(actions)                            envs/nightmare_v3_env.py:145-311
  * actions: device float32 [N, act_stride], first 18 columns used (:156).  step_counter is the
  * value of common_step_counter AFTER this step's increment (:213); it is the RNG counter. */

@@ -51,6 +51,18 @@ class Batch:
         if env_offset:
             _lib.check(_lib.lib.nm_batch_set_env_offset(self._h, env_offset))
 
+    def set_domain_randomization(self, dr, ranges=None, resample_on_reset=False):
+        """``dr``: float32 CUDA tensor [num_envs, 4] (friction, kv, base-mass scale, unused) or None to switch DR off."""
+        if dr is None:
+            _lib.check(_lib.lib.nm_batch_set_domain_randomization(self._h, None, None, 0))
+            self.dr = None
+            return
+        if dr.shape != (self.n, 4) or dr.dtype != torch.float32 or dr.device != self.device or not dr.is_contiguous():
+            raise ValueError("dr must be a contiguous float32 [num_envs, 4] tensor on the batch's device")
+        r = (ctypes.c_float * 6)(*([float(x) for x in ranges] if ranges is not None else [1.0] * 6))
+        _lib.check(_lib.lib.nm_batch_set_domain_randomization(self._h, dr.data_ptr(), r, 1 if (resample_on_reset and ranges is not None) else 0))
+        self.dr = dr
+
     def _stream(self):
         return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 

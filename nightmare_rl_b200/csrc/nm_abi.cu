@@ -445,6 +445,7 @@ extern "C" int nm_batch_create(const nm_model* m, int num_envs, int device, uint
   a.sensordata = bufs->sensordata; a.episode_acc = bufs->episode_acc; a.debug = bufs->debug;
   a.in_actions = nullptr; a.act_stride = 0; a.in_ctrl = nullptr;
   a.host_obs = nullptr; a.host_rew = nullptr; a.host_done = nullptr;
+  a.dr = nullptr; a.dr_on_reset = 0;
   *out = b;
   return NM_OK;
 }
@@ -454,6 +455,14 @@ extern "C" void nm_batch_destroy(nm_batch* b) {
   cudaFree(b->d_model); cudaFree(b->d_cfg); cudaFree(b->d_hull); cudaFree(b->d_nbr_adr); cudaFree(b->d_nbr); cudaFree(b->d_hint); cudaFree(b->d_acc);
   if (b->d_stage_actions) cudaFree(b->d_stage_actions);
   delete b;
+}
+
+extern "C" int nm_batch_set_domain_randomization(nm_batch* b, float* dr, const float* ranges, int resample_on_reset) {
+  if (!b) return fail(NM_ERR_ARG, "null batch");
+  b->args.dr = dr;
+  b->args.dr_on_reset = (dr && ranges && resample_on_reset) ? 1 : 0;
+  for (int i = 0; i < 6; i++) b->args.dr_range[i] = ranges ? ranges[i] : 1.f;
+  return NM_OK;
 }
 
 extern "C" int nm_batch_set_env_offset(nm_batch* b, int64_t first) {

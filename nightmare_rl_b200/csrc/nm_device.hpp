@@ -87,6 +87,8 @@ struct NmKernelArgs {
   float* acc_cur; float* acc_next;             // library-owned double-buffered accumulators behind episode_acc
   // host-resident callers (nm_step_host, zero-copy): pinned host memory mapped into the device address space, or null
   float* host_obs; float* host_rew; long long* host_done;
+  // domain randomisation (opt-in): [N,4] = (friction scale, kv scale, base-mass scale, unused), or null
+  float* dr; int dr_on_reset; float dr_range[6];
   // inputs
   const float* in_actions; int act_stride;   // env mode
   const float* in_ctrl;                       // physics-only mode

@@ -430,6 +430,11 @@ __global__ void __launch_bounds__(BLOCK, MINB) nm_step_kernel(const NmKernelArgs
   // support-vertex hint of this lane's hull (pure accelerator: any start vertex gives the same support vertex up to exact ties)
   int hint = G.has ? A.hull_hint[(size_t)env * NM_OCT + l] : 0;
   hint = (hint >= 0 && hint < G.hull_num) ? hint : 0;
+  // domain randomisation (opt-in, NOT in the reference): per-env scales of contact friction, actuator kv and base mass.
+  // All 1 when disabled -- multiplying by 1.0f is exact, so the reference path is bit-identical with or without it.
+  float dr_mu = 1.f, dr_kv = 1.f, dr_bm = 1.f;
+  if (A.dr != nullptr) { const float4 d4 = __ldg(reinterpret_cast<const float4*>(A.dr) + env); dr_mu = d4.x; dr_kv = d4.y; dr_bm = d4.z; }
+  const float b_mass = sm.b_mass * dr_bm, total_mass = fmaf(sm.b_mass, dr_bm - 1.f, sm.total_mass);
 
 #pragma unroll 1
   for (int sub = 0; sub < A.nstep; sub++) {
@@ -466,11 +471,13 @@ __global__ void __launch_bounds__(BLOCK, MINB) nm_step_kernel(const NmKernelArgs
     const V3 xip_b = p + mul(Rb, ld3(sm.b_ipos));
     float Iwb[6];
     rot_inertia(Rb, sm.b_iloc, Iwb);
+#pragma unroll
+    for (int i = 0; i < 6; i++) Iwb[i] *= dr_bm;
 
     // ================================================================ P2 comPos: subtree COM, c-frame inertias and dofs
     V3 msum = fma3(L.mass[0], xip[0], fma3(L.mass[1], xip[1], L.mass[2] * xip[2]));
     msum = oct_sum3(msum);
-    const V3 com = (1.f / sm.total_mass) * fma3(sm.b_mass, xip_b, msum);
+    const V3 com = (1.f / total_mass) * fma3(b_mass, xip_b, msum);
     In ci[3];
     SV cd[3];
 #pragma unroll
@@ -479,7 +486,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) nm_step_kernel(const NmKernelArgs
       cd[j].w = axw[j];
       cd[j].v = cross(axw[j], com - anc[j]);
     }
-    const In cib = make_inertia(Iwb, sm.b_mass, xip_b - com);
+    const In cib = make_inertia(Iwb, b_mass, xip_b - com);
     const V3 offb = com - p;
     SV cdr[3];                 // base rotational dofs (body-frame axes); translational dofs are [0; e_i]
 #pragma unroll
@@ -556,10 +563,10 @@ __global__ void __launch_bounds__(BLOCK, MINB) nm_step_kernel(const NmKernelArgs
     for (int j = 0; j < 3; j++) {
       float c = fminf(fmaxf(ctrl[j], L.clo[j]), L.chi[j]);
       float g = L.gear[j];
-      float frc = fmaf(L.gain0[j], c, L.bias0[j]) + L.bias1[j] * (th[j] * g) + L.bias2[j] * (thd[j] * g);
+      float frc = fmaf(L.gain0[j] * dr_kv, c, L.bias0[j]) + L.bias1[j] * (th[j] * g) + (L.bias2[j] * dr_kv) * (thd[j] * g);
       frc = fminf(fmaxf(frc, L.flo[j]), L.fhi[j]);
       rk[j] = (g * frc - L.damping[j] * thd[j] - bias_k[j]) * isleg;
-      hD[j] = h * (sm.imp_damp * L.damping[j] - sm.imp_act * L.bias2[j] * g * g) * isleg;   // -h * d(qfrc_smooth)/d(qvel), diagonal
+      hD[j] = h * (sm.imp_damp * L.damping[j] - sm.imp_act * (L.bias2[j] * dr_kv) * g * g) * isleg;   // -h * d(qfrc_smooth)/d(qvel), diagonal
     }
 #pragma unroll
     for (int i = 0; i < 6; i++) rb[i] = -bias_b[i];
@@ -692,7 +699,8 @@ __global__ void __launch_bounds__(BLOCK, MINB) nm_step_kernel(const NmKernelArgs
       // and the affine term split as beta0 + s*beta_t.  The four pyramid edges are Jn +- mu*Jt: every edge
       // quantity (diagonal, residual, coupling) is a +-mu combination of these, so edges are never materialised.
       const V3 fr0 = ld3(sm.frame), fr1 = ld3(sm.frame + 3), fr2 = ld3(sm.frame + 6);
-      const float mu = G.mu;
+      const float mu = G.mu * dr_mu;
+      const float rfac = G.rfac * (dr_mu * dr_mu) * (1.f + mu * mu) / (1.f + G.mu * G.mu);   // R scales with mu^2 (1 + mu^2)
       for (int c = 0; c < nc; c++) {
         const V3 r = cb.pos[c] - com;
         V3 colb[6], colk[3];
@@ -729,7 +737,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) nm_step_kernel(const NmKernelArgs
         }
         const float pos = cdist[c] - G.margin;
         const float imp = impedance(G, pos);
-        const float R = fmaxf(G.rfac * (1.f - imp) / imp, NM_MINVAL);
+        const float R = fmaxf(rfac * (1.f - imp) / imp, NM_MINVAL);
         cb.R[c] = R;
         const float kd = G.K * imp * pos;
         const float rinv = 1.f / R;
@@ -1101,6 +1109,16 @@ __global__ void __launch_bounds__(BLOCK, MINB) nm_step_kernel(const NmKernelArgs
   if (reset) {
     resample_commands(c, A.seed, genv, A.step_counter, 1, cmd);
     ep_len = 0;
+    if (A.dr != nullptr && A.dr_on_reset && w7) {           // new physical parameters for the new episode
+      unsigned rn[4];
+      philox4x32((unsigned)A.seed, (unsigned)genv, (unsigned)A.step_counter, (unsigned)((unsigned long long)A.step_counter >> 32), 3u, (unsigned)(A.seed >> 32), rn);
+      float4 d4;
+      d4.x = fmaf(u01(rn[0]), A.dr_range[1] - A.dr_range[0], A.dr_range[0]);
+      d4.y = fmaf(u01(rn[1]), A.dr_range[3] - A.dr_range[2], A.dr_range[2]);
+      d4.z = fmaf(u01(rn[2]), A.dr_range[5] - A.dr_range[4], A.dr_range[4]);
+      d4.w = 0.f;
+      reinterpret_cast<float4*>(A.dr)[env] = d4;
+    }
   }
   // E14 rewards (alphabetical accumulation, termination last)
   float fat_term = 0.f;

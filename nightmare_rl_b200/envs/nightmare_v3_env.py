@@ -191,6 +191,25 @@ class NightmareV3Env:
     def render(self):
         return None
 
+    # ------------------------------------------------------------------ domain randomisation (new, opt-in; not in the reference)
+    def set_domain_randomization(self, friction=(0.5, 1.25), kv=(0.8, 1.2), base_mass=(-0.3, 0.3), resample_on_reset=True, seed=0):
+        """Per-env physical parameters (BASELINE config 3): contact-friction scale ~ U(friction), actuator kv scale ~ U(kv),
+        base mass + U(base_mass) kg.  Drawn now for every env and, with ``resample_on_reset``, again inside the step
+        kernel whenever an env resets.  ``set_domain_randomization(None)`` switches it off.  Parity with the reference is
+        defined with DR off (the reference has none)."""
+        if friction is None:
+            self._batch.set_domain_randomization(None)
+            return None
+        m0 = float(self.model.arrays["body_mass"][1])
+        ranges = [friction[0], friction[1], kv[0], kv[1], 1.0 + base_mass[0] / m0, 1.0 + base_mass[1] / m0]
+        g = torch.Generator(device=self.device).manual_seed(int(seed) + 7919 * self.env_offset)
+        u = torch.rand(self.num_envs, 4, device=self.device, generator=g)
+        lo = torch.tensor([ranges[0], ranges[2], ranges[4], 0.0], device=self.device)
+        hi = torch.tensor([ranges[1], ranges[3], ranges[5], 0.0], device=self.device)
+        dr = (lo + u * (hi - lo)).contiguous()
+        self._batch.set_domain_randomization(dr, ranges, resample_on_reset)
+        return dr
+
     # ------------------------------------------------------------------ raw state access (parity harness, checkpoints)
     def get_state(self):
         b = self._batch

@@ -263,3 +263,58 @@ def test_full_size_properties():
     qn = env.get_state()[0][:, 3:7].norm(dim=1)
     assert (qn - 1).abs().max() < 1e-4
     assert total_done > 0
+
+
+def test_domain_randomization_opt_in():
+    """DR is a new opt-in feature (not in the reference): scales of 1 leave the step bit-identical; a heavier base shows
+    up in the resting contact forces; envs that reset draw new parameters inside the ranges."""
+    from nightmare_rl_b200.envs.nightmare_v3_config import NightmareV3Config
+    from nightmare_rl_b200.envs.nightmare_v3_env import NightmareV3Env
+
+    def make(n, seed=2):
+        cfg = NightmareV3Config()
+        cfg.env.num_envs = n
+        cfg.env.model_path = NMB
+        cfg.viewer.render = cfg.viewer.record_states = False
+        e = NightmareV3Env(cfg, seed=seed)
+        e.reset()
+        return e
+    n = 512
+    a, b = make(n), make(n)
+    ones = torch.ones(n, 4, device=a.device)
+    b._batch.set_domain_randomization(ones)
+    g = torch.Generator(device=a.device).manual_seed(1)
+    for t in range(25):
+        act = torch.randn(n, 18, device=a.device, generator=g)
+        o1, _, r1, d1, _ = a.step(act)
+        o2, _, r2, d2, _ = b.step(act)
+        assert torch.equal(o1, o2) and torch.equal(r1, r2) and torch.equal(d1, d2)
+    assert torch.equal(a.get_state()[0], b.get_state()[0])
+    # heavier base -> larger resting contact force (zero actions = default stance), compared on the settled batches
+    heavy, light = make(n), make(n)
+    dr = torch.ones(n, 4, device=a.device)
+    dr[:, 2] = 1.5
+    heavy._batch.set_domain_randomization(dr)
+    zero = torch.zeros(n, 18, device=a.device)
+    fh = fl = 0.0
+    for t in range(120):
+        heavy.step(zero); light.step(zero)
+        if t >= 100:
+            fh += float(heavy._batch.sensordata[:, 6:13].sum(1).mean()); fl += float(light._batch.sensordata[:, 6:13].sum(1).mean())
+    m_b, m_tot = float(heavy.model.arrays["body_mass"][1]), float(heavy.model.arrays["body_mass"][1:].sum())
+    want = (m_tot + 0.5 * m_b) / m_tot
+    assert abs(fl / 20 - m_tot * 9.81) < 0.25 * m_tot * 9.81                    # the robots do stand on their feet
+    assert abs((fh / fl) - want) < 0.15 * want
+    # resampling inside the step kernel when an env resets
+    e = make(n)
+    dr0 = e.set_domain_randomization(friction=(0.5, 1.25), kv=(0.8, 1.2), base_mass=(-0.3, 0.3), resample_on_reset=True).clone()
+    e.episode_length_buf = torch.full((n,), 1249, dtype=torch.int64)
+    e.episode_length_buf[: n // 2] = 5
+    e.step(zero); e.step(zero)
+    dr1 = e._batch.dr
+    lo = torch.tensor([0.5, 0.8, 1.0 - 0.3 / m_b], device=a.device)
+    hi = torch.tensor([1.25, 1.2, 1.0 + 0.3 / m_b], device=a.device)
+    assert ((dr1[:, :3] >= lo - 1e-6) & (dr1[:, :3] <= hi + 1e-6)).all() and ((dr0[:, :3] >= lo - 1e-6) & (dr0[:, :3] <= hi + 1e-6)).all()
+    changed = (dr1 != dr0).any(dim=1)
+    assert changed[n // 2:].all() and not changed[: n // 2].any()               # only the timed-out half was redrawn
+    assert torch.isfinite(e.obs_buf).all()
