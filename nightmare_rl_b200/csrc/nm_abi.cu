@@ -375,6 +375,7 @@ struct nm_batch {
   float4* d_hull;
   int* d_nbr_adr;
   int* d_nbr;
+  float4* d_edge;
   int* d_hint;
   float* d_acc;          // [2][19] double-buffered episode accumulators
   int parity;
@@ -429,6 +430,27 @@ extern "C" int nm_batch_create(const nm_model* m, int num_envs, int device, uint
   CUDA_OK(cudaMemcpy(b->d_nbr_adr, m->nbr_adr.data(), sizeof(int) * m->nbr_adr.size(), cudaMemcpyHostToDevice));
   CUDA_OK(cudaMalloc(&b->d_nbr, sizeof(int) * (m->nbr.size() + 1)));
   CUDA_OK(cudaMemcpy(b->d_nbr, m->nbr.data(), sizeof(int) * m->nbr.size(), cudaMemcpyHostToDevice));
+  {
+    // edge table: neighbour coordinates next to the neighbour id (one load level less in the support-vertex walk)
+    if (m->hull4.size() > 0x1ff * 64) { /* vertex ids are geom-local; checked per geom below */ }
+    std::vector<float4> edge(m->nbr.size() + 4);
+    for (int g = 0; g < NM_OCT; g++) {
+      const NmGeom& G = m->dev.leg[g].geom;
+      if (!G.has) continue;
+      if (G.hull_num > 0x1ff) return fail(NM_ERR_UNSUPPORTED, "convex hulls with more than 511 vertices are not supported");
+      for (int v = 0; v < G.hull_num; v++) {
+        if (m->nbr_adr[G.hull_adr + v + 1] - m->nbr_adr[G.hull_adr + v] > 63) return fail(NM_ERR_UNSUPPORTED, "hull vertex with more than 63 neighbours");
+        for (int e = m->nbr_adr[G.hull_adr + v]; e < m->nbr_adr[G.hull_adr + v + 1]; e++) {
+          const int u = m->nbr[e];
+          float4 q = m->hull4[G.hull_adr + u];
+          memcpy(&q.w, &u, 4);
+          edge[e] = q;
+        }
+      }
+    }
+    CUDA_OK(cudaMalloc(&b->d_edge, sizeof(float4) * edge.size()));
+    CUDA_OK(cudaMemcpy(b->d_edge, edge.data(), sizeof(float4) * edge.size(), cudaMemcpyHostToDevice));
+  }
   CUDA_OK(cudaMalloc(&b->d_hint, sizeof(int) * (size_t)num_envs * NM_OCT));
   CUDA_OK(cudaMemset(b->d_hint, 0, sizeof(int) * (size_t)num_envs * NM_OCT));
   CUDA_OK(cudaMalloc(&b->d_acc, sizeof(float) * 2 * (NM_NREW + 1)));
@@ -436,7 +458,7 @@ extern "C" int nm_batch_create(const nm_model* m, int num_envs, int device, uint
   NmKernelArgs& a = b->args;
   a.hull_hint = b->d_hint;
   a.ep_means = bufs->ep_means; a.time_outs_latched = bufs->time_outs_latched;
-  a.model = b->d_model; a.cfg = b->d_cfg; a.hull_vert = b->d_hull; a.hull_nbr_adr = b->d_nbr_adr; a.hull_nbr = b->d_nbr;
+  a.model = b->d_model; a.cfg = b->d_cfg; a.hull_vert = b->d_hull; a.hull_nbr_adr = b->d_nbr_adr; a.hull_nbr = b->d_nbr; a.hull_edge = b->d_edge;
   a.num_envs = num_envs; a.nstep = cfg ? cfg->decimation : 1; a.step_counter = 0; a.env_offset = 0; a.seed = seed;
   a.qpos = bufs->qpos; a.qvel = bufs->qvel; a.warm = bufs->warm; a.actions = bufs->actions; a.dof_pos = bufs->dof_pos;
   a.dof_vel = bufs->dof_vel; a.commands = bufs->commands; a.episode_length = reinterpret_cast<long long*>(bufs->episode_length);
@@ -452,7 +474,7 @@ extern "C" int nm_batch_create(const nm_model* m, int num_envs, int device, uint
 
 extern "C" void nm_batch_destroy(nm_batch* b) {
   if (!b) return;
-  cudaFree(b->d_model); cudaFree(b->d_cfg); cudaFree(b->d_hull); cudaFree(b->d_nbr_adr); cudaFree(b->d_nbr); cudaFree(b->d_hint); cudaFree(b->d_acc);
+  cudaFree(b->d_model); cudaFree(b->d_cfg); cudaFree(b->d_hull); cudaFree(b->d_nbr_adr); cudaFree(b->d_nbr); cudaFree(b->d_edge); cudaFree(b->d_hint); cudaFree(b->d_acc);
   if (b->d_stage_actions) cudaFree(b->d_stage_actions);
   delete b;
 }

@@ -72,6 +72,7 @@ struct NmKernelArgs {
   const float4* hull_vert;
   const int* hull_nbr_adr;
   const int* hull_nbr;
+  const float4* hull_edge;    // per directed hull edge: the neighbour's coordinates (xyz) and its geom-local vertex id (w, int bits)
   int* hull_hint;            // [N, NM_OCT] last support vertex per collision hull (library-owned scratch)
   int num_envs;
   int nstep;

@@ -428,8 +428,9 @@ __global__ void __launch_bounds__(BLOCK, MINB) nm_step_kernel(const NmKernelArgs
   int bad = 0;
   ConBlk cb;
   // support-vertex hint of this lane's hull (pure accelerator: any start vertex gives the same support vertex up to exact ties)
+  // packed: vertex (9 bits) | its degree (6 bits, 0 = unknown) | first edge of its neighbour list (from bit 15)
   int hint = G.has ? A.hull_hint[(size_t)env * NM_OCT + l] : 0;
-  hint = (hint >= 0 && hint < G.hull_num) ? hint : 0;
+  hint = (hint >= 0 && (hint & 0x1ff) < G.hull_num) ? hint : 0;
   // domain randomisation (opt-in, NOT in the reference): per-env scales of contact friction, actuator kv and base mass.
   // All 1 when disabled -- multiplying by 1.0f is exact, so the reference path is bit-identical with or without it.
   float dr_mu = 1.f, dr_kv = 1.f, dr_bm = 1.f;
@@ -582,9 +583,10 @@ __global__ void __launch_bounds__(BLOCK, MINB) nm_step_kernel(const NmKernelArgs
     TSTAMP(5 + 10 * sub);
     PHASE_SYNC();
     // ================================================================ P4 collision: convex hull vs plane
-    // Support vertex by hill-climbing the hull graph (a local minimum of a linear function on a convex hull
-    // is the global one), warm-started from the previous substep's / step's support vertex (A.hull_hint):
-    // the walk is then usually a single round over ~6 neighbours instead of ~6 rounds / ~40 vertices.
+    // Support vertex by hill-climbing the hull graph (a local minimum of a linear function on a convex hull is the
+    // global one), warm-started from the previous substep's / step's support vertex.  The hint word also remembers
+    // where that vertex's neighbour list lives, and the edge table stores every neighbour's COORDINATES next to its
+    // id, so the usual case (support vertex unchanged) costs one level of loads instead of three dependent ones.
     const V3 pn = ld3(sm.plane_n);
     int nc = 0;
     float cdist[NM_MAXC];
@@ -593,53 +595,43 @@ __global__ void __launch_bounds__(BLOCK, MINB) nm_step_kernel(const NmKernelArgs
       const V3 dl = mulT(Xg, pn);                        // plane normal in the geom frame; minimise dl . v
       const float4* hv = A.hull_vert + G.hull_adr;
       const int* nadr = A.hull_nbr_adr + G.hull_adr;
-      int best = hint;
-      float4 v4 = __ldg(hv + best);
-      float bval = fmaf(dl.x, v4.x, fmaf(dl.y, v4.y, dl.z * v4.z));
-      int e0, e1;
+      int best = hint & 0x1ff, deg = (hint >> 9) & 0x3f, e0 = hint >> 15;
+      float4 vb = __ldg(hv + best);
+      float bval = fmaf(dl.x, vb.x, fmaf(dl.y, vb.y, dl.z * vb.z));
       for (;;) {
-        e0 = __ldg(nadr + best); e1 = __ldg(nadr + best + 1);
+        if (deg == 0) { e0 = __ldg(nadr + best); deg = __ldg(nadr + best + 1) - e0; }
         int nb = best;
-        for (int e = e0; e < e1; e += 4) {                // 4 neighbours per trip: loads issued together, compared in list order
-          const int el = e1 - 1;
-          const int u0 = __ldg(A.hull_nbr + e), u1 = __ldg(A.hull_nbr + min(e + 1, el)), u2 = __ldg(A.hull_nbr + min(e + 2, el)),
-                    u3 = __ldg(A.hull_nbr + min(e + 3, el));
-          const float4 w0 = __ldg(hv + u0), w1 = __ldg(hv + u1), w2 = __ldg(hv + u2), w3 = __ldg(hv + u3);
+        const int el = e0 + deg - 1;
+        for (int e = e0; e <= el; e += 4) {              // 4 neighbours per trip: loads issued together, compared in list order
+          const float4 w0 = __ldg(A.hull_edge + e), w1 = __ldg(A.hull_edge + min(e + 1, el)), w2 = __ldg(A.hull_edge + min(e + 2, el)),
+                       w3 = __ldg(A.hull_edge + min(e + 3, el));
           const float a0 = fmaf(dl.x, w0.x, fmaf(dl.y, w0.y, dl.z * w0.z)), a1 = fmaf(dl.x, w1.x, fmaf(dl.y, w1.y, dl.z * w1.z));
           const float a2 = fmaf(dl.x, w2.x, fmaf(dl.y, w2.y, dl.z * w2.z)), a3 = fmaf(dl.x, w3.x, fmaf(dl.y, w3.y, dl.z * w3.z));
-          if (a0 < bval) { bval = a0; nb = u0; }
-          if (a1 < bval) { bval = a1; nb = u1; }
-          if (a2 < bval) { bval = a2; nb = u2; }
-          if (a3 < bval) { bval = a3; nb = u3; }
+          if (a0 < bval) { bval = a0; nb = __float_as_int(w0.w); vb = w0; }
+          if (a1 < bval) { bval = a1; nb = __float_as_int(w1.w); vb = w1; }
+          if (a2 < bval) { bval = a2; nb = __float_as_int(w2.w); vb = w2; }
+          if (a3 < bval) { bval = a3; nb = __float_as_int(w3.w); vb = w3; }
         }
         if (nb == best) break;
-        best = nb;
+        best = nb; deg = 0;
       }
-      hint = best;
-      v4 = __ldg(hv + best);
-      V3 wv = pg + mul(Xg, mk(v4.x, v4.y, v4.z));
+      hint = best | (deg << 9) | (e0 << 15);
+      V3 wv = pg + mul(Xg, mk(vb.x, vb.y, vb.z));
       float dist = dot(pn, wv) - sm.plane_d;
       if (dist <= G.margin) {
         cdist[0] = dist; cvert[0] = best; cb.pos[0] = fma3(-0.5f * dist, pn, wv); nc = 1;
         const float thr2 = (0.3f * G.rbound) * (0.3f * G.rbound);
         const float dpl = dot(pn, pg) - sm.plane_d;       // cheap pre-test in the geom frame: dist(u) ~= dl.v_u + dpl
-        for (int e = e0; e < e1 && nc < NM_MAXC; e += 4) {   // up to 3 more among the support vertex's neighbours
-          // four neighbours per trip (loads issued together); almost all fail the cheap depth pre-test
-          const int el = e1 - 1;
-          int uu[4];
-          float dd[4];
+        const int el = e0 + deg - 1;
+        for (int e = e0; e <= el && nc < NM_MAXC; e += 4) {   // up to 3 more among the support vertex's neighbours
+          // four neighbours per trip (L1-resident after the walk); almost all fail the cheap depth pre-test
+          float4 ww[4];
 #pragma unroll
-          for (int k = 0; k < 4; k++) uu[k] = __ldg(A.hull_nbr + min(e + k, el));
-#pragma unroll
-          for (int k = 0; k < 4; k++) {
-            const float4 w4 = __ldg(hv + uu[k]);
-            dd[k] = fmaf(dl.x, w4.x, fmaf(dl.y, w4.y, dl.z * w4.z)) + dpl;
-          }
+          for (int k = 0; k < 4; k++) ww[k] = __ldg(A.hull_edge + min(e + k, el));
 #pragma unroll
           for (int k = 0; k < 4; k++) {
-            if (e + k > el || nc >= NM_MAXC || dd[k] > G.margin + 1e-4f) continue;
-            const int u = uu[k];
-            const float4 w4 = __ldg(hv + u);
+            const float4 w4 = ww[k];
+            if (e + k > el || nc >= NM_MAXC || fmaf(dl.x, w4.x, fmaf(dl.y, w4.y, dl.z * w4.z)) + dpl > G.margin + 1e-4f) continue;
             V3 wu = pg + mul(Xg, mk(w4.x, w4.y, w4.z));
             float du = dot(pn, wu) - sm.plane_d;
             if (du > G.margin) continue;
@@ -647,7 +639,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) nm_step_kernel(const NmKernelArgs
             bool close = false;
             for (int q = 0; q < nc; q++) { V3 d3 = cb.pos[q] - cp; close |= dot(d3, d3) < thr2; }
             if (close) continue;
-            cdist[nc] = du; cvert[nc] = u; cb.pos[nc] = cp; nc++;
+            cdist[nc] = du; cvert[nc] = __float_as_int(w4.w); cb.pos[nc] = cp; nc++;
           }
         }
       }
