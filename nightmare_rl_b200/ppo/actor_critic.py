@@ -42,7 +42,6 @@ class ActorCritic(nn.Module):
         self.critic = _mlp(num_critic_obs, list(critic_hidden_dims), 1, activation)
         self.std = nn.Parameter(init_noise_std * torch.ones(num_actions))
         self.distribution = None
-        Normal.set_default_validate_args = False
 
     # rsl_rl API -----------------------------------------------------------------------------------
     def reset(self, dones=None):
@@ -65,7 +64,9 @@ class ActorCritic(nn.Module):
 
     def update_distribution(self, observations):
         mean = self.actor(observations)
-        self.distribution = Normal(mean, mean * 0.0 + self.std)
+        # validate_args=False: argument validation reads a reduction back on the host (a sync per call, and illegal
+        # inside a CUDA-graph capture)
+        self.distribution = Normal(mean, mean * 0.0 + self.std, validate_args=False)
 
     def act(self, observations, **kwargs):
         self.update_distribution(observations)

@@ -23,7 +23,7 @@ def _world():
 class PPO:
     def __init__(self, actor_critic, num_learning_epochs=1, num_mini_batches=1, clip_param=0.2, gamma=0.998, lam=0.95,
                  value_loss_coef=1.0, entropy_coef=0.0, learning_rate=1e-3, max_grad_norm=1.0, use_clipped_value_loss=True,
-                 schedule="fixed", desired_kl=0.01, device="cpu", fused_rollout=None, seed=0, env_offset=0):
+                 schedule="fixed", desired_kl=0.01, device="cpu", fused_rollout=None, seed=0, env_offset=0, graph_update=None):
         self.device = torch.device(device)
         if self.device.type == "cuda" and self.device.index is None:
             self.device = torch.device("cuda", torch.cuda.current_device())
@@ -50,6 +50,16 @@ class PPO:
         self._weights_dirty = False
         self._act_calls = 0
         self._flat_grad = None
+        # CUDA-graph replay of the mini-batch update (single-process CUDA runs): the update is ~200 tiny kernels per
+        # mini-batch and otherwise bound by PyTorch's per-op launch overhead.  The optimiser then keeps its learning rate
+        # in a device tensor and the KL-adaptive schedule runs on the device as well (same rule, no host read-back).
+        if graph_update is None:
+            graph_update = self.device.type == "cuda" and self.world == 1
+        self.graph_update = bool(graph_update) and self.device.type == "cuda" and self.world == 1
+        self._graph = None
+        if self.graph_update:
+            self._lr_t = torch.tensor(float(learning_rate), device=self.device)
+            self.optimizer = optim.Adam(self.actor_critic.parameters(), lr=self._lr_t, capturable=True, foreach=True)
 
     def init_storage(self, num_envs, num_transitions_per_env, actor_obs_shape, critic_obs_shape, action_shape):
         self.storage = RolloutStorage(num_envs, num_transitions_per_env, actor_obs_shape, critic_obs_shape, action_shape, self.device)
@@ -63,6 +73,21 @@ class PPO:
     def weights_changed(self):
         """Call after loading a checkpoint: the packed copy the fused kernel reads is refreshed before the next act()."""
         self._weights_dirty = True
+
+    def optimizer_reloaded(self):
+        """After ``optimizer.load_state_dict``: re-attach the device-resident learning rate and drop the captured graph
+        (the optimiser's state tensors have new addresses)."""
+        lr = self.optimizer.param_groups[0]["lr"]
+        self.learning_rate = float(lr)
+        if self.graph_update:
+            self._lr_t.fill_(self.learning_rate)
+            for g in self.optimizer.param_groups:
+                g["lr"] = self._lr_t
+                g["capturable"] = True
+            for stt in self.optimizer.state.values():
+                if "step" in stt and torch.is_tensor(stt["step"]):
+                    stt["step"] = stt["step"].to(self.device)
+            self._graph = None
 
     # ------------------------------------------------------------------ rollout
     def act(self, obs, critic_obs):
@@ -120,6 +145,107 @@ class PPO:
 
     # ------------------------------------------------------------------ update
     def update(self):
+        if self.graph_update:
+            return self._update_graphed()
+        return self._update_eager()
+
+    # one mini-batch of the update rule on explicit tensors (shared by the eager and the graph-captured path)
+    def _minibatch_loss(self, obs_b, cobs_b, act_b, tgt_val_b, adv_b, ret_b, old_logp_b, old_mu_b, old_sigma_b):
+        ac = self.actor_critic
+        ac.update_distribution(obs_b)                      # rsl_rl calls act() here and discards the sample
+        logp_b = ac.get_actions_log_prob(act_b)
+        value_b = ac.evaluate(cobs_b)
+        mu_b, sigma_b, entropy_b = ac.action_mean, ac.action_std, ac.entropy
+        with torch.no_grad():
+            kl = torch.sum(torch.log(sigma_b / old_sigma_b + 1.0e-5)
+                           + (torch.square(old_sigma_b) + torch.square(old_mu_b - mu_b)) / (2.0 * torch.square(sigma_b)) - 0.5, axis=-1)
+            kl_mean = torch.mean(kl)
+        ratio = torch.exp(logp_b - torch.squeeze(old_logp_b))
+        adv = torch.squeeze(adv_b)
+        surrogate = -adv * ratio
+        surrogate_clipped = -adv * torch.clamp(ratio, 1.0 - self.clip_param, 1.0 + self.clip_param)
+        surrogate_loss = torch.max(surrogate, surrogate_clipped).mean()
+        if self.use_clipped_value_loss:
+            value_clipped = tgt_val_b + (value_b - tgt_val_b).clamp(-self.clip_param, self.clip_param)
+            value_loss = torch.max((value_b - ret_b).pow(2), (value_clipped - ret_b).pow(2)).mean()
+        else:
+            value_loss = (ret_b - value_b).pow(2).mean()
+        loss = surrogate_loss + self.value_loss_coef * value_loss - self.entropy_coef * entropy_b.mean()
+        return loss, value_loss.detach(), surrogate_loss.detach(), kl_mean
+
+    def _graph_step(self):
+        """Body that is captured once and replayed per mini-batch: gather by the static index tensor, loss, backward,
+        device-side KL-adaptive learning rate, gradient clipping, Adam."""
+        st, b = self.storage, self._g_idx
+        obs = st.observations.flatten(0, 1)
+        cobs = st.privileged_observations.flatten(0, 1) if st.privileged_observations is not None else obs
+        loss, v_loss, s_loss, kl_mean = self._minibatch_loss(
+            obs[b], cobs[b], st.actions.flatten(0, 1)[b], st.values.flatten(0, 1)[b], st.advantages.flatten(0, 1)[b],
+            st.returns.flatten(0, 1)[b], st.actions_log_prob.flatten(0, 1)[b], st.mu.flatten(0, 1)[b], st.sigma.flatten(0, 1)[b])
+        if self.desired_kl is not None and self.schedule == "adaptive":
+            lr = self._lr_t
+            down = torch.clamp(lr / 1.5, min=1e-5)
+            up = torch.clamp(lr * 1.5, max=1e-2)
+            new_lr = torch.where(kl_mean > self.desired_kl * 2.0, down,
+                                 torch.where((kl_mean < self.desired_kl / 2.0) & (kl_mean > 0.0), up, lr))
+            lr.copy_(new_lr)
+        self.optimizer.zero_grad(set_to_none=False)
+        loss.backward()
+        nn.utils.clip_grad_norm_(self.actor_critic.parameters(), self.max_grad_norm, foreach=True)
+        self.optimizer.step()
+        self._g_vloss += v_loss
+        self._g_sloss += s_loss
+
+    def _update_graphed(self):
+        st = self.storage
+        batch = st.num_envs * st.num_transitions_per_env
+        mb = batch // self.num_mini_batches
+        if self._graph is None:
+            self._g_idx = torch.zeros(mb, dtype=torch.int64, device=self.device)
+            self._g_vloss = torch.zeros((), device=self.device)
+            self._g_sloss = torch.zeros((), device=self.device)
+            # gradients must exist (and keep their addresses) before capture
+            for p in self.actor_critic.parameters():
+                if p.grad is None:
+                    p.grad = torch.zeros_like(p)
+            snap = [p.detach().clone() for p in self.actor_critic.parameters()]
+            opt_state = None
+            side = torch.cuda.Stream(device=self.device)
+            side.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(side):               # warm-up on a side stream (allocator / cuBLAS / optimiser state)
+                self._g_idx.copy_(torch.arange(mb, device=self.device))     # (does not touch the global RNG stream)
+                lr_keep = self._lr_t.clone()
+                for _ in range(2):
+                    self._graph_step()
+                # undo the warm-up's effect on the parameters and the schedule; Adam's moments restart from zero
+                with torch.no_grad():
+                    for p, q in zip(self.actor_critic.parameters(), snap):
+                        p.copy_(q)
+                    self._lr_t.copy_(lr_keep)
+                    for stt in self.optimizer.state.values():
+                        for k, v in stt.items():
+                            if torch.is_tensor(v):
+                                v.zero_()
+            torch.cuda.current_stream(self.device).wait_stream(side)
+            self._graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self._graph):
+                self._graph_step()
+            # the capture itself does not execute; state is as after the restore above
+        self._g_vloss.zero_()
+        self._g_sloss.zero_()
+        indices = torch.randperm(self.num_mini_batches * mb, device=self.device)
+        for _ in range(self.num_learning_epochs):
+            for i in range(self.num_mini_batches):
+                self._g_idx.copy_(indices[i * mb:(i + 1) * mb])
+                self._graph.replay()
+        n_upd = self.num_learning_epochs * self.num_mini_batches
+        self.storage.clear()
+        self._weights_dirty = True
+        out = torch.stack([self._g_vloss / n_upd, self._g_sloss / n_upd, self._lr_t]).tolist()      # one host read per iteration
+        self.learning_rate = out[2]
+        return out[0], out[1]
+
+    def _update_eager(self):
         mean_value_loss = torch.zeros((), device=self.device)
         mean_surrogate_loss = torch.zeros((), device=self.device)
         ac = self.actor_critic

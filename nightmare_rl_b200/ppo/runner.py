@@ -180,7 +180,11 @@ class OnPolicyRunner:
     def save(self, path, infos=None):
         if self.rank != 0:
             return
-        torch.save({"model_state_dict": self.alg.actor_critic.state_dict(), "optimizer_state_dict": self.alg.optimizer.state_dict(),
+        opt = self.alg.optimizer.state_dict()
+        for g in opt["param_groups"]:                       # plain-float learning rate, as rsl_rl's checkpoints have it
+            if torch.is_tensor(g.get("lr")):
+                g["lr"] = float(g["lr"])
+        torch.save({"model_state_dict": self.alg.actor_critic.state_dict(), "optimizer_state_dict": opt,
                     "iter": self.current_learning_iteration, "infos": infos}, path)
 
     def load(self, path, load_optimizer=True):
@@ -188,6 +192,8 @@ class OnPolicyRunner:
         self.alg.actor_critic.load_state_dict(loaded["model_state_dict"])
         if load_optimizer:
             self.alg.optimizer.load_state_dict(loaded["optimizer_state_dict"])
+            if hasattr(self.alg, "optimizer_reloaded"):
+                self.alg.optimizer_reloaded()
         self.current_learning_iteration = loaded["iter"]
         if hasattr(self.alg, "weights_changed"):
             self.alg.weights_changed()

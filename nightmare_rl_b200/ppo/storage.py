@@ -64,15 +64,15 @@ class RolloutStorage:
             delta = self.rewards[step] + not_terminal * gamma * next_values - self.values[step]
             advantage = delta + not_terminal * gamma * lam * advantage
             self.returns[step] = advantage + self.values[step]
-        self.advantages = self.returns - self.values
+        adv = self.returns - self.values                    # written back IN PLACE: captured CUDA graphs keep reading this buffer
         if reduce_moments is None:
-            self.advantages = (self.advantages - self.advantages.mean()) / (self.advantages.std() + 1e-8)
+            self.advantages.copy_((adv - adv.mean()) / (adv.std() + 1e-8))
         else:
-            a = self.advantages.double()
+            a = adv.double()
             s, ss, n = reduce_moments(a.sum(), (a * a).sum(), torch.tensor(float(a.numel()), device=a.device, dtype=torch.float64))
             mean = s / n
             var = (ss - n * mean * mean) / (n - 1.0)          # unbiased, like torch.std
-            self.advantages = ((a - mean) / (var.clamp_min(0).sqrt() + 1e-8)).float()
+            self.advantages.copy_(((a - mean) / (var.clamp_min(0).sqrt() + 1e-8)).float())
 
     def get_statistics(self):
         done = self.dones.clone()
