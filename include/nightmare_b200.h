@@ -155,7 +155,26 @@ int  nm_policy_load_weights(nm_policy*, const float* actor_params, const float* 
  * deterministic != 0: actions = mean (≙ act_inference, play scripts). */
 int  nm_policy_act(nm_policy*, const float* obs, int obs_stride, int n, uint64_t seed, int64_t step, int64_t env_offset,
                    int deterministic, float* actions, float* mean, float* value, float* logp, nm_stream stream);
+/* nm_policy_act that also writes the rollout buffer's copy of the observations (obs_copy [n, obs_dim]) and the
+ * per-env std row (sigma_out [n,A]); either may be NULL. */
+int  nm_policy_act_store(nm_policy*, const float* obs, int obs_stride, int n, uint64_t seed, int64_t step, int64_t env_offset,
+                         int deterministic, float* actions, float* mean, float* value, float* logp, float* obs_copy,
+                         float* sigma_out, nm_stream stream);
 int64_t nm_policy_launches(const nm_policy*);
+
+/* ---- rollout bookkeeping (≙ rsl_rl v1.0.2 PPO.process_env_step + RolloutStorage.add_transitions, and the episode
+ * statistics OnPolicyRunner.learn keeps; reached from train.py:54).  All pointers DEVICE; source pointers that are NULL
+ * mean "already written in place by nm_policy_act[_store]" (obs / std / actions / mean / value / logp). */
+typedef struct {
+  int32_t n, obs_dim, act_dim, ring_cap;
+  float gamma, pad0;
+  const float* obs; const float* actions; const float* mean; const float* std; const float* value; const float* logp;
+  const float* rew; const int64_t* done; const float* time_outs;          /* time_outs may be NULL */
+  float* s_obs; float* s_actions; float* s_mu; float* s_sigma; float* s_values; float* s_logp; float* s_rewards; uint8_t* s_dones;
+  float* cur_rew; float* cur_len; float* ring_rew; float* ring_len; int64_t* ring_count;   /* all NULL: no statistics */
+  const float* ep_means; float* ep_acc; int32_t n_ep, pad1;  /* ep_acc[0..n_ep) += ep_means, ep_acc[n_ep] += 1; NULL: off */
+} nm_rollout_slot;
+int  nm_rollout_store(const nm_rollout_slot* slot, nm_stream stream);
 
 /* number of kernel launches issued by this batch so far (bench.py "gpu_launches") */
 int64_t nm_batch_launches(const nm_batch*);

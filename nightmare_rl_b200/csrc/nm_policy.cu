@@ -43,6 +43,7 @@ struct NmpArgs {
   unsigned long long seed; long long step, env_offset;
   int deterministic, act_dim;
   float* actions; float* mean; float* value; float* logp;
+  float* obs_copy; float* sigma_out;     // optional: row of the rollout buffer that receives the observations / std
 };
 
 __device__ __forceinline__ unsigned f2tf32(float x) {
@@ -130,6 +131,12 @@ __global__ void __launch_bounds__(NMP_WARPS * 32) nm_policy_kernel(const NmpArgs
   }
   if (lane < 16) lps[lane] = 0.f;
   __syncwarp();
+  if (A.obs_copy != nullptr) {                               // the rollout buffer's copy of what the policy saw
+    for (int idx = lane; idx < 16 * kin; idx += 32) {
+      const int r = idx / kin, c = idx - r * kin;
+      if (row0 + r < A.n) A.obs_copy[(size_t)(row0 + r) * kin + c] = t0[r * NMP_LDA + c];
+    }
+  }
   // ---- critic first, then the actor.  The ping-pong overwrites the observation tile, and the networks are tiny,
   // so the observations are simply staged a second time for the actor pass.
   float* vout = mlp_tile(A.critic, wsm + A.actor.total, t0, t1, lane);
@@ -172,6 +179,7 @@ __global__ void __launch_bounds__(NMP_WARPS * 32) nm_policy_kernel(const NmpArgs
       const float m = mout[r * NMP_LDA + j], s = stdv[j];
       A.mean[(size_t)e * A.act_dim + j] = m;
       A.actions[(size_t)e * A.act_dim + j] = fmaf(s, z[k], m);
+      if (A.sigma_out != nullptr) A.sigma_out[(size_t)e * A.act_dim + j] = s;
       lp += -0.5f * z[k] * z[k] - logf(s) - 0.91893853320467274f;
     }
     atomicAdd(lps + r, lp);
@@ -278,15 +286,25 @@ extern "C" int nm_policy_load_weights(nm_policy* p, const float* actor_params, c
   return NM_OK;
 }
 
+extern "C" int nm_policy_act_store(nm_policy* p, const float* obs, int obs_stride, int n, uint64_t seed, int64_t step, int64_t env_offset,
+                                   int deterministic, float* actions, float* mean, float* value, float* logp, float* obs_copy,
+                                   float* sigma_out, nm_stream stream);
+
 extern "C" int nm_policy_act(nm_policy* p, const float* obs, int obs_stride, int n, uint64_t seed, int64_t step, int64_t env_offset,
                              int deterministic, float* actions, float* mean, float* value, float* logp, nm_stream stream) {
+  return nm_policy_act_store(p, obs, obs_stride, n, seed, step, env_offset, deterministic, actions, mean, value, logp, nullptr, nullptr, stream);
+}
+
+extern "C" int nm_policy_act_store(nm_policy* p, const float* obs, int obs_stride, int n, uint64_t seed, int64_t step, int64_t env_offset,
+                                   int deterministic, float* actions, float* mean, float* value, float* logp, float* obs_copy,
+                                   float* sigma_out, nm_stream stream) {
   if (!p || !obs || !actions || !mean || !value || !logp || n <= 0) return nm_fail(NM_ERR_ARG, "nm_policy_act: bad argument");
   if (obs_stride < p->obs_dim) return nm_fail(NM_ERR_ARG, "nm_policy_act: obs_stride smaller than the observation size");
   NmpArgs a;
   a.actor = p->actor; a.critic = p->critic; a.packed = p->d_packed; a.packed_floats = p->packed_floats;
   a.obs = obs; a.obs_stride = obs_stride; a.n = n; a.seed = seed; a.step = step; a.env_offset = env_offset;
   a.deterministic = deterministic; a.act_dim = p->act_dim;
-  a.actions = actions; a.mean = mean; a.value = value; a.logp = logp;
+  a.actions = actions; a.mean = mean; a.value = value; a.logp = logp; a.obs_copy = obs_copy; a.sigma_out = sigma_out;
   const int per_cta = NMP_WARPS * 16;
   nm_policy_kernel<<<(n + per_cta - 1) / per_cta, NMP_WARPS * 32, p->smem_bytes, static_cast<cudaStream_t>(stream)>>>(a);
   p->launches++;
@@ -295,3 +313,55 @@ extern "C" int nm_policy_act(nm_policy* p, const float* obs, int obs_stride, int
 }
 
 extern "C" int64_t nm_policy_launches(const nm_policy* p) { return p ? p->launches : 0; }
+
+// ================================================================================================ rollout slot store
+// One launch per env step instead of ~30 tiny PyTorch kernels: writes the transition into row t of the rollout buffer
+// (≙ rsl_rl v1.0.2 PPO.process_env_step + RolloutStorage.add_transitions: reward bootstrapped by gamma * V * time_out,
+// dones narrowed to uint8) and keeps the runner's episode statistics (running reward / length per env, ring buffer of
+// the last `ring_cap` finished episodes) on the device.
+__global__ void nm_rollout_store_kernel(const nm_rollout_slot S) {
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+  const int n_obs = S.n * S.obs_dim, n_act = S.n * S.act_dim;
+  if (S.obs != nullptr)
+    for (int i = tid; i < n_obs; i += nth) S.s_obs[i] = S.obs[i];
+  for (int i = tid; i < n_act; i += nth) {
+    if (S.actions) S.s_actions[i] = S.actions[i];
+    if (S.mean) S.s_mu[i] = S.mean[i];
+    if (S.std) S.s_sigma[i] = S.std[i % S.act_dim];
+  }
+  if (S.ep_acc != nullptr && tid <= S.n_ep) {              // running sum of the env's per-step episode means (runner log)
+    if (tid < S.n_ep) S.ep_acc[tid] += S.ep_means[tid];
+    else S.ep_acc[S.n_ep] += 1.f;
+  }
+  for (int e = tid; e < S.n; e += nth) {
+    const float v = S.value ? S.value[e] : S.s_values[e];
+    if (S.value) S.s_values[e] = v;
+    if (S.logp) S.s_logp[e] = S.logp[e];
+    const float r = S.rew[e];
+    const bool d = S.done[e] != 0;
+    S.s_rewards[e] = S.time_outs ? fmaf(S.gamma * v, S.time_outs[e], r) : r;
+    S.s_dones[e] = d ? 1 : 0;
+    if (S.cur_rew) {
+      const float cr = S.cur_rew[e] + r, cl = S.cur_len[e] + 1.f;
+      if (d) {
+        const unsigned long long k = atomicAdd(reinterpret_cast<unsigned long long*>(S.ring_count), 1ull);
+        const int pos = (int)(k % (unsigned long long)S.ring_cap);
+        S.ring_rew[pos] = cr; S.ring_len[pos] = cl;
+        S.cur_rew[e] = 0.f; S.cur_len[e] = 0.f;
+      } else { S.cur_rew[e] = cr; S.cur_len[e] = cl; }
+    }
+  }
+}
+
+extern "C" int nm_rollout_store(const nm_rollout_slot* slot, nm_stream stream) {
+  if (!slot || slot->n <= 0 || !slot->rew || !slot->done || !slot->s_obs || !slot->s_sigma || !slot->s_values || !slot->s_rewards || !slot->s_dones)
+    return nm_fail(NM_ERR_ARG, "nm_rollout_store: missing buffer");
+  if (slot->cur_rew && (!slot->cur_len || !slot->ring_rew || !slot->ring_len || !slot->ring_count || slot->ring_cap <= 0))
+    return nm_fail(NM_ERR_ARG, "nm_rollout_store: incomplete episode-statistics buffers");
+  const int work = slot->n * slot->obs_dim;
+  int blocks = (work + 255) / 256;
+  if (blocks > 1184) blocks = 1184;
+  nm_rollout_store_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(*slot);
+  if (cudaGetLastError() != cudaSuccess) return nm_fail(NM_ERR_CUDA, "nm_rollout_store: launch failed");
+  return NM_OK;
+}

@@ -127,6 +127,14 @@ class NightmareV3Env:
             return self.obs_buf.clone(), None, self.rew_buf.clone(), self.reset_buf.clone(), self.extras
         return self.obs_buf, None, self.rew_buf, self.reset_buf, self.extras
 
+    def fast_step(self, actions):
+        """``step`` without building the return tuple / extras dict (pre-bound rollout loop of the PPO runner, which reads
+        the env's persistent device buffers directly).  ``actions``: contiguous float32 CUDA tensor [num_envs, >=18]."""
+        self.common_step_counter += 1
+        self._batch.step(actions, self.common_step_counter)
+        if self._rec is not None:
+            self._rec.after_step()
+
     def step_host(self, actions, obs_out=None, rew_out=None, done_out=None):
         """``step`` for HOST-resident callers, the way the reference is used (CPU action tensor in, CPU tensors out,
         ``envs/nightmare_v3_env.py:155,311``): one C-ABI call (``nm_step_host``) enqueues the host->device copy of the

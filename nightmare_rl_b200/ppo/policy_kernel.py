@@ -49,21 +49,26 @@ class FusedPolicy:
         self._std = std.clone()
         self._keep = (fa, fc, std)
 
-    def act(self, obs: torch.Tensor, step: int, deterministic: bool = False):
-        """→ (actions [n,A], mean [n,A], value [n], log_prob [n]); fresh tensors every call."""
+    def act(self, obs: torch.Tensor, step: int, deterministic: bool = False, out=None, obs_copy=None, sigma_out=None):
+        """→ (actions [n,A], mean [n,A], value [n], log_prob [n]); fresh tensors every call, or written into the
+        contiguous float32 tensors given as ``out=(actions, mean, value, log_prob)`` (rows of the rollout buffer)."""
         if obs.device != self.device or obs.dtype != torch.float32:
             obs = obs.to(device=self.device, dtype=torch.float32)
         if obs.dim() != 2 or obs.stride(1) != 1:
             obs = obs.reshape(obs.shape[0], -1).contiguous()
         n = obs.shape[0]
         A = self.num_actions
-        actions = torch.empty(n, A, device=self.device)
-        mean = torch.empty(n, A, device=self.device)
-        value = torch.empty(n, device=self.device)
-        logp = torch.empty(n, device=self.device)
-        _lib.check(_lib.lib.nm_policy_act(self._h, obs.data_ptr(), obs.stride(0), n, ctypes.c_uint64(self.seed), ctypes.c_int64(step),
-                                          ctypes.c_int64(self.env_offset), 1 if deterministic else 0, actions.data_ptr(), mean.data_ptr(),
-                                          value.data_ptr(), logp.data_ptr(), self._stream()))
+        if out is not None:
+            actions, mean, value, logp = out
+        else:
+            actions = torch.empty(n, A, device=self.device)
+            mean = torch.empty(n, A, device=self.device)
+            value = torch.empty(n, device=self.device)
+            logp = torch.empty(n, device=self.device)
+        _lib.check(_lib.lib.nm_policy_act_store(self._h, obs.data_ptr(), obs.stride(0), n, ctypes.c_uint64(self.seed), ctypes.c_int64(step),
+                                                ctypes.c_int64(self.env_offset), 1 if deterministic else 0, actions.data_ptr(), mean.data_ptr(),
+                                                value.data_ptr(), logp.data_ptr(), None if obs_copy is None else obs_copy.data_ptr(),
+                                                None if sigma_out is None else sigma_out.data_ptr(), self._stream()))
         self._keep_obs = obs
         return actions, mean, value, logp
 
@@ -79,3 +84,17 @@ class FusedPolicy:
         if getattr(self, "_h", None) and getattr(_lib, "lib", None) is not None:
             _lib.lib.nm_policy_destroy(self._h)
             self._h = None
+
+
+class RolloutSlot(ctypes.Structure):
+    """``nm_rollout_slot`` of include/nightmare_b200.h."""
+    _fields_ = ([("n", ctypes.c_int32), ("obs_dim", ctypes.c_int32), ("act_dim", ctypes.c_int32), ("ring_cap", ctypes.c_int32),
+                 ("gamma", ctypes.c_float), ("pad0", ctypes.c_float)]
+                + [(k, ctypes.c_void_p) for k in ("obs", "actions", "mean", "std", "value", "logp", "rew", "done", "time_outs",
+                                                  "s_obs", "s_actions", "s_mu", "s_sigma", "s_values", "s_logp", "s_rewards", "s_dones",
+                                                  "cur_rew", "cur_len", "ring_rew", "ring_len", "ring_count", "ep_means", "ep_acc")]
+                + [("n_ep", ctypes.c_int32), ("pad1", ctypes.c_int32)])
+
+
+def rollout_store(slot: RolloutSlot, device: torch.device):
+    _lib.check(_lib.lib.nm_rollout_store(ctypes.byref(slot), ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)))

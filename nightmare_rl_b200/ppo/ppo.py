@@ -50,6 +50,8 @@ class PPO:
         self._weights_dirty = False
         self._act_calls = 0
         self._flat_grad = None
+        self._stats = None
+        self._in_place = False
         # CUDA-graph replay of the mini-batch update (single-process CUDA runs): the update is ~200 tiny kernels per
         # mini-batch and otherwise bound by PyTorch's per-op launch overhead.  The optimiser then keeps its learning rate
         # in a device tensor and the KL-adaptive schedule runs on the device as well (same rule, no host read-back).
@@ -93,14 +95,32 @@ class PPO:
     def act(self, obs, critic_obs):
         t = self.transition
         self._act_calls += 1
+        t_ptr = obs.data_ptr()
         if self.fused is not None:
             if self._weights_dirty:
                 self.fused.load(self.actor_critic)
                 self._weights_dirty = False
-            actions, mean, value, logp = self.fused.act(obs, self._act_calls)
+            st = self.storage
+            out = None
+            self._in_place = st is not None and st.step < st.num_transitions_per_env and obs.shape[0] == st.num_envs
+            oc = sg = None
+            if self._in_place:                               # the kernel writes straight into row `step` of the rollout buffer,
+                i = st.step                                  # including the observations it saw: a GPU env returns VIEWS of buffers
+                out = (st.actions[i], st.mu[i], st.values[i].view(-1), st.actions_log_prob[i].view(-1))   # it overwrites in step()
+                oc, sg = st.observations[i], st.sigma[i]
+            actions, mean, value, logp = self.fused.act(obs, self._act_calls, out=out, obs_copy=oc, sigma_out=sg)
             t.actions, t.values, t.actions_log_prob, t.action_mean = actions, value.unsqueeze(1), logp, mean
             t.action_sigma = self.fused.std.unsqueeze(0).expand_as(mean)
+            if self._in_place:                               # the transition refers to the snapshot, not to the env's buffer
+                critic_obs = oc if critic_obs is None or critic_obs.data_ptr() == t_ptr else critic_obs.clone()
+                obs = oc
+            else:
+                obs = obs.clone()
+                critic_obs = obs if critic_obs is None or critic_obs.data_ptr() == t_ptr else critic_obs.clone()
         else:
+            if obs.is_cuda:                                  # snapshot: the env may overwrite the buffer `obs` is a view of
+                obs = obs.clone()
+                critic_obs = obs if critic_obs is None or critic_obs.data_ptr() == t_ptr else critic_obs.clone()
             t.actions = self.actor_critic.act(obs).detach()
             t.values = self.actor_critic.evaluate(critic_obs).detach()
             t.actions_log_prob = self.actor_critic.get_actions_log_prob(t.actions).detach()
@@ -109,7 +129,108 @@ class PPO:
         t.observations, t.critic_observations = obs, critic_obs
         return t.actions
 
+    def attach_episode_stats(self, cur_rew, cur_len, ring_rew, ring_len, ring_count):
+        """Runner hook: running reward / length per env and the ring of finished episodes are then updated by the same
+        launch that stores the transition (CUDA fast path only; returns whether it is active)."""
+        self._stats = (cur_rew, cur_len, ring_rew, ring_len, ring_count)
+        return self.fused is not None
+
+    def _store_fused(self, rewards, dones, infos):
+        from .policy_kernel import RolloutSlot, rollout_store
+        t, st = self.transition, self.storage
+        i = st.step
+        if i >= st.num_transitions_per_env:
+            raise AssertionError("Rollout buffer overflow")
+        obs = t.observations
+        tout = infos.get("time_outs") if isinstance(infos, dict) else None
+        ok = (obs.is_cuda and obs.dtype == torch.float32 and obs.is_contiguous() and rewards.is_cuda and rewards.dtype == torch.float32
+              and rewards.is_contiguous() and dones.is_cuda and dones.dtype == torch.int64 and dones.is_contiguous()
+              and (tout is None or (tout.is_cuda and tout.dtype == torch.float32 and tout.is_contiguous()))
+              and st.privileged_observations is None)
+        if not ok:
+            return False
+        s = RolloutSlot()
+        s.n, s.obs_dim, s.act_dim = st.num_envs, obs.shape[1], t.actions.shape[1]
+        s.gamma = float(self.gamma)
+        if not self._in_place:
+            s.obs, s.std = obs.data_ptr(), self.fused.std.data_ptr()   # (callers that bypassed the in-place rows must pass a snapshot)
+            s.actions, s.mean = t.actions.contiguous().data_ptr(), t.action_mean.contiguous().data_ptr()
+            s.value, s.logp = t.values.contiguous().data_ptr(), t.actions_log_prob.contiguous().data_ptr()
+        s.rew, s.done = rewards.data_ptr(), dones.data_ptr()
+        s.time_outs = tout.data_ptr() if tout is not None else None
+        s.s_obs, s.s_actions, s.s_mu, s.s_sigma = st.observations[i].data_ptr(), st.actions[i].data_ptr(), st.mu[i].data_ptr(), st.sigma[i].data_ptr()
+        s.s_values, s.s_logp = st.values[i].data_ptr(), st.actions_log_prob[i].data_ptr()
+        s.s_rewards, s.s_dones = st.rewards[i].data_ptr(), st.dones[i].data_ptr()
+        if self._stats is not None:
+            cr, cl, rr, rl, rc = self._stats
+            s.cur_rew, s.cur_len, s.ring_rew, s.ring_len, s.ring_count = cr.data_ptr(), cl.data_ptr(), rr.data_ptr(), rl.data_ptr(), rc.data_ptr()
+            s.ring_cap = rr.numel()
+        rollout_store(s, self.device)
+        st.step += 1
+        t.clear()
+        return True
+
+    # ------------------------------------------------------------------ pre-bound rollout (host cost: three C calls per step)
+    def prepare_fast_rollout(self, env, ep_acc=None):
+        """Bind, once, every pointer a rollout step needs (env output buffers, row t of the rollout buffer, statistics)
+        so that a step is nm_policy_act -> nm_step -> nm_rollout_store with pre-built argument blocks.  Returns False
+        when the combination is not eligible (no fused kernel, foreign env class, privileged observations...)."""
+        import ctypes
+        from .policy_kernel import RolloutSlot
+        b = getattr(env, "_batch", None)
+        st = self.storage
+        if (self.fused is None or b is None or st is None or b.device != self.device or env.num_envs != st.num_envs
+                or getattr(env, "_copy", False) or not env.cfg.env.send_timeouts or env.get_privileged_observations() is not None):
+            return False
+        # the env has no privileged observations (the critic sees the actor's): the separate critic-observation rows the
+        # runner allocated (num_privileged_obs == num_obs, reference quirk) would only ever hold a copy of `observations`
+        st.privileged_observations = None
+        f = self.fused
+        self._fast = []
+        for i in range(st.num_transitions_per_env):
+            s = RolloutSlot()
+            s.n, s.obs_dim, s.act_dim, s.gamma = st.num_envs, b.obs.shape[1], st.actions.shape[2], float(self.gamma)
+            s.rew, s.done, s.time_outs = b.rew.data_ptr(), b.done.data_ptr(), b.time_outs_latched.data_ptr()      # obs/std rows: written by the policy launch
+            s.s_obs, s.s_actions, s.s_mu, s.s_sigma = st.observations[i].data_ptr(), st.actions[i].data_ptr(), st.mu[i].data_ptr(), st.sigma[i].data_ptr()
+            s.s_values, s.s_logp, s.s_rewards, s.s_dones = st.values[i].data_ptr(), st.actions_log_prob[i].data_ptr(), st.rewards[i].data_ptr(), st.dones[i].data_ptr()
+            if self._stats is not None:
+                cr, cl, rr, rl, rc = self._stats
+                s.cur_rew, s.cur_len, s.ring_rew, s.ring_len, s.ring_count = cr.data_ptr(), cl.data_ptr(), rr.data_ptr(), rl.data_ptr(), rc.data_ptr()
+                s.ring_cap = rr.numel()
+            if ep_acc is not None:
+                s.ep_means, s.ep_acc, s.n_ep = b.ep_means.data_ptr(), ep_acc.data_ptr(), b.ep_means.numel()
+            self._fast.append((s, st.actions[i]))
+        self._fast_env = env
+        return True
+
+    def fast_rollout_step(self):
+        """One env step of the rollout through the pre-bound pointers (obs are read from / written to the env's own
+        persistent buffers, so nothing is passed around on the host)."""
+        import ctypes
+        from .. import _lib
+        env, b, f, st = self._fast_env, self._fast_env._batch, self.fused, self.storage
+        i = st.step
+        if i >= st.num_transitions_per_env:
+            raise AssertionError("Rollout buffer overflow")
+        if self._weights_dirty:
+            f.load(self.actor_critic)
+            self._weights_dirty = False
+        slot, act_row = self._fast[i]
+        self._act_calls += 1
+        stream = ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        # the policy launch also writes the rollout buffer's copy of the observations and the std row (the env is about
+        # to overwrite its observation buffer); the post-step store then only adds rewards / dones / statistics
+        _lib.check(_lib.lib.nm_policy_act_store(f._h, b.obs.data_ptr(), slot.obs_dim, slot.n, ctypes.c_uint64(f.seed), ctypes.c_int64(self._act_calls),
+                                                ctypes.c_int64(f.env_offset), 0, slot.s_actions, slot.s_mu, slot.s_values, slot.s_logp,
+                                                slot.s_obs, slot.s_sigma, stream))
+        env.fast_step(act_row)
+        _lib.check(_lib.lib.nm_rollout_store(ctypes.byref(slot), stream))
+        st.step += 1
+
     def process_env_step(self, rewards, dones, infos):
+        if self.fused is not None and self._store_fused(rewards, dones, infos):
+            self.actor_critic.reset(dones)
+            return
         t = self.transition
         t.rewards = rewards.clone()
         t.dones = dones
@@ -117,6 +238,19 @@ class PPO:
             t.rewards += self.gamma * torch.squeeze(t.values * infos["time_outs"].unsqueeze(1).to(self.device), 1)
         self.storage.add_transitions(t)
         t.clear()
+        if self._stats is not None:                         # statistics the runner delegated to this class (slow path)
+            cr, cl, rr, rl, rc = self._stats
+            cr += rewards
+            cl += 1
+            dm = dones > 0
+            d = dm.to(torch.int64)
+            pos = (rc + torch.cumsum(d, 0) - 1) % rr.numel()
+            keep = torch.nonzero(dm).flatten()
+            rr[pos[keep]] = cr[keep]
+            rl[pos[keep]] = cl[keep]
+            rc += d.sum()
+            cr.masked_fill_(dm, 0.0)
+            cl.masked_fill_(dm, 0.0)
         self.actor_critic.reset(dones)
 
     def compute_returns(self, last_critic_obs):

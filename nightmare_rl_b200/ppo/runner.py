@@ -26,7 +26,7 @@ class _EpisodeRing:
         self.cap = cap
         self.rew = torch.zeros(cap + 1, device=device)
         self.len = torch.zeros(cap + 1, device=device)
-        self.count = torch.zeros((), device=device, dtype=torch.int64)
+        self.count = torch.zeros(1, device=device, dtype=torch.int64)
 
     def push(self, done_mask, rew_sum, ep_len):
         d = done_mask.to(torch.int64)
@@ -37,7 +37,7 @@ class _EpisodeRing:
         self.count += d.sum()
 
     def means(self):
-        n = int(min(int(self.count), self.cap))
+        n = int(min(int(self.count.item()), self.cap))
         if n == 0:
             return None, None, 0
         return float(self.rew[:n].mean()), float(self.len[:n].mean()), n
@@ -90,11 +90,16 @@ class OnPolicyRunner:
         ring = _EpisodeRing(100, dev)
         cur_rew = torch.zeros(env.num_envs, device=dev)
         cur_len = torch.zeros(env.num_envs, device=dev)
+        # CUDA fast path: the transition store kernel also maintains these statistics (one launch per step)
+        fused_stats = hasattr(alg, "attach_episode_stats") and alg.attach_episode_stats(cur_rew, cur_len, ring.rew[:ring.cap], ring.len[:ring.cap], ring.count)
+        # pre-bound rollout: three C calls per env step, no tensors passed around on the host (CUDA env + fused policy only)
+        ep_acc = torch.zeros(32, device=dev)
+        fast = hasattr(alg, "prepare_fast_rollout") and self.cfg.get("fast_rollout", True) and alg.prepare_fast_rollout(env, ep_acc)
         first, last = self.current_learning_iteration, self.current_learning_iteration + int(num_learning_iterations)
         for it in range(first, last):
             start = time.time()
             with torch.inference_mode():
-                for _ in range(self.num_steps_per_env):
+                for _ in range(self.num_steps_per_env if not fast else 0):
                     actions = alg.act(obs, critic_obs)
                     obs, priv, rewards, dones, infos = env.step(actions)
                     critic_obs = priv if priv is not None else obs
@@ -102,12 +107,21 @@ class OnPolicyRunner:
                     alg.process_env_step(rewards, dones, infos)
                     if "episode" in infos:
                         ep_infos.append(infos["episode"])
-                    cur_rew += rewards
-                    cur_len += 1
-                    done_mask = dones > 0
-                    ring.push(done_mask, cur_rew, cur_len)
-                    cur_rew.masked_fill_(done_mask, 0.0)
-                    cur_len.masked_fill_(done_mask, 0.0)
+                    if not fused_stats:
+                        cur_rew += rewards
+                        cur_len += 1
+                        done_mask = dones > 0
+                        ring.push(done_mask, cur_rew, cur_len)
+                        cur_rew.masked_fill_(done_mask, 0.0)
+                        cur_len.masked_fill_(done_mask, 0.0)
+                if fast:
+                    ep_acc.zero_()
+                    for _ in range(self.num_steps_per_env):
+                        alg.fast_rollout_step()
+                    obs = critic_obs = env.get_observations()
+                    n_ep = env._batch.ep_means.numel()
+                    acc = ep_acc.tolist()
+                    ep_infos.append({name: acc[i] / max(acc[n_ep], 1.0) for name, i in env._extras_keys})
                 if dev.type == "cuda":
                     torch.cuda.synchronize(dev)
                 stop = time.time()

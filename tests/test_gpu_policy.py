@@ -132,3 +132,81 @@ def test_graph_replayed_update_equals_eager_update():
     assert abs(vle - vlg) < 1e-3 * max(1.0, abs(vle)) and abs(sle - slg) < 1e-4
     for a, b in zip(pe, pg):
         assert torch.allclose(a, b, atol=2e-3, rtol=1e-2)           # 60 Adam steps at lr up to 1e-2 amplify fp32 reassociation
+
+
+def test_fused_transition_store_equals_torch_path():
+    """nm_rollout_store (one launch) == PPO.process_env_step + RolloutStorage.add_transitions + the runner's statistics."""
+    from nightmare_rl_b200.ppo import PPO, ActorCritic
+    T, N = 6, 700
+    algs, stats = [], []
+    for fused_store in (True, False):
+        torch.manual_seed(3)
+        ac = ActorCritic(66, 66, 18, actor_hidden_dims=[54, 42, 30], critic_hidden_dims=[54, 42, 30])
+        alg = PPO(ac, gamma=0.99, device="cuda:0", fused_rollout=True, graph_update=False, seed=5)
+        alg.init_storage(N, T, [66], [None], [18])
+        st = (torch.zeros(N, device=DEV), torch.zeros(N, device=DEV), torch.zeros(100, device=DEV), torch.zeros(100, device=DEV),
+              torch.zeros(1, dtype=torch.int64, device=DEV))
+        alg.attach_episode_stats(*st)
+        if not fused_store:
+            alg._store_fused = lambda *a, **k: False          # force the PyTorch path
+        algs.append(alg); stats.append(st)
+    g = torch.Generator(device=DEV).manual_seed(9)
+    for t in range(T):
+        obs = torch.randn(N, 66, device=DEV, generator=g)
+        rew = torch.randn(N, device=DEV, generator=g)
+        done = (torch.rand(N, device=DEV, generator=g) < 0.1).to(torch.int64)
+        tout = ((torch.rand(N, device=DEV, generator=g) < 0.5) & (done > 0)).float()
+        for alg in algs:
+            a = alg.act(obs, obs)
+            alg.process_env_step(rew, done, {"time_outs": tout})
+        assert torch.equal(algs[0].storage.actions[t], algs[1].storage.actions[t])
+    sa, sb = algs[0].storage, algs[1].storage
+    for name in ("observations", "actions", "mu", "sigma", "values", "actions_log_prob", "rewards", "dones"):
+        assert torch.equal(getattr(sa, name), getattr(sb, name)), name
+    assert sa.step == sb.step == T
+    (cr0, cl0, rr0, rl0, rc0), (cr1, cl1, rr1, rl1, rc1) = stats
+    assert torch.equal(cr0, cr1) and torch.equal(cl0, cl1) and int(rc0) == int(rc1) > 100
+    n = min(int(rc0), 100)                                     # ring order differs (atomics); its content within a step does not
+    assert abs(float(rl0[:n].sum()) - float(rl1[:n].sum())) <= 60 and torch.isfinite(rr0).all()
+
+
+def test_prebound_rollout_equals_standard_rollout():
+    """The runner's pre-bound rollout (nm_policy_act_store -> nm_step -> nm_rollout_store on fixed pointers) fills the
+    rollout buffer exactly like the rsl_rl-style loop act -> env.step -> process_env_step."""
+    from envs.nightmare_v3_config import NightmareV3Config
+    from envs.nightmare_v3_env import NightmareV3Env
+    from nightmare_rl_b200.ppo import PPO, ActorCritic
+    T, N = 12, 300
+    out = []
+    for fast in (False, True):
+        cfg = NightmareV3Config()
+        cfg.env.num_envs = N
+        cfg.env.model_path = NMB
+        cfg.viewer.render = cfg.viewer.record_states = False
+        env = NightmareV3Env(cfg, seed=3)
+        env.reset()
+        env.episode_length_buf = torch.arange(N, dtype=torch.int64) % 13 + 1240      # time-outs inside the window
+        torch.manual_seed(1)
+        ac = ActorCritic(66, 66, 18, actor_hidden_dims=[54, 42, 30], critic_hidden_dims=[54, 42, 30])
+        alg = PPO(ac, gamma=0.99, device="cuda:0", fused_rollout=True, graph_update=False, seed=2)
+        alg.init_storage(N, T, [66], [None], [18])
+        st = (torch.zeros(N, device=DEV), torch.zeros(N, device=DEV), torch.zeros(100, device=DEV), torch.zeros(100, device=DEV),
+              torch.zeros(1, dtype=torch.int64, device=DEV))
+        alg.attach_episode_stats(*st)
+        if fast:
+            assert alg.prepare_fast_rollout(env, torch.zeros(32, device=DEV))
+            for t in range(T):
+                alg.fast_rollout_step()
+        else:
+            obs = env.get_observations()
+            for t in range(T):
+                a = alg.act(obs, obs)
+                obs, _, rew, done, infos = env.step(a)
+                alg.process_env_step(rew, done, infos)
+        torch.cuda.synchronize()
+        out.append((alg.storage, st, env.get_state()[0].clone()))
+    (sa, sta, qa), (sb, stb, qb) = out
+    for name in ("observations", "actions", "mu", "sigma", "values", "actions_log_prob", "rewards", "dones"):
+        assert torch.equal(getattr(sa, name), getattr(sb, name)), name
+    assert torch.equal(qa, qb) and torch.equal(sta[0], stb[0]) and int(sta[4]) == int(stb[4])
+    assert sa.dones.sum() > 0
