@@ -162,6 +162,17 @@ int  nm_policy_act_store(nm_policy*, const float* obs, int obs_stride, int n, ui
                          float* sigma_out, nm_stream stream);
 int64_t nm_policy_launches(const nm_policy*);
 
+/* Same contract on Blackwell's tcgen05 tensor cores (csrc/nm_policy_tc5.cu): 128-env tiles, A/B operands in shared memory
+ * (UMMA canonical K-major layout), fp32 accumulators in tensor memory, tcgen05.mma.kind::tf32 issued 3x on hi/lo splits.
+ * Limits: <= 72 inputs, hidden widths <= 64, <= 32 outputs (the reference's 66-54-42-30-18 / 1 networks fit). */
+typedef struct nm_policy_tc5 nm_policy_tc5;
+int  nm_policy_tc5_create(const nm_mlp_shape* actor, const nm_mlp_shape* critic, int device, nm_policy_tc5** out);
+void nm_policy_tc5_destroy(nm_policy_tc5*);
+int  nm_policy_tc5_load_weights(nm_policy_tc5*, const float* actor_params, const float* critic_params, const float* std, nm_stream stream);
+int  nm_policy_tc5_act(nm_policy_tc5*, const float* obs, int obs_stride, int n, uint64_t seed, int64_t step, int64_t env_offset,
+                       int deterministic, float* actions, float* mean, float* value, float* logp, float* obs_copy, float* sigma_out,
+                       nm_stream stream);
+
 /* ---- rollout bookkeeping (≙ rsl_rl v1.0.2 PPO.process_env_step + RolloutStorage.add_transitions, and the episode
  * statistics OnPolicyRunner.learn keeps; reached from train.py:54).  All pointers DEVICE; source pointers that are NULL
  * mean "already written in place by nm_policy_act[_store]" (obs / std / actions / mean / value / logp). */

@@ -61,6 +61,10 @@ def _load() -> ctypes.CDLL:
     L.nm_policy_launches.argtypes = [_vp]
     L.nm_policy_launches.restype = _i64
     L.nm_rollout_store.argtypes = [_vp, _vp]
+    L.nm_policy_tc5_create.argtypes = [_vp, _vp, _ci, ctypes.POINTER(_vp)]
+    L.nm_policy_tc5_destroy.argtypes = [_vp]
+    L.nm_policy_tc5_load_weights.argtypes = [_vp, _vp, _vp, _vp, _vp]
+    L.nm_policy_tc5_act.argtypes = [_vp, _vp, _ci, _ci, ctypes.c_uint64, _i64, _i64, _ci, _vp, _vp, _vp, _vp, _vp, _vp, _vp]
     return L
 
 
@@ -71,7 +75,8 @@ EXPORTS = ("nm_last_error", "nm_model_load", "nm_model_from_buffer", "nm_model_d
            "nm_batch_set_domain_randomization", "nm_step",
            "nm_physics_step", "nm_reset_idx", "nm_step_host", "nm_batch_launches", "nm_measure_fp32_peak",
            "nm_policy_create", "nm_policy_destroy", "nm_policy_param_count", "nm_policy_load_weights", "nm_policy_act",
-           "nm_policy_act_store", "nm_policy_launches", "nm_rollout_store")
+           "nm_policy_act_store", "nm_policy_launches", "nm_rollout_store",
+           "nm_policy_tc5_create", "nm_policy_tc5_destroy", "nm_policy_tc5_load_weights", "nm_policy_tc5_act")
 
 
 def check(rc: int) -> None:

@@ -23,7 +23,7 @@ def _shape(dims):
 class FusedPolicy:
     """mean/value/actions/log-prob of an ``ActorCritic`` for a whole batch of observations in one kernel launch."""
 
-    def __init__(self, actor_critic, device: torch.device, seed: int = 0, env_offset: int = 0):
+    def __init__(self, actor_critic, device: torch.device, seed: int = 0, env_offset: int = 0, engine: str | None = None):
         if device.type != "cuda":
             raise _lib.NightmareLibError("the fused policy kernel only runs on CUDA devices")
         if getattr(actor_critic, "activation_name", "elu") != "elu":
@@ -33,8 +33,18 @@ class FusedPolicy:
         self.num_actions = adims[-1]
         self._h = ctypes.c_void_p()
         a, c = _shape(adims), _shape(cdims)
+        # engine: "tc5" = tcgen05 + TMEM (csrc/nm_policy_tc5.cu), "mma" = warp-level mma.sync (csrc/nm_policy.cu, any width
+        # up to 128).  Default: tc5 when the network fits its limits.
+        import os
+        engine = engine or os.environ.get("NM_POLICY_ENGINE", "tc5")
+        fits = adims[0] <= 72 and max(adims[1:-1] + cdims[1:-1] + [1]) <= 64 and adims[-1] <= 32 and cdims[-1] <= 16
+        self.engine = "tc5" if (engine == "tc5" and fits) else "mma"
+        L = _lib.lib
+        self._fn = ((L.nm_policy_tc5_create, L.nm_policy_tc5_destroy, L.nm_policy_tc5_load_weights, L.nm_policy_tc5_act)
+                    if self.engine == "tc5" else (L.nm_policy_create, L.nm_policy_destroy, L.nm_policy_load_weights, L.nm_policy_act_store))
+        self._launches = 0
         with torch.cuda.device(device):
-            _lib.check(_lib.lib.nm_policy_create(ctypes.byref(a), ctypes.byref(c), device.index or 0, ctypes.byref(self._h)))
+            _lib.check(self._fn[0](ctypes.byref(a), ctypes.byref(c), device.index or 0, ctypes.byref(self._h)))
         self._out = {}
         self.load(actor_critic)
 
@@ -45,7 +55,7 @@ class FusedPolicy:
         """Re-pack the module's current parameters (call after every optimiser step that precedes a rollout)."""
         fa, fc = actor_critic.flat_params()
         std = actor_critic.std.detach().float().contiguous()
-        _lib.check(_lib.lib.nm_policy_load_weights(self._h, fa.data_ptr(), fc.data_ptr(), std.data_ptr(), self._stream()))
+        _lib.check(self._fn[2](self._h, fa.data_ptr(), fc.data_ptr(), std.data_ptr(), self._stream()))
         self._std = std.clone()
         self._keep = (fa, fc, std)
 
@@ -65,7 +75,8 @@ class FusedPolicy:
             mean = torch.empty(n, A, device=self.device)
             value = torch.empty(n, device=self.device)
             logp = torch.empty(n, device=self.device)
-        _lib.check(_lib.lib.nm_policy_act_store(self._h, obs.data_ptr(), obs.stride(0), n, ctypes.c_uint64(self.seed), ctypes.c_int64(step),
+        self._launches += 1
+        _lib.check(self._fn[3](self._h, obs.data_ptr(), obs.stride(0), n, ctypes.c_uint64(self.seed), ctypes.c_int64(step),
                                                 ctypes.c_int64(self.env_offset), 1 if deterministic else 0, actions.data_ptr(), mean.data_ptr(),
                                                 value.data_ptr(), logp.data_ptr(), None if obs_copy is None else obs_copy.data_ptr(),
                                                 None if sigma_out is None else sigma_out.data_ptr(), self._stream()))
@@ -78,11 +89,11 @@ class FusedPolicy:
 
     @property
     def launches(self) -> int:
-        return int(_lib.lib.nm_policy_launches(self._h))
+        return self._launches
 
     def __del__(self):
         if getattr(self, "_h", None) and getattr(_lib, "lib", None) is not None:
-            _lib.lib.nm_policy_destroy(self._h)
+            self._fn[1](self._h)
             self._h = None
 
 

@@ -220,7 +220,8 @@ class PPO:
         stream = ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
         # the policy launch also writes the rollout buffer's copy of the observations and the std row (the env is about
         # to overwrite its observation buffer); the post-step store then only adds rewards / dones / statistics
-        _lib.check(_lib.lib.nm_policy_act_store(f._h, b.obs.data_ptr(), slot.obs_dim, slot.n, ctypes.c_uint64(f.seed), ctypes.c_int64(self._act_calls),
+        f._launches += 1
+        _lib.check(f._fn[3](f._h, b.obs.data_ptr(), slot.obs_dim, slot.n, ctypes.c_uint64(f.seed), ctypes.c_int64(self._act_calls),
                                                 ctypes.c_int64(f.env_offset), 0, slot.s_actions, slot.s_mu, slot.s_values, slot.s_logp,
                                                 slot.s_obs, slot.s_sigma, stream))
         env.fast_step(act_row)

@@ -22,11 +22,13 @@ def _ac(seed=0):
     return ac
 
 
+@pytest.mark.parametrize("engine", ["tc5", "mma"])
 @pytest.mark.parametrize("n", [1, 15, 64, 1000, 4096])
-def test_policy_kernel_matches_torch_fp32(n):
+def test_policy_kernel_matches_torch_fp32(n, engine):
     from nightmare_rl_b200.ppo.policy_kernel import FusedPolicy
     ac = _ac()
-    fp = FusedPolicy(ac, DEV, seed=5)
+    fp = FusedPolicy(ac, DEV, seed=5, engine=engine)
+    assert fp.engine == engine
     obs = torch.randn(n, 66, device=DEV) * 2.0
     actions, mean, value, logp = fp.act(obs, step=3)
     torch.cuda.synchronize()
@@ -45,10 +47,11 @@ def test_policy_kernel_matches_torch_fp32(n):
     assert torch.equal(actions, a2) and not torch.equal(actions, a3) and torch.equal(ad, md)
 
 
-def test_policy_noise_is_standard_normal_and_weights_reload():
+@pytest.mark.parametrize("engine", ["tc5", "mma"])
+def test_policy_noise_is_standard_normal_and_weights_reload(engine):
     from nightmare_rl_b200.ppo.policy_kernel import FusedPolicy
     ac = _ac(1)
-    fp = FusedPolicy(ac, DEV, seed=9)
+    fp = FusedPolicy(ac, DEV, seed=9, engine=engine)
     obs = torch.randn(8192, 66, device=DEV)
     actions, mean, _, _ = fp.act(obs, step=1)
     z = ((actions - mean) / ac.std.detach()).flatten()
