@@ -324,7 +324,7 @@ __device__ __forceinline__ void resample_commands(const NmDevCfg& c, unsigned lo
   cmd[0] = cx * keep; cmd[1] = cy * keep; cmd[2] = cw;
 }
 
-// per-lane contact blocks (local memory, L1-resident): 53 floats per contact.  The three whitened contact-frame
+// per-lane contact blocks (local memory, L1-resident): 55 floats per contact.  The three whitened contact-frame
 // rows couple a contact to the rest of the system; the 4x4 Gram matrix of its own pyramid edges Jn +- mu*Jt
 // (computed from the edge vectors themselves, no cancellation) carries the coupling among its four rows.
 struct ConBlk {
@@ -334,10 +334,89 @@ struct ConBlk {
   float adi[NM_MAXC][4];    // 1 / (|edge|^2 + R)
   float G[NM_MAXC][10];     // Gram matrix of the 4 pyramid edges (= A restricted to this contact, without R):
                             //   00 11 22 33 | 01 23 (opposing pairs) | 02 03 12 13 (across the two tangents)
+  float ik[NM_MAXC][2];     // 1 / (G_aa + G_bb - 2 G_ab) of the two opposing pairs (noslip curvature), 0 if degenerate
   float f[NM_MAXC][4];      // pyramid-edge forces
   float R[NM_MAXC];
   V3 pos[NM_MAXC];
 };
+
+// register image of one contact block, and one Gauss-Seidel visit of it (PGS: 4 single edges with R; noslip: 2 pairs)
+struct ConRegs { float Y[3][6], Z[3][3], G[10], b[4], adi[4], R, f[4], ik[2]; };
+__device__ __forceinline__ void con_load(const ConBlk& cb, int c, ConRegs& k) {
+#pragma unroll
+  for (int f = 0; f < 3; f++) {
+#pragma unroll
+    for (int a = 0; a < 6; a++) k.Y[f][a] = cb.Y[c][f][a];
+#pragma unroll
+    for (int j = 0; j < 3; j++) k.Z[f][j] = cb.Z[c][f][j];
+  }
+#pragma unroll
+  for (int i = 0; i < 10; i++) k.G[i] = cb.G[c][i];
+#pragma unroll
+  for (int i = 0; i < 4; i++) { k.b[i] = cb.b[c][i]; k.adi[i] = cb.adi[c][i]; k.f[i] = cb.f[c][i]; }
+  k.R = cb.R[c];
+  k.ik[0] = cb.ik[c][0]; k.ik[1] = cb.ik[c][1];
+}
+// Residuals of the 4 edges against the CURRENT dual state, all at once: r_e = b_e + (p0 +- mu*p_t), p_a = Y_a.u + Z_a.w
+// (three independent dot products); the Gauss-Seidel coupling among the 4 rows of the contact is then applied through its
+// edge Gram matrix instead of re-walking u after every row.
+__device__ __forceinline__ void con_sweep(ConRegs& k, float* u, float* wv, float mu, bool in_noslip, float& improvement) {
+  float p0 = 0.f, p1 = 0.f, p2 = 0.f;
+#pragma unroll
+  for (int a = 0; a < 6; a++) { const float ua = u[a]; p0 = fmaf(k.Y[0][a], ua, p0); p1 = fmaf(k.Y[1][a], ua, p1); p2 = fmaf(k.Y[2][a], ua, p2); }
+#pragma unroll
+  for (int j = 0; j < 3; j++) { const float wj = wv[j]; p0 = fmaf(k.Z[0][j], wj, p0); p1 = fmaf(k.Z[1][j], wj, p1); p2 = fmaf(k.Z[2][j], wj, p2); }
+  float r[4] = {k.b[0] + fmaf(mu, p1, p0), k.b[1] + fmaf(-mu, p1, p0), k.b[2] + fmaf(mu, p2, p0), k.b[3] + fmaf(-mu, p2, p0)};
+  float* o = k.f;
+  float d[4];
+  const float g00 = k.G[0], g11 = k.G[1], g22 = k.G[2], g33 = k.G[3], g01 = k.G[4], g23 = k.G[5];
+  const float g02 = k.G[6], g03 = k.G[7], g12 = k.G[8], g13 = k.G[9];
+  if (!in_noslip) {
+    const float R = k.R;
+    const float gd[4] = {g00, g11, g22, g33};
+#pragma unroll
+    for (int e = 0; e < 4; e++) {
+      const float res = fmaf(R, o[e], r[e]);
+      float fnew = fmaxf(0.f, fmaf(-res, k.adi[e], o[e]));
+      float de = fnew - o[e];
+      float change = de * fmaf(0.5f * de, gd[e] + R, res);
+      if (change > 1e-10f) { de = 0.f; fnew = o[e]; change = 0.f; }
+      improvement -= change;
+      o[e] = fnew; d[e] = de;
+      if (e == 0) { r[1] = fmaf(de, g01, r[1]); r[2] = fmaf(de, g02, r[2]); r[3] = fmaf(de, g03, r[3]); }
+      if (e == 1) { r[2] = fmaf(de, g12, r[2]); r[3] = fmaf(de, g13, r[3]); }
+      if (e == 2) { r[3] = fmaf(de, g23, r[3]); }
+    }
+  } else {
+#pragma unroll
+    for (int t = 0; t < 2; t++) {
+      const float a00 = t ? g22 : g00, a11 = t ? g33 : g11, a01 = t ? g23 : g01;
+      const float o0 = o[2 * t], o1 = o[2 * t + 1], res0 = r[2 * t], res1 = r[2 * t + 1];
+      const float bc0 = res0 - a00 * o0 - a01 * o1, bc1 = res1 - a01 * o0 - a11 * o1;
+      const float mid = 0.5f * (o0 + o1);
+      const float K0 = mid * (a00 - a11) + bc0 - bc1;
+      float f0, f1;
+      if (k.ik[t] == 0.f) { f0 = mid; f1 = mid; }
+      else {
+        float x = -K0 * k.ik[t];
+        if (x < -mid) { f0 = 0.f; f1 = 2.f * mid; }
+        else if (x > mid) { f0 = 2.f * mid; f1 = 0.f; }
+        else { f0 = mid + x; f1 = mid - x; }
+      }
+      float d0 = f0 - o0, d1 = f1 - o1;
+      float change = 0.5f * (d0 * (a00 * d0 + a01 * d1) + d1 * (a01 * d0 + a11 * d1)) + d0 * res0 + d1 * res1;
+      if (change > 1e-10f) { f0 = o0; f1 = o1; d0 = 0.f; d1 = 0.f; change = 0.f; }
+      improvement -= change;
+      o[2 * t] = f0; o[2 * t + 1] = f1; d[2 * t] = d0; d[2 * t + 1] = d1;
+      if (t == 0) { r[2] = fmaf(d0, g02, fmaf(d1, g12, r[2])); r[3] = fmaf(d0, g03, fmaf(d1, g13, r[3])); }
+    }
+  }
+  const float c0 = (d[0] + d[1]) + (d[2] + d[3]), c1 = mu * (d[0] - d[1]), c2 = mu * (d[2] - d[3]);
+#pragma unroll
+  for (int a = 0; a < 6; a++) u[a] = fmaf(k.Y[0][a], c0, fmaf(k.Y[1][a], c1, fmaf(k.Y[2][a], c2, u[a])));
+#pragma unroll
+  for (int j = 0; j < 3; j++) wv[j] = fmaf(k.Z[0][j], c0, fmaf(k.Z[1][j], c1, fmaf(k.Z[2][j], c2, wv[j])));
+}
 
 enum { RW_ACTION_RATE = 0, RW_ANG_VEL_XY, RW_BASE_HEIGHT, RW_BODY_CONTACT_FORCES, RW_COLLISION, RW_DEFAULT_POSITION,
        RW_DOF_ACC, RW_DOF_VEL, RW_FEET_AIR_TIME, RW_FEET_CONTACT_FORCES, RW_FEET_STUMBLE, RW_LIN_VEL_Z, RW_ORIENTATION,
@@ -754,6 +833,12 @@ __global__ void __launch_bounds__(BLOCK, MINB) nm_step_kernel(const NmKernelArgs
             cb.G[c][k] = t;
             if (k < 4) cb.adi[c][k] = 1.f / (t + R);
           }
+          // noslip pair curvature K1 = a00 + a11 - 2 a01 is a constant of the contact: inverted once (0 = degenerate)
+#pragma unroll
+          for (int t = 0; t < 2; t++) {
+            const float K1 = cb.G[c][2 * t] + cb.G[c][2 * t + 1] - 2.f * cb.G[c][4 + t];
+            cb.ik[c][t] = K1 < NM_MINVAL ? 0.f : 1.f / K1;
+          }
 #pragma unroll
           for (int e = 0; e < 4; e++) {
             const float sg = (e & 1) ? -mu : mu;
@@ -802,6 +887,11 @@ __global__ void __launch_bounds__(BLOCK, MINB) nm_step_kernel(const NmKernelArgs
 
       // ---- sweeps: rows in contact order (base geom first, then legs 1..6), Gauss-Seidel through u.
       // sweep 0..iterations-1: PGS on single edges (with R); then noslip on opposing edge pairs (without R, sum fixed).
+      // the 255-register instantiation keeps this lane's first contact block in registers for all sweeps; the
+      // 128-register one (large batches, throughput bound) would only spill it, and re-reads it from local memory
+      constexpr bool kCache0 = BLOCK == 128;
+      ConRegs k0;
+      if (kCache0) con_load(cb, 0, k0);
       const int npgs = sm.iterations, nsweep = sm.iterations + sm.noslip_iterations;
       bool active = ncon_env > 0;
       bool in_noslip = false;
@@ -836,69 +926,12 @@ __global__ void __launch_bounds__(BLOCK, MINB) nm_step_kernel(const NmKernelArgs
           // lane of this octet that owns slot `slot` (none: broadcast from lane 0, u is unchanged there)
           const int owner = (owner_tab >> (4 * slot)) & 0xf;
           if (active && nc > 0 && my_slot == slot) {
-            for (int c = 0; c < nc; c++) {
-              // residuals of the 4 edges against the CURRENT dual state, all at once: r_e = b_e + (p0 +- mu*p_t),
-              // p_a = Y_a.u + Z_a.w (three independent dot products); the Gauss-Seidel coupling among the 4 rows of
-              // this contact is then applied through its edge Gram matrix instead of re-walking u after every row.
-              float p0 = 0.f, p1 = 0.f, p2 = 0.f;
-#pragma unroll
-              for (int a = 0; a < 6; a++) { const float ua = u[a]; p0 = fmaf(cb.Y[c][0][a], ua, p0); p1 = fmaf(cb.Y[c][1][a], ua, p1); p2 = fmaf(cb.Y[c][2][a], ua, p2); }
-#pragma unroll
-              for (int j = 0; j < 3; j++) { const float wj = wv[j]; p0 = fmaf(cb.Z[c][0][j], wj, p0); p1 = fmaf(cb.Z[c][1][j], wj, p1); p2 = fmaf(cb.Z[c][2][j], wj, p2); }
-              float r[4] = {cb.b[c][0] + fmaf(mu, p1, p0), cb.b[c][1] + fmaf(-mu, p1, p0), cb.b[c][2] + fmaf(mu, p2, p0), cb.b[c][3] + fmaf(-mu, p2, p0)};
-              float o[4] = {cb.f[c][0], cb.f[c][1], cb.f[c][2], cb.f[c][3]};
-              float d[4];
-              const float g00 = cb.G[c][0], g11 = cb.G[c][1], g22 = cb.G[c][2], g33 = cb.G[c][3], g01 = cb.G[c][4], g23 = cb.G[c][5];
-              const float g02 = cb.G[c][6], g03 = cb.G[c][7], g12 = cb.G[c][8], g13 = cb.G[c][9];
-              if (!in_noslip) {
-                // PGS: edges one after the other, each with its regulariser R
-                const float R = cb.R[c];
-                const float gd[4] = {g00, g11, g22, g33};
-#pragma unroll
-                for (int e = 0; e < 4; e++) {
-                  const float res = fmaf(R, o[e], r[e]);
-                  float fnew = fmaxf(0.f, fmaf(-res, cb.adi[c][e], o[e]));
-                  float de = fnew - o[e];
-                  float change = de * fmaf(0.5f * de, gd[e] + R, res);
-                  if (change > 1e-10f) { de = 0.f; fnew = o[e]; change = 0.f; }
-                  improvement -= change;
-                  o[e] = fnew; d[e] = de;
-                  if (e == 0) { r[1] = fmaf(de, g01, r[1]); r[2] = fmaf(de, g02, r[2]); r[3] = fmaf(de, g03, r[3]); }
-                  if (e == 1) { r[2] = fmaf(de, g12, r[2]); r[3] = fmaf(de, g13, r[3]); }
-                  if (e == 2) { r[3] = fmaf(de, g23, r[3]); }
-                }
-              } else {
-                // noslip: each opposing pair re-solved jointly without R, its sum kept fixed
-#pragma unroll
-                for (int t = 0; t < 2; t++) {
-                  const float a00 = t ? g22 : g00, a11 = t ? g33 : g11, a01 = t ? g23 : g01;
-                  const float o0 = o[2 * t], o1 = o[2 * t + 1], res0 = r[2 * t], res1 = r[2 * t + 1];
-                  const float bc0 = res0 - a00 * o0 - a01 * o1, bc1 = res1 - a01 * o0 - a11 * o1;
-                  const float mid = 0.5f * (o0 + o1);
-                  const float K1 = a00 + a11 - 2.f * a01;
-                  const float K0 = mid * (a00 - a11) + bc0 - bc1;
-                  float f0, f1;
-                  if (K1 < NM_MINVAL) { f0 = mid; f1 = mid; }
-                  else {
-                    float x = -K0 / K1;
-                    if (x < -mid) { f0 = 0.f; f1 = 2.f * mid; }
-                    else if (x > mid) { f0 = 2.f * mid; f1 = 0.f; }
-                    else { f0 = mid + x; f1 = mid - x; }
-                  }
-                  float d0 = f0 - o0, d1 = f1 - o1;
-                  float change = 0.5f * (d0 * (a00 * d0 + a01 * d1) + d1 * (a01 * d0 + a11 * d1)) + d0 * res0 + d1 * res1;
-                  if (change > 1e-10f) { f0 = o0; f1 = o1; d0 = 0.f; d1 = 0.f; change = 0.f; }
-                  improvement -= change;
-                  o[2 * t] = f0; o[2 * t + 1] = f1; d[2 * t] = d0; d[2 * t + 1] = d1;
-                  if (t == 0) { r[2] = fmaf(d0, g02, fmaf(d1, g12, r[2])); r[3] = fmaf(d0, g03, fmaf(d1, g13, r[3])); }
-                }
-              }
-              cb.f[c][0] = o[0]; cb.f[c][1] = o[1]; cb.f[c][2] = o[2]; cb.f[c][3] = o[3];
-              const float c0 = (d[0] + d[1]) + (d[2] + d[3]), c1 = mu * (d[0] - d[1]), c2 = mu * (d[2] - d[3]);
-#pragma unroll
-              for (int a = 0; a < 6; a++) u[a] = fmaf(cb.Y[c][0][a], c0, fmaf(cb.Y[c][1][a], c1, fmaf(cb.Y[c][2][a], c2, u[a])));
-#pragma unroll
-              for (int j = 0; j < 3; j++) wv[j] = fmaf(cb.Z[c][0][j], c0, fmaf(cb.Z[c][1][j], c1, fmaf(cb.Z[c][2][j], c2, wv[j])));
+            if (kCache0) con_sweep(k0, u, wv, mu, in_noslip, improvement);   // first contact of the lane: cached in registers
+            for (int c = kCache0 ? 1 : 0; c < nc; c++) {                      // further contacts (rare): through local memory
+              ConRegs kc;
+              con_load(cb, c, kc);
+              con_sweep(kc, u, wv, mu, in_noslip, improvement);
+              cb.f[c][0] = kc.f[0]; cb.f[c][1] = kc.f[1]; cb.f[c][2] = kc.f[2]; cb.f[c][3] = kc.f[3];
             }
           }
 #pragma unroll
@@ -908,6 +941,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) nm_step_kernel(const NmKernelArgs
         if (active) { if (in_noslip) dbg_noslip++; else dbg_pgs++; }
         if (improvement * sm.solver_scale < (in_noslip ? sm.noslip_tolerance : sm.tolerance)) active = false;
       }
+      if (kCache0 && nc > 0) { cb.f[0][0] = k0.f[0]; cb.f[0][1] = k0.f[1]; cb.f[0][2] = k0.f[2]; cb.f[0][3] = k0.f[3]; }
       // final constraint acceleration x = M^-1 J^T f
       {
         bwd6(F.S, F.Si, u, xb);
