@@ -39,7 +39,7 @@ UNIT = "env-steps/s"
 BYTES_PER_ENV_STEP = 1464
 FLOPS_PER_ENV_STEP = 71_800
 # dram__bytes_read.sum + dram__bytes_write.sum of nm_step_kernel<true> per 4096-env launch (ncu --set full, profiles/r01_notes.md)
-NCU_DRAM_BYTES_PER_LAUNCH_4096 = 4_414_208
+NCU_DRAM_BYTES_PER_LAUNCH_4096 = 11_502_848
 
 
 def _workload(envs_per_gpu, decimation=2):

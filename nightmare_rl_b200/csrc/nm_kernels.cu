@@ -430,6 +430,10 @@ enum { RW_ACTION_RATE = 0, RW_ANG_VEL_XY, RW_BASE_HEIGHT, RW_BODY_CONTACT_FORCES
 #define NM_LARGE_BLOCK 256
 #define NM_LARGE_MINB 2
 #endif
+#ifndef NM_SMALL_BLOCK
+#define NM_SMALL_BLOCK 128
+#define NM_SMALL_MINB 2
+#endif
 template <bool ENV, int BLOCK, int MINB>
 __global__ void __launch_bounds__(BLOCK, MINB) nm_step_kernel(const NmKernelArgs A) {
   __shared__ NmDevModel sm;
@@ -889,7 +893,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) nm_step_kernel(const NmKernelArgs
       // sweep 0..iterations-1: PGS on single edges (with R); then noslip on opposing edge pairs (without R, sum fixed).
       // the 255-register instantiation keeps this lane's first contact block in registers for all sweeps; the
       // 128-register one (large batches, throughput bound) would only spill it, and re-reads it from local memory
-      constexpr bool kCache0 = BLOCK == 128;
+      constexpr bool kCache0 = BLOCK * MINB <= 256;          // i.e. the 255-register budget
       ConRegs k0;
       if (kCache0) con_load(cb, 0, k0);
       const int npgs = sm.iterations, nsweep = sm.iterations + sm.noslip_iterations;
@@ -1347,9 +1351,9 @@ void nm_launch_step(const NmKernelArgs& a, bool env_mode, void* stream) {
   }
   const bool one_wave = threads <= sms * 8 * 32;           // fits one wave of the 255-register build (8 warps/SM)
   if (one_wave) {
-    const int blocks = (threads + 127) / 128;
-    if (env_mode) nm_step_kernel<true, 128, 2><<<blocks, 128, 0, st>>>(a);
-    else nm_step_kernel<false, 128, 2><<<blocks, 128, 0, st>>>(a);
+    const int blocks = (threads + NM_SMALL_BLOCK - 1) / NM_SMALL_BLOCK;
+    if (env_mode) nm_step_kernel<true, NM_SMALL_BLOCK, NM_SMALL_MINB><<<blocks, NM_SMALL_BLOCK, 0, st>>>(a);
+    else nm_step_kernel<false, NM_SMALL_BLOCK, NM_SMALL_MINB><<<blocks, NM_SMALL_BLOCK, 0, st>>>(a);
   } else {
     const int blocks = (threads + NM_LARGE_BLOCK - 1) / NM_LARGE_BLOCK;
     if (env_mode) nm_step_kernel<true, NM_LARGE_BLOCK, NM_LARGE_MINB><<<blocks, NM_LARGE_BLOCK, 0, st>>>(a);

@@ -89,13 +89,30 @@ __device__ __forceinline__ int t5_idx(int row, int col, int kpad) { return (row 
 
 // One network over the CTA's 128-row tile.  On entry A_hi/A_lo hold the observations (layout for kpad of layer 0).
 // Hidden layers rewrite A_hi/A_lo; the last layer's accumulator row is returned in out[] (first kout entries).
-__device__ __forceinline__ void t5_net(const T5Net& net, const float* gsrc, float* A_hi, float* A_lo, float* W, float* Bias, unsigned tmem,
-                                       unsigned long long* bar, unsigned& phase, float* out) {
+// one thread: TMA bulk copy (cp.async.bulk, SASS UBLKCP) of a network's packed weights [W_hi | W_lo | bias] into smem
+__device__ __forceinline__ void t5_issue_weights(const T5Net& net, const float* gsrc, float* W, unsigned long long* wbar) {
+  const unsigned bytes = (unsigned)(2 * net.plane_floats + net.bias_floats) * 4u;
+  const unsigned b32 = smem_u32(wbar);
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");          // earlier generic-proxy reads of W precede the async write
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b32), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(W)), "l"(gsrc), "r"(bytes),
+               "r"(b32)
+               : "memory");
+}
+__device__ __forceinline__ void t5_wait(unsigned long long* bar, unsigned parity) {
+  unsigned done = 0, spins = 0;
+  const unsigned b32 = smem_u32(bar);
+  while (!done) {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done) : "r"(b32), "r"(parity) : "memory");
+    if (++spins > (1u << 24)) { asm volatile("trap;"); }                  // never hang the GPU on a bad descriptor
+  }
+}
+
+__device__ __forceinline__ void t5_net(const T5Net& net, float* A_hi, float* A_lo, float* W, unsigned tmem, unsigned long long* bar,
+                                       unsigned& phase, unsigned long long* wbar, unsigned wparity, float* out) {
   const int tid = threadIdx.x, warp = tid >> 5;
-  // stage this network's weights (hi plane, lo plane, biases) — already in the canonical layout in global memory
-  const int nw = 2 * net.plane_floats + net.bias_floats;
-  for (int i = tid; i < nw; i += T5_ROWS) W[i] = __ldg(gsrc + i);
-  (void)Bias;
+  t5_wait(wbar, wparity);                                    // this network's weights have landed (bulk copy issued earlier)
   const float* bias = W + 2 * net.plane_floats;
   for (int l = 0; l < net.nl; l++) {
     const T5Layer& L = net.L[l];
@@ -118,17 +135,8 @@ __device__ __forceinline__ void t5_net(const T5Net& net, const float* gsrc, floa
       }
       asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
     }
-    // everyone waits for the accumulator of this layer
-    {
-      unsigned done = 0, spins = 0;
-      const unsigned b32 = smem_u32(bar);
-      while (!done) {
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(done) : "r"(b32), "r"(phase) : "memory");
-        if (++spins > (1u << 24)) { asm volatile("trap;"); }                // never hang the GPU on a bad descriptor
-      }
-      phase ^= 1u;
-    }
+    t5_wait(bar, phase);                                     // everyone waits for the accumulator of this layer
+    phase ^= 1u;
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const unsigned taddr = tmem + ((unsigned)(warp * 32) << 16);
     const bool last = l == net.nl - 1;
@@ -161,7 +169,7 @@ __device__ __forceinline__ void t5_net(const T5Net& net, const float* gsrc, floa
 
 __global__ void __launch_bounds__(T5_ROWS, 1) nm_policy_tc5_kernel(const T5Args A) {
   extern __shared__ __align__(1024) float t5_smem[];
-  __shared__ __align__(8) unsigned long long bar;
+  __shared__ __align__(8) unsigned long long bar, wbar;
   __shared__ unsigned tmem_base_s;
   const int tid = threadIdx.x, warp = tid >> 5;
   const int kp0 = A.actor.L[0].kpad, kin = A.actor.L[0].kin;
@@ -174,6 +182,7 @@ __global__ void __launch_bounds__(T5_ROWS, 1) nm_policy_tc5_kernel(const T5Args 
   }
   if (tid == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&wbar)));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -197,10 +206,12 @@ __global__ void __launch_bounds__(T5_ROWS, 1) nm_policy_tc5_kernel(const T5Args 
   };
   const int a_floats = 2 * A.actor.plane_floats + A.actor.bias_floats;
   float vout[32], mout[32];
+  if (tid == 0) t5_issue_weights(A.critic, A.packed + a_floats, W, &wbar);     // lands while the observations are staged
   stage_obs();
-  t5_net(A.critic, A.packed + a_floats, A_hi, A_lo, W, nullptr, tmem, &bar, phase, vout);
+  t5_net(A.critic, A_hi, A_lo, W, tmem, &bar, phase, &wbar, 0u, vout);
+  if (tid == 0) t5_issue_weights(A.actor, A.packed, W, &wbar);                 // critic MMAs are complete: reuse the buffer
   stage_obs();
-  t5_net(A.actor, A.packed, A_hi, A_lo, W, nullptr, tmem, &bar, phase, mout);
+  t5_net(A.actor, A_hi, A_lo, W, tmem, &bar, phase, &wbar, 1u, mout);
 
   // ---- epilogue: thread r = environment r of the tile
   const int e = row0 + tid;
