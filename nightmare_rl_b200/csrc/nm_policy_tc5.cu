@@ -22,6 +22,7 @@
 #include "../../include/nightmare_b200.h"
 
 #define T5_ROWS 128
+#define T5_THREADS 256
 #define T5_MAXL 6
 #define T5_TMEM_COLS 64
 
@@ -61,15 +62,14 @@ __device__ __forceinline__ void t5_mma(unsigned tmem_d, unsigned long long a, un
   asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
                ::"r"(tmem_d), "l"(a), "l"(b), "r"(idesc), "r"(accumulate) : "memory");
 }
-__device__ __forceinline__ void t5_ld16(unsigned taddr, float* v) {
-  unsigned r[16];
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-                 "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+__device__ __forceinline__ void t5_ld8(unsigned taddr, float* v) {
+  unsigned r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
                : "r"(taddr));
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-  for (int i = 0; i < 16; i++) v[i] = __uint_as_float(r[i]);
+  for (int i = 0; i < 8; i++) v[i] = __uint_as_float(r[i]);
 }
 
 __device__ __noinline__ void t5_philox(unsigned k0, unsigned k1, unsigned c0, unsigned c1, unsigned c2, unsigned c3, unsigned* out) {
@@ -109,9 +109,14 @@ __device__ __forceinline__ void t5_wait(unsigned long long* bar, unsigned parity
   }
 }
 
-__device__ __forceinline__ void t5_net(const T5Net& net, float* A_hi, float* A_lo, float* W, unsigned tmem, unsigned long long* bar,
-                                       unsigned& phase, unsigned long long* wbar, unsigned wparity, float* out) {
-  const int tid = threadIdx.x, warp = tid >> 5;
+// One network over the CTA's 128-row tile.  Layer 0 reads the observation operand (X), hidden layers read and rewrite the
+// hidden operand (H; in place is safe: the MMAs of a layer have completed before its epilogue runs).  256 threads: warp w
+// owns accumulator lanes 32*(w&3).. (rows of the tile) and the column half (w>>2) of every layer's output; the last
+// layer's half row is returned in out[0..16).
+__device__ __forceinline__ void t5_net(const T5Net& net, const float* X_hi, const float* X_lo, float* H_hi, float* H_lo, float* W, unsigned tmem,
+                                       unsigned long long* bar, unsigned& phase, unsigned long long* wbar, unsigned wparity, float* out) {
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int row = (warp & 3) * 32 + lane, half = warp >> 2;
   t5_wait(wbar, wparity);                                    // this network's weights have landed (bulk copy issued earlier)
   const float* bias = W + 2 * net.plane_floats;
   for (int l = 0; l < net.nl; l++) {
@@ -122,7 +127,7 @@ __device__ __forceinline__ void t5_net(const T5Net& net, float* A_hi, float* A_l
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const unsigned idesc = t5_idesc(L.npad);
       const unsigned sbo = (unsigned)(L.kpad >> 2) * 128u;
-      const unsigned a_hi = smem_u32(A_hi), a_lo = smem_u32(A_lo);
+      const unsigned a_hi = smem_u32(l == 0 ? X_hi : H_hi), a_lo = smem_u32(l == 0 ? X_lo : H_lo);
       const unsigned w_hi = smem_u32(W + L.w_off), w_lo = smem_u32(W + net.plane_floats + L.w_off);
       const int nks = L.kpad >> 3;
       for (int ks = 0; ks < nks; ks++) {
@@ -138,26 +143,26 @@ __device__ __forceinline__ void t5_net(const T5Net& net, float* A_hi, float* A_l
     t5_wait(bar, phase);                                     // everyone waits for the accumulator of this layer
     phase ^= 1u;
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const unsigned taddr = tmem + ((unsigned)(warp * 32) << 16);
     const bool last = l == net.nl - 1;
-    const int kp_next = L.npad;
+    const int kp_next = L.npad, ncol = L.npad >> 1, cbeg = half * ncol;      // this warp's column range [cbeg, cbeg + ncol)
+    const unsigned taddr = tmem + ((unsigned)((warp & 3) * 32) << 16) + (unsigned)cbeg;
+    const int rbase = (row >> 3) * (kp_next >> 2) * 32 + (row & 7) * 4;
 #pragma unroll
     for (int cc = 0; cc < T5_TMEM_COLS / 16; cc++) {           // compile-time column blocks keep out[] in registers
-      const int c0 = cc * 16;
-      if (c0 < L.npad) {
-        float v[16];
-        t5_ld16(taddr + (unsigned)c0, v);
+      if (cc * 8 < ncol) {
+        float v[8];
+        t5_ld8(taddr + (unsigned)(cc * 8), v);
 #pragma unroll
-        for (int i = 0; i < 16; i++) {
-          const int col = c0 + i;
+        for (int i = 0; i < 8; i++) {
+          const int col = cbeg + cc * 8 + i;
           float x = v[i] + bias[L.b_off + col];
-          if (last) { if (col < 32) out[col < 32 ? col : 0] = x; }
+          if (last) { if (cc < 2) out[(cc < 2 ? cc : 0) * 8 + i] = x; }
           else {
-            x = (col < L.kout) ? (x > 0.f ? x : expm1f(x)) : 0.f;           // ELU; padded columns stay exactly zero
+            x = (col < L.kout) ? (x > 0.f ? x : __expf(x) - 1.f) : 0.f;      // ELU; padded columns stay exactly zero
             const unsigned h = t5_tf32(x);
-            const int idx = t5_idx(tid, col, kp_next);
-            A_hi[idx] = __uint_as_float(h);
-            A_lo[idx] = __uint_as_float(t5_tf32(x - __uint_as_float(h)));
+            const int idx = rbase + (col >> 2) * 32 + (col & 3);
+            H_hi[idx] = __uint_as_float(h);
+            H_lo[idx] = __uint_as_float(t5_tf32(x - __uint_as_float(h)));
           }
         }
       }
@@ -167,15 +172,18 @@ __device__ __forceinline__ void t5_net(const T5Net& net, float* A_hi, float* A_l
   __syncthreads();
 }
 
-__global__ void __launch_bounds__(T5_ROWS, 1) nm_policy_tc5_kernel(const T5Args A) {
+__global__ void __launch_bounds__(T5_THREADS, 1) nm_policy_tc5_kernel(const T5Args A) {
   extern __shared__ __align__(1024) float t5_smem[];
   __shared__ __align__(8) unsigned long long bar, wbar;
   __shared__ unsigned tmem_base_s;
-  const int tid = threadIdx.x, warp = tid >> 5;
+  __shared__ float lp_s[T5_ROWS];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int kp0 = A.actor.L[0].kpad, kin = A.actor.L[0].kin;
-  float* A_hi = t5_smem;
-  float* A_lo = A_hi + T5_ROWS * 72;
-  float* W = A_lo + T5_ROWS * 72;
+  float* X_hi = t5_smem;                                       // observations  [128 x 72], hi / lo TF32 planes
+  float* X_lo = X_hi + T5_ROWS * 72;
+  float* H_hi = X_lo + T5_ROWS * 72;                           // hidden activations [128 x <=64]
+  float* H_lo = H_hi + T5_ROWS * 64;
+  float* W = H_lo + T5_ROWS * 64;
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"((unsigned)T5_TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -185,73 +193,74 @@ __global__ void __launch_bounds__(T5_ROWS, 1) nm_policy_tc5_kernel(const T5Args 
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&wbar)));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  if (tid < T5_ROWS) lp_s[tid] = 0.f;
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const unsigned tmem = tmem_base_s;
   const int row0 = blockIdx.x * T5_ROWS;
   unsigned phase = 0;
-
-  auto stage_obs = [&]() {
-    for (int idx = tid; idx < T5_ROWS * kp0; idx += T5_ROWS) {
-      const int r = idx / kp0, c = idx - r * kp0;
-      const int e = row0 + r;
-      const float x = (c < kin && e < A.n) ? A.obs[(size_t)e * A.obs_stride + c] : 0.f;
-      const unsigned h = t5_tf32(x);
-      const int j = t5_idx(r, c, kp0);
-      A_hi[j] = __uint_as_float(h);
-      A_lo[j] = __uint_as_float(t5_tf32(x - __uint_as_float(h)));
-      if (A.obs_copy != nullptr && c < kin && e < A.n) A.obs_copy[(size_t)e * kin + c] = x;
-    }
-  };
   const int a_floats = 2 * A.actor.plane_floats + A.actor.bias_floats;
-  float vout[32], mout[32];
   if (tid == 0) t5_issue_weights(A.critic, A.packed + a_floats, W, &wbar);     // lands while the observations are staged
-  stage_obs();
-  t5_net(A.critic, A_hi, A_lo, W, tmem, &bar, phase, &wbar, 0u, vout);
+  // observations: staged once (both networks read them), split into TF32 hi/lo planes in the UMMA operand layout
+  for (int idx = tid; idx < T5_ROWS * kp0; idx += T5_THREADS) {
+    const int r = idx / kp0, c = idx - r * kp0;
+    const int e = row0 + r;
+    const float x = (c < kin && e < A.n) ? A.obs[(size_t)e * A.obs_stride + c] : 0.f;
+    const unsigned h = t5_tf32(x);
+    const int j = t5_idx(r, c, kp0);
+    X_hi[j] = __uint_as_float(h);
+    X_lo[j] = __uint_as_float(t5_tf32(x - __uint_as_float(h)));
+    if (A.obs_copy != nullptr && c < kin && e < A.n) A.obs_copy[(size_t)e * kin + c] = x;
+  }
+  float vout[16], mout[16];
+  t5_net(A.critic, X_hi, X_lo, H_hi, H_lo, W, tmem, &bar, phase, &wbar, 0u, vout);
   if (tid == 0) t5_issue_weights(A.actor, A.packed, W, &wbar);                 // critic MMAs are complete: reuse the buffer
-  stage_obs();
-  t5_net(A.actor, A_hi, A_lo, W, tmem, &bar, phase, &wbar, 1u, mout);
+  t5_net(A.actor, X_hi, X_lo, H_hi, H_lo, W, tmem, &bar, phase, &wbar, 1u, mout);
 
-  // ---- epilogue: thread r = environment r of the tile
-  const int e = row0 + tid;
+  // ---- epilogue: thread (row, half) = environment row of the tile, action columns [16*half, 16*half + 16)
+  const int row = (warp & 3) * 32 + lane, half = warp >> 2;
+  const int e = row0 + row;
   if (e < A.n) {
     const float* stdv = A.packed + a_floats + 2 * A.critic.plane_floats + A.critic.bias_floats;
-    A.value[e] = vout[0];
+    if (half == 0) A.value[e] = vout[0];
     float lp = 0.f;
-    const int ngrp = (A.act_dim + 3) >> 2;
-    for (int q = 0; q < ngrp; q++) {
-      float z[4] = {0.f, 0.f, 0.f, 0.f};
-      if (!A.deterministic) {
-        unsigned rn[4];
-        const long long genv = A.env_offset + e;
-        t5_philox((unsigned)A.seed, (unsigned)genv, (unsigned)A.step, (unsigned)((unsigned long long)A.step >> 32), 0x40000000u + (unsigned)q,
-                  (unsigned)(A.seed >> 32) ^ (unsigned)((unsigned long long)genv >> 32), rn);
-        const float u0 = ((float)(rn[0] >> 8) + 1.f) * (1.f / 16777216.f), u1 = (float)(rn[1] >> 8) * (1.f / 16777216.f);
-        const float u2 = ((float)(rn[2] >> 8) + 1.f) * (1.f / 16777216.f), u3 = (float)(rn[3] >> 8) * (1.f / 16777216.f);
-        const float ra = sqrtf(-2.f * logf(u0)), rb = sqrtf(-2.f * logf(u2));
-        float s0, c0, s1, c1;
-        sincospif(2.f * u1, &s0, &c0);
-        sincospif(2.f * u3, &s1, &c1);
-        z[0] = ra * c0; z[1] = ra * s0; z[2] = rb * c1; z[3] = rb * s1;
-      }
 #pragma unroll
-      for (int k = 0; k < 4; k++) {
-        const int j = q * 4 + k;
-        if (j >= A.act_dim) break;
-        float m = 0.f;
+    for (int qq = 0; qq < 4; qq++) {
+      const int q = half * 4 + qq;                              // Philox block of action columns 4q .. 4q+3
+      if (q * 4 < A.act_dim) {
+        float z[4] = {0.f, 0.f, 0.f, 0.f};
+        if (!A.deterministic) {
+          unsigned rn[4];
+          const long long genv = A.env_offset + e;
+          t5_philox((unsigned)A.seed, (unsigned)genv, (unsigned)A.step, (unsigned)((unsigned long long)A.step >> 32), 0x40000000u + (unsigned)q,
+                    (unsigned)(A.seed >> 32) ^ (unsigned)((unsigned long long)genv >> 32), rn);
+          const float u0 = ((float)(rn[0] >> 8) + 1.f) * (1.f / 16777216.f), u1 = (float)(rn[1] >> 8) * (1.f / 16777216.f);
+          const float u2 = ((float)(rn[2] >> 8) + 1.f) * (1.f / 16777216.f), u3 = (float)(rn[3] >> 8) * (1.f / 16777216.f);
+          const float ra = sqrtf(-2.f * logf(u0)), rb = sqrtf(-2.f * logf(u2));
+          float s0, c0, s1, c1;
+          sincospif(2.f * u1, &s0, &c0);
+          sincospif(2.f * u3, &s1, &c1);
+          z[0] = ra * c0; z[1] = ra * s0; z[2] = rb * c1; z[3] = rb * s1;
+        }
 #pragma unroll
-        for (int c = 0; c < 32; c++) if (c == j) m = mout[c];             // register-resident row, compile-time indices
-        const float s = __ldg(stdv + j);
-        A.mean[(size_t)e * A.act_dim + j] = m;
-        A.actions[(size_t)e * A.act_dim + j] = fmaf(s, z[k], m);
-        if (A.sigma_out != nullptr) A.sigma_out[(size_t)e * A.act_dim + j] = s;
-        lp += -0.5f * z[k] * z[k] - logf(s) - 0.91893853320467274f;
+        for (int k = 0; k < 4; k++) {
+          const int j = q * 4 + k;
+          if (j < A.act_dim) {
+            const float m = mout[qq * 4 + k];
+            const float s = __ldg(stdv + j);
+            A.mean[(size_t)e * A.act_dim + j] = m;
+            A.actions[(size_t)e * A.act_dim + j] = fmaf(s, z[k], m);
+            if (A.sigma_out != nullptr) A.sigma_out[(size_t)e * A.act_dim + j] = s;
+            lp += -0.5f * z[k] * z[k] - logf(s) - 0.91893853320467274f;
+          }
+        }
       }
     }
-    A.logp[e] = lp;
+    atomicAdd(lp_s + row, lp);
   }
   __syncthreads();
+  if (tid < T5_ROWS && row0 + tid < A.n) A.logp[row0 + tid] = lp_s[tid];
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((unsigned)T5_TMEM_COLS) : "memory");
 }
 
@@ -309,6 +318,7 @@ static int t5_layout(const nm_mlp_shape* s, T5Net& n, bool is_actor) {
     L.npad = (L.kout + 15) & ~15;                              // UMMA M=128 needs N % 16 == 0, 16 <= N <= 256
     if (L.kpad > 72 || L.npad > T5_TMEM_COLS || L.kin < 1 || L.kout < 1) return -1;
     if (l == n.nl - 1 && L.npad > 32) return -1;
+    if ((L.npad >> 1) % 8 != 0) return -1;                      // the epilogue splits the columns over two warp groups, 8 at a time
     L.w_off = woff; woff += L.npad * L.kpad;
     L.b_off = boff; boff += L.npad;
     L.src_w = src; src += L.kin * L.kout;
@@ -334,7 +344,7 @@ extern "C" int nm_policy_tc5_create(const nm_mlp_shape* actor, const nm_mlp_shap
   const int af = 2 * p->actor.plane_floats + p->actor.bias_floats, cf = 2 * p->critic.plane_floats + p->critic.bias_floats;
   p->packed_floats = af + cf + 64;
   const int wmax = af > cf ? af : cf;
-  p->smem_bytes = sizeof(float) * (size_t)(2 * T5_ROWS * 72 + wmax) + 1024;
+  p->smem_bytes = sizeof(float) * (size_t)(2 * T5_ROWS * 72 + 2 * T5_ROWS * 64 + wmax) + 1024;
   if (p->smem_bytes > 227 * 1024) { delete p; return nm_fail(NM_ERR_UNSUPPORTED, "nm_policy_tc5_create: weights do not fit in shared memory"); }
   if (cudaSetDevice(device) != cudaSuccess || cudaMalloc(&p->d_packed, sizeof(float) * p->packed_floats) != cudaSuccess ||
       cudaMemset(p->d_packed, 0, sizeof(float) * p->packed_floats) != cudaSuccess ||
@@ -374,7 +384,7 @@ extern "C" int nm_policy_tc5_act(nm_policy_tc5* p, const float* obs, int obs_str
   a.obs = obs; a.obs_stride = obs_stride; a.n = n; a.seed = seed; a.step = step; a.env_offset = env_offset;
   a.deterministic = deterministic; a.act_dim = p->act_dim;
   a.actions = actions; a.mean = mean; a.value = value; a.logp = logp; a.obs_copy = obs_copy; a.sigma_out = sigma_out;
-  nm_policy_tc5_kernel<<<(n + T5_ROWS - 1) / T5_ROWS, T5_ROWS, p->smem_bytes, static_cast<cudaStream_t>(stream)>>>(a);
+  nm_policy_tc5_kernel<<<(n + T5_ROWS - 1) / T5_ROWS, T5_THREADS, p->smem_bytes, static_cast<cudaStream_t>(stream)>>>(a);
   if (cudaGetLastError() != cudaSuccess) return nm_fail(NM_ERR_CUDA, "nm_policy_tc5_act: launch failed");
   return NM_OK;
 }
