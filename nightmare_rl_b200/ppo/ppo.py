@@ -52,12 +52,12 @@ class PPO:
         self._flat_grad = None
         self._stats = None
         self._in_place = False
-        # CUDA-graph replay of the mini-batch update (single-process CUDA runs): the update is ~200 tiny kernels per
+        # CUDA-graph replay of the mini-batch update (CUDA runs; NCCL collectives are captured too): ~200 tiny kernels per
         # mini-batch and otherwise bound by PyTorch's per-op launch overhead.  The optimiser then keeps its learning rate
         # in a device tensor and the KL-adaptive schedule runs on the device as well (same rule, no host read-back).
         if graph_update is None:
-            graph_update = self.device.type == "cuda" and self.world == 1
-        self.graph_update = bool(graph_update) and self.device.type == "cuda" and self.world == 1
+            graph_update = self.device.type == "cuda"
+        self.graph_update = bool(graph_update) and self.device.type == "cuda"
         self._graph = None
         if self.graph_update:
             self._lr_t = torch.tensor(float(learning_rate), device=self.device)
@@ -75,6 +75,12 @@ class PPO:
     def weights_changed(self):
         """Call after loading a checkpoint: the packed copy the fused kernel reads is refreshed before the next act()."""
         self._weights_dirty = True
+
+    def release_graph(self):
+        """Drop the captured update graph (it holds NCCL work when ranks > 1; release it before the process group goes)."""
+        self._graph = None
+        if self.device.type == "cuda":
+            torch.cuda.synchronize(self.device)
 
     def optimizer_reloaded(self):
         """After ``optimizer.load_state_dict``: re-attach the device-resident learning rate and drop the captured graph
@@ -317,6 +323,9 @@ class PPO:
         loss, v_loss, s_loss, kl_mean = self._minibatch_loss(
             obs[b], cobs[b], st.actions.flatten(0, 1)[b], st.values.flatten(0, 1)[b], st.advantages.flatten(0, 1)[b],
             st.returns.flatten(0, 1)[b], st.actions_log_prob.flatten(0, 1)[b], st.mu.flatten(0, 1)[b], st.sigma.flatten(0, 1)[b])
+        if self.world > 1:                                   # every rank takes the same learning-rate decision
+            dist.all_reduce(kl_mean)
+            kl_mean = kl_mean / self.world
         if self.desired_kl is not None and self.schedule == "adaptive":
             lr = self._lr_t
             down = torch.clamp(lr / 1.5, min=1e-5)
@@ -326,6 +335,8 @@ class PPO:
             lr.copy_(new_lr)
         self.optimizer.zero_grad(set_to_none=False)
         loss.backward()
+        if self.world > 1:                                   # NCCL all-reduce of the flat gradient, captured with the rest
+            self._allreduce_grads()
         nn.utils.clip_grad_norm_(self.actor_critic.parameters(), self.max_grad_norm, foreach=True)
         self.optimizer.step()
         self._g_vloss += v_loss

@@ -69,6 +69,8 @@ def main():
     iters = args.iterations if args.iterations is not None else train_cfg.runner.max_iterations
     runner.learn(num_learning_iterations=iters, init_at_random_ep_len=True)
     if world > 1:
+        runner.alg.release_graph()
+        dist.barrier()
         dist.destroy_process_group()
 
 
