@@ -52,6 +52,7 @@ class PPO:
         self._flat_grad = None
         self._stats = None
         self._in_place = False
+        self.tf32_backward = True
         # CUDA-graph replay of the mini-batch update (CUDA runs; NCCL collectives are captured too): ~200 tiny kernels per
         # mini-batch and otherwise bound by PyTorch's per-op launch overhead.  The optimiser then keeps its learning rate
         # in a device tensor and the KL-adaptive schedule runs on the device as well (same rule, no host read-back).
@@ -284,6 +285,20 @@ class PPO:
             p.grad.copy_(self._flat_grad[off:off + p.numel()].view_as(p.grad))
             off += p.numel()
 
+    def _backward(self, loss):
+        """Backward pass with TF32 tensor-core GEMMs on CUDA.  The forward pass stays fp32 (the probability ratio against the
+        rollout's log-probs must be exact); the weight-gradient GEMMs contract over the whole mini-batch (K = 81 920 at 4096
+        envs) and are what cuBLAS otherwise runs as CUDA-core SIMT kernels — 26 of the 48 ms of an update."""
+        if self.device.type != "cuda" or not self.tf32_backward:
+            loss.backward()
+            return
+        prev = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = True
+        try:
+            loss.backward()
+        finally:
+            torch.backends.cuda.matmul.allow_tf32 = prev
+
     # ------------------------------------------------------------------ update
     def update(self):
         if self.graph_update:
@@ -334,7 +349,7 @@ class PPO:
                                  torch.where((kl_mean < self.desired_kl / 2.0) & (kl_mean > 0.0), up, lr))
             lr.copy_(new_lr)
         self.optimizer.zero_grad(set_to_none=False)
-        loss.backward()
+        self._backward(loss)
         if self.world > 1:                                   # NCCL all-reduce of the flat gradient, captured with the rest
             self._allreduce_grads()
         nn.utils.clip_grad_norm_(self.actor_critic.parameters(), self.max_grad_norm, foreach=True)
@@ -431,7 +446,7 @@ class PPO:
             loss = surrogate_loss + self.value_loss_coef * value_loss - self.entropy_coef * entropy_b.mean()
 
             self.optimizer.zero_grad()
-            loss.backward()
+            self._backward(loss)
             if self.world > 1:
                 self._allreduce_grads()
             nn.utils.clip_grad_norm_(ac.parameters(), self.max_grad_norm)
