@@ -213,3 +213,20 @@ def test_prebound_rollout_equals_standard_rollout():
         assert torch.equal(getattr(sa, name), getattr(sb, name)), name
     assert torch.equal(qa, qb) and torch.equal(sta[0], stb[0]) and int(sta[4]) == int(stb[4])
     assert sa.dones.sum() > 0
+
+
+def test_split_k_linear_backward_matches_plain_linear():
+    """The split-K weight-gradient GEMM of the update's Linear layers == autograd's plain nn.Linear (fp32)."""
+    from nightmare_rl_b200.ppo.actor_critic import _Linear
+    torch.manual_seed(0)
+    lin = _Linear(66, 54).to(DEV)
+    ref = torch.nn.Linear(66, 54).to(DEV)
+    ref.load_state_dict(lin.state_dict())
+    x = torch.randn(81920, 66, device=DEV, requires_grad=True)
+    x2 = x.detach().clone().requires_grad_(True)
+    w = torch.randn(81920, 54, device=DEV)
+    (lin(x) * w).sum().backward()
+    (ref(x2) * w).sum().backward()
+    assert torch.allclose(lin.weight.grad, ref.weight.grad, rtol=1e-4, atol=1e-2)
+    assert torch.allclose(lin.bias.grad, ref.bias.grad, rtol=1e-4, atol=1e-2)
+    assert torch.allclose(x.grad, x2.grad, rtol=1e-4, atol=1e-4)
