@@ -401,9 +401,20 @@ static void fill_cfg(const nm_envcfg& c, NmDevCfg& d) {
   for (int i = 0; i < 66; i++) d.noise_vec[i] = (float)c.noise_vec[i];
 }
 
+static int batch_create_impl(const nm_model* m, int num_envs, int device, uint64_t seed, const nm_envcfg* cfg, const nm_buffers* bufs, nm_batch* b);
+
 extern "C" int nm_batch_create(const nm_model* m, int num_envs, int device, uint64_t seed, const nm_envcfg* cfg,
                                const nm_buffers* bufs, nm_batch** out) {
   if (!m || !bufs || !out || num_envs <= 0) return fail(NM_ERR_ARG, "nm_batch_create: bad argument");
+  nm_batch* b = new nm_batch();
+  memset(b, 0, sizeof(*b));
+  const int rc = batch_create_impl(m, num_envs, device, seed, cfg, bufs, b);
+  if (rc != NM_OK) { nm_batch_destroy(b); return rc; }        // frees whatever was allocated before the failure
+  *out = b;
+  return NM_OK;
+}
+
+static int batch_create_impl(const nm_model* m, int num_envs, int device, uint64_t seed, const nm_envcfg* cfg, const nm_buffers* bufs, nm_batch* b) {
   if (m->nleg != 6 || m->nq != NM_NQ || m->nv != NM_NV)
     return fail(NM_ERR_UNSUPPORTED, "the env-step kernel is laid out for the 6-leg / 18-dof Nightmare topology");
   if (!bufs->qpos || !bufs->qvel || !bufs->warm || !bufs->sensordata) return fail(NM_ERR_ARG, "physics buffers must be non-null");
@@ -415,8 +426,6 @@ extern "C" int nm_batch_create(const nm_model* m, int num_envs, int device, uint
   CUDA_OK(cudaGetDeviceCount(&ndev));
   if (device < 0 || device >= ndev) return fail(NM_ERR_CUDA, "no such CUDA device");
   CUDA_OK(cudaSetDevice(device));
-  nm_batch* b = new nm_batch();
-  memset(b, 0, sizeof(*b));
   b->model = m; b->n = num_envs; b->device = device;
   CUDA_OK(cudaMalloc(&b->d_model, sizeof(NmDevModel)));
   CUDA_OK(cudaMemcpy(b->d_model, &m->dev, sizeof(NmDevModel), cudaMemcpyHostToDevice));
@@ -468,7 +477,6 @@ extern "C" int nm_batch_create(const nm_model* m, int num_envs, int device, uint
   a.in_actions = nullptr; a.act_stride = 0; a.in_ctrl = nullptr;
   a.host_obs = nullptr; a.host_rew = nullptr; a.host_done = nullptr;
   a.dr = nullptr; a.dr_on_reset = 0;
-  *out = b;
   return NM_OK;
 }
 
