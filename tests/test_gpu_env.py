@@ -318,3 +318,41 @@ def test_domain_randomization_opt_in():
     changed = (dr1 != dr0).any(dim=1)
     assert changed[n // 2:].all() and not changed[: n // 2].any()               # only the timed-out half was redrawn
     assert torch.isfinite(e.obs_buf).all()
+
+
+def test_largest_batch_properties():
+    """BASELINE's largest per-GPU size (131 072 envs, the <256 threads, 128 registers> build): invariants after a few steps."""
+    from nightmare_rl_b200.envs.nightmare_v3_config import NightmareV3Config
+    from nightmare_rl_b200.envs.nightmare_v3_env import NightmareV3Env
+    n = 131072
+    cfg = NightmareV3Config()
+    cfg.env.num_envs = n
+    cfg.env.model_path = NMB
+    cfg.viewer.render = cfg.viewer.record_states = False
+    env = NightmareV3Env(cfg, seed=1)
+    env.reset()
+    env.episode_length_buf = torch.randint_like(env.episode_length_buf, high=1250)
+    gen = torch.Generator(device=env.device).manual_seed(0)
+    for t in range(12):
+        prev = env.episode_length_buf.clone()
+        obs, _, rew, done, _ = env.step(torch.randn(n, 18, device=env.device, generator=gen))
+        d = done.bool()
+        assert torch.equal(env.episode_length_buf[~d], prev[~d] + 1) and (env.episode_length_buf[d] == 0).all()
+    assert torch.isfinite(obs).all() and torch.isfinite(rew).all() and obs.abs().max() <= 100.0
+    q = env.get_state()[0]
+    assert ((q[:, 3:7].norm(dim=1) - 1).abs() < 1e-4).all()
+    # env i is independent of the batch it sits in: the first 256 envs match a 256-env run with the same seed and actions
+    cfg2 = NightmareV3Config()
+    cfg2.env.num_envs = 256
+    cfg2.env.model_path = NMB
+    cfg2.viewer.render = cfg2.viewer.record_states = False
+    small = NightmareV3Env(cfg2, seed=1)
+    small.reset()
+    big = NightmareV3Env(cfg, seed=1)
+    big.reset()
+    gen = torch.Generator(device=env.device).manual_seed(3)
+    for t in range(8):
+        a = torch.randn(n, 18, device=env.device, generator=gen)
+        ob, _, rb, db, _ = big.step(a)
+        os_, _, rs, ds, _ = small.step(a[:256].contiguous())
+        assert torch.equal(ob[:256], os_) and torch.equal(rb[:256], rs) and torch.equal(db[:256], ds)
