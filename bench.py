@@ -209,7 +209,7 @@ def run_ours(args):
     # ---- end to end through the public API with host buffers
     h_act = torch.randn(16, E, 18).pin_memory()
     h_obs, h_rew, h_done = torch.empty(E, 66).pin_memory(), torch.empty(E).pin_memory(), torch.empty(E, dtype=torch.int64).pin_memory()
-    Ke = min(K, 200)
+    Ke = min(K, 500)
     for i in range(3):
         env.step_host(h_act[i % 16], h_obs, h_rew, h_done)
     barrier()
@@ -296,7 +296,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=1000)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--envs-per-gpu", type=int, default=4096)
