@@ -122,7 +122,7 @@ def run_reference(args):
         return
     cores = os.cpu_count() or 1
     n = args.envs_per_gpu
-    steps = max(1, min(args.steps, 40))            # bounded: each step is one pass over the whole 4096-env batch
+    steps = max(1, min(args.steps, 800))           # bounded (~10 s): each step is one pass over the whole 4096-env batch
     val, per = cpu_env_steps_per_s(n, steps, min(args.warmup, 2), cores)
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 2),
@@ -266,7 +266,7 @@ def run_ours(args):
         fp32_peak = _lib.lib.nm_measure_fp32_peak(None)
         tfs = FLOPS_PER_ENV_STEP * E / (kern_ms * 1e-3) / 1e12
         cores = os.cpu_count() or 1
-        cpu_steps = 25
+        cpu_steps = 800                                   # ~10 s of CPU work on 16 cores
         cpu_val, _ = cpu_env_steps_per_s(E, cpu_steps, 2, cores)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
