@@ -144,17 +144,26 @@ class NightmareV3Env:
         if self._host is None:
             pin = lambda *s, **k: torch.empty(*s, **k).pin_memory()
             self._host = (pin(self.num_envs, 66), pin(self.num_envs), pin(self.num_envs, dtype=torch.int64))
-        obs_out = self._host[0] if obs_out is None else obs_out
-        rew_out = self._host[1] if rew_out is None else rew_out
-        done_out = self._host[2] if done_out is None else done_out
+            self._host_call = _lib.lib.nm_step_host
+            self._host_touts = self._batch.time_outs_latched if self.cfg.env.send_timeouts else None
+        if obs_out is None:
+            obs_out, rew_out, done_out = self._host
         a = actions
         if not torch.is_tensor(a) or a.device.type != "cpu" or a.dtype != torch.float32 or not a.is_contiguous():
             a = torch.as_tensor(a).detach().to("cpu", torch.float32).contiguous()
-        if a.dim() != 2 or a.shape[0] != self.num_envs or a.shape[1] < 18:
-            raise ValueError(f"actions must be [num_envs, >=18], got {tuple(a.shape)}")
+        shp = a.shape
+        if len(shp) != 2 or shp[0] != self.num_envs or shp[1] < 18:
+            raise ValueError(f"actions must be [num_envs, >=18], got {tuple(shp)}")
         self.common_step_counter += 1
-        self._batch.step_host(a, self.common_step_counter, obs_out, rew_out, done_out)
-        self._refresh_extras(fresh=False)                  # views of the device-side latches (valid until the next step)
+        b = self._batch
+        rc = self._host_call(b._h, a.data_ptr(), shp[1], self.common_step_counter, obs_out.data_ptr(), rew_out.data_ptr(), done_out.data_ptr(),
+                             torch.cuda.current_stream(self.device).cuda_stream)
+        if rc != 0:
+            _lib.check(rc)
+        ex = self.extras                                      # views of the device-side latches (valid until the next step)
+        ex["episode"] = self._extras_views
+        if self._host_touts is not None:
+            ex["time_outs"] = self._host_touts
         if self._rec is not None:
             self._rec.after_step()
         return obs_out, None, rew_out, done_out, self.extras
