@@ -356,3 +356,30 @@ def test_largest_batch_properties():
         ob, _, rb, db, _ = big.step(a)
         os_, _, rs, ds, _ = small.step(a[:256].contiguous())
         assert torch.equal(ob[:256], os_) and torch.equal(rb[:256], rs) and torch.equal(db[:256], ds)
+
+
+def test_observation_noise_matches_oracle():
+    """cfg.noise.add_noise (reference envs/nightmare_v3_env.py:304-305, off by default; the literal 12-DoF noise vector,
+    quirk Q8): same counter-based uniform stream in the kernel and in the oracle."""
+    from nightmare_rl_b200.envs.nightmare_v3_config import NightmareV3Config
+    cfg = NightmareV3Config()
+    cfg.noise.add_noise = True
+    st = _lockstep(cfg, 128, 12, seed=5)
+    eo = np.concatenate(st["obs_all"])
+    assert np.percentile(eo, 99) < 5e-5 and st["obs"] < 2e-2
+    # and the noise is really there: same seed without noise gives different observations in the noisy columns only
+    G = _G()
+    cfgs = []
+    outs = []
+    for noisy in (False, True):
+        c = NightmareV3Config()
+        c.noise.add_noise = noisy
+        c, ob, gb = G.make_env_pair(64, 9, c)
+        ob.env_reset_idx(np.arange(64))
+        G.sync_env_from_oracle(ob, gb)
+        gb.step(torch.zeros(64, 18), 1)
+        torch.cuda.synchronize()
+        outs.append(gb.obs.cpu().numpy())
+    d = np.abs(outs[0] - outs[1]).max(axis=0)
+    nz = np.r_[np.arange(0, 9), np.arange(12, 36)]                      # entries with a non-zero noise scale (Q8 layout)
+    assert (d[nz] > 0).all() and (np.delete(d, nz) == 0).all()
