@@ -383,3 +383,30 @@ def test_observation_noise_matches_oracle():
     d = np.abs(outs[0] - outs[1]).max(axis=0)
     nz = np.r_[np.arange(0, 9), np.arange(12, 36)]                      # entries with a non-zero noise scale (Q8 layout)
     assert (d[nz] > 0).all() and (np.delete(d, nz) == 0).all()
+
+
+def test_state_recorder_pickle_format(tmp_path):
+    """cfg.viewer.record_states (default on in the reference, envs/nightmare_v3_config.py:33): env-0 trajectories are pickled as
+    a list of (time, qpos[25], qvel[24], act) per episode — the format open_custom_play.py:50-66 replays."""
+    import pickle
+    from nightmare_rl_b200.envs.nightmare_v3_config import NightmareV3Config
+    from nightmare_rl_b200.envs.nightmare_v3_env import NightmareV3Env
+    cfg = NightmareV3Config()
+    cfg.env.num_envs = 8
+    cfg.env.model_path = NMB
+    cfg.viewer.render = False
+    cfg.viewer.record_states = True
+    env = NightmareV3Env(cfg, log_dir=str(tmp_path), seed=0)
+    env.reset()
+    env.episode_length_buf = torch.full((8,), 1240, dtype=torch.int64)         # env 0 times out after ~11 steps
+    for t in range(40):
+        env.step(torch.zeros(8, 18))
+    env._rec.flush()
+    files = sorted(f for f in os.listdir(tmp_path) if f.endswith(".pkl"))
+    assert files, "no trajectory file was written when env 0 reset"
+    rows = pickle.load(open(os.path.join(tmp_path, files[0]), "rb"))
+    assert isinstance(rows, list) and len(rows) >= 5
+    t0, q0, v0, a0 = rows[0]
+    assert np.asarray(q0).shape == (25,) and np.asarray(v0).shape == (24,) and isinstance(t0, float)
+    times = [r[0] for r in rows]
+    assert all(b > a for a, b in zip(times, times[1:])) and abs((times[1] - times[0]) - 0.016) < 1e-9
