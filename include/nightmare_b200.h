@@ -187,6 +187,20 @@ typedef struct {
 } nm_rollout_slot;
 int  nm_rollout_store(const nm_rollout_slot* slot, nm_stream stream);
 
+/* ---- PPO loss head (≙ the distribution / loss part of rsl_rl v1.0.2 PPO.update, train.py:54): forward sums and the
+ * gradients w.r.t. mu, value and std in one launch.  All pointers DEVICE float32; n samples, act_dim actions.
+ * out[0..2] = sum surrogate, sum value loss, sum KL; g_mu [n,A], g_value [n] and g_std [A] are d(loss)/d(.) for
+ * loss = mean(surrogate) + value_coef*mean(value loss) - entropy_coef*mean(entropy), EXCEPT the entropy term of g_std
+ * (-entropy_coef/std, sample independent), which the caller adds. */
+typedef struct {
+  int32_t n, act_dim, use_clipped_value_loss, pad0;
+  float clip, value_coef, pad1, pad2;
+  const float* mu; const float* value; const float* std; const float* actions; const float* old_logp; const float* old_mu;
+  const float* old_sigma; const float* adv; const float* ret; const float* tgt_val;
+  float* out; float* g_mu; float* g_value; float* g_std;
+} nm_ppo_head_args;
+int  nm_ppo_head(const nm_ppo_head_args* head, nm_stream stream);
+
 /* number of kernel launches issued by this batch so far (bench.py "gpu_launches") */
 int64_t nm_batch_launches(const nm_batch*);
 

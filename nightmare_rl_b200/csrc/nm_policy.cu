@@ -365,3 +365,86 @@ extern "C" int nm_rollout_store(const nm_rollout_slot* slot, nm_stream stream) {
   if (cudaGetLastError() != cudaSuccess) return nm_fail(NM_ERR_CUDA, "nm_rollout_store: launch failed");
   return NM_OK;
 }
+
+// ================================================================================================ PPO loss head
+// ≙ the distribution / loss part of rsl_rl v1.0.2 PPO.update (reached from train.py:54): Normal log-prob of the stored
+// actions, probability ratio, clipped surrogate, clipped value loss, entropy bonus and the KL estimate of the adaptive
+// learning-rate rule — forward value AND its gradients w.r.t. the network outputs (mu, value) and the std parameter, in
+// one launch, one thread per sample.  It replaces ~120 element-wise / reduction kernels of the autograd graph per
+// mini-batch; the MLPs themselves stay with autograd + cuBLAS.
+//   out[0] = sum surrogate, out[1] = sum value loss, out[2] = sum KL   (caller divides by n)
+__global__ void nm_ppo_head_kernel(const nm_ppo_head_args H) {
+  __shared__ float s_red[3];
+  __shared__ float s_gstd[64];
+  if (threadIdx.x < 3) s_red[threadIdx.x] = 0.f;
+  if (threadIdx.x < 64) s_gstd[threadIdx.x] = 0.f;
+  __syncthreads();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int A = H.act_dim;
+  float surr = 0.f, vloss = 0.f, kl = 0.f;
+  if (i < H.n) {
+    const float inv_n = 1.f / (float)H.n;
+    float logp = 0.f;
+    for (int j = 0; j < A; j++) {
+      const float s = H.std[j], m = H.mu[(size_t)i * A + j];
+      const float z = (H.actions[(size_t)i * A + j] - m) / s;
+      logp += -0.5f * z * z - logf(s) - 0.91893853320467274f;
+      const float os = H.old_sigma[(size_t)i * A + j], dm = H.old_mu[(size_t)i * A + j] - m;
+      kl += logf(s / os + 1.0e-5f) + (os * os + dm * dm) / (2.f * s * s) - 0.5f;
+    }
+    const float adv = H.adv[i];
+    const float ratio = expf(logp - H.old_logp[i]);
+    const float lo = 1.f - H.clip, hi = 1.f + H.clip;
+    const float rc = fminf(fmaxf(ratio, lo), hi);
+    const float s1 = -adv * ratio, s2 = -adv * rc;
+    surr = fmaxf(s1, s2);
+    // d surr / d logp: torch.max routes ties to its first argument (the unclipped term); clamp passes the gradient inside [lo, hi]
+    float g = 0.f;
+    if (s1 >= s2) g = s1;                                   // d(-adv*ratio)/dlogp = -adv*ratio
+    else if (ratio >= lo && ratio <= hi) g = s2;
+    g *= inv_n;
+    for (int j = 0; j < A; j++) {
+      const float s = H.std[j];
+      const float z = (H.actions[(size_t)i * A + j] - H.mu[(size_t)i * A + j]) / s;
+      H.g_mu[(size_t)i * A + j] = g * z / s;
+      atomicAdd(s_gstd + j, g * (z * z - 1.f) / s);
+    }
+    const float v = H.value[i], R = H.ret[i];
+    float dv;
+    if (H.use_clipped_value_loss) {
+      const float tv = H.tgt_val[i];
+      const float dcl = fminf(fmaxf(v - tv, -H.clip), H.clip);
+      const float vc = tv + dcl;
+      const float l1 = (v - R) * (v - R), l2 = (vc - R) * (vc - R);
+      vloss = fmaxf(l1, l2);
+      if (l1 >= l2) dv = 2.f * (v - R);
+      else dv = (v - tv >= -H.clip && v - tv <= H.clip) ? 2.f * (vc - R) : 0.f;
+    } else {
+      vloss = (R - v) * (R - v);
+      dv = 2.f * (v - R);
+    }
+    H.g_value[i] = H.value_coef * dv * inv_n;
+  }
+  // block reduction of the three sums, then one atomic per block
+  for (int o = 16; o > 0; o >>= 1) {
+    surr += __shfl_xor_sync(0xffffffffu, surr, o);
+    vloss += __shfl_xor_sync(0xffffffffu, vloss, o);
+    kl += __shfl_xor_sync(0xffffffffu, kl, o);
+  }
+  if ((threadIdx.x & 31) == 0) { atomicAdd(s_red, surr); atomicAdd(s_red + 1, vloss); atomicAdd(s_red + 2, kl); }
+  __syncthreads();
+  if (threadIdx.x < 3) atomicAdd(H.out + threadIdx.x, s_red[threadIdx.x]);
+  if (threadIdx.x < A) atomicAdd(H.g_std + threadIdx.x, s_gstd[threadIdx.x]);
+}
+
+extern "C" int nm_ppo_head(const nm_ppo_head_args* h, nm_stream stream) {
+  if (!h || h->n <= 0 || h->act_dim < 1 || h->act_dim > 64 || !h->mu || !h->value || !h->std || !h->actions || !h->old_logp || !h->old_mu ||
+      !h->old_sigma || !h->adv || !h->ret || !h->tgt_val || !h->out || !h->g_mu || !h->g_value || !h->g_std)
+    return nm_fail(NM_ERR_ARG, "nm_ppo_head: bad argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (cudaMemsetAsync(h->out, 0, 3 * sizeof(float), st) != cudaSuccess || cudaMemsetAsync(h->g_std, 0, h->act_dim * sizeof(float), st) != cudaSuccess)
+    return nm_fail(NM_ERR_CUDA, "nm_ppo_head: memset failed");
+  nm_ppo_head_kernel<<<(h->n + 127) / 128, 128, 0, st>>>(*h);
+  if (cudaGetLastError() != cudaSuccess) return nm_fail(NM_ERR_CUDA, "nm_ppo_head: launch failed");
+  return NM_OK;
+}

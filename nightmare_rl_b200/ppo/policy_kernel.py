@@ -109,3 +109,48 @@ class RolloutSlot(ctypes.Structure):
 
 def rollout_store(slot: RolloutSlot, device: torch.device):
     _lib.check(_lib.lib.nm_rollout_store(ctypes.byref(slot), ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)))
+
+
+class PPOHeadArgs(ctypes.Structure):
+    """``nm_ppo_head_args`` of include/nightmare_b200.h."""
+    _fields_ = ([("n", ctypes.c_int32), ("act_dim", ctypes.c_int32), ("use_clipped_value_loss", ctypes.c_int32), ("pad0", ctypes.c_int32),
+                 ("clip", ctypes.c_float), ("value_coef", ctypes.c_float), ("pad1", ctypes.c_float), ("pad2", ctypes.c_float)]
+                + [(k, ctypes.c_void_p) for k in ("mu", "value", "std", "actions", "old_logp", "old_mu", "old_sigma", "adv", "ret", "tgt_val",
+                                                  "out", "g_mu", "g_value", "g_std")])
+
+
+class FusedPPOHead(torch.autograd.Function):
+    """loss = mean(clipped surrogate) + value_coef * mean(clipped value loss) - entropy_coef * mean(entropy), its value-loss /
+    surrogate / KL means, and its gradients w.r.t. (mu, value, std) from ONE kernel launch (csrc/nm_policy.cu,
+    nm_ppo_head) instead of ~120 element-wise autograd kernels.  Returns (loss, value_loss, surrogate_loss, kl_mean)."""
+
+    @staticmethod
+    def forward(ctx, mu, value, std, actions, old_logp, old_mu, old_sigma, adv, ret, tgt_val, clip, value_coef, entropy_coef, use_clipped):
+        n, A = mu.shape
+        c = lambda t: t.contiguous()
+        mu_, value_, std_ = c(mu), c(value.reshape(-1)), c(std)
+        bufs = [c(actions), c(old_logp.reshape(-1)), c(old_mu), c(old_sigma), c(adv.reshape(-1)), c(ret.reshape(-1)), c(tgt_val.reshape(-1))]
+        out = torch.empty(3, device=mu.device)
+        g_mu = torch.empty_like(mu_)
+        g_value = torch.empty_like(value_)
+        g_std = torch.empty_like(std_)
+        h = PPOHeadArgs()
+        h.n, h.act_dim, h.use_clipped_value_loss = n, A, 1 if use_clipped else 0
+        h.clip, h.value_coef = float(clip), float(value_coef)
+        h.mu, h.value, h.std = mu_.data_ptr(), value_.data_ptr(), std_.data_ptr()
+        (h.actions, h.old_logp, h.old_mu, h.old_sigma, h.adv, h.ret, h.tgt_val) = [t.data_ptr() for t in bufs]
+        h.out, h.g_mu, h.g_value, h.g_std = out.data_ptr(), g_mu.data_ptr(), g_value.data_ptr(), g_std.data_ptr()
+        _lib.check(_lib.lib.nm_ppo_head(ctypes.byref(h), ctypes.c_void_p(torch.cuda.current_stream(mu.device).cuda_stream)))
+        sums = out / n
+        entropy = (0.5 + 0.5 * 1.8378770664093453 + torch.log(std_)).sum()           # identical for every sample
+        loss = sums[0] + value_coef * sums[1] - entropy_coef * entropy
+        g_std = g_std - entropy_coef / std_
+        ctx.save_for_backward(g_mu, g_value, g_std)
+        ctx.vshape = value.shape
+        ctx._keep = (mu_, value_, std_, bufs)
+        return loss, sums[1], sums[0], sums[2]
+
+    @staticmethod
+    def backward(ctx, g_loss, g_v, g_s, g_k):
+        g_mu, g_value, g_std = ctx.saved_tensors
+        return (g_loss * g_mu, (g_loss * g_value).view(ctx.vshape), g_loss * g_std) + (None,) * 11

@@ -53,6 +53,7 @@ class PPO:
         self._stats = None
         self._in_place = False
         self.tf32_backward = True
+        self.fused_head = self.device.type == "cuda"
         # CUDA-graph replay of the mini-batch update (CUDA runs; NCCL collectives are captured too): ~200 tiny kernels per
         # mini-batch and otherwise bound by PyTorch's per-op launch overhead.  The optimiser then keeps its learning rate
         # in a device tensor and the KL-adaptive schedule runs on the device as well (same rule, no host read-back).
@@ -307,6 +308,17 @@ class PPO:
 
     # one mini-batch of the update rule on explicit tensors (shared by the eager and the graph-captured path)
     def _minibatch_loss(self, obs_b, cobs_b, act_b, tgt_val_b, adv_b, ret_b, old_logp_b, old_mu_b, old_sigma_b):
+        ac = self.actor_critic
+        if self.fused_head and obs_b.is_cuda:
+            # networks through autograd + cuBLAS, everything after them (Normal log-prob, ratio, clipped surrogate, clipped value
+            # loss, entropy, KL) and its gradients in one kernel
+            from .policy_kernel import FusedPPOHead
+            mu_b = ac.actor(obs_b)
+            value_b = ac.evaluate(cobs_b)
+            loss, value_loss, surrogate_loss, kl_mean = FusedPPOHead.apply(
+                mu_b, value_b, ac.std, act_b, old_logp_b, old_mu_b, old_sigma_b, adv_b, ret_b, tgt_val_b,
+                self.clip_param, self.value_loss_coef, self.entropy_coef, self.use_clipped_value_loss)
+            return loss, value_loss.detach(), surrogate_loss.detach(), kl_mean.detach()
         ac = self.actor_critic
         ac.update_distribution(obs_b)                      # rsl_rl calls act() here and discards the sample
         logp_b = ac.get_actions_log_prob(act_b)

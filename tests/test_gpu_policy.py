@@ -230,3 +230,39 @@ def test_split_k_linear_backward_matches_plain_linear():
     assert torch.allclose(lin.weight.grad, ref.weight.grad, rtol=1e-4, atol=1e-2)
     assert torch.allclose(lin.bias.grad, ref.bias.grad, rtol=1e-4, atol=1e-2)
     assert torch.allclose(x.grad, x2.grad, rtol=1e-4, atol=1e-4)
+
+
+def test_fused_ppo_head_matches_autograd():
+    """nm_ppo_head (loss sums + gradients in one launch) == the eager rsl_rl loss through autograd, incl. clip edges."""
+    from nightmare_rl_b200.ppo import PPO, ActorCritic
+    torch.manual_seed(0)
+    n = 5000
+    ac = ActorCritic(66, 66, 18, actor_hidden_dims=[54, 42, 30], critic_hidden_dims=[54, 42, 30])
+    alg = PPO(ac, clip_param=0.2, value_loss_coef=1.0, entropy_coef=0.0015, device="cuda:0", fused_rollout=False, graph_update=False)
+    with torch.no_grad():
+        ac.std.copy_(torch.linspace(0.5, 1.5, 18))
+    g = torch.Generator(device=DEV).manual_seed(1)
+    obs = torch.randn(n, 66, device=DEV, generator=g)
+    with torch.no_grad():
+        ac.update_distribution(obs)
+        mu0 = ac.action_mean.clone()
+        act = mu0 + ac.std * torch.randn(n, 18, device=DEV, generator=g)
+        old_mu = mu0 + 0.05 * torch.randn(n, 18, device=DEV, generator=g)
+        old_sigma = (ac.std * (1 + 0.05 * torch.randn(18, device=DEV, generator=g))).expand(n, 18).contiguous()
+        old_logp = (ac.get_actions_log_prob(act) + 0.3 * torch.randn(n, device=DEV, generator=g)).unsqueeze(1)      # ratios on both sides of the clip
+        v0 = ac.evaluate(obs)
+        tgt = v0 + 0.3 * torch.randn(n, 1, device=DEV, generator=g)
+        ret = v0 + torch.randn(n, 1, device=DEV, generator=g)
+        adv = torch.randn(n, 1, device=DEV, generator=g)
+    res = []
+    for fused in (False, True):
+        alg.fused_head = fused
+        for p in ac.parameters():
+            p.grad = None
+        loss, vl, sl, kl = alg._minibatch_loss(obs, obs, act, tgt, adv, ret, old_logp, old_mu, old_sigma)
+        loss.backward()
+        res.append((float(loss), float(vl), float(sl), float(kl), [p.grad.clone() for p in ac.parameters()]))
+    (l0, v0_, s0, k0, g0), (l1, v1, s1, k1, g1) = res
+    assert abs(l0 - l1) < 1e-4 * max(1, abs(l0)) and abs(v0_ - v1) < 1e-4 * max(1, abs(v0_)) and abs(s0 - s1) < 1e-5 and abs(k0 - k1) < 1e-5
+    for a, b in zip(g0, g1):
+        assert torch.allclose(a, b, rtol=2e-3, atol=2e-6), (a - b).abs().max()
