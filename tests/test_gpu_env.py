@@ -410,3 +410,46 @@ def test_state_recorder_pickle_format(tmp_path):
     assert np.asarray(q0).shape == (25,) and np.asarray(v0).shape == (24,) and isinstance(t0, float)
     times = [r[0] for r in rows]
     assert all(b > a for a, b in zip(times, times[1:])) and abs((times[1] - times[0]) - 0.016) < 1e-9
+
+
+
+def test_scripted_gait_through_env():
+    """The reference's scripted gait (nikengine fixture) fed through NightmareV3Env.step as actions: the CUDA env walks the
+    way the oracle env does -- no terminations, same path -- and batch phase shifts de-synchronise the envs."""
+    import os
+    from conftest import ROOT
+    from nightmare_rl_b200.envs.scripted_gait import ScriptedGait
+    from nightmare_rl_b200.envs.nightmare_v3_env import NightmareV3Env
+    fix = os.path.join(ROOT, "tests", "golden", "nikengine_gait_targets.npz")
+    G = _G()
+    n = 8
+    cfg, ob, _ = G.make_env_pair(n, seed=5)
+    cfg.env.model_path = NMB
+    cfg.viewer.render = cfg.viewer.record_states = False
+    env = NightmareV3Env(cfg, seed=5)
+    env.reset_idx(np.arange(n))
+    ob.env_reset_idx(np.arange(n))
+    gait = ScriptedGait(fix, n, G.DEV, action_scale=cfg.control.action_scale)
+    opos, gpos, dones = [], [], 0
+    worst_obs = 0.0
+    for t in range(560):
+        a = gait.actions()
+        obs, _, rew, done, _ = env.step(a)
+        oobs, orew, odone, _, _, _ = ob.env_step(a.cpu().numpy())
+        dones += int(done.sum()) + int(odone.sum())
+        if t < 100:
+            worst_obs = max(worst_obs, float(np.abs(obs.cpu().numpy() - oobs).max()))
+        opos.append(ob.get_state()[0][:, :3].copy())
+        gpos.append(env.get_state()[0][:, :3].cpu().numpy())
+    opos, gpos = np.array(opos), np.array(gpos)
+    print(f"\n[gait-env] 560 env steps: worst |obs diff| over the first 100 steps {worst_obs:.2e}; base path difference at the end "
+          f"{np.abs(opos[-1] - gpos[-1]).max():.2e} m after walking {np.linalg.norm(gpos[-1, 0, :2] - gpos[299, 0, :2]):.3f} m")
+    assert dones == 0
+    assert worst_obs < 2e-3
+    assert np.linalg.norm(gpos[-1, :, :2] - gpos[299, :, :2], axis=1).min() > 0.3          # it walks
+    assert np.abs(opos - gpos).max() < 0.01                                                 # and along the oracle's path (1 cm over 9 s)
+    shifted = ScriptedGait(fix, 4, G.DEV, phase_shift=7)
+    idx = shifted.index(0).cpu().numpy()
+    assert list(idx) == [0, 7, 14, 21]
+    far = shifted.index(5000).cpu().numpy()
+    assert ((far >= shifted.loop[0]) & (far < shifted.loop[1])).all()

@@ -152,6 +152,54 @@ def test_hundred_step_settle_trajectory():
     assert (ob.get(0, "ncon")[0] >= 3)
 
 
+def test_walking_gait_trajectory():
+    """100 free-running env steps of WALKING: 64 envs start at different phases of the reference's own scripted tripod gait
+    (tests/golden/nikengine_gait_targets.npz, generated from nikengine by tools/make_gait_golden.py) and follow it with the
+    keyboard player's PD law (reference custom_play.py:73-76, kp 12).  Stance/swing switching of six feet, yet the walk is
+    not chaotic (fp32-storage sensitivity of the oracle stays ~3e-6), so every env must meet the north_star 1e-3."""
+    import os
+    from conftest import ROOT
+    G = _common()
+    cm, dm, om = G.models()
+    T = np.load(os.path.join(ROOT, "tests", "golden", "nikengine_gait_targets.npz"))["targets"]
+    one = G.O.OracleBatch(om, 1)
+    states = []
+    for th in T[:740]:
+        q, v, w = one.get_state()
+        states.append((q[0].copy(), v[0].copy(), w[0].copy()))
+        one.physics_step(((th - q[0, -18:]) * 12.0)[None], 2, 1)
+    n = 64
+    start = 340 + np.arange(n) * 6                                      # forward walk, turning and backward walk
+    q0, v0, w0 = (np.array([states[s][k] for s in start]).astype(np.float32) for k in range(3))
+    ob, ob32, gb = G.O.OracleBatch(om, n), G.O.OracleBatch(om, n), G.Batch(dm, n, G.DEV)
+    ob.set_state(q0, v0, w0)
+    ob32.set_state(q0, v0, w0)
+    G.push_state(gb, q0, v0, w0)
+    dev_gpu, dev_o32 = np.zeros(n), np.zeros(n)
+    touch = 0
+    for t in range(100):
+        q, _, _ = ob.get_state()
+        ctrl = ((T[start + t] - q[:, 7:]) * 12.0).astype(np.float32)
+        ob.physics_step(ctrl, 2, 8)
+        ob32.physics_step(ctrl, 2, 8)
+        q2, v2, w2 = ob32.get_state()
+        ob32.set_state(q2.astype(np.float32), v2.astype(np.float32), w2.astype(np.float32))
+        gb.physics_step(torch.from_numpy(ctrl), 2)
+        torch.cuda.synchronize()
+        oq, ov, _ = ob.get_state()
+        gq, gv, _ = G.gpu_state(gb)
+        dev_gpu = np.maximum(dev_gpu, np.maximum(G.per_env_rel(gq, oq), G.per_env_rel(gv, ov, floor=0.1)))
+        dev_o32 = np.maximum(dev_o32, np.maximum(G.per_env_rel(q2, oq), G.per_env_rel(v2, ov, floor=0.1)))
+        feet_o = np.array([ob.get(i, "sensordata")[6:12] > 0 for i in range(n)])
+        feet_g = gb.sensordata[:, 6:12].cpu().numpy() > 0
+        touch += int((feet_o != feet_g).sum())
+    print(f"\n[gait] 100 free-running walking steps, {n} envs: GPU-vs-oracle deviation median {np.median(dev_gpu):.2e} worst {dev_gpu.max():.2e}; "
+          f"oracle fp32-storage sensitivity worst {dev_o32.max():.2e}; foot-contact flag mismatches {touch} of {100 * n * 6}")
+    assert dev_o32.max() <= 5e-5                                        # the workload is non-chaotic by the oracle's own measure
+    assert dev_gpu.max() < 1e-3
+    assert touch <= 100 * n * 6 * 2e-3                                  # flags flip only at touch-down / lift-off instants
+
+
 def test_determinism_and_batch_independence():
     """Bitwise reproducible, and env i does not depend on its neighbours or on the batch size (the
     property multi-GPU sharding relies on)."""
