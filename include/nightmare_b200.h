@@ -201,6 +201,30 @@ typedef struct {
 } nm_ppo_head_args;
 int  nm_ppo_head(const nm_ppo_head_args* head, nm_stream stream);
 
+/* ---- one PPO mini-batch in one launch (csrc/nm_ppo_grad.cu; ≙ rsl_rl v1.0.2 PPO.update's loop body up to loss.backward(),
+ * train.py:54): rows idx[0..n) of the flat rollout buffers are gathered, actor and critic evaluated (3xTF32 tensor-core
+ * forward), the loss head of nm_ppo_head applied, and d(loss)/d(parameter) accumulated for every parameter (TF32 backward).
+ * All pointers DEVICE.  idx may be NULL (rows 0..n-1).  *_params / g_*: the network's parameters / gradients flattened in
+ * PyTorch order (layer0.weight [out][in], layer0.bias, ...); the g_* buffers and out are ZEROED by the call.
+ * out[0..2] = sum surrogate, sum value loss, sum KL over the n samples; g_std includes the entropy term. */
+typedef struct {
+  int32_t n, obs_dim, act_dim, use_clipped_value_loss;
+  float clip, value_coef, entropy_coef, pad0;
+  const int64_t* idx;
+  const float* obs; const float* critic_obs; const float* actions; const float* old_logp; const float* old_mu; const float* old_sigma;
+  const float* adv; const float* ret; const float* tgt_val;
+  const float* actor_params; const float* critic_params; const float* std;
+  float* g_actor; float* g_critic; float* g_std; float* out;
+} nm_ppo_grad_args;
+int  nm_ppo_grad(const nm_mlp_shape* actor, const nm_mlp_shape* critic, const nm_ppo_grad_args* args, nm_stream stream);
+
+/* ---- GAE(lambda) over a stored rollout (≙ rsl_rl v1.0.2 RolloutStorage.compute_returns, train.py:54).  All pointers
+ * DEVICE; rewards / values / returns / advantages float32 [T, n], dones uint8 [T, n], last_values float32 [n].
+ * Writes returns and the RAW advantages (returns - values) and moments[0..1] = their sum and sum of squares (fp64),
+ * from which the caller normalises them. */
+int  nm_gae(int T, int n, const float* rewards, const uint8_t* dones, const float* values, const float* last_values, float gamma,
+            float lam, float* returns, float* advantages, double* moments, nm_stream stream);
+
 /* number of kernel launches issued by this batch so far (bench.py "gpu_launches") */
 int64_t nm_batch_launches(const nm_batch*);
 

@@ -154,3 +154,78 @@ class FusedPPOHead(torch.autograd.Function):
     def backward(ctx, g_loss, g_v, g_s, g_k):
         g_mu, g_value, g_std = ctx.saved_tensors
         return (g_loss * g_mu, (g_loss * g_value).view(ctx.vshape), g_loss * g_std) + (None,) * 11
+
+
+class PPOGradArgs(ctypes.Structure):
+    """``nm_ppo_grad_args`` of include/nightmare_b200.h."""
+    _fields_ = ([("n", ctypes.c_int32), ("obs_dim", ctypes.c_int32), ("act_dim", ctypes.c_int32), ("use_clipped_value_loss", ctypes.c_int32),
+                 ("clip", ctypes.c_float), ("value_coef", ctypes.c_float), ("entropy_coef", ctypes.c_float), ("pad0", ctypes.c_float)]
+                + [(k, ctypes.c_void_p) for k in ("idx", "obs", "critic_obs", "actions", "old_logp", "old_mu", "old_sigma", "adv", "ret", "tgt_val",
+                                                  "actor_params", "critic_params", "std", "g_actor", "g_critic", "g_std", "out")])
+
+
+class FusedPPOGrad:
+    """Gradient of the PPO mini-batch loss for every parameter of an ``ActorCritic`` in one kernel launch (nm_ppo_grad).
+
+    The module's parameters are re-seated as views of ONE flat buffer (std | actor | critic, PyTorch order) and their ``.grad``
+    as views of a second one, so the kernel, the gradient all-reduce, the norm clip and the optimiser all work on the same
+    memory without copies."""
+
+    def __init__(self, actor_critic, device):
+        if device.type != "cuda":
+            raise _lib.NightmareLibError("nm_ppo_grad only runs on CUDA devices")
+        if getattr(actor_critic, "activation_name", "elu") != "elu":
+            raise _lib.NightmareLibError("nm_ppo_grad implements ELU hidden activations only")
+        import torch.nn as nn
+        ac = actor_critic
+        adims, cdims = ac.layer_dims()
+        self.shape_a, self.shape_c = _shape(adims), _shape(cdims)
+        self.obs_dim, self.act_dim = adims[0], adims[-1]
+        groups = [[ac.std],
+                  [p for m in ac.actor if isinstance(m, nn.Linear) for p in (m.weight, m.bias)],
+                  [p for m in ac.critic if isinstance(m, nn.Linear) for p in (m.weight, m.bias)]]
+        listed = [p for grp in groups for p in grp]
+        if {id(p) for p in listed} != {id(p) for p in ac.parameters()} or any(p.dtype != torch.float32 for p in listed):
+            raise _lib.NightmareLibError("nm_ppo_grad: unexpected parameter set (std + Linear layers in float32 expected)")
+        total = sum(p.numel() for p in listed)
+        self.flat = torch.empty(total, device=device)
+        self.flat_grad = torch.zeros(total, device=device)
+        self.offsets = []
+        off = 0
+        with torch.no_grad():
+            for grp in groups:
+                self.offsets.append(off)
+                for p in grp:
+                    n = p.numel()
+                    self.flat[off:off + n].copy_(p.detach().reshape(-1))
+                    p.data = self.flat[off:off + n].view_as(p)
+                    p.grad = self.flat_grad[off:off + n].view_as(p)
+                    off += n
+        self.out = torch.zeros(4, device=device)
+        self.device = device
+        self._keep = None
+
+    def __call__(self, n, idx, obs, critic_obs, actions, old_logp, old_mu, old_sigma, adv, ret, tgt_val, clip, value_coef, entropy_coef,
+                 use_clipped_value_loss):
+        """All tensors flat rollout buffers ([rows, ...], float32, contiguous); idx int64 [n] or None.  Leaves the gradient in
+        ``flat_grad`` (and therefore in every ``p.grad``) and returns ``out`` = [sum surrogate, sum value loss, sum KL, 0]."""
+        for t_ in (obs, critic_obs, actions, old_logp, old_mu, old_sigma, adv, ret, tgt_val):
+            if t_.dtype != torch.float32 or not t_.is_contiguous() or t_.device != self.device:
+                raise _lib.NightmareLibError("nm_ppo_grad: rollout buffers must be contiguous float32 tensors on the policy's device")
+        if idx is not None and (idx.dtype != torch.int64 or not idx.is_contiguous()):
+            raise _lib.NightmareLibError("nm_ppo_grad: idx must be a contiguous int64 tensor")
+        a = PPOGradArgs()
+        a.n, a.obs_dim, a.act_dim, a.use_clipped_value_loss = int(n), self.obs_dim, self.act_dim, 1 if use_clipped_value_loss else 0
+        a.clip, a.value_coef, a.entropy_coef = float(clip), float(value_coef), float(entropy_coef)
+        a.idx = idx.data_ptr() if idx is not None else None
+        a.obs, a.critic_obs, a.actions = obs.data_ptr(), critic_obs.data_ptr(), actions.data_ptr()
+        a.old_logp, a.old_mu, a.old_sigma = old_logp.data_ptr(), old_mu.data_ptr(), old_sigma.data_ptr()
+        a.adv, a.ret, a.tgt_val = adv.data_ptr(), ret.data_ptr(), tgt_val.data_ptr()
+        o_std, o_a, o_c = self.offsets
+        base, gbase = self.flat.data_ptr(), self.flat_grad.data_ptr()
+        a.std, a.actor_params, a.critic_params = base + 4 * o_std, base + 4 * o_a, base + 4 * o_c
+        a.g_std, a.g_actor, a.g_critic = gbase + 4 * o_std, gbase + 4 * o_a, gbase + 4 * o_c
+        a.out = self.out.data_ptr()
+        _lib.check(_lib.lib.nm_ppo_grad(ctypes.byref(self.shape_a), ctypes.byref(self.shape_c), ctypes.byref(a),
+                                        ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)))
+        return self.out

@@ -8,6 +8,8 @@ optimiser step are averaged with ONE all-reduce of a flat buffer (15 043 paramet
 every rank takes the same learning-rate decision, and advantages are normalised with global moments."""
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.distributed as dist
 import torch.nn as nn
@@ -54,6 +56,10 @@ class PPO:
         self._in_place = False
         self.tf32_backward = True
         self.fused_head = self.device.type == "cuda"
+        # whole mini-batch gradient (gather + both MLPs forward/backward + loss head) in one kernel; needs ELU networks that
+        # fit one SM's shared memory, otherwise the autograd path (with the fused head) stays
+        self.fused_grad = None
+        self._want_fused_grad = self.device.type == "cuda" and os.environ.get("NM_PPO_FUSED_GRAD", "1") != "0"
         # CUDA-graph replay of the mini-batch update (CUDA runs; NCCL collectives are captured too): ~200 tiny kernels per
         # mini-batch and otherwise bound by PyTorch's per-op launch overhead.  The optimiser then keeps its learning rate
         # in a device tensor and the KL-adaptive schedule runs on the device as well (same rule, no host read-back).
@@ -63,7 +69,14 @@ class PPO:
         self._graph = None
         if self.graph_update:
             self._lr_t = torch.tensor(float(learning_rate), device=self.device)
-            self.optimizer = optim.Adam(self.actor_critic.parameters(), lr=self._lr_t, capturable=True, foreach=True)
+            if self._want_fused_grad:
+                try:
+                    from .policy_kernel import FusedPPOGrad
+                    self.fused_grad = FusedPPOGrad(self.actor_critic, self.device)
+                except Exception:                              # unsupported network: autograd path
+                    self.fused_grad = None
+            self.optimizer = optim.Adam(self.actor_critic.parameters(), lr=self._lr_t, capturable=True,
+                                        **({"fused": True} if self.fused_grad is not None else {"foreach": True}))
 
     def init_storage(self, num_envs, num_transitions_per_env, actor_obs_shape, critic_obs_shape, action_shape):
         self.storage = RolloutStorage(num_envs, num_transitions_per_env, actor_obs_shape, critic_obs_shape, action_shape, self.device)
@@ -347,10 +360,21 @@ class PPO:
         st, b = self.storage, self._g_idx
         obs = st.observations.flatten(0, 1)
         cobs = st.privileged_observations.flatten(0, 1) if st.privileged_observations is not None else obs
-        loss, v_loss, s_loss, kl_mean = self._minibatch_loss(
-            obs[b], cobs[b], st.actions.flatten(0, 1)[b], st.values.flatten(0, 1)[b], st.advantages.flatten(0, 1)[b],
-            st.returns.flatten(0, 1)[b], st.actions_log_prob.flatten(0, 1)[b], st.mu.flatten(0, 1)[b], st.sigma.flatten(0, 1)[b])
+        fg = self.fused_grad
+        if fg is not None:
+            # one kernel: gather + forward + loss head + backward of both networks, gradient left in fg.flat_grad (= every p.grad)
+            n = b.numel()
+            out = fg(n, b, obs, cobs, st.actions.flatten(0, 1), st.actions_log_prob.flatten(0, 1), st.mu.flatten(0, 1), st.sigma.flatten(0, 1),
+                     st.advantages.flatten(0, 1), st.returns.flatten(0, 1), st.values.flatten(0, 1),
+                     self.clip_param, self.value_loss_coef, self.entropy_coef, self.use_clipped_value_loss)
+            sums = out / n
+            s_loss, v_loss, kl_mean = sums[0], sums[1], sums[2]
+        else:
+            loss, v_loss, s_loss, kl_mean = self._minibatch_loss(
+                obs[b], cobs[b], st.actions.flatten(0, 1)[b], st.values.flatten(0, 1)[b], st.advantages.flatten(0, 1)[b],
+                st.returns.flatten(0, 1)[b], st.actions_log_prob.flatten(0, 1)[b], st.mu.flatten(0, 1)[b], st.sigma.flatten(0, 1)[b])
         if self.world > 1:                                   # every rank takes the same learning-rate decision
+            kl_mean = kl_mean.clone()
             dist.all_reduce(kl_mean)
             kl_mean = kl_mean / self.world
         if self.desired_kl is not None and self.schedule == "adaptive":
@@ -360,11 +384,19 @@ class PPO:
             new_lr = torch.where(kl_mean > self.desired_kl * 2.0, down,
                                  torch.where((kl_mean < self.desired_kl / 2.0) & (kl_mean > 0.0), up, lr))
             lr.copy_(new_lr)
-        self.optimizer.zero_grad(set_to_none=False)
-        self._backward(loss)
-        if self.world > 1:                                   # NCCL all-reduce of the flat gradient, captured with the rest
-            self._allreduce_grads()
-        nn.utils.clip_grad_norm_(self.actor_critic.parameters(), self.max_grad_norm, foreach=True)
+        if fg is not None:
+            g = fg.flat_grad
+            if self.world > 1:                               # NCCL all-reduce of the flat gradient, captured with the rest
+                dist.all_reduce(g)
+                g.div_(self.world)
+            # clip_grad_norm_ on the flat vector: same 2-norm, same 1e-6 guard, same clamp of the coefficient to 1
+            g.mul_(torch.clamp(self.max_grad_norm / (torch.linalg.vector_norm(g) + 1e-6), max=1.0))
+        else:
+            self.optimizer.zero_grad(set_to_none=False)
+            self._backward(loss)
+            if self.world > 1:
+                self._allreduce_grads()
+            nn.utils.clip_grad_norm_(self.actor_critic.parameters(), self.max_grad_norm, foreach=True)
         self.optimizer.step()
         self._g_vloss += v_loss
         self._g_sloss += s_loss

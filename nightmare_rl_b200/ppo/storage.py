@@ -57,6 +57,9 @@ class RolloutStorage:
     def compute_returns(self, last_values, gamma, lam, reduce_moments=None):
         """GAE(lambda); ``reduce_moments(sum, sumsq, count)`` lets a multi-process job normalise advantages with the
         moments of the GLOBAL batch (None: local batch, exactly rsl_rl's behaviour)."""
+        if self.values.is_cuda and self.fused_gae:
+            self._compute_returns_fused(last_values, gamma, lam, reduce_moments)
+            return
         advantage = 0
         for step in reversed(range(self.num_transitions_per_env)):
             next_values = last_values if step == self.num_transitions_per_env - 1 else self.values[step + 1]
@@ -73,6 +76,30 @@ class RolloutStorage:
             mean = s / n
             var = (ss - n * mean * mean) / (n - 1.0)          # unbiased, like torch.std
             self.advantages.copy_(((a - mean) / (var.clamp_min(0).sqrt() + 1e-8)).float())
+
+    fused_gae = True
+
+    def _compute_returns_fused(self, last_values, gamma, lam, reduce_moments):
+        """Same recursion in one kernel (nm_gae): one thread per environment walks the T steps; the advantage moments come back
+        in fp64 and the normalisation is three small tensor ops."""
+        import ctypes
+
+        from .. import _lib
+        T, N = self.num_transitions_per_env, self.num_envs
+        dev = self.values.device
+        if getattr(self, "_moments", None) is None:
+            self._moments = torch.zeros(2, device=dev, dtype=torch.float64)
+        lv = last_values.detach().reshape(-1).float().contiguous()
+        _lib.check(_lib.lib.nm_gae(T, N, self.rewards.data_ptr(), self.dones.data_ptr(), self.values.data_ptr(), lv.data_ptr(),
+                                   float(gamma), float(lam), self.returns.data_ptr(), self.advantages.data_ptr(), self._moments.data_ptr(),
+                                   ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
+        s, ss = self._moments[0], self._moments[1]
+        n = torch.tensor(float(T * N), device=dev, dtype=torch.float64)
+        if reduce_moments is not None:
+            s, ss, n = reduce_moments(s, ss, n)
+        mean = s / n
+        var = (ss - n * mean * mean) / (n - 1.0)              # unbiased, like torch.std
+        self.advantages.sub_(mean.float()).div_(var.clamp_min(0).sqrt().float() + 1e-8)
 
     def get_statistics(self):
         done = self.dones.clone()

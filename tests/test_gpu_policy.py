@@ -266,3 +266,79 @@ def test_fused_ppo_head_matches_autograd():
     assert abs(l0 - l1) < 1e-4 * max(1, abs(l0)) and abs(v0_ - v1) < 1e-4 * max(1, abs(v0_)) and abs(s0 - s1) < 1e-5 and abs(k0 - k1) < 1e-5
     for a, b in zip(g0, g1):
         assert torch.allclose(a, b, rtol=2e-3, atol=2e-6), (a - b).abs().max()
+
+
+def test_fused_ppo_grad_matches_autograd():
+    """nm_ppo_grad (gather + both MLPs forward/backward + loss head in one launch) == autograd on the eager rsl_rl loss:
+    loss sums to fp32 accuracy (3xTF32 forward), gradients to TF32-backward accuracy; ragged batch (n % 128 != 0)."""
+    from nightmare_rl_b200.ppo import PPO, ActorCritic
+    torch.manual_seed(0)
+    rows, n = 3000, 2477
+    ac = ActorCritic(66, 66, 18, actor_hidden_dims=[54, 42, 30], critic_hidden_dims=[54, 42, 30])
+    alg = PPO(ac, clip_param=0.2, value_loss_coef=1.0, entropy_coef=0.0015, device="cuda:0", fused_rollout=False, graph_update=True)
+    assert alg.fused_grad is not None
+    fg = alg.fused_grad
+    with torch.no_grad():
+        ac.std.copy_(torch.linspace(0.5, 1.5, 18))
+    assert ac.std.data_ptr() == fg.flat.data_ptr()                     # parameters are views of the flat buffer
+    g = torch.Generator(device=DEV).manual_seed(1)
+    obs = torch.randn(rows, 66, device=DEV, generator=g)
+    with torch.no_grad():
+        ac.update_distribution(obs)
+        mu0 = ac.action_mean.clone()
+        act = mu0 + ac.std * torch.randn(rows, 18, device=DEV, generator=g)
+        old_mu = mu0 + 0.05 * torch.randn(rows, 18, device=DEV, generator=g)
+        old_sigma = (ac.std * (1 + 0.05 * torch.randn(18, device=DEV, generator=g))).expand(rows, 18).contiguous()
+        old_logp = (ac.get_actions_log_prob(act) + 0.3 * torch.randn(rows, device=DEV, generator=g)).unsqueeze(1).contiguous()
+        v0 = ac.evaluate(obs)
+        tgt = (v0 + 0.3 * torch.randn(rows, 1, device=DEV, generator=g)).contiguous()
+        ret = (v0 + torch.randn(rows, 1, device=DEV, generator=g)).contiguous()
+        adv = torch.randn(rows, 1, device=DEV, generator=g)
+    idx = torch.randperm(rows, device=DEV, generator=g)[:n].contiguous()
+    out = fg(n, idx, obs, obs, act, old_logp, old_mu, old_sigma, adv, ret, tgt, 0.2, 1.0, 0.0015, True)
+    torch.cuda.synchronize()
+    sums = (out / n).tolist()
+    got = fg.flat_grad.clone()
+    # autograd reference on the same rows, fp32 backward
+    alg.fused_head = False
+    alg.tf32_backward = False
+    params = list(ac.parameters())
+    loss, vl, sl, kl = alg._minibatch_loss(obs[idx], obs[idx], act[idx], tgt[idx], adv[idx], ret[idx], old_logp[idx], old_mu[idx], old_sigma[idx])
+    grads = torch.autograd.grad(loss, params)
+    assert abs(sums[0] - float(sl)) < 2e-5 and abs(sums[1] - float(vl)) < 1e-4 * max(1.0, float(vl)) and abs(sums[2] - float(kl)) < 2e-5, (sums, float(sl), float(vl), float(kl))
+    worst = 0.0
+    for p, gr in zip(params, grads):
+        off = (p.data_ptr() - fg.flat.data_ptr()) // 4
+        mine = got[off:off + p.numel()].view_as(p)
+        scale = gr.abs().max().item()
+        err = (mine - gr).abs().max().item() / max(scale, 1e-12)
+        worst = max(worst, err)
+        assert err < 5e-3, (tuple(p.shape), err, scale)
+    print(f"\n[ppo-grad] worst gradient error relative to each tensor's max |grad|: {worst:.2e}")
+    # identity rows (idx = None) and an exact multiple of the CTA batch
+    out2 = fg(256, None, obs, obs, act, old_logp, old_mu, old_sigma, adv, ret, tgt, 0.2, 1.0, 0.0015, True)
+    torch.cuda.synchronize()
+    sl2 = alg._minibatch_loss(obs[:256], obs[:256], act[:256], tgt[:256], adv[:256], ret[:256], old_logp[:256], old_mu[:256], old_sigma[:256])[2]
+    assert abs(out2[0].item() / 256 - float(sl2)) < 2e-5
+
+
+def test_fused_gae_matches_loop():
+    """nm_gae == the rsl_rl compute_returns loop (returns exactly up to fp32 rounding, normalised advantages to 1e-5)."""
+    from nightmare_rl_b200.ppo.storage import RolloutStorage
+    T, N = 24, 1000
+    g = torch.Generator(device=DEV).manual_seed(3)
+    sts = []
+    for fused in (False, True):
+        st = RolloutStorage(N, T, [66], [None], [18], device=DEV)
+        st.fused_gae = fused
+        gg = torch.Generator(device=DEV).manual_seed(3)
+        st.rewards.copy_(torch.randn(T, N, 1, device=DEV, generator=gg))
+        st.values.copy_(torch.randn(T, N, 1, device=DEV, generator=gg))
+        st.dones.copy_((torch.rand(T, N, 1, device=DEV, generator=gg) < 0.05).to(torch.uint8))
+        last = torch.randn(N, 1, device=DEV, generator=gg)
+        st.compute_returns(last, 0.99, 0.95)
+        sts.append(st)
+    torch.cuda.synchronize()
+    assert torch.allclose(sts[0].returns, sts[1].returns, rtol=1e-5, atol=1e-5)
+    assert torch.allclose(sts[0].advantages, sts[1].advantages, rtol=1e-4, atol=1e-5)
+    assert abs(sts[1].advantages.mean().item()) < 1e-5 and abs(sts[1].advantages.std().item() - 1) < 1e-4

@@ -7,6 +7,7 @@ Prints the stall-reason totals, the opcode mix and the source lines that collect
 samples for one profiled launch.  With --regions the samples are bucketed by the `// ====` section
 banners of nm_kernels.cu (kinematics, CRBA, collision, PGS, ...)."""
 import argparse
+import os
 import collections
 import csv
 import io
@@ -49,8 +50,8 @@ def main():
     for s in secs:
         if s[1] not in kernels:
             kernels.append(s[1])
-    mine = [s for s in secs if s[0].endswith("nm_kernels.cu")]
-    per_launch = len(mine) // max(1, len([1 for s in secs if s[0].endswith("nm_kernels.cu")]) // max(1, len(set(s[1] for s in mine)))) if mine else 0
+    mine = [s for s in secs if s[0].endswith(os.path.basename(a.src))]
+    per_launch = len(mine) // max(1, len([1 for s in secs if s[0].endswith(os.path.basename(a.src))]) // max(1, len(set(s[1] for s in mine)))) if mine else 0
     sec = mine[a.launch] if a.launch < len(mine) else mine[0]
     hdr = rows[sec[2]]
     ci = {c: i for i, c in enumerate(hdr)}
