@@ -43,6 +43,9 @@ struct T5Args {
 // ---------------------------------------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ unsigned t5_tf32(float x) { unsigned r; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x)); return r; }
+// hi/lo split for the per-element hot loops: cvt.rna.tf32 is a ~4-instruction sequence on sm_100a, a mask is one.  hi = x with the
+// 13 low mantissa bits cleared (exact TF32), lo = x - hi (exact in fp32); the tensor core ignores lo's own low bits (< 2^-20 |x|).
+__device__ __forceinline__ unsigned t5_hi(float x) { return __float_as_uint(x) & 0xffffe000u; }
 
 // UMMA shared-memory descriptor, K-major, SWIZZLE_NONE: 8-row x 16-byte core matrices; LBO = byte distance between the
 // two 16-byte K chunks of one MMA, SBO = byte distance between 8-row groups (cute/arch/mma_sm100_desc.hpp SmemDescriptor)
@@ -159,10 +162,10 @@ __device__ __forceinline__ void t5_net(const T5Net& net, const float* X_hi, cons
           if (last) { if (cc < 2) out[(cc < 2 ? cc : 0) * 8 + i] = x; }
           else {
             x = (col < L.kout) ? (x > 0.f ? x : __expf(x) - 1.f) : 0.f;      // ELU; padded columns stay exactly zero
-            const unsigned h = t5_tf32(x);
+            const unsigned h = t5_hi(x);
             const int idx = rbase + (col >> 2) * 32 + (col & 3);
             H_hi[idx] = __uint_as_float(h);
-            H_lo[idx] = __uint_as_float(t5_tf32(x - __uint_as_float(h)));
+            H_lo[idx] = x - __uint_as_float(h);
           }
         }
       }
