@@ -33,7 +33,14 @@ def main():
     ap.add_argument("--envs", type=int, default=128)
     ap.add_argument("--steps", type=int, default=300)
     ap.add_argument("--every", type=int, default=3)
+    ap.add_argument("--gait", action="store_true", help="drive ONE env with the reference's scripted tripod gait "
+                    "(tests/golden/nikengine_gait_targets.npz) instead of random actions")
     a = ap.parse_args()
+    gait = None
+    if a.gait:
+        z = np.load(os.path.join(ROOT, "tests", "golden", "nikengine_gait_targets.npz"))
+        gait = ((z["targets"] + np.array([0.0, np.pi / 5, 0.0] * 6)) / 0.2).astype(np.float32)
+        a.envs, a.steps = 1, len(gait)
     cm = mjcf.CompiledModel.load(NMB)
     A = cm.arrays
     hv = A["hull_vert"].reshape(-1, 3).astype(np.float64)
@@ -53,10 +60,11 @@ def main():
     ob = O.OracleBatch(om, a.envs, seed=1, envcfg=build_envcfg(cfg, 0.008))
     ob.env_reset_idx(np.arange(a.envs))
     rng = np.random.default_rng(1)
-    ob.env_set("ep_len", rng.integers(0, 1250, a.envs).astype(np.float64))
+    if gait is None:
+        ob.env_set("ep_len", rng.integers(0, 1250, a.envs).astype(np.float64))
     mind, inside, samples, fallen = [], 0, 0, 0
     for t in range(a.steps):
-        ob.env_step(rng.normal(size=(a.envs, 18)).astype(np.float32), 8)
+        ob.env_step(gait[t][None] if gait is not None else rng.normal(size=(a.envs, 18)).astype(np.float32), 8)
         if t % a.every:
             continue
         ob.forward(None, 8)
@@ -81,7 +89,7 @@ def main():
             samples += 1
     mind = np.array(mind)
     fin = mind[np.isfinite(mind)]
-    print(f"{samples} env-states sampled from {a.envs} envs x {a.steps} random-action steps")
+    print(f"{samples} env-states sampled from {a.envs} envs x {a.steps} {'scripted-gait' if gait is not None else 'random-action'} steps")
     print(f"closest approach of any tibia pair (vertex-to-vertex): min {fin.min() * 1e3:.1f} mm, 1st percentile {np.percentile(fin, 1) * 1e3:.1f} mm, median {np.median(fin) * 1e3:.1f} mm")
     print(f"states with a tibia pair closer than 5 mm: {(fin < 0.005).sum()} ({100.0 * (fin < 0.005).sum() / samples:.3f} %), closer than 20 mm: {(fin < 0.02).sum()}")
     print(f"states with interpenetrating tibia hulls (vertex-in-hull test): {inside} ({100.0 * inside / samples:.3f} %)")
