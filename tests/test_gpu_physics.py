@@ -200,6 +200,87 @@ def test_walking_gait_trajectory():
     assert touch <= 100 * n * 6 * 2e-3                                  # flags flip only at touch-down / lift-off instants
 
 
+def test_simple_test_variant_timestep_and_decimation(tmp_path):
+    """The reference's CPU throughput script runs the same model at timestep 0.0025 with decimation 4 and zero ctrl
+    (simple_test.py:21-28).  Same here: the kernel takes the timestep from the compiled model and any number of substeps per
+    call.  32 slightly different robots are dropped from qpos0 and settle flat on the floor (hull and tibias lying on their
+    faces: up to 8 contacts, the most tie-prone configuration there is).  Every substep is compared in lockstep; a substep whose
+    CONTACT SET differs (a support vertex chosen among vertices of equal depth to < 1e-7 m, or a contact appearing one substep
+    earlier) is a different, equally valid input to the solver and is counted, not compared."""
+    from nightmare_rl_b200 import _lib, mjcf
+    from conftest import NMB
+    G = _common()
+    cm = mjcf.CompiledModel.load(NMB)
+    cm.arrays["opt_real"][0] = 0.0025
+    path = str(tmp_path / "dt0025.nmb")
+    cm.save(path)
+    dm, om = _lib.Model(cm.to_bytes()), G.O.OracleModel(path)
+    assert abs(dm.timestep - 0.0025) < 1e-12
+    n, T = 32, 480
+    rng = np.random.default_rng(11)
+    qpos = np.tile(cm.qpos0, (n, 1))
+    qpos[:, 7:] += rng.uniform(-0.2, 0.2, (n, 18))
+    ob, gb, gb4 = G.O.OracleBatch(om, n), G.Batch(dm, n, G.DEV, debug=True), G.Batch(dm, n, G.DEV)
+    z = np.zeros((n, 24))
+    ob.set_state(qpos.astype(np.float32), z, z)
+    ctrl = np.zeros((n, 18), dtype=np.float32)
+    tctrl = torch.from_numpy(ctrl)
+    worst, set_diff, compared, max_tie_depth = 0.0, 0, 0, 0.0
+    dec_dev = []
+    for t in range(T):
+        q, v, w = ob.get_state()
+        q, v, w = q.astype(np.float32), v.astype(np.float32), w.astype(np.float32)
+        ob.set_state(q, v, w)
+        G.push_state(gb, q, v, w)
+        if t % 4 == 0:                                                  # decimation: one call with nstep=4 == four calls with nstep=1
+            G.push_state(gb4, q, v, w)
+            gb4.physics_step(tctrl, 4)
+            chain = G.Batch(dm, n, G.DEV)
+            G.push_state(chain, q, v, w)
+            for _ in range(4):
+                chain.physics_step(tctrl, 1)
+            torch.cuda.synchronize()
+            # not bitwise: a fresh call re-normalises the stored quaternion when it loads it (as mj_kinematics does every substep),
+            # inside a call the integrated quaternion stays in registers -- an ulp-level difference that a tie can amplify
+            dq = G.per_env_rel(G.gpu_state(gb4)[0], G.gpu_state(chain)[0])
+            dv = G.per_env_rel(G.gpu_state(gb4)[1], G.gpu_state(chain)[1], floor=0.1)
+            dec_dev.append(np.maximum(dq, dv))
+        ob.physics_step(ctrl, 1, 8)
+        gb.physics_step(tctrl, 1)
+        torch.cuda.synchronize()
+        oq, ov, _ = ob.get_state()
+        gq, gv, _ = G.gpu_state(gb)
+        dbg = gb.debug.cpu().numpy()
+        same = np.ones(n, dtype=bool)
+        for i in range(n):
+            if int(ob.get(i, "ncon")[0]) != int(dbg[i, 0]):
+                same[i] = False
+                continue
+            con = ob.get(i, "contact").reshape(-1, 7)
+            for lane, geom in [(6, 1)] + [(k, 2 + k) for k in range(6)]:
+                mine = con[con[:, 1] == geom]
+                rec = dbg[i, 8 + lane * 12: 8 + lane * 12 + 9]
+                for c in range(len(mine)):
+                    if int(rec[1 + 2 * c]) != int(mine[c, 2]):
+                        same[i] = False
+                        max_tie_depth = max(max_tie_depth, abs(rec[2 + 2 * c] - mine[c, 3]))
+        d = np.maximum(G.per_env_rel(gq, oq), G.per_env_rel(gv, ov, floor=0.1))
+        set_diff += int((~same).sum())
+        compared += int(same.sum())
+        if same.any():
+            worst = max(worst, float(d[same].max()))
+    print(f"\n[dt=0.0025] {T} lockstep substeps x {n} envs: compared {compared}, contact set differs in {set_diff} "
+          f"(largest depth gap between the two candidate vertices {max_tie_depth:.1e} m); worst single-substep deviation {worst:.2e}; "
+          f"base height at the end {gq[:, 2].mean():.4f} m")
+    dec = np.concatenate(dec_dev)
+    print(f"[dt=0.0025] one call with nstep=4 vs four calls with nstep=1: median deviation {np.median(dec):.1e}, p99 {np.percentile(dec, 99):.1e}, "
+          f"above 1e-4: {(dec > 1e-4).sum()} of {dec.size}")
+    assert np.median(dec) < 1e-6 and (dec > 1e-4).mean() < 0.02
+    assert worst < 2e-4
+    assert set_diff < 0.01 * n * T and max_tie_depth < 1e-7
+    assert gq[:, 2].max() < 0.03 and np.isfinite(gq).all()              # they have landed (released at 0.15 m) and lie on the hull
+
+
 def test_determinism_and_batch_independence():
     """Bitwise reproducible, and env i does not depend on its neighbours or on the batch size (the
     property multi-GPU sharding relies on)."""
