@@ -9,7 +9,8 @@
 // small GEMMs, 8 split-K weight-gradient GEMMs, element-wise and reduction kernels) and 1.35 ms at 81 920 samples; the
 // networks are so small (66-54-42-30-18 / 1, 15 k parameters) that everything fits in one SM's shared memory.
 //
-// Grid: blockIdx.y = network (0 actor, 1 critic), blockIdx.x = persistent CTA walking 128-sample batches.  Per CTA
+// Grid: one persistent CTA per SM; the first `actor_ctas` CTAs work on the actor, the others on the critic, each walking
+// 128-sample batches.  Per CTA
 // (8 warps): the net's weights, transposed and zero padded, and a gradient accumulator of the same shape live in
 // shared memory for the whole launch; every warp owns 16 samples of the batch and keeps all of its layer activations
 // in shared memory.
@@ -23,6 +24,7 @@
 //   end       one pass of global atomic adds per CTA into the PyTorch-layout gradient vectors
 #include <cuda_runtime.h>
 
+#include <cstdlib>
 #include <cstring>
 #include <string>
 
@@ -49,6 +51,7 @@ struct PgNet {
 struct PgArgs {
   PgNet net[2];
   nm_ppo_grad_args a;
+  int actor_ctas;                       // CTAs [0, actor_ctas) work on the actor, the rest on the critic
 };
 
 // TF32 operands.  `cvt.rna.tf32.f32` costs ~4 instructions on sm_100a (first ncu capture: 21 % of all executed
@@ -70,7 +73,9 @@ __device__ __forceinline__ void pg_prefetch(const void* p) { asm volatile("prefe
 
 __global__ void __launch_bounds__(PG_WARPS * 32, 1) nm_ppo_grad_kernel(const PgArgs P) {
   extern __shared__ __align__(16) float smem[];
-  const int which = blockIdx.y;
+  const int which = (int)blockIdx.x >= P.actor_ctas ? 1 : 0;
+  const int cta = which ? (int)blockIdx.x - P.actor_ctas : (int)blockIdx.x;         // index and count among this network's CTAs
+  const int nctas = which ? (int)gridDim.x - P.actor_ctas : P.actor_ctas;
   const PgNet& N = P.net[which];
   const nm_ppo_grad_args& A = P.a;
   const float* __restrict__ src = which ? A.critic_params : A.actor_params;
@@ -104,13 +109,13 @@ __global__ void __launch_bounds__(PG_WARPS * 32, 1) nm_ppo_grad_kernel(const PgA
   const float inv_n = 1.f / (float)A.n;
   float acc_s = 0.f, acc_v = 0.f, acc_k = 0.f;
 
-  for (int batch = blockIdx.x; batch * PG_ROWS < A.n; batch += gridDim.x) {
+  for (int batch = cta; batch * PG_ROWS < A.n; batch += nctas) {
     const int row0 = batch * PG_ROWS + warp * 16;
     // ---------------------------------------------------------------- gather the 16 observation rows of this warp
     long long ri = -1;
     if (lane < 16 && row0 + lane < A.n) ri = A.idx ? A.idx[row0 + lane] : (long long)(row0 + lane);
     {                                                          // pull the NEXT batch's rows towards L2 while this one computes
-      const int nrow = row0 + gridDim.x * PG_ROWS + lane;
+      const int nrow = row0 + nctas * PG_ROWS + lane;
       if (lane < 16 && nrow < A.n) {
         const long long rn = A.idx ? A.idx[nrow] : (long long)nrow;
         const char* po = reinterpret_cast<const char*>(xin + rn * A.obs_dim);
@@ -404,7 +409,7 @@ __global__ void __launch_bounds__(PG_WARPS * 32, 1) nm_ppo_grad_kernel(const PgA
   if (which == 0) {
     if (tid < A.act_dim) {
       float v = s_gstd[tid];
-      if (blockIdx.x == 0) v += -A.entropy_coef / s_std[tid];          // d(-entropy_coef * mean entropy)/d std, sample independent
+      if (cta == 0) v += -A.entropy_coef / s_std[tid];          // d(-entropy_coef * mean entropy)/d std, sample independent
       atomicAdd(A.g_std + tid, v);
     }
     if (tid == 0) { atomicAdd(A.out, s_red[0]); atomicAdd(A.out + 2, s_red[2]); }
@@ -471,9 +476,14 @@ extern "C" int nm_ppo_grad(const nm_mlp_shape* actor, const nm_mlp_shape* critic
     return nm_fail(NM_ERR_CUDA, "nm_ppo_grad: memset failed");
   P.a = *a;
   const int batches = (a->n + PG_ROWS - 1) / PG_ROWS;
-  int per_net = sms / 2 > 0 ? sms / 2 : 1;                      // one CTA per SM, half of the SMs per network
-  if (per_net > batches) per_net = batches;
-  nm_ppo_grad_kernel<<<dim3(per_net, 2), PG_WARPS * 32, smem, st>>>(P);
+  // one CTA per SM; the actor (wider output layer, Gaussian head) gets the larger share of the SMs
+  int n_act = (sms * 9 + 8) / 16, n_cri = sms - n_act;
+  if (const char* e = getenv("NM_PG_ACTOR_CTAS")) { const int v = atoi(e); if (v > 0 && v < sms) { n_act = v; n_cri = sms - v; } }
+  if (n_cri < 1) { n_act = 1; n_cri = 1; }
+  if (n_act > batches) n_act = batches;
+  if (n_cri > batches) n_cri = batches;
+  P.actor_ctas = n_act;
+  nm_ppo_grad_kernel<<<n_act + n_cri, PG_WARPS * 32, smem, st>>>(P);
   if (cudaGetLastError() != cudaSuccess) return nm_fail(NM_ERR_CUDA, "nm_ppo_grad: launch failed");
   return NM_OK;
 }
