@@ -9,17 +9,18 @@
 // small GEMMs, 8 split-K weight-gradient GEMMs, element-wise and reduction kernels) and 1.35 ms at 81 920 samples; the
 // networks are so small (66-54-42-30-18 / 1, 15 k parameters) that everything fits in one SM's shared memory.
 //
-// Grid: one persistent CTA per SM; the first `actor_ctas` CTAs work on the actor, the others on the critic, each walking
+// Grid: one persistent CTA (16 warps) per SM; the first `actor_ctas` CTAs work on the actor, the others on the critic, each walking
 // 128-sample batches.  Per CTA
-// (8 warps): the net's weights, transposed and zero padded, and a gradient accumulator of the same shape live in
-// shared memory for the whole launch; every warp owns 16 samples of the batch and keeps all of its layer activations
-// in shared memory.
-//   forward   per warp, mma.sync.m16n8k8 TF32 issued 3x on hi/lo splits (fp32-level accuracy: the probability ratio
+// the net's weights, transposed and zero padded, and a gradient accumulator of the same shape live in shared memory for
+// the whole launch; every PAIR of warps owns 16 samples of the batch, keeps all of their layer activations in shared
+// memory and splits the output tiles of each layer between its two warps (shared memory caps the CTA at 8 sample tiles;
+// the second warp per tile doubles the warps the schedulers can choose from).
+//   forward   per warp pair, mma.sync.m16n8k8 TF32 issued 3x on hi/lo splits (fp32-level accuracy: the probability ratio
 //             must be 1 when the policy has not changed), ELU, activations of every layer kept
-//   head      per warp, two lanes per sample; writes d(loss)/d(output) over the output tile
+//   head      four lanes per sample (8 samples per warp); writes d(loss)/d(output) over the output tile
 //   backward  layer by layer: bias gradient = column sums (shared-memory atomics); weight gradient = H^T dZ over the
 //             CTA's 128 samples (K = 128) with each 16x8 output tile owned by one warp, accumulated in shared memory
-//             without atomics; input gradient per warp, ELU derivative applied from the stored activation, written in
+//             without atomics; input gradient per warp pair, ELU derivative applied from the stored activation, written in
 //             place over that activation (single-pass TF32, like the TF32 autograd backward it replaces)
 //   end       one pass of global atomic adds per CTA into the PyTorch-layout gradient vectors
 #include <cuda_runtime.h>
@@ -32,8 +33,9 @@
 
 #define PG_MAXL 6
 #define PG_MAXW 128
-#define PG_WARPS 8
+#define PG_WARPS 8            // 16-sample tiles per CTA batch
 #define PG_ROWS (PG_WARPS * 16)
+#define PG_THREADS (PG_WARPS * 64)   // TWO warps per tile: they split the output tiles of every layer between them
 
 int nm_fail(int code, const std::string& msg);   // nm_abi.cu
 
@@ -71,7 +73,10 @@ __device__ __forceinline__ void pg_mma(float* c, const unsigned* a, unsigned b0,
 
 __device__ __forceinline__ void pg_prefetch(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
-__global__ void __launch_bounds__(PG_WARPS * 32, 1) nm_ppo_grad_kernel(const PgArgs P) {
+// barrier of the two warps that share a tile (ids 1..PG_WARPS; 0 is __syncthreads)
+__device__ __forceinline__ void pg_pair_sync(int tile) { asm volatile("bar.sync %0, 64;" ::"r"(tile + 1) : "memory"); }
+
+__global__ void __launch_bounds__(PG_THREADS, 1) nm_ppo_grad_kernel(const PgArgs P) {
   extern __shared__ __align__(16) float smem[];
   const int which = (int)blockIdx.x >= P.actor_ctas ? 1 : 0;
   const int cta = which ? (int)blockIdx.x - P.actor_ctas : (int)blockIdx.x;         // index and count among this network's CTAs
@@ -86,7 +91,8 @@ __global__ void __launch_bounds__(PG_WARPS * 32, 1) nm_ppo_grad_kernel(const PgA
   float* s_std = act + PG_WARPS * N.region;    // [64]
   float* s_gstd = s_std + 64;                  // [64]
   float* s_red = s_gstd + 64;                  // [4]
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const int tid = threadIdx.x, wid = tid >> 5, warp = wid >> 1, hw = wid & 1, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  // `warp` = tile index (16 samples), `hw` = which of the tile's two warps this is, `wid` = warp index in the CTA
   const int nl = N.nl;
 
   for (int i = tid; i < 2 * N.total; i += blockDim.x) W[i] = 0.f;          // W and G are adjacent
@@ -116,7 +122,7 @@ __global__ void __launch_bounds__(PG_WARPS * 32, 1) nm_ppo_grad_kernel(const PgA
     if (lane < 16 && row0 + lane < A.n) ri = A.idx ? A.idx[row0 + lane] : (long long)(row0 + lane);
     {                                                          // pull the NEXT batch's rows towards L2 while this one computes
       const int nrow = row0 + nctas * PG_ROWS + lane;
-      if (lane < 16 && nrow < A.n) {
+      if (hw == 0 && lane < 16 && nrow < A.n) {
         const long long rn = A.idx ? A.idx[nrow] : (long long)nrow;
         const char* po = reinterpret_cast<const char*>(xin + rn * A.obs_dim);
         const int ob = A.obs_dim * 4;
@@ -139,8 +145,8 @@ __global__ void __launch_bounds__(PG_WARPS * 32, 1) nm_ppo_grad_kernel(const PgA
     }
     {
       const int kin = N.kin[0], kp = N.kpad[0], lda = N.lda[0];
-#pragma unroll
-      for (int r0 = 0; r0 < 16; r0 += 8) {                     // 32 independent loads in flight per lane
+      {                                                        // each warp of the pair stages 8 rows; 32 independent loads per lane
+        const int r0 = hw * 8;
         float v[8][4];
 #pragma unroll
         for (int rr = 0; rr < 8; rr++) {
@@ -160,7 +166,7 @@ __global__ void __launch_bounds__(PG_WARPS * 32, 1) nm_ppo_grad_kernel(const PgA
           }
       }
     }
-    __syncwarp();
+    pg_pair_sync(warp);
     // ---------------------------------------------------------------- forward, all activations kept
     for (int l = 0; l < nl; l++) {
       const float* Wl = W + N.woff[l];
@@ -170,8 +176,9 @@ __global__ void __launch_bounds__(PG_WARPS * 32, 1) nm_ppo_grad_kernel(const PgA
       const bool last = l == nl - 1;
       float* out = last ? O : R + N.aoff[l + 1];
       const int ldout = last ? ldo : N.lda[l + 1];
-      for (int nt0 = 0; nt0 < nn; nt0 += 4) {                  // 4 output tiles per pass share the A fragments
-        const int cnt = nn - nt0 < 4 ? nn - nt0 : 4;
+      const int nhalf = (nn + 1) >> 1, nbeg = hw ? nhalf : 0, nend = hw ? nn : nhalf;      // this warp's share of the output tiles
+      for (int nt0 = nbeg; nt0 < nend; nt0 += 4) {             // 4 output tiles per pass share the A fragments
+        const int cnt = nend - nt0 < 4 ? nend - nt0 : 4;
         float ch[4][4], cl[4][4];
 #pragma unroll
         for (int q = 0; q < 4; q++) {
@@ -214,19 +221,19 @@ __global__ void __launch_bounds__(PG_WARPS * 32, 1) nm_ppo_grad_kernel(const PgA
           }
         }
       }
-      __syncwarp();
+      pg_pair_sync(warp);
     }
     // ---------------------------------------------------------------- loss head: O <- d(loss)/d(output)
     if (which == 0) {
-      const int r = lane >> 1, h = lane & 1;
+      const int r = hw * 8 + (lane >> 2), h = lane & 3;        // 4 lanes per sample, 8 samples per warp
       const long long rr = __shfl_sync(0xffffffffu, ri, r);
       const bool valid = rr >= 0;
       const int Ad = A.act_dim;
       float logp = 0.f, kl = 0.f;
-      const int half_n = (Ad + 1) >> 1;
+      const int quarter_n = (Ad + 3) >> 2;
       if (valid) {
 #pragma unroll 3
-        for (int j = h; j < Ad; j += 2) {
+        for (int j = h; j < Ad; j += 4) {
           const float s = s_std[j], m = O[r * ldo + j];
           const float z = (__ldg(A.actions + rr * Ad + j) - m) / s;
           logp += -0.5f * z * z - logf(s) - 0.91893853320467274f;
@@ -235,8 +242,8 @@ __global__ void __launch_bounds__(PG_WARPS * 32, 1) nm_ppo_grad_kernel(const PgA
           O[r * ldo + j] = z;                                  // the mean is not needed again; keep z for the gradient
         }
       }
-      logp += __shfl_xor_sync(0xffffffffu, logp, 1);
-      kl += __shfl_xor_sync(0xffffffffu, kl, 1);
+      logp += __shfl_xor_sync(0xffffffffu, logp, 1); logp += __shfl_xor_sync(0xffffffffu, logp, 2);
+      kl += __shfl_xor_sync(0xffffffffu, kl, 1); kl += __shfl_xor_sync(0xffffffffu, kl, 2);
       float gl = 0.f;
       if (valid) {
         const float adv = __ldg(A.adv + rr);
@@ -250,8 +257,8 @@ __global__ void __launch_bounds__(PG_WARPS * 32, 1) nm_ppo_grad_kernel(const PgA
         gl *= inv_n;
         if (h == 0) { acc_s += fmaxf(s1, s2); acc_k += kl; }
       }
-      for (int q = 0; q < half_n; q++) {                       // same trip count in every lane: the shuffles below are warp-wide
-        const int j = 2 * q + h;
+      for (int q = 0; q < quarter_n; q++) {                    // same trip count in every lane: the shuffles below are warp-wide
+        const int j = 4 * q + h;
         const bool ok = j < Ad;
         float gm = 0.f, gs = 0.f;
         if (ok && valid) {
@@ -260,14 +267,17 @@ __global__ void __launch_bounds__(PG_WARPS * 32, 1) nm_ppo_grad_kernel(const PgA
           gs = gl * (z * z - 1.f) / s;
         }
         if (ok) O[r * ldo + j] = gm;
-        for (int o = 2; o < 32; o <<= 1) gs += __shfl_xor_sync(0xffffffffu, gs, o);      // over the 16 samples, per action column
-        if (r == 0 && ok) atomicAdd(s_gstd + j, gs);
+        for (int o = 4; o < 32; o <<= 1) gs += __shfl_xor_sync(0xffffffffu, gs, o);      // over this warp's 8 samples, per action column
+        if ((lane >> 2) == 0 && ok) atomicAdd(s_gstd + j, gs);
       }
     } else {
-      if (lane < 16) {
+      const int r = hw * 8 + lane;
+      const long long rc_ = __shfl_sync(0xffffffffu, ri, r & 15);
+      if (lane < 8) {
+        const long long ri = rc_;
         float gv = 0.f;
         if (ri >= 0) {
-          const float v = O[lane * ldo], Rt = __ldg(A.ret + ri);
+          const float v = O[r * ldo], Rt = __ldg(A.ret + ri);
           float dv;
           if (A.use_clipped_value_loss) {
             const float tv = __ldg(A.tgt_val + ri);
@@ -283,10 +293,10 @@ __global__ void __launch_bounds__(PG_WARPS * 32, 1) nm_ppo_grad_kernel(const PgA
           }
           gv = A.value_coef * dv * inv_n;
         }
-        O[lane * ldo] = gv;
+        O[r * ldo] = gv;
       }
     }
-    __syncwarp();
+    pg_pair_sync(warp);
     // ---------------------------------------------------------------- backward
     for (int l = nl - 1; l >= 0; l--) {
       const bool last = l == nl - 1;
@@ -295,7 +305,7 @@ __global__ void __launch_bounds__(PG_WARPS * 32, 1) nm_ppo_grad_kernel(const PgA
       const int np = N.npad[l], kp = N.kpad[l], lda = N.lda[l], ldw = N.ldw[l];
       {                                                        // bias gradient: column sums of this warp's 16 rows
         const float* D = R + doff;
-        for (int n = lane; n < np; n += 32) {
+        for (int n = lane + 32 * hw; n < np; n += 64) {
           float s = 0.f;
 #pragma unroll
           for (int r = 0; r < 16; r++) s += D[r * ldd + n];
@@ -307,7 +317,7 @@ __global__ void __launch_bounds__(PG_WARPS * 32, 1) nm_ppo_grad_kernel(const PgA
         const int mt = (kp + 15) >> 4, nt = np >> 3;
         float* Gl = G + N.woff[l];
         const int npair = (nt + 1) >> 1;                       // units of two neighbouring 16x8 tiles share the A fragments
-        for (int unit = warp; unit < mt * npair; unit += PG_WARPS) {
+        for (int unit = wid; unit < mt * npair; unit += 2 * PG_WARPS) {
           const int mi = unit / npair, pj = unit - mi * npair;
           const int m0 = mi * 16, n0 = pj * 16;
           const bool hi_ok = m0 + 8 < kp;                      // rows m0+8.. exist (kp is a multiple of 8)
@@ -353,8 +363,9 @@ __global__ void __launch_bounds__(PG_WARPS * 32, 1) nm_ppo_grad_kernel(const PgA
         const float* Wl = W + N.woff[l];
         float* H = R + N.aoff[l];
         const int nk = np >> 3, nc = kp >> 3;
-        for (int ct0 = 0; ct0 < nc; ct0 += 4) {                // 4 output tiles per pass share the dZ fragments
-          const int cnt = nc - ct0 < 4 ? nc - ct0 : 4;
+        const int chalf = (nc + 1) >> 1, cbeg = hw ? chalf : 0, cend = hw ? nc : chalf;
+        for (int ct0 = cbeg; ct0 < cend; ct0 += 4) {           // 4 output tiles per pass share the dZ fragments
+          const int cnt = cend - ct0 < 4 ? cend - ct0 : 4;
           float c[4][4];
 #pragma unroll
           for (int i = 0; i < 16; i++) (&c[0][0])[i] = 0.f;
@@ -385,7 +396,7 @@ __global__ void __launch_bounds__(PG_WARPS * 32, 1) nm_ppo_grad_kernel(const PgA
             }
           }
         }
-        __syncwarp();
+        pg_pair_sync(warp);
       }
     }
   }
@@ -483,7 +494,7 @@ extern "C" int nm_ppo_grad(const nm_mlp_shape* actor, const nm_mlp_shape* critic
   if (n_act > batches) n_act = batches;
   if (n_cri > batches) n_cri = batches;
   P.actor_ctas = n_act;
-  nm_ppo_grad_kernel<<<n_act + n_cri, PG_WARPS * 32, smem, st>>>(P);
+  nm_ppo_grad_kernel<<<n_act + n_cri, PG_THREADS, smem, st>>>(P);
   if (cudaGetLastError() != cudaSuccess) return nm_fail(NM_ERR_CUDA, "nm_ppo_grad: launch failed");
   return NM_OK;
 }
