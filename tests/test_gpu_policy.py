@@ -344,3 +344,50 @@ def test_fused_gae_matches_loop():
     assert torch.allclose(sts[0].returns, sts[1].returns, rtol=1e-5, atol=1e-5)
     assert torch.allclose(sts[0].advantages, sts[1].advantages, rtol=1e-4, atol=1e-5)
     assert abs(sts[1].advantages.mean().item()) < 1e-5 and abs(sts[1].advantages.std().item() - 1) < 1e-4
+
+
+def test_checkpoint_resume_with_fused_update(tmp_path):
+    """train.py -r flow (reference train.py:49-52): save, rebuild, load, continue.  With the fused update the parameters and
+    their gradients are views of two flat buffers; loading a checkpoint must keep them so (in-place copies) and Adam's state
+    must come back with it."""
+    from envs.helpers import class_to_dict
+    from envs.nightmare_v3_config import NightmareV3Config, NightmareV3ConfigPPO
+    from envs.nightmare_v3_env import NightmareV3Env
+    from rsl_rl.runners import OnPolicyRunner
+
+    def make(sub):
+        cfg, tc = NightmareV3Config(), NightmareV3ConfigPPO()
+        cfg.env.num_envs = 256
+        cfg.env.model_path = NMB
+        cfg.viewer.render = cfg.viewer.record_states = False
+        tc.runner.num_steps_per_env = 8
+        log_dir = str(tmp_path / sub)
+        os.makedirs(log_dir)
+        env = NightmareV3Env(cfg, log_dir=log_dir, num_threads=1)
+        return OnPolicyRunner(env, class_to_dict(tc), log_dir=log_dir, device=cfg.rl_device)
+
+    r1 = make("a")
+    r1.learn(num_learning_iterations=3, init_at_random_ep_len=True)
+    assert r1.alg.fused_grad is not None
+    path = str(tmp_path / "ck.pt")
+    r1.save(path)
+    saved = {k: v.clone() for k, v in r1.alg.actor_critic.state_dict().items()}
+    exp_avg = r1.alg.optimizer.state[r1.alg.actor_critic.std]["exp_avg"].clone()
+    lr1 = r1.alg.learning_rate
+    ck = torch.load(path, map_location="cpu", weights_only=False)
+    assert set(ck.keys()) == {"model_state_dict", "optimizer_state_dict", "iter", "infos"}
+    assert isinstance(ck["optimizer_state_dict"]["param_groups"][0]["lr"], float)
+    assert set(ck["model_state_dict"].keys()) == {"std"} | {f"{net}.{i}.{w}" for net in ("actor", "critic") for i in (0, 2, 4, 6) for w in ("weight", "bias")}
+    r2 = make("b")
+    r2.load(path)
+    fg = r2.alg.fused_grad
+    lo, hi = fg.flat.data_ptr(), fg.flat.data_ptr() + 4 * fg.flat.numel()
+    for k, p in r2.alg.actor_critic.named_parameters():
+        assert lo <= p.data_ptr() < hi and p.grad is not None and fg.flat_grad.data_ptr() <= p.grad.data_ptr() < fg.flat_grad.data_ptr() + 4 * fg.flat_grad.numel()
+        assert torch.equal(p.detach(), saved[k])
+    assert torch.equal(r2.alg.optimizer.state[r2.alg.actor_critic.std]["exp_avg"], exp_avg)
+    assert abs(r2.alg.learning_rate - lr1) < 1e-12 and r2.current_learning_iteration == 3
+    r2.learn(num_learning_iterations=2)
+    assert np.isfinite(r2.last_log["value_loss"]) and r2.current_learning_iteration == 5
+    moved = max((p.detach() - saved[k]).abs().max().item() for k, p in r2.alg.actor_critic.named_parameters())
+    assert 0 < moved < 0.5
