@@ -1,7 +1,10 @@
 /* nm_oracle.c — CPU oracle, plain C, fp64.  TEST INFRASTRUCTURE ONLY (see nm_oracle.h).
  *
  * Restates, stage by stage, what the reference executes for one environment step:
- *   env layer : /root/reference/envs/nightmare_v3_env.py:145-371,399-497
+ *   env layer : /root/reference/envs/nightmare_v3_env.py:145-371,399-497.  PINNED: the reference's own, unmodified
+ *               NightmareV3Env code was run in the build container over a stand-in for its seven MuJoCo calls
+ *               (tools/make_refenv_golden.py); this file reproduces its observations and rewards bit for bit and its
+ *               flags / counters / commands exactly (tests/test_reference_env_golden.py).
  *   physics   : MuJoCo 3.1.2 mj_step (called at envs/nightmare_v3_env.py:200), published pipeline
  *               (SURVEY.md §3.2 and Appendix A).  MuJoCo is a third-party dependency that is absent
  *               from /root/reference and not installable here -> PARITY UNPINNED against real MuJoCo.
@@ -1246,8 +1249,10 @@ static void env_step_one(nmo_batch* b, int i, const float* act, float* obs, floa
   double prev_dof_vel[18];
   for (int j = 0; j < 18; j++) {
     e->prev_actions[j] = e->actions[j];
-    double a = (double)act[j] * c->action_scale;
-    e->actions[j] = a < -c->clip_actions ? -c->clip_actions : (a > c->clip_actions ? c->clip_actions : a);
+    /* the reference scales and clips the policy's float32 tensor in float32 (numpy: float32 array * python float stays
+     * float32, envs/nightmare_v3_env.py:155-156) and only then mixes it with float64 buffers */
+    const float a32 = act[j] * (float)c->action_scale, lim = (float)c->clip_actions;
+    e->actions[j] = (double)(a32 < -lim ? -lim : (a32 > lim ? lim : a32));
     prev_dof_vel[j] = e->dof_vel[j];
   }
   /* E3/E4: PD law from the carried (possibly stale) dof_pos */

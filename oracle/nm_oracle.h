@@ -6,9 +6,13 @@
  *                  (third-party, pinned `mujoco<=3.1.2` in requirements.txt:2, NOT vendored in the
  *                  reference tree; restated from its published pipeline).
  *
- * PARITY UNPINNED: the reference holds no golden vectors / tests for this path and MuJoCo cannot be
- * installed in this environment, so this oracle is validated by physical invariants only
- * (tests/test_oracle_physics.py) — see DESIGN.md "Oracle".
+ * ENV LAYER PINNED: checked against the outputs of the reference's own, unmodified NightmareV3Env code run in the
+ * build container over a stand-in for its MuJoCo calls (tools/make_refenv_golden.py -> tests/golden/
+ * reference_env_on_oracle_physics.npz; tests/test_reference_env_golden.py: observations and rewards bit-identical).
+ * PHYSICS PARITY UNPINNED: the reference holds no golden vectors / tests for this path and MuJoCo cannot be
+ * installed in this environment, so the mj_step restatement is validated by physical invariants
+ * (tests/test_oracle_physics.py) and by the behaviour of the reference's scripted gait on it (tests/test_gait.py)
+ * only — see DESIGN.md "Oracle".
  *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference leg may use it.
  */

@@ -68,8 +68,8 @@ class MirrorEnv:
     def step(self, actions):
         cfg = self.cfg
         self.prev_actions = self.actions
-        all_actions = np.asarray(actions, dtype=np.float64) * cfg.control.action_scale
-        self.actions = np.clip(all_actions[:, :18], -cfg.normalization.clip_actions, cfg.normalization.clip_actions)
+        all_actions = np.asarray(actions, dtype=np.float32) * cfg.control.action_scale          # float32, as with the policy's tensor (:155)
+        self.actions = np.clip(all_actions[:, :18], -cfg.normalization.clip_actions, cfg.normalization.clip_actions).astype(np.float64)
         prev_dof_vel = self.dof_vel.copy()
         velocity_command = ((self.actions - self.default_dof_pos) - self.dof_pos) * cfg.control.p_gain
         self.batch.physics_step(velocity_command, cfg.control.decimation)

@@ -453,3 +453,39 @@ def test_scripted_gait_through_env():
     assert list(idx) == [0, 7, 14, 21]
     far = shifted.index(5000).cpu().numpy()
     assert ((far >= shifted.loop[0]) & (far < shifted.loop[1])).all()
+
+
+@pytest.mark.parametrize("name", ["default", "all_terms"])
+def test_cuda_env_tracks_reference_code_golden(name):
+    """The CUDA env, free running, against what the reference's own NightmareV3Env.step code returned on the oracle's physics
+    (tests/golden/reference_env_on_oracle_physics.npz, tools/make_refenv_golden.py): reset / time-out flags, episode lengths
+    and resampled commands exact over the whole sequence; observations and rewards while fp32 drift is still small."""
+    from test_reference_env_golden import scenario_cfg
+    from nightmare_rl_b200.envs.nightmare_v3_env import NightmareV3Env
+    g = np.load(os.path.join(ROOT, "tests", "golden", "reference_env_on_oracle_physics.npz"))
+    acts, ep0 = g[f"{name}.actions"], g[f"{name}.ep0"]
+    T, n = acts.shape[:2]
+    cfg = scenario_cfg(name, n)
+    cfg.env.model_path = NMB
+    cfg.viewer.render = cfg.viewer.record_states = False
+    env = NightmareV3Env(cfg, seed=int(g["seed"]))
+    env.reset_idx(np.arange(n))
+    env.episode_length_buf = torch.from_numpy(ep0.astype(np.int64))          # rebinding, like rsl_rl does (train.py:54)
+    worst_obs = worst_rew = 0.0
+    flag_diff = 0
+    for t in range(T):
+        obs, _, rew, done, extras = env.step(torch.from_numpy(acts[t]))
+        d = done.cpu().numpy()
+        flag_diff += int((d != g[f"{name}.done"][t]).sum())
+        same = d == g[f"{name}.done"][t]
+        assert np.array_equal(env.time_out_buf.cpu().numpy()[same].astype(bool), g[f"{name}.time_out"][t][same])
+        if flag_diff == 0:
+            assert np.array_equal(env.episode_length_buf.cpu().numpy(), g[f"{name}.ep_len"][t])
+            assert np.abs(env.commands.cpu().numpy() - g[f"{name}.commands"][t]).max() < 1e-6
+            if t < 25:
+                worst_obs = max(worst_obs, float(np.abs(obs.cpu().numpy() - g[f"{name}.obs"][t]).max()))
+                worst_rew = max(worst_rew, float(np.abs(rew.cpu().numpy() - g[f"{name}.rew"][t]).max()))
+    print(f"\n[cuda vs reference env code, {name}] {T} free-running steps x {n} envs: flag differences {flag_diff}; first 25 steps worst |obs| "
+          f"{worst_obs:.1e} |rew| {worst_rew:.1e}")
+    assert flag_diff == 0
+    assert worst_obs < 5e-3 and worst_rew < 2e-3
