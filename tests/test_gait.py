@@ -22,9 +22,6 @@ def _yaw(q):
 @pytest.mark.skipif(not os.path.isdir("/root/reference/nikengine"), reason="reference tree not present (GPU box)")
 def test_fixture_reproduces_from_reference_engine(tmp_path):
     """The fixture is the reference gait engine's output, bit for bit (generator: tools/make_gait_golden.py)."""
-    code = ("import sys, runpy, numpy as np; sys.argv=['x','/root/reference'];"
-            f"import os; m=runpy.run_path(r'{ROOT}/tools/make_gait_golden.py');"
-            f"m['ROOT']; ")
     # run the generator into a scratch root so the committed file is not touched
     scratch = tmp_path / "tests" / "golden"
     scratch.mkdir(parents=True)

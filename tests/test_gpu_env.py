@@ -455,7 +455,7 @@ def test_scripted_gait_through_env():
     assert ((far >= shifted.loop[0]) & (far < shifted.loop[1])).all()
 
 
-@pytest.mark.parametrize("name", ["default", "all_terms"])
+@pytest.mark.parametrize("name", ["default", "all_terms", "noise"])
 def test_cuda_env_tracks_reference_code_golden(name):
     """The CUDA env, free running, against what the reference's own NightmareV3Env.step code returned on the oracle's physics
     (tests/golden/reference_env_on_oracle_physics.npz, tools/make_refenv_golden.py): reset / time-out flags, episode lengths

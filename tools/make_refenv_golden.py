@@ -125,8 +125,18 @@ class PhiloxCommands:
         self.phase, self.ids, self.draw = 0, None, 0
 
     def rand(self, *shape):
-        assert self.ids is not None and shape == (len(self.ids),), f"unexpected np.random.rand{shape} from the reference env"
         step = int(self.env.common_step_counter)
+        if self.ids is None and shape == (self.env.num_envs, 66):
+            # observation noise (:300-301): uniform k of env i is word k % 4 of the Philox block with counter word 2 + k // 4
+            out = np.zeros(shape)
+            for i in range(shape[0]):
+                for blk in range(17):
+                    r = O.philox4x32(self.seed & 0xFFFFFFFF, i, step & 0xFFFFFFFF, step >> 32, 2 + blk, self.seed >> 32)
+                    for q in range(4):
+                        if 4 * blk + q < 66:
+                            out[i, 4 * blk + q] = float(r[q] >> 8) / 16777216.0
+            return out
+        assert self.ids is not None and shape == (len(self.ids),), f"unexpected np.random.rand{shape} from the reference env"
         out = np.zeros(len(self.ids))
         for k, i in enumerate(self.ids):
             r = O.philox4x32(self.seed & 0xFFFFFFFF, int(i), step & 0xFFFFFFFF, step >> 32, self.phase, self.seed >> 32)
@@ -237,6 +247,10 @@ def scenarios():
         s.lin_vel_z, s.ang_vel_xy, s.base_height, s.torques, s.dof_vel, s.feet_air_time, s.stand_still, s.feet_contact_forces = (
             -2.0, -0.05, -1.0, -1e-5, -1e-4, 1.0, -0.5, -0.01)
     yield "all_terms", n, a[:50], ep0, strict
+
+    def noisy(cfg):                                             # observation noise with the reference's 12-DoF slice boundaries (quirk Q8)
+        cfg.noise.add_noise = True
+    yield "noise", n, a[:20], ep0, noisy
 
 
 def main():
