@@ -482,9 +482,13 @@ extern "C" int nm_ppo_grad(const nm_mlp_shape* actor, const nm_mlp_shape* critic
   }
   const int pa = na.src_w[na.nl - 1] + na.kin[na.nl - 1] * na.kout[na.nl - 1] + na.kout[na.nl - 1];
   const int pc = nc.src_w[nc.nl - 1] + nc.kin[nc.nl - 1] * nc.kout[nc.nl - 1] + nc.kout[nc.nl - 1];
-  if (cudaMemsetAsync(a->g_actor, 0, sizeof(float) * pa, st) != cudaSuccess || cudaMemsetAsync(a->g_critic, 0, sizeof(float) * pc, st) != cudaSuccess ||
-      cudaMemsetAsync(a->g_std, 0, sizeof(float) * a->act_dim, st) != cudaSuccess || cudaMemsetAsync(a->out, 0, sizeof(float) * 4, st) != cudaSuccess)
+  if (a->g_std + a->act_dim == a->g_actor && a->g_actor + pa == a->g_critic && a->g_critic + pc == a->out) {
+    // std | actor | critic | sums in one buffer (how the Python side lays them out): one memset node instead of four
+    if (cudaMemsetAsync(a->g_std, 0, sizeof(float) * (a->act_dim + pa + pc + 4), st) != cudaSuccess) return nm_fail(NM_ERR_CUDA, "nm_ppo_grad: memset failed");
+  } else if (cudaMemsetAsync(a->g_actor, 0, sizeof(float) * pa, st) != cudaSuccess || cudaMemsetAsync(a->g_critic, 0, sizeof(float) * pc, st) != cudaSuccess ||
+             cudaMemsetAsync(a->g_std, 0, sizeof(float) * a->act_dim, st) != cudaSuccess || cudaMemsetAsync(a->out, 0, sizeof(float) * 4, st) != cudaSuccess) {
     return nm_fail(NM_ERR_CUDA, "nm_ppo_grad: memset failed");
+  }
   P.a = *a;
   const int batches = (a->n + PG_ROWS - 1) / PG_ROWS;
   // one CTA per SM; the actor (wider output layer, Gaussian head) gets the larger share of the SMs

@@ -189,7 +189,9 @@ class FusedPPOGrad:
             raise _lib.NightmareLibError("nm_ppo_grad: unexpected parameter set (std + Linear layers in float32 expected)")
         total = sum(p.numel() for p in listed)
         self.flat = torch.empty(total, device=device)
-        self.flat_grad = torch.zeros(total, device=device)
+        # gradient vector and the kernel's 4 loss sums in ONE buffer: a multi-GPU job averages both with a single all-reduce
+        self.ext = torch.zeros(total + 4, device=device)
+        self.flat_grad = self.ext[:total]
         self.offsets = []
         off = 0
         with torch.no_grad():
@@ -201,7 +203,7 @@ class FusedPPOGrad:
                     p.data = self.flat[off:off + n].view_as(p)
                     p.grad = self.flat_grad[off:off + n].view_as(p)
                     off += n
-        self.out = torch.zeros(4, device=device)
+        self.out = self.ext[total:]
         self.device = device
         self._keep = None
 

@@ -367,16 +367,19 @@ class PPO:
             out = fg(n, b, obs, cobs, st.actions.flatten(0, 1), st.actions_log_prob.flatten(0, 1), st.mu.flatten(0, 1), st.sigma.flatten(0, 1),
                      st.advantages.flatten(0, 1), st.returns.flatten(0, 1), st.values.flatten(0, 1),
                      self.clip_param, self.value_loss_coef, self.entropy_coef, self.use_clipped_value_loss)
+            if self.world > 1:                               # ONE NCCL all-reduce (captured with the rest) averages the flat gradient
+                dist.all_reduce(fg.ext)                      # and the loss / KL sums, so every rank takes the same learning-rate decision
+                fg.ext.div_(self.world)
             sums = out / n
             s_loss, v_loss, kl_mean = sums[0], sums[1], sums[2]
         else:
             loss, v_loss, s_loss, kl_mean = self._minibatch_loss(
                 obs[b], cobs[b], st.actions.flatten(0, 1)[b], st.values.flatten(0, 1)[b], st.advantages.flatten(0, 1)[b],
                 st.returns.flatten(0, 1)[b], st.actions_log_prob.flatten(0, 1)[b], st.mu.flatten(0, 1)[b], st.sigma.flatten(0, 1)[b])
-        if self.world > 1:                                   # every rank takes the same learning-rate decision
-            kl_mean = kl_mean.clone()
-            dist.all_reduce(kl_mean)
-            kl_mean = kl_mean / self.world
+            if self.world > 1:                               # every rank takes the same learning-rate decision
+                kl_mean = kl_mean.clone()
+                dist.all_reduce(kl_mean)
+                kl_mean = kl_mean / self.world
         if self.desired_kl is not None and self.schedule == "adaptive":
             lr = self._lr_t
             down = torch.clamp(lr / 1.5, min=1e-5)
@@ -386,9 +389,6 @@ class PPO:
             lr.copy_(new_lr)
         if fg is not None:
             g = fg.flat_grad
-            if self.world > 1:                               # NCCL all-reduce of the flat gradient, captured with the rest
-                dist.all_reduce(g)
-                g.div_(self.world)
             # clip_grad_norm_ on the flat vector: same 2-norm, same 1e-6 guard, same clamp of the coefficient to 1
             g.mul_(torch.clamp(self.max_grad_norm / (torch.linalg.vector_norm(g) + 1e-6), max=1.0))
         else:

@@ -489,3 +489,14 @@ def test_cuda_env_tracks_reference_code_golden(name):
           f"{worst_obs:.1e} |rew| {worst_rew:.1e}")
     assert flag_diff == 0
     assert worst_obs < 5e-3 and worst_rew < 2e-3
+
+
+def test_simple_test_script_runs():
+    """The reference's throughput script under its own name and flags (simple_test.py), on the GPU."""
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "simple_test.py"), "-e", "512", "-s", "20", "-d", "4", "-t", "3"],
+                         capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    last = out.stdout.strip().splitlines()[-1].split()
+    assert last[1:] == ["steps", "per", "second"] and float(last[0]) > 1e5
