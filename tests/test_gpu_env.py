@@ -500,3 +500,4 @@ def test_simple_test_script_runs():
     assert out.returncode == 0, out.stderr[-2000:]
     last = out.stdout.strip().splitlines()[-1].split()
     assert last[1:] == ["steps", "per", "second"] and float(last[0]) > 1e5
+

@@ -128,3 +128,29 @@ def test_get_load_path(tmp_path):
     assert get_load_path(str(tmp_path), checkpoint=100).endswith("model_100.pt")
     with pytest.raises(ValueError):
         get_load_path(str(tmp_path / "void"))
+
+
+def test_second_model_through_compiler_and_loader():
+    """BASELINE configs[3] names anymal_c as the model that exercises the generic compiler / loader.  Its MJCF (includes,
+    nested default classes, explicit inertials, primitive collision geoms, position actuators; reference
+    models/anymal_c/anymal_c.xml) compiles to models/anymal_c/anymal_c.nmb in the same container format as the hexapod's.
+    Its STEP is not implemented (the kernels have no Newton solver / elliptic cones / condim 6 / joint limits /
+    frictionloss): nm_model_from_buffer must say so instead of simulating something else."""
+    from conftest import ROOT
+    from nightmare_rl_b200 import _lib, mjcf
+    path = os.path.join(ROOT, "models", "anymal_c", "anymal_c.nmb")
+    cm = mjcf.CompiledModel.load(path)
+    assert (cm.nq, cm.nv, cm.nu, cm.nbody, cm.ngeom) == (19, 18, 12, 14, 45)
+    assert cm.names["body"][:5] == ["world", "base", "LF_HIP", "LF_THIGH", "LF_SHANK"]
+    assert abs(cm.arrays["body_mass"].sum() - 44.96518) < 1e-6
+    assert np.bincount(cm.arrays["geom_type"], minlength=8).tolist() == [1, 0, 4, 0, 0, 29, 11, 0]      # plane, 4 foot spheres, cylinders, boxes
+    assert abs(float(cm.arrays["opt_real"][0]) - 0.002) < 1e-12
+    # the C ABI validates a model against what the step kernels implement when it builds the device image: refused, with the reason
+    with pytest.raises(_lib.NightmareLibError) as ei:
+        _lib.Model(cm.to_bytes())
+    assert 'only solver="PGS" is implemented' in str(ei.value)
+    if os.path.isdir("/root/reference/models/anymal_c"):         # the committed file is what the compiler produces from the reference MJCF
+        fresh = mjcf.compile_mjcf("/root/reference/models/anymal_c/scene.xml")
+        assert set(fresh.arrays) == set(cm.arrays)
+        for k, v in fresh.arrays.items():
+            assert np.array_equal(v, cm.arrays[k]), k
