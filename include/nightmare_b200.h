@@ -218,6 +218,18 @@ typedef struct {
 } nm_ppo_grad_args;
 int  nm_ppo_grad(const nm_mlp_shape* actor, const nm_mlp_shape* critic, const nm_ppo_grad_args* args, nm_stream stream);
 
+/* ---- optimiser tail of one PPO mini-batch (≙ rsl_rl v1.0.2 PPO.update after loss.backward(), train.py:54): KL-adaptive
+ * learning rate (x / 1.5 on KL outside [desired/2, 2*desired], bounds [1e-5, 1e-2]), clip_grad_norm_ and torch.optim.Adam's
+ * update, over flat DEVICE float32 vectors, in one single-CTA launch.  sums = out[] of nm_ppo_grad (sum surrogate, sum value
+ * loss, sum KL), n_samples its n.  step and lr are DEVICE scalars (in/out); loss_acc[0..1] += mean value loss, mean surrogate
+ * (may be NULL).  grads are left clipped. */
+typedef struct {
+  int32_t n_params, n_samples, adaptive, pad0;
+  float desired_kl, max_grad_norm, beta1, beta2, eps, pad1, pad2, pad3;
+  float* params; float* grads; float* exp_avg; float* exp_avg_sq; float* step; float* lr; const float* sums; float* loss_acc;
+} nm_ppo_adam_args;
+int  nm_ppo_adam(const nm_ppo_adam_args* args, nm_stream stream);
+
 /* ---- GAE(lambda) over a stored rollout (≙ rsl_rl v1.0.2 RolloutStorage.compute_returns, train.py:54).  All pointers
  * DEVICE; rewards / values / returns / advantages float32 [T, n], dones uint8 [T, n], last_values float32 [n].
  * Writes returns and the RAW advantages (returns - values) and moments[0..1] = their sum and sum of squares (fp64),

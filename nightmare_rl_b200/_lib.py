@@ -63,6 +63,7 @@ def _load() -> ctypes.CDLL:
     L.nm_rollout_store.argtypes = [_vp, _vp]
     L.nm_ppo_head.argtypes = [_vp, _vp]
     L.nm_ppo_grad.argtypes = [_vp, _vp, _vp, _vp]
+    L.nm_ppo_adam.argtypes = [_vp, _vp]
     L.nm_gae.argtypes = [ctypes.c_int, ctypes.c_int, _vp, _vp, _vp, _vp, ctypes.c_float, ctypes.c_float, _vp, _vp, _vp, _vp]
     L.nm_policy_tc5_create.argtypes = [_vp, _vp, _ci, ctypes.POINTER(_vp)]
     L.nm_policy_tc5_destroy.argtypes = [_vp]
@@ -78,7 +79,7 @@ EXPORTS = ("nm_last_error", "nm_model_load", "nm_model_from_buffer", "nm_model_d
            "nm_batch_set_domain_randomization", "nm_step",
            "nm_physics_step", "nm_reset_idx", "nm_step_host", "nm_batch_launches", "nm_measure_fp32_peak",
            "nm_policy_create", "nm_policy_destroy", "nm_policy_param_count", "nm_policy_load_weights", "nm_policy_act",
-           "nm_policy_act_store", "nm_policy_launches", "nm_rollout_store", "nm_ppo_head", "nm_ppo_grad", "nm_gae",
+           "nm_policy_act_store", "nm_policy_launches", "nm_rollout_store", "nm_ppo_head", "nm_ppo_grad", "nm_gae", "nm_ppo_adam",
            "nm_policy_tc5_create", "nm_policy_tc5_destroy", "nm_policy_tc5_load_weights", "nm_policy_tc5_act")
 
 

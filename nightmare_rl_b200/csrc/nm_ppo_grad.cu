@@ -545,3 +545,59 @@ extern "C" int nm_gae(int T, int n, const float* rewards, const uint8_t* dones, 
   if (cudaGetLastError() != cudaSuccess) return nm_fail(NM_ERR_CUDA, "nm_gae: launch failed");
   return NM_OK;
 }
+
+// ================================================================================================ optimiser tail
+// Everything rsl_rl v1.0.2 PPO.update does per mini-batch AFTER loss.backward() (train.py:54 -> PPO.update): the KL-adaptive
+// learning rate (desired_kl rule, bounds [1e-5, 1e-2], envs/nightmare_v3_config.py:125-129), clip_grad_norm_(max_grad_norm)
+// and torch.optim.Adam's step -- for the 15 k parameters of this policy ~20 tiny PyTorch kernels, here ONE single-CTA launch
+// over the flat parameter / gradient / moment vectors.  Same arithmetic as torch: bias-corrected first and second
+// moments, denom = sqrt(v) / sqrt(1 - beta2^t) + eps, p -= lr / (1 - beta1^t) * m / denom.
+__global__ void __launch_bounds__(1024, 1) nm_ppo_adam_kernel(const nm_ppo_adam_args A) {
+  __shared__ double s_part[32];
+  __shared__ float s_coef, s_lr, s_bc1, s_bc2s;
+  const int tid = threadIdx.x;
+  double ss = 0.0;
+  for (int i = tid; i < A.n_params; i += blockDim.x) { const float g = A.grads[i]; ss += (double)g * (double)g; }
+  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  if ((tid & 31) == 0) s_part[tid >> 5] = ss;
+  __syncthreads();
+  if (tid == 0) {
+    double tot = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); w++) tot += s_part[w];
+    const float norm = (float)sqrt(tot);
+    s_coef = fminf(A.max_grad_norm / (norm + 1e-6f), 1.f);
+    float lr = *A.lr;
+    const float inv_n = 1.f / (float)A.n_samples;
+    if (A.adaptive) {
+      const float kl = A.sums[2] * inv_n;
+      if (kl > A.desired_kl * 2.f) lr = fmaxf(lr / 1.5f, 1e-5f);
+      else if (kl < A.desired_kl * 0.5f && kl > 0.f) lr = fminf(lr * 1.5f, 1e-2f);
+      *A.lr = lr;
+    }
+    const float t = *A.step + 1.f;
+    *A.step = t;
+    s_lr = lr;
+    s_bc1 = 1.f - powf(A.beta1, t);
+    s_bc2s = sqrtf(1.f - powf(A.beta2, t));
+    if (A.loss_acc) { A.loss_acc[0] += A.sums[1] * inv_n; A.loss_acc[1] += A.sums[0] * inv_n; }
+  }
+  __syncthreads();
+  const float coef = s_coef, step_size = s_lr / s_bc1, bc2s = s_bc2s;
+  for (int i = tid; i < A.n_params; i += blockDim.x) {
+    const float g = A.grads[i] * coef;
+    const float m = A.exp_avg[i] + (g - A.exp_avg[i]) * (1.f - A.beta1);          // torch: exp_avg.lerp_(grad, 1 - beta1)
+    const float v = A.exp_avg_sq[i] * A.beta2 + (1.f - A.beta2) * g * g;          // torch: mul_(beta2).addcmul_(grad, grad, 1 - beta2)
+    A.exp_avg[i] = m;
+    A.exp_avg_sq[i] = v;
+    A.grads[i] = g;
+    A.params[i] -= step_size * (m / (sqrtf(v) / bc2s + A.eps));
+  }
+}
+
+extern "C" int nm_ppo_adam(const nm_ppo_adam_args* a, nm_stream stream) {
+  if (!a || a->n_params <= 0 || a->n_samples <= 0 || !a->params || !a->grads || !a->exp_avg || !a->exp_avg_sq || !a->step || !a->lr || !a->sums)
+    return nm_fail(NM_ERR_ARG, "nm_ppo_adam: bad argument");
+  nm_ppo_adam_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(*a);
+  if (cudaGetLastError() != cudaSuccess) return nm_fail(NM_ERR_CUDA, "nm_ppo_adam: launch failed");
+  return NM_OK;
+}

@@ -164,6 +164,13 @@ class PPOGradArgs(ctypes.Structure):
                                                   "actor_params", "critic_params", "std", "g_actor", "g_critic", "g_std", "out")])
 
 
+class PPOAdamArgs(ctypes.Structure):
+    """``nm_ppo_adam_args`` of include/nightmare_b200.h."""
+    _fields_ = ([("n_params", ctypes.c_int32), ("n_samples", ctypes.c_int32), ("adaptive", ctypes.c_int32), ("pad0", ctypes.c_int32)]
+                + [(k, ctypes.c_float) for k in ("desired_kl", "max_grad_norm", "beta1", "beta2", "eps", "pad1", "pad2", "pad3")]
+                + [(k, ctypes.c_void_p) for k in ("params", "grads", "exp_avg", "exp_avg_sq", "step", "lr", "sums", "loss_acc")])
+
+
 class FusedPPOGrad:
     """Gradient of the PPO mini-batch loss for every parameter of an ``ActorCritic`` in one kernel launch (nm_ppo_grad).
 
@@ -193,12 +200,19 @@ class FusedPPOGrad:
         self.ext = torch.zeros(total + 4, device=device)
         self.flat_grad = self.ext[:total]
         self.offsets = []
+        self.param_slices = []                        # (parameter, offset, numel) in flat order
+        # Adam moments and step count, flat like the parameters; the torch optimiser's per-parameter state entries are views
+        # of them (seat_optimizer_state), so optimizer.state_dict() / load_state_dict() keep rsl_rl's checkpoint format
+        self.exp_avg = torch.zeros(total, device=device)
+        self.exp_avg_sq = torch.zeros(total, device=device)
+        self.step = torch.zeros((), device=device)
         off = 0
         with torch.no_grad():
             for grp in groups:
                 self.offsets.append(off)
                 for p in grp:
                     n = p.numel()
+                    self.param_slices.append((p, off, n))
                     self.flat[off:off + n].copy_(p.detach().reshape(-1))
                     p.data = self.flat[off:off + n].view_as(p)
                     p.grad = self.flat_grad[off:off + n].view_as(p)
@@ -231,3 +245,27 @@ class FusedPPOGrad:
         _lib.check(_lib.lib.nm_ppo_grad(ctypes.byref(self.shape_a), ctypes.byref(self.shape_c), ctypes.byref(a),
                                         ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)))
         return self.out
+
+    def seat_optimizer_state(self, optimizer):
+        """Make ``optimizer.state[p]`` = views of the flat moment vectors (and one shared step counter).  Values already in the
+        optimiser's state -- i.e. just loaded from a checkpoint -- are copied into the flat vectors first."""
+        with torch.no_grad():
+            for p, off, n in self.param_slices:
+                st = optimizer.state[p]
+                m, v = self.exp_avg[off:off + n].view_as(p), self.exp_avg_sq[off:off + n].view_as(p)
+                if "exp_avg" in st and st["exp_avg"].data_ptr() != m.data_ptr():
+                    m.copy_(st["exp_avg"].to(self.device))
+                    v.copy_(st["exp_avg_sq"].to(self.device))
+                    self.step.copy_(torch.as_tensor(st["step"], dtype=torch.float32).to(self.device))
+                st["exp_avg"], st["exp_avg_sq"], st["step"] = m, v, self.step
+
+    def adam(self, n_samples, lr, loss_acc, adaptive, desired_kl, max_grad_norm, beta1, beta2, eps):
+        """KL-adaptive learning rate + gradient-norm clip + Adam step on the flat vectors, one launch (nm_ppo_adam)."""
+        a = PPOAdamArgs()
+        a.n_params, a.n_samples, a.adaptive = self.flat.numel(), int(n_samples), 1 if adaptive else 0
+        a.desired_kl, a.max_grad_norm = float(desired_kl or 0.0), float(max_grad_norm)
+        a.beta1, a.beta2, a.eps = float(beta1), float(beta2), float(eps)
+        a.params, a.grads, a.exp_avg, a.exp_avg_sq = self.flat.data_ptr(), self.flat_grad.data_ptr(), self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr()
+        a.step, a.lr, a.sums = self.step.data_ptr(), lr.data_ptr(), self.out.data_ptr()
+        a.loss_acc = loss_acc.data_ptr() if loss_acc is not None else None
+        _lib.check(_lib.lib.nm_ppo_adam(ctypes.byref(a), ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)))

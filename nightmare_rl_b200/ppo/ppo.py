@@ -75,8 +75,15 @@ class PPO:
                     self.fused_grad = FusedPPOGrad(self.actor_critic, self.device)
                 except Exception:                              # unsupported network: autograd path
                     self.fused_grad = None
-            self.optimizer = optim.Adam(self.actor_critic.parameters(), lr=self._lr_t, capturable=True,
-                                        **({"fused": True} if self.fused_grad is not None else {"foreach": True}))
+            self.optimizer = optim.Adam(self.actor_critic.parameters(), lr=self._lr_t, capturable=True, foreach=True)
+            if self.fused_grad is not None:
+                # the update itself is nm_ppo_adam on the flat vectors; the torch optimiser object stays as the holder of
+                # hyper-parameters and of the (re-seated) state, so checkpoints keep rsl_rl's optimizer_state_dict layout
+                g0 = self.optimizer.param_groups[0]
+                if g0.get("amsgrad") or g0.get("weight_decay") or g0.get("maximize"):
+                    self.fused_grad = None
+                else:
+                    self.fused_grad.seat_optimizer_state(self.optimizer)
 
     def init_storage(self, num_envs, num_transitions_per_env, actor_obs_shape, critic_obs_shape, action_shape):
         self.storage = RolloutStorage(num_envs, num_transitions_per_env, actor_obs_shape, critic_obs_shape, action_shape, self.device)
@@ -110,6 +117,8 @@ class PPO:
             for stt in self.optimizer.state.values():
                 if "step" in stt and torch.is_tensor(stt["step"]):
                     stt["step"] = stt["step"].to(self.device)
+            if self.fused_grad is not None:
+                self.fused_grad.seat_optimizer_state(self.optimizer)
             self._graph = None
 
     # ------------------------------------------------------------------ rollout
@@ -370,8 +379,6 @@ class PPO:
             if self.world > 1:                               # ONE NCCL all-reduce (captured with the rest) averages the flat gradient
                 dist.all_reduce(fg.ext)                      # and the loss / KL sums, so every rank takes the same learning-rate decision
                 fg.ext.div_(self.world)
-            sums = out / n
-            s_loss, v_loss, kl_mean = sums[0], sums[1], sums[2]
         else:
             loss, v_loss, s_loss, kl_mean = self._minibatch_loss(
                 obs[b], cobs[b], st.actions.flatten(0, 1)[b], st.values.flatten(0, 1)[b], st.advantages.flatten(0, 1)[b],
@@ -380,6 +387,12 @@ class PPO:
                 kl_mean = kl_mean.clone()
                 dist.all_reduce(kl_mean)
                 kl_mean = kl_mean / self.world
+        if fg is not None:
+            # KL-adaptive learning rate, clip_grad_norm_ and the Adam step in one launch on the flat vectors
+            g0 = self.optimizer.param_groups[0]
+            fg.adam(n, self._lr_t, self._g_losses, self.desired_kl is not None and self.schedule == "adaptive", self.desired_kl,
+                    self.max_grad_norm, g0["betas"][0], g0["betas"][1], g0["eps"])
+            return
         if self.desired_kl is not None and self.schedule == "adaptive":
             lr = self._lr_t
             down = torch.clamp(lr / 1.5, min=1e-5)
@@ -387,16 +400,11 @@ class PPO:
             new_lr = torch.where(kl_mean > self.desired_kl * 2.0, down,
                                  torch.where((kl_mean < self.desired_kl / 2.0) & (kl_mean > 0.0), up, lr))
             lr.copy_(new_lr)
-        if fg is not None:
-            g = fg.flat_grad
-            # clip_grad_norm_ on the flat vector: same 2-norm, same 1e-6 guard, same clamp of the coefficient to 1
-            g.mul_(torch.clamp(self.max_grad_norm / (torch.linalg.vector_norm(g) + 1e-6), max=1.0))
-        else:
-            self.optimizer.zero_grad(set_to_none=False)
-            self._backward(loss)
-            if self.world > 1:
-                self._allreduce_grads()
-            nn.utils.clip_grad_norm_(self.actor_critic.parameters(), self.max_grad_norm, foreach=True)
+        self.optimizer.zero_grad(set_to_none=False)
+        self._backward(loss)
+        if self.world > 1:
+            self._allreduce_grads()
+        nn.utils.clip_grad_norm_(self.actor_critic.parameters(), self.max_grad_norm, foreach=True)
         self.optimizer.step()
         self._g_vloss += v_loss
         self._g_sloss += s_loss
@@ -407,8 +415,8 @@ class PPO:
         mb = batch // self.num_mini_batches
         if self._graph is None:
             self._g_idx = torch.zeros(mb, dtype=torch.int64, device=self.device)
-            self._g_vloss = torch.zeros((), device=self.device)
-            self._g_sloss = torch.zeros((), device=self.device)
+            self._g_losses = torch.zeros(2, device=self.device)           # [value loss, surrogate loss] accumulated over the mini-batches
+            self._g_vloss, self._g_sloss = self._g_losses[0], self._g_losses[1]
             # gradients must exist (and keep their addresses) before capture
             for p in self.actor_critic.parameters():
                 if p.grad is None:
