@@ -233,3 +233,37 @@ def test_threads_do_not_change_results(oracle_model):
         out.append(b.get_state())
     for a, c in zip(*out):
         assert np.array_equal(a, c)
+
+
+def test_pgs_converges_to_the_complementarity_solution(compiled_model, tmp_path):
+    """With many sweeps (and no noslip pass) the projected Gauss-Seidel iteration must land on the solution of the contact LCP
+    it is a solver for:  f >= 0,  (A + R) f + b >= 0,  f . ((A + R) f + b) = 0   (pyramidal rows, Appendix A.6).
+    A wrong projection, update order or residual in the sweep would stall somewhere else."""
+    cm = mjcf.CompiledModel(dict((k, v.copy()) for k, v in compiled_model.arrays.items()), compiled_model.names)
+    cm.arrays["opt_int"][3] = 400            # iterations
+    cm.arrays["opt_int"][4] = 0              # noslip_iterations
+    p = str(tmp_path / "pgs400.nmb")
+    cm.save(p)
+    om = O.OracleModel(p)
+    rng = np.random.default_rng(4)
+    checked = 0
+    for trial in range(6):
+        b = O.OracleBatch(om, 1)
+        q, v, w = b.get_state()
+        q[0, 7:] += rng.uniform(-0.3, 0.3, 18)
+        q[0, 2] = rng.uniform(0.03, 0.12)
+        b.set_state(q, v, w)
+        for t in range(40):
+            b.physics_step(rng.uniform(-8, 8, (1, 18)) if t % 5 == 0 else None, 1)
+            ne = int(b.get(0, "nefc")[0])
+            if ne == 0:
+                continue
+            AR = b.get(0, "efc_AR").reshape(ne, ne)
+            bb, f = b.get(0, "efc_b"), b.get(0, "efc_force")
+            r = AR @ f + bb
+            scale = max(1.0, np.abs(bb).max())
+            assert (f >= 0).all()
+            assert r.min() > -1e-4 * scale, (trial, t, r.min())          # the sweeps stop on the cost-improvement tolerance (1e-8, scaled): residual ~ its square root
+            assert np.abs(f * r).max() < 1e-4 * scale * max(1.0, f.max()), (trial, t)
+            checked += 1
+    assert checked > 100
