@@ -294,6 +294,48 @@ def test_simple_test_variant_timestep_and_decimation(tmp_path):
     assert gq[:, 2].max() < 0.03 and np.isfinite(gq).all()              # they have landed (released at 0.15 m) and lie on the hull
 
 
+@pytest.mark.parametrize("theta,along,slides", [(30, np.pi / 4, False), (40, np.pi / 4, True), (40, 0.0, False), (50, 0.0, True)])
+def test_slope_hold_and_slide_matches_oracle(tmp_path, theta, along, slides):
+    """Tilted gravity = a robot lying on a slope (tests/test_oracle_physics.py::test_pyramidal_friction_cone_holds_and_slides):
+    below the pyramidal cone's critical angle (45 deg along a tangent axis, 35.3 deg along the diagonal) it stays, above it
+    slides.  Sustained sliding friction is a regime the other parity tests barely touch; the CUDA step must hold / slide exactly
+    where the oracle does and cover the same distance."""
+    from nightmare_rl_b200 import _lib, mjcf
+    from conftest import NMB
+    G = _common()
+    cm = mjcf.CompiledModel.load(NMB)
+    th = np.radians(theta)
+    cm.arrays["opt_real"][1:4] = [9.81 * np.sin(th) * np.cos(along), 9.81 * np.sin(th) * np.sin(along), -9.81 * np.cos(th)]
+    path = str(tmp_path / "tilt.nmb")
+    cm.save(path)
+    dm, om = _lib.Model(cm.to_bytes()), G.O.OracleModel(path)
+    n = 16
+    rng = np.random.default_rng(2)
+    qpos = np.tile(cm.qpos0, (n, 1))
+    qpos[:, 7:] += rng.uniform(-0.1, 0.1, (n, 18))
+    q32, z = qpos.astype(np.float32), np.zeros((n, 24))
+    ob, gb = G.O.OracleBatch(om, n), G.Batch(dm, n, G.DEV)
+    ob.set_state(q32, z, z)
+    G.push_state(gb, q32, z, z)
+    ctrl = np.zeros((n, 18), dtype=np.float32)
+    ob.physics_step(ctrl, 250, 8)                                       # 2 s, free running on both sides
+    for _ in range(125):
+        gb.physics_step(torch.from_numpy(ctrl), 2)
+    torch.cuda.synchronize()
+    oq, ov, _ = ob.get_state()
+    gq, gv, _ = G.gpu_state(gb)
+    d_o, d_g = np.linalg.norm(oq[:, :2], axis=1), np.linalg.norm(gq[:, :2], axis=1)
+    s_o, s_g = np.linalg.norm(ov[:, :2], axis=1), np.linalg.norm(gv[:, :2], axis=1)
+    print(f"\n[slope {theta} deg, along {along:.2f}] oracle: distance {d_o.mean():.3f} m speed {s_o.mean():.3f} m/s; "
+          f"cuda: distance {d_g.mean():.3f} m speed {s_g.mean():.3f} m/s; worst distance gap {np.abs(d_o - d_g).max():.4f} m")
+    if slides:
+        assert s_o.min() > 1.0 and s_g.min() > 1.0
+        assert (np.abs(d_o - d_g) < 0.03 * d_o + 0.02).all()
+    else:
+        assert s_o.max() < 0.1 and s_g.max() < 0.1
+        assert np.abs(d_o - d_g).max() < 0.02
+
+
 def test_determinism_and_batch_independence():
     """Bitwise reproducible, and env i does not depend on its neighbours or on the batch size (the
     property multi-GPU sharding relies on)."""

@@ -267,3 +267,28 @@ def test_pgs_converges_to_the_complementarity_solution(compiled_model, tmp_path)
             assert np.abs(f * r).max() < 1e-4 * scale * max(1.0, f.max()), (trial, t)
             checked += 1
     assert checked > 100
+
+
+def _tilted(compiled_model, tmp_path, theta_deg, along):
+    """Model variant whose gravity is tilted by theta towards the horizontal direction `along` (a tilted floor, seen from the floor)."""
+    cm = mjcf.CompiledModel(dict((k, v.copy()) for k, v in compiled_model.arrays.items()), compiled_model.names)
+    th = np.radians(theta_deg)
+    cm.arrays["opt_real"][1:4] = [9.81 * np.sin(th) * np.cos(along), 9.81 * np.sin(th) * np.sin(along), -9.81 * np.cos(th)]
+    p = str(tmp_path / f"tilt_{theta_deg}_{along:.2f}.nmb")
+    cm.save(p)
+    return cm, p
+
+
+def test_pyramidal_friction_cone_holds_and_slides(compiled_model, tmp_path):
+    """Friction 1 with MuJoCo's pyramidal cone: |T1| + |T2| <= mu N in the contact frame.  A robot lying on a slope therefore
+    stays put below 45 degrees when the slope runs along a tangent axis (world x on the flat floor) but already slides at
+    atan(1/sqrt 2) = 35.3 degrees along the diagonal -- the anisotropy is a documented property of the pyramidal approximation
+    and a sharp test of how the four edge rows are built and projected."""
+    def speed_after(theta, along):
+        _, p = _tilted(compiled_model, tmp_path, theta, along)
+        b = O.OracleBatch(O.OracleModel(p), 1)
+        b.physics_step(np.zeros((1, 18)), 250)                       # 2 s: drop, settle, then hold or slide
+        _, v, _ = b.get_state()
+        return float(np.linalg.norm(v[0, :2]))
+    assert speed_after(40, 0.0) < 0.1 and speed_after(50, 0.0) > 2.0             # along a tangent axis: threshold 45 degrees
+    assert speed_after(30, np.pi / 4) < 0.1 and speed_after(40, np.pi / 4) > 1.0   # along the diagonal: threshold 35.3 degrees
