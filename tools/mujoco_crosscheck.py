@@ -30,6 +30,9 @@ def main():
     ap.add_argument("--model", required=True, help="mjmodel.xml of the reference (models/nightmare_v3/mjmodel.xml)")
     ap.add_argument("--steps", type=int, default=200, help="env steps (2 substeps each) to replay")
     ap.add_argument("--tol", type=float, default=1e-9)
+    ap.add_argument("--write-golden", action="store_true",
+                    help="also record MuJoCo's own trajectory for the BASELINE configs[0] action sequence as tests/golden/mujoco_config1.npz; "
+                         "tests/test_mujoco_golden.py (skipped while that file is absent) then pins the oracle's physics against it")
     a = ap.parse_args()
     try:
         import mujoco as mj
@@ -117,6 +120,22 @@ def main():
                 worst["qpos after step"] = max(worst.get("qpos after step", 0.0), float(np.abs(q[0] - d.qpos).max()))
                 worst["qvel after step"] = max(worst.get("qvel after step", 0.0), float(np.abs(v[0] - d.qvel).max()))
                 worst["qacc_warmstart"] = max(worst.get("qacc_warmstart", 0.0), float(np.abs(w[0] - d.qacc_warmstart).max()))
+        if a.write_golden:
+            d2 = mj.MjData(m)
+            gen2 = torch.Generator().manual_seed(0)
+            rec = dict(qpos=[], qvel=[], warm=[], ctrl=[], sensordata=[], ncon=[])
+            for t in range(a.steps):
+                act = np.clip(torch.rand(18, generator=gen2).numpy() * 2 - 1, -1, 1) * 0.2
+                c = ((act - default) - d2.qpos[-18:]) * 20.0
+                d2.ctrl[:] = c
+                for sub in range(2):
+                    rec["ctrl"].append(c.copy())
+                    mj.mj_step(m, d2)
+                    rec["qpos"].append(d2.qpos.copy()); rec["qvel"].append(d2.qvel.copy()); rec["warm"].append(d2.qacc_warmstart.copy())
+                    rec["sensordata"].append(d2.sensordata.copy()); rec["ncon"].append(d2.ncon)
+            out = os.path.join(ROOT, "tests", "golden", "mujoco_config1.npz")
+            np.savez_compressed(out, version=mj.__version__, **{k: np.array(v) for k, v in rec.items()})
+            print("wrote", out)
         print(f"per-stage worst deviation over {a.steps} env steps (oracle re-synchronised to MuJoCo before every substep):")
         for k, v in worst.items():
             print(f"  {k:28s} {v:.3e}" if isinstance(v, float) else f"  {k:28s} {v}")
