@@ -1,34 +1,38 @@
-"""Helper functions with the reference's behaviour (``envs/helpers.py``)."""
+"""The two helpers the reference's scripts import from ``envs.helpers`` -- same names, same results."""
 import os
 
 
 def class_to_dict(obj):
-    """Plain-dict view of a config object (reference ``envs/helpers.py:3-18``).
+    """Recursive plain-dict view of a config object (what the reference's ``envs/helpers.py:3-18`` returns).
 
-    Keys come from ``dir(obj)`` and are therefore ALPHABETICAL; the env relies on that for the
-    order in which reward terms are summed."""
+    Public attributes are visited in ``dir()`` order, i.e. ALPHABETICALLY, and the resulting dict keeps that order: the env
+    sums its reward terms in the order of this dict, so the ordering is part of the contract."""
     if not hasattr(obj, "__dict__"):
-        return obj
-    out = {}
-    for key in dir(obj):
-        if key.startswith("_"):
-            continue
-        value = getattr(obj, key)
-        out[key] = [class_to_dict(v) for v in value] if isinstance(value, list) else class_to_dict(value)
-    return out
+        return obj                                           # a leaf: number, string, None, ...
+
+    def view(value):
+        return [class_to_dict(item) for item in value] if isinstance(value, list) else class_to_dict(value)
+
+    return {name: view(getattr(obj, name)) for name in dir(obj) if not name.startswith("_")}
+
+
+def _zero_padded(name, width=15):
+    return name.rjust(width, "0")                            # "model_50.pt" < "model_100.pt" once both are padded
 
 
 def get_load_path(root, load_run=-1, checkpoint=-1):
-    """Newest run directory / highest-numbered ``model_*.pt`` (reference ``envs/helpers.py:20-42``)."""
+    """``<root>/<run>/<model file>`` to resume from (reference ``envs/helpers.py:20-42``): ``load_run == -1`` picks the
+    lexicographically last run directory (they are named by date) and ignores ``exported``; ``checkpoint == -1`` the
+    highest-numbered ``model_*.pt``.  An unreadable or empty ``root`` raises ``ValueError("No runs in this directory: ...")``
+    even when an explicit ``load_run`` is given, as the reference does."""
     try:
-        runs = sorted(r for r in os.listdir(root) if r != "exported")
-        newest = os.path.join(root, runs[-1])
+        candidates = [entry for entry in os.listdir(root) if entry != "exported"]
+        candidates.sort()
+        latest = candidates[-1]
     except Exception as exc:
         raise ValueError("No runs in this directory: " + root) from exc
-    run_dir = newest if load_run == -1 else os.path.join(root, load_run)
-    if checkpoint == -1:
-        models = sorted((f for f in os.listdir(run_dir) if "model" in f), key=lambda m: "{0:0>15}".format(m))
-        model = models[-1]
-    else:
-        model = "model_{}.pt".format(checkpoint)
-    return os.path.join(run_dir, model)
+    run_dir = os.path.join(root, latest if load_run == -1 else load_run)
+    if checkpoint != -1:
+        return os.path.join(run_dir, "model_{}.pt".format(checkpoint))
+    saved = [entry for entry in os.listdir(run_dir) if "model" in entry]
+    return os.path.join(run_dir, max(saved, key=_zero_padded))
