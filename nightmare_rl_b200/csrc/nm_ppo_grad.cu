@@ -552,12 +552,29 @@ extern "C" int nm_gae(int T, int n, const float* rewards, const uint8_t* dones, 
 // and torch.optim.Adam's step -- for the 15 k parameters of this policy ~20 tiny PyTorch kernels, here ONE single-CTA launch
 // over the flat parameter / gradient / moment vectors.  Same arithmetic as torch: bias-corrected first and second
 // moments, denom = sqrt(v) / sqrt(1 - beta2^t) + eps, p -= lr / (1 - beta1^t) * m / denom.
+#define PA_PER 16            // vector elements per thread held in registers on the fast path (n_params <= 16 * 1024)
+
 __global__ void __launch_bounds__(1024, 1) nm_ppo_adam_kernel(const nm_ppo_adam_args A) {
   __shared__ double s_part[32];
   __shared__ float s_coef, s_lr, s_bc1, s_bc2s;
   const int tid = threadIdx.x;
+  const bool fast = A.n_params <= PA_PER * 1024;
+  // fast path: gradients and parameters live in registers across the norm reduction, loads are issued in batches of 32
+  float g[PA_PER], p[PA_PER];
   double ss = 0.0;
-  for (int i = tid; i < A.n_params; i += blockDim.x) { const float g = A.grads[i]; ss += (double)g * (double)g; }
+  if (fast) {
+#pragma unroll
+    for (int k = 0; k < PA_PER; k++) {
+      const int i = tid + k * 1024;
+      const bool ok = i < A.n_params;
+      g[k] = ok ? A.grads[i] : 0.f;
+      p[k] = ok ? A.params[i] : 0.f;
+    }
+#pragma unroll
+    for (int k = 0; k < PA_PER; k++) ss += (double)g[k] * (double)g[k];
+  } else {
+    for (int i = tid; i < A.n_params; i += blockDim.x) { const float gi = A.grads[i]; ss += (double)gi * (double)gi; }
+  }
   for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
   if ((tid & 31) == 0) s_part[tid >> 5] = ss;
   __syncthreads();
@@ -583,14 +600,40 @@ __global__ void __launch_bounds__(1024, 1) nm_ppo_adam_kernel(const nm_ppo_adam_
   }
   __syncthreads();
   const float coef = s_coef, step_size = s_lr / s_bc1, bc2s = s_bc2s;
-  for (int i = tid; i < A.n_params; i += blockDim.x) {
-    const float g = A.grads[i] * coef;
-    const float m = A.exp_avg[i] + (g - A.exp_avg[i]) * (1.f - A.beta1);          // torch: exp_avg.lerp_(grad, 1 - beta1)
-    const float v = A.exp_avg_sq[i] * A.beta2 + (1.f - A.beta2) * g * g;          // torch: mul_(beta2).addcmul_(grad, grad, 1 - beta2)
-    A.exp_avg[i] = m;
-    A.exp_avg_sq[i] = v;
-    A.grads[i] = g;
-    A.params[i] -= step_size * (m / (sqrtf(v) / bc2s + A.eps));
+  // torch.optim.Adam: exp_avg.lerp_(grad, 1 - beta1); exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1 - beta2);
+  //                   param.addcdiv_(exp_avg, exp_avg_sq.sqrt() / sqrt(1 - beta2^t) + eps, -lr / (1 - beta1^t))
+  if (fast) {
+    float m[PA_PER], v[PA_PER];                              // (64 registers per thread at 1024 threads: the moments come second)
+#pragma unroll
+    for (int k = 0; k < PA_PER; k++) {
+      const int i = tid + k * 1024;
+      const bool ok = i < A.n_params;
+      m[k] = ok ? A.exp_avg[i] : 0.f;
+      v[k] = ok ? A.exp_avg_sq[i] : 0.f;
+    }
+#pragma unroll
+    for (int k = 0; k < PA_PER; k++) {
+      const int i = tid + k * 1024;
+      if (i < A.n_params) {
+        const float gi = g[k] * coef;
+        const float mi = m[k] + (gi - m[k]) * (1.f - A.beta1);
+        const float vi = v[k] * A.beta2 + (1.f - A.beta2) * gi * gi;
+        A.exp_avg[i] = mi;
+        A.exp_avg_sq[i] = vi;
+        A.grads[i] = gi;
+        A.params[i] = p[k] - step_size * (mi / (sqrtf(vi) / bc2s + A.eps));
+      }
+    }
+  } else {
+    for (int i = tid; i < A.n_params; i += blockDim.x) {
+      const float gi = A.grads[i] * coef;
+      const float mi = A.exp_avg[i] + (gi - A.exp_avg[i]) * (1.f - A.beta1);
+      const float vi = A.exp_avg_sq[i] * A.beta2 + (1.f - A.beta2) * gi * gi;
+      A.exp_avg[i] = mi;
+      A.exp_avg_sq[i] = vi;
+      A.grads[i] = gi;
+      A.params[i] -= step_size * (mi / (sqrtf(vi) / bc2s + A.eps));
+    }
   }
 }
 

@@ -26,6 +26,14 @@ for N in ([int(x) for x in sys.argv[1:]] or [4096, 16384]):
         fg(*args)
     e1.record(); torch.cuda.synchronize()
     print(f"N={N}: nm_ppo_grad (n={n}) {e0.elapsed_time(e1) / 20 * 1e3:.0f} us per mini-batch")
+    lr_t, acc = torch.tensor(1e-3, device=dev), torch.zeros(2, device=dev)
+    for _ in range(3):
+        fg.adam(n, lr_t, acc, True, 0.01, 1.0, 0.9, 0.999, 1e-8)
+    torch.cuda.synchronize(); e0.record()
+    for _ in range(20):
+        fg.adam(n, lr_t, acc, True, 0.01, 1.0, 0.9, 0.999, 1e-8)
+    e1.record(); torch.cuda.synchronize()
+    print(f"N={N}: nm_ppo_adam {e0.elapsed_time(e1) / 20 * 1e3:.1f} us per call")
     t0 = time.perf_counter(); alg.compute_returns(torch.zeros(N, 66, device=dev)); torch.cuda.synchronize(); t1 = time.perf_counter()
     st.step = T
     alg.update(); st.step = T
