@@ -23,6 +23,8 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--no-flush", action="store_true", help="do not evict L2 between timed steps")
     ap.add_argument("--settle", type=int, default=40, help="untimed steps so that robots are on the ground")
+    ap.add_argument("--gait", action="store_true", help="drive the robots with the reference's scripted tripod gait (phase-shifted per env, "
+                    "tests/golden/nikengine_gait_targets.npz) instead of N(0,1) actions: walking contacts instead of thrashing")
     a = ap.parse_args()
     dev = torch.device("cuda:0")
     gen = torch.Generator(device=dev).manual_seed(7)
@@ -36,22 +38,32 @@ def main():
         env = NightmareV3Env(cfg, seed=1, device=dev)
         env.reset()
         env.episode_length_buf = torch.randint(0, 1250, (n,), device=dev, generator=gen)
-        acts = torch.randn(8, n, 18, device=dev, generator=gen)
+        if a.gait:
+            from nightmare_rl_b200.envs.scripted_gait import ScriptedGait
+            g = ScriptedGait(os.path.join(ROOT, "tests", "golden", "nikengine_gait_targets.npz"), n, dev, phase_shift=3)
+            a.settle = max(a.settle, 330)                        # past the engine's wake-up: everybody is walking when timing starts
+            seq = [g.actions().contiguous() for _ in range(a.settle + a.steps)]
+            acts = None
+        else:
+            acts = torch.randn(8, n, 18, device=dev, generator=gen)
+            seq = [acts[i % 8] for i in range(a.settle + a.steps)]
         for i in range(a.settle):
-            env._batch.step(acts[i % 8], 10 + i)
+            env._batch.step(seq[i], 10 + i)
         torch.cuda.synchronize()
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
         for i in range(a.steps):
             if not a.no_flush:
                 flush.zero_()
             ev[i][0].record()
-            env._batch.step(acts[i % 8], 1000 + i)
+            env._batch.step(seq[a.settle + i], 1000 + i)
             ev[i][1].record()
         torch.cuda.synchronize()
         ms = sorted(x.elapsed_time(y) for x, y in ev)
         med = ms[len(ms) // 2]
         out.append(f"N={n}: median {med * 1e3:.1f} us/step  {n / med / 1e3:.1f} M env-steps/s (min {ms[0] * 1e3:.1f} us)")
-        del env, acts
+        done_frac = float(env.reset_buf.float().mean())
+        out[-1] += f" resets/step {done_frac:.4f}"
+        del env, acts, seq
         torch.cuda.empty_cache()
     print(os.environ.get("NIGHTMARE_B200_LIB", "default lib"), "|", " | ".join(out))
 
