@@ -501,3 +501,26 @@ def test_simple_test_script_runs():
     last = out.stdout.strip().splitlines()[-1].split()
     assert last[1:] == ["steps", "per", "second"] and float(last[0]) > 1e5
 
+
+
+def test_cuda_reset_tracks_reference_code_golden():
+    """NightmareV3Env.reset() (reset_idx(all) + one zero-action step) and the steps after it against the reference's own code."""
+    from test_reference_env_golden import scenario_cfg
+    from nightmare_rl_b200.envs.nightmare_v3_env import NightmareV3Env
+    g = np.load(os.path.join(ROOT, "tests", "golden", "reference_env_on_oracle_physics.npz"))
+    acts = g["via_reset.actions"]
+    T, n = acts.shape[:2]
+    cfg = scenario_cfg("via_reset", n)
+    cfg.env.model_path = NMB
+    cfg.viewer.render = cfg.viewer.record_states = False
+    env = NightmareV3Env(cfg, seed=int(g["seed"]))
+    obs0, priv0 = env.reset()
+    assert priv0 is None
+    worst = float(np.abs(obs0.cpu().numpy() - g["via_reset.reset_obs"]).max())
+    for t in range(T):
+        obs, _, rew, done, _ = env.step(torch.from_numpy(acts[t]))
+        assert np.array_equal(done.cpu().numpy(), g["via_reset.done"][t])
+        assert np.array_equal(env.episode_length_buf.cpu().numpy(), g["via_reset.ep_len"][t])
+        worst = max(worst, float(np.abs(obs.cpu().numpy() - g["via_reset.obs"][t]).max()), float(np.abs(rew.cpu().numpy() - g["via_reset.rew"][t]).max()))
+    print(f"\n[cuda reset vs reference env code] reset + {T} steps x {n} envs: worst |obs, rew| difference {worst:.1e}")
+    assert worst < 1e-3

@@ -94,3 +94,21 @@ def test_fixture_regenerates_from_reference_tree(tmp_path):
             assert np.allclose(a[k], b[k], rtol=0, atol=1e-6), k
         else:
             assert np.array_equal(a[k], b[k]), k
+
+
+def test_reset_reproduces_reference_code():
+    """`reset()` of the reference = reset_idx(all) followed by one zero-action step whose observations it returns (:392-396);
+    the steps after it see the stale-buffer quirks of a just-reset batch (Q2: first PD law from the buffers of the zero step)."""
+    g = np.load(FIX)
+    acts = g["via_reset.actions"]
+    T, n = acts.shape[:2]
+    om = O.OracleModel(NMB)
+    b = O.OracleBatch(om, n, seed=int(g["seed"]), envcfg=build_envcfg(scenario_cfg("via_reset", n), 0.008))
+    b.env_reset_idx(np.arange(n))
+    obs0 = b.env_step(np.zeros((n, 18), dtype=np.float32))[0]
+    assert np.array_equal(obs0, g["via_reset.reset_obs"])
+    for t in range(T):
+        obs, rew, done, tout, _, _ = b.env_step(acts[t])
+        assert np.array_equal(obs, g["via_reset.obs"][t]) and np.array_equal(rew, g["via_reset.rew"][t])
+        assert np.array_equal(done, g["via_reset.done"][t])
+        assert np.array_equal(b.env_get("ep_len").astype(np.int64), g["via_reset.ep_len"][t])

@@ -173,7 +173,7 @@ def load_reference_env(ref, nmb_path=NMB):
     return mod, cfgmod
 
 
-def run_reference(ref, n, actions, ep0=None, seed=SEED, cfg_edit=None):
+def run_reference(ref, n, actions, ep0=None, seed=SEED, cfg_edit=None, via_reset=False):
     mod, cfgmod = load_reference_env(ref)
     cfg = cfgmod.NightmareV3Config()
     cfg.env.num_envs = n
@@ -203,7 +203,13 @@ def run_reference(ref, n, actions, ep0=None, seed=SEED, cfg_edit=None):
     np.random.rand = rng.rand
     rec = dict(obs=[], rew=[], done=[], time_out=[], commands=[], ep_len=[], qpos=[], ep_keys=None, ep_vals=[], ep_valid=[], time_outs_extra=[])
     try:
-        env.reset_idx(np.arange(n))                              # what the GPU class and the oracle do before the first step
+        if via_reset:                                            # the reference's reset(): reset_idx(all) + one zero-action step (:392-396)
+            with contextlib.redirect_stdout(io.StringIO()):
+                obs0, priv0 = env.reset()
+            assert priv0 is None
+            rec["reset_obs"] = obs0.numpy().copy()
+        else:
+            env.reset_idx(np.arange(n))                          # what the GPU class and the oracle do before the first step
         if ep0 is not None:
             env.episode_length_buf = torch.tensor(np.array(ep0), dtype=torch.int64)   # a copy, re-bound like rsl_rl does (train.py:54)
         for a in actions:
@@ -251,15 +257,16 @@ def scenarios():
     def noisy(cfg):                                             # observation noise with the reference's 12-DoF slice boundaries (quirk Q8)
         cfg.noise.add_noise = True
     yield "noise", n, a[:20], ep0, noisy
+    yield "via_reset", n, a[:10], None, None                    # starts with the reference's reset() instead of reset_idx(all)
 
 
 def main():
     ref = sys.argv[1] if len(sys.argv) > 1 else "/root/reference"
     out = {}
     for name, n, a, ep0, edit in scenarios():
-        r = run_reference(ref, n, a, ep0, cfg_edit=edit)
+        r = run_reference(ref, n, a, ep0, cfg_edit=edit, via_reset=(name == "via_reset"))
         out[f"{name}.actions"] = a
-        out[f"{name}.ep0"] = ep0
+        out[f"{name}.ep0"] = ep0 if ep0 is not None else np.zeros(0, dtype=np.int64)
         for k, v in r.items():
             out[f"{name}.{k}"] = v
         print(f"{name}: {len(a)} steps x {n} envs, resets {int(r['done'].sum())}, time-outs {int(r['time_out'].sum())}, "
