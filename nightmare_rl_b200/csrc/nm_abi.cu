@@ -103,7 +103,8 @@ static void local_inertia(const double* iquat, const double* diag, float* out) {
 static int build_device_model(nm_model* m) {
   const int *sizes, *oi;
   const double* orl;
-  if (!get(m, "sizes", 2, sizes) || !get(m, "opt_int", 2, oi) || !get(m, "opt_real", 0, orl))
+  long long n_oi = 0;
+  if (!get(m, "sizes", 2, sizes) || !get(m, "opt_int", 2, oi, &n_oi) || !get(m, "opt_real", 0, orl))
     return fail(NM_ERR_FORMAT, "nmb: missing header arrays (sizes/opt_int/opt_real)");
   m->nq = sizes[0]; m->nv = sizes[1]; m->nu = sizes[2]; m->nbody = sizes[3]; m->njnt = sizes[4];
   m->ngeom = sizes[5]; m->nsite = sizes[6]; m->nsensor = sizes[7]; m->nhv = sizes[8]; m->nhn = sizes[9];
@@ -295,6 +296,7 @@ static int build_device_model(nm_model* m) {
   D.solver_scale = (float)(1.0 / (meaninertia * (m->nv > 1 ? m->nv : 1)));
   D.iterations = oi[3];
   D.noslip_iterations = oi[4];
+  D.planemesh_maxcon = (n_oi > 7 && oi[7] >= 1 && oi[7] <= NM_MAXC) ? oi[7] : NM_MAXC;
   D.integrator = integrator;
   D.imp_act = integrator == 3 ? 1.f : 0.f;
   D.imp_damp = (integrator == 3 || oi[5]) ? 1.f : 0.f;

@@ -49,6 +49,7 @@ struct alignas(16) NmDevModel {
   float gravity[3];
   float timestep, tolerance, noslip_tolerance, solver_scale;
   int iterations, noslip_iterations, nleg, integrator;
+  int planemesh_maxcon, pad_m[3];   // contacts per plane-mesh pair (opt_int[7] of the model file, 1..NM_MAXC)
   float imp_damp, imp_act;  // which velocity derivatives enter the implicit velocity update (implicitfast: both; Euler+eulerdamp: damping)
   float qpos0[32];
 };

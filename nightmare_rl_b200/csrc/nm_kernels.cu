@@ -706,7 +706,8 @@ __global__ void __launch_bounds__(BLOCK, MINB) nm_step_kernel(const NmKernelArgs
         const float thr2 = (0.3f * G.rbound) * (0.3f * G.rbound);
         const float dpl = dot(pn, pg) - sm.plane_d;       // cheap pre-test in the geom frame: dist(u) ~= dl.v_u + dpl
         const int el = e0 + deg - 1;
-        for (int e = e0; e <= el && nc < NM_MAXC; e += 4) {   // up to 3 more among the support vertex's neighbours
+        const int maxc = sm.planemesh_maxcon;              // model option, <= NM_MAXC (kept out of the loop bounds: they stay compile-time)
+        for (int e = e0; e <= el && nc < NM_MAXC; e += 4) {   // up to maxc - 1 more among the support vertex's neighbours
           // four neighbours per trip (L1-resident after the walk); almost all fail the cheap depth pre-test
           float4 ww[4];
 #pragma unroll
@@ -721,7 +722,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) nm_step_kernel(const NmKernelArgs
             V3 cp = fma3(-0.5f * du, pn, wu);
             bool close = false;
             for (int q = 0; q < nc; q++) { V3 d3 = cb.pos[q] - cp; close |= dot(d3, d3) < thr2; }
-            if (close) continue;
+            if (close || nc >= maxc) continue;
             cdist[nc] = du; cvert[nc] = __float_as_int(w4.w); cb.pos[nc] = cp; nc++;
           }
         }

@@ -762,7 +762,11 @@ def compile_mjcf(path: str) -> CompiledModel:
     G = lambda key, shape, dt=np.float64: np.asarray([g[key] for g in geoms], dtype=dt).reshape(shape)
     arrays = {
         "sizes": i32([nq, nv, nu, nbody, njnt, ngeom, len(site_body), len(sensor_site), len(hull_vert), len(hull_nbr)]),
-        "opt_int": i32([integrator, solver, cone, o["iterations"], o["noslip_iterations"], int(o["eulerdamp"]), o["ls_iterations"]]),
+        # last entry: how many contacts one plane-mesh pair may produce (support vertex + neighbours).  4 follows SURVEY.md
+        # Appendix A.2 as recalled ("up to 3 more"); the entry exists so that a MuJoCo cross-check can correct it to whatever
+        # mjc_PlaneConvex really does by re-saving the model, without touching oracle or kernel code
+        "opt_int": i32([integrator, solver, cone, o["iterations"], o["noslip_iterations"], int(o["eulerdamp"]), o["ls_iterations"],
+                        PLANEMESH_MAXCON]),
         "opt_real": f64([o["timestep"], *o["gravity"], o["tolerance"], o["noslip_tolerance"], o["impratio"], meaninertia], -1),
         "qpos0": qpos0,
         "body_parent": i32([b.parent for b in p.bodies]),
@@ -798,6 +802,9 @@ def compile_mjcf(path: str) -> CompiledModel:
     }
     names = dict(body=body_names, joint=jnt_names, geom=geom_names, site=site_names, actuator=act_names, sensor=sensor_names)
     return CompiledModel(arrays, names)
+
+
+PLANEMESH_MAXCON = 4
 
 
 def load_model(path: str) -> CompiledModel:

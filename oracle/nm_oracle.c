@@ -31,6 +31,7 @@ struct nmo_model {
   unsigned char* raw;
   int nq, nv, nu, nbody, njnt, ngeom, nsite, nsensor, nhv, nhn;
   int integrator, solver, cone, iterations, noslip_iterations, eulerdamp;
+  int planemesh_maxcon; /* contacts per plane-mesh pair (opt_int[7]; 4 when the model file predates the entry) */
   double timestep, gravity[3], tolerance, noslip_tolerance, impratio, meaninertia;
   const double *qpos0, *body_pos, *body_quat, *body_ipos, *body_iquat, *body_mass, *body_inertia, *body_invweight0;
   const int *body_parent, *body_rootid, *body_jntadr, *body_jntnum, *body_dofadr, *body_dofnum;
@@ -101,13 +102,15 @@ nmo_model* nmo_model_load(const char* path, char* err, int errlen) {
   }
   fclose(f);
   const int* sizes = (const int*)nmb_find(m->raw, "sizes", NULL, NULL);
-  const int* oi = (const int*)nmb_find(m->raw, "opt_int", NULL, NULL);
+  long long noi = 0;
+  const int* oi = (const int*)nmb_find(m->raw, "opt_int", NULL, &noi);
   const double* orl = (const double*)nmb_find(m->raw, "opt_real", NULL, NULL);
   if (!sizes || !oi || !orl) { snprintf(err, errlen, "nmb: missing header arrays"); nmo_model_free(m); return NULL; }
   m->nq = sizes[0]; m->nv = sizes[1]; m->nu = sizes[2]; m->nbody = sizes[3]; m->njnt = sizes[4];
   m->ngeom = sizes[5]; m->nsite = sizes[6]; m->nsensor = sizes[7]; m->nhv = sizes[8]; m->nhn = sizes[9];
   m->integrator = oi[0]; m->solver = oi[1]; m->cone = oi[2]; m->iterations = oi[3];
   m->noslip_iterations = oi[4]; m->eulerdamp = oi[5];
+  m->planemesh_maxcon = (noi > 7 && oi[7] >= 1 && oi[7] <= 4) ? oi[7] : 4;
   m->timestep = orl[0]; m->gravity[0] = orl[1]; m->gravity[1] = orl[2]; m->gravity[2] = orl[3];
   m->tolerance = orl[4]; m->noslip_tolerance = orl[5]; m->impratio = orl[6]; m->meaninertia = orl[7];
   GETP(qpos0, double); GETP(body_pos, double); GETP(body_quat, double); GETP(body_ipos, double);
@@ -555,7 +558,7 @@ static void collision(const nmo_model* m, data_t* d) {
         /* pass 0: the support vertex.  pass 1: its hull-graph neighbours (up to 3 more contacts) */
         int lo = pass == 0 ? 0 : m->hull_nbr_adr[adr + best];
         int hi = pass == 0 ? 1 : m->hull_nbr_adr[adr + best + 1];
-        for (int e = lo; e < hi && cnt < 4 && d->ncon < NMO_MAXCON; e++) {
+        for (int e = lo; e < hi && cnt < m->planemesh_maxcon && d->ncon < NMO_MAXCON; e++) {
           int v = pass == 0 ? best : m->hull_nbr[e];
           double w[3], dist;
           if (pass == 0) { memcpy(w, bestw, sizeof(w)); dist = bestd; }

@@ -336,6 +336,57 @@ def test_slope_hold_and_slide_matches_oracle(tmp_path, theta, along, slides):
         assert np.abs(d_o - d_g).max() < 0.02
 
 
+def test_plane_mesh_contact_cap_option(tmp_path):
+    """The contacts-per-plane-mesh-pair cap is a model option (opt_int[7], tests/test_oracle_physics.py): with it set to 3 the
+    kernel and the oracle must both produce at most 3 contacts per hull and still agree in lockstep."""
+    from nightmare_rl_b200 import _lib, mjcf
+    from conftest import NMB
+    G = _common()
+    cm = mjcf.CompiledModel.load(NMB)
+    cm.arrays["opt_int"][7] = 3
+    path = str(tmp_path / "cap3.nmb")
+    cm.save(path)
+    dm, om = _lib.Model(cm.to_bytes()), G.O.OracleModel(path)
+    rng = np.random.default_rng(1)
+    n, T = 256, 50
+    qpos = np.tile(cm.qpos0, (n, 1))
+    qpos[:, 7:] += rng.uniform(-0.6, 0.6, (n, 18))
+    qpos[:, 2] = rng.uniform(0.03, 0.22, n)
+    qpos[:, 3:7] = rng.normal(size=(n, 4))
+    qpos[:, 3:7] /= np.linalg.norm(qpos[:, 3:7], axis=1, keepdims=True)
+    ob, gb = G.O.OracleBatch(om, n), G.Batch(dm, n, G.DEV, debug=True)
+    ob.set_state(qpos.astype(np.float32), np.zeros((n, 24)), np.zeros((n, 24)))
+    ctrl = np.zeros((n, 18), dtype=np.float32)
+    worst, most, compared = 0.0, 0, 0
+    for t in range(T):
+        q, v, w = ob.get_state()
+        q, v, w = q.astype(np.float32), v.astype(np.float32), w.astype(np.float32)
+        ob.set_state(q, v, w)
+        G.push_state(gb, q, v, w)
+        ob.physics_step(ctrl, 1, 8)
+        gb.physics_step(torch.from_numpy(ctrl), 1)
+        torch.cuda.synchronize()
+        dbg = gb.debug.cpu().numpy()
+        oncon = np.array([ob.get(i, "ncon")[0] for i in range(n)])
+        assert np.array_equal(oncon, dbg[:, 0]), f"substep {t}: contact counts differ"
+        per_lane = dbg[:, 8:8 + 7 * 12].reshape(n, 7, 12)[:, :, 0]
+        most = max(most, int(per_lane.max()))
+        same = np.ones(n, dtype=bool)
+        for i in np.nonzero(oncon)[0]:
+            con = ob.get(i, "contact").reshape(-1, 7)
+            for lane, geom in [(6, 1)] + [(k, 2 + k) for k in range(6)]:
+                mine = con[con[:, 1] == geom]
+                rec = dbg[i, 8 + lane * 12: 8 + lane * 12 + 9]
+                same[i] &= all(int(rec[1 + 2 * c]) == int(mine[c, 2]) for c in range(len(mine)))
+        oq, ov, _ = ob.get_state()
+        gq, gv, _ = G.gpu_state(gb)
+        d = np.maximum(G.per_env_rel(gq, oq), G.per_env_rel(gv, ov, floor=0.1))
+        worst = max(worst, float(d[same].max()))
+        compared += int(same.sum())
+    print(f"\n[cap 3] {T} lockstep substeps x {n} envs: most contacts on one hull {most}, compared {compared}, worst deviation {worst:.2e}")
+    assert most == 3 and compared > 0.98 * n * T and worst < 2e-4
+
+
 def test_determinism_and_batch_independence():
     """Bitwise reproducible, and env i does not depend on its neighbours or on the batch size (the
     property multi-GPU sharding relies on)."""

@@ -292,3 +292,34 @@ def test_pyramidal_friction_cone_holds_and_slides(compiled_model, tmp_path):
         return float(np.linalg.norm(v[0, :2]))
     assert speed_after(40, 0.0) < 0.1 and speed_after(50, 0.0) > 2.0             # along a tangent axis: threshold 45 degrees
     assert speed_after(30, np.pi / 4) < 0.1 and speed_after(40, np.pi / 4) > 1.0   # along the diagonal: threshold 35.3 degrees
+
+
+def test_plane_mesh_contact_cap_is_a_model_option(compiled_model, tmp_path):
+    """How many contacts one plane-mesh pair may produce is stored in the model file (opt_int[7], default 4 = support vertex + up
+    to 3 neighbours as recalled in SURVEY.md Appendix A.2).  It is an option precisely because that number could not be checked
+    against MuJoCo here: a cross-check that finds a different cap fixes it by re-saving the model."""
+    assert int(compiled_model.arrays["opt_int"][7]) == 4
+    rng = np.random.default_rng(1)
+    n = 64
+    qpos = np.tile(compiled_model.qpos0, (n, 1))
+    qpos[:, 7:] += rng.uniform(-0.6, 0.6, (n, 18))
+    qpos[:, 2] = rng.uniform(0.03, 0.22, n)
+    qpos[:, 3:7] = rng.normal(size=(n, 4))
+    qpos[:, 3:7] /= np.linalg.norm(qpos[:, 3:7], axis=1, keepdims=True)
+    most = {}
+    for cap in (4, 3, 1):
+        cm = mjcf.CompiledModel(dict((k, v.copy()) for k, v in compiled_model.arrays.items()), compiled_model.names)
+        cm.arrays["opt_int"][7] = cap
+        p = str(tmp_path / f"cap{cap}.nmb")
+        cm.save(p)
+        b = O.OracleBatch(O.OracleModel(p), n)
+        b.set_state(qpos, np.zeros((n, 24)), np.zeros((n, 24)))
+        most[cap] = 0
+        for _ in range(60):                                      # tumbling robots land on hull faces and tibia flanks
+            b.physics_step(np.zeros((n, 18)), 1, 8)
+            for i in range(n):
+                con = b.get(i, "contact").reshape(-1, 7)
+                if len(con):
+                    most[cap] = max(most[cap], int(np.bincount(con[:, 1].astype(int)).max()))
+        assert np.isfinite(b.get_state()[0]).all()
+    assert most == {4: 4, 3: 3, 1: 1}, most
