@@ -323,3 +323,38 @@ def test_plane_mesh_contact_cap_is_a_model_option(compiled_model, tmp_path):
                     most[cap] = max(most[cap], int(np.bincount(con[:, 1].astype(int)).max()))
         assert np.isfinite(b.get_state()[0]).all()
     assert most == {4: 4, 3: 3, 1: 1}, most
+
+
+def test_passive_contact_never_gains_energy(compiled_model, oracle_model):
+    """Zero controls: the velocity servos act as dampers and the soft contacts follow a critically damped reference
+    (solref 0.02 / 1), so a robot dropped in any pose must never have more mechanical energy than it started with, and must end
+    well below it.  (Within one impact the energy is not monotone: at dt = 8 ms the contact 'spring' takes up joules at 4 cm of
+    penetration and the pyramidal edges that oppose sliding keep pushing while the hull already separates, so a tumbling robot
+    bounces -- losing energy on every bounce.)  A sign error in aref, in the pyramid rows or in J'f would pump energy in."""
+    rng = np.random.default_rng(9)
+    n = 16
+    qpos = np.tile(compiled_model.qpos0, (n, 1))
+    qpos[:, 7:] += rng.uniform(-0.5, 0.5, (n, 18))
+    qpos[:, 2] = rng.uniform(0.35, 0.45, n)                   # clear of the floor in every orientation: no energy pre-stored in penetration
+    qpos[:, 3:7] = rng.normal(size=(n, 4))
+    qpos[:, 3:7] /= np.linalg.norm(qpos[:, 3:7], axis=1, keepdims=True)
+    b = O.OracleBatch(oracle_model, n)
+    b.set_state(qpos, np.zeros((n, 24)), np.zeros((n, 24)))
+
+    def energy():
+        b.forward(np.zeros((n, 18)), 8)
+        out = np.zeros(n)
+        for i in range(n):
+            M = b.get(i, "M").reshape(24, 24)
+            qv = b.get(i, "qvel")
+            z = b.get(i, "xipos").reshape(-1, 3)[:, 2]
+            out[i] = 0.5 * qv @ M @ qv + 9.81 * (compiled_model.body_mass * z).sum()
+        return out
+
+    e0 = energy()
+    for _ in range(375):                                       # 3 s
+        b.physics_step(np.zeros((n, 18)), 1, 8)
+        e = energy()
+        assert (e <= e0 + 0.02).all(), float((e - e0).max())
+    assert (e0 - e > 6.0).all()                                # dropped from ~0.4 m: m g h = 11.8 J, ~2.5 J left lying on the floor
+    assert np.abs(b.get_state()[1]).max() < 1.0                # and it has come to rest
