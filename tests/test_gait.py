@@ -89,3 +89,22 @@ def test_oracle_walks_with_the_reference_gait():
         assert np.corrcoef(c[:, tri].T).min() > 0.5
     # at every instant at least one tripod carries the robot
     assert (np.maximum(c[:, [0, 2, 4]].sum(1), c[:, [1, 3, 5]].sum(1)) >= 2).mean() > 0.97
+
+
+def test_scripted_gait_action_source_on_cpu():
+    """ScriptedGait (product-side helper) is plain torch: index arithmetic, phase shifts, looping and the action map
+    a = (theta + default_dof_pos) / action_scale can be checked without a GPU."""
+    import torch
+    from nightmare_rl_b200.envs.scripted_gait import ScriptedGait
+    z = np.load(FIX)
+    g = ScriptedGait(FIX, 5, torch.device("cpu"), action_scale=0.2, phase_shift=11)
+    assert g.index(0).tolist() == [0, 11, 22, 33, 44]
+    a0 = g.actions()                                             # internal counter: step 0
+    default = np.array([0.0, np.pi / 5, 0.0] * 6)
+    assert np.allclose(a0[2].numpy() * 0.2 - default, z["targets"][22], atol=1e-6)
+    assert g.t == 1 and np.allclose(g.joint_targets(3)[1].numpy(), z["targets"][14], atol=1e-7)
+    lo, hi = g.loop
+    assert z["commands"][lo].any() and z["commands"][hi - 1].any() and not z["commands"][lo - 1].any()
+    far = g.index(10 * len(z["targets"]) + 7)
+    assert ((far >= lo) & (far < hi)).all() and len(set(far.tolist())) == 5      # loops inside the walking part, envs stay out of phase
+    assert (a0.abs() * 0.2 <= 1.0).all()                          # inside the env's clip range
