@@ -25,7 +25,8 @@ extern "C" {
 #define NM_NSENSOR 13     /* mjmodel.xml:156-170 */
 #define NM_NREW 18        /* reward terms in alphabetical order (envs/helpers.py:7) */
 #define NM_MAXCON_GEOM 4  /* plane-mesh: support vertex + up to 3 more */
-#define NM_DBG_STRIDE 160 /* floats per env in the optional debug buffer */
+#define NM_DBG_STRIDE 288 /* floats per env in the optional debug buffer */
+#define NM_REC_STRIDE 52  /* floats per row of the env-0 recorder ring: done flag, qpos[25], qvel[24], 2 pad */
 
 typedef enum {
   NM_OK = 0,
@@ -45,7 +46,10 @@ typedef void* nm_stream;   /* cudaStream_t */
  * the way NightmareV3Env.__init__ does it (envs/nightmare_v3_env.py:99-137).  Same layout as the
  * oracle's nmo_envcfg. */
 typedef struct {
-  int32_t decimation, num_actions, tibia_contact_mode, body_contact_mode, add_noise, resample_period, strict_reference, pad0;
+  int32_t decimation, num_actions, tibia_contact_mode, body_contact_mode, add_noise, resample_period;
+  int32_t strict_reference;   /* 1: extras["time_outs"] / ["episode"] latched only on steps where an env reset (quirk Q10, :363-371);
+                                 0: time_outs refreshed every step (training mode, identical whenever >= 1 env resets) */
+  int32_t pad0;
   double action_scale, clip_actions, p_gain, clip_obs;
   double default_pos[NM_NDOF];
   double obs_lin_vel, obs_ang_vel, obs_dof_pos, obs_dof_vel;
@@ -114,6 +118,12 @@ int  nm_batch_set_env_offset(nm_batch*, int64_t first_global_env);
  * ranges = {mu_lo, mu_hi, kv_lo, kv_hi, mass_lo, mass_hi}: when resample_on_reset != 0 an env that resets inside nm_step
  * draws new scales uniformly from them (Philox phase 3).  With all scales 1 the step is bit-identical to DR off. */
 int  nm_batch_set_domain_randomization(nm_batch*, float* dr, const float* ranges, int resample_on_reset);
+
+/* ≙ the env-0 state recorder                                envs/nightmare_v3_env.py:261-272
+ * ring: DEVICE float32 [capacity, NM_REC_STRIDE], caller-owned (NULL switches it off).  Every nm_step / nm_step_host then
+ * writes row (number of steps since this call) % capacity = {done flag of env 0, its qpos[25], its qvel[24]} as they are
+ * BEFORE reset_idx runs (the reference appends the row at :272, ahead of reset_idx at :274). */
+int  nm_batch_set_recorder(nm_batch*, float* ring, int capacity);
 
 /* ≙ NightmareV3Env.step(actions)                            envs/nightmare_v3_env.py:145-311
  * actions: device float32 [N, act_stride], first 18 columns used (:156).  step_counter is the

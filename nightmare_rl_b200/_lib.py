@@ -10,7 +10,8 @@ import os
 from .build import LIB_PATH
 from .envcfg import EnvCfgStruct, NREW
 
-NM_DBG_STRIDE = 160
+NM_DBG_STRIDE = 288
+NM_REC_STRIDE = 52
 _vp, _ci, _i64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64
 
 
@@ -43,6 +44,7 @@ def _load() -> ctypes.CDLL:
     L.nm_batch_create.argtypes = [_vp, _ci, _ci, ctypes.c_uint64, _vp, ctypes.POINTER(NmBuffers), ctypes.POINTER(_vp)]
     L.nm_batch_destroy.argtypes = [_vp]
     L.nm_batch_set_env_offset.argtypes = [_vp, _i64]
+    L.nm_batch_set_recorder.argtypes = [_vp, _vp, _ci]
     L.nm_batch_set_domain_randomization.argtypes = [_vp, _vp, ctypes.POINTER(ctypes.c_float), _ci]
     L.nm_step.argtypes = [_vp, _vp, _ci, _i64, _vp]
     L.nm_physics_step.argtypes = [_vp, _vp, _ci, _vp]
@@ -76,7 +78,7 @@ lib = _load()
 
 EXPORTS = ("nm_last_error", "nm_model_load", "nm_model_from_buffer", "nm_model_destroy", "nm_model_size", "nm_model_timestep",
            "nm_name2id", "nm_model_qpos0", "nm_batch_create", "nm_batch_destroy", "nm_batch_set_env_offset",
-           "nm_batch_set_domain_randomization", "nm_step",
+           "nm_batch_set_domain_randomization", "nm_batch_set_recorder", "nm_step",
            "nm_physics_step", "nm_reset_idx", "nm_step_host", "nm_batch_launches", "nm_measure_fp32_peak",
            "nm_policy_create", "nm_policy_destroy", "nm_policy_param_count", "nm_policy_load_weights", "nm_policy_act",
            "nm_policy_act_store", "nm_policy_launches", "nm_rollout_store", "nm_ppo_head", "nm_ppo_grad", "nm_gae", "nm_ppo_adam",

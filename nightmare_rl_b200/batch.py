@@ -63,6 +63,17 @@ class Batch:
         _lib.check(_lib.lib.nm_batch_set_domain_randomization(self._h, dr.data_ptr(), r, 1 if (resample_on_reset and ranges is not None) else 0))
         self.dr = dr
 
+    def set_recorder(self, ring):
+        """``ring``: float32 CUDA tensor [capacity, NM_REC_STRIDE]; every following step writes env 0's pre-reset
+        (done, qpos, qvel) into row (steps since this call) % capacity.  None switches the recorder off."""
+        if ring is None:
+            _lib.check(_lib.lib.nm_batch_set_recorder(self._h, None, 0))
+        else:
+            if ring.dim() != 2 or ring.shape[1] != _lib.NM_REC_STRIDE or ring.dtype != torch.float32 or ring.device != self.device or not ring.is_contiguous():
+                raise ValueError("recorder ring must be a contiguous float32 [capacity, NM_REC_STRIDE] tensor on the batch's device")
+            _lib.check(_lib.lib.nm_batch_set_recorder(self._h, ring.data_ptr(), ring.shape[0]))
+        self._rec_ring = ring
+
     def _stream(self):
         return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 

@@ -384,12 +384,23 @@ struct nm_batch {
   float* d_stage_actions;
   size_t stage_cap;
   int64_t launches;
+  float* rec_ring;       // env-0 recorder ring (caller-owned) and its write cursor
+  int rec_cap;
+  int64_t rec_count;
+};
+
+// every entry point runs with the batch's device current and restores the caller's (a batch on cuda:1 used from a thread whose
+// current device is 0 would otherwise launch on a foreign stream)
+struct DevGuard {
+  int prev = -1, dev;
+  explicit DevGuard(int d) : dev(d) { if (cudaGetDevice(&prev) != cudaSuccess) prev = -1; if (prev != dev) cudaSetDevice(dev); }
+  ~DevGuard() { if (prev >= 0 && prev != dev) cudaSetDevice(prev); }
 };
 
 static void fill_cfg(const nm_envcfg& c, NmDevCfg& d) {
   memset(&d, 0, sizeof(d));
   d.decimation = c.decimation; d.tibia_mode = c.tibia_contact_mode; d.body_mode = c.body_contact_mode;
-  d.add_noise = c.add_noise; d.resample_period = c.resample_period;
+  d.add_noise = c.add_noise; d.resample_period = c.resample_period; d.strict = c.strict_reference ? 1 : 0;
   d.action_scale = (float)c.action_scale; d.clip_actions = (float)c.clip_actions; d.p_gain = (float)c.p_gain; d.clip_obs = (float)c.clip_obs;
   for (int i = 0; i < 18; i++) d.default_pos[i] = (float)c.default_pos[i];
   d.obs_lin_vel = (float)c.obs_lin_vel; d.obs_ang_vel = (float)c.obs_ang_vel; d.obs_dof_pos = (float)c.obs_dof_pos; d.obs_dof_vel = (float)c.obs_dof_vel;
@@ -478,7 +489,7 @@ static int batch_create_impl(const nm_model* m, int num_envs, int device, uint64
   a.sensordata = bufs->sensordata; a.episode_acc = bufs->episode_acc; a.debug = bufs->debug;
   a.in_actions = nullptr; a.act_stride = 0; a.in_ctrl = nullptr;
   a.host_obs = nullptr; a.host_rew = nullptr; a.host_done = nullptr;
-  a.dr = nullptr; a.dr_on_reset = 0;
+  a.dr = nullptr; a.dr_on_reset = 0; a.rec_row = nullptr;
   return NM_OK;
 }
 
@@ -497,6 +508,17 @@ extern "C" int nm_batch_set_domain_randomization(nm_batch* b, float* dr, const f
   return NM_OK;
 }
 
+extern "C" int nm_batch_set_recorder(nm_batch* b, float* ring, int capacity) {
+  if (!b || (ring && capacity <= 0)) return fail(NM_ERR_ARG, "nm_batch_set_recorder: bad argument");
+  b->rec_ring = ring; b->rec_cap = ring ? capacity : 0; b->rec_count = 0;
+  return NM_OK;
+}
+
+static inline float* next_rec_row(nm_batch* b) {
+  if (!b->rec_ring) return nullptr;
+  return b->rec_ring + (size_t)(b->rec_count++ % b->rec_cap) * NM_REC_STRIDE;
+}
+
 extern "C" int nm_batch_set_env_offset(nm_batch* b, int64_t first) {
   if (!b) return fail(NM_ERR_ARG, "null batch");
   b->args.env_offset = first;
@@ -507,8 +529,10 @@ extern "C" int nm_step(nm_batch* b, const float* actions, int act_stride, int64_
   if (!b || !actions) return fail(NM_ERR_ARG, "nm_step: null argument");
   if (!b->args.obs) return fail(NM_ERR_ARG, "nm_step: batch was created without env buffers");
   if (act_stride < NM_NDOF) return fail(NM_ERR_ARG, "nm_step: actions need at least 18 columns");
+  DevGuard guard(b->device);
   NmKernelArgs a = b->args;
   a.in_actions = actions; a.act_stride = act_stride; a.step_counter = step_counter;
+  a.rec_row = next_rec_row(b);
   a.acc_cur = b->d_acc + (NM_NREW + 1) * b->parity;
   a.acc_next = b->d_acc + (NM_NREW + 1) * (b->parity ^ 1);
   b->parity ^= 1;
@@ -521,6 +545,7 @@ extern "C" int nm_step(nm_batch* b, const float* actions, int act_stride, int64_
 
 extern "C" int nm_physics_step(nm_batch* b, const float* ctrl, int nstep, nm_stream stream) {
   if (!b || !ctrl || nstep < 1) return fail(NM_ERR_ARG, "nm_physics_step: bad argument");
+  DevGuard guard(b->device);
   NmKernelArgs a = b->args;
   a.in_ctrl = ctrl; a.nstep = nstep;
   nm_launch_step(a, false, stream);
@@ -533,6 +558,7 @@ extern "C" int nm_reset_idx(nm_batch* b, const int64_t* env_ids, int n, int64_t 
   if (!b || (n > 0 && !env_ids)) return fail(NM_ERR_ARG, "nm_reset_idx: bad argument");
   if (!b->args.obs) return fail(NM_ERR_ARG, "nm_reset_idx: batch was created without env buffers");
   if (n <= 0) return NM_OK;
+  DevGuard guard(b->device);
   NmKernelArgs a = b->args;
   a.step_counter = step_counter;
   nm_launch_reset(a, reinterpret_cast<const long long*>(env_ids), n, stream);
@@ -559,8 +585,10 @@ extern "C" int nm_step_host(nm_batch* b, const float* h_actions, int act_stride,
   if (ma && mo && mr && md) {
     if (!b->args.obs) return fail(NM_ERR_ARG, "nm_step_host: batch was created without env buffers");
     if (act_stride < NM_NDOF) return fail(NM_ERR_ARG, "nm_step_host: actions need at least 18 columns");
+    DevGuard guard(b->device);
     NmKernelArgs a = b->args;
     a.in_actions = static_cast<const float*>(ma); a.act_stride = act_stride; a.step_counter = step_counter;
+    a.rec_row = next_rec_row(b);
     a.host_obs = static_cast<float*>(mo); a.host_rew = static_cast<float*>(mr); a.host_done = static_cast<long long*>(md);
     a.acc_cur = b->d_acc + (NM_NREW + 1) * b->parity;
     a.acc_next = b->d_acc + (NM_NREW + 1) * (b->parity ^ 1);
@@ -573,6 +601,7 @@ extern "C" int nm_step_host(nm_batch* b, const float* h_actions, int act_stride,
     return NM_OK;
   }
   // Pageable host memory: staged copies on the same stream
+  DevGuard guard(b->device);
   const size_t need = (size_t)b->n * act_stride * sizeof(float);
   if (need > b->stage_cap) {
     if (b->d_stage_actions) cudaFree(b->d_stage_actions);

@@ -56,7 +56,9 @@ struct alignas(16) NmDevModel {
 
 // env-layer scalars in fp32 (from nm_envcfg)
 struct alignas(16) NmDevCfg {
-  int decimation, tibia_mode, body_mode, add_noise, resample_period, pad[3];
+  int decimation, tibia_mode, body_mode, add_noise, resample_period;
+  int strict;               // 1 (default): extras latched only on steps where >= 1 env reset (quirk Q10); 0: time_outs refreshed every step
+  int pad[2];
   float action_scale, clip_actions, p_gain, clip_obs;
   float default_pos[18];
   float obs_lin_vel, obs_ang_vel, obs_dof_pos, obs_dof_vel;
@@ -86,6 +88,7 @@ struct NmKernelArgs {
   long long* episode_length; float* episode_sums; float* feet_air_time; int* contact_bits;
   float* obs; float* rew; long long* done; float* time_outs; float* sensordata; float* episode_acc; float* debug;
   float* ep_means; float* time_outs_latched;   // extras, refreshed only on steps where >= 1 env reset (env.py:363-371)
+  float* rec_row;                              // env-0 recorder (env.py:261-272): [done, qpos(25), qvel(24)] BEFORE reset_idx, or null
   float* acc_cur; float* acc_next;             // library-owned double-buffered accumulators behind episode_acc
   // host-resident callers (nm_step_host, zero-copy): pinned host memory mapped into the device address space, or null
   float* host_obs; float* host_rew; long long* host_done;

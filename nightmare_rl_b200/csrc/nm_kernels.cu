@@ -984,7 +984,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) nm_step_kernel(const NmKernelArgs
 
     // ================================================================ optional debug record (parity harness)
     if (A.debug != nullptr && valid && sub == A.nstep - 1) {
-      float* dbg = A.debug + (size_t)env * 160;
+      float* dbg = A.debug + (size_t)env * 288;
       if (l == 0) {
         dbg[0] = (float)ncon_env; dbg[1] = (float)dbg_pgs; dbg[2] = (float)dbg_noslip; dbg[3] = (float)dbg_warm;
 #pragma unroll
@@ -998,6 +998,12 @@ __global__ void __launch_bounds__(BLOCK, MINB) nm_step_kernel(const NmKernelArgs
       if (leg) {
 #pragma unroll
         for (int j = 0; j < 3; j++) { dbg[102 + jo + j] = xsk[j]; dbg[134 + jo + j] = xsk[j] + xk[j]; }
+      }
+      if (l < 7 && any_contact) {                   // pyramid-edge forces of this lane's contacts (stage attribution)
+        float* g = dbg + 160 + l * 16;
+        for (int c = 0; c < nc; c++)
+#pragma unroll
+          for (int e = 0; e < 4; e++) g[4 * c + e] = cb.f[c][e];
       }
     }
 
@@ -1217,6 +1223,21 @@ __global__ void __launch_bounds__(BLOCK, MINB) nm_step_kernel(const NmKernelArgs
     atomicAdd(A.acc_cur + 18, 1.f);
   }
 
+  // E12 env-0 recorder (env.py:261-272): the reference appends data[0].qpos/qvel BEFORE reset_idx (:274), so on a reset
+  // step the recorded row is the terminal state, not qpos0
+  if (A.rec_row != nullptr && valid && env == 0) {
+    float* rr = A.rec_row;
+    if (leg) {
+#pragma unroll
+      for (int j = 0; j < 3; j++) { rr[1 + 7 + jo + j] = th[j]; rr[26 + 6 + jo + j] = thd[j]; }
+    }
+    if (l == 7) {
+      rr[0] = reset ? 1.f : 0.f;
+      rr[1] = p.x; rr[2] = p.y; rr[3] = p.z; rr[4] = q0; rr[5] = q1; rr[6] = q2; rr[7] = q3;
+      rr[26] = vlin.x; rr[27] = vlin.y; rr[28] = vlin.z; rr[29] = wloc.x; rr[30] = wloc.y; rr[31] = wloc.z;
+    }
+  }
+
   // ------------------------------------------------------------------ write back
   if (valid) {
     float* qpo = A.qpos + (size_t)env * 25;
@@ -1334,7 +1355,7 @@ __global__ void nm_finalize_kernel(const NmKernelArgs A) {
     A.acc_next[i] = 0.f;
     if (i < 18 && cnt > 0.f) A.ep_means[i] = v / cnt * A.cfg->inv_episode_length_s;
   }
-  if (cnt > 0.f && i < A.num_envs) A.time_outs_latched[i] = A.time_outs[i];
+  if ((cnt > 0.f || A.cfg->strict == 0) && i < A.num_envs) A.time_outs_latched[i] = A.time_outs[i];
 }
 
 void nm_launch_finalize(const NmKernelArgs& a, void* stream) {
@@ -1344,12 +1365,11 @@ void nm_launch_finalize(const NmKernelArgs& a, void* stream) {
 void nm_launch_step(const NmKernelArgs& a, bool env_mode, void* stream) {
   const int threads = a.num_envs * NM_OCT;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  static int sms = 0;
-  if (sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
-  }
+  static int sms_of[64] = {0};                          // per device (the ABI makes the batch's device current before launching)
+  int dev = 0;
+  cudaGetDevice(&dev);
+  int& sms = sms_of[dev & 63];
+  if (sms == 0 && (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0)) sms = 148;
   const bool one_wave = threads <= sms * 8 * 32;           // fits one wave of the 255-register build (8 warps/SM)
   if (one_wave) {
     const int blocks = (threads + NM_SMALL_BLOCK - 1) / NM_SMALL_BLOCK;

@@ -81,7 +81,9 @@ def build_envcfg(cfg, timestep: float) -> EnvCfgStruct:
     s.body_contact_mode = int(cfg.env.body_contact_mode)
     s.add_noise = int(bool(cfg.noise.add_noise))
     s.resample_period = int(cfg.commands.resampling_time / dt)
-    s.strict_reference = 1
+    # quirk Q10 switch: 1 (default) latches extras only on steps where an env reset, like the reference; 0 refreshes
+    # extras['time_outs'] every step (cfg.env.strict_reference = False)
+    s.strict_reference = 1 if getattr(cfg.env, "strict_reference", True) else 0
     s.action_scale = cfg.control.action_scale
     s.clip_actions = cfg.normalization.clip_actions
     s.p_gain = cfg.control.p_gain

@@ -246,25 +246,21 @@ class NightmareV3Env:
 class _StateRecorder:
     """Env-0 trajectory recorder (reference :261-272, replayed by ``open_custom_play.py:50-66``).
 
-    The reference appends ``(time, qpos, qvel, act)`` of env 0 every step and pickles the list whenever
-    env 0 resets.  Doing that literally would force a device->host sync per step; instead rows are
-    staged in a device ring buffer and flushed every ``flush_every`` steps (one small D2H copy), which
-    produces the same files with the same contents (file names carry the flush time)."""
+    The reference appends ``(time, qpos, qvel, act)`` of env 0 every step -- BEFORE ``reset_idx`` (:272 precedes :274),
+    so on a reset step the row holds the terminal state -- and pickles the list whenever env 0 resets, before appending
+    that step's row.  Here the step kernel itself writes env 0's pre-reset ``(done, qpos, qvel)`` into a device ring
+    (``nm_batch_set_recorder``; no extra launches), which is flushed with one small D2H copy every ``flush_every``
+    steps: same rows, same files (file names carry the flush time instead of the reset time)."""
 
     def __init__(self, env: "NightmareV3Env", log_dir: str, flush_every: int = 256):
         self.env, self.log_dir, self.k = env, log_dir, flush_every
-        self.ring = torch.zeros(flush_every, 1 + 25 + 24 + 1, device=env.device)
+        self.ring = torch.zeros(flush_every, _lib.NM_REC_STRIDE, device=env.device)
+        env._batch.set_recorder(self.ring)
         self.fill = 0
         self.rows: list = []
         self.sim_time = 0.0
 
     def after_step(self):
-        e = self.env
-        b = e._batch
-        row = self.ring[self.fill]
-        row[1:26] = b.qpos[0]
-        row[26:50] = b.qvel[0]
-        row[50] = b.done[0].to(torch.float32)
         self.fill += 1
         if self.fill == self.k:
             self.flush()
@@ -274,9 +270,10 @@ class _StateRecorder:
             return
         host = self.ring[: self.fill].cpu().numpy().astype(np.float64)
         self.fill = 0
+        self.env._batch.set_recorder(self.ring)          # restart the ring's write cursor at row 0
         for r in host:
             self.sim_time += self.env.dt          # data.time is never reset by reset_idx (quirk Q3)
-            if r[50] != 0:
+            if r[0] != 0:
                 os.makedirs(self.log_dir, exist_ok=True)
                 with open(f"{self.log_dir}/{int(time.time())}.pkl", "wb") as fh:
                     pickle.dump(self.rows, fh)

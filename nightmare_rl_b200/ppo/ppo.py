@@ -422,7 +422,9 @@ class PPO:
                 if p.grad is None:
                     p.grad = torch.zeros_like(p)
             snap = [p.detach().clone() for p in self.actor_critic.parameters()]
-            opt_state = None
+            # optimiser state that already exists (moments / step reloaded from a checkpoint by `train.py -r`, or carried over
+            # a release_graph()) must survive the warm-up steps: snapshot it, restore it afterwards
+            opt_snap = {id(v): v.detach().clone() for stt in self.optimizer.state.values() for v in stt.values() if torch.is_tensor(v)}
             side = torch.cuda.Stream(device=self.device)
             side.wait_stream(torch.cuda.current_stream(self.device))
             with torch.cuda.stream(side):               # warm-up on a side stream (allocator / cuBLAS / optimiser state)
@@ -430,7 +432,8 @@ class PPO:
                 lr_keep = self._lr_t.clone()
                 for _ in range(2):
                     self._graph_step()
-                # undo the warm-up's effect on the parameters and the schedule; Adam's moments restart from zero
+                # undo the warm-up's effect on the parameters, the schedule and Adam's state (state created by the warm-up
+                # itself restarts from zero, state that existed before continues from its values)
                 with torch.no_grad():
                     for p, q in zip(self.actor_critic.parameters(), snap):
                         p.copy_(q)
@@ -438,7 +441,10 @@ class PPO:
                     for stt in self.optimizer.state.values():
                         for k, v in stt.items():
                             if torch.is_tensor(v):
-                                v.zero_()
+                                if id(v) in opt_snap:
+                                    v.copy_(opt_snap[id(v)])
+                                else:
+                                    v.zero_()
             torch.cuda.current_stream(self.device).wait_stream(side)
             self._graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self._graph):

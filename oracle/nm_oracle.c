@@ -17,6 +17,17 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <tgmath.h>   /* sqrt/sin/cos/pow/exp/acos/fabs follow the type of `real` */
+#undef I              /* complex.h's imaginary unit, pulled in by tgmath.h */
+
+/* Arithmetic type of the restatement.  The oracle proper is fp64 (libnm_oracle.so).  The same source compiled with
+ * -DNMO_REAL=float -fsingle-precision-constant (libnm_oracle_f32.so) is the "honest fp32 implementation of the same
+ * pipeline": its deviation from the fp64 build on the lockstep suites is the arithmetic floor the fp32 CUDA kernels are
+ * measured against (tools/fp32_floor.py, profiles/r02_fp32_floor.md).  The C ABI is double in both builds. */
+#ifndef NMO_REAL
+#define NMO_REAL double
+#endif
+typedef NMO_REAL real;
 
 #define MINVAL 1e-15
 #define MAXVAL 1e10
@@ -29,24 +40,25 @@ enum { INT_EULER = 0, INT_RK4 = 1, INT_IMPLICIT = 2, INT_IMPLICITFAST = 3 };
 /* ------------------------------------------------------------------------------------------ model */
 struct nmo_model {
   unsigned char* raw;
+  void* owned[64]; int nowned;   /* model arrays converted to `real` */
   int nq, nv, nu, nbody, njnt, ngeom, nsite, nsensor, nhv, nhn;
   int integrator, solver, cone, iterations, noslip_iterations, eulerdamp;
   int planemesh_maxcon; /* contacts per plane-mesh pair (opt_int[7]; 4 when the model file predates the entry) */
-  double timestep, gravity[3], tolerance, noslip_tolerance, impratio, meaninertia;
-  const double *qpos0, *body_pos, *body_quat, *body_ipos, *body_iquat, *body_mass, *body_inertia, *body_invweight0;
+  real timestep, gravity[3], tolerance, noslip_tolerance, impratio, meaninertia;
+  const real *qpos0, *body_pos, *body_quat, *body_ipos, *body_iquat, *body_mass, *body_inertia, *body_invweight0;
   const int *body_parent, *body_rootid, *body_jntadr, *body_jntnum, *body_dofadr, *body_dofnum;
   const int *jnt_type, *jnt_body, *jnt_qposadr, *jnt_dofadr;
-  const double *jnt_pos, *jnt_axis;
+  const real *jnt_pos, *jnt_axis;
   const int *dof_body, *dof_jnt, *dof_parent;
-  const double *dof_damping, *dof_armature;
+  const real *dof_damping, *dof_armature;
   const int *act_dof, *act_ctrllimited, *act_forcelimited;
-  const double *act_gain, *act_bias, *act_gear, *act_ctrlrange, *act_forcerange;
+  const real *act_gain, *act_bias, *act_gear, *act_ctrlrange, *act_forcerange;
   const int *geom_type, *geom_body, *geom_condim, *geom_priority, *geom_plane, *geom_hull_adr, *geom_hull_num;
-  const double *geom_pos, *geom_quat, *geom_size, *geom_friction, *geom_solref, *geom_solimp, *geom_margin, *geom_gap, *geom_rbound;
+  const real *geom_pos, *geom_quat, *geom_size, *geom_friction, *geom_solref, *geom_solimp, *geom_margin, *geom_gap, *geom_rbound;
   const float* hull_vert;
   const int *hull_nbr_adr, *hull_nbr;
   const int *site_body, *sensor_site;
-  const double *site_pos, *site_size;
+  const real *site_pos, *site_size;
 };
 
 static const void* nmb_find(const unsigned char* raw, const char* name, int* code, long long* count) {
@@ -83,6 +95,21 @@ static const void* nmb_find(const unsigned char* raw, const char* name, int* cod
       return NULL;                                                            \
     }                                                                         \
   } while (0)
+/* fp64 array of the model file -> array of `real` owned by the model */
+#define GETR(field)                                                           \
+  do {                                                                        \
+    long long cnt_ = 0;                                                       \
+    const double* src_ = (const double*)nmb_find(m->raw, #field, NULL, &cnt_); \
+    if (!src_) {                                                              \
+      snprintf(err, errlen, "nmb: missing array '%s'", #field);               \
+      nmo_model_free(m);                                                      \
+      return NULL;                                                            \
+    }                                                                         \
+    real* dst_ = (real*)malloc(sizeof(real) * (size_t)(cnt_ > 0 ? cnt_ : 1)); \
+    for (long long k_ = 0; k_ < cnt_; k_++) dst_[k_] = (real)src_[k_];        \
+    m->owned[m->nowned++] = dst_;                                             \
+    m->field = dst_;                                                          \
+  } while (0)
 
 nmo_model* nmo_model_load(const char* path, char* err, int errlen) {
   char dummy[8];
@@ -113,26 +140,27 @@ nmo_model* nmo_model_load(const char* path, char* err, int errlen) {
   m->planemesh_maxcon = (noi > 7 && oi[7] >= 1 && oi[7] <= 4) ? oi[7] : 4;
   m->timestep = orl[0]; m->gravity[0] = orl[1]; m->gravity[1] = orl[2]; m->gravity[2] = orl[3];
   m->tolerance = orl[4]; m->noslip_tolerance = orl[5]; m->impratio = orl[6]; m->meaninertia = orl[7];
-  GETP(qpos0, double); GETP(body_pos, double); GETP(body_quat, double); GETP(body_ipos, double);
-  GETP(body_iquat, double); GETP(body_mass, double); GETP(body_inertia, double); GETP(body_invweight0, double);
+  GETR(qpos0); GETR(body_pos); GETR(body_quat); GETR(body_ipos);
+  GETR(body_iquat); GETR(body_mass); GETR(body_inertia); GETR(body_invweight0);
   GETP(body_parent, int); GETP(body_rootid, int); GETP(body_jntadr, int); GETP(body_jntnum, int);
   GETP(body_dofadr, int); GETP(body_dofnum, int);
   GETP(jnt_type, int); GETP(jnt_body, int); GETP(jnt_qposadr, int); GETP(jnt_dofadr, int);
-  GETP(jnt_pos, double); GETP(jnt_axis, double);
-  GETP(dof_body, int); GETP(dof_jnt, int); GETP(dof_parent, int); GETP(dof_damping, double); GETP(dof_armature, double);
+  GETR(jnt_pos); GETR(jnt_axis);
+  GETP(dof_body, int); GETP(dof_jnt, int); GETP(dof_parent, int); GETR(dof_damping); GETR(dof_armature);
   GETP(act_dof, int); GETP(act_ctrllimited, int); GETP(act_forcelimited, int);
-  GETP(act_gain, double); GETP(act_bias, double); GETP(act_gear, double); GETP(act_ctrlrange, double); GETP(act_forcerange, double);
+  GETR(act_gain); GETR(act_bias); GETR(act_gear); GETR(act_ctrlrange); GETR(act_forcerange);
   GETP(geom_type, int); GETP(geom_body, int); GETP(geom_condim, int); GETP(geom_priority, int); GETP(geom_plane, int);
   GETP(geom_hull_adr, int); GETP(geom_hull_num, int);
-  GETP(geom_pos, double); GETP(geom_quat, double); GETP(geom_size, double); GETP(geom_friction, double);
-  GETP(geom_solref, double); GETP(geom_solimp, double); GETP(geom_margin, double); GETP(geom_gap, double); GETP(geom_rbound, double);
+  GETR(geom_pos); GETR(geom_quat); GETR(geom_size); GETR(geom_friction);
+  GETR(geom_solref); GETR(geom_solimp); GETR(geom_margin); GETR(geom_gap); GETR(geom_rbound);
   GETP(hull_vert, float); GETP(hull_nbr_adr, int); GETP(hull_nbr, int);
-  GETP(site_body, int); GETP(sensor_site, int); GETP(site_pos, double); GETP(site_size, double);
+  GETP(site_body, int); GETP(sensor_site, int); GETR(site_pos); GETR(site_size);
   return m;
 }
 
 void nmo_model_free(nmo_model* m) {
   if (!m) return;
+  for (int i = 0; i < m->nowned; i++) free(m->owned[i]);
   free(m->raw);
   free(m);
 }
@@ -150,53 +178,53 @@ int nmo_model_size(const nmo_model* m, const char* w) {
 }
 
 /* ------------------------------------------------------------------------------------------ small math */
-static inline double dot3(const double* a, const double* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
-static inline void cross3(double* r, const double* a, const double* b) {
-  double x = a[1] * b[2] - a[2] * b[1], y = a[2] * b[0] - a[0] * b[2], z = a[0] * b[1] - a[1] * b[0];
+static inline real dot3(const real* a, const real* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+static inline void cross3(real* r, const real* a, const real* b) {
+  real x = a[1] * b[2] - a[2] * b[1], y = a[2] * b[0] - a[0] * b[2], z = a[0] * b[1] - a[1] * b[0];
   r[0] = x; r[1] = y; r[2] = z;
 }
-static inline double normalize3(double* v) {
-  double n = sqrt(dot3(v, v));
+static inline real normalize3(real* v) {
+  real n = sqrt(dot3(v, v));
   if (n < MINVAL) { v[0] = 1; v[1] = 0; v[2] = 0; return 0; }
   v[0] /= n; v[1] /= n; v[2] /= n;
   return n;
 }
-static inline void normalize4(double* q) {
-  double n = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+static inline void normalize4(real* q) {
+  real n = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
   if (n < MINVAL) { q[0] = 1; q[1] = q[2] = q[3] = 0; return; }
   q[0] /= n; q[1] /= n; q[2] /= n; q[3] /= n;
 }
-static inline void mul_quat(double* r, const double* a, const double* b) {
-  double w = a[0] * b[0] - a[1] * b[1] - a[2] * b[2] - a[3] * b[3];
-  double x = a[0] * b[1] + a[1] * b[0] + a[2] * b[3] - a[3] * b[2];
-  double y = a[0] * b[2] - a[1] * b[3] + a[2] * b[0] + a[3] * b[1];
-  double z = a[0] * b[3] + a[1] * b[2] - a[2] * b[1] + a[3] * b[0];
+static inline void mul_quat(real* r, const real* a, const real* b) {
+  real w = a[0] * b[0] - a[1] * b[1] - a[2] * b[2] - a[3] * b[3];
+  real x = a[0] * b[1] + a[1] * b[0] + a[2] * b[3] - a[3] * b[2];
+  real y = a[0] * b[2] - a[1] * b[3] + a[2] * b[0] + a[3] * b[1];
+  real z = a[0] * b[3] + a[1] * b[2] - a[2] * b[1] + a[3] * b[0];
   r[0] = w; r[1] = x; r[2] = y; r[3] = z;
 }
-static inline void quat2mat(double* m, const double* q) {
-  double w = q[0], x = q[1], y = q[2], z = q[3];
+static inline void quat2mat(real* m, const real* q) {
+  real w = q[0], x = q[1], y = q[2], z = q[3];
   m[0] = w * w + x * x - y * y - z * z; m[1] = 2 * (x * y - w * z); m[2] = 2 * (x * z + w * y);
   m[3] = 2 * (x * y + w * z); m[4] = w * w - x * x + y * y - z * z; m[5] = 2 * (y * z - w * x);
   m[6] = 2 * (x * z - w * y); m[7] = 2 * (y * z + w * x); m[8] = w * w - x * x - y * y + z * z;
 }
-static inline void mat_vec3(double* r, const double* m, const double* v) {
-  double x = m[0] * v[0] + m[1] * v[1] + m[2] * v[2];
-  double y = m[3] * v[0] + m[4] * v[1] + m[5] * v[2];
-  double z = m[6] * v[0] + m[7] * v[1] + m[8] * v[2];
+static inline void mat_vec3(real* r, const real* m, const real* v) {
+  real x = m[0] * v[0] + m[1] * v[1] + m[2] * v[2];
+  real y = m[3] * v[0] + m[4] * v[1] + m[5] * v[2];
+  real z = m[6] * v[0] + m[7] * v[1] + m[8] * v[2];
   r[0] = x; r[1] = y; r[2] = z;
 }
-static inline void axisangle2quat(double* q, const double* axis, double angle) {
-  double s = sin(0.5 * angle);
+static inline void axisangle2quat(real* q, const real* axis, real angle) {
+  real s = sin(0.5 * angle);
   q[0] = cos(0.5 * angle); q[1] = axis[0] * s; q[2] = axis[1] * s; q[3] = axis[2] * s;
 }
 /* rotate vector by quaternion (≙ mju_rotVecQuat, env.py:217-219) */
-static inline void rot_vec_quat(double* r, const double* v, const double* q) {
-  double m[9];
+static inline void rot_vec_quat(real* r, const real* v, const real* q) {
+  real m[9];
   quat2mat(m, q);
   mat_vec3(r, m, v);
 }
 /* spatial inertia (10 numbers: Ixx Iyy Izz Ixy Ixz Iyz, m*r(3), m) times motion vector [w; v] */
-static void mul_inert_vec(double* res, const double* i, const double* v) {
+static void mul_inert_vec(real* res, const real* i, const real* v) {
   res[0] = i[0] * v[0] + i[3] * v[1] + i[4] * v[2] - i[8] * v[4] + i[7] * v[5];
   res[1] = i[3] * v[0] + i[1] * v[1] + i[5] * v[2] + i[8] * v[3] - i[6] * v[5];
   res[2] = i[4] * v[0] + i[5] * v[1] + i[2] * v[2] - i[7] * v[3] + i[6] * v[4];
@@ -205,8 +233,8 @@ static void mul_inert_vec(double* res, const double* i, const double* v) {
   res[5] = i[7] * v[0] - i[6] * v[1] + i[9] * v[5];
 }
 /* motion x motion */
-static void cross_motion(double* r, const double* vel, const double* v) {
-  double a[3], b[3], c[3];
+static void cross_motion(real* r, const real* vel, const real* v) {
+  real a[3], b[3], c[3];
   cross3(a, vel, v);          /* w x v_ang */
   cross3(b, vel, v + 3);      /* w x v_lin */
   cross3(c, vel + 3, v);      /* vlin x v_ang */
@@ -214,8 +242,8 @@ static void cross_motion(double* r, const double* vel, const double* v) {
   r[3] = b[0] + c[0]; r[4] = b[1] + c[1]; r[5] = b[2] + c[2];
 }
 /* motion x* force */
-static void cross_force(double* r, const double* vel, const double* f) {
-  double a[3], b[3], c[3];
+static void cross_force(real* r, const real* vel, const real* f) {
+  real a[3], b[3], c[3];
   cross3(a, vel, f);          /* w x f_ang */
   cross3(b, vel + 3, f + 3);  /* v x f_lin */
   cross3(c, vel, f + 3);      /* w x f_lin */
@@ -225,54 +253,85 @@ static void cross_force(double* r, const double* vel, const double* f) {
 
 /* ------------------------------------------------------------------------------------------ per-env data */
 typedef struct {
-  double dist, pos[3], frame[9], mu, solref[2], solimp[5], margin;
+  real dist, pos[3], frame[9], mu, solref[2], solimp[5], margin;
   int geom1, geom2, body1, body2, vert, efc_address, dim;
 } contact_t;
 
 typedef struct {
   /* state */
-  double *qpos, *qvel, *qacc_warmstart, *ctrl, time;
+  real *qpos, *qvel, *qacc_warmstart, *ctrl, time;
   /* position-dependent */
-  double *xpos, *xquat, *xmat, *xipos, *ximat, *xanchor, *xaxis, *site_xpos, *subtree_com, *cinert, *crb, *cdof;
-  double *M, *L;               /* dense mass matrix and its Cholesky factor (lower) */
-  double *MH, *LH;             /* M - h*qDeriv of the implicit velocity update and its factor */
+  real *xpos, *xquat, *xmat, *xipos, *ximat, *xanchor, *xaxis, *site_xpos, *subtree_com, *cinert, *crb, *cdof;
+  real *M, *L;               /* dense mass matrix and its Cholesky factor (lower) */
+  real *MH, *LH;             /* M - h*qDeriv of the implicit velocity update and its factor */
   /* velocity-dependent */
-  double *cvel, *cdof_dot, *qfrc_bias, *qfrc_passive, *qfrc_actuator, *qfrc_smooth, *qacc_smooth;
-  double *qfrc_constraint, *qacc, *act_force;
+  real *cvel, *cdof_dot, *qfrc_bias, *qfrc_passive, *qfrc_actuator, *qfrc_smooth, *qacc_smooth;
+  real *qfrc_constraint, *qacc, *act_force;
   /* contacts / constraints */
   int ncon, nefc;
   contact_t con[NMO_MAXCON];
-  double *efc_J, *efc_pos, *efc_margin, *efc_diagApprox, *efc_R, *efc_D, *efc_aref, *efc_vel, *efc_b, *efc_force, *efc_AR;
+  real *efc_J, *efc_pos, *efc_margin, *efc_diagApprox, *efc_R, *efc_D, *efc_aref, *efc_vel, *efc_b, *efc_force, *efc_AR;
   int solver_niter, noslip_niter, warm_used, nwarn;
-  double* sensordata;
-  double* scratch;   /* >= 8*nv + MAXEFC*nv */
+  real* sensordata;
+  real* scratch;   /* >= 8*nv + MAXEFC*nv */
 } data_t;
 
 #define MAXEFC (4 * NMO_MAXCON)
 
 /* env layer carry state (envs/nightmare_v3_env.py:56-97) */
 typedef struct {
-  double actions[18], prev_actions[18], dof_pos[18], dof_vel[18], commands[3];
-  double base_lin_vel[3], base_ang_vel[3], projected_gravity[3], base_height;
-  double tibia_f[6], feet_f[6], body_f, dof_acc[18];
-  double feet_air_time[6];
+  real actions[18], prev_actions[18], dof_pos[18], dof_vel[18], commands[3];
+  real base_lin_vel[3], base_ang_vel[3], projected_gravity[3], base_height;
+  real tibia_f[6], feet_f[6], body_f, dof_acc[18];
+  real feet_air_time[6];
   int last_contacts[6], last_contacts_filt[6];
-  double episode_sums[NMO_NREW], sums_at_reset[NMO_NREW];
+  real episode_sums[NMO_NREW], sums_at_reset[NMO_NREW];
   int64_t ep_len;
   int reset_buf, time_out;
 } envstate_t;
+
+/* nmo_envcfg (double, C ABI) converted to the arithmetic type */
+typedef struct {
+  int decimation, num_actions, tibia_contact_mode, body_contact_mode, add_noise, resample_period, strict_reference;
+  real action_scale, clip_actions, p_gain, clip_obs;
+  real default_pos[18];
+  real obs_lin_vel, obs_ang_vel, obs_dof_pos, obs_dof_vel;
+  real max_lin_vel_x, max_ang_vel, max_episode_length, max_episode_length_s;
+  real termination_contact_force, tibia_max_contact_force, body_max_contact_force;
+  real tracking_sigma, base_height_target, max_contact_force, dt;
+  real rew_scale[NMO_NREW];
+  real noise_vec[66];
+} cfg_t;
+
+static void cfg_convert(cfg_t* o, const nmo_envcfg* c) {
+  memset(o, 0, sizeof(*o));
+  o->decimation = c->decimation; o->num_actions = c->num_actions; o->tibia_contact_mode = c->tibia_contact_mode;
+  o->body_contact_mode = c->body_contact_mode; o->add_noise = c->add_noise; o->resample_period = c->resample_period;
+  o->strict_reference = c->strict_reference;
+  o->action_scale = (real)c->action_scale; o->clip_actions = (real)c->clip_actions; o->p_gain = (real)c->p_gain; o->clip_obs = (real)c->clip_obs;
+  for (int k = 0; k < 18; k++) o->default_pos[k] = (real)c->default_pos[k];
+  o->obs_lin_vel = (real)c->obs_lin_vel; o->obs_ang_vel = (real)c->obs_ang_vel; o->obs_dof_pos = (real)c->obs_dof_pos; o->obs_dof_vel = (real)c->obs_dof_vel;
+  o->max_lin_vel_x = (real)c->max_lin_vel_x; o->max_ang_vel = (real)c->max_ang_vel;
+  o->max_episode_length = (real)c->max_episode_length; o->max_episode_length_s = (real)c->max_episode_length_s;
+  o->termination_contact_force = (real)c->termination_contact_force; o->tibia_max_contact_force = (real)c->tibia_max_contact_force;
+  o->body_max_contact_force = (real)c->body_max_contact_force;
+  o->tracking_sigma = (real)c->tracking_sigma; o->base_height_target = (real)c->base_height_target; o->max_contact_force = (real)c->max_contact_force;
+  o->dt = (real)c->dt;
+  for (int k = 0; k < NMO_NREW; k++) o->rew_scale[k] = (real)c->rew_scale[k];
+  for (int k = 0; k < 66; k++) o->noise_vec[k] = (real)c->noise_vec[k];
+}
 
 struct nmo_batch {
   const nmo_model* m;
   int n;
   uint64_t seed;
-  nmo_envcfg cfg;
+  cfg_t cfg;
   data_t* d;
   envstate_t* e;
   int64_t step_counter;
 };
 
-static double* dalloc(size_t n) { return (double*)calloc(n ? n : 1, sizeof(double)); }
+static real* dalloc(size_t n) { return (real*)calloc(n ? n : 1, sizeof(real)); }
 
 static void data_init(const nmo_model* m, data_t* d) {
   int nv = m->nv, nb = m->nbody;
@@ -291,11 +350,11 @@ static void data_init(const nmo_model* m, data_t* d) {
   d->efc_force = dalloc(MAXEFC); d->efc_AR = dalloc((size_t)MAXEFC * MAXEFC);
   d->sensordata = dalloc(m->nsensor);
   d->scratch = dalloc(16 * nv + (size_t)MAXEFC * nv + 16 * nb);
-  memcpy(d->qpos, m->qpos0, sizeof(double) * m->nq);
+  memcpy(d->qpos, m->qpos0, sizeof(real) * m->nq);
 }
 
 static void data_free(data_t* d) {
-  double** p[] = {&d->qpos, &d->qvel, &d->qacc_warmstart, &d->ctrl, &d->xpos, &d->xquat, &d->xmat, &d->xipos, &d->ximat,
+  real** p[] = {&d->qpos, &d->qvel, &d->qacc_warmstart, &d->ctrl, &d->xpos, &d->xquat, &d->xmat, &d->xipos, &d->ximat,
                   &d->xanchor, &d->xaxis, &d->site_xpos, &d->subtree_com, &d->cinert, &d->crb, &d->cdof, &d->M, &d->L, &d->MH, &d->LH,
                   &d->cvel, &d->cdof_dot, &d->qfrc_bias, &d->qfrc_passive, &d->qfrc_actuator, &d->qfrc_smooth,
                   &d->qacc_smooth, &d->qfrc_constraint, &d->qacc, &d->act_force, &d->efc_J, &d->efc_pos, &d->efc_margin,
@@ -306,38 +365,38 @@ static void data_free(data_t* d) {
 
 /* ------------------------------------------------------------------------------------------ P1 kinematics */
 static void kinematics(const nmo_model* m, data_t* d) {
-  double* xpos = d->xpos; double* xquat = d->xquat; double* xmat = d->xmat;
+  real* xpos = d->xpos; real* xquat = d->xquat; real* xmat = d->xmat;
   xpos[0] = xpos[1] = xpos[2] = 0;
   xquat[0] = 1; xquat[1] = xquat[2] = xquat[3] = 0;
   quat2mat(xmat, xquat);
-  memset(d->xipos, 0, 3 * sizeof(double));
+  memset(d->xipos, 0, 3 * sizeof(real));
   quat2mat(d->ximat, xquat);
   for (int i = 1; i < m->nbody; i++) {
     int pid = m->body_parent[i], ja = m->body_jntadr[i], jn = m->body_jntnum[i];
-    double pos[3], quat[4];
+    real pos[3], quat[4];
     if (jn == 1 && m->jnt_type[ja] == JNT_FREE) {
       int qa = m->jnt_qposadr[ja];
-      memcpy(pos, d->qpos + qa, 3 * sizeof(double));
-      memcpy(quat, d->qpos + qa + 3, 4 * sizeof(double));
+      memcpy(pos, d->qpos + qa, 3 * sizeof(real));
+      memcpy(quat, d->qpos + qa + 3, 4 * sizeof(real));
       normalize4(quat);
-      memcpy(d->xanchor + 3 * ja, pos, 3 * sizeof(double));
+      memcpy(d->xanchor + 3 * ja, pos, 3 * sizeof(real));
       d->xaxis[3 * ja] = 0; d->xaxis[3 * ja + 1] = 0; d->xaxis[3 * ja + 2] = 1;
     } else {
-      double t[3];
+      real t[3];
       mat_vec3(t, xmat + 9 * pid, m->body_pos + 3 * i);
       for (int k = 0; k < 3; k++) pos[k] = xpos[3 * pid + k] + t[k];
       mul_quat(quat, xquat + 4 * pid, m->body_quat + 4 * i);
       for (int j = ja; j < ja + jn; j++) {
-        double mat[9], anchor[3], axis[3];
+        real mat[9], anchor[3], axis[3];
         quat2mat(mat, quat);
         mat_vec3(anchor, mat, m->jnt_pos + 3 * j);
         for (int k = 0; k < 3; k++) anchor[k] += pos[k];
         mat_vec3(axis, mat, m->jnt_axis + 3 * j);
         memcpy(d->xanchor + 3 * j, anchor, sizeof(anchor));
         memcpy(d->xaxis + 3 * j, axis, sizeof(axis));
-        double q = d->qpos[m->jnt_qposadr[j]] - m->qpos0[m->jnt_qposadr[j]];
+        real q = d->qpos[m->jnt_qposadr[j]] - m->qpos0[m->jnt_qposadr[j]];
         if (m->jnt_type[j] == JNT_HINGE) {
-          double qloc[4], qn[4], off[3];
+          real qloc[4], qn[4], off[3];
           axisangle2quat(qloc, m->jnt_axis + 3 * j, q);
           mul_quat(qn, quat, qloc);
           memcpy(quat, qn, sizeof(qn));
@@ -353,7 +412,7 @@ static void kinematics(const nmo_model* m, data_t* d) {
     memcpy(xpos + 3 * i, pos, sizeof(pos));
     memcpy(xquat + 4 * i, quat, sizeof(quat));
     quat2mat(xmat + 9 * i, quat);
-    double t[3], qi[4];
+    real t[3], qi[4];
     mat_vec3(t, xmat + 9 * i, m->body_ipos + 3 * i);
     for (int k = 0; k < 3; k++) d->xipos[3 * i + k] = pos[k] + t[k];
     mul_quat(qi, quat, m->body_iquat + 4 * i);
@@ -361,7 +420,7 @@ static void kinematics(const nmo_model* m, data_t* d) {
   }
   for (int s = 0; s < m->nsite; s++) {
     int b = m->site_body[s];
-    double t[3];
+    real t[3];
     mat_vec3(t, xmat + 9 * b, m->site_pos + 3 * s);
     for (int k = 0; k < 3; k++) d->site_xpos[3 * s + k] = xpos[3 * b + k] + t[k];
   }
@@ -370,7 +429,7 @@ static void kinematics(const nmo_model* m, data_t* d) {
 /* ------------------------------------------------------------------------------------------ P2 comPos */
 static void com_pos(const nmo_model* m, data_t* d) {
   int nb = m->nbody;
-  double* smass = d->scratch;
+  real* smass = d->scratch;
   for (int i = 0; i < nb; i++) {
     smass[i] = m->body_mass[i];
     for (int k = 0; k < 3; k++) d->subtree_com[3 * i + k] = m->body_mass[i] * d->xipos[3 * i + k];
@@ -381,16 +440,16 @@ static void com_pos(const nmo_model* m, data_t* d) {
     for (int k = 0; k < 3; k++) d->subtree_com[3 * p + k] += d->subtree_com[3 * i + k];
   }
   for (int i = 0; i < nb; i++) {
-    if (smass[i] < MINVAL) memcpy(d->subtree_com + 3 * i, d->xipos + 3 * i, 3 * sizeof(double));
+    if (smass[i] < MINVAL) memcpy(d->subtree_com + 3 * i, d->xipos + 3 * i, 3 * sizeof(real));
     else for (int k = 0; k < 3; k++) d->subtree_com[3 * i + k] /= smass[i];
   }
   for (int i = 1; i < nb; i++) {
-    const double* R = d->ximat + 9 * i;
-    const double* I = m->body_inertia + 3 * i;
-    const double* c = d->subtree_com + 3 * m->body_rootid[i];
-    double mass = m->body_mass[i], r[3];
+    const real* R = d->ximat + 9 * i;
+    const real* I = m->body_inertia + 3 * i;
+    const real* c = d->subtree_com + 3 * m->body_rootid[i];
+    real mass = m->body_mass[i], r[3];
     for (int k = 0; k < 3; k++) r[k] = d->xipos[3 * i + k] - c[k];
-    double* ci = d->cinert + 10 * i;
+    real* ci = d->cinert + 10 * i;
     /* R diag(I) R^T */
     ci[0] = R[0] * R[0] * I[0] + R[1] * R[1] * I[1] + R[2] * R[2] * I[2];
     ci[1] = R[3] * R[3] * I[0] + R[4] * R[4] * I[1] + R[5] * R[5] * I[2];
@@ -408,47 +467,47 @@ static void com_pos(const nmo_model* m, data_t* d) {
     ci[6] = mass * r[0]; ci[7] = mass * r[1]; ci[8] = mass * r[2];
     ci[9] = mass;
   }
-  memset(d->cinert, 0, 10 * sizeof(double));
+  memset(d->cinert, 0, 10 * sizeof(real));
   for (int j = 0; j < m->njnt; j++) {
     int b = m->jnt_body[j], da = m->jnt_dofadr[j];
-    const double* c = d->subtree_com + 3 * m->body_rootid[b];
-    double off[3];
+    const real* c = d->subtree_com + 3 * m->body_rootid[b];
+    real off[3];
     for (int k = 0; k < 3; k++) off[k] = c[k] - d->xanchor[3 * j + k];
     if (m->jnt_type[j] == JNT_FREE) {
       for (int k = 0; k < 3; k++) {
-        double* cd = d->cdof + 6 * (da + k);
-        memset(cd, 0, 6 * sizeof(double));
+        real* cd = d->cdof + 6 * (da + k);
+        memset(cd, 0, 6 * sizeof(real));
         cd[3 + k] = 1;
       }
       for (int k = 0; k < 3; k++) {
-        double* cd = d->cdof + 6 * (da + 3 + k);
-        double ax[3] = {d->xmat[9 * b + k], d->xmat[9 * b + 3 + k], d->xmat[9 * b + 6 + k]};
+        real* cd = d->cdof + 6 * (da + 3 + k);
+        real ax[3] = {d->xmat[9 * b + k], d->xmat[9 * b + 3 + k], d->xmat[9 * b + 6 + k]};
         memcpy(cd, ax, sizeof(ax));
         cross3(cd + 3, ax, off);
       }
     } else if (m->jnt_type[j] == JNT_HINGE) {
-      double* cd = d->cdof + 6 * da;
-      memcpy(cd, d->xaxis + 3 * j, 3 * sizeof(double));
+      real* cd = d->cdof + 6 * da;
+      memcpy(cd, d->xaxis + 3 * j, 3 * sizeof(real));
       cross3(cd + 3, d->xaxis + 3 * j, off);
     } else { /* slide */
-      double* cd = d->cdof + 6 * da;
+      real* cd = d->cdof + 6 * da;
       cd[0] = cd[1] = cd[2] = 0;
-      memcpy(cd + 3, d->xaxis + 3 * j, 3 * sizeof(double));
+      memcpy(cd + 3, d->xaxis + 3 * j, 3 * sizeof(real));
     }
   }
 }
 
 /* ------------------------------------------------------------------------------------------ P3 CRBA + factor */
-static int cholesky(double* L, const double* A, int n) {
-  memcpy(L, A, sizeof(double) * n * n);
+static int cholesky(real* L, const real* A, int n) {
+  memcpy(L, A, sizeof(real) * n * n);
   for (int j = 0; j < n; j++) {
-    double s = L[j * n + j];
+    real s = L[j * n + j];
     for (int k = 0; k < j; k++) s -= L[j * n + k] * L[j * n + k];
     if (s < MINVAL) return -1;
     s = sqrt(s);
     L[j * n + j] = s;
     for (int i = j + 1; i < n; i++) {
-      double t = L[i * n + j];
+      real t = L[i * n + j];
       for (int k = 0; k < j; k++) t -= L[i * n + k] * L[j * n + k];
       L[i * n + j] = t / s;
     }
@@ -456,14 +515,14 @@ static int cholesky(double* L, const double* A, int n) {
   }
   return 0;
 }
-static void chol_solve(const double* L, int n, double* x) {
+static void chol_solve(const real* L, int n, real* x) {
   for (int i = 0; i < n; i++) {
-    double s = x[i];
+    real s = x[i];
     for (int k = 0; k < i; k++) s -= L[i * n + k] * x[k];
     x[i] = s / L[i * n + i];
   }
   for (int i = n - 1; i >= 0; i--) {
-    double s = x[i];
+    real s = x[i];
     for (int k = i + 1; k < n; k++) s -= L[k * n + i] * x[k];
     x[i] = s / L[i * n + i];
   }
@@ -471,17 +530,17 @@ static void chol_solve(const double* L, int n, double* x) {
 
 static void crb(const nmo_model* m, data_t* d) {
   int nv = m->nv, nb = m->nbody;
-  memcpy(d->crb, d->cinert, sizeof(double) * 10 * nb);
+  memcpy(d->crb, d->cinert, sizeof(real) * 10 * nb);
   for (int i = nb - 1; i > 0; i--) {
     int p = m->body_parent[i];
     if (p > 0) for (int k = 0; k < 10; k++) d->crb[10 * p + k] += d->crb[10 * i + k];
   }
-  memset(d->M, 0, sizeof(double) * nv * nv);
+  memset(d->M, 0, sizeof(real) * nv * nv);
   for (int i = 0; i < nv; i++) {
-    double buf[6];
+    real buf[6];
     mul_inert_vec(buf, d->crb + 10 * m->dof_body[i], d->cdof + 6 * i);
     for (int j = i; j >= 0; j = m->dof_parent[j]) {
-      double s = 0;
+      real s = 0;
       for (int k = 0; k < 6; k++) s += d->cdof[6 * j + k] * buf[k];
       d->M[i * nv + j] = d->M[j * nv + i] = s;
     }
@@ -491,13 +550,13 @@ static void crb(const nmo_model* m, data_t* d) {
 }
 
 /* ------------------------------------------------------------------------------------------ P4 collision */
-static void make_frame(double* f) {
+static void make_frame(real* f) {
   /* f[0:3] = normal; build tangents (≙ mju_makeFrame) */
   normalize3(f);
-  double* y = f + 3;
+  real* y = f + 3;
   y[0] = 0; y[1] = 0; y[2] = 0;
   if (f[1] < 0.5 && f[1] > -0.5) y[1] = 1; else y[2] = 1;
-  double dd = dot3(f, y);
+  real dd = dot3(f, y);
   for (int k = 0; k < 3; k++) y[k] -= dd * f[k];
   normalize3(y);
   cross3(f + 6, f, y);
@@ -505,7 +564,7 @@ static void make_frame(double* f) {
 
 static void mix_params(const nmo_model* m, int g1, int g2, contact_t* c) {
   int p1 = m->geom_priority[g1], p2 = m->geom_priority[g2];
-  const double *f1 = m->geom_friction + 3 * g1, *f2 = m->geom_friction + 3 * g2;
+  const real *f1 = m->geom_friction + 3 * g1, *f2 = m->geom_friction + 3 * g2;
   if (p1 == p2) {
     c->mu = f1[0] > f2[0] ? f1[0] : f2[0];
     c->dim = m->geom_condim[g1] > m->geom_condim[g2] ? m->geom_condim[g1] : m->geom_condim[g2];
@@ -515,8 +574,8 @@ static void mix_params(const nmo_model* m, int g1, int g2, contact_t* c) {
     int g = p1 > p2 ? g1 : g2;
     c->mu = m->geom_friction[3 * g];
     c->dim = m->geom_condim[g];
-    memcpy(c->solref, m->geom_solref + 2 * g, 2 * sizeof(double));
-    memcpy(c->solimp, m->geom_solimp + 5 * g, 5 * sizeof(double));
+    memcpy(c->solref, m->geom_solref + 2 * g, 2 * sizeof(real));
+    memcpy(c->solimp, m->geom_solimp + 5 * g, 5 * sizeof(real));
   }
   c->margin = (m->geom_margin[g1] > m->geom_margin[g2] ? m->geom_margin[g1] : m->geom_margin[g2]) -
               (m->geom_gap[g1] > m->geom_gap[g2] ? m->geom_gap[g1] : m->geom_gap[g2]);
@@ -529,27 +588,27 @@ static void collision(const nmo_model* m, data_t* d) {
     if (pg < 0) continue;
     int pb = m->geom_body[pg], b = m->geom_body[g];
     /* plane frame in world */
-    double pq[4], pm[9], ppos[3], t[3];
+    real pq[4], pm[9], ppos[3], t[3];
     mul_quat(pq, d->xquat + 4 * pb, m->geom_quat + 4 * pg);
     quat2mat(pm, pq);
     mat_vec3(t, d->xmat + 9 * pb, m->geom_pos + 3 * pg);
     for (int k = 0; k < 3; k++) ppos[k] = d->xpos[3 * pb + k] + t[k];
-    double n[3] = {pm[2], pm[5], pm[8]};
-    double margin = m->geom_margin[g] > m->geom_margin[pg] ? m->geom_margin[g] : m->geom_margin[pg];
-    const double* R = d->xmat + 9 * b;
-    const double* p = d->xpos + 3 * b;
+    real n[3] = {pm[2], pm[5], pm[8]};
+    real margin = m->geom_margin[g] > m->geom_margin[pg] ? m->geom_margin[g] : m->geom_margin[pg];
+    const real* R = d->xmat + 9 * b;
+    const real* p = d->xpos + 3 * b;
     if (m->geom_type[g] == GEOM_MESH) {
       int adr = m->geom_hull_adr[g], num = m->geom_hull_num[g];
       /* support vertex along -n: exhaustive argmin of n.(v - ppos), lowest index wins ties
          (MuJoCo hill-climbs the hull graph; identical on a convex hull except for exact ties) */
       int best = -1;
-      double bestd = 0, bestw[3] = {0, 0, 0};
+      real bestd = 0, bestw[3] = {0, 0, 0};
       for (int v = 0; v < num; v++) {
-        double lv[3] = {m->hull_vert[3 * (adr + v)], m->hull_vert[3 * (adr + v) + 1], m->hull_vert[3 * (adr + v) + 2]};
-        double w[3];
+        real lv[3] = {m->hull_vert[3 * (adr + v)], m->hull_vert[3 * (adr + v) + 1], m->hull_vert[3 * (adr + v) + 2]};
+        real w[3];
         mat_vec3(w, R, lv);
         for (int k = 0; k < 3; k++) w[k] += p[k];
-        double dist = (w[0] - ppos[0]) * n[0] + (w[1] - ppos[1]) * n[1] + (w[2] - ppos[2]) * n[2];
+        real dist = (w[0] - ppos[0]) * n[0] + (w[1] - ppos[1]) * n[1] + (w[2] - ppos[2]) * n[2];
         if (best < 0 || dist < bestd) { best = v; bestd = dist; memcpy(bestw, w, sizeof(w)); }
       }
       if (best < 0 || bestd > margin) continue;
@@ -560,20 +619,20 @@ static void collision(const nmo_model* m, data_t* d) {
         int hi = pass == 0 ? 1 : m->hull_nbr_adr[adr + best + 1];
         for (int e = lo; e < hi && cnt < m->planemesh_maxcon && d->ncon < NMO_MAXCON; e++) {
           int v = pass == 0 ? best : m->hull_nbr[e];
-          double w[3], dist;
+          real w[3], dist;
           if (pass == 0) { memcpy(w, bestw, sizeof(w)); dist = bestd; }
           else {
-            double lv[3] = {m->hull_vert[3 * (adr + v)], m->hull_vert[3 * (adr + v) + 1], m->hull_vert[3 * (adr + v) + 2]};
+            real lv[3] = {m->hull_vert[3 * (adr + v)], m->hull_vert[3 * (adr + v) + 1], m->hull_vert[3 * (adr + v) + 2]};
             mat_vec3(w, R, lv);
             for (int k = 0; k < 3; k++) w[k] += p[k];
             dist = (w[0] - ppos[0]) * n[0] + (w[1] - ppos[1]) * n[1] + (w[2] - ppos[2]) * n[2];
             if (dist > margin) continue;
           }
-          double cp[3];
+          real cp[3];
           for (int k = 0; k < 3; k++) cp[k] = w[k] - 0.5 * dist * n[k];
           int tooclose = 0;
           for (int c = first; c < first + cnt; c++) {
-            double dx = d->con[c].pos[0] - cp[0], dy = d->con[c].pos[1] - cp[1], dz = d->con[c].pos[2] - cp[2];
+            real dx = d->con[c].pos[0] - cp[0], dy = d->con[c].pos[1] - cp[1], dz = d->con[c].pos[2] - cp[2];
             if (sqrt(dx * dx + dy * dy + dz * dz) < TOLPLANEMESH * m->geom_rbound[g]) tooclose = 1;
           }
           if (tooclose) continue;
@@ -588,10 +647,10 @@ static void collision(const nmo_model* m, data_t* d) {
         }
       }
     } else if (m->geom_type[g] == GEOM_SPHERE) {
-      double gc[3];
+      real gc[3];
       mat_vec3(gc, R, m->geom_pos + 3 * g);
       for (int k = 0; k < 3; k++) gc[k] += p[k];
-      double dist = (gc[0] - ppos[0]) * n[0] + (gc[1] - ppos[1]) * n[1] + (gc[2] - ppos[2]) * n[2] - m->geom_size[3 * g];
+      real dist = (gc[0] - ppos[0]) * n[0] + (gc[1] - ppos[1]) * n[1] + (gc[2] - ppos[2]) * n[2] - m->geom_size[3 * g];
       if (dist > margin || d->ncon >= NMO_MAXCON) continue;
       contact_t* c = d->con + d->ncon++;
       c->dist = dist;
@@ -605,34 +664,34 @@ static void collision(const nmo_model* m, data_t* d) {
 }
 
 /* ------------------------------------------------------------------------------------------ P5 constraints */
-static void jac_point(const nmo_model* m, const data_t* d, int body, const double* point, double* jacp /*3 x nv*/) {
+static void jac_point(const nmo_model* m, const data_t* d, int body, const real* point, real* jacp /*3 x nv*/) {
   int nv = m->nv;
-  memset(jacp, 0, sizeof(double) * 3 * nv);
+  memset(jacp, 0, sizeof(real) * 3 * nv);
   if (body <= 0) return;
-  double off[3];
-  const double* c = d->subtree_com + 3 * m->body_rootid[body];
+  real off[3];
+  const real* c = d->subtree_com + 3 * m->body_rootid[body];
   for (int k = 0; k < 3; k++) off[k] = point[k] - c[k];
   int b = body;
   while (b > 0 && m->body_dofnum[b] == 0) b = m->body_parent[b];
   if (b <= 0) return;
   for (int i = m->body_dofadr[b] + m->body_dofnum[b] - 1; i >= 0; i = m->dof_parent[i]) {
-    double t[3];
+    real t[3];
     cross3(t, d->cdof + 6 * i, off);
     for (int k = 0; k < 3; k++) jacp[k * nv + i] = d->cdof[6 * i + 3 + k] + t[k];
   }
 }
 
-static double impedance(const double* solimp, double pos, double margin) {
-  double dmin = solimp[0], dmax = solimp[1], width = solimp[2], mid = solimp[3], power = solimp[4];
+static real impedance(const real* solimp, real pos, real margin) {
+  real dmin = solimp[0], dmax = solimp[1], width = solimp[2], mid = solimp[3], power = solimp[4];
   if (dmin < 0.0001) dmin = 0.0001; if (dmin > 0.9999) dmin = 0.9999;
   if (dmax < 0.0001) dmax = 0.0001; if (dmax > 0.9999) dmax = 0.9999;
   if (mid < 0.0001) mid = 0.0001; if (mid > 0.9999) mid = 0.9999;
   if (power < 1) power = 1;
   if (dmin == dmax || width <= MINVAL) return 0.5 * (dmin + dmax);
-  double x = fabs((pos - margin) / width);
+  real x = fabs((pos - margin) / width);
   if (x >= 1) return dmax;
   if (x <= 0) return dmin;
-  double y;
+  real y;
   if (power == 1) y = x;
   else if (x <= mid) y = pow(x, power) / pow(mid, power - 1);
   else y = 1 - pow(1 - x, power) / pow(1 - mid, power - 1);
@@ -642,8 +701,8 @@ static double impedance(const double* solimp, double pos, double margin) {
 static void make_constraint(const nmo_model* m, data_t* d) {
   int nv = m->nv;
   d->nefc = 0;
-  double* jac1 = d->scratch;            /* 3 x nv */
-  double* jac2 = d->scratch + 3 * nv;   /* 3 x nv */
+  real* jac1 = d->scratch;            /* 3 x nv */
+  real* jac2 = d->scratch + 3 * nv;   /* 3 x nv */
   for (int ci = 0; ci < d->ncon; ci++) {
     contact_t* c = d->con + ci;
     c->efc_address = -1;
@@ -651,18 +710,18 @@ static void make_constraint(const nmo_model* m, data_t* d) {
     c->efc_address = d->nefc;
     jac_point(m, d, c->body1, c->pos, jac1);
     jac_point(m, d, c->body2, c->pos, jac2);
-    double Jc[3][64];   /* rows in contact frame; nv <= 64 */
+    real Jc[3][64];   /* rows in contact frame; nv <= 64 */
     for (int r = 0; r < 3; r++)
       for (int i = 0; i < nv; i++) {
-        double s = 0;
+        real s = 0;
         for (int k = 0; k < 3; k++) s += c->frame[3 * r + k] * (jac2[k * nv + i] - jac1[k * nv + i]);
         Jc[r][i] = s;
       }
-    double tran = m->body_invweight0[2 * c->body1] + m->body_invweight0[2 * c->body2];
+    real tran = m->body_invweight0[2 * c->body1] + m->body_invweight0[2 * c->body2];
     for (int r = 0; r < 4; r++) {
       int e = d->nefc++;
       int t = 1 + r / 2;
-      double sgn = (r % 2 == 0) ? 1.0 : -1.0;
+      real sgn = (r % 2 == 0) ? 1.0 : -1.0;
       for (int i = 0; i < nv; i++) d->efc_J[e * nv + i] = Jc[0][i] + sgn * c->mu * Jc[t][i];
       d->efc_pos[e] = c->dist;
       d->efc_margin[e] = c->margin;
@@ -674,9 +733,9 @@ static void make_constraint(const nmo_model* m, data_t* d) {
     contact_t* c = d->con + ci;
     if (c->efc_address < 0) continue;
     int e0 = c->efc_address;
-    double tc = c->solref[0], dr = c->solref[1], dmax = c->solimp[1];
+    real tc = c->solref[0], dr = c->solref[1], dmax = c->solimp[1];
     if (dmax < 0.0001) dmax = 0.0001; if (dmax > 0.9999) dmax = 0.9999;
-    double K, B;
+    real K, B;
     if (tc > 0) {
       if (tc < 2 * m->timestep) tc = 2 * m->timestep;   /* refsafe */
       K = 1.0 / (dmax * dmax * tc * tc * dr * dr);
@@ -687,18 +746,18 @@ static void make_constraint(const nmo_model* m, data_t* d) {
     }
     for (int r = 0; r < 4; r++) {
       int e = e0 + r;
-      double imp = impedance(c->solimp, d->efc_pos[e], d->efc_margin[e]);
-      double R = (1 - imp) * d->efc_diagApprox[e] / imp;
+      real imp = impedance(c->solimp, d->efc_pos[e], d->efc_margin[e]);
+      real R = (1 - imp) * d->efc_diagApprox[e] / imp;
       if (R < MINVAL) R = MINVAL;
       d->efc_R[e] = R;
-      double vel = 0;
+      real vel = 0;
       for (int i = 0; i < nv; i++) vel += d->efc_J[e * nv + i] * d->qvel[i];
       d->efc_vel[e] = vel;
       d->efc_aref[e] = -B * vel - K * imp * (d->efc_pos[e] - d->efc_margin[e]);
     }
     /* pyramidal cone: all edges share R = 2 mu^2 R[first]  (mu regularised by impratio) */
-    double mureg = c->mu / sqrt(m->impratio > MINVAL ? m->impratio : 1.0);
-    double Rpy = 2 * mureg * mureg * d->efc_R[e0];
+    real mureg = c->mu / sqrt(m->impratio > MINVAL ? m->impratio : 1.0);
+    real Rpy = 2 * mureg * mureg * d->efc_R[e0];
     if (Rpy < MINVAL) Rpy = MINVAL;
     for (int r = 0; r < 4; r++) { d->efc_R[e0 + r] = Rpy; d->efc_D[e0 + r] = 1.0 / Rpy; }
   }
@@ -707,14 +766,14 @@ static void make_constraint(const nmo_model* m, data_t* d) {
 /* ------------------------------------------------------------------------------------------ P6 projectConstraint */
 static void project_constraint(const nmo_model* m, data_t* d) {
   int nv = m->nv, ne = d->nefc;
-  double* X = d->scratch + 16 * nv;  /* ne x nv : rows = M^-1 J_e^T */
+  real* X = d->scratch + 16 * nv;  /* ne x nv : rows = M^-1 J_e^T */
   for (int e = 0; e < ne; e++) {
-    memcpy(X + e * nv, d->efc_J + e * nv, sizeof(double) * nv);
+    memcpy(X + e * nv, d->efc_J + e * nv, sizeof(real) * nv);
     chol_solve(d->L, nv, X + e * nv);
   }
   for (int a = 0; a < ne; a++)
     for (int b = 0; b < ne; b++) {
-      double s = 0;
+      real s = 0;
       for (int i = 0; i < nv; i++) s += d->efc_J[a * nv + i] * X[b * nv + i];
       d->efc_AR[a * ne + b] = s + (a == b ? d->efc_R[a] : 0);
     }
@@ -722,15 +781,15 @@ static void project_constraint(const nmo_model* m, data_t* d) {
 
 /* ------------------------------------------------------------------------------------------ P7 comVel + rne */
 static void com_vel(const nmo_model* m, data_t* d) {
-  memset(d->cvel, 0, 6 * sizeof(double));
+  memset(d->cvel, 0, 6 * sizeof(real));
   for (int i = 1; i < m->nbody; i++) {
-    double cvel[6];
+    real cvel[6];
     memcpy(cvel, d->cvel + 6 * m->body_parent[i], sizeof(cvel));
     int bda = m->body_dofadr[i];
     for (int j = m->body_jntadr[i]; j >= 0 && j < m->body_jntadr[i] + m->body_jntnum[i]; j++) {
       if (m->jnt_type[j] == JNT_FREE) {
         for (int k = 0; k < 3; k++) {
-          memset(d->cdof_dot + 6 * (bda + k), 0, 6 * sizeof(double));
+          memset(d->cdof_dot + 6 * (bda + k), 0, 6 * sizeof(real));
           for (int c = 0; c < 6; c++) cvel[c] += d->cdof[6 * (bda + k) + c] * d->qvel[bda + k];
         }
         bda += 3;
@@ -748,16 +807,16 @@ static void com_vel(const nmo_model* m, data_t* d) {
   }
 }
 
-static void rne(const nmo_model* m, data_t* d, double* result) {
+static void rne(const nmo_model* m, data_t* d, real* result) {
   int nb = m->nbody, nv = m->nv;
-  double* cacc = d->scratch;            /* 6 x nb */
-  double* cfrc = d->scratch + 6 * nb;   /* 6 x nb */
-  memset(cacc, 0, 6 * sizeof(double));
+  real* cacc = d->scratch;            /* 6 x nb */
+  real* cfrc = d->scratch + 6 * nb;   /* 6 x nb */
+  memset(cacc, 0, 6 * sizeof(real));
   for (int k = 0; k < 3; k++) cacc[3 + k] = -m->gravity[k];
-  memset(cfrc, 0, 6 * sizeof(double));
+  memset(cfrc, 0, 6 * sizeof(real));
   for (int i = 1; i < nb; i++) {
-    double tmp[6], tmp1[6];
-    memcpy(cacc + 6 * i, cacc + 6 * m->body_parent[i], 6 * sizeof(double));
+    real tmp[6], tmp1[6];
+    memcpy(cacc + 6 * i, cacc + 6 * m->body_parent[i], 6 * sizeof(real));
     for (int j = 0; j < m->body_dofnum[i]; j++) {
       int dd = m->body_dofadr[i] + j;
       for (int c = 0; c < 6; c++) cacc[6 * i + c] += d->cdof_dot[6 * dd + c] * d->qvel[dd];
@@ -772,7 +831,7 @@ static void rne(const nmo_model* m, data_t* d, double* result) {
     if (p > 0) for (int c = 0; c < 6; c++) cfrc[6 * p + c] += cfrc[6 * i + c];
   }
   for (int i = 0; i < nv; i++) {
-    double s = 0;
+    real s = 0;
     for (int c = 0; c < 6; c++) s += d->cdof[6 * i + c] * cfrc[6 * m->dof_body[i] + c];
     result[i] = s;
   }
@@ -784,17 +843,17 @@ static void fwd_velocity_actuation_acceleration(const nmo_model* m, data_t* d) {
   com_vel(m, d);
   for (int i = 0; i < nv; i++) d->qfrc_passive[i] = -m->dof_damping[i] * d->qvel[i];
   rne(m, d, d->qfrc_bias);
-  memset(d->qfrc_actuator, 0, sizeof(double) * nv);
+  memset(d->qfrc_actuator, 0, sizeof(real) * nv);
   for (int a = 0; a < m->nu; a++) {
-    double ctrl = d->ctrl[a];
+    real ctrl = d->ctrl[a];
     if (m->act_ctrllimited[a]) {
       if (ctrl < m->act_ctrlrange[2 * a]) ctrl = m->act_ctrlrange[2 * a];
       if (ctrl > m->act_ctrlrange[2 * a + 1]) ctrl = m->act_ctrlrange[2 * a + 1];
     }
     int dof = m->act_dof[a], jid = m->dof_jnt[dof];
-    double gear = m->act_gear[a];
-    double length = d->qpos[m->jnt_qposadr[jid]] * gear, velocity = d->qvel[dof] * gear;
-    double f = m->act_gain[3 * a] * ctrl + m->act_bias[3 * a] + m->act_bias[3 * a + 1] * length + m->act_bias[3 * a + 2] * velocity;
+    real gear = m->act_gear[a];
+    real length = d->qpos[m->jnt_qposadr[jid]] * gear, velocity = d->qvel[dof] * gear;
+    real f = m->act_gain[3 * a] * ctrl + m->act_bias[3 * a] + m->act_bias[3 * a + 1] * length + m->act_bias[3 * a + 2] * velocity;
     if (m->act_forcelimited[a]) {
       if (f < m->act_forcerange[2 * a]) f = m->act_forcerange[2 * a];
       if (f > m->act_forcerange[2 * a + 1]) f = m->act_forcerange[2 * a + 1];
@@ -813,7 +872,7 @@ static void fwd_velocity_actuation_acceleration(const nmo_model* m, data_t* d) {
 static void dual_finish(const nmo_model* m, data_t* d) {
   int nv = m->nv, ne = d->nefc;
   for (int i = 0; i < nv; i++) {
-    double s = 0;
+    real s = 0;
     for (int e = 0; e < ne; e++) s += d->efc_J[e * nv + i] * d->efc_force[e];
     d->qfrc_constraint[i] = s;
     d->qacc[i] = s;
@@ -827,45 +886,45 @@ static void fwd_constraint(const nmo_model* m, data_t* d) {
   d->solver_niter = d->noslip_niter = 0;
   d->warm_used = 0;
   if (ne == 0) {
-    memcpy(d->qacc, d->qacc_smooth, sizeof(double) * nv);
-    memcpy(d->qacc_warmstart, d->qacc_smooth, sizeof(double) * nv);
-    memset(d->qfrc_constraint, 0, sizeof(double) * nv);
+    memcpy(d->qacc, d->qacc_smooth, sizeof(real) * nv);
+    memcpy(d->qacc_warmstart, d->qacc_smooth, sizeof(real) * nv);
+    memset(d->qfrc_constraint, 0, sizeof(real) * nv);
     return;
   }
-  const double* AR = d->efc_AR;
-  double* f = d->efc_force;
+  const real* AR = d->efc_AR;
+  real* f = d->efc_force;
   /* b = J qacc_smooth - aref */
   for (int e = 0; e < ne; e++) {
-    double s = 0;
+    real s = 0;
     for (int i = 0; i < nv; i++) s += d->efc_J[e * nv + i] * d->qacc_smooth[i];
     d->efc_b[e] = s - d->efc_aref[e];
   }
   /* warm start: forces implied by qacc_warmstart, kept only if their dual cost beats f = 0 */
   for (int e = 0; e < ne; e++) {
-    double jar = -d->efc_aref[e];
+    real jar = -d->efc_aref[e];
     for (int i = 0; i < nv; i++) jar += d->efc_J[e * nv + i] * d->qacc_warmstart[i];
     f[e] = jar < 0 ? -d->efc_D[e] * jar : 0;
   }
-  double cost = 0;
+  real cost = 0;
   for (int a = 0; a < ne; a++) {
-    double s = 0;
+    real s = 0;
     for (int b = 0; b < ne; b++) s += AR[a * ne + b] * f[b];
     cost += 0.5 * f[a] * s + f[a] * d->efc_b[a];
   }
-  if (cost > 0) memset(f, 0, sizeof(double) * ne); else d->warm_used = 1;
+  if (cost > 0) memset(f, 0, sizeof(real) * ne); else d->warm_used = 1;
 
-  double scale = 1.0 / (m->meaninertia * (nv > 1 ? nv : 1));
+  real scale = 1.0 / (m->meaninertia * (nv > 1 ? nv : 1));
   /* PGS (pyramidal rows are scalar inequality constraints) */
   for (int it = 0; it < m->iterations; it++) {
-    double improvement = 0;
+    real improvement = 0;
     for (int e = 0; e < ne; e++) {
-      double res = d->efc_b[e];
+      real res = d->efc_b[e];
       for (int b = 0; b < ne; b++) res += AR[e * ne + b] * f[b];
-      double old = f[e];
+      real old = f[e];
       f[e] -= res / AR[e * ne + e];
       if (f[e] < 0) f[e] = 0;
-      double delta = f[e] - old;
-      double change = 0.5 * delta * delta * AR[e * ne + e] + delta * res;
+      real delta = f[e] - old;
+      real change = 0.5 * delta * delta * AR[e * ne + e] + delta * res;
       if (change > 1e-10) { f[e] = old; change = 0; }
       improvement -= change;
     }
@@ -873,36 +932,36 @@ static void fwd_constraint(const nmo_model* m, data_t* d) {
     if (improvement * scale < m->tolerance) break;
   }
   dual_finish(m, d);
-  memcpy(d->qacc_warmstart, d->qacc, sizeof(double) * nv);   /* saved BEFORE noslip */
+  memcpy(d->qacc_warmstart, d->qacc, sizeof(real) * nv);   /* saved BEFORE noslip */
 
   /* noslip post-processing: friction dimensions re-solved without regularisation */
   if (m->noslip_iterations > 0) {
     for (int it = 0; it < m->noslip_iterations; it++) {
-      double improvement = 0;
+      real improvement = 0;
       for (int ci = 0; ci < d->ncon; ci++) {
         int e0 = d->con[ci].efc_address;
         if (e0 < 0) continue;
         for (int j = e0; j < e0 + 4; j += 2) {
-          double res[2], old[2] = {f[j], f[j + 1]};
+          real res[2], old[2] = {f[j], f[j + 1]};
           for (int k = 0; k < 2; k++) {
-            double s = d->efc_b[j + k];
+            real s = d->efc_b[j + k];
             for (int b = 0; b < ne; b++) s += AR[(j + k) * ne + b] * f[b];
             res[k] = s - d->efc_R[j + k] * f[j + k];
           }
-          double Ac[4] = {AR[j * ne + j] - d->efc_R[j], AR[j * ne + j + 1], AR[(j + 1) * ne + j], AR[(j + 1) * ne + j + 1] - d->efc_R[j + 1]};
-          double bc[2] = {res[0] - Ac[0] * old[0] - Ac[1] * old[1], res[1] - Ac[2] * old[0] - Ac[3] * old[1]};
-          double mid = 0.5 * (old[0] + old[1]);
-          double K1 = Ac[0] + Ac[3] - Ac[1] - Ac[2];
-          double K0 = mid * (Ac[0] - Ac[3]) + bc[0] - bc[1];
+          real Ac[4] = {AR[j * ne + j] - d->efc_R[j], AR[j * ne + j + 1], AR[(j + 1) * ne + j], AR[(j + 1) * ne + j + 1] - d->efc_R[j + 1]};
+          real bc[2] = {res[0] - Ac[0] * old[0] - Ac[1] * old[1], res[1] - Ac[2] * old[0] - Ac[3] * old[1]};
+          real mid = 0.5 * (old[0] + old[1]);
+          real K1 = Ac[0] + Ac[3] - Ac[1] - Ac[2];
+          real K0 = mid * (Ac[0] - Ac[3]) + bc[0] - bc[1];
           if (K1 < MINVAL) { f[j] = f[j + 1] = mid; }
           else {
-            double x = -K0 / K1;
+            real x = -K0 / K1;
             if (x < -mid) { f[j] = 0; f[j + 1] = 2 * mid; }
             else if (x > mid) { f[j] = 2 * mid; f[j + 1] = 0; }
             else { f[j] = mid + x; f[j + 1] = mid - x; }
           }
-          double dl[2] = {f[j] - old[0], f[j + 1] - old[1]};
-          double change = 0.5 * (dl[0] * (Ac[0] * dl[0] + Ac[1] * dl[1]) + dl[1] * (Ac[2] * dl[0] + Ac[3] * dl[1])) + dl[0] * res[0] + dl[1] * res[1];
+          real dl[2] = {f[j] - old[0], f[j + 1] - old[1]};
+          real change = 0.5 * (dl[0] * (Ac[0] * dl[0] + Ac[1] * dl[1]) + dl[1] * (Ac[2] * dl[0] + Ac[3] * dl[1])) + dl[0] * res[0] + dl[1] * res[1];
           if (change > 1e-10) { f[j] = old[0]; f[j + 1] = old[1]; change = 0; }
           improvement -= change;
         }
@@ -915,13 +974,13 @@ static void fwd_constraint(const nmo_model* m, data_t* d) {
 }
 
 /* ------------------------------------------------------------------------------------------ P10 touch sensors */
-static double ray_sphere(const double* center, double radius, const double* pnt, const double* vec) {
-  double dif[3] = {pnt[0] - center[0], pnt[1] - center[1], pnt[2] - center[2]};
-  double a = dot3(vec, vec), b = dot3(vec, dif), c = dot3(dif, dif) - radius * radius;
-  double det = b * b - a * c;
+static real ray_sphere(const real* center, real radius, const real* pnt, const real* vec) {
+  real dif[3] = {pnt[0] - center[0], pnt[1] - center[1], pnt[2] - center[2]};
+  real a = dot3(vec, vec), b = dot3(vec, dif), c = dot3(dif, dif) - radius * radius;
+  real det = b * b - a * c;
   if (det < MINVAL || a < MINVAL) return -1;
   det = sqrt(det);
-  double x0 = (-b - det) / a, x1 = (-b + det) / a;
+  real x0 = (-b - det) / a, x1 = (-b + det) / a;
   if (x0 >= 0) return x0;
   if (x1 >= 0) return x1;
   return -1;
@@ -930,14 +989,14 @@ static double ray_sphere(const double* center, double radius, const double* pnt,
 static void sensor_touch(const nmo_model* m, data_t* d) {
   for (int s = 0; s < m->nsensor; s++) {
     int site = m->sensor_site[s], body = m->site_body[site];
-    double sum = 0;
+    real sum = 0;
     for (int ci = 0; ci < d->ncon; ci++) {
       const contact_t* c = d->con + ci;
       if (c->efc_address < 0 || (c->body1 != body && c->body2 != body)) continue;
-      double fn = 0;
+      real fn = 0;
       for (int r = 0; r < 4; r++) fn += d->efc_force[c->efc_address + r];
       if (fn <= 0) continue;
-      double ray[3] = {c->frame[0] * fn, c->frame[1] * fn, c->frame[2] * fn};
+      real ray[3] = {c->frame[0] * fn, c->frame[1] * fn, c->frame[2] * fn};
       normalize3(ray);
       if (c->body2 == body) { ray[0] = -ray[0]; ray[1] = -ray[1]; ray[2] = -ray[2]; }
       if (ray_sphere(d->site_xpos + 3 * site, m->site_size[site], c->pos, ray) >= 0) sum += fn;
@@ -959,13 +1018,13 @@ static void forward(const nmo_model* m, data_t* d) {
   sensor_touch(m, d);
 }
 
-static void integrate_pos(const nmo_model* m, double* qpos, const double* qvel, double h) {
+static void integrate_pos(const nmo_model* m, real* qpos, const real* qvel, real h) {
   for (int j = 0; j < m->njnt; j++) {
     int qa = m->jnt_qposadr[j], da = m->jnt_dofadr[j];
     if (m->jnt_type[j] == JNT_FREE) {
       for (int k = 0; k < 3; k++) qpos[qa + k] += h * qvel[da + k];
-      double w[3] = {qvel[da + 3], qvel[da + 4], qvel[da + 5]}, qr[4], qn[4];
-      double angle = h * normalize3(w);
+      real w[3] = {qvel[da + 3], qvel[da + 4], qvel[da + 5]}, qr[4], qn[4];
+      real angle = h * normalize3(w);
       axisangle2quat(qr, w, angle);
       normalize4(qpos + qa + 3);
       mul_quat(qn, qpos + qa + 3, qr);
@@ -983,30 +1042,30 @@ static int bad_state(const nmo_model* m, const data_t* d) {
 }
 
 static void reset_data(const nmo_model* m, data_t* d) {
-  memcpy(d->qpos, m->qpos0, sizeof(double) * m->nq);
-  memset(d->qvel, 0, sizeof(double) * m->nv);
-  memset(d->qacc_warmstart, 0, sizeof(double) * m->nv);
+  memcpy(d->qpos, m->qpos0, sizeof(real) * m->nq);
+  memset(d->qvel, 0, sizeof(real) * m->nv);
+  memset(d->qacc_warmstart, 0, sizeof(real) * m->nv);
   d->time = 0;
   d->nwarn++;
 }
 
 static void step1(const nmo_model* m, data_t* d) {
   int nv = m->nv;
-  double h = m->timestep;
+  real h = m->timestep;
   if (bad_state(m, d)) reset_data(m, d);      /* ≙ mj_checkPos / mj_checkVel */
   forward(m, d);
   for (int i = 0; i < nv; i++)
     if (!(fabs(d->qacc[i]) < MAXVAL)) { reset_data(m, d); forward(m, d); break; }   /* ≙ mj_checkAcc */
-  double* qacc = d->scratch;
+  real* qacc = d->scratch;
   if (m->integrator == INT_IMPLICITFAST || m->integrator == INT_IMPLICIT) {
     /* implicitfast: qDeriv = d(qfrc_smooth)/d(qvel) restricted to actuator + passive terms (diagonal here) */
-    double* A = d->MH;
-    double* L = d->LH;
-    memcpy(A, d->M, sizeof(double) * nv * nv);
+    real* A = d->MH;
+    real* L = d->LH;
+    memcpy(A, d->M, sizeof(real) * nv * nv);
     for (int i = 0; i < nv; i++) A[i * nv + i] += h * m->dof_damping[i];
     for (int a = 0; a < m->nu; a++) {
       int dof = m->act_dof[a];
-      double g = m->act_gear[a];
+      real g = m->act_gear[a];
       A[dof * nv + dof] -= h * m->act_bias[3 * a + 2] * g * g;
     }
     cholesky(L, A, nv);
@@ -1016,15 +1075,15 @@ static void step1(const nmo_model* m, data_t* d) {
     int any = 0;
     for (int i = 0; i < nv; i++) if (m->dof_damping[i] > 0) any = 1;
     if (any && m->eulerdamp) {
-      double* A = d->MH;
-      double* L = d->LH;
-      memcpy(A, d->M, sizeof(double) * nv * nv);
+      real* A = d->MH;
+      real* L = d->LH;
+      memcpy(A, d->M, sizeof(real) * nv * nv);
       for (int i = 0; i < nv; i++) A[i * nv + i] += h * m->dof_damping[i];
       cholesky(L, A, nv);
       for (int i = 0; i < nv; i++) qacc[i] = d->qfrc_smooth[i] + d->qfrc_constraint[i];
       chol_solve(L, nv, qacc);
     } else {
-      memcpy(qacc, d->qacc, sizeof(double) * nv);
+      memcpy(qacc, d->qacc, sizeof(real) * nv);
     }
   }
   for (int i = 0; i < nv; i++) d->qvel[i] += h * qacc[i];
@@ -1043,14 +1102,14 @@ void nmo_philox4x32(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1, uint32_t
   }
   out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
-static inline double u01(uint32_t x) { return (double)(x >> 8) * (1.0 / 16777216.0); }
+static inline real u01(uint32_t x) { return (real)(x >> 8) * (1.0 / 16777216.0); }
 
 /* ------------------------------------------------------------------------------------------ batch */
 nmo_batch* nmo_batch_create(const nmo_model* m, int n, uint64_t seed, const nmo_envcfg* cfg) {
   if (m->nv > 64) return NULL;
   nmo_batch* b = (nmo_batch*)calloc(1, sizeof(nmo_batch));
   b->m = m; b->n = n; b->seed = seed;
-  if (cfg) b->cfg = *cfg;
+  if (cfg) cfg_convert(&b->cfg, cfg);
   b->d = (data_t*)calloc(n, sizeof(data_t));
   b->e = (envstate_t*)calloc(n, sizeof(envstate_t));
   for (int i = 0; i < n; i++) { data_init(m, b->d + i); b->e[i].reset_buf = 1; }
@@ -1062,17 +1121,19 @@ void nmo_batch_free(nmo_batch* b) {
   free(b->d); free(b->e); free(b);
 }
 void nmo_set_state(nmo_batch* b, const double* qpos, const double* qvel, const double* warm) {
+  const int nq = b->m->nq, nv = b->m->nv;
   for (int i = 0; i < b->n; i++) {
-    if (qpos) memcpy(b->d[i].qpos, qpos + (size_t)i * b->m->nq, sizeof(double) * b->m->nq);
-    if (qvel) memcpy(b->d[i].qvel, qvel + (size_t)i * b->m->nv, sizeof(double) * b->m->nv);
-    if (warm) memcpy(b->d[i].qacc_warmstart, warm + (size_t)i * b->m->nv, sizeof(double) * b->m->nv);
+    if (qpos) for (int k = 0; k < nq; k++) b->d[i].qpos[k] = (real)qpos[(size_t)i * nq + k];
+    if (qvel) for (int k = 0; k < nv; k++) b->d[i].qvel[k] = (real)qvel[(size_t)i * nv + k];
+    if (warm) for (int k = 0; k < nv; k++) b->d[i].qacc_warmstart[k] = (real)warm[(size_t)i * nv + k];
   }
 }
 void nmo_get_state(const nmo_batch* b, double* qpos, double* qvel, double* warm) {
+  const int nq = b->m->nq, nv = b->m->nv;
   for (int i = 0; i < b->n; i++) {
-    if (qpos) memcpy(qpos + (size_t)i * b->m->nq, b->d[i].qpos, sizeof(double) * b->m->nq);
-    if (qvel) memcpy(qvel + (size_t)i * b->m->nv, b->d[i].qvel, sizeof(double) * b->m->nv);
-    if (warm) memcpy(warm + (size_t)i * b->m->nv, b->d[i].qacc_warmstart, sizeof(double) * b->m->nv);
+    if (qpos) for (int k = 0; k < nq; k++) qpos[(size_t)i * nq + k] = (double)b->d[i].qpos[k];
+    if (qvel) for (int k = 0; k < nv; k++) qvel[(size_t)i * nv + k] = (double)b->d[i].qvel[k];
+    if (warm) for (int k = 0; k < nv; k++) warm[(size_t)i * nv + k] = (double)b->d[i].qacc_warmstart[k];
   }
 }
 
@@ -1109,14 +1170,18 @@ static void run_parallel(job_t proto, int nthreads) {
   free(th); free(jobs);
 }
 
+static void set_ctrl(nmo_batch* b, const double* ctrl) {
+  const int nu = b->m->nu;
+  if (ctrl) for (int i = 0; i < b->n; i++) for (int k = 0; k < nu; k++) b->d[i].ctrl[k] = (real)ctrl[(size_t)i * nu + k];
+}
 void nmo_physics_step(nmo_batch* b, const double* ctrl, int nstep, int nthreads) {
-  if (ctrl) for (int i = 0; i < b->n; i++) memcpy(b->d[i].ctrl, ctrl + (size_t)i * b->m->nu, sizeof(double) * b->m->nu);
+  set_ctrl(b, ctrl);
   job_t j; memset(&j, 0, sizeof(j));
   j.b = b; j.nstep = nstep; j.mode = 0;
   run_parallel(j, nthreads);
 }
 void nmo_forward(nmo_batch* b, const double* ctrl, int nthreads) {
-  if (ctrl) for (int i = 0; i < b->n; i++) memcpy(b->d[i].ctrl, ctrl + (size_t)i * b->m->nu, sizeof(double) * b->m->nu);
+  set_ctrl(b, ctrl);
   job_t j; memset(&j, 0, sizeof(j));
   j.b = b; j.mode = 1;
   run_parallel(j, nthreads);
@@ -1169,7 +1234,7 @@ enum { RW_ACTION_RATE = 0, RW_ANG_VEL_XY, RW_BASE_HEIGHT, RW_BODY_CONTACT_FORCES
 /* ≙ _resample_commands (env.py:321-333) with the counter-based RNG this project defines
    (the reference uses the unseeded global numpy MT19937, which cannot be reproduced) */
 static void resample_commands(nmo_batch* b, int i, int phase) {
-  const nmo_envcfg* c = &b->cfg;
+  const cfg_t* c = &b->cfg;
   envstate_t* e = b->e + i;
   uint32_t r[4];
   nmo_philox4x32((uint32_t)b->seed, (uint32_t)i, (uint32_t)b->step_counter, (uint32_t)((uint64_t)b->step_counter >> 32), (uint32_t)phase,
@@ -1177,8 +1242,8 @@ static void resample_commands(nmo_batch* b, int i, int phase) {
   e->commands[0] = u01(r[0]) * 2 * c->max_lin_vel_x - c->max_lin_vel_x;
   e->commands[1] = 0;
   e->commands[2] = u01(r[1]) * 2 * c->max_ang_vel - c->max_ang_vel;
-  double nrm = sqrt(e->commands[0] * e->commands[0] + e->commands[1] * e->commands[1]);
-  double keep = nrm > 0.02 ? 1.0 : 0.0;
+  real nrm = sqrt(e->commands[0] * e->commands[0] + e->commands[1] * e->commands[1]);
+  real keep = nrm > 0.02 ? 1.0 : 0.0;
   e->commands[0] *= keep; e->commands[1] *= keep;
 }
 
@@ -1187,26 +1252,26 @@ static void reset_one(nmo_batch* b, int i) {
   const nmo_model* m = b->m;
   data_t* d = b->d + i;
   envstate_t* e = b->e + i;
-  memcpy(d->qpos, m->qpos0, sizeof(double) * m->nq);
-  memset(d->qvel, 0, sizeof(double) * m->nv);
+  memcpy(d->qpos, m->qpos0, sizeof(real) * m->nq);
+  memset(d->qvel, 0, sizeof(real) * m->nv);
   resample_commands(b, i, 1);
   memset(e->feet_air_time, 0, sizeof(e->feet_air_time));
   e->ep_len = 0;
   e->reset_buf = 1;
 }
 
-static double reward_term(nmo_batch* b, envstate_t* e, int k) {
-  const nmo_envcfg* c = &b->cfg;
-  double s = 0;
+static real reward_term(nmo_batch* b, envstate_t* e, int k) {
+  const cfg_t* c = &b->cfg;
+  real s = 0;
   switch (k) {
-    case RW_ACTION_RATE: for (int j = 0; j < 18; j++) { double x = e->prev_actions[j] - e->actions[j]; s += x * x; } return s;
+    case RW_ACTION_RATE: for (int j = 0; j < 18; j++) { real x = e->prev_actions[j] - e->actions[j]; s += x * x; } return s;
     case RW_ANG_VEL_XY: return e->base_ang_vel[0] * e->base_ang_vel[0] + e->base_ang_vel[1] * e->base_ang_vel[1];
-    case RW_BASE_HEIGHT: { double x = e->base_height - c->base_height_target; return x * x; }
+    case RW_BASE_HEIGHT: { real x = e->base_height - c->base_height_target; return x * x; }
     case RW_BODY_CONTACT_FORCES:
       if (c->tibia_contact_mode == 1) for (int j = 0; j < 6; j++) s += e->tibia_f[j];
       if (c->body_contact_mode == 1) s += e->body_f;
       return s;
-    case RW_DEFAULT_POSITION: for (int j = 0; j < 18; j++) { double x = e->dof_pos[j] - c->default_pos[j]; s += x * x; } return s;
+    case RW_DEFAULT_POSITION: for (int j = 0; j < 18; j++) { real x = e->dof_pos[j] - c->default_pos[j]; s += x * x; } return s;
     case RW_DOF_ACC: for (int j = 0; j < 18; j++) s += e->dof_acc[j] * e->dof_acc[j]; return s;
     case RW_DOF_VEL: for (int j = 0; j < 18; j++) s += e->dof_vel[j] * e->dof_vel[j]; return s;
     case RW_FEET_AIR_TIME: {   /* stateful, env.py:447-477 */
@@ -1217,26 +1282,26 @@ static double reward_term(nmo_batch* b, envstate_t* e, int k) {
         e->feet_air_time[j] *= (filt == e->last_contacts_filt[j]) ? 1.0 : 0.0;
         e->last_contacts[j] = contact;
         e->last_contacts_filt[j] = filt;
-        double t = e->feet_air_time[j];
-        double r = (t > 1.0 ? (t - 1.0) : 0.0) + (t < 0.5 ? (0.5 - t) : 0.0);
+        real t = e->feet_air_time[j];
+        real r = (t > 1.0 ? (t - 1.0) : 0.0) + (t < 0.5 ? (0.5 - t) : 0.0);
         s += r * r;
       }
       return s;
     }
     case RW_FEET_CONTACT_FORCES:
-      for (int j = 0; j < 6; j++) { double x = (e->feet_f[j] - c->max_contact_force) * (e->feet_f[j] > c->max_contact_force ? 1.0 : 0.0); s += x * x; }
+      for (int j = 0; j < 6; j++) { real x = (e->feet_f[j] - c->max_contact_force) * (e->feet_f[j] > c->max_contact_force ? 1.0 : 0.0); s += x * x; }
       return s;
     case RW_LIN_VEL_Z: return e->base_lin_vel[2] * e->base_lin_vel[2];
     case RW_ORIENTATION: return e->projected_gravity[0] * e->projected_gravity[0] + e->projected_gravity[1] * e->projected_gravity[1];
     case RW_STAND_STILL: {
       for (int j = 0; j < 18; j++) s += fabs(e->dof_pos[j] - c->default_pos[j]);
-      double nrm = sqrt(e->commands[0] * e->commands[0] + e->commands[1] * e->commands[1]);
+      real nrm = sqrt(e->commands[0] * e->commands[0] + e->commands[1] * e->commands[1]);
       return s * (nrm < 0.01 ? 1.0 : 0.0);
     }
     case RW_TORQUES: return 0.0;   /* qfrc_applied is never written (quirk Q7) */
-    case RW_TRACKING_ANG_VEL: { double x = e->commands[2] - e->base_ang_vel[2]; return exp(-x * x / c->tracking_sigma); }
+    case RW_TRACKING_ANG_VEL: { real x = e->commands[2] - e->base_ang_vel[2]; return exp(-x * x / c->tracking_sigma); }
     case RW_TRACKING_LIN_VEL: {
-      double x = e->commands[0] - e->base_lin_vel[0], y = e->commands[1] - e->base_lin_vel[1];
+      real x = e->commands[0] - e->base_lin_vel[0], y = e->commands[1] - e->base_lin_vel[1];
       return exp(-(x * x + y * y) / c->tracking_sigma);
     }
     default: return 0.0;   /* collision / feet_stumble have no function in the reference */
@@ -1245,17 +1310,17 @@ static double reward_term(nmo_batch* b, envstate_t* e, int k) {
 
 static void env_step_one(nmo_batch* b, int i, const float* act, float* obs, float* rew, int64_t* done) {
   const nmo_model* m = b->m;
-  const nmo_envcfg* c = &b->cfg;
+  const cfg_t* c = &b->cfg;
   data_t* d = b->d + i;
   envstate_t* e = b->e + i;
   /* E1 */
-  double prev_dof_vel[18];
+  real prev_dof_vel[18];
   for (int j = 0; j < 18; j++) {
     e->prev_actions[j] = e->actions[j];
     /* the reference scales and clips the policy's float32 tensor in float32 (numpy: float32 array * python float stays
      * float32, envs/nightmare_v3_env.py:155-156) and only then mixes it with float64 buffers */
     const float a32 = act[j] * (float)c->action_scale, lim = (float)c->clip_actions;
-    e->actions[j] = (double)(a32 < -lim ? -lim : (a32 > lim ? lim : a32));
+    e->actions[j] = (real)(a32 < -lim ? -lim : (a32 > lim ? lim : a32));
     prev_dof_vel[j] = e->dof_vel[j];
   }
   /* E3/E4: PD law from the carried (possibly stale) dof_pos */
@@ -1268,8 +1333,8 @@ static void env_step_one(nmo_batch* b, int i, const float* act, float* obs, floa
   int fj = -1;
   for (int j = 0; j < m->njnt; j++) if (m->jnt_type[j] == JNT_FREE) { fj = j; break; }
   int bb = m->jnt_body[fj], qa = m->jnt_qposadr[fj];
-  double bq[4] = {d->qpos[qa + 3], -d->qpos[qa + 4], -d->qpos[qa + 5], -d->qpos[qa + 6]};
-  double grav[3] = {0, 0, -9.81};
+  real bq[4] = {d->qpos[qa + 3], -d->qpos[qa + 4], -d->qpos[qa + 5], -d->qpos[qa + 6]};
+  real grav[3] = {0, 0, -9.81};
   rot_vec_quat(e->base_lin_vel, d->cvel + 6 * bb + 3, bq);
   rot_vec_quat(e->base_ang_vel, d->cvel + 6 * bb, bq);
   rot_vec_quat(e->projected_gravity, grav, bq);
@@ -1284,16 +1349,16 @@ static void env_step_one(nmo_batch* b, int i, const float* act, float* obs, floa
   /* E10 */
   if (c->resample_period > 0 && e->ep_len % c->resample_period == 0) resample_commands(b, i, 0);
   /* E11 */
-  e->time_out = (double)e->ep_len > c->max_episode_length;
+  e->time_out = (real)e->ep_len > c->max_episode_length;
   int reset = e->time_out;
-  double fmax = e->feet_f[0], tmax = e->tibia_f[0];
+  real fmax = e->feet_f[0], tmax = e->tibia_f[0];
   for (int j = 1; j < 6; j++) { if (e->feet_f[j] > fmax) fmax = e->feet_f[j]; if (e->tibia_f[j] > tmax) tmax = e->tibia_f[j]; }
   reset |= fmax > c->termination_contact_force;
   if (c->tibia_contact_mode == 2) reset |= tmax > c->tibia_max_contact_force;
   if (c->body_contact_mode == 2) reset |= e->body_f > c->body_max_contact_force;
   {
-    const double* pg = e->projected_gravity;
-    double nrm = sqrt(pg[0] * pg[0] + pg[1] * pg[1] + pg[2] * pg[2]);
+    const real* pg = e->projected_gravity;
+    real nrm = sqrt(pg[0] * pg[0] + pg[1] * pg[1] + pg[2] * pg[2]);
     reset |= acos(-pg[2] / nrm) > 60.0 * M_PI / 180.0;
   }
   e->reset_buf = reset;
@@ -1305,20 +1370,20 @@ static void env_step_one(nmo_batch* b, int i, const float* act, float* obs, floa
     memset(e->episode_sums, 0, sizeof(e->episode_sums));
   }
   /* E14: rewards from pre-reset buffers, post-reset commands (quirk Q1) */
-  double total = 0;
+  real total = 0;
   for (int k = 0; k < NMO_NREW; k++) {
     if (k == RW_TERMINATION || c->rew_scale[k] == 0) continue;
-    double r = reward_term(b, e, k) * c->rew_scale[k];
+    real r = reward_term(b, e, k) * c->rew_scale[k];
     total += r;
     e->episode_sums[k] += r;
   }
   if (c->rew_scale[RW_TERMINATION] != 0) {
-    double r = (double)(e->reset_buf * (e->time_out ? 0 : 1)) * c->rew_scale[RW_TERMINATION];
+    real r = (real)(e->reset_buf * (e->time_out ? 0 : 1)) * c->rew_scale[RW_TERMINATION];
     total += r;
     e->episode_sums[RW_TERMINATION] += r;
   }
   /* E15 */
-  double o[66];
+  real o[66];
   for (int k = 0; k < 3; k++) {
     o[k] = e->base_lin_vel[k] * c->obs_lin_vel;
     o[3 + k] = e->base_ang_vel[k] * c->obs_ang_vel;
@@ -1339,7 +1404,7 @@ static void env_step_one(nmo_batch* b, int i, const float* act, float* obs, floa
     }
   }
   for (int k = 0; k < 66; k++) {
-    double v = o[k] < -c->clip_obs ? -c->clip_obs : (o[k] > c->clip_obs ? c->clip_obs : o[k]);
+    real v = o[k] < -c->clip_obs ? -c->clip_obs : (o[k] > c->clip_obs ? c->clip_obs : o[k]);
     obs[k] = (float)v;
   }
   *rew = (float)total;
@@ -1361,12 +1426,12 @@ void nmo_env_step(nmo_batch* b, const float* actions, int act_stride, float* obs
     if (time_outs) time_outs[i] = b->e[i].time_out ? 1.0f : 0.0f;
     if (b->e[i].reset_buf) {
       nres++;
-      for (int k = 0; k < NMO_NREW; k++) acc[k] += b->e[i].sums_at_reset[k];
+      for (int k = 0; k < NMO_NREW; k++) acc[k] += (double)b->e[i].sums_at_reset[k];
     }
   }
   /* extras["episode"]["rew_k"] = mean over reset envs / max_episode_length_s (env.py:366) */
   if (ep_sum_means)
-    for (int k = 0; k < NMO_NREW; k++) ep_sum_means[k] = nres ? acc[k] / nres / b->cfg.max_episode_length_s : 0.0;
+    for (int k = 0; k < NMO_NREW; k++) ep_sum_means[k] = nres ? acc[k] / nres / (double)b->cfg.max_episode_length_s : 0.0;
   if (num_reset) *num_reset = nres;
 }
 
@@ -1408,9 +1473,9 @@ int nmo_env_set(nmo_batch* b, const char* name, const double* in, int count) {
       for (int k = 0; k < (per); k++) lhs = (type)in[i * (per) + k];            \
     return 0;                                                                   \
   }
-  ESET("ep_len", b->e[i].ep_len, int64_t, 1) ESET("commands", b->e[i].commands[k], double, 3)
-  ESET("actions", b->e[i].actions[k], double, 18) ESET("dof_pos", b->e[i].dof_pos[k], double, 18)
-  ESET("dof_vel", b->e[i].dof_vel[k], double, 18) ESET("episode_sums", b->e[i].episode_sums[k], double, NMO_NREW)
+  ESET("ep_len", b->e[i].ep_len, int64_t, 1) ESET("commands", b->e[i].commands[k], real, 3)
+  ESET("actions", b->e[i].actions[k], real, 18) ESET("dof_pos", b->e[i].dof_pos[k], real, 18)
+  ESET("dof_vel", b->e[i].dof_vel[k], real, 18) ESET("episode_sums", b->e[i].episode_sums[k], real, NMO_NREW)
   if (!strcmp(name, "step_counter")) { b->step_counter = (int64_t)in[0]; return 0; }
   return -1;
 }

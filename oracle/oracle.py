@@ -12,20 +12,24 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
+_LIBS = {}
+# "f64": the oracle.  "f32": the same source in fp32 arithmetic (rounding floor of an fp32 implementation).
+# "cnt": fp64 with floating-point operation counters (algorithmic FLOP count of one env step).
+_SO = {"f64": "libnm_oracle.so", "f32": "libnm_oracle_f32.so", "cnt": "libnm_oracle_cnt.so"}
 
 
-def build(force: bool = False) -> str:
-    so = os.path.join(_HERE, "libnm_oracle.so")
-    src = [os.path.join(_HERE, f) for f in ("nm_oracle.c", "nm_oracle.h")]
+def build(force: bool = False, variant: str = "f64") -> str:
+    so = os.path.join(_HERE, _SO[variant])
+    src = [os.path.join(_HERE, f) for f in ("nm_oracle.c", "nm_oracle.h", "Makefile")]
     if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in src if os.path.exists(s)):
-        subprocess.check_call(["make", "-C", _HERE, "-s"])
+        subprocess.check_call(["make", "-C", _HERE, "-s", _SO[variant]])
     return so
 
 
-def lib():
+def lib(variant: str = "f64"):
     global _LIB
-    if _LIB is None:
-        L = ctypes.CDLL(build())
+    if variant not in _LIBS:
+        L = ctypes.CDLL(build(variant=variant))
         vp, ci, cd = ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_double)
         L.nmo_model_load.restype = vp
         L.nmo_model_load.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ci]
@@ -44,8 +48,13 @@ def lib():
         L.nmo_env_get.argtypes = [vp, ctypes.c_char_p, vp, ci]
         L.nmo_env_set.argtypes = [vp, ctypes.c_char_p, vp, ci]
         L.nmo_philox4x32.argtypes = [ctypes.c_uint32] * 6 + [vp]
-        _LIB = L
-    return _LIB
+        if variant == "cnt":
+            L.nmo_flop_counts.argtypes = [vp, ci]
+            L.nmo_flop_reset.argtypes = []
+        _LIBS[variant] = L
+        if variant == "f64":
+            _LIB = L
+    return _LIBS[variant]
 
 
 def _ptr(a):
@@ -59,17 +68,19 @@ def philox4x32(k0, k1, c0, c1, c2, c3):
 
 
 class OracleModel:
-    def __init__(self, nmb_path: str):
+    def __init__(self, nmb_path: str, variant: str = "f64"):
         err = ctypes.create_string_buffer(256)
-        self.h = lib().nmo_model_load(nmb_path.encode(), err, 256)
+        self.variant = variant
+        self.L = lib(variant)
+        self.h = self.L.nmo_model_load(nmb_path.encode(), err, 256)
         if not self.h:
             raise RuntimeError(err.value.decode())
         for k in ("nq", "nv", "nu", "nbody", "njnt", "ngeom", "nsite", "nsensor"):
-            setattr(self, k, lib().nmo_model_size(self.h, k.encode()))
+            setattr(self, k, self.L.nmo_model_size(self.h, k.encode()))
 
     def __del__(self):
-        if getattr(self, "h", None) and _LIB is not None:
-            _LIB.nmo_model_free(self.h)
+        if getattr(self, "h", None) and getattr(self, "L", None) is not None:
+            self.L.nmo_model_free(self.h)
             self.h = None
 
 
@@ -79,38 +90,39 @@ class OracleBatch:
     def __init__(self, model: OracleModel, num_envs: int, seed: int = 0, envcfg=None):
         self.model, self.n = model, num_envs
         self._cfg = envcfg
-        self.h = lib().nmo_batch_create(model.h, num_envs, seed, ctypes.byref(envcfg) if envcfg is not None else None)
+        self.L = model.L
+        self.h = self.L.nmo_batch_create(model.h, num_envs, seed, ctypes.byref(envcfg) if envcfg is not None else None)
         if not self.h:
             raise RuntimeError("nmo_batch_create failed")
 
     def __del__(self):
-        if getattr(self, "h", None) and _LIB is not None:
-            _LIB.nmo_batch_free(self.h)
+        if getattr(self, "h", None) and getattr(self, "L", None) is not None:
+            self.L.nmo_batch_free(self.h)
             self.h = None
 
     # ---- raw physics
     def set_state(self, qpos=None, qvel=None, warm=None):
         c = lambda a: None if a is None else np.ascontiguousarray(a, dtype=np.float64)
         qpos, qvel, warm = c(qpos), c(qvel), c(warm)
-        lib().nmo_set_state(self.h, _ptr(qpos), _ptr(qvel), _ptr(warm))
+        self.L.nmo_set_state(self.h, _ptr(qpos), _ptr(qvel), _ptr(warm))
 
     def get_state(self):
         m = self.model
         qpos, qvel, warm = np.zeros((self.n, m.nq)), np.zeros((self.n, m.nv)), np.zeros((self.n, m.nv))
-        lib().nmo_get_state(self.h, _ptr(qpos), _ptr(qvel), _ptr(warm))
+        self.L.nmo_get_state(self.h, _ptr(qpos), _ptr(qvel), _ptr(warm))
         return qpos, qvel, warm
 
     def physics_step(self, ctrl=None, nstep=1, nthreads=1):
         ctrl = None if ctrl is None else np.ascontiguousarray(ctrl, dtype=np.float64)
-        lib().nmo_physics_step(self.h, _ptr(ctrl), nstep, nthreads)
+        self.L.nmo_physics_step(self.h, _ptr(ctrl), nstep, nthreads)
 
     def forward(self, ctrl=None, nthreads=1):
         ctrl = None if ctrl is None else np.ascontiguousarray(ctrl, dtype=np.float64)
-        lib().nmo_forward(self.h, _ptr(ctrl), nthreads)
+        self.L.nmo_forward(self.h, _ptr(ctrl), nthreads)
 
     def get(self, env: int, name: str, cap: int = 65536):
         buf = np.zeros(cap)
-        n = lib().nmo_get_array(self.h, env, name.encode(), _ptr(buf), cap)
+        n = self.L.nmo_get_array(self.h, env, name.encode(), _ptr(buf), cap)
         if n < 0:
             raise KeyError(name)
         return buf[:n].copy()
@@ -124,13 +136,13 @@ class OracleBatch:
         tout = np.zeros(self.n, dtype=np.float32)
         means = np.zeros(18)
         nres = ctypes.c_int(0)
-        lib().nmo_env_step(self.h, _ptr(a), a.shape[1], _ptr(obs), _ptr(rew), _ptr(done), _ptr(tout), _ptr(means),
+        self.L.nmo_env_step(self.h, _ptr(a), a.shape[1], _ptr(obs), _ptr(rew), _ptr(done), _ptr(tout), _ptr(means),
                            ctypes.byref(nres), nthreads)
         return obs, rew, done, tout, means, nres.value
 
     def env_reset_idx(self, ids):
         ids = np.ascontiguousarray(ids, dtype=np.int64)
-        lib().nmo_env_reset_idx(self.h, _ptr(ids), ids.size)
+        self.L.nmo_env_reset_idx(self.h, _ptr(ids), ids.size)
 
     def env_get(self, name: str):
         per = {"ep_len": 1, "commands": 3, "actions": 18, "dof_pos": 18, "dof_vel": 18, "episode_sums": 18,
@@ -138,15 +150,15 @@ class OracleBatch:
                "tibia_f": 6, "feet_f": 6, "body_f": 1, "base_lin_vel": 3, "base_ang_vel": 3, "projected_gravity": 3}.get(name)
         if name == "step_counter":
             buf = np.zeros(1)
-            lib().nmo_env_get(self.h, name.encode(), _ptr(buf), 1)
+            self.L.nmo_env_get(self.h, name.encode(), _ptr(buf), 1)
             return buf[0]
         buf = np.zeros(self.n * per)
-        if lib().nmo_env_get(self.h, name.encode(), _ptr(buf), buf.size) < 0:
+        if self.L.nmo_env_get(self.h, name.encode(), _ptr(buf), buf.size) < 0:
             raise KeyError(name)
         return buf.reshape(self.n, per) if per > 1 else buf
 
     def env_set(self, name: str, values):
         v = np.ascontiguousarray(values, dtype=np.float64).reshape(-1)
-        rc = lib().nmo_env_set(self.h, name.encode(), _ptr(v), v.size)
+        rc = self.L.nmo_env_set(self.h, name.encode(), _ptr(v), v.size)
         if rc != 0:
             raise ValueError(f"env_set({name}) failed: {rc}")

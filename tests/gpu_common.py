@@ -25,6 +25,12 @@ def per_env_rel(a, b, floor=1e-3):
     return np.abs(a - b).max(axis=1) / np.maximum(np.abs(b).max(axis=1), floor)
 
 
+def elem_rel(a, b, floor=1e-2):
+    """element-wise |a-b| / max(|b|, floor), worst element of each env (per_env_rel can hide a large relative error
+    on a small component behind the env's largest one)."""
+    return (np.abs(a - b) / np.maximum(np.abs(b), floor)).max(axis=1)
+
+
 def gpu_state(gb):
     return gb.qpos.cpu().numpy(), gb.qvel.cpu().numpy(), gb.warm.cpu().numpy()
 

@@ -4,8 +4,10 @@ Tolerances (BASELINE.json north_star): qpos/qvel <= 1e-5 relative after one step
 The kernels compute in fp32; errors are reported relative to the largest magnitude of each env's own
 state vector.  Contact-free steps meet 1e-5 outright.  In stiff contact (tibia links of 0.12 kg under
 forces of up to a few hundred N) fp32 rounding is amplified by the constraint solve: the median and the
-99th percentile meet 1e-5 / 2e-5, the worst env out of ~30 000 env-steps is allowed 2e-4; all of it is
-rounding, not semantics (contact sets, solver iteration counts and warm-start decisions are compared too)."""
+99th percentile meet 1e-5; the worst env out of ~30 000 env-steps is asserted against the rounding floor of an
+fp32 implementation, measured in the same test with the oracle's own source compiled in float arithmetic
+(libnm_oracle_f32.so; profiles/r02_fp32_floor.md).  Contact sets, solver iteration counts and warm-start
+decisions are compared too."""
 import numpy as np
 import pytest
 import torch
@@ -53,12 +55,22 @@ def test_in_contact_lockstep(tumbling):
 
     `tumbling`: base orientation uniform over SO(3), spinning at up to 3 rad/s, joints up to +-0.6 rad -- robots land on
     their backs, sides and tibia flanks, so the support-vertex walk on the hulls (warm-started hill climb on the GPU, exhaustive
-    scan in the oracle) is exercised from every direction instead of only near upright."""
+    scan in the oracle) is exercised from every direction instead of only near upright.
+
+    Bound that is asserted.  north_star asks for 1e-5 relative after one step.  The median and the 99th percentile of the
+    per-env error meet it outright.  The worst env-steps do not, and cannot in fp32: the SAME comparison is made here, substep
+    by substep on the same inputs, for `libnm_oracle_f32.so` -- the oracle's own source compiled with float arithmetic
+    (tools/fp32_floor.py, profiles/r02_fp32_floor.md).  Its worst case is the rounding floor of this pipeline (a 0.12 kg
+    tibia in stiff contact amplifies rounding of M, J and qacc_smooth ~1000x); the CUDA kernel's maximum is asserted against
+    that floor, its quantiles against north_star.  Stage attribution (qacc_smooth / contact forces / qacc) is printed for both."""
     G = _common()
     cm, dm, om = G.models()
+    from conftest import NMB
+    om32 = G.O.OracleModel(NMB, variant="f32")
     rng = np.random.default_rng(1 if tumbling else 0)
     n, T = 512, 60
     ob = G.O.OracleBatch(om, n)
+    fb = G.O.OracleBatch(om32, n)
     gb = G.Batch(dm, n, G.DEV, debug=True)
     qpos = np.tile(cm.qpos0, (n, 1))
     qvel = np.zeros((n, 24))
@@ -74,19 +86,26 @@ def test_in_contact_lockstep(tumbling):
         qpos[:, 3:7] += rng.normal(size=(n, 4)) * 0.1
     qpos[:, 3:7] /= np.linalg.norm(qpos[:, 3:7], axis=1, keepdims=True)
     ob.set_state(qpos.astype(np.float32), qvel.astype(np.float32), np.zeros((n, 24)))
-    errs_v, errs_q, errs_s = [], [], []
+    errs_v, errs_q, errs_s, errs_e = [], [], [], []
+    floor_v, floor_q, floor_e = [], [], []
+    st_g = {k: [] for k in ("qacc_smooth", "efc_force", "qacc")}
+    st_f = {k: [] for k in ("qacc_smooth", "efc_force", "qacc")}
     ncon_total = vert_mismatch = contacts = flag_mismatch = 0
+    rel = lambda x, y: np.abs(x - y).max() / max(np.abs(y).max(), 1e-3)
     for t in range(T):
         if t % 4 == 0:
             ctrl = rng.uniform(-8, 8, (n, 18)).astype(np.float32)
         q, v, w = ob.get_state()
         q32, v32, w32 = q.astype(np.float32), v.astype(np.float32), w.astype(np.float32)
         ob.set_state(q32, v32, w32)
+        fb.set_state(q32, v32, w32)
         G.push_state(gb, q32, v32, w32)
         ob.physics_step(ctrl, 1, 8)
+        fb.physics_step(ctrl, 1, 8)
         gb.physics_step(torch.from_numpy(ctrl), 1)
         torch.cuda.synchronize()
         oq, ov, _ = ob.get_state()
+        fq, fv, _ = fb.get_state()
         gq, gv, _ = G.gpu_state(gb)
         dbg = gb.debug.cpu().numpy()
         # --- contact sets: count per env exact, support vertices identical (ties aside)
@@ -94,8 +113,12 @@ def test_in_contact_lockstep(tumbling):
         assert np.array_equal(oncon, dbg[:, 0]), f"substep {t}: contact counts differ"
         ncon_total += int(oncon.sum())
         tie = np.zeros(n, dtype=bool)          # envs whose support vertex differs from the oracle's (equal depth: a tie)
+        ftie = np.zeros(n, dtype=bool)         # same for the fp32 build of the oracle
         for i in np.nonzero(oncon)[0]:
             con = ob.get(i, "contact").reshape(-1, 7)
+            fcon = fb.get(i, "contact").reshape(-1, 7)
+            ftie[i] = fcon.shape != con.shape or not np.array_equal(fcon[:, :3], con[:, :3])
+            gforce = []
             for lane, geom in [(6, 1)] + [(k, 2 + k) for k in range(6)]:
                 mine = con[con[:, 1] == geom]
                 rec = dbg[i, 8 + lane * 12: 8 + lane * 12 + 9]
@@ -106,20 +129,46 @@ def test_in_contact_lockstep(tumbling):
                         vert_mismatch += 1
                         tie[i] = True
                     assert abs(rec[2 + 2 * c] - mine[c, 3]) < 2e-7          # penetration depth [m]
+                    gforce.append(dbg[i, 160 + lane * 16 + 4 * c: 160 + lane * 16 + 4 * c + 4])
+            if not tie[i] and i % 8 == 0:      # stage attribution on a sample of envs (rows are in MuJoCo's order on both sides)
+                of = ob.get(i, "efc_force")
+                st_g["efc_force"].append(rel(np.concatenate(gforce), of))
+                st_g["qacc_smooth"].append(rel(dbg[i, 96:120], ob.get(i, "qacc_smooth")))
+                st_g["qacc"].append(rel(dbg[i, 128:152], ob.get(i, "qacc")))
+                if not ftie[i]:
+                    for k in st_f:
+                        st_f[k].append(rel(fb.get(i, k), ob.get(i, k)))
+        ftie |= np.array([fb.get(i, "ncon")[0] for i in range(n)]) != oncon
         oflag = np.array([ob.get(i, "solver_niter") for i in range(n)])
         flag_mismatch += int((oflag != dbg[:, 1:4]).any(axis=1).sum())
         # a tie (two hull vertices at the same depth, checked to 2e-7 m above) puts the contact point elsewhere on a
         # flat face: a legitimately different, equally valid contact -- not a rounding error, so not in these statistics
         errs_v.append(G.per_env_rel(gv, ov)[~tie]); errs_q.append(G.per_env_rel(gq, oq)[~tie])
+        errs_e.append(G.elem_rel(gv, ov)[~tie])
+        floor_v.append(G.per_env_rel(fv, ov)[~ftie]); floor_q.append(G.per_env_rel(fq, oq)[~ftie])
+        floor_e.append(G.elem_rel(fv, ov)[~ftie])
         osens = np.array([ob.get(i, "sensordata") for i in range(n)])
         errs_s.append((np.abs(gb.sensordata.cpu().numpy() - osens).max(axis=1) / np.maximum(1.0, np.abs(osens).max(axis=1)))[~tie])
-    ev, eq, es = np.concatenate(errs_v), np.concatenate(errs_q), np.concatenate(errs_s)
-    print(f"\n[lockstep{' tumbling' if tumbling else ''}] contacts {contacts} vertex mismatches {vert_mismatch} solver-flag mismatches {flag_mismatch}/{n*T}; "
-          f"qvel rel median {np.median(ev):.2e} p99 {np.percentile(ev, 99):.2e} max {ev.max():.2e}; qpos max {eq.max():.2e}; sensors max {es.max():.2e}")
+    ev, eq, es, ee = (np.concatenate(x) for x in (errs_v, errs_q, errs_s, errs_e))
+    fv_, fq_, fe_ = (np.concatenate(x) for x in (floor_v, floor_q, floor_e))
+    tag = "lockstep tumbling" if tumbling else "lockstep"
+    print(f"\n[{tag}] contacts {contacts} vertex mismatches {vert_mismatch} solver-flag mismatches {flag_mismatch}/{n*T}")
+    print(f"[{tag}] qvel per-env rel   CUDA median {np.median(ev):.2e} p99 {np.percentile(ev, 99):.2e} max {ev.max():.2e} | "
+          f"fp32 oracle median {np.median(fv_):.2e} p99 {np.percentile(fv_, 99):.2e} max {fv_.max():.2e}")
+    print(f"[{tag}] qpos per-env rel   CUDA max {eq.max():.2e} | fp32 oracle max {fq_.max():.2e}; sensors CUDA max {es.max():.2e}")
+    print(f"[{tag}] qvel element-wise rel (|d|/max(|ref|,1e-2))  CUDA median {np.median(ee):.2e} p99 {np.percentile(ee, 99):.2e} max {ee.max():.2e} | "
+          f"fp32 oracle median {np.median(fe_):.2e} p99 {np.percentile(fe_, 99):.2e} max {fe_.max():.2e}")
+    for k in st_g:
+        a, b = np.array(st_g[k]), np.array(st_f[k])
+        print(f"[{tag}] stage {k:12s} rel: CUDA median {np.median(a):.2e} p99 {np.percentile(a, 99):.2e} max {a.max():.2e} | "
+              f"fp32 oracle median {np.median(b):.2e} p99 {np.percentile(b, 99):.2e} max {b.max():.2e}")
     assert ncon_total > (10000 if tumbling else 20000)
     assert vert_mismatch <= max(2, contacts // 2000)
-    assert np.median(ev) < 1e-5 and np.percentile(ev, 99) < 2e-5 and ev.max() < 2e-4
-    assert eq.max() < (2e-5 if tumbling else 1e-5)          # tumbling: qvel up to 18 rad/s through the fp32 quaternion integration
+    # north_star (1e-5 after one step) at the median and the 99th percentile; the maximum against the fp32 floor
+    assert np.median(ev) < 1e-6 and np.percentile(ev, 99) < 1e-5
+    assert ev.max() < max(1e-5, 2.0 * fv_.max())
+    assert np.percentile(eq, 99.9) < 1e-5 and eq.max() < max(1e-5, 3.0 * fq_.max())
+    assert np.percentile(ee, 99) < max(1e-5, 2.0 * np.percentile(fe_, 99))
     assert np.percentile(es, 99) < 1e-4 and es.max() < 2e-3
     assert flag_mismatch < 0.02 * n * T
 

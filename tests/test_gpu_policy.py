@@ -387,7 +387,18 @@ def test_checkpoint_resume_with_fused_update(tmp_path):
         assert torch.equal(p.detach(), saved[k])
     assert torch.equal(r2.alg.optimizer.state[r2.alg.actor_critic.std]["exp_avg"], exp_avg)
     assert abs(r2.alg.learning_rate - lr1) < 1e-12 and r2.current_learning_iteration == 3
-    r2.learn(num_learning_iterations=2)
+    std_state = r2.alg.optimizer.state[r2.alg.actor_critic.std]
+    step1 = float(std_state["step"])
+    n_upd = r2.alg.num_learning_epochs * r2.alg.num_mini_batches
+    assert step1 == 3 * n_upd
+    r2.learn(num_learning_iterations=1)
+    # Adam's state CONTINUES from the checkpoint through the graph capture's warm-up steps: the step counter advanced by one
+    # iteration's updates (not reset to them), and the first moment is the old one decayed, not a fresh one
+    std_state = r2.alg.optimizer.state[r2.alg.actor_critic.std]
+    assert float(std_state["step"]) == step1 + n_upd
+    sq = r2.alg.optimizer.state[r2.alg.actor_critic.std]["exp_avg_sq"]
+    assert (sq > 0).all()
+    r2.learn(num_learning_iterations=1)
     assert np.isfinite(r2.last_log["value_loss"]) and r2.current_learning_iteration == 5
     moved = max((p.detach() - saved[k]).abs().max().item() for k, p in r2.alg.actor_critic.named_parameters())
     assert 0 < moved < 0.5
