@@ -29,6 +29,31 @@
 #endif
 typedef NMO_REAL real;
 
+/* ---- floating-point operation counters (libnm_oracle_cnt.so, -DNMO_COUNT_FLOPS; compiled out otherwise).
+ * Every add / subtract / multiply / divide / sqrt / sin / cos / exp / pow of the restated pipeline adds 1 to the counter of
+ * the stage that is running (an FMA-able multiply-add therefore counts 2).  In the dense linear-algebra loops only
+ * multiply-adds whose two operands are both non-zero are counted, so the figure is that of an implementation which, like
+ * MuJoCo's tree-sparse L'DL and sparse Jacobians, skips structural zeros; the exhaustive support-vertex scan is counted as the
+ * hill climb from vertex 0 that MuJoCo performs (same result).  bench.py reads these as the ALGORITHMIC flops per env-step.
+ * Not thread safe: the counting build is driven with nthreads = 1. */
+enum { ST_KIN = 0, ST_COMPOS, ST_CRB, ST_FACTOR, ST_COLLISION, ST_MAKECON, ST_PROJECT, ST_COMVEL_RNE, ST_ACTUATION, ST_WARMSTART,
+       ST_PGS, ST_NOSLIP, ST_FINISH, ST_SENSOR, ST_INTEGRATE, ST_ENV, ST_COUNT };
+#ifdef NMO_COUNT_FLOPS
+static double g_flops[ST_COUNT];
+static int g_stage = ST_ENV, g_mute = 0;
+#define STAGE(s) (g_stage = (s))
+#define MUTE(on) (g_mute = (on))
+#define FLOP(n) (g_flops[g_stage] += g_mute ? 0.0 : (double)(n))
+#define FLOP_NZ(a, b, n) do { if (!g_mute && (a) != 0 && (b) != 0) g_flops[g_stage] += (double)(n); } while (0)
+void nmo_flop_counts(double* out, int cap) { for (int i = 0; i < ST_COUNT && i < cap; i++) out[i] = g_flops[i]; }
+void nmo_flop_reset(void) { memset(g_flops, 0, sizeof(g_flops)); }
+#else
+#define STAGE(s) ((void)0)
+#define MUTE(on) ((void)0)
+#define FLOP(n) ((void)0)
+#define FLOP_NZ(a, b, n) ((void)0)
+#endif
+
 #define MINVAL 1e-15
 #define MAXVAL 1e10
 #define TOLPLANEMESH 0.3 /* extra plane-mesh contacts must be this fraction of rbound apart (Appendix A.2) */
@@ -178,23 +203,27 @@ int nmo_model_size(const nmo_model* m, const char* w) {
 }
 
 /* ------------------------------------------------------------------------------------------ small math */
-static inline real dot3(const real* a, const real* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+static inline real dot3(const real* a, const real* b) { FLOP(5); return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
 static inline void cross3(real* r, const real* a, const real* b) {
+  FLOP(9);
   real x = a[1] * b[2] - a[2] * b[1], y = a[2] * b[0] - a[0] * b[2], z = a[0] * b[1] - a[1] * b[0];
   r[0] = x; r[1] = y; r[2] = z;
 }
 static inline real normalize3(real* v) {
+  FLOP(4);
   real n = sqrt(dot3(v, v));
   if (n < MINVAL) { v[0] = 1; v[1] = 0; v[2] = 0; return 0; }
   v[0] /= n; v[1] /= n; v[2] /= n;
   return n;
 }
 static inline void normalize4(real* q) {
+  FLOP(12);
   real n = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
   if (n < MINVAL) { q[0] = 1; q[1] = q[2] = q[3] = 0; return; }
   q[0] /= n; q[1] /= n; q[2] /= n; q[3] /= n;
 }
 static inline void mul_quat(real* r, const real* a, const real* b) {
+  FLOP(28);
   real w = a[0] * b[0] - a[1] * b[1] - a[2] * b[2] - a[3] * b[3];
   real x = a[0] * b[1] + a[1] * b[0] + a[2] * b[3] - a[3] * b[2];
   real y = a[0] * b[2] - a[1] * b[3] + a[2] * b[0] + a[3] * b[1];
@@ -202,18 +231,21 @@ static inline void mul_quat(real* r, const real* a, const real* b) {
   r[0] = w; r[1] = x; r[2] = y; r[3] = z;
 }
 static inline void quat2mat(real* m, const real* q) {
+  FLOP(31);
   real w = q[0], x = q[1], y = q[2], z = q[3];
   m[0] = w * w + x * x - y * y - z * z; m[1] = 2 * (x * y - w * z); m[2] = 2 * (x * z + w * y);
   m[3] = 2 * (x * y + w * z); m[4] = w * w - x * x + y * y - z * z; m[5] = 2 * (y * z - w * x);
   m[6] = 2 * (x * z - w * y); m[7] = 2 * (y * z + w * x); m[8] = w * w - x * x - y * y + z * z;
 }
 static inline void mat_vec3(real* r, const real* m, const real* v) {
+  FLOP(15);
   real x = m[0] * v[0] + m[1] * v[1] + m[2] * v[2];
   real y = m[3] * v[0] + m[4] * v[1] + m[5] * v[2];
   real z = m[6] * v[0] + m[7] * v[1] + m[8] * v[2];
   r[0] = x; r[1] = y; r[2] = z;
 }
 static inline void axisangle2quat(real* q, const real* axis, real angle) {
+  FLOP(7);
   real s = sin(0.5 * angle);
   q[0] = cos(0.5 * angle); q[1] = axis[0] * s; q[2] = axis[1] * s; q[3] = axis[2] * s;
 }
@@ -225,6 +257,7 @@ static inline void rot_vec_quat(real* r, const real* v, const real* q) {
 }
 /* spatial inertia (10 numbers: Ixx Iyy Izz Ixy Ixz Iyz, m*r(3), m) times motion vector [w; v] */
 static void mul_inert_vec(real* res, const real* i, const real* v) {
+  FLOP(42);
   res[0] = i[0] * v[0] + i[3] * v[1] + i[4] * v[2] - i[8] * v[4] + i[7] * v[5];
   res[1] = i[3] * v[0] + i[1] * v[1] + i[5] * v[2] + i[8] * v[3] - i[6] * v[5];
   res[2] = i[4] * v[0] + i[5] * v[1] + i[2] * v[2] - i[7] * v[3] + i[6] * v[4];
@@ -234,6 +267,7 @@ static void mul_inert_vec(real* res, const real* i, const real* v) {
 }
 /* motion x motion */
 static void cross_motion(real* r, const real* vel, const real* v) {
+  FLOP(3);
   real a[3], b[3], c[3];
   cross3(a, vel, v);          /* w x v_ang */
   cross3(b, vel, v + 3);      /* w x v_lin */
@@ -243,6 +277,7 @@ static void cross_motion(real* r, const real* vel, const real* v) {
 }
 /* motion x* force */
 static void cross_force(real* r, const real* vel, const real* f) {
+  FLOP(3);
   real a[3], b[3], c[3];
   cross3(a, vel, f);          /* w x f_ang */
   cross3(b, vel + 3, f + 3);  /* v x f_lin */
@@ -365,6 +400,7 @@ static void data_free(data_t* d) {
 
 /* ------------------------------------------------------------------------------------------ P1 kinematics */
 static void kinematics(const nmo_model* m, data_t* d) {
+  STAGE(ST_KIN);
   real* xpos = d->xpos; real* xquat = d->xquat; real* xmat = d->xmat;
   xpos[0] = xpos[1] = xpos[2] = 0;
   xquat[0] = 1; xquat[1] = xquat[2] = xquat[3] = 0;
@@ -385,12 +421,14 @@ static void kinematics(const nmo_model* m, data_t* d) {
       real t[3];
       mat_vec3(t, xmat + 9 * pid, m->body_pos + 3 * i);
       for (int k = 0; k < 3; k++) pos[k] = xpos[3 * pid + k] + t[k];
+      FLOP(3);
       mul_quat(quat, xquat + 4 * pid, m->body_quat + 4 * i);
       for (int j = ja; j < ja + jn; j++) {
         real mat[9], anchor[3], axis[3];
         quat2mat(mat, quat);
         mat_vec3(anchor, mat, m->jnt_pos + 3 * j);
         for (int k = 0; k < 3; k++) anchor[k] += pos[k];
+        FLOP(7);
         mat_vec3(axis, mat, m->jnt_axis + 3 * j);
         memcpy(d->xanchor + 3 * j, anchor, sizeof(anchor));
         memcpy(d->xaxis + 3 * j, axis, sizeof(axis));
@@ -415,6 +453,7 @@ static void kinematics(const nmo_model* m, data_t* d) {
     real t[3], qi[4];
     mat_vec3(t, xmat + 9 * i, m->body_ipos + 3 * i);
     for (int k = 0; k < 3; k++) d->xipos[3 * i + k] = pos[k] + t[k];
+    FLOP(3);
     mul_quat(qi, quat, m->body_iquat + 4 * i);
     quat2mat(d->ximat + 9 * i, qi);
   }
@@ -423,12 +462,15 @@ static void kinematics(const nmo_model* m, data_t* d) {
     real t[3];
     mat_vec3(t, xmat + 9 * b, m->site_pos + 3 * s);
     for (int k = 0; k < 3; k++) d->site_xpos[3 * s + k] = xpos[3 * b + k] + t[k];
+    FLOP(3);
   }
 }
 
 /* ------------------------------------------------------------------------------------------ P2 comPos */
 static void com_pos(const nmo_model* m, data_t* d) {
+  STAGE(ST_COMPOS);
   int nb = m->nbody;
+  FLOP(3 * nb + 4 * (nb - 1) + 3 * nb);   /* mass-weighted positions, subtree accumulation, division */
   real* smass = d->scratch;
   for (int i = 0; i < nb; i++) {
     smass[i] = m->body_mass[i];
@@ -466,6 +508,7 @@ static void com_pos(const nmo_model* m, data_t* d) {
     ci[5] -= mass * r[1] * r[2];
     ci[6] = mass * r[0]; ci[7] = mass * r[1]; ci[8] = mass * r[2];
     ci[9] = mass;
+    FLOP(3 + 6 * 8 + 9 + 12 + 3);         /* r, R diag(I) R^T (6 entries), parallel-axis terms, m*r */
   }
   memset(d->cinert, 0, 10 * sizeof(real));
   for (int j = 0; j < m->njnt; j++) {
@@ -473,6 +516,7 @@ static void com_pos(const nmo_model* m, data_t* d) {
     const real* c = d->subtree_com + 3 * m->body_rootid[b];
     real off[3];
     for (int k = 0; k < 3; k++) off[k] = c[k] - d->xanchor[3 * j + k];
+    FLOP(3);
     if (m->jnt_type[j] == JNT_FREE) {
       for (int k = 0; k < 3; k++) {
         real* cd = d->cdof + 6 * (da + k);
@@ -502,13 +546,15 @@ static int cholesky(real* L, const real* A, int n) {
   memcpy(L, A, sizeof(real) * n * n);
   for (int j = 0; j < n; j++) {
     real s = L[j * n + j];
-    for (int k = 0; k < j; k++) s -= L[j * n + k] * L[j * n + k];
+    for (int k = 0; k < j; k++) { FLOP_NZ(L[j * n + k], L[j * n + k], 2); s -= L[j * n + k] * L[j * n + k]; }
     if (s < MINVAL) return -1;
     s = sqrt(s);
+    FLOP(1);
     L[j * n + j] = s;
     for (int i = j + 1; i < n; i++) {
       real t = L[i * n + j];
-      for (int k = 0; k < j; k++) t -= L[i * n + k] * L[j * n + k];
+      for (int k = 0; k < j; k++) { FLOP_NZ(L[i * n + k], L[j * n + k], 2); t -= L[i * n + k] * L[j * n + k]; }
+      FLOP_NZ(t, 1, 1);
       L[i * n + j] = t / s;
     }
     for (int k = j + 1; k < n; k++) L[j * n + k] = 0;
@@ -518,22 +564,25 @@ static int cholesky(real* L, const real* A, int n) {
 static void chol_solve(const real* L, int n, real* x) {
   for (int i = 0; i < n; i++) {
     real s = x[i];
-    for (int k = 0; k < i; k++) s -= L[i * n + k] * x[k];
+    for (int k = 0; k < i; k++) { FLOP_NZ(L[i * n + k], x[k], 2); s -= L[i * n + k] * x[k]; }
+    FLOP_NZ(s, 1, 1);
     x[i] = s / L[i * n + i];
   }
   for (int i = n - 1; i >= 0; i--) {
     real s = x[i];
-    for (int k = i + 1; k < n; k++) s -= L[k * n + i] * x[k];
+    for (int k = i + 1; k < n; k++) { FLOP_NZ(L[k * n + i], x[k], 2); s -= L[k * n + i] * x[k]; }
+    FLOP_NZ(s, 1, 1);
     x[i] = s / L[i * n + i];
   }
 }
 
 static void crb(const nmo_model* m, data_t* d) {
+  STAGE(ST_CRB);
   int nv = m->nv, nb = m->nbody;
   memcpy(d->crb, d->cinert, sizeof(real) * 10 * nb);
   for (int i = nb - 1; i > 0; i--) {
     int p = m->body_parent[i];
-    if (p > 0) for (int k = 0; k < 10; k++) d->crb[10 * p + k] += d->crb[10 * i + k];
+    if (p > 0) { FLOP(10); for (int k = 0; k < 10; k++) d->crb[10 * p + k] += d->crb[10 * i + k]; }
   }
   memset(d->M, 0, sizeof(real) * nv * nv);
   for (int i = 0; i < nv; i++) {
@@ -541,11 +590,12 @@ static void crb(const nmo_model* m, data_t* d) {
     mul_inert_vec(buf, d->crb + 10 * m->dof_body[i], d->cdof + 6 * i);
     for (int j = i; j >= 0; j = m->dof_parent[j]) {
       real s = 0;
-      for (int k = 0; k < 6; k++) s += d->cdof[6 * j + k] * buf[k];
+      for (int k = 0; k < 6; k++) { FLOP_NZ(d->cdof[6 * j + k], buf[k], 2); s += d->cdof[6 * j + k] * buf[k]; }
       d->M[i * nv + j] = d->M[j * nv + i] = s;
     }
     d->M[i * nv + i] += m->dof_armature[i];
   }
+  STAGE(ST_FACTOR);
   if (cholesky(d->L, d->M, nv) != 0) d->nwarn++;
 }
 
@@ -581,7 +631,31 @@ static void mix_params(const nmo_model* m, int g1, int g2, contact_t* c) {
               (m->geom_gap[g1] > m->geom_gap[g2] ? m->geom_gap[g1] : m->geom_gap[g2]);
 }
 
+#ifdef NMO_COUNT_FLOPS
+/* operations of the hill climb from hull vertex 0 to the support vertex (what mjc_PlaneConvex does): one 5-flop dot
+ * product per neighbour examined; rotating the direction into the geom frame costs 15 */
+static void count_hill_climb(const nmo_model* m, int adr, int num, const real* R, const real* n) {
+  real dl[3] = {R[0] * n[0] + R[3] * n[1] + R[6] * n[2], R[1] * n[0] + R[4] * n[1] + R[7] * n[2], R[2] * n[0] + R[5] * n[1] + R[8] * n[2]};
+  FLOP(15 + 5);
+  int best = 0;
+  real bv = dl[0] * m->hull_vert[3 * adr] + dl[1] * m->hull_vert[3 * adr + 1] + dl[2] * m->hull_vert[3 * adr + 2];
+  for (;;) {
+    int nb = best;
+    for (int e = m->hull_nbr_adr[adr + best]; e < m->hull_nbr_adr[adr + best + 1]; e++) {
+      int v = m->hull_nbr[e];
+      real val = dl[0] * m->hull_vert[3 * (adr + v)] + dl[1] * m->hull_vert[3 * (adr + v) + 1] + dl[2] * m->hull_vert[3 * (adr + v) + 2];
+      FLOP(5);
+      if (val < bv) { bv = val; nb = v; }
+    }
+    if (nb == best) break;
+    best = nb;
+  }
+  (void)num;
+}
+#endif
+
 static void collision(const nmo_model* m, data_t* d) {
+  STAGE(ST_COLLISION);
   d->ncon = 0;
   for (int g = 0; g < m->ngeom; g++) {
     int pg = m->geom_plane[g];
@@ -603,6 +677,10 @@ static void collision(const nmo_model* m, data_t* d) {
          (MuJoCo hill-climbs the hull graph; identical on a convex hull except for exact ties) */
       int best = -1;
       real bestd = 0, bestw[3] = {0, 0, 0};
+#ifdef NMO_COUNT_FLOPS
+      count_hill_climb(m, adr, num, R, n);
+#endif
+      MUTE(1);                                   /* the exhaustive scan is counted as the hill climb above */
       for (int v = 0; v < num; v++) {
         real lv[3] = {m->hull_vert[3 * (adr + v)], m->hull_vert[3 * (adr + v) + 1], m->hull_vert[3 * (adr + v) + 2]};
         real w[3];
@@ -611,6 +689,8 @@ static void collision(const nmo_model* m, data_t* d) {
         real dist = (w[0] - ppos[0]) * n[0] + (w[1] - ppos[1]) * n[1] + (w[2] - ppos[2]) * n[2];
         if (best < 0 || dist < bestd) { best = v; bestd = dist; memcpy(bestw, w, sizeof(w)); }
       }
+      MUTE(0);
+      FLOP(15 + 3 + 8);                          /* support vertex to world, distance to the plane */
       if (best < 0 || bestd > margin) continue;
       int first = d->ncon, cnt = 0;
       for (int pass = 0; pass < 2; pass++) {
@@ -626,10 +706,12 @@ static void collision(const nmo_model* m, data_t* d) {
             mat_vec3(w, R, lv);
             for (int k = 0; k < 3; k++) w[k] += p[k];
             dist = (w[0] - ppos[0]) * n[0] + (w[1] - ppos[1]) * n[1] + (w[2] - ppos[2]) * n[2];
+            FLOP(3 + 8);
             if (dist > margin) continue;
           }
           real cp[3];
           for (int k = 0; k < 3; k++) cp[k] = w[k] - 0.5 * dist * n[k];
+          FLOP(7 + 9 * cnt);
           int tooclose = 0;
           for (int c = first; c < first + cnt; c++) {
             real dx = d->con[c].pos[0] - cp[0], dy = d->con[c].pos[1] - cp[1], dz = d->con[c].pos[2] - cp[2];
@@ -677,11 +759,13 @@ static void jac_point(const nmo_model* m, const data_t* d, int body, const real*
   for (int i = m->body_dofadr[b] + m->body_dofnum[b] - 1; i >= 0; i = m->dof_parent[i]) {
     real t[3];
     cross3(t, d->cdof + 6 * i, off);
+    FLOP(3);
     for (int k = 0; k < 3; k++) jacp[k * nv + i] = d->cdof[6 * i + 3 + k] + t[k];
   }
 }
 
 static real impedance(const real* solimp, real pos, real margin) {
+  FLOP(8);
   real dmin = solimp[0], dmax = solimp[1], width = solimp[2], mid = solimp[3], power = solimp[4];
   if (dmin < 0.0001) dmin = 0.0001; if (dmin > 0.9999) dmin = 0.9999;
   if (dmax < 0.0001) dmax = 0.0001; if (dmax > 0.9999) dmax = 0.9999;
@@ -699,6 +783,7 @@ static real impedance(const real* solimp, real pos, real margin) {
 }
 
 static void make_constraint(const nmo_model* m, data_t* d) {
+  STAGE(ST_MAKECON);
   int nv = m->nv;
   d->nefc = 0;
   real* jac1 = d->scratch;            /* 3 x nv */
@@ -714,7 +799,7 @@ static void make_constraint(const nmo_model* m, data_t* d) {
     for (int r = 0; r < 3; r++)
       for (int i = 0; i < nv; i++) {
         real s = 0;
-        for (int k = 0; k < 3; k++) s += c->frame[3 * r + k] * (jac2[k * nv + i] - jac1[k * nv + i]);
+        for (int k = 0; k < 3; k++) { FLOP_NZ(jac2[k * nv + i] - jac1[k * nv + i], 1, 3); s += c->frame[3 * r + k] * (jac2[k * nv + i] - jac1[k * nv + i]); }
         Jc[r][i] = s;
       }
     real tran = m->body_invweight0[2 * c->body1] + m->body_invweight0[2 * c->body2];
@@ -722,7 +807,8 @@ static void make_constraint(const nmo_model* m, data_t* d) {
       int e = d->nefc++;
       int t = 1 + r / 2;
       real sgn = (r % 2 == 0) ? 1.0 : -1.0;
-      for (int i = 0; i < nv; i++) d->efc_J[e * nv + i] = Jc[0][i] + sgn * c->mu * Jc[t][i];
+      for (int i = 0; i < nv; i++) { FLOP_NZ(Jc[0][i], 1, 2); d->efc_J[e * nv + i] = Jc[0][i] + sgn * c->mu * Jc[t][i]; }
+      FLOP(3);
       d->efc_pos[e] = c->dist;
       d->efc_margin[e] = c->margin;
       d->efc_diagApprox[e] = tran + c->mu * c->mu * tran;
@@ -751,7 +837,8 @@ static void make_constraint(const nmo_model* m, data_t* d) {
       if (R < MINVAL) R = MINVAL;
       d->efc_R[e] = R;
       real vel = 0;
-      for (int i = 0; i < nv; i++) vel += d->efc_J[e * nv + i] * d->qvel[i];
+      FLOP(4 + 6);
+      for (int i = 0; i < nv; i++) { FLOP_NZ(d->efc_J[e * nv + i], d->qvel[i], 2); vel += d->efc_J[e * nv + i] * d->qvel[i]; }
       d->efc_vel[e] = vel;
       d->efc_aref[e] = -B * vel - K * imp * (d->efc_pos[e] - d->efc_margin[e]);
     }
@@ -765,6 +852,7 @@ static void make_constraint(const nmo_model* m, data_t* d) {
 
 /* ------------------------------------------------------------------------------------------ P6 projectConstraint */
 static void project_constraint(const nmo_model* m, data_t* d) {
+  STAGE(ST_PROJECT);
   int nv = m->nv, ne = d->nefc;
   real* X = d->scratch + 16 * nv;  /* ne x nv : rows = M^-1 J_e^T */
   for (int e = 0; e < ne; e++) {
@@ -774,13 +862,15 @@ static void project_constraint(const nmo_model* m, data_t* d) {
   for (int a = 0; a < ne; a++)
     for (int b = 0; b < ne; b++) {
       real s = 0;
-      for (int i = 0; i < nv; i++) s += d->efc_J[a * nv + i] * X[b * nv + i];
+      /* A is symmetric: an implementation computes the upper triangle once (count b >= a only) */
+      for (int i = 0; i < nv; i++) { if (b >= a) FLOP_NZ(d->efc_J[a * nv + i], X[b * nv + i], 2); s += d->efc_J[a * nv + i] * X[b * nv + i]; }
       d->efc_AR[a * ne + b] = s + (a == b ? d->efc_R[a] : 0);
     }
 }
 
 /* ------------------------------------------------------------------------------------------ P7 comVel + rne */
 static void com_vel(const nmo_model* m, data_t* d) {
+  STAGE(ST_COMVEL_RNE);
   memset(d->cvel, 0, 6 * sizeof(real));
   for (int i = 1; i < m->nbody; i++) {
     real cvel[6];
@@ -790,15 +880,16 @@ static void com_vel(const nmo_model* m, data_t* d) {
       if (m->jnt_type[j] == JNT_FREE) {
         for (int k = 0; k < 3; k++) {
           memset(d->cdof_dot + 6 * (bda + k), 0, 6 * sizeof(real));
-          for (int c = 0; c < 6; c++) cvel[c] += d->cdof[6 * (bda + k) + c] * d->qvel[bda + k];
+          for (int c = 0; c < 6; c++) { FLOP_NZ(d->cdof[6 * (bda + k) + c], d->qvel[bda + k], 2); cvel[c] += d->cdof[6 * (bda + k) + c] * d->qvel[bda + k]; }
         }
         bda += 3;
         for (int k = 0; k < 3; k++) cross_motion(d->cdof_dot + 6 * (bda + k), cvel, d->cdof + 6 * (bda + k));
         for (int k = 0; k < 3; k++)
-          for (int c = 0; c < 6; c++) cvel[c] += d->cdof[6 * (bda + k) + c] * d->qvel[bda + k];
+          for (int c = 0; c < 6; c++) { FLOP_NZ(d->cdof[6 * (bda + k) + c], d->qvel[bda + k], 2); cvel[c] += d->cdof[6 * (bda + k) + c] * d->qvel[bda + k]; }
         bda += 3;
       } else {
         cross_motion(d->cdof_dot + 6 * bda, cvel, d->cdof + 6 * bda);
+        FLOP(12);
         for (int c = 0; c < 6; c++) cvel[c] += d->cdof[6 * bda + c] * d->qvel[bda];
         bda++;
       }
@@ -819,20 +910,21 @@ static void rne(const nmo_model* m, data_t* d, real* result) {
     memcpy(cacc + 6 * i, cacc + 6 * m->body_parent[i], 6 * sizeof(real));
     for (int j = 0; j < m->body_dofnum[i]; j++) {
       int dd = m->body_dofadr[i] + j;
-      for (int c = 0; c < 6; c++) cacc[6 * i + c] += d->cdof_dot[6 * dd + c] * d->qvel[dd];
+      for (int c = 0; c < 6; c++) { FLOP_NZ(d->cdof_dot[6 * dd + c], d->qvel[dd], 2); cacc[6 * i + c] += d->cdof_dot[6 * dd + c] * d->qvel[dd]; }
     }
     mul_inert_vec(cfrc + 6 * i, d->cinert + 10 * i, cacc + 6 * i);
     mul_inert_vec(tmp, d->cinert + 10 * i, d->cvel + 6 * i);
     cross_force(tmp1, d->cvel + 6 * i, tmp);
     for (int c = 0; c < 6; c++) cfrc[6 * i + c] += tmp1[c];
+    FLOP(6);
   }
   for (int i = nb - 1; i > 0; i--) {
     int p = m->body_parent[i];
-    if (p > 0) for (int c = 0; c < 6; c++) cfrc[6 * p + c] += cfrc[6 * i + c];
+    if (p > 0) { FLOP(6); for (int c = 0; c < 6; c++) cfrc[6 * p + c] += cfrc[6 * i + c]; }
   }
   for (int i = 0; i < nv; i++) {
     real s = 0;
-    for (int c = 0; c < 6; c++) s += d->cdof[6 * i + c] * cfrc[6 * m->dof_body[i] + c];
+    for (int c = 0; c < 6; c++) { FLOP_NZ(d->cdof[6 * i + c], 1, 2); s += d->cdof[6 * i + c] * cfrc[6 * m->dof_body[i] + c]; }
     result[i] = s;
   }
 }
@@ -843,6 +935,8 @@ static void fwd_velocity_actuation_acceleration(const nmo_model* m, data_t* d) {
   com_vel(m, d);
   for (int i = 0; i < nv; i++) d->qfrc_passive[i] = -m->dof_damping[i] * d->qvel[i];
   rne(m, d, d->qfrc_bias);
+  STAGE(ST_ACTUATION);
+  FLOP(nv);
   memset(d->qfrc_actuator, 0, sizeof(real) * nv);
   for (int a = 0; a < m->nu; a++) {
     real ctrl = d->ctrl[a];
@@ -859,26 +953,30 @@ static void fwd_velocity_actuation_acceleration(const nmo_model* m, data_t* d) {
       if (f > m->act_forcerange[2 * a + 1]) f = m->act_forcerange[2 * a + 1];
     }
     d->act_force[a] = f;
+    FLOP(10);
     d->qfrc_actuator[dof] += gear * f;
   }
   for (int i = 0; i < nv; i++) {
     d->qfrc_smooth[i] = d->qfrc_passive[i] - d->qfrc_bias[i] + d->qfrc_actuator[i];
     d->qacc_smooth[i] = d->qfrc_smooth[i];
   }
+  FLOP(2 * nv);
   chol_solve(d->L, nv, d->qacc_smooth);
 }
 
 /* ------------------------------------------------------------------------------------------ P9 constraint solve */
 static void dual_finish(const nmo_model* m, data_t* d) {
+  STAGE(ST_FINISH);
   int nv = m->nv, ne = d->nefc;
   for (int i = 0; i < nv; i++) {
     real s = 0;
-    for (int e = 0; e < ne; e++) s += d->efc_J[e * nv + i] * d->efc_force[e];
+    for (int e = 0; e < ne; e++) { FLOP_NZ(d->efc_J[e * nv + i], d->efc_force[e], 2); s += d->efc_J[e * nv + i] * d->efc_force[e]; }
     d->qfrc_constraint[i] = s;
     d->qacc[i] = s;
   }
   chol_solve(d->L, nv, d->qacc);
   for (int i = 0; i < nv; i++) d->qacc[i] += d->qacc_smooth[i];
+  FLOP(nv);
 }
 
 static void fwd_constraint(const nmo_model* m, data_t* d) {
@@ -893,32 +991,38 @@ static void fwd_constraint(const nmo_model* m, data_t* d) {
   }
   const real* AR = d->efc_AR;
   real* f = d->efc_force;
+  STAGE(ST_WARMSTART);
   /* b = J qacc_smooth - aref */
   for (int e = 0; e < ne; e++) {
     real s = 0;
-    for (int i = 0; i < nv; i++) s += d->efc_J[e * nv + i] * d->qacc_smooth[i];
+    FLOP(1);
+    for (int i = 0; i < nv; i++) { FLOP_NZ(d->efc_J[e * nv + i], 1, 2); s += d->efc_J[e * nv + i] * d->qacc_smooth[i]; }
     d->efc_b[e] = s - d->efc_aref[e];
   }
   /* warm start: forces implied by qacc_warmstart, kept only if their dual cost beats f = 0 */
   for (int e = 0; e < ne; e++) {
     real jar = -d->efc_aref[e];
-    for (int i = 0; i < nv; i++) jar += d->efc_J[e * nv + i] * d->qacc_warmstart[i];
+    FLOP(2);
+    for (int i = 0; i < nv; i++) { FLOP_NZ(d->efc_J[e * nv + i], d->qacc_warmstart[i], 2); jar += d->efc_J[e * nv + i] * d->qacc_warmstart[i]; }
     f[e] = jar < 0 ? -d->efc_D[e] * jar : 0;
   }
   real cost = 0;
   for (int a = 0; a < ne; a++) {
     real s = 0;
-    for (int b = 0; b < ne; b++) s += AR[a * ne + b] * f[b];
+    for (int b = 0; b < ne; b++) { FLOP_NZ(AR[a * ne + b], f[b], 2); s += AR[a * ne + b] * f[b]; }
+    FLOP(5);
     cost += 0.5 * f[a] * s + f[a] * d->efc_b[a];
   }
   if (cost > 0) memset(f, 0, sizeof(real) * ne); else d->warm_used = 1;
 
   real scale = 1.0 / (m->meaninertia * (nv > 1 ? nv : 1));
   /* PGS (pyramidal rows are scalar inequality constraints) */
+  STAGE(ST_PGS);
   for (int it = 0; it < m->iterations; it++) {
     real improvement = 0;
     for (int e = 0; e < ne; e++) {
       real res = d->efc_b[e];
+      FLOP(2 * ne + 10);                        /* residual of a dense row of A, update, cost change */
       for (int b = 0; b < ne; b++) res += AR[e * ne + b] * f[b];
       real old = f[e];
       f[e] -= res / AR[e * ne + e];
@@ -936,6 +1040,7 @@ static void fwd_constraint(const nmo_model* m, data_t* d) {
 
   /* noslip post-processing: friction dimensions re-solved without regularisation */
   if (m->noslip_iterations > 0) {
+    STAGE(ST_NOSLIP);
     for (int it = 0; it < m->noslip_iterations; it++) {
       real improvement = 0;
       for (int ci = 0; ci < d->ncon; ci++) {
@@ -943,6 +1048,7 @@ static void fwd_constraint(const nmo_model* m, data_t* d) {
         if (e0 < 0) continue;
         for (int j = e0; j < e0 + 4; j += 2) {
           real res[2], old[2] = {f[j], f[j + 1]};
+          FLOP(2 * (2 * ne + 2) + 40);            /* two dense-row residuals, the 2x2 pair problem, cost change */
           for (int k = 0; k < 2; k++) {
             real s = d->efc_b[j + k];
             for (int b = 0; b < ne; b++) s += AR[(j + k) * ne + b] * f[b];
@@ -987,6 +1093,7 @@ static real ray_sphere(const real* center, real radius, const real* pnt, const r
 }
 
 static void sensor_touch(const nmo_model* m, data_t* d) {
+  STAGE(ST_SENSOR);
   for (int s = 0; s < m->nsensor; s++) {
     int site = m->sensor_site[s], body = m->site_body[site];
     real sum = 0;
@@ -996,6 +1103,7 @@ static void sensor_touch(const nmo_model* m, data_t* d) {
       real fn = 0;
       for (int r = 0; r < 4; r++) fn += d->efc_force[c->efc_address + r];
       if (fn <= 0) continue;
+      FLOP(3 + 3 + 25);
       real ray[3] = {c->frame[0] * fn, c->frame[1] * fn, c->frame[2] * fn};
       normalize3(ray);
       if (c->body2 == body) { ray[0] = -ray[0]; ray[1] = -ray[1]; ray[2] = -ray[2]; }
@@ -1019,6 +1127,7 @@ static void forward(const nmo_model* m, data_t* d) {
 }
 
 static void integrate_pos(const nmo_model* m, real* qpos, const real* qvel, real h) {
+  FLOP(2 * m->nv);
   for (int j = 0; j < m->njnt; j++) {
     int qa = m->jnt_qposadr[j], da = m->jnt_dofadr[j];
     if (m->jnt_type[j] == JNT_FREE) {
@@ -1057,6 +1166,8 @@ static void step1(const nmo_model* m, data_t* d) {
   for (int i = 0; i < nv; i++)
     if (!(fabs(d->qacc[i]) < MAXVAL)) { reset_data(m, d); forward(m, d); break; }   /* ≙ mj_checkAcc */
   real* qacc = d->scratch;
+  STAGE(ST_INTEGRATE);
+  FLOP(2 * nv + 2 * nv + 3 * m->nu);
   if (m->integrator == INT_IMPLICITFAST || m->integrator == INT_IMPLICIT) {
     /* implicitfast: qDeriv = d(qfrc_smooth)/d(qvel) restricted to actuator + passive terms (diagonal here) */
     real* A = d->MH;
@@ -1313,6 +1424,9 @@ static void env_step_one(nmo_batch* b, int i, const float* act, float* obs, floa
   const cfg_t* c = &b->cfg;
   data_t* d = b->d + i;
   envstate_t* e = b->e + i;
+  STAGE(ST_ENV);
+  /* E1/E3 36+54, E7 3 rotations 3*(31+15), E9 36+6, E11 ~20, E14 active terms ~200, E15 ~70 + clip */
+  FLOP(90 + 138 + 42 + 20 + 200 + 70);
   /* E1 */
   real prev_dof_vel[18];
   for (int j = 0; j < 18; j++) {
@@ -1327,6 +1441,7 @@ static void env_step_one(nmo_batch* b, int i, const float* act, float* obs, floa
   for (int j = 0; j < 18; j++) d->ctrl[j] = ((e->actions[j] - c->default_pos[j]) - e->dof_pos[j]) * c->p_gain;
   /* E5 */
   for (int s = 0; s < c->decimation; s++) step1(m, d);
+  STAGE(ST_ENV);
   /* E6 */
   e->ep_len += 1;
   /* E7: base frame quantities; cvel/xipos/sensordata are one substep stale (quirk Q4) */
@@ -1476,6 +1591,8 @@ int nmo_env_set(nmo_batch* b, const char* name, const double* in, int count) {
   ESET("ep_len", b->e[i].ep_len, int64_t, 1) ESET("commands", b->e[i].commands[k], real, 3)
   ESET("actions", b->e[i].actions[k], real, 18) ESET("dof_pos", b->e[i].dof_pos[k], real, 18)
   ESET("dof_vel", b->e[i].dof_vel[k], real, 18) ESET("episode_sums", b->e[i].episode_sums[k], real, NMO_NREW)
+  ESET("feet_air_time", b->e[i].feet_air_time[k], real, 6) ESET("last_contacts", b->e[i].last_contacts[k], int, 6)
+  ESET("last_contacts_filt", b->e[i].last_contacts_filt[k], int, 6)
   if (!strcmp(name, "step_counter")) { b->step_counter = (int64_t)in[0]; return 0; }
   return -1;
 }
