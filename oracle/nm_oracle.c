@@ -69,6 +69,8 @@ struct nmo_model {
   int nq, nv, nu, nbody, njnt, ngeom, nsite, nsensor, nhv, nhn;
   int integrator, solver, cone, iterations, noslip_iterations, eulerdamp;
   int planemesh_maxcon; /* contacts per plane-mesh pair (opt_int[7]; 4 when the model file predates the entry) */
+  int mpr_iterations;   /* opt_int[8], MuJoCo default 50 */
+  real mpr_tolerance;   /* opt_real[8], MuJoCo default 1e-6 */
   real timestep, gravity[3], tolerance, noslip_tolerance, impratio, meaninertia;
   const real *qpos0, *body_pos, *body_quat, *body_ipos, *body_iquat, *body_mass, *body_inertia, *body_invweight0;
   const int *body_parent, *body_rootid, *body_jntadr, *body_jntnum, *body_dofadr, *body_dofnum;
@@ -78,8 +80,8 @@ struct nmo_model {
   const real *dof_damping, *dof_armature;
   const int *act_dof, *act_ctrllimited, *act_forcelimited;
   const real *act_gain, *act_bias, *act_gear, *act_ctrlrange, *act_forcerange;
-  const int *geom_type, *geom_body, *geom_condim, *geom_priority, *geom_plane, *geom_hull_adr, *geom_hull_num;
-  const real *geom_pos, *geom_quat, *geom_size, *geom_friction, *geom_solref, *geom_solimp, *geom_margin, *geom_gap, *geom_rbound;
+  const int *geom_type, *geom_body, *geom_condim, *geom_priority, *geom_plane, *geom_hull_adr, *geom_hull_num, *geom_contype, *geom_conaffinity;
+  const real *geom_pos, *geom_quat, *geom_size, *geom_friction, *geom_solref, *geom_solimp, *geom_margin, *geom_gap, *geom_rbound, *geom_center;
   const float* hull_vert;
   const int *hull_nbr_adr, *hull_nbr;
   const int *site_body, *sensor_site;
@@ -156,15 +158,18 @@ nmo_model* nmo_model_load(const char* path, char* err, int errlen) {
   const int* sizes = (const int*)nmb_find(m->raw, "sizes", NULL, NULL);
   long long noi = 0;
   const int* oi = (const int*)nmb_find(m->raw, "opt_int", NULL, &noi);
-  const double* orl = (const double*)nmb_find(m->raw, "opt_real", NULL, NULL);
+  long long norl = 0;
+  const double* orl = (const double*)nmb_find(m->raw, "opt_real", NULL, &norl);
   if (!sizes || !oi || !orl) { snprintf(err, errlen, "nmb: missing header arrays"); nmo_model_free(m); return NULL; }
   m->nq = sizes[0]; m->nv = sizes[1]; m->nu = sizes[2]; m->nbody = sizes[3]; m->njnt = sizes[4];
   m->ngeom = sizes[5]; m->nsite = sizes[6]; m->nsensor = sizes[7]; m->nhv = sizes[8]; m->nhn = sizes[9];
   m->integrator = oi[0]; m->solver = oi[1]; m->cone = oi[2]; m->iterations = oi[3];
   m->noslip_iterations = oi[4]; m->eulerdamp = oi[5];
   m->planemesh_maxcon = (noi > 7 && oi[7] >= 1 && oi[7] <= 4) ? oi[7] : 4;
+  m->mpr_iterations = (noi > 8 && oi[8] > 0) ? oi[8] : 50;
   m->timestep = orl[0]; m->gravity[0] = orl[1]; m->gravity[1] = orl[2]; m->gravity[2] = orl[3];
   m->tolerance = orl[4]; m->noslip_tolerance = orl[5]; m->impratio = orl[6]; m->meaninertia = orl[7];
+  m->mpr_tolerance = (norl > 8 && orl[8] > 0) ? (real)orl[8] : (real)1e-6;
   GETR(qpos0); GETR(body_pos); GETR(body_quat); GETR(body_ipos);
   GETR(body_iquat); GETR(body_mass); GETR(body_inertia); GETR(body_invweight0);
   GETP(body_parent, int); GETP(body_rootid, int); GETP(body_jntadr, int); GETP(body_jntnum, int);
@@ -175,9 +180,9 @@ nmo_model* nmo_model_load(const char* path, char* err, int errlen) {
   GETP(act_dof, int); GETP(act_ctrllimited, int); GETP(act_forcelimited, int);
   GETR(act_gain); GETR(act_bias); GETR(act_gear); GETR(act_ctrlrange); GETR(act_forcerange);
   GETP(geom_type, int); GETP(geom_body, int); GETP(geom_condim, int); GETP(geom_priority, int); GETP(geom_plane, int);
-  GETP(geom_hull_adr, int); GETP(geom_hull_num, int);
+  GETP(geom_hull_adr, int); GETP(geom_hull_num, int); GETP(geom_contype, int); GETP(geom_conaffinity, int);
   GETR(geom_pos); GETR(geom_quat); GETR(geom_size); GETR(geom_friction);
-  GETR(geom_solref); GETR(geom_solimp); GETR(geom_margin); GETR(geom_gap); GETR(geom_rbound);
+  GETR(geom_solref); GETR(geom_solimp); GETR(geom_margin); GETR(geom_gap); GETR(geom_rbound); GETR(geom_center);
   GETP(hull_vert, float); GETP(hull_nbr_adr, int); GETP(hull_nbr, int);
   GETP(site_body, int); GETP(sensor_site, int); GETR(site_pos); GETR(site_size);
   return m;
@@ -307,6 +312,7 @@ typedef struct {
   contact_t con[NMO_MAXCON];
   real *efc_J, *efc_pos, *efc_margin, *efc_diagApprox, *efc_R, *efc_D, *efc_aref, *efc_vel, *efc_b, *efc_force, *efc_AR;
   int solver_niter, noslip_niter, warm_used, nwarn;
+  long nmpr;            /* narrow-phase (MPR) calls so far */
   real* sensordata;
   real* scratch;   /* >= 8*nv + MAXEFC*nv */
 } data_t;
@@ -631,6 +637,214 @@ static void mix_params(const nmo_model* m, int g1, int g2, contact_t* c) {
               (m->geom_gap[g1] > m->geom_gap[g2] ? m->geom_gap[g1] : m->geom_gap[g2]);
 }
 
+
+/* ------------------------------------------------------------------------------------------ P4b convex-convex narrow phase
+ * MuJoCo 3.1.2 collides two convex meshes with libccd's Minkowski Portal Refinement (mjc_Convex -> ccdMPRPenetration,
+ * libccd is vendored by MuJoCo, absent from /root/reference): centres = the geoms' frame origins (the mesh centre of
+ * mass), support = hull vertex maximising the direction, tolerance opt.mpr_tolerance = 1e-6, at most opt.mpr_iterations = 50
+ * refinement steps; one contact per pair (multiccd is off by default): dist = -depth, normal = direction from geom1 to geom2,
+ * pos = midpoint of the two witness points.  Restated from libccd's published algorithm (src/mpr.c, vec3.c): portal
+ * discovery, portal refinement, penetration from the final portal.  Reached from models/nightmare_v3/mjmodel.xml:47
+ * (tibia contype=2 / conaffinity=3 => the 15 tibia-tibia pairs). */
+#include <float.h>
+#define CCD_EPS ((real)(sizeof(real) == 8 ? DBL_EPSILON : FLT_EPSILON))
+typedef struct { real v[3], v1[3], v2[3]; } supp_t;                 /* point of the Minkowski difference obj1 - obj2 and its two witnesses */
+typedef struct { const nmo_model* m; const real *R, *p; int adr, num; real center[3]; } hull_t;
+
+static inline int ccd_zero(real x) { return fabs(x) < CCD_EPS; }
+static inline int ccd_eq(real a_, real b_) {
+  real ab = fabs(a_ - b_);
+  if (ab < CCD_EPS) return 1;
+  real a = fabs(a_), b = fabs(b_);
+  return b > a ? ab < CCD_EPS * b : ab < CCD_EPS * a;
+}
+static inline int ccd_vec_eq(const real* a, const real* b) { return ccd_eq(a[0], b[0]) && ccd_eq(a[1], b[1]) && ccd_eq(a[2], b[2]); }
+static inline void vsub(real* r, const real* a, const real* b) { FLOP(3); r[0] = a[0] - b[0]; r[1] = a[1] - b[1]; r[2] = a[2] - b[2]; }
+static inline void ccd_normalize(real* v) { FLOP(9); real n = sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]); v[0] /= n; v[1] /= n; v[2] /= n; }
+
+/* support point of a hull in world direction `dir`: exhaustive argmax over the hull vertices, first index wins ties
+ * (MuJoCo hill-climbs the hull graph: same vertex except for exact ties) */
+static void hull_support(const hull_t* o, const real* dir, real* out) {
+  const real* R = o->R;
+  real dl[3] = {R[0] * dir[0] + R[3] * dir[1] + R[6] * dir[2], R[1] * dir[0] + R[4] * dir[1] + R[7] * dir[2], R[2] * dir[0] + R[5] * dir[1] + R[8] * dir[2]};
+  int best = 0;
+  real bv = 0;
+  for (int v = 0; v < o->num; v++) {
+    const float* h = o->m->hull_vert + 3 * (o->adr + v);
+    real val = dl[0] * (real)h[0] + dl[1] * (real)h[1] + dl[2] * (real)h[2];
+    if (v == 0 || val > bv) { bv = val; best = v; }
+  }
+  FLOP(15 + 5 * o->num + 18);
+  const float* h = o->m->hull_vert + 3 * (o->adr + best);
+  real lv[3] = {(real)h[0], (real)h[1], (real)h[2]};
+  mat_vec3(out, R, lv);
+  for (int k = 0; k < 3; k++) out[k] += o->p[k];
+}
+static void mpr_support(const hull_t* a, const hull_t* b, const real* dir, supp_t* s) {
+  real nd[3] = {-dir[0], -dir[1], -dir[2]};
+  hull_support(a, dir, s->v1);
+  hull_support(b, nd, s->v2);
+  vsub(s->v, s->v1, s->v2);
+}
+static void portal_dir(const supp_t* P, real* dir) {
+  real a[3], b[3];
+  vsub(a, P[2].v, P[1].v);
+  vsub(b, P[3].v, P[1].v);
+  cross3(dir, a, b);
+  ccd_normalize(dir);
+}
+static int portal_reach_tolerance(const supp_t* P, const supp_t* v4, const real* dir, real tol) {
+  real dv1 = dot3(P[1].v, dir), dv2 = dot3(P[2].v, dir), dv3 = dot3(P[3].v, dir), dv4 = dot3(v4->v, dir);
+  real d1 = dv4 - dv1, d2 = dv4 - dv2, d3 = dv4 - dv3;
+  if (d2 < d1) d1 = d2;
+  if (d3 < d1) d1 = d3;
+  return ccd_eq(d1, tol) || d1 < tol;
+}
+static void expand_portal(supp_t* P, const supp_t* v4) {
+  real v4v0[3];
+  cross3(v4v0, v4->v, P[0].v);
+  if (dot3(P[1].v, v4v0) > 0) {
+    if (dot3(P[2].v, v4v0) > 0) P[1] = *v4; else P[3] = *v4;
+  } else {
+    if (dot3(P[3].v, v4v0) > 0) P[2] = *v4; else P[1] = *v4;
+  }
+}
+static real point_seg_dist2(const real* x0, const real* b, real* wit) {      /* P = origin */
+  real d[3];
+  vsub(d, b, x0);
+  real t = -dot3(x0, d) / dot3(d, d);
+  if (t < 0 || ccd_zero(t)) { memcpy(wit, x0, 3 * sizeof(real)); return dot3(x0, x0); }
+  if (t > 1 || ccd_eq(t, 1)) { memcpy(wit, b, 3 * sizeof(real)); return dot3(b, b); }
+  for (int k = 0; k < 3; k++) wit[k] = d[k] * t + x0[k];
+  return dot3(wit, wit);
+}
+/* squared distance of the origin from the triangle (x0, B, C) and the closest point (≙ ccdVec3PointTriDist2) */
+static real origin_tri_dist2(const real* x0, const real* B, const real* C, real* wit) {
+  real d1[3], d2[3];
+  vsub(d1, B, x0);
+  vsub(d2, C, x0);
+  real v = dot3(d1, d1), w = dot3(d2, d2), p = dot3(x0, d1), q = dot3(x0, d2), r = dot3(d1, d2);
+  real den = w * v - r * r, s, t;
+  if (ccd_zero(den)) { s = t = -1; }
+  else { s = (q * r - w * p) / den; t = (-s * r - q) / w; }
+  if ((ccd_zero(s) || s > 0) && (ccd_eq(s, 1) || s < 1) && (ccd_zero(t) || t > 0) && (ccd_eq(t, 1) || t < 1) && (ccd_eq(t + s, 1) || t + s < 1)) {
+    for (int k = 0; k < 3; k++) wit[k] = x0[k] + s * d1[k] + t * d2[k];
+    return dot3(wit, wit);
+  }
+  real w2[3];
+  real dist = point_seg_dist2(x0, B, wit);
+  real dd = point_seg_dist2(x0, C, w2);
+  if (dd < dist) { dist = dd; memcpy(wit, w2, sizeof(w2)); }
+  dd = point_seg_dist2(B, C, w2);
+  if (dd < dist) { dist = dd; memcpy(wit, w2, sizeof(w2)); }
+  return dist;
+}
+static void mpr_find_pos(const supp_t* P, real* pos) {
+  real dir[3], vec[3], b[4];
+  portal_dir(P, dir);
+  cross3(vec, P[1].v, P[2].v); b[0] = dot3(vec, P[3].v);
+  cross3(vec, P[3].v, P[2].v); b[1] = dot3(vec, P[0].v);
+  cross3(vec, P[0].v, P[1].v); b[2] = dot3(vec, P[3].v);
+  cross3(vec, P[2].v, P[1].v); b[3] = dot3(vec, P[0].v);
+  real sum = b[0] + b[1] + b[2] + b[3];
+  if (ccd_zero(sum) || sum < 0) {
+    b[0] = 0;
+    cross3(vec, P[2].v, P[3].v); b[1] = dot3(vec, dir);
+    cross3(vec, P[3].v, P[1].v); b[2] = dot3(vec, dir);
+    cross3(vec, P[1].v, P[2].v); b[3] = dot3(vec, dir);
+    sum = b[1] + b[2] + b[3];
+  }
+  real inv = 1 / sum;
+  for (int k = 0; k < 3; k++) {
+    real p1 = 0, p2 = 0;
+    for (int i = 0; i < 4; i++) { p1 += P[i].v1[k] * b[i]; p2 += P[i].v2[k] * b[i]; }
+    pos[k] = (p1 * inv + p2 * inv) * (real)0.5;
+  }
+  FLOP(60);
+}
+/* returns 1 with depth / dir / pos when the hulls intersect, 0 otherwise (≙ ccdMPRPenetration == 0 and dir != 0) */
+static int mpr_penetration(const nmo_model* m, const hull_t* A, const hull_t* B, real* depth, real* dir_out, real* pos) {
+  supp_t P[4], v4;
+  real dir[3], va[3], vb[3], dot;
+  /* ---- portal discovery */
+  memcpy(P[0].v1, A->center, 3 * sizeof(real));
+  memcpy(P[0].v2, B->center, 3 * sizeof(real));
+  vsub(P[0].v, P[0].v1, P[0].v2);
+  real zero3[3] = {0, 0, 0};
+  if (ccd_vec_eq(P[0].v, zero3)) P[0].v[0] += CCD_EPS * 10;
+  for (int k = 0; k < 3; k++) dir[k] = -P[0].v[k];
+  ccd_normalize(dir);
+  mpr_support(A, B, dir, &P[1]);
+  dot = dot3(P[1].v, dir);
+  if (ccd_zero(dot) || dot < 0) return 0;
+  cross3(dir, P[0].v, P[1].v);
+  if (ccd_zero(dot3(dir, dir))) {
+    if (ccd_vec_eq(P[1].v, zero3)) return 0;                       /* touching contact on v1: depth 0, direction undefined -> MuJoCo drops it */
+    /* origin on the v0-v1 segment */
+    for (int k = 0; k < 3; k++) pos[k] = (P[1].v1[k] + P[1].v2[k]) * (real)0.5;
+    memcpy(dir_out, P[1].v, 3 * sizeof(real));
+    *depth = sqrt(dot3(dir_out, dir_out));
+    ccd_normalize(dir_out);
+    return 1;
+  }
+  ccd_normalize(dir);
+  mpr_support(A, B, dir, &P[2]);
+  dot = dot3(P[2].v, dir);
+  if (ccd_zero(dot) || dot < 0) return 0;
+  vsub(va, P[1].v, P[0].v);
+  vsub(vb, P[2].v, P[0].v);
+  cross3(dir, va, vb);
+  ccd_normalize(dir);
+  if (dot3(dir, P[0].v) > 0) {                                     /* portal faces oriented away from the origin */
+    supp_t t = P[1]; P[1] = P[2]; P[2] = t;
+    for (int k = 0; k < 3; k++) dir[k] = -dir[k];
+  }
+  for (;;) {
+    mpr_support(A, B, dir, &P[3]);
+    dot = dot3(P[3].v, dir);
+    if (ccd_zero(dot) || dot < 0) return 0;
+    int cont = 0;
+    cross3(va, P[1].v, P[3].v);
+    dot = dot3(va, P[0].v);
+    if (dot < 0 && !ccd_zero(dot)) { P[2] = P[3]; cont = 1; }       /* origin outside (v1, v0, v3) */
+    if (!cont) {
+      cross3(va, P[3].v, P[2].v);
+      dot = dot3(va, P[0].v);
+      if (dot < 0 && !ccd_zero(dot)) { P[1] = P[3]; cont = 1; }     /* origin outside (v3, v0, v2) */
+    }
+    if (!cont) break;
+    vsub(va, P[1].v, P[0].v);
+    vsub(vb, P[2].v, P[0].v);
+    cross3(dir, va, vb);
+    ccd_normalize(dir);
+  }
+  /* ---- portal refinement: does the portal enclose the origin? */
+  for (;;) {
+    portal_dir(P, dir);
+    dot = dot3(dir, P[1].v);
+    if (ccd_zero(dot) || dot > 0) break;                            /* origin inside the portal */
+    mpr_support(A, B, dir, &v4);
+    dot = dot3(v4.v, dir);
+    if (!(ccd_zero(dot) || dot > 0) || portal_reach_tolerance(P, &v4, dir, m->mpr_tolerance)) return 0;
+    expand_portal(P, &v4);
+  }
+  /* ---- penetration depth / direction / position from the refined portal */
+  for (unsigned long it = 0;; it++) {
+    portal_dir(P, dir);
+    mpr_support(A, B, dir, &v4);
+    if (portal_reach_tolerance(P, &v4, dir, m->mpr_tolerance) || it > (unsigned long)m->mpr_iterations) {
+      real wit[3];
+      *depth = sqrt(origin_tri_dist2(P[1].v, P[2].v, P[3].v, wit));
+      if (ccd_zero(*depth)) return 0;                               /* touching: direction undefined -> no contact in MuJoCo */
+      memcpy(dir_out, wit, sizeof(wit));
+      ccd_normalize(dir_out);
+      mpr_find_pos(P, pos);
+      return 1;
+    }
+    expand_portal(P, &v4);
+  }
+}
+
 #ifdef NMO_COUNT_FLOPS
 /* operations of the hill climb from hull vertex 0 to the support vertex (what mjc_PlaneConvex does): one 5-flop dot
  * product per neighbour examined; rotating the direction into the geom frame costs 15 */
@@ -741,6 +955,37 @@ static void collision(const nmo_model* m, data_t* d) {
       make_frame(c->frame);
       c->geom1 = pg; c->geom2 = g; c->body1 = pb; c->body2 = b; c->vert = -1;
       mix_params(m, pg, g, c);
+    }
+  }
+  /* convex-convex pairs, after all pairs with the world body: MuJoCo orders contacts by the pair's (body1, body2) signature */
+  for (int g1 = 0; g1 < m->ngeom; g1++) {
+    if (m->geom_type[g1] != GEOM_MESH || m->geom_hull_num[g1] <= 0) continue;
+    for (int g2 = g1 + 1; g2 < m->ngeom; g2++) {
+      if (m->geom_type[g2] != GEOM_MESH || m->geom_hull_num[g2] <= 0) continue;
+      int b1 = m->geom_body[g1], b2 = m->geom_body[g2];
+      if (b1 == b2 || b1 == 0 || b2 == 0) continue;
+      if (!((m->geom_contype[g1] & m->geom_conaffinity[g2]) || (m->geom_contype[g2] & m->geom_conaffinity[g1]))) continue;
+      if (m->body_parent[b1] == b2 || m->body_parent[b2] == b1) continue;          /* parent-child filter */
+      hull_t A = {m, d->xmat + 9 * b1, d->xpos + 3 * b1, m->geom_hull_adr[g1], m->geom_hull_num[g1], {0, 0, 0}};
+      hull_t B = {m, d->xmat + 9 * b2, d->xpos + 3 * b2, m->geom_hull_adr[g2], m->geom_hull_num[g2], {0, 0, 0}};
+      mat_vec3(A.center, A.R, m->geom_center + 3 * g1);
+      mat_vec3(B.center, B.R, m->geom_center + 3 * g2);
+      for (int k = 0; k < 3; k++) { A.center[k] += A.p[k]; B.center[k] += B.p[k]; }
+      real margin = m->geom_margin[g1] > m->geom_margin[g2] ? m->geom_margin[g1] : m->geom_margin[g2];
+      real cc[3];
+      vsub(cc, A.center, B.center);
+      FLOP(6 + 8);
+      if (sqrt(dot3(cc, cc)) > margin + m->geom_rbound[g1] + m->geom_rbound[g2]) continue;   /* bounding spheres */
+      real depth, dir[3], pos[3];
+      d->nmpr++;
+      if (!mpr_penetration(m, &A, &B, &depth, dir, pos) || d->ncon >= NMO_MAXCON) continue;
+      contact_t* c = d->con + d->ncon++;
+      c->dist = margin - depth;
+      memcpy(c->pos, pos, sizeof(pos));
+      memcpy(c->frame, dir, sizeof(dir));
+      make_frame(c->frame);
+      c->geom1 = g1; c->geom2 = g2; c->body1 = b1; c->body2 = b2; c->vert = -1;
+      mix_params(m, g1, g2, c);
     }
   }
 }
@@ -1326,6 +1571,11 @@ int nmo_get_array(const nmo_batch* b, int env, const char* name, double* out, in
   if (!strcmp(name, "time")) { if (cap > 0) out[0] = d->time; return 1; }
   if (!strcmp(name, "solver_niter")) { if (cap > 0) out[0] = d->solver_niter; if (cap > 1) out[1] = d->noslip_niter; if (cap > 2) out[2] = d->warm_used; return 3; }
   if (!strcmp(name, "nwarn")) { if (cap > 0) out[0] = d->nwarn; return 1; }
+  if (!strcmp(name, "nmpr")) { if (cap > 0) out[0] = (double)d->nmpr; return 1; }
+  if (!strcmp(name, "contact_frame")) {   /* per contact: normal(3) */
+    for (int c = 0; c < d->ncon && 3 * c + 2 < cap; c++) { out[3 * c] = d->con[c].frame[0]; out[3 * c + 1] = d->con[c].frame[1]; out[3 * c + 2] = d->con[c].frame[2]; }
+    return d->ncon * 3;
+  }
   if (!strcmp(name, "contact")) {   /* per contact: geom1 geom2 vert dist pos(3) */
     int c_ = d->ncon * 7;
     for (int c = 0; c < d->ncon && 7 * c + 6 < cap; c++) {
