@@ -662,20 +662,30 @@ static inline int ccd_vec_eq(const real* a, const real* b) { return ccd_eq(a[0],
 static inline void vsub(real* r, const real* a, const real* b) { FLOP(3); r[0] = a[0] - b[0]; r[1] = a[1] - b[1]; r[2] = a[2] - b[2]; }
 static inline void ccd_normalize(real* v) { FLOP(9); real n = sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]); v[0] /= n; v[1] /= n; v[2] /= n; }
 
-/* support point of a hull in world direction `dir`: exhaustive argmax over the hull vertices, first index wins ties
- * (MuJoCo hill-climbs the hull graph: same vertex except for exact ties) */
+/* support point of a hull in world direction `dir`: hill climb on the hull's vertex graph from vertex 0, the way MuJoCo's
+ * mesh support function walks mesh_graph (a local maximum of a linear function on a convex polytope is the global one;
+ * neighbours are visited in list order, a neighbour replaces the current best only if strictly better) */
 static void hull_support(const hull_t* o, const real* dir, real* out) {
   const real* R = o->R;
+  const nmo_model* m = o->m;
   real dl[3] = {R[0] * dir[0] + R[3] * dir[1] + R[6] * dir[2], R[1] * dir[0] + R[4] * dir[1] + R[7] * dir[2], R[2] * dir[0] + R[5] * dir[1] + R[8] * dir[2]};
+  FLOP(15 + 5 + 18);
   int best = 0;
-  real bv = 0;
-  for (int v = 0; v < o->num; v++) {
-    const float* h = o->m->hull_vert + 3 * (o->adr + v);
-    real val = dl[0] * (real)h[0] + dl[1] * (real)h[1] + dl[2] * (real)h[2];
-    if (v == 0 || val > bv) { bv = val; best = v; }
+  const float* h = m->hull_vert + 3 * o->adr;
+  real bv = dl[0] * (real)h[0] + dl[1] * (real)h[1] + dl[2] * (real)h[2];
+  for (;;) {
+    int nb = best;
+    for (int e = m->hull_nbr_adr[o->adr + best]; e < m->hull_nbr_adr[o->adr + best + 1]; e++) {
+      int v = m->hull_nbr[e];
+      h = m->hull_vert + 3 * (o->adr + v);
+      real val = dl[0] * (real)h[0] + dl[1] * (real)h[1] + dl[2] * (real)h[2];
+      FLOP(5);
+      if (val > bv) { bv = val; nb = v; }
+    }
+    if (nb == best) break;
+    best = nb;
   }
-  FLOP(15 + 5 * o->num + 18);
-  const float* h = o->m->hull_vert + 3 * (o->adr + best);
+  h = m->hull_vert + 3 * (o->adr + best);
   real lv[3] = {(real)h[0], (real)h[1], (real)h[2]};
   mat_vec3(out, R, lv);
   for (int k = 0; k < 3; k++) out[k] += o->p[k];
