@@ -25,7 +25,7 @@ extern "C" {
 #define NM_NSENSOR 13     /* mjmodel.xml:156-170 */
 #define NM_NREW 18        /* reward terms in alphabetical order (envs/helpers.py:7) */
 #define NM_MAXCON_GEOM 4  /* plane-mesh: support vertex + up to 3 more */
-#define NM_DBG_STRIDE 288 /* floats per env in the optional debug buffer */
+#define NM_DBG_STRIDE 320 /* floats per env in the optional debug buffer */
 #define NM_REC_STRIDE 52  /* floats per row of the env-0 recorder ring: done flag, qpos[25], qvel[24], 2 pad */
 
 typedef enum {

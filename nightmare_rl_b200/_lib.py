@@ -10,7 +10,7 @@ import os
 from .build import LIB_PATH
 from .envcfg import EnvCfgStruct, NREW
 
-NM_DBG_STRIDE = 288
+NM_DBG_STRIDE = 320
 NM_REC_STRIDE = 52
 _vp, _ci, _i64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64
 

@@ -276,6 +276,84 @@ static int build_device_model(nm_model* m) {
     G.dmin = (float)clampd(solimp[0]); G.dmax = (float)dmax; G.width = (float)solimp[2];
     G.mid = (float)clampd(solimp[3]); G.power = (float)(solimp[4] < 1 ? 1 : solimp[4]);
   }
+  // ---- convex-convex pairs between the legs' hulls (reference mjmodel.xml:47: tibia contype=2 / conaffinity=3).  MuJoCo's
+  // filter: (contype1 & conaffinity2) || (contype2 & conaffinity1), different bodies, not parent and child.
+  {
+    const int *contype = nullptr, *conaff = nullptr;
+    const double* center = nullptr;
+    const bool have = get(m, "geom_contype", 2, contype) && get(m, "geom_conaffinity", 2, conaff) && get(m, "geom_center", 0, center);
+    std::vector<int> geom_of(NM_OCT, -1);
+    for (int g = 0; g < m->ngeom; g++) {
+      if (geom_type[g] != 7) continue;
+      for (int k = 0; k < nleg; k++) if (geom_body[g] == last_link[k] && D.leg[k].geom.has) geom_of[k] = g;
+      if (geom_body[g] == 1) geom_of[6] = g;
+    }
+    D.pair_mask = 0;
+    if (have) {
+      int idx = 0;
+      for (int i = 0; i < 6; i++)
+        for (int j = i + 1; j < 6; j++, idx++) {
+          if (i >= nleg || j >= nleg || geom_of[i] < 0 || geom_of[j] < 0) continue;
+          const int gi = geom_of[i], gj = geom_of[j];
+          if (!((contype[gi] & conaff[gj]) || (contype[gj] & conaff[gi]))) continue;
+          const NmGeom &A = D.leg[i].geom, &B = D.leg[j].geom;
+          if (A.mu != B.mu || A.K != B.K || A.B != B.B || A.dmin != B.dmin || A.dmax != B.dmax || A.width != B.width || A.mid != B.mid ||
+              A.power != B.power || A.margin != B.margin || geom_priority[gi] != geom_priority[gj])
+            return fail(NM_ERR_UNSUPPORTED, "leg hulls that collide with each other must share their contact parameters");
+          D.pair_mask |= 1 << idx;
+        }
+      // base hull against leg hulls, or any other convex-convex pair, is not handled by the kernel: refuse rather than ignore
+      for (int g1 = 0; g1 < m->ngeom; g1++)
+        for (int g2 = g1 + 1; g2 < m->ngeom; g2++) {
+          if (geom_type[g1] != 7 || geom_type[g2] != 7 || geom_body[g1] == geom_body[g2]) continue;
+          if (!((contype[g1] & conaff[g2]) || (contype[g2] & conaff[g1]))) continue;
+          if (body_parent[geom_body[g1]] == geom_body[g2] || body_parent[geom_body[g2]] == geom_body[g1]) continue;
+          bool l1 = false, l2 = false;
+          for (int k = 0; k < nleg; k++) { l1 |= geom_of[k] == g1; l2 |= geom_of[k] == g2; }
+          if (!(l1 && l2)) return fail(NM_ERR_UNSUPPORTED, "convex-convex pairs are implemented between the legs' last-link hulls only");
+        }
+    }
+    for (int k = 0; k < nleg; k++) {
+      NmGeom& G = D.leg[k].geom;
+      if (!G.has || geom_of[k] < 0) continue;
+      const int g = geom_of[k];
+      const float* hv = hull_vert + 3 * (size_t)G.hull_adr;
+      double c[3] = {0, 0, 0};
+      if (have) for (int a = 0; a < 3; a++) c[a] = center[3 * g + a];
+      else { for (int v = 0; v < G.hull_num; v++) for (int a = 0; a < 3; a++) c[a] += hv[3 * v + a] / G.hull_num; }
+      for (int a = 0; a < 3; a++) G.center[a] = (float)c[a];
+      // bounding capsule: principal axis of the vertex cloud (power iteration on its covariance), extent along it, largest
+      // distance from the axis
+      double mean[3] = {0, 0, 0}, C[9] = {0};
+      for (int v = 0; v < G.hull_num; v++) for (int a = 0; a < 3; a++) mean[a] += hv[3 * v + a] / (double)G.hull_num;
+      for (int v = 0; v < G.hull_num; v++)
+        for (int a = 0; a < 3; a++) for (int b2 = 0; b2 < 3; b2++) C[3 * a + b2] += (hv[3 * v + a] - mean[a]) * (hv[3 * v + b2] - mean[b2]);
+      double u[3] = {1, 1, 1};
+      for (int it = 0; it < 200; it++) {
+        double w[3] = {C[0] * u[0] + C[1] * u[1] + C[2] * u[2], C[3] * u[0] + C[4] * u[1] + C[5] * u[2], C[6] * u[0] + C[7] * u[1] + C[8] * u[2]};
+        const double nn = std::sqrt(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]);
+        if (nn < 1e-30) break;
+        for (int a = 0; a < 3; a++) u[a] = w[a] / nn;
+      }
+      double tmin = 1e30, tmax = -1e30, rmax = 0;
+      for (int v = 0; v < G.hull_num; v++) {
+        double d[3] = {hv[3 * v] - mean[0], hv[3 * v + 1] - mean[1], hv[3 * v + 2] - mean[2]};
+        const double t = d[0] * u[0] + d[1] * u[1] + d[2] * u[2];
+        tmin = std::fmin(tmin, t); tmax = std::fmax(tmax, t);
+        const double pr[3] = {d[0] - t * u[0], d[1] - t * u[1], d[2] - t * u[2]};
+        rmax = std::fmax(rmax, std::sqrt(pr[0] * pr[0] + pr[1] * pr[1] + pr[2] * pr[2]));
+      }
+      for (int a = 0; a < 3; a++) { G.cap_a[a] = (float)(mean[a] + tmin * u[a]); G.cap_b[a] = (float)(mean[a] + tmax * u[a]); }
+      G.cap_r = (float)(rmax * 1.0001 + 1e-6);
+      const double mureg = G.mu / std::sqrt(impratio > 1e-15 ? impratio : 1.0);
+      G.rfac_self = (float)(2.0 * mureg * mureg * (1.0 + (double)G.mu * G.mu) * body_invweight0[2 * geom_body[g]]);
+    }
+    long long n_or = 0;
+    const double* orl2 = nullptr;
+    get(m, "opt_real", 0, orl2, &n_or);
+    D.mpr_iterations = (n_oi > 8 && oi[8] > 0) ? oi[8] : 50;
+    D.mpr_tolerance = (n_or > 8 && orl2[8] > 0) ? (float)orl2[8] : 1e-6f;
+  }
   // ---- touch sensors: [nleg x slot0 | nleg x slot1 | base]  (mjmodel.xml:157-169, env.py:224-226)
   if (m->nsensor != 0) {
     if (m->nsensor != 2 * nleg + 1) return fail(NM_ERR_UNSUPPORTED, "touch sensors must be laid out as [legs..., feet..., base]");

@@ -11,6 +11,8 @@
 #define NM_OCT 8            // lanes per environment: 6 leg lanes + base-geom lane + spare
 #define NM_MAXC 4           // contacts per collision geom
 #define NM_NOBS_DEV 66      // observation entries per env (envs/nightmare_v3_config.py:11)
+#define NM_MAXPAIR 4        // simultaneous convex-convex (tibia-tibia) contacts per environment; further ones are dropped
+#define NM_DBG 320          // floats per env of the optional debug record (== NM_DBG_STRIDE of the C ABI)
 #ifndef NM_BLOCK
 #define NM_BLOCK 64         // threads per CTA = 8 environments
 #endif
@@ -22,6 +24,11 @@ struct NmGeom {
   float rfac;               // R = rfac * (1-imp)/imp   (pyramidal: 2 mu_reg^2 * (1+mu^2) * invweight)
   float K, B;               // reference-acceleration spring/damper from solref
   float dmin, dmax, width, mid, power;
+  // convex-convex pairs (mjmodel.xml:47: the tibia geoms collide with each other)
+  float center[3];          // MPR centre: the mesh's centre of mass, body frame (MuJoCo: the geom frame origin)
+  float cap_a[3], cap_b[3]; // bounding capsule of the hull, body frame: segment end points ...
+  float cap_r;              // ... and radius (conservative broad phase: hulls whose capsules do not overlap cannot intersect)
+  float rfac_self;          // this body's share of a pair contact's R: 2 mu_reg^2 (1+mu^2) * body_invweight0
 };
 
 struct NmLeg {
@@ -49,7 +56,10 @@ struct alignas(16) NmDevModel {
   float gravity[3];
   float timestep, tolerance, noslip_tolerance, solver_scale;
   int iterations, noslip_iterations, nleg, integrator;
-  int planemesh_maxcon, pad_m[3];   // contacts per plane-mesh pair (opt_int[7] of the model file, 1..NM_MAXC)
+  int planemesh_maxcon;     // contacts per plane-mesh pair (opt_int[7] of the model file, 1..NM_MAXC)
+  int pair_mask;            // bit idx(i,j), i<j lexicographic over the leg lanes: the hulls of legs i and j collide
+  int mpr_iterations;       // opt.mpr_iterations (50)
+  float mpr_tolerance;      // opt.mpr_tolerance (1e-6)
   float imp_damp, imp_act;  // which velocity derivatives enter the implicit velocity update (implicitfast: both; Euler+eulerdamp: damping)
   float qpos0[32];
 };

@@ -360,8 +360,9 @@ __device__ __forceinline__ void con_load(const ConBlk& cb, int c, ConRegs& k) {
 // Residuals of the 4 edges against the CURRENT dual state, all at once: r_e = b_e + (p0 +- mu*p_t), p_a = Y_a.u + Z_a.w
 // (three independent dot products); the Gauss-Seidel coupling among the 4 rows of the contact is then applied through its
 // edge Gram matrix instead of re-walking u after every row.
-__device__ __forceinline__ void con_sweep(ConRegs& k, float* u, float* wv, float mu, bool in_noslip, float& improvement) {
-  float p0 = 0.f, p1 = 0.f, p2 = 0.f;
+__device__ __forceinline__ void con_sweep(ConRegs& k, float* u, float* wv, float mu, bool in_noslip, float& improvement,
+                                          float pe0 = 0.f, float pe1 = 0.f, float pe2 = 0.f, float* cout = nullptr) {
+  float p0 = pe0, p1 = pe1, p2 = pe2;          // (pair contacts: the other leg's Z.w, plane contacts: 0)
 #pragma unroll
   for (int a = 0; a < 6; a++) { const float ua = u[a]; p0 = fmaf(k.Y[0][a], ua, p0); p1 = fmaf(k.Y[1][a], ua, p1); p2 = fmaf(k.Y[2][a], ua, p2); }
 #pragma unroll
@@ -412,10 +413,209 @@ __device__ __forceinline__ void con_sweep(ConRegs& k, float* u, float* wv, float
     }
   }
   const float c0 = (d[0] + d[1]) + (d[2] + d[3]), c1 = mu * (d[0] - d[1]), c2 = mu * (d[2] - d[3]);
+  if (cout != nullptr) { cout[0] = c0; cout[1] = c1; cout[2] = c2; }
 #pragma unroll
   for (int a = 0; a < 6; a++) u[a] = fmaf(k.Y[0][a], c0, fmaf(k.Y[1][a], c1, fmaf(k.Y[2][a], c2, u[a])));
 #pragma unroll
   for (int j = 0; j < 3; j++) wv[j] = fmaf(k.Z[0][j], c0, fmaf(k.Z[1][j], c1, fmaf(k.Z[2][j], c2, wv[j])));
+}
+
+
+// ================================================================================================ convex-convex pairs
+// Tibia-tibia contacts (reference models/nightmare_v3/mjmodel.xml:47).  MuJoCo collides two convex meshes with libccd's
+// Minkowski Portal Refinement; the same algorithm is restated here in fp32, run
+// by the whole octet: the portal is replicated in all eight lanes, the support query (the only loop over hull vertices) is
+// split across them.  Coordinates are relative to the base origin, so that fp32 resolution does not depend on how far the
+// robot has walked.  Cold code: it runs only for pairs whose bounding capsules overlap.
+struct HullPose { float X[9], p[3], c[3]; int adr, num; };
+struct PairBlk {                 // one pair contact, shared memory; everything but Zi/Zj is the same for the whole octet
+  float Y[3][6], Zi[3][3], Zj[3][3], G[10], b[4], adi[4], f[4], ik[2], R, dist;
+  float pos[3], nrm[3], mu;
+  int li, lj;
+};
+struct Supp { V3 v, v1, v2; };
+#define NM_CCD_EPS 1.1920929e-07f
+__device__ __forceinline__ bool ccd_zero(float x) { return fabsf(x) < NM_CCD_EPS; }
+__device__ __forceinline__ bool ccd_eq(float a_, float b_) {
+  const float ab = fabsf(a_ - b_);
+  if (ab < NM_CCD_EPS) return true;
+  const float a = fabsf(a_), b = fabsf(b_);
+  return b > a ? ab < NM_CCD_EPS * b : ab < NM_CCD_EPS * a;
+}
+__device__ __forceinline__ float dot_plain(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+__device__ __forceinline__ V3 normalized(V3 v) { const float n = sqrtf(dot_plain(v, v)); return mk(v.x / n, v.y / n, v.z / n); }
+
+// support vertex of a hull along `dir` (world): argmax over all hull vertices, 1/8 of them per lane, lowest index wins ties
+__device__ __noinline__ V3 hull_support_oct(const float4* __restrict__ hull_vert, const HullPose* h, V3 dir, int l, unsigned omask) {
+  const float* X = h->X;
+  const V3 dl = mk(X[0] * dir.x + X[3] * dir.y + X[6] * dir.z, X[1] * dir.x + X[4] * dir.y + X[7] * dir.z, X[2] * dir.x + X[5] * dir.y + X[8] * dir.z);
+  const float4* hv = hull_vert + h->adr;
+  float best = -CUDART_INF_F;
+  int bi = 0x7fffffff;
+  for (int v = l; v < h->num; v += 8) {
+    const float4 q = __ldg(hv + v);
+    const float val = dl.x * q.x + dl.y * q.y + dl.z * q.z;
+    if (val > best) { best = val; bi = v; }
+  }
+#pragma unroll
+  for (int o = 1; o < 8; o <<= 1) {
+    const float ov = __shfl_xor_sync(omask, best, o);
+    const int oi = __shfl_xor_sync(omask, bi, o);
+    if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+  }
+  const float4 q = __ldg(hv + bi);
+  return mk(X[0] * q.x + X[1] * q.y + X[2] * q.z + h->p[0], X[3] * q.x + X[4] * q.y + X[5] * q.z + h->p[1], X[6] * q.x + X[7] * q.y + X[8] * q.z + h->p[2]);
+}
+__device__ __forceinline__ void mpr_support(const float4* hv, const HullPose* A, const HullPose* B, V3 dir, int l, unsigned om, Supp& s) {
+  s.v1 = hull_support_oct(hv, A, dir, l, om);
+  s.v2 = hull_support_oct(hv, B, mk(-dir.x, -dir.y, -dir.z), l, om);
+  s.v = s.v1 - s.v2;
+}
+__device__ __forceinline__ V3 portal_dir(const Supp* P) { return normalized(cross(P[2].v - P[1].v, P[3].v - P[1].v)); }
+__device__ __forceinline__ bool portal_reach_tolerance(const Supp* P, const Supp& v4, V3 dir, float tol) {
+  const float dv4 = dot_plain(v4.v, dir);
+  const float d1 = fminf(fminf(dv4 - dot_plain(P[1].v, dir), dv4 - dot_plain(P[2].v, dir)), dv4 - dot_plain(P[3].v, dir));
+  return ccd_eq(d1, tol) || d1 < tol;
+}
+__device__ __forceinline__ void expand_portal(Supp* P, const Supp& v4) {
+  const V3 v4v0 = cross(v4.v, P[0].v);
+  if (dot_plain(P[1].v, v4v0) > 0.f) {
+    if (dot_plain(P[2].v, v4v0) > 0.f) P[1] = v4; else P[3] = v4;
+  } else {
+    if (dot_plain(P[3].v, v4v0) > 0.f) P[2] = v4; else P[1] = v4;
+  }
+}
+__device__ __forceinline__ float point_seg_dist2(V3 x0, V3 b, V3& wit) {       // distance of the origin from the segment (x0, b)
+  const V3 d = b - x0;
+  const float t = -dot_plain(x0, d) / dot_plain(d, d);
+  if (t < 0.f || ccd_zero(t)) { wit = x0; return dot_plain(x0, x0); }
+  if (t > 1.f || ccd_eq(t, 1.f)) { wit = b; return dot_plain(b, b); }
+  wit = mk(d.x * t + x0.x, d.y * t + x0.y, d.z * t + x0.z);
+  return dot_plain(wit, wit);
+}
+__device__ __forceinline__ float origin_tri_dist2(V3 x0, V3 B, V3 C, V3& wit) {
+  const V3 d1 = B - x0, d2 = C - x0;
+  const float v = dot_plain(d1, d1), w = dot_plain(d2, d2), p = dot_plain(x0, d1), q = dot_plain(x0, d2), r = dot_plain(d1, d2);
+  const float den = w * v - r * r;
+  float s, t;
+  if (ccd_zero(den)) { s = t = -1.f; }
+  else { s = (q * r - w * p) / den; t = (-s * r - q) / w; }
+  if ((ccd_zero(s) || s > 0.f) && (ccd_eq(s, 1.f) || s < 1.f) && (ccd_zero(t) || t > 0.f) && (ccd_eq(t, 1.f) || t < 1.f) && (ccd_eq(t + s, 1.f) || t + s < 1.f)) {
+    wit = mk(x0.x + s * d1.x + t * d2.x, x0.y + s * d1.y + t * d2.y, x0.z + s * d1.z + t * d2.z);
+    return dot_plain(wit, wit);
+  }
+  V3 w2;
+  float dist = point_seg_dist2(x0, B, wit);
+  float dd = point_seg_dist2(x0, C, w2);
+  if (dd < dist) { dist = dd; wit = w2; }
+  dd = point_seg_dist2(B, C, w2);
+  if (dd < dist) { dist = dd; wit = w2; }
+  return dist;
+}
+// out = {depth, normal(3), position(3)}; true when the hulls intersect (≙ ccdMPRPenetration == 0 with a defined direction)
+__device__ __noinline__ bool mpr_penetration_oct(const float4* __restrict__ hv, const HullPose* A, const HullPose* B, float tol, int maxit, int l,
+                                                 unsigned om, float* out) {
+  Supp P[4], v4;
+  V3 dir, va;
+  float d;
+  P[0].v1 = ld3(A->c); P[0].v2 = ld3(B->c); P[0].v = P[0].v1 - P[0].v2;
+  if (ccd_eq(P[0].v.x, 0.f) && ccd_eq(P[0].v.y, 0.f) && ccd_eq(P[0].v.z, 0.f)) P[0].v.x += NM_CCD_EPS * 10.f;
+  dir = normalized(mk(-P[0].v.x, -P[0].v.y, -P[0].v.z));
+  mpr_support(hv, A, B, dir, l, om, P[1]);
+  d = dot_plain(P[1].v, dir);
+  if (ccd_zero(d) || d < 0.f) return false;
+  dir = cross(P[0].v, P[1].v);
+  if (ccd_zero(dot_plain(dir, dir))) {
+    if (ccd_eq(P[1].v.x, 0.f) && ccd_eq(P[1].v.y, 0.f) && ccd_eq(P[1].v.z, 0.f)) return false;     // touching on v1: direction undefined
+    const V3 n = normalized(P[1].v);                                                                // origin on the v0-v1 segment
+    out[0] = sqrtf(dot_plain(P[1].v, P[1].v)); out[1] = n.x; out[2] = n.y; out[3] = n.z;
+    out[4] = 0.5f * (P[1].v1.x + P[1].v2.x); out[5] = 0.5f * (P[1].v1.y + P[1].v2.y); out[6] = 0.5f * (P[1].v1.z + P[1].v2.z);
+    return true;
+  }
+  dir = normalized(dir);
+  mpr_support(hv, A, B, dir, l, om, P[2]);
+  d = dot_plain(P[2].v, dir);
+  if (ccd_zero(d) || d < 0.f) return false;
+  dir = normalized(cross(P[1].v - P[0].v, P[2].v - P[0].v));
+  if (dot_plain(dir, P[0].v) > 0.f) {
+    const Supp t = P[1]; P[1] = P[2]; P[2] = t;
+    dir = mk(-dir.x, -dir.y, -dir.z);
+  }
+  for (int guard = 0; guard < 64; guard++) {                       // portal discovery (libccd has no bound here; 64 is never reached)
+    mpr_support(hv, A, B, dir, l, om, P[3]);
+    d = dot_plain(P[3].v, dir);
+    if (ccd_zero(d) || d < 0.f) return false;
+    bool cont = false;
+    va = cross(P[1].v, P[3].v);
+    d = dot_plain(va, P[0].v);
+    if (d < 0.f && !ccd_zero(d)) { P[2] = P[3]; cont = true; }
+    if (!cont) {
+      va = cross(P[3].v, P[2].v);
+      d = dot_plain(va, P[0].v);
+      if (d < 0.f && !ccd_zero(d)) { P[1] = P[3]; cont = true; }
+    }
+    if (!cont) break;
+    dir = normalized(cross(P[1].v - P[0].v, P[2].v - P[0].v));
+  }
+  for (int guard = 0; guard < 256; guard++) {                      // portal refinement
+    dir = portal_dir(P);
+    d = dot_plain(dir, P[1].v);
+    if (ccd_zero(d) || d > 0.f) break;
+    mpr_support(hv, A, B, dir, l, om, v4);
+    d = dot_plain(v4.v, dir);
+    if (!(ccd_zero(d) || d > 0.f) || portal_reach_tolerance(P, v4, dir, tol)) return false;
+    expand_portal(P, v4);
+  }
+  for (int it = 0;; it++) {                                        // penetration from the refined portal
+    dir = portal_dir(P);
+    mpr_support(hv, A, B, dir, l, om, v4);
+    if (portal_reach_tolerance(P, v4, dir, tol) || it > maxit) {
+      V3 wit;
+      const float depth = sqrtf(origin_tri_dist2(P[1].v, P[2].v, P[3].v, wit));
+      if (ccd_zero(depth)) return false;
+      const V3 n = normalized(wit);
+      // position: barycentric coordinates of the origin ray in the portal (≙ findPos)
+      float b[4];
+      b[0] = dot_plain(cross(P[1].v, P[2].v), P[3].v);
+      b[1] = dot_plain(cross(P[3].v, P[2].v), P[0].v);
+      b[2] = dot_plain(cross(P[0].v, P[1].v), P[3].v);
+      b[3] = dot_plain(cross(P[2].v, P[1].v), P[0].v);
+      float sum = b[0] + b[1] + b[2] + b[3];
+      if (ccd_zero(sum) || sum < 0.f) {
+        b[0] = 0.f;
+        b[1] = dot_plain(cross(P[2].v, P[3].v), dir);
+        b[2] = dot_plain(cross(P[3].v, P[1].v), dir);
+        b[3] = dot_plain(cross(P[1].v, P[2].v), dir);
+        sum = b[1] + b[2] + b[3];
+      }
+      const float inv = 1.f / sum;
+      V3 p1 = mk(0, 0, 0), p2 = mk(0, 0, 0);
+#pragma unroll
+      for (int i = 0; i < 4; i++) { p1 = p1 + b[i] * P[i].v1; p2 = p2 + b[i] * P[i].v2; }
+      out[0] = depth; out[1] = n.x; out[2] = n.y; out[3] = n.z;
+      out[4] = 0.5f * (p1.x * inv + p2.x * inv); out[5] = 0.5f * (p1.y * inv + p2.y * inv); out[6] = 0.5f * (p1.z * inv + p2.z * inv);
+      return true;
+    }
+    expand_portal(P, v4);
+  }
+}
+// squared distance between two segments (bounding-capsule broad phase)
+__device__ __forceinline__ float segseg_dist2(V3 p1, V3 q1, V3 p2, V3 q2) {
+  const V3 d1 = q1 - p1, d2 = q2 - p2, r = p1 - p2;
+  const float a = dot(d1, d1), e = dot(d2, d2), f = dot(d2, r), c = dot(d1, r), b = dot(d1, d2);
+  const float den = a * e - b * b;
+  float s = den > 1e-12f ? fminf(fmaxf((b * f - c * e) / den, 0.f), 1.f) : 0.f;
+  float t = (b * s + f) / fmaxf(e, 1e-20f);
+  if (t < 0.f) { t = 0.f; s = fminf(fmaxf(-c / fmaxf(a, 1e-20f), 0.f), 1.f); }
+  else if (t > 1.f) { t = 1.f; s = fminf(fmaxf((b - c) / fmaxf(a, 1e-20f), 0.f), 1.f); }
+  const V3 dd = (p1 + s * d1) - (p2 + t * d2);
+  return dot(dd, dd);
+}
+__device__ __forceinline__ float oct_sum_m(unsigned om, float v) {
+  v += __shfl_xor_sync(om, v, 1);
+  v += __shfl_xor_sync(om, v, 2);
+  v += __shfl_xor_sync(om, v, 4);
+  return v;
 }
 
 enum { RW_ACTION_RATE = 0, RW_ANG_VEL_XY, RW_BASE_HEIGHT, RW_BODY_CONTACT_FORCES, RW_COLLISION, RW_DEFAULT_POSITION,
@@ -441,6 +641,10 @@ __global__ void __launch_bounds__(BLOCK, MINB) nm_step_kernel(const NmKernelArgs
   // observations of the CTA's environments, staged so that they leave the SM as fully coalesced rows (to HBM and,
   // for host-resident callers, straight to pinned host memory over PCIe)
   __shared__ __align__(16) float obs_tile[ENV ? (BLOCK / NM_OCT) * NM_NOBS_DEV : 4];
+  // convex-convex pairs (cold): per environment 6 hull poses and up to NM_MAXPAIR contact blocks, dynamic shared memory
+  extern __shared__ __align__(16) unsigned char dyn_smem[];
+  HullPose* const pose_s = reinterpret_cast<HullPose*>(dyn_smem) + (threadIdx.x >> 3) * 6;
+  PairBlk* const pblk = reinterpret_cast<PairBlk*>(dyn_smem + sizeof(HullPose) * 6 * (BLOCK / NM_OCT)) + (threadIdx.x >> 3) * NM_MAXPAIR;
   {
     static_assert(sizeof(NmDevModel) % 16 == 0 && sizeof(NmDevCfg) % 16 == 0, "constant tables are copied as int4");
     const int4* src = reinterpret_cast<const int4*>(A.model);
@@ -728,7 +932,144 @@ __global__ void __launch_bounds__(BLOCK, MINB) nm_step_kernel(const NmKernelArgs
         }
       }
     }
-    const int ncon_env = oct_sumi(nc);
+    // ================================================================ P4b convex-convex pairs between the legs' hulls
+    // Broad phase on bounding capsules (hot, ~3 segment-segment tests per lane); MPR + contact block only for overlapping
+    // capsules (cold: the whole warp skips it when none of its 4 environments has a candidate).
+    const unsigned omask = 0xffu << obase;
+    int npair = 0;                                  // pair contacts of this environment (same in all 8 lanes)
+    if (sm.pair_mask != 0) {
+      const V3 prel = pg - p;                       // hull frame origin relative to the base origin
+      const V3 ca = prel + mul(Xg, ld3(G.cap_a)), cbp = prel + mul(Xg, ld3(G.cap_b));
+      unsigned cand = 0u;                           // bit idx(i,j) of the candidate pairs this lane found
+#pragma unroll
+      for (int dlt = 1; dlt <= 3; dlt++) {
+        const int other = l < 6 ? (l + dlt) % 6 : l;
+        const int src = obase | other;
+        const V3 oa = mk(__shfl_sync(FULL, ca.x, src), __shfl_sync(FULL, ca.y, src), __shfl_sync(FULL, ca.z, src));
+        const V3 ob = mk(__shfl_sync(FULL, cbp.x, src), __shfl_sync(FULL, cbp.y, src), __shfl_sync(FULL, cbp.z, src));
+        const float orad = __shfl_sync(FULL, G.cap_r, src);
+        const int i = min(l, other), j = max(l, other);
+        const int idx = i * 5 - (i * (i - 1)) / 2 + (j - i - 1);          // lexicographic index of (i, j), i < j < 6
+        const float thr = G.cap_r + orad + 1e-4f;
+        if (l < 6 && (dlt < 3 || l < 3) && ((sm.pair_mask >> idx) & 1) && segseg_dist2(ca, cbp, oa, ob) < thr * thr) cand |= 1u << idx;
+      }
+      if (__any_sync(FULL, cand != 0u)) {
+        cand |= __shfl_xor_sync(FULL, cand, 1); cand |= __shfl_xor_sync(FULL, cand, 2); cand |= __shfl_xor_sync(FULL, cand, 4);
+        if (l < 6) {                                // stage the six hull poses of the environment
+          HullPose& hp = pose_s[l];
+#pragma unroll
+          for (int k = 0; k < 9; k++) hp.X[k] = Xg.a[k];
+          hp.p[0] = prel.x; hp.p[1] = prel.y; hp.p[2] = prel.z;
+          const V3 cw = prel + mul(Xg, ld3(G.center));
+          hp.c[0] = cw.x; hp.c[1] = cw.y; hp.c[2] = cw.z;
+          hp.adr = G.hull_adr; hp.num = G.hull_num;
+        }
+        __syncwarp();
+        const V3 comr = com - p;
+        int idx = 0;
+        for (int i = 0; i < 5; i++)
+          for (int j = i + 1; j < 6; j++, idx++) {
+            const bool mine = (cand >> idx) & 1u;
+            if (!__any_sync(FULL, mine)) continue;
+            if (!mine || npair >= NM_MAXPAIR) continue;          // (uniform within the octet)
+            float mo[7];
+            if (!mpr_penetration_oct(A.hull_vert, &pose_s[i], &pose_s[j], sm.mpr_tolerance, sm.mpr_iterations, l, omask, mo)) continue;
+            // ---- contact frame (≙ mju_makeFrame on the MPR direction), rows of body j minus rows of body i
+            PairBlk& P = pblk[npair];
+            const V3 n = normalized(mk(mo[1], mo[2], mo[3]));
+            V3 t1 = (n.y < 0.5f && n.y > -0.5f) ? mk(0.f, 1.f, 0.f) : mk(0.f, 0.f, 1.f);
+            { const float dd = dot_plain(n, t1); t1 = normalized(mk(t1.x - dd * n.x, t1.y - dd * n.y, t1.z - dd * n.z)); }
+            const V3 t2 = cross(n, t1);
+            const V3 frm[3] = {n, t1, t2};
+            const V3 r = mk(mo[4], mo[5], mo[6]) - comr;       // contact point relative to the c-frame origin
+            const float sgn = l == i ? -1.f : (l == j ? 1.f : 0.f);
+            V3 colk[3];
+#pragma unroll
+            for (int q = 0; q < 3; q++) colk[q] = sgn * (cd[q].v + cross(cd[q].w, r));
+            const float mu = G.mu * dr_mu;                       // (lanes i and j agree: shared contact parameters)
+            float Y[3][6], Z[3][3], vb[3], as[3], aw[3];
+#pragma unroll
+            for (int f = 0; f < 3; f++) {
+              float Jk[3], Jt[6];
+#pragma unroll
+              for (int q = 0; q < 3; q++) Jk[q] = dot(frm[f], colk[q]);
+#pragma unroll
+              for (int a = 0; a < 6; a++) Jt[a] = oct_sum_m(omask, -fmaf(Jk[0], F.E[0][a], fmaf(Jk[1], F.E[1][a], Jk[2] * F.E[2][a])));
+              fwd6(F.S, F.Si, Jt, Y[f]);
+              fwd3(F.g, F.gi, Jk, Z[f]);
+              vb[f] = oct_sum_m(omask, Jk[0] * thd[0] + Jk[1] * thd[1] + Jk[2] * thd[2]);
+              as[f] = oct_sum_m(omask, fmaf(Jk[0], xsk[0], fmaf(Jk[1], xsk[1], Jk[2] * xsk[2])));
+              aw[f] = oct_sum_m(omask, fmaf(Jk[0], awk[0], fmaf(Jk[1], awk[1], Jk[2] * awk[2])));
+            }
+            const float dist = G.margin - mo[0];
+            const float pos = dist - G.margin;
+            const float imp = impedance(G, pos);
+            const float rself = oct_sum_m(omask, (l == i || l == j) ? G.rfac_self * (dr_mu * dr_mu) * (1.f + mu * mu) / (1.f + G.mu * G.mu) : 0.f);
+            const float R = fmaxf(rself * (1.f - imp) / imp, NM_MINVAL);
+            const float kd = G.K * imp * pos, rinv = 1.f / R;
+            float ey[4][6], ez[4][3];
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+              const float sg = (e & 1) ? -mu : mu;
+#pragma unroll
+              for (int a = 0; a < 6; a++) ey[e][a] = fmaf(sg, Y[1 + (e >> 1)][a], Y[0][a]);
+#pragma unroll
+              for (int q = 0; q < 3; q++) ez[e][q] = fmaf(sg, Z[1 + (e >> 1)][q], Z[0][q]);
+            }
+            float Gm[10];
+            const int gi_[10] = {0, 1, 2, 3, 0, 2, 0, 0, 1, 1}, gj_[10] = {0, 1, 2, 3, 1, 3, 2, 3, 2, 3};
+#pragma unroll
+            for (int k = 0; k < 10; k++) {
+              float t = 0.f;
+#pragma unroll
+              for (int q = 0; q < 3; q++) t = fmaf(ez[gi_[k]][q], ez[gj_[k]][q], t);
+              t = oct_sum_m(omask, t);                           // both legs' parts
+#pragma unroll
+              for (int a = 0; a < 6; a++) t = fmaf(ey[gi_[k]][a], ey[gj_[k]][a], t);
+              Gm[k] = t;
+            }
+            if (l == i || l == j) {
+              float (*Zs)[3] = l == i ? P.Zi : P.Zj;
+#pragma unroll
+              for (int f = 0; f < 3; f++)
+#pragma unroll
+                for (int q = 0; q < 3; q++) Zs[f][q] = Z[f][q];
+            }
+            if (l == i) {                                        // the octet-uniform part is written once, by the lane whose geom parameters apply
+#pragma unroll
+              for (int f = 0; f < 3; f++)
+#pragma unroll
+                for (int a = 0; a < 6; a++) P.Y[f][a] = Y[f][a];
+#pragma unroll
+              for (int k = 0; k < 10; k++) P.G[k] = Gm[k];
+#pragma unroll
+              for (int e = 0; e < 4; e++) {
+                const float sg = (e & 1) ? -mu : mu;
+                const int t = 1 + (e >> 1);
+                const float aref = -G.B * fmaf(sg, vb[t], vb[0]) - kd;
+                P.b[e] = fmaf(sg, as[t], as[0]) - aref;
+                P.adi[e] = 1.f / (Gm[e] + R);
+                const float jar = fmaf(sg, aw[t], aw[0]) - aref;
+                P.f[e] = jar < 0.f ? -jar * rinv : 0.f;
+              }
+#pragma unroll
+              for (int t = 0; t < 2; t++) {
+                const float K1 = Gm[2 * t] + Gm[2 * t + 1] - 2.f * Gm[4 + t];
+                P.ik[t] = K1 < NM_MINVAL ? 0.f : 1.f / K1;
+              }
+              P.R = R; P.dist = dist; P.mu = mu;
+              P.pos[0] = mo[4] + p.x; P.pos[1] = mo[5] + p.y; P.pos[2] = mo[6] + p.z;
+              P.nrm[0] = n.x; P.nrm[1] = n.y; P.nrm[2] = n.z;
+              P.li = i; P.lj = j;
+            }
+            npair++;
+          }
+        __syncwarp();
+      }
+    }
+    int npair_max = max(npair, __shfl_xor_sync(FULL, npair, 8));
+    npair_max = max(npair_max, __shfl_xor_sync(FULL, npair_max, 16));          // warp-uniform
+    const int ncon_env = oct_sumi(nc) + npair;
     // Sweep order inside an env is MuJoCo's row order: base geom (lane 6) first, then legs 0..5.  Each octet walks ITS
     // OWN list of contact-owning lanes: in slot k of a sweep the k-th owner of every octet works, so a sweep costs
     // max(#owners per env) slots for the warp, not |union of owner lanes over its 4 envs|.
@@ -740,7 +1081,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) nm_step_kernel(const NmKernelArgs
     int nslot = __popc(ord);
     nslot = max(nslot, __shfl_xor_sync(FULL, nslot, 8));
     nslot = max(nslot, __shfl_xor_sync(FULL, nslot, 16));                   // warp-uniform: slots per sweep
-    const bool any_contact = nslot > 0;
+    const bool any_contact = nslot > 0 || npair_max > 0;
     unsigned owner_tab = 0u;                                              // 4 bits per slot: owning lane of this octet (0 if none)
     {
       unsigned t = ord;
@@ -875,6 +1216,22 @@ __global__ void __launch_bounds__(BLOCK, MINB) nm_step_kernel(const NmKernelArgs
         const float hR = 0.5f * cb.R[c];
         cl += f0 * fmaf(hR, f0, cb.b[c][0]) + f1 * fmaf(hR, f1, cb.b[c][1]) + f2 * fmaf(hR, f2, cb.b[c][2]) + f3 * fmaf(hR, f3, cb.b[c][3]);
       }
+      for (int pi = 0; pi < npair; pi++) {                    // pair contacts: Y and the cost terms enter once (lane li), Z on both legs
+        const PairBlk& P = pblk[pi];
+        const float f0 = P.f[0], f1 = P.f[1], f2 = P.f[2], f3 = P.f[3];
+        const float c0 = (f0 + f1) + (f2 + f3), c1 = P.mu * (f0 - f1), c2 = P.mu * (f2 - f3);
+        if (l == P.li) {
+#pragma unroll
+          for (int a = 0; a < 6; a++) u[a] = fmaf(P.Y[0][a], c0, fmaf(P.Y[1][a], c1, fmaf(P.Y[2][a], c2, u[a])));
+          const float hR = 0.5f * P.R;
+          cl += f0 * fmaf(hR, f0, P.b[0]) + f1 * fmaf(hR, f1, P.b[1]) + f2 * fmaf(hR, f2, P.b[2]) + f3 * fmaf(hR, f3, P.b[3]);
+        }
+        if (l == P.li || l == P.lj) {
+          const float (*Zs)[3] = l == P.li ? P.Zi : P.Zj;
+#pragma unroll
+          for (int j = 0; j < 3; j++) wv[j] = fmaf(Zs[0][j], c0, fmaf(Zs[1][j], c1, fmaf(Zs[2][j], c2, wv[j])));
+        }
+      }
       float uu = 0.f;
 #pragma unroll
       for (int a = 0; a < 6; a++) { u[a] = oct_sum(u[a]); uu = fmaf(u[a], u[a], uu); }
@@ -884,11 +1241,14 @@ __global__ void __launch_bounds__(BLOCK, MINB) nm_step_kernel(const NmKernelArgs
         for (int c = 0; c < nc; c++)
 #pragma unroll
           for (int rr = 0; rr < 4; rr++) cb.f[c][rr] = 0.f;
+        for (int pi = 0; pi < npair; pi++)
+          if (l == pblk[pi].li) { pblk[pi].f[0] = 0.f; pblk[pi].f[1] = 0.f; pblk[pi].f[2] = 0.f; pblk[pi].f[3] = 0.f; }
 #pragma unroll
         for (int a = 0; a < 6; a++) u[a] = 0.f;
 #pragma unroll
         for (int j = 0; j < 3; j++) wv[j] = 0.f;
       } else dbg_warm = ncon_env > 0 ? 1 : 0;
+      if (npair_max > 0) __syncwarp();
 
       // ---- sweeps: rows in contact order (base geom first, then legs 1..6), Gauss-Seidel through u.
       // sweep 0..iterations-1: PGS on single edges (with R); then noslip on opposing edge pairs (without R, sum fixed).
@@ -942,6 +1302,37 @@ __global__ void __launch_bounds__(BLOCK, MINB) nm_step_kernel(const NmKernelArgs
 #pragma unroll
           for (int a = 0; a < 6; a++) u[a] = oct_bcast(u[a], obase | owner);
         }
+        // pair contacts: rows after all plane contacts (MuJoCo orders contacts by body pair; the world body's pairs come first).
+        // All eight lanes run the visit on identical (shared-memory) data, so u stays replicated without a broadcast; the
+        // two legs' Z.w enter through one octet sum, and each of the two lanes applies its own Z to its w.
+        for (int pi = 0; pi < npair_max; pi++) {
+          if (active && pi < npair) {
+            PairBlk& P = pblk[pi];
+            const bool isI = l == P.li, isJ = l == P.lj;
+            ConRegs kp;
+            float zl[3][3];
+#pragma unroll
+            for (int f = 0; f < 3; f++) {
+#pragma unroll
+              for (int a = 0; a < 6; a++) kp.Y[f][a] = P.Y[f][a];
+#pragma unroll
+              for (int j = 0; j < 3; j++) { kp.Z[f][j] = 0.f; zl[f][j] = isI ? P.Zi[f][j] : (isJ ? P.Zj[f][j] : 0.f); }
+            }
+#pragma unroll
+            for (int i = 0; i < 10; i++) kp.G[i] = P.G[i];
+#pragma unroll
+            for (int i = 0; i < 4; i++) { kp.b[i] = P.b[i]; kp.adi[i] = P.adi[i]; kp.f[i] = P.f[i]; }
+            kp.R = P.R; kp.ik[0] = P.ik[0]; kp.ik[1] = P.ik[1];
+            float zs[3], cc[3], imp_other = 0.f, wz[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+            for (int f = 0; f < 3; f++) zs[f] = oct_sum_m(omask, fmaf(zl[f][0], wv[0], fmaf(zl[f][1], wv[1], zl[f][2] * wv[2])));
+            con_sweep(kp, u, wz, P.mu, in_noslip, isI ? improvement : imp_other, zs[0], zs[1], zs[2], cc);
+#pragma unroll
+            for (int j = 0; j < 3; j++) wv[j] = fmaf(zl[0][j], cc[0], fmaf(zl[1][j], cc[1], fmaf(zl[2][j], cc[2], wv[j])));
+            if (isI) { P.f[0] = kp.f[0]; P.f[1] = kp.f[1]; P.f[2] = kp.f[2]; P.f[3] = kp.f[3]; }
+          }
+          __syncwarp();
+        }
         improvement = oct_sum(improvement);
         if (active) { if (in_noslip) dbg_noslip++; else dbg_pgs++; }
         if (improvement * sm.solver_scale < (in_noslip ? sm.noslip_tolerance : sm.tolerance)) active = false;
@@ -974,6 +1365,16 @@ __global__ void __launch_bounds__(BLOCK, MINB) nm_step_kernel(const NmKernelArgs
         if (L.site_r[0] >= 0.f && ray_sphere(pg + mul(Xg, ld3(L.site_pos[0])), L.site_r[0], cb.pos[c], ray) >= 0.f) fn_slot0 += fn;
         if (L.site_r[1] >= 0.f && ray_sphere(pg + mul(Xg, ld3(L.site_pos[1])), L.site_r[1], cb.pos[c], ray) >= 0.f) fn_slot1 += fn;
       }
+      for (int pi = 0; pi < npair; pi++) {                   // pair contacts load both legs' sensors (ray along +-normal)
+        const PairBlk& P = pblk[pi];
+        if (l != P.li && l != P.lj) continue;
+        const float fn = P.f[0] + P.f[1] + P.f[2] + P.f[3];
+        if (fn <= 0.f) continue;
+        const float sg = l == P.lj ? -1.f : 1.f;             // the normal points from body i to body j; flipped for the second body
+        const V3 ray = mk(sg * P.nrm[0], sg * P.nrm[1], sg * P.nrm[2]), cp = ld3(P.pos);
+        if (L.site_r[0] >= 0.f && ray_sphere(pg + mul(Xg, ld3(L.site_pos[0])), L.site_r[0], cp, ray) >= 0.f) fn_slot0 += fn;
+        if (L.site_r[1] >= 0.f && ray_sphere(pg + mul(Xg, ld3(L.site_pos[1])), L.site_r[1], cp, ray) >= 0.f) fn_slot1 += fn;
+      }
     }
     TSTAMP(8 + 10 * sub);
     PHASE_SYNC();
@@ -984,7 +1385,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) nm_step_kernel(const NmKernelArgs
 
     // ================================================================ optional debug record (parity harness)
     if (A.debug != nullptr && valid && sub == A.nstep - 1) {
-      float* dbg = A.debug + (size_t)env * 288;
+      float* dbg = A.debug + (size_t)env * NM_DBG;
       if (l == 0) {
         dbg[0] = (float)ncon_env; dbg[1] = (float)dbg_pgs; dbg[2] = (float)dbg_noslip; dbg[3] = (float)dbg_warm;
 #pragma unroll
@@ -998,6 +1399,15 @@ __global__ void __launch_bounds__(BLOCK, MINB) nm_step_kernel(const NmKernelArgs
       if (leg) {
 #pragma unroll
         for (int j = 0; j < 3; j++) { dbg[102 + jo + j] = xsk[j]; dbg[134 + jo + j] = xsk[j] + xk[j]; }
+      }
+      if (l == 0) {
+        dbg[4] = (float)npair;
+        for (int pi = 0; pi < npair; pi++) {
+          const PairBlk& P = pblk[pi];
+          float* g = dbg + 288 + 8 * pi;
+          g[0] = (float)P.li; g[1] = (float)P.lj; g[2] = P.dist; g[3] = P.pos[0]; g[4] = P.pos[1]; g[5] = P.pos[2];
+          g[6] = P.f[0] + P.f[1] + P.f[2] + P.f[3]; g[7] = P.nrm[2];
+        }
       }
       if (l < 7 && any_contact) {                   // pyramid-edge forces of this lane's contacts (stage attribution)
         float* g = dbg + 160 + l * 16;
@@ -1362,6 +1772,8 @@ void nm_launch_finalize(const NmKernelArgs& a, void* stream) {
   nm_finalize_kernel<<<(a.num_envs + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
 }
 
+static size_t step_dyn_smem(int block) { return (size_t)(block / NM_OCT) * (6 * sizeof(HullPose) + NM_MAXPAIR * sizeof(PairBlk)); }
+
 void nm_launch_step(const NmKernelArgs& a, bool env_mode, void* stream) {
   const int threads = a.num_envs * NM_OCT;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -1371,14 +1783,22 @@ void nm_launch_step(const NmKernelArgs& a, bool env_mode, void* stream) {
   int& sms = sms_of[dev & 63];
   if (sms == 0 && (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0)) sms = 148;
   const bool one_wave = threads <= sms * 8 * 32;           // fits one wave of the 255-register build (8 warps/SM)
+  static bool attr_set[64] = {false};                      // the large-block build needs > 48 KB of shared memory in total
+  if (!attr_set[dev & 63]) {
+    cudaFuncSetAttribute(nm_step_kernel<true, NM_LARGE_BLOCK, NM_LARGE_MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)step_dyn_smem(NM_LARGE_BLOCK));
+    cudaFuncSetAttribute(nm_step_kernel<false, NM_LARGE_BLOCK, NM_LARGE_MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)step_dyn_smem(NM_LARGE_BLOCK));
+    cudaFuncSetAttribute(nm_step_kernel<true, NM_SMALL_BLOCK, NM_SMALL_MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)step_dyn_smem(NM_SMALL_BLOCK));
+    cudaFuncSetAttribute(nm_step_kernel<false, NM_SMALL_BLOCK, NM_SMALL_MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)step_dyn_smem(NM_SMALL_BLOCK));
+    attr_set[dev & 63] = true;
+  }
   if (one_wave) {
     const int blocks = (threads + NM_SMALL_BLOCK - 1) / NM_SMALL_BLOCK;
-    if (env_mode) nm_step_kernel<true, NM_SMALL_BLOCK, NM_SMALL_MINB><<<blocks, NM_SMALL_BLOCK, 0, st>>>(a);
-    else nm_step_kernel<false, NM_SMALL_BLOCK, NM_SMALL_MINB><<<blocks, NM_SMALL_BLOCK, 0, st>>>(a);
+    if (env_mode) nm_step_kernel<true, NM_SMALL_BLOCK, NM_SMALL_MINB><<<blocks, NM_SMALL_BLOCK, step_dyn_smem(NM_SMALL_BLOCK), st>>>(a);
+    else nm_step_kernel<false, NM_SMALL_BLOCK, NM_SMALL_MINB><<<blocks, NM_SMALL_BLOCK, step_dyn_smem(NM_SMALL_BLOCK), st>>>(a);
   } else {
     const int blocks = (threads + NM_LARGE_BLOCK - 1) / NM_LARGE_BLOCK;
-    if (env_mode) nm_step_kernel<true, NM_LARGE_BLOCK, NM_LARGE_MINB><<<blocks, NM_LARGE_BLOCK, 0, st>>>(a);
-    else nm_step_kernel<false, NM_LARGE_BLOCK, NM_LARGE_MINB><<<blocks, NM_LARGE_BLOCK, 0, st>>>(a);
+    if (env_mode) nm_step_kernel<true, NM_LARGE_BLOCK, NM_LARGE_MINB><<<blocks, NM_LARGE_BLOCK, step_dyn_smem(NM_LARGE_BLOCK), st>>>(a);
+    else nm_step_kernel<false, NM_LARGE_BLOCK, NM_LARGE_MINB><<<blocks, NM_LARGE_BLOCK, step_dyn_smem(NM_LARGE_BLOCK), st>>>(a);
   }
 }
 

@@ -520,3 +520,90 @@ def test_large_batch_kernel_variant():
           f"mean contacts {ncon.mean():.1f}")
     assert ncon.mean() > 1.0
     assert np.median(ev) < 1e-5 and np.percentile(ev, 99) < 5e-5 and np.percentile(ev, 99.9) < 1e-3 and eq.max() < 1e-4
+
+
+def test_tibia_tibia_contacts_lockstep():
+    """Convex-convex contacts between the tibia hulls (reference models/nightmare_v3/mjmodel.xml:47, MuJoCo: libccd MPR).
+    256 robots with their legs thrown across each other (joints +-1 rad around the stance), lockstep against the oracle:
+    every substep starts from the oracle's state rounded to fp32.
+
+    * WHICH pairs touch must agree exactly, grazing contacts (< 0.1 mm) aside.
+    * MPR is discontinuous in its inputs (tests/test_oracle_tibia_contacts.py::stable_pairs): on the pairs whose fp64 result
+      does not move under a 1e-12 rad perturbation -- decided by the oracle alone -- depth and position must agree for at
+      least 90 % (the float build of the oracle itself reaches ~94 %, same test file).
+    * On environments whose contacts all agree, the one-step state error is held to the bounds of the plane-contact suite."""
+    G = _common()
+    from test_oracle_tibia_contacts import stable_pairs
+    cm, dm, om = G.models()
+    rng = np.random.default_rng(5)
+    n, T = 256, 30
+    ob = G.O.OracleBatch(om, n)
+    gb = G.Batch(dm, n, G.DEV, debug=True)
+    qpos = np.tile(cm.qpos0, (n, 1))
+    qpos[:, 7:] += rng.uniform(-1.0, 1.0, (n, 18))
+    qpos[:, 2] = rng.uniform(0.06, 0.3, n)
+    qpos[:, 3:7] += rng.normal(size=(n, 4)) * 0.15
+    qpos[:, 3:7] /= np.linalg.norm(qpos[:, 3:7], axis=1, keepdims=True)
+    ob.set_state(qpos.astype(np.float32), np.zeros((n, 24)), np.zeros((n, 24)))
+    pairs = graze = stable = agree = set_mismatch = dropped = 0
+    errs_v, errs_q = [], []
+    for t in range(T):
+        if t % 4 == 0:
+            ctrl = rng.uniform(-8, 8, (n, 18)).astype(np.float32)
+        q, v, w = ob.get_state()
+        q32, v32, w32 = q.astype(np.float32), v.astype(np.float32), w.astype(np.float32)
+        _, ok = stable_pairs(q32, rng, trials=2)
+        ob.set_state(q32, v32, w32)
+        G.push_state(gb, q32, v32, w32)
+        ob.physics_step(ctrl, 1, 8)
+        gb.physics_step(torch.from_numpy(ctrl), 1)
+        torch.cuda.synchronize()
+        oq, ov, _ = ob.get_state()
+        gq, gv, _ = G.gpu_state(gb)
+        dbg = gb.debug.cpu().numpy()
+        good = np.ones(n, dtype=bool)
+        for i in range(n):
+            con = ob.get(i, "contact").reshape(-1, 7)
+            plane, pr = con[con[:, 0] == 0], con[con[:, 0] >= 2]
+            o_pairs = {(int(c[0]) - 2, int(c[1]) - 2): c for c in pr}
+            if len(o_pairs) > 4:                           # NM_MAXPAIR: further simultaneous pairs are dropped by the kernel
+                dropped += 1
+                good[i] = False
+                continue
+            g_pairs = {(int(dbg[i, 288 + 8 * k]), int(dbg[i, 288 + 8 * k + 1])): dbg[i, 288 + 8 * k: 288 + 8 * k + 8] for k in range(int(dbg[i, 4]))}
+            for key in set(o_pairs) | set(g_pairs):
+                pairs += 1
+                if key not in o_pairs or key not in g_pairs:
+                    depth = -(o_pairs[key][3] if key in o_pairs else g_pairs[key][2])
+                    if depth < 1e-4:
+                        graze += 1
+                    else:
+                        set_mismatch += 1
+                    good[i] = False
+                    continue
+                oc, gc = o_pairs[key], g_pairs[key]
+                same = abs(oc[3] - gc[2]) < 2e-6 and np.abs(oc[4:7] - gc[3:6]).max() < 1e-5
+                if (key[0] + 2, key[1] + 2) in ok[i]:
+                    stable += 1
+                    agree += bool(same)
+                good[i] &= bool(same)
+            # plane contacts: same count and support vertices, as in the plane-contact suite
+            if int(dbg[i, 0]) != len(con):
+                good[i] = False
+                continue
+            for lane, geom in [(6, 1)] + [(k, 2 + k) for k in range(6)]:
+                mine = plane[plane[:, 1] == geom]
+                rec = dbg[i, 8 + lane * 12: 8 + lane * 12 + 9]
+                if int(rec[0]) != len(mine) or any(int(rec[1 + 2 * c]) != int(mine[c, 2]) for c in range(len(mine))):
+                    good[i] = False
+        has_pair = dbg[:, 4] > 0
+        sel = good & has_pair
+        errs_v.append(G.per_env_rel(gv, ov)[sel]); errs_q.append(G.per_env_rel(gq, oq)[sel])
+    ev, eq = np.concatenate(errs_v), np.concatenate(errs_q)
+    print(f"\n[tibia-tibia] {pairs} pair contacts ({graze} grazing ones differ, {set_mismatch} other set mismatches, {dropped} env-steps with > 4 pairs); "
+          f"{stable} stable, {agree} of them agree in depth/position; on {ev.size} env-steps with agreeing pair contacts: qvel rel median {np.median(ev):.2e} "
+          f"p99 {np.percentile(ev, 99):.2e} max {ev.max():.2e}, qpos max {eq.max():.2e}")
+    assert pairs > 1000 and stable > 0.6 * pairs
+    assert set_mismatch == 0
+    assert agree >= 0.9 * stable
+    assert ev.size > 300 and np.median(ev) < 1e-5 and np.percentile(ev, 99) < 1e-3
