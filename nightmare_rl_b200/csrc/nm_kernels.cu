@@ -937,7 +937,11 @@ __global__ void __launch_bounds__(BLOCK, MINB) nm_step_kernel(const NmKernelArgs
     // capsules (cold: the whole warp skips it when none of its 4 environments has a candidate).
     const unsigned omask = 0xffu << obase;
     int npair = 0;                                  // pair contacts of this environment (same in all 8 lanes)
+#ifdef NM_NO_PAIRS
+    if (false) {
+#else
     if (sm.pair_mask != 0) {
+#endif
       const V3 prel = pg - p;                       // hull frame origin relative to the base origin
       const V3 ca = prel + mul(Xg, ld3(G.cap_a)), cbp = prel + mul(Xg, ld3(G.cap_b));
       unsigned cand = 0u;                           // bit idx(i,j) of the candidate pairs this lane found
@@ -967,7 +971,9 @@ __global__ void __launch_bounds__(BLOCK, MINB) nm_step_kernel(const NmKernelArgs
         __syncwarp();
         const V3 comr = com - p;
         int idx = 0;
+#pragma unroll 1
         for (int i = 0; i < 5; i++)
+#pragma unroll 1
           for (int j = i + 1; j < 6; j++, idx++) {
             const bool mine = (cand >> idx) & 1u;
             if (!__any_sync(FULL, mine)) continue;

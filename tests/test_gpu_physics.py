@@ -42,10 +42,17 @@ def test_contact_free_single_step():
     torch.cuda.synchronize()
     oq, ov, ow = ob.get_state()
     gq, gv, gw = G.gpu_state(gb)
-    assert G.per_env_rel(gq, oq).max() < 1e-5
-    assert G.per_env_rel(gv, ov).max() < 1e-5
-    assert G.per_env_rel(gw, ow).max() < 1e-5                      # qacc_warmstart = qacc_smooth when nothing touches
-    assert (gb.debug[:, 0] == 0).all() and (gb.sensordata == 0).all()
+    # legs thrown up to +-0.8 rad from the stance cross each other in ~10 % of the robots (tibia-tibia contacts, covered by
+    # test_tibia_tibia_contacts_lockstep): both sides must agree on WHICH robots are contact free, and those are compared
+    free = np.array([ob.get(i, "ncon")[0] for i in range(n)]) == 0
+    gfree = (gb.debug[:, 0] == 0).cpu().numpy()
+    depth = np.array([-(ob.get(i, "contact").reshape(-1, 7)[:, 3].min()) if not free[i] else 1.0 for i in range(n)])
+    assert (free == gfree)[depth > 1e-4].all() and free.sum() > 0.7 * n
+    free &= gfree
+    assert G.per_env_rel(gq, oq)[free].max() < 1e-5
+    assert G.per_env_rel(gv, ov)[free].max() < 1e-5
+    assert G.per_env_rel(gw, ow)[free].max() < 1e-5                # qacc_warmstart = qacc_smooth when nothing touches
+    assert (gb.sensordata.cpu().numpy()[free] == 0).all()
 
 
 @pytest.mark.parametrize("tumbling", [False, True])
