@@ -357,32 +357,36 @@ __device__ __forceinline__ void con_load(const ConBlk& cb, int c, ConRegs& k) {
   k.R = cb.R[c];
   k.ik[0] = cb.ik[c][0]; k.ik[1] = cb.ik[c][1];
 }
-// Residuals of the 4 edges against the CURRENT dual state, all at once: r_e = b_e + (p0 +- mu*p_t), p_a = Y_a.u + Z_a.w
-// (three independent dot products); the Gauss-Seidel coupling among the 4 rows of the contact is then applied through its
-// edge Gram matrix instead of re-walking u after every row.
-__device__ __forceinline__ void con_sweep(ConRegs& k, float* u, float* wv, float mu, bool in_noslip, float& improvement,
-                                          float pe0 = 0.f, float pe1 = 0.f, float pe2 = 0.f, float* cout = nullptr) {
-  float p0 = pe0, p1 = pe1, p2 = pe2;          // (pair contacts: the other leg's Z.w, plane contacts: 0)
-#pragma unroll
-  for (int a = 0; a < 6; a++) { const float ua = u[a]; p0 = fmaf(k.Y[0][a], ua, p0); p1 = fmaf(k.Y[1][a], ua, p1); p2 = fmaf(k.Y[2][a], ua, p2); }
-#pragma unroll
-  for (int j = 0; j < 3; j++) { const float wj = wv[j]; p0 = fmaf(k.Z[0][j], wj, p0); p1 = fmaf(k.Z[1][j], wj, p1); p2 = fmaf(k.Z[2][j], wj, p2); }
-  float r[4] = {k.b[0] + fmaf(mu, p1, p0), k.b[1] + fmaf(-mu, p1, p0), k.b[2] + fmaf(mu, p2, p0), k.b[3] + fmaf(-mu, p2, p0)};
-  float* o = k.f;
-  float d[4];
-  const float g00 = k.G[0], g11 = k.G[1], g22 = k.G[2], g33 = k.G[3], g01 = k.G[4], g23 = k.G[5];
-  const float g02 = k.G[6], g03 = k.G[7], g12 = k.G[8], g13 = k.G[9];
+// One Gauss-Seidel visit of a contact.  Residuals of the 4 edges against the CURRENT dual state, all at once:
+// r_e = b_e + (p0 +- mu*p_t), p_a = Y_a.u + Z_a.w (three independent dot products, summed as a tree); the Gauss-Seidel coupling
+// among the 4 rows of the contact is applied through its edge Gram matrix instead of re-walking u after every row.
+//
+// The visit is the unit of the kernel's critical path (one lane per environment works, 7 sweeps x contacts visits per substep),
+// so the dependent chain is kept as short as the arithmetic allows:
+//   PGS   : f_new = max(0, f*(1 - R*adi) - r*adi)  -- everything that does not depend on r is formed ahead of the chain;
+//   noslip: x = -(Kc + r0 - r1) * ik, clamped to +-mid, with Kc (the part of K0 that only depends on the old forces) ahead of it;
+//   MuJoCo's "reject an update that increases the cost by more than 1e-10" guard is evaluated OFF the chain for all rows of
+//   the visit; it practically never fires (an exact row minimisation cannot increase a convex cost), and when it does the
+//   visit is redone row by row with the guard in line (con_visit_guarded, cold).
+struct VisitIO { float f[4], r[4], G[10], adi[4], ik[2], R, d[4], impr; };
+__device__ __noinline__ void con_visit_guarded(VisitIO& v, int in_noslip) {
+  float* o = v.f;
+  float* r = v.r;
+  float* d = v.d;
+  float impr = 0.f;
+  const float g00 = v.G[0], g11 = v.G[1], g22 = v.G[2], g33 = v.G[3], g01 = v.G[4], g23 = v.G[5];
+  const float g02 = v.G[6], g03 = v.G[7], g12 = v.G[8], g13 = v.G[9];
   if (!in_noslip) {
-    const float R = k.R;
+    const float R = v.R;
     const float gd[4] = {g00, g11, g22, g33};
 #pragma unroll
     for (int e = 0; e < 4; e++) {
       const float res = fmaf(R, o[e], r[e]);
-      float fnew = fmaxf(0.f, fmaf(-res, k.adi[e], o[e]));
+      float fnew = fmaxf(0.f, fmaf(-res, v.adi[e], o[e]));
       float de = fnew - o[e];
       float change = de * fmaf(0.5f * de, gd[e] + R, res);
       if (change > 1e-10f) { de = 0.f; fnew = o[e]; change = 0.f; }
-      improvement -= change;
+      impr -= change;
       o[e] = fnew; d[e] = de;
       if (e == 0) { r[1] = fmaf(de, g01, r[1]); r[2] = fmaf(de, g02, r[2]); r[3] = fmaf(de, g03, r[3]); }
       if (e == 1) { r[2] = fmaf(de, g12, r[2]); r[3] = fmaf(de, g13, r[3]); }
@@ -397,9 +401,9 @@ __device__ __forceinline__ void con_sweep(ConRegs& k, float* u, float* wv, float
       const float mid = 0.5f * (o0 + o1);
       const float K0 = mid * (a00 - a11) + bc0 - bc1;
       float f0, f1;
-      if (k.ik[t] == 0.f) { f0 = mid; f1 = mid; }
+      if (v.ik[t] == 0.f) { f0 = mid; f1 = mid; }
       else {
-        float x = -K0 * k.ik[t];
+        float x = -K0 * v.ik[t];
         if (x < -mid) { f0 = 0.f; f1 = 2.f * mid; }
         else if (x > mid) { f0 = 2.f * mid; f1 = 0.f; }
         else { f0 = mid + x; f1 = mid - x; }
@@ -407,11 +411,95 @@ __device__ __forceinline__ void con_sweep(ConRegs& k, float* u, float* wv, float
       float d0 = f0 - o0, d1 = f1 - o1;
       float change = 0.5f * (d0 * (a00 * d0 + a01 * d1) + d1 * (a01 * d0 + a11 * d1)) + d0 * res0 + d1 * res1;
       if (change > 1e-10f) { f0 = o0; f1 = o1; d0 = 0.f; d1 = 0.f; change = 0.f; }
-      improvement -= change;
+      impr -= change;
       o[2 * t] = f0; o[2 * t + 1] = f1; d[2 * t] = d0; d[2 * t + 1] = d1;
       if (t == 0) { r[2] = fmaf(d0, g02, fmaf(d1, g12, r[2])); r[3] = fmaf(d0, g03, fmaf(d1, g13, r[3])); }
     }
   }
+  v.impr = impr;
+}
+
+__device__ __forceinline__ void con_sweep(ConRegs& k, float* u, float* wv, float mu, bool in_noslip, float& improvement,
+                                          float pe0 = 0.f, float pe1 = 0.f, float pe2 = 0.f, float* cout = nullptr) {
+  // (pair contacts: pe = the two legs' Z.w, k.Z = 0; plane contacts: pe = 0)
+  float pp[3];
+#pragma unroll
+  for (int f = 0; f < 3; f++) {
+    const float ta = fmaf(k.Y[f][0], u[0], fmaf(k.Y[f][1], u[1], k.Y[f][2] * u[2]));
+    const float tb = fmaf(k.Y[f][3], u[3], fmaf(k.Y[f][4], u[4], k.Y[f][5] * u[5]));
+    const float tc = fmaf(k.Z[f][0], wv[0], fmaf(k.Z[f][1], wv[1], k.Z[f][2] * wv[2]));
+    pp[f] = (ta + tb) + (tc + (f == 0 ? pe0 : (f == 1 ? pe1 : pe2)));
+  }
+  const float p0 = pp[0], p1 = pp[1], p2 = pp[2];
+  const float r0[4] = {fmaf(mu, p1, p0 + k.b[0]), fmaf(-mu, p1, p0 + k.b[1]), fmaf(mu, p2, p0 + k.b[2]), fmaf(-mu, p2, p0 + k.b[3])};
+  float r[4] = {r0[0], r0[1], r0[2], r0[3]};
+  float* o = k.f;
+  const float fo[4] = {o[0], o[1], o[2], o[3]};
+  float d[4], fn[4];
+  const float g00 = k.G[0], g11 = k.G[1], g22 = k.G[2], g33 = k.G[3], g01 = k.G[4], g23 = k.G[5];
+  const float g02 = k.G[6], g03 = k.G[7], g12 = k.G[8], g13 = k.G[9];
+  float impr = 0.f;
+  bool bad = false;
+  if (!in_noslip) {
+    const float R = k.R;
+    const float gd[4] = {g00, g11, g22, g33};
+    float t0[4];
+#pragma unroll
+    for (int e = 0; e < 4; e++) t0[e] = fo[e] * fmaf(-R, k.adi[e], 1.f);          // ahead of the chain
+#pragma unroll
+    for (int e = 0; e < 4; e++) {
+      fn[e] = fmaxf(0.f, fmaf(-r[e], k.adi[e], t0[e]));                            // chain: FFMA, FMNMX,
+      const float de = fn[e] - fo[e];                                               //        FADD,
+      d[e] = de;
+      if (e == 0) { r[1] = fmaf(de, g01, r[1]); r[2] = fmaf(de, g02, r[2]); r[3] = fmaf(de, g03, r[3]); }   // FFMA
+      if (e == 1) { r[2] = fmaf(de, g12, r[2]); r[3] = fmaf(de, g13, r[3]); }
+      if (e == 2) { r[3] = fmaf(de, g23, r[3]); }
+    }
+    // cost changes and the guard, off the chain (r[e] here is the residual row e saw: rows > e were updated after it)
+    float rs[4] = {r0[0], fmaf(d[0], g01, r0[1]), 0.f, 0.f};
+    rs[2] = fmaf(d[1], g12, fmaf(d[0], g02, r0[2]));
+    rs[3] = r[3];
+#pragma unroll
+    for (int e = 0; e < 4; e++) {
+      const float res = fmaf(R, fo[e], rs[e]);
+      const float change = d[e] * fmaf(0.5f * d[e], gd[e] + R, res);
+      bad |= change > 1e-10f;
+      impr -= change;
+    }
+  } else {
+#pragma unroll
+    for (int t = 0; t < 2; t++) {
+      const float a00 = t ? g22 : g00, a11 = t ? g33 : g11, a01 = t ? g23 : g01;
+      const float o0 = fo[2 * t], o1 = fo[2 * t + 1];
+      const float mid = 0.5f * (o0 + o1);
+      const float Kc = fmaf(mid, a00 - a11, fmaf(a11 - a01, o1, -(a00 - a01) * o0));  // ahead of the chain
+      const float nik = -k.ik[t];
+      const float res0 = r[2 * t], res1 = r[2 * t + 1];
+      const float x = fminf(fmaxf(((res0 - res1) + Kc) * nik, -mid), mid);          // chain: FADD, FADD, FMUL, FMNMX x2,
+      const float f0 = mid + x, f1 = mid - x;                                         //        FADD,
+      const float d0 = f0 - o0, d1 = f1 - o1;                                         //        FADD,
+      fn[2 * t] = f0; fn[2 * t + 1] = f1; d[2 * t] = d0; d[2 * t + 1] = d1;
+      if (t == 0) { r[2] = fmaf(d0, g02, fmaf(d1, g12, r[2])); r[3] = fmaf(d0, g03, fmaf(d1, g13, r[3])); }   // FFMA x2
+      const float change = 0.5f * (d0 * (a00 * d0 + a01 * d1) + d1 * (a01 * d0 + a11 * d1)) + d0 * res0 + d1 * res1;
+      bad |= change > 1e-10f;
+      impr -= change;
+    }
+  }
+  if (bad) {                         // cold: redo the visit with the guard in line
+    VisitIO v;
+#pragma unroll
+    for (int e = 0; e < 4; e++) { v.f[e] = fo[e]; v.r[e] = r0[e]; v.adi[e] = k.adi[e]; }
+#pragma unroll
+    for (int i = 0; i < 10; i++) v.G[i] = k.G[i];
+    v.ik[0] = k.ik[0]; v.ik[1] = k.ik[1]; v.R = k.R;
+    con_visit_guarded(v, in_noslip ? 1 : 0);
+#pragma unroll
+    for (int e = 0; e < 4; e++) { fn[e] = v.f[e]; d[e] = v.d[e]; }
+    impr = v.impr;
+  }
+  improvement += impr;
+#pragma unroll
+  for (int e = 0; e < 4; e++) o[e] = fn[e];
   const float c0 = (d[0] + d[1]) + (d[2] + d[3]), c1 = mu * (d[0] - d[1]), c2 = mu * (d[2] - d[3]);
   if (cout != nullptr) { cout[0] = c0; cout[1] = c1; cout[2] = c2; }
 #pragma unroll
@@ -419,7 +507,6 @@ __device__ __forceinline__ void con_sweep(ConRegs& k, float* u, float* wv, float
 #pragma unroll
   for (int j = 0; j < 3; j++) wv[j] = fmaf(k.Z[0][j], c0, fmaf(k.Z[1][j], c1, fmaf(k.Z[2][j], c2, wv[j])));
 }
-
 
 // ================================================================================================ convex-convex pairs
 // Tibia-tibia contacts (reference models/nightmare_v3/mjmodel.xml:47).  MuJoCo collides two convex meshes with libccd's
@@ -599,16 +686,17 @@ __device__ __noinline__ bool mpr_penetration_oct(const float4* __restrict__ hv, 
     expand_portal(P, v4);
   }
 }
-// squared distance between two segments (bounding-capsule broad phase)
-__device__ __forceinline__ float segseg_dist2(V3 p1, V3 q1, V3 p2, V3 q2) {
-  const V3 d1 = q1 - p1, d2 = q2 - p2, r = p1 - p2;
-  const float a = dot(d1, d1), e = dot(d2, d2), f = dot(d2, r), c = dot(d1, r), b = dot(d1, d2);
-  const float den = a * e - b * b;
-  float s = den > 1e-12f ? fminf(fmaxf((b * f - c * e) / den, 0.f), 1.f) : 0.f;
-  float t = (b * s + f) / fmaxf(e, 1e-20f);
-  if (t < 0.f) { t = 0.f; s = fminf(fmaxf(-c / fmaxf(a, 1e-20f), 0.f), 1.f); }
-  else if (t > 1.f) { t = 1.f; s = fminf(fmaxf((b - c) / fmaxf(a, 1e-20f), 0.f), 1.f); }
-  const V3 dd = (p1 + s * d1) - (p2 + t * d2);
+// squared distance between two segments (bounding-capsule broad phase); ia / ie = 1 / squared lengths (model constants).
+// Approximate division: the caller compares against a threshold with 0.1 mm of slack.
+__device__ __forceinline__ float segseg_dist2(V3 p1, V3 d1, float ia, V3 p2, V3 d2, float ie) {
+  const V3 r = p1 - p2;
+  const float f = dot(d2, r), c = dot(d1, r), b = dot(d1, d2);
+  const float den = fmaf(-b, b, __fdividef(1.f, ia * ie));
+  float s = den > 1e-12f ? __saturatef(__fdividef(fmaf(b, f, -c * __fdividef(1.f, ie)), den)) : 0.f;
+  float t = fmaf(b, s, f) * ie;
+  if (t < 0.f) { t = 0.f; s = __saturatef(-c * ia); }
+  else if (t > 1.f) { t = 1.f; s = __saturatef((b - c) * ia); }
+  const V3 dd = fma3(s, d1, p1) - fma3(t, d2, p2);
   return dot(dd, dd);
 }
 __device__ __forceinline__ float oct_sum_m(unsigned om, float v) {
@@ -645,6 +733,8 @@ __global__ void __launch_bounds__(BLOCK, MINB) nm_step_kernel(const NmKernelArgs
   extern __shared__ __align__(16) unsigned char dyn_smem[];
   HullPose* const pose_s = reinterpret_cast<HullPose*>(dyn_smem) + (threadIdx.x >> 3) * 6;
   PairBlk* const pblk = reinterpret_cast<PairBlk*>(dyn_smem + sizeof(HullPose) * 6 * (BLOCK / NM_OCT)) + (threadIdx.x >> 3) * NM_MAXPAIR;
+  // bounding capsules of the six leg hulls (hot): start point and direction, one float4 pair per leg
+  float4* const cap_s = reinterpret_cast<float4*>(dyn_smem + (sizeof(HullPose) * 6 + sizeof(PairBlk) * NM_MAXPAIR) * (BLOCK / NM_OCT)) + (threadIdx.x >> 3) * 12;
   {
     static_assert(sizeof(NmDevModel) % 16 == 0 && sizeof(NmDevCfg) % 16 == 0, "constant tables are copied as int4");
     const int4* src = reinterpret_cast<const int4*>(A.model);
@@ -943,19 +1033,25 @@ __global__ void __launch_bounds__(BLOCK, MINB) nm_step_kernel(const NmKernelArgs
     if (sm.pair_mask != 0) {
 #endif
       const V3 prel = pg - p;                       // hull frame origin relative to the base origin
-      const V3 ca = prel + mul(Xg, ld3(G.cap_a)), cbp = prel + mul(Xg, ld3(G.cap_b));
+      const V3 ca = prel + mul(Xg, ld3(G.cap_a)), cdir = mul(Xg, ld3(G.cap_b) - ld3(G.cap_a));
+      if (l < 6) {
+        cap_s[2 * l] = make_float4(ca.x, ca.y, ca.z, cdir.x);
+        cap_s[2 * l + 1] = make_float4(cdir.y, cdir.z, 0.f, 0.f);
+      }
+      __syncwarp();
       unsigned cand = 0u;                           // bit idx(i,j) of the candidate pairs this lane found
+      if (l < 6) {
 #pragma unroll
-      for (int dlt = 1; dlt <= 3; dlt++) {
-        const int other = l < 6 ? (l + dlt) % 6 : l;
-        const int src = obase | other;
-        const V3 oa = mk(__shfl_sync(FULL, ca.x, src), __shfl_sync(FULL, ca.y, src), __shfl_sync(FULL, ca.z, src));
-        const V3 ob = mk(__shfl_sync(FULL, cbp.x, src), __shfl_sync(FULL, cbp.y, src), __shfl_sync(FULL, cbp.z, src));
-        const float orad = __shfl_sync(FULL, G.cap_r, src);
-        const int i = min(l, other), j = max(l, other);
-        const int idx = i * 5 - (i * (i - 1)) / 2 + (j - i - 1);          // lexicographic index of (i, j), i < j < 6
-        const float thr = G.cap_r + orad + 1e-4f;
-        if (l < 6 && (dlt < 3 || l < 3) && ((sm.pair_mask >> idx) & 1) && segseg_dist2(ca, cbp, oa, ob) < thr * thr) cand |= 1u << idx;
+        for (int dlt = 1; dlt <= 3; dlt++) {
+          const int other = (l + dlt) % 6;
+          const int i = min(l, other), j = max(l, other);
+          const int idx = i * 5 - (i * (i - 1)) / 2 + (j - i - 1);          // lexicographic index of (i, j), i < j < 6
+          if ((dlt == 3 && l >= 3) || !((sm.pair_mask >> idx) & 1)) continue;
+          const float4 q0 = cap_s[2 * other], q1 = cap_s[2 * other + 1];
+          const NmGeom& Go = sm.leg[other].geom;
+          const float thr = G.cap_r + Go.cap_r + 1e-4f;
+          if (segseg_dist2(ca, cdir, G.cap_il2, mk(q0.x, q0.y, q0.z), mk(q0.w, q1.x, q1.y), Go.cap_il2) < thr * thr) cand |= 1u << idx;
+        }
       }
       if (__any_sync(FULL, cand != 0u)) {
         cand |= __shfl_xor_sync(FULL, cand, 1); cand |= __shfl_xor_sync(FULL, cand, 2); cand |= __shfl_xor_sync(FULL, cand, 4);
@@ -1778,7 +1874,7 @@ void nm_launch_finalize(const NmKernelArgs& a, void* stream) {
   nm_finalize_kernel<<<(a.num_envs + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
 }
 
-static size_t step_dyn_smem(int block) { return (size_t)(block / NM_OCT) * (6 * sizeof(HullPose) + NM_MAXPAIR * sizeof(PairBlk)); }
+static size_t step_dyn_smem(int block) { return (size_t)(block / NM_OCT) * (6 * sizeof(HullPose) + NM_MAXPAIR * sizeof(PairBlk) + 12 * sizeof(float4)); }
 
 void nm_launch_step(const NmKernelArgs& a, bool env_mode, void* stream) {
   const int threads = a.num_envs * NM_OCT;

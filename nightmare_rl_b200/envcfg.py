@@ -80,7 +80,8 @@ def build_envcfg(cfg, timestep: float) -> EnvCfgStruct:
     s.tibia_contact_mode = int(cfg.env.tibia_contact_mode)
     s.body_contact_mode = int(cfg.env.body_contact_mode)
     s.add_noise = int(bool(cfg.noise.add_noise))
-    s.resample_period = int(cfg.commands.resampling_time / dt)
+    # int32 field of the C ABI: a resampling time beyond ~1e7 s (play.py uses 1e9 to switch resampling off) saturates instead of wrapping
+    s.resample_period = int(min(cfg.commands.resampling_time / dt, 2 ** 31 - 1))
     # quirk Q10 switch: 1 (default) latches extras only on steps where an env reset, like the reference; 0 refreshes
     # extras['time_outs'] every step (cfg.env.strict_reference = False)
     s.strict_reference = 1 if getattr(cfg.env, "strict_reference", True) else 0

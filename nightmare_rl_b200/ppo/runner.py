@@ -154,6 +154,18 @@ class OnPolicyRunner:
             for key in ep_infos[0]:
                 vals = torch.stack([torch.as_tensor(e[key], device=self.device).float().reshape(()) for e in ep_infos])
                 ep_means[key] = float(vals.mean())
+        if self.world > 1:
+            # every rank holds the statistics of its own env shard: reduce them (episode means weighted by the number of
+            # finished episodes in each rank's ring, per-term episode means averaged) so that rank 0 logs the whole job
+            keys = sorted(ep_means)
+            loc = torch.tensor([(mean_rew or 0.0) * n_ep, (mean_len or 0.0) * n_ep, float(n_ep)] + [ep_means[k] for k in keys],
+                               device=self.device, dtype=torch.float64)
+            dist.all_reduce(loc)
+            n_all = float(loc[2])
+            if n_all > 0:
+                mean_rew, mean_len, n_ep = float(loc[0]) / n_all, float(loc[1]) / n_all, int(n_all)
+            for i, k in enumerate(keys):
+                ep_means[k] = float(loc[3 + i]) / self.world
         self.last_log = dict(iteration=it, fps=fps, collection_time=collection_time, learn_time=learn_time, value_loss=v_loss,
                              surrogate_loss=s_loss, mean_reward=mean_rew, mean_episode_length=mean_len, mean_noise_std=mean_std,
                              learning_rate=self.alg.learning_rate, episode=ep_means, total_timesteps=self.tot_timesteps)
