@@ -346,6 +346,7 @@ static int build_device_model(nm_model* m) {
       for (int a = 0; a < 3; a++) { G.cap_a[a] = (float)(mean[a] + tmin * u[a]); G.cap_b[a] = (float)(mean[a] + tmax * u[a]); }
       G.cap_r = (float)(rmax * 1.0001 + 1e-6);
       G.cap_il2 = (float)(1.0 / std::fmax((tmax - tmin) * (tmax - tmin), 1e-12));
+      G.cap_len = (float)((tmax - tmin) * 1.0001);
       const double mureg = G.mu / std::sqrt(impratio > 1e-15 ? impratio : 1.0);
       G.rfac_self = (float)(2.0 * mureg * mureg * (1.0 + (double)G.mu * G.mu) * body_invweight0[2 * geom_body[g]]);
     }

@@ -29,6 +29,7 @@ struct NmGeom {
   float cap_a[3], cap_b[3]; // bounding capsule of the hull, body frame: segment end points ...
   float cap_r;              // ... and radius (conservative broad phase: hulls whose capsules do not overlap cannot intersect)
   float cap_il2;            // 1 / |cap_b - cap_a|^2
+  float cap_len;            // |cap_b - cap_a|
   float rfac_self;          // this body's share of a pair contact's R: 2 mu_reg^2 (1+mu^2) * body_invweight0
 };
 
