@@ -623,6 +623,134 @@ __device__ __forceinline__ float oct_sum_m(unsigned om, float v) {
   return v;
 }
 
+// Everything the cold pair path needs from the step kernel's registers, handed over through (local) memory so that the cold
+// code lives in its own function and leaves the register allocation of the hot kernel alone (measured: inlined it cost 6 us
+// per 4096-env step without ever executing).
+struct PairIn {
+  float E[3][6], S[21], Si[6], g[6], gi[3];     // block factors of M
+  SV cd[3];                                      // this leg's c-frame dofs
+  float thd[3], xsk[3], awk[3];                  // joint velocities, smooth accelerations, warm-start accelerations
+  V3 comr, p;                                    // c-frame origin relative to the base origin; base origin
+  float X[9];                                    // hull frame
+  V3 prel;                                       // hull frame origin relative to the base origin
+  float dr_mu;
+};
+__device__ __noinline__ int pair_contacts_cold(const PairIn& in, const NmGeom& G, const float4* __restrict__ hull_vert, HullPose* pose_s, PairBlk* pblk,
+                                               unsigned cand, float mpr_tol, int mpr_iter, int l, unsigned omask) {
+  int npair = 0;
+  cand |= __shfl_xor_sync(omask, cand, 1); cand |= __shfl_xor_sync(omask, cand, 2); cand |= __shfl_xor_sync(omask, cand, 4);
+  if (l < 6) {                                // stage the six hull poses of the environment
+    HullPose& hp = pose_s[l];
+#pragma unroll
+    for (int k = 0; k < 9; k++) hp.X[k] = in.X[k];
+    hp.p[0] = in.prel.x; hp.p[1] = in.prel.y; hp.p[2] = in.prel.z;
+    const float* X = in.X;
+    hp.c[0] = in.prel.x + X[0] * G.center[0] + X[1] * G.center[1] + X[2] * G.center[2];
+    hp.c[1] = in.prel.y + X[3] * G.center[0] + X[4] * G.center[1] + X[5] * G.center[2];
+    hp.c[2] = in.prel.z + X[6] * G.center[0] + X[7] * G.center[1] + X[8] * G.center[2];
+    hp.adr = G.hull_adr; hp.num = G.hull_num;
+  }
+  __syncwarp(omask);
+  int idx = 0;
+#pragma unroll 1
+  for (int i = 0; i < 5; i++)
+#pragma unroll 1
+    for (int j = i + 1; j < 6; j++, idx++) {
+      if (!((cand >> idx) & 1u) || npair >= NM_MAXPAIR) continue;          // (uniform within the octet)
+      float mo[7];
+      if (!mpr_penetration_oct(hull_vert, &pose_s[i], &pose_s[j], mpr_tol, mpr_iter, l, omask, mo)) continue;
+      // ---- contact frame (≙ mju_makeFrame on the MPR direction), rows of body j minus rows of body i
+      PairBlk& P = pblk[npair];
+      const V3 n = normalized(mk(mo[1], mo[2], mo[3]));
+      V3 t1 = (n.y < 0.5f && n.y > -0.5f) ? mk(0.f, 1.f, 0.f) : mk(0.f, 0.f, 1.f);
+      { const float dd = dot_plain(n, t1); t1 = normalized(mk(t1.x - dd * n.x, t1.y - dd * n.y, t1.z - dd * n.z)); }
+      const V3 t2 = cross(n, t1);
+      const V3 frm[3] = {n, t1, t2};
+      const V3 r = mk(mo[4], mo[5], mo[6]) - in.comr;       // contact point relative to the c-frame origin
+      const float sgn = l == i ? -1.f : (l == j ? 1.f : 0.f);
+      V3 colk[3];
+#pragma unroll
+      for (int q = 0; q < 3; q++) colk[q] = sgn * (in.cd[q].v + cross(in.cd[q].w, r));
+      const float mu = G.mu * in.dr_mu;                      // (lanes i and j agree: shared contact parameters)
+      float Y[3][6], Z[3][3], vb[3], as[3], aw[3];
+#pragma unroll 1
+      for (int f = 0; f < 3; f++) {
+        float Jk[3], Jt[6];
+#pragma unroll
+        for (int q = 0; q < 3; q++) Jk[q] = dot(frm[f], colk[q]);
+#pragma unroll
+        for (int a = 0; a < 6; a++) Jt[a] = oct_sum_m(omask, -fmaf(Jk[0], in.E[0][a], fmaf(Jk[1], in.E[1][a], Jk[2] * in.E[2][a])));
+        fwd6(in.S, in.Si, Jt, Y[f]);
+        fwd3(in.g, in.gi, Jk, Z[f]);
+        vb[f] = oct_sum_m(omask, Jk[0] * in.thd[0] + Jk[1] * in.thd[1] + Jk[2] * in.thd[2]);
+        as[f] = oct_sum_m(omask, fmaf(Jk[0], in.xsk[0], fmaf(Jk[1], in.xsk[1], Jk[2] * in.xsk[2])));
+        aw[f] = oct_sum_m(omask, fmaf(Jk[0], in.awk[0], fmaf(Jk[1], in.awk[1], Jk[2] * in.awk[2])));
+      }
+      const float dist = G.margin - mo[0];
+      const float pos = dist - G.margin;
+      const float imp = impedance(G, pos);
+      const float rself = oct_sum_m(omask, (l == i || l == j) ? G.rfac_self * (in.dr_mu * in.dr_mu) * (1.f + mu * mu) / (1.f + G.mu * G.mu) : 0.f);
+      const float R = fmaxf(rself * (1.f - imp) / imp, NM_MINVAL);
+      const float kd = G.K * imp * pos, rinv = 1.f / R;
+      float ey[4][6], ez[4][3];
+#pragma unroll
+      for (int e = 0; e < 4; e++) {
+        const float sg = (e & 1) ? -mu : mu;
+#pragma unroll
+        for (int a = 0; a < 6; a++) ey[e][a] = fmaf(sg, Y[1 + (e >> 1)][a], Y[0][a]);
+#pragma unroll
+        for (int q = 0; q < 3; q++) ez[e][q] = fmaf(sg, Z[1 + (e >> 1)][q], Z[0][q]);
+      }
+      float Gm[10];
+      const int gi_[10] = {0, 1, 2, 3, 0, 2, 0, 0, 1, 1}, gj_[10] = {0, 1, 2, 3, 1, 3, 2, 3, 2, 3};
+#pragma unroll 1
+      for (int k = 0; k < 10; k++) {
+        float t = 0.f;
+        for (int q = 0; q < 3; q++) t = fmaf(ez[gi_[k]][q], ez[gj_[k]][q], t);
+        t = oct_sum_m(omask, t);                           // both legs' parts
+        for (int a = 0; a < 6; a++) t = fmaf(ey[gi_[k]][a], ey[gj_[k]][a], t);
+        Gm[k] = t;
+      }
+      if (l == i || l == j) {
+        float (*Zs)[3] = l == i ? P.Zi : P.Zj;
+#pragma unroll
+        for (int f = 0; f < 3; f++)
+#pragma unroll
+          for (int q = 0; q < 3; q++) Zs[f][q] = Z[f][q];
+      }
+      if (l == i) {                                        // the octet-uniform part is written once, by the lane whose geom parameters apply
+#pragma unroll
+        for (int f = 0; f < 3; f++)
+#pragma unroll
+          for (int a = 0; a < 6; a++) P.Y[f][a] = Y[f][a];
+#pragma unroll
+        for (int k = 0; k < 10; k++) P.G[k] = Gm[k];
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+          const float sg = (e & 1) ? -mu : mu;
+          const int t = 1 + (e >> 1);
+          const float aref = -G.B * fmaf(sg, vb[t], vb[0]) - kd;
+          P.b[e] = fmaf(sg, as[t], as[0]) - aref;
+          P.adi[e] = 1.f / (Gm[e] + R);
+          const float jar = fmaf(sg, aw[t], aw[0]) - aref;
+          P.f[e] = jar < 0.f ? -jar * rinv : 0.f;
+        }
+#pragma unroll
+        for (int t = 0; t < 2; t++) {
+          const float K1 = Gm[2 * t] + Gm[2 * t + 1] - 2.f * Gm[4 + t];
+          P.ik[t] = K1 < NM_MINVAL ? 0.f : 1.f / K1;
+        }
+        P.R = R; P.dist = dist; P.mu = mu;
+        P.pos[0] = mo[4] + in.p.x; P.pos[1] = mo[5] + in.p.y; P.pos[2] = mo[6] + in.p.z;
+        P.nrm[0] = n.x; P.nrm[1] = n.y; P.nrm[2] = n.z;
+        P.li = i; P.lj = j;
+      }
+      npair++;
+    }
+  __syncwarp(omask);
+  return npair;
+}
+
 enum { RW_ACTION_RATE = 0, RW_ANG_VEL_XY, RW_BASE_HEIGHT, RW_BODY_CONTACT_FORCES, RW_COLLISION, RW_DEFAULT_POSITION,
        RW_DOF_ACC, RW_DOF_VEL, RW_FEET_AIR_TIME, RW_FEET_CONTACT_FORCES, RW_FEET_STUMBLE, RW_LIN_VEL_Z, RW_ORIENTATION,
        RW_STAND_STILL, RW_TERMINATION, RW_TORQUES, RW_TRACKING_ANG_VEL, RW_TRACKING_LIN_VEL };
@@ -988,123 +1116,61 @@ __global__ void __launch_bounds__(BLOCK, MINB) nm_step_kernel(const NmKernelArgs
           if (segseg_dist2(ca, cdir, G.cap_il2, oa, od, Go.cap_il2) < thr * thr) cand |= 1u << idx;
         }
       }
-#ifdef NM_PAIRS_BROAD_ONLY
-      if (cand == 0xffffffffu) {
-#else
-      if (__any_sync(FULL, cand != 0u)) {
-#endif
-        cand |= __shfl_xor_sync(FULL, cand, 1); cand |= __shfl_xor_sync(FULL, cand, 2); cand |= __shfl_xor_sync(FULL, cand, 4);
-        if (l < 6) {                                // stage the six hull poses of the environment
-          HullPose& hp = pose_s[l];
-#pragma unroll
-          for (int k = 0; k < 9; k++) hp.X[k] = Xg.a[k];
-          hp.p[0] = prel.x; hp.p[1] = prel.y; hp.p[2] = prel.z;
+      if (__any_sync(FULL, cand != 0u)) {          // cold: at least one of the warp's 4 environments has a candidate pair
+        unsigned oc = cand;
+        oc |= __shfl_xor_sync(FULL, oc, 1); oc |= __shfl_xor_sync(FULL, oc, 2); oc |= __shfl_xor_sync(FULL, oc, 4);
+        // First step of MPR, here and on scalars only: the hulls are disjoint when they are separated along the line between
+        // their centres, h_i(dir) + h_j(-dir) <= 0 with h(d) = max over hull vertices of d.x (1/8 of the vertices per lane).
+        // That is how MPR itself answers almost every candidate (pairs that are close but do not touch), at a third of the
+        // cost of entering the cold path; only the pairs that survive go there.
+        if (oc != 0u) {
           const V3 cw = prel + mul(Xg, ld3(G.center));
-          hp.c[0] = cw.x; hp.c[1] = cw.y; hp.c[2] = cw.z;
-          hp.adr = G.hull_adr; hp.num = G.hull_num;
-        }
-        __syncwarp();
-        const V3 comr = com - p;
-        int idx = 0;
-#pragma unroll 1
-        for (int i = 0; i < 5; i++)
-#pragma unroll 1
-          for (int j = i + 1; j < 6; j++, idx++) {
-            const bool mine = (cand >> idx) & 1u;
-            if (!__any_sync(FULL, mine)) continue;
-            if (!mine || npair >= NM_MAXPAIR) continue;          // (uniform within the octet)
-            float mo[7];
-            if (!mpr_penetration_oct(A.hull_vert, &pose_s[i], &pose_s[j], sm.mpr_tolerance, sm.mpr_iterations, l, omask, mo)) continue;
-            // ---- contact frame (≙ mju_makeFrame on the MPR direction), rows of body j minus rows of body i
-            PairBlk& P = pblk[npair];
-            const V3 n = normalized(mk(mo[1], mo[2], mo[3]));
-            V3 t1 = (n.y < 0.5f && n.y > -0.5f) ? mk(0.f, 1.f, 0.f) : mk(0.f, 0.f, 1.f);
-            { const float dd = dot_plain(n, t1); t1 = normalized(mk(t1.x - dd * n.x, t1.y - dd * n.y, t1.z - dd * n.z)); }
-            const V3 t2 = cross(n, t1);
-            const V3 frm[3] = {n, t1, t2};
-            const V3 r = mk(mo[4], mo[5], mo[6]) - comr;       // contact point relative to the c-frame origin
-            const float sgn = l == i ? -1.f : (l == j ? 1.f : 0.f);
-            V3 colk[3];
+          unsigned rem = oc;
+          oc = 0u;
+          while (rem != 0u) {
+            const int idx = __ffs(rem) - 1;
+            rem &= rem - 1u;
+            int i = 0, base = 0;
+            while (idx >= base + 5 - i) { base += 5 - i; i++; }                // lexicographic (i, j) of the pair
+            const int j = i + 1 + (idx - base);
+            const int si = obase | i, sj = obase | j;
+            const V3 ci = mk(__shfl_sync(omask, cw.x, si), __shfl_sync(omask, cw.y, si), __shfl_sync(omask, cw.z, si));
+            const V3 cj = mk(__shfl_sync(omask, cw.x, sj), __shfl_sync(omask, cw.y, sj), __shfl_sync(omask, cw.z, sj));
+            const V3 dir = normalized(cj - ci);
+            const V3 dloc = mulT(Xg, l == j ? mk(-dir.x, -dir.y, -dir.z) : dir);   // the direction in this lane's hull frame
+            const float off = dot_plain(prel, dir);
+            const V3 di = mk(__shfl_sync(omask, dloc.x, si), __shfl_sync(omask, dloc.y, si), __shfl_sync(omask, dloc.z, si));
+            const V3 dj = mk(__shfl_sync(omask, dloc.x, sj), __shfl_sync(omask, dloc.y, sj), __shfl_sync(omask, dloc.z, sj));
+            const float oi = __shfl_sync(omask, off, si), oj = __shfl_sync(omask, off, sj);
+            const NmGeom &Gi = sm.leg[i].geom, &Gj = sm.leg[j].geom;
+            float hi = -CUDART_INF_F, hj = -CUDART_INF_F;
+            const float4* hvi = A.hull_vert + Gi.hull_adr;
+            const float4* hvj = A.hull_vert + Gj.hull_adr;
+            for (int v = l; v < Gi.hull_num; v += 8) { const float4 q = __ldg(hvi + v); hi = fmaxf(hi, di.x * q.x + di.y * q.y + di.z * q.z); }
+            for (int v = l; v < Gj.hull_num; v += 8) { const float4 q = __ldg(hvj + v); hj = fmaxf(hj, dj.x * q.x + dj.y * q.y + dj.z * q.z); }
 #pragma unroll
-            for (int q = 0; q < 3; q++) colk[q] = sgn * (cd[q].v + cross(cd[q].w, r));
-            const float mu = G.mu * dr_mu;                       // (lanes i and j agree: shared contact parameters)
-            float Y[3][6], Z[3][3], vb[3], as[3], aw[3];
-#pragma unroll
-            for (int f = 0; f < 3; f++) {
-              float Jk[3], Jt[6];
-#pragma unroll
-              for (int q = 0; q < 3; q++) Jk[q] = dot(frm[f], colk[q]);
-#pragma unroll
-              for (int a = 0; a < 6; a++) Jt[a] = oct_sum_m(omask, -fmaf(Jk[0], F.E[0][a], fmaf(Jk[1], F.E[1][a], Jk[2] * F.E[2][a])));
-              fwd6(F.S, F.Si, Jt, Y[f]);
-              fwd3(F.g, F.gi, Jk, Z[f]);
-              vb[f] = oct_sum_m(omask, Jk[0] * thd[0] + Jk[1] * thd[1] + Jk[2] * thd[2]);
-              as[f] = oct_sum_m(omask, fmaf(Jk[0], xsk[0], fmaf(Jk[1], xsk[1], Jk[2] * xsk[2])));
-              aw[f] = oct_sum_m(omask, fmaf(Jk[0], awk[0], fmaf(Jk[1], awk[1], Jk[2] * awk[2])));
-            }
-            const float dist = G.margin - mo[0];
-            const float pos = dist - G.margin;
-            const float imp = impedance(G, pos);
-            const float rself = oct_sum_m(omask, (l == i || l == j) ? G.rfac_self * (dr_mu * dr_mu) * (1.f + mu * mu) / (1.f + G.mu * G.mu) : 0.f);
-            const float R = fmaxf(rself * (1.f - imp) / imp, NM_MINVAL);
-            const float kd = G.K * imp * pos, rinv = 1.f / R;
-            float ey[4][6], ez[4][3];
-#pragma unroll
-            for (int e = 0; e < 4; e++) {
-              const float sg = (e & 1) ? -mu : mu;
-#pragma unroll
-              for (int a = 0; a < 6; a++) ey[e][a] = fmaf(sg, Y[1 + (e >> 1)][a], Y[0][a]);
-#pragma unroll
-              for (int q = 0; q < 3; q++) ez[e][q] = fmaf(sg, Z[1 + (e >> 1)][q], Z[0][q]);
-            }
-            float Gm[10];
-            const int gi_[10] = {0, 1, 2, 3, 0, 2, 0, 0, 1, 1}, gj_[10] = {0, 1, 2, 3, 1, 3, 2, 3, 2, 3};
-#pragma unroll
-            for (int k = 0; k < 10; k++) {
-              float t = 0.f;
-#pragma unroll
-              for (int q = 0; q < 3; q++) t = fmaf(ez[gi_[k]][q], ez[gj_[k]][q], t);
-              t = oct_sum_m(omask, t);                           // both legs' parts
-#pragma unroll
-              for (int a = 0; a < 6; a++) t = fmaf(ey[gi_[k]][a], ey[gj_[k]][a], t);
-              Gm[k] = t;
-            }
-            if (l == i || l == j) {
-              float (*Zs)[3] = l == i ? P.Zi : P.Zj;
-#pragma unroll
-              for (int f = 0; f < 3; f++)
-#pragma unroll
-                for (int q = 0; q < 3; q++) Zs[f][q] = Z[f][q];
-            }
-            if (l == i) {                                        // the octet-uniform part is written once, by the lane whose geom parameters apply
-#pragma unroll
-              for (int f = 0; f < 3; f++)
-#pragma unroll
-                for (int a = 0; a < 6; a++) P.Y[f][a] = Y[f][a];
-#pragma unroll
-              for (int k = 0; k < 10; k++) P.G[k] = Gm[k];
-#pragma unroll
-              for (int e = 0; e < 4; e++) {
-                const float sg = (e & 1) ? -mu : mu;
-                const int t = 1 + (e >> 1);
-                const float aref = -G.B * fmaf(sg, vb[t], vb[0]) - kd;
-                P.b[e] = fmaf(sg, as[t], as[0]) - aref;
-                P.adi[e] = 1.f / (Gm[e] + R);
-                const float jar = fmaf(sg, aw[t], aw[0]) - aref;
-                P.f[e] = jar < 0.f ? -jar * rinv : 0.f;
-              }
-#pragma unroll
-              for (int t = 0; t < 2; t++) {
-                const float K1 = Gm[2 * t] + Gm[2 * t + 1] - 2.f * Gm[4 + t];
-                P.ik[t] = K1 < NM_MINVAL ? 0.f : 1.f / K1;
-              }
-              P.R = R; P.dist = dist; P.mu = mu;
-              P.pos[0] = mo[4] + p.x; P.pos[1] = mo[5] + p.y; P.pos[2] = mo[6] + p.z;
-              P.nrm[0] = n.x; P.nrm[1] = n.y; P.nrm[2] = n.z;
-              P.li = i; P.lj = j;
-            }
-            npair++;
+            for (int o = 1; o < 8; o <<= 1) { hi = fmaxf(hi, __shfl_xor_sync(omask, hi, o)); hj = fmaxf(hj, __shfl_xor_sync(omask, hj, o)); }
+            if ((hi + oi) + (hj - oj) > -1e-6f) oc |= 1u << idx;                // not clearly separated along this axis: full MPR decides
           }
+        }
+        if (oc != 0u) {                             // (uniform within the octet)
+          cand = oc;
+          PairIn in;
+#pragma unroll
+          for (int q = 0; q < 3; q++) {
+#pragma unroll
+            for (int a = 0; a < 6; a++) in.E[q][a] = F.E[q][a];
+            in.cd[q] = cd[q]; in.thd[q] = thd[q]; in.xsk[q] = xsk[q]; in.awk[q] = awk[q]; in.gi[q] = F.gi[q];
+          }
+#pragma unroll
+          for (int a = 0; a < 21; a++) in.S[a] = F.S[a];
+#pragma unroll
+          for (int a = 0; a < 6; a++) { in.Si[a] = F.Si[a]; in.g[a] = F.g[a]; }
+#pragma unroll
+          for (int k = 0; k < 9; k++) in.X[k] = Xg.a[k];
+          in.comr = com - p; in.p = p; in.prel = prel; in.dr_mu = dr_mu;
+          npair = pair_contacts_cold(in, G, A.hull_vert, pose_s, pblk, cand, sm.mpr_tolerance, sm.mpr_iterations, l, omask);
+        }
         __syncwarp();
       }
     }

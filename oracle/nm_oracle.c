@@ -59,7 +59,10 @@ void nmo_flop_reset(void) { memset(g_flops, 0, sizeof(g_flops)); }
 #define TOLPLANEMESH 0.3 /* extra plane-mesh contacts must be this fraction of rbound apart (Appendix A.2) */
 
 enum { JNT_FREE = 0, JNT_BALL = 1, JNT_SLIDE = 2, JNT_HINGE = 3 };
-enum { GEOM_PLANE = 0, GEOM_SPHERE = 2, GEOM_MESH = 7 };
+enum { GEOM_PLANE = 0, GEOM_SPHERE = 2, GEOM_CAPSULE = 3, GEOM_CYLINDER = 5, GEOM_BOX = 6, GEOM_MESH = 7 };
+enum { SOL_PGS = 0, SOL_CG = 1, SOL_NEWTON = 2 };
+enum { CONE_PYRAMIDAL = 0, CONE_ELLIPTIC = 1 };
+enum { EFC_FRICTION = 0, EFC_LIMIT = 1, EFC_CONTACT_PYR = 2, EFC_CONTACT_ELL = 3 };
 enum { INT_EULER = 0, INT_RK4 = 1, INT_IMPLICIT = 2, INT_IMPLICITFAST = 3 };
 
 /* ------------------------------------------------------------------------------------------ model */
@@ -77,7 +80,8 @@ struct nmo_model {
   const int *jnt_type, *jnt_body, *jnt_qposadr, *jnt_dofadr;
   const real *jnt_pos, *jnt_axis;
   const int *dof_body, *dof_jnt, *dof_parent;
-  const real *dof_damping, *dof_armature;
+  const real *dof_damping, *dof_armature, *dof_frictionloss, *dof_invweight0, *jnt_range;
+  const int* jnt_limited;
   const int *act_dof, *act_ctrllimited, *act_forcelimited;
   const real *act_gain, *act_bias, *act_gear, *act_ctrlrange, *act_forcerange;
   const int *geom_type, *geom_body, *geom_condim, *geom_priority, *geom_plane, *geom_hull_adr, *geom_hull_num, *geom_contype, *geom_conaffinity;
@@ -177,6 +181,7 @@ nmo_model* nmo_model_load(const char* path, char* err, int errlen) {
   GETP(jnt_type, int); GETP(jnt_body, int); GETP(jnt_qposadr, int); GETP(jnt_dofadr, int);
   GETR(jnt_pos); GETR(jnt_axis);
   GETP(dof_body, int); GETP(dof_jnt, int); GETP(dof_parent, int); GETR(dof_damping); GETR(dof_armature);
+  GETR(dof_frictionloss); GETR(dof_invweight0); GETR(jnt_range); GETP(jnt_limited, int);
   GETP(act_dof, int); GETP(act_ctrllimited, int); GETP(act_forcelimited, int);
   GETR(act_gain); GETR(act_bias); GETR(act_gear); GETR(act_ctrlrange); GETR(act_forcerange);
   GETP(geom_type, int); GETP(geom_body, int); GETP(geom_condim, int); GETP(geom_priority, int); GETP(geom_plane, int);
@@ -294,6 +299,7 @@ static void cross_force(real* r, const real* vel, const real* f) {
 /* ------------------------------------------------------------------------------------------ per-env data */
 typedef struct {
   real dist, pos[3], frame[9], mu, solref[2], solimp[5], margin;
+  real friction[5];      /* tangent 1, tangent 2, torsional, rolling 1, rolling 2 (elliptic cones, condim up to 6) */
   int geom1, geom2, body1, body2, vert, efc_address, dim;
 } contact_t;
 
@@ -311,13 +317,15 @@ typedef struct {
   int ncon, nefc;
   contact_t con[NMO_MAXCON];
   real *efc_J, *efc_pos, *efc_margin, *efc_diagApprox, *efc_R, *efc_D, *efc_aref, *efc_vel, *efc_b, *efc_force, *efc_AR;
+  real *efc_frictionloss, *efc_jar;
+  int *efc_type, *efc_id;    /* row type (EFC_*) and the dof / joint / contact it belongs to */
   int solver_niter, noslip_niter, warm_used, nwarn;
-  long nmpr;            /* narrow-phase (MPR) calls so far */
+  long nmpr, nmpr_hit, nsupp;   /* narrow-phase (MPR) calls, those that found a contact, support-function evaluations so far */
   real* sensordata;
   real* scratch;   /* >= 8*nv + MAXEFC*nv */
 } data_t;
 
-#define MAXEFC (4 * NMO_MAXCON)
+#define MAXEFC (6 * NMO_MAXCON + 64)
 
 /* env layer carry state (envs/nightmare_v3_env.py:56-97) */
 typedef struct {
@@ -389,8 +397,10 @@ static void data_init(const nmo_model* m, data_t* d) {
   d->efc_diagApprox = dalloc(MAXEFC); d->efc_R = dalloc(MAXEFC); d->efc_D = dalloc(MAXEFC);
   d->efc_aref = dalloc(MAXEFC); d->efc_vel = dalloc(MAXEFC); d->efc_b = dalloc(MAXEFC);
   d->efc_force = dalloc(MAXEFC); d->efc_AR = dalloc((size_t)MAXEFC * MAXEFC);
+  d->efc_frictionloss = dalloc(MAXEFC); d->efc_jar = dalloc(MAXEFC);
+  d->efc_type = (int*)calloc(MAXEFC, sizeof(int)); d->efc_id = (int*)calloc(MAXEFC, sizeof(int));
   d->sensordata = dalloc(m->nsensor);
-  d->scratch = dalloc(16 * nv + (size_t)MAXEFC * nv + 16 * nb);
+  d->scratch = dalloc(16 * nv + (size_t)MAXEFC * nv + 16 * nb + 4 * (size_t)nv * nv + 8 * MAXEFC);
   memcpy(d->qpos, m->qpos0, sizeof(real) * m->nq);
 }
 
@@ -400,8 +410,9 @@ static void data_free(data_t* d) {
                   &d->cvel, &d->cdof_dot, &d->qfrc_bias, &d->qfrc_passive, &d->qfrc_actuator, &d->qfrc_smooth,
                   &d->qacc_smooth, &d->qfrc_constraint, &d->qacc, &d->act_force, &d->efc_J, &d->efc_pos, &d->efc_margin,
                   &d->efc_diagApprox, &d->efc_R, &d->efc_D, &d->efc_aref, &d->efc_vel, &d->efc_b, &d->efc_force,
-                  &d->efc_AR, &d->sensordata, &d->scratch};
+                  &d->efc_AR, &d->sensordata, &d->scratch, &d->efc_frictionloss, &d->efc_jar};
   for (size_t i = 0; i < sizeof(p) / sizeof(p[0]); i++) free(*p[i]);
+  free(d->efc_type); free(d->efc_id);
 }
 
 /* ------------------------------------------------------------------------------------------ P1 kinematics */
@@ -621,6 +632,12 @@ static void make_frame(real* f) {
 static void mix_params(const nmo_model* m, int g1, int g2, contact_t* c) {
   int p1 = m->geom_priority[g1], p2 = m->geom_priority[g2];
   const real *f1 = m->geom_friction + 3 * g1, *f2 = m->geom_friction + 3 * g2;
+  {
+    const real* fw = p1 == p2 ? NULL : (p1 > p2 ? f1 : f2);
+    real fr[3];
+    for (int k = 0; k < 3; k++) fr[k] = fw ? fw[k] : (f1[k] > f2[k] ? f1[k] : f2[k]);
+    c->friction[0] = c->friction[1] = fr[0]; c->friction[2] = fr[1]; c->friction[3] = c->friction[4] = fr[2];
+  }
   if (p1 == p2) {
     c->mu = f1[0] > f2[0] ? f1[0] : f2[0];
     c->dim = m->geom_condim[g1] > m->geom_condim[g2] ? m->geom_condim[g1] : m->geom_condim[g2];
@@ -665,9 +682,11 @@ static inline void ccd_normalize(real* v) { FLOP(9); real n = sqrt(v[0] * v[0] +
 /* support point of a hull in world direction `dir`: hill climb on the hull's vertex graph from vertex 0, the way MuJoCo's
  * mesh support function walks mesh_graph (a local maximum of a linear function on a convex polytope is the global one;
  * neighbours are visited in list order, a neighbour replaces the current best only if strictly better) */
+static long g_nsupp = 0;
 static void hull_support(const hull_t* o, const real* dir, real* out) {
   const real* R = o->R;
   const nmo_model* m = o->m;
+  g_nsupp++;
   real dl[3] = {R[0] * dir[0] + R[3] * dir[1] + R[6] * dir[2], R[1] * dir[0] + R[4] * dir[1] + R[7] * dir[2], R[2] * dir[0] + R[5] * dir[1] + R[8] * dir[2]};
   FLOP(15 + 5 + 18);
   int best = 0;
@@ -965,6 +984,78 @@ static void collision(const nmo_model* m, data_t* d) {
       make_frame(c->frame);
       c->geom1 = pg; c->geom2 = g; c->body1 = pb; c->body2 = b; c->vert = -1;
       mix_params(m, pg, g, c);
+    } else if (m->geom_type[g] == GEOM_BOX || m->geom_type[g] == GEOM_CYLINDER) {
+      /* geom frame in world */
+      real gq[4], gm[9], gc[3], cpos[4][3], cdist[4];
+      int cnt = 0;
+      mul_quat(gq, d->xquat + 4 * b, m->geom_quat + 4 * g);
+      quat2mat(gm, gq);
+      mat_vec3(gc, R, m->geom_pos + 3 * g);
+      for (int k = 0; k < 3; k++) gc[k] += p[k];
+      const real* size = m->geom_size + 3 * g;
+      real dif[3];
+      vsub(dif, gc, ppos);
+      const real dist0 = dot3(dif, n);
+      if (m->geom_type[g] == GEOM_BOX) {
+        /* ≙ mjc_PlaneBox: the corners below the margin that point towards the plane, in corner order, at most 4 */
+        for (int i = 0; i < 8 && cnt < 4; i++) {
+          real vec[3] = {(i & 1) ? size[0] : -size[0], (i & 2) ? size[1] : -size[1], (i & 4) ? size[2] : -size[2]}, corner[3];
+          mat_vec3(corner, gm, vec);
+          const real ldist = dot3(n, corner);
+          if (dist0 + ldist > margin || ldist > 0) continue;
+          cdist[cnt] = dist0 + ldist;
+          for (int k = 0; k < 3; k++) cpos[cnt][k] = corner[k] - n[k] * cdist[cnt] * (real)0.5 + gc[k];
+          FLOP(8);
+          cnt++;
+        }
+      } else {
+        /* ≙ mjc_PlaneCylinder: two points on the rim line nearest the plane, then two more on the near disk */
+        real axis[3] = {gm[2], gm[5], gm[8]}, vec[3];
+        real prjaxis = dot3(n, axis);
+        if (prjaxis > 0) { for (int k = 0; k < 3; k++) axis[k] = -axis[k]; prjaxis = -prjaxis; }
+        for (int k = 0; k < 3; k++) vec[k] = axis[k] * prjaxis - n[k];
+        const real len2 = dot3(vec, vec);
+        if (len2 >= MINVAL * MINVAL) { const real scl = size[0] / sqrt(len2); for (int k = 0; k < 3; k++) vec[k] *= scl; }
+        else { vec[0] = gm[0] * size[0]; vec[1] = gm[3] * size[0]; vec[2] = gm[6] * size[0]; }
+        const real prjvec = dot3(vec, n);
+        for (int k = 0; k < 3; k++) axis[k] *= size[1];
+        prjaxis *= size[1];
+        FLOP(30);
+        if (dist0 + prjaxis + prjvec <= margin) {
+          cdist[cnt] = dist0 + prjaxis + prjvec;
+          for (int k = 0; k < 3; k++) cpos[cnt][k] = gc[k] + vec[k] + axis[k] - n[k] * cdist[cnt] * (real)0.5;
+          cnt++;
+          if (dist0 - prjaxis + prjvec <= margin) {
+            cdist[cnt] = dist0 - prjaxis + prjvec;
+            for (int k = 0; k < 3; k++) cpos[cnt][k] = gc[k] + vec[k] - axis[k] - n[k] * cdist[cnt] * (real)0.5;
+            cnt++;
+          }
+          const real prjvec1 = -prjvec * (real)0.5;
+          if (dist0 + prjaxis + prjvec1 <= margin) {
+            real vec1[3];
+            cross3(vec1, vec, axis);
+            normalize3(vec1);
+            const real sc = size[0] * sqrt((real)3.0) * (real)0.5;
+            for (int k = 0; k < 3; k++) vec1[k] *= sc;
+            for (int sgn = 0; sgn < 2; sgn++) {
+              cdist[cnt] = dist0 + prjaxis + prjvec1;
+              for (int k = 0; k < 3; k++)
+                cpos[cnt][k] = gc[k] + (sgn ? -vec1[k] : vec1[k]) + axis[k] - vec[k] * (real)0.5 - n[k] * cdist[cnt] * (real)0.5;
+              cnt++;
+            }
+            FLOP(40);
+          }
+        }
+      }
+      for (int q = 0; q < cnt && d->ncon < NMO_MAXCON; q++) {
+        contact_t* c = d->con + d->ncon++;
+        c->dist = cdist[q];
+        memcpy(c->pos, cpos[q], 3 * sizeof(real));
+        memcpy(c->frame, n, sizeof(n));
+        make_frame(c->frame);
+        c->geom1 = pg; c->geom2 = g; c->body1 = pb; c->body2 = b; c->vert = q;
+        mix_params(m, pg, g, c);
+      }
     }
   }
   /* convex-convex pairs, after all pairs with the world body: MuJoCo orders contacts by the pair's (body1, body2) signature */
@@ -988,7 +1079,11 @@ static void collision(const nmo_model* m, data_t* d) {
       if (sqrt(dot3(cc, cc)) > margin + m->geom_rbound[g1] + m->geom_rbound[g2]) continue;   /* bounding spheres */
       real depth, dir[3], pos[3];
       d->nmpr++;
-      if (!mpr_penetration(m, &A, &B, &depth, dir, pos) || d->ncon >= NMO_MAXCON) continue;
+      const long s0 = g_nsupp;
+      const int hit = mpr_penetration(m, &A, &B, &depth, dir, pos);
+      d->nsupp += g_nsupp - s0;
+      if (!hit || d->ncon >= NMO_MAXCON) continue;
+      d->nmpr_hit++;
       contact_t* c = d->con + d->ncon++;
       c->dist = margin - depth;
       memcpy(c->pos, pos, sizeof(pos));
@@ -1037,12 +1132,132 @@ static real impedance(const real* solimp, real pos, real margin) {
   return dmin + y * (dmax - dmin);
 }
 
+/* rotational Jacobian of a body (3 x nv): column i = angular part of cdof i for the dofs of the body's chain */
+static void jac_rot(const nmo_model* m, const data_t* d, int body, real* jacr) {
+  int nv = m->nv;
+  memset(jacr, 0, sizeof(real) * 3 * nv);
+  int b = body;
+  while (b > 0 && m->body_dofnum[b] == 0) b = m->body_parent[b];
+  if (b <= 0) return;
+  for (int i = m->body_dofadr[b] + m->body_dofnum[b] - 1; i >= 0; i = m->dof_parent[i])
+    for (int k = 0; k < 3; k++) jacr[k * nv + i] = d->cdof[6 * i + k];
+}
+
+/* stiffness / damping of the reference acceleration from solref (≙ MuJoCo's getsolparam, with the refsafe clamp) */
+static void sol_kb(const nmo_model* m, const real* solref, const real* solimp, real* K, real* B) {
+  real tc = solref[0], dr = solref[1], dmax = solimp[1];
+  if (dmax < 0.0001) dmax = 0.0001; if (dmax > 0.9999) dmax = 0.9999;
+  if (tc > 0) {
+    if (tc < 2 * m->timestep) tc = 2 * m->timestep;
+    *K = 1.0 / (dmax * dmax * tc * tc * dr * dr);
+    *B = 2.0 / (dmax * tc);
+  } else {
+    *K = -tc / (dmax * dmax);
+    *B = -dr / dmax;
+  }
+}
+
+static const real DEF_SOLREF[2] = {0.02, 1.0}, DEF_SOLIMP[5] = {0.9, 0.95, 0.001, 0.5, 2.0};   /* MuJoCo defaults (dof / joint solref, solimp) */
+
 static void make_constraint(const nmo_model* m, data_t* d) {
   STAGE(ST_MAKECON);
   int nv = m->nv;
   d->nefc = 0;
   real* jac1 = d->scratch;            /* 3 x nv */
   real* jac2 = d->scratch + 3 * nv;   /* 3 x nv */
+  /* ---- rows come in MuJoCo's order: dof friction loss, joint limits, contacts (mj_makeConstraint) */
+  for (int i = 0; i < nv; i++) {
+    if (!(m->dof_frictionloss[i] > 0) || d->nefc >= MAXEFC) continue;
+    int e = d->nefc++;
+    memset(d->efc_J + e * nv, 0, sizeof(real) * nv);
+    d->efc_J[e * nv + i] = 1;
+    d->efc_pos[e] = 0; d->efc_margin[e] = 0; d->efc_diagApprox[e] = m->dof_invweight0[i];
+    d->efc_frictionloss[e] = m->dof_frictionloss[i];
+    d->efc_type[e] = EFC_FRICTION; d->efc_id[e] = i;
+  }
+  for (int j = 0; j < m->njnt; j++) {
+    if (!m->jnt_limited[j] || (m->jnt_type[j] != JNT_HINGE && m->jnt_type[j] != JNT_SLIDE)) continue;
+    const real value = d->qpos[m->jnt_qposadr[j]];
+    for (int side = -1; side <= 1; side += 2) {            /* lower limit first, then upper */
+      const real dist = side * (m->jnt_range[2 * j + (side + 1) / 2] - value);
+      if (!(dist < 0) || d->nefc >= MAXEFC) continue;      /* joint margin 0 */
+      int e = d->nefc++;
+      memset(d->efc_J + e * nv, 0, sizeof(real) * nv);
+      d->efc_J[e * nv + m->jnt_dofadr[j]] = -side;
+      d->efc_pos[e] = dist; d->efc_margin[e] = 0; d->efc_diagApprox[e] = m->dof_invweight0[m->jnt_dofadr[j]];
+      d->efc_frictionloss[e] = 0;
+      d->efc_type[e] = EFC_LIMIT; d->efc_id[e] = j;
+    }
+  }
+  for (int e = 0; e < d->nefc; e++) {                      /* impedance, R, reference acceleration of the rows above */
+    real K, B;
+    sol_kb(m, DEF_SOLREF, DEF_SOLIMP, &K, &B);
+    const real imp = impedance(DEF_SOLIMP, d->efc_pos[e], d->efc_margin[e]);
+    real R = (1 - imp) * d->efc_diagApprox[e] / imp;
+    if (R < MINVAL) R = MINVAL;
+    d->efc_R[e] = R; d->efc_D[e] = 1 / R;
+    real vel = 0;
+    for (int i = 0; i < nv; i++) vel += d->efc_J[e * nv + i] * d->qvel[i];
+    d->efc_vel[e] = vel;
+    d->efc_aref[e] = -B * vel - K * imp * (d->efc_pos[e] - d->efc_margin[e]);
+    FLOP(12);
+  }
+  if (m->cone == CONE_ELLIPTIC) {
+    /* ---- elliptic cones: one row per contact dimension (normal, 2 tangents, torsion, 2 rolling), condim 1 / 3 / 4 / 6 */
+    real* jr1 = d->scratch + 6 * nv;
+    real* jr2 = d->scratch + 9 * nv;
+    for (int ci = 0; ci < d->ncon; ci++) {
+      contact_t* c = d->con + ci;
+      c->efc_address = -1;
+      const int dim = c->dim;
+      if ((dim != 1 && dim != 3 && dim != 4 && dim != 6) || d->nefc + dim > MAXEFC) { d->nwarn++; continue; }
+      const int e0 = c->efc_address = d->nefc;
+      jac_point(m, d, c->body1, c->pos, jac1);
+      jac_point(m, d, c->body2, c->pos, jac2);
+      if (dim > 3) { jac_rot(m, d, c->body1, jr1); jac_rot(m, d, c->body2, jr2); }
+      const real tran = m->body_invweight0[2 * c->body1] + m->body_invweight0[2 * c->body2];
+      const real rot = m->body_invweight0[2 * c->body1 + 1] + m->body_invweight0[2 * c->body2 + 1];
+      for (int r = 0; r < dim; r++) {
+        int e = d->nefc++;
+        const real* fr = c->frame + 3 * (r < 3 ? r : r - 3);
+        const real *ja = r < 3 ? jac1 : jr1, *jb = r < 3 ? jac2 : jr2;
+        for (int i = 0; i < nv; i++) {
+          real s2 = 0;
+          for (int k = 0; k < 3; k++) s2 += fr[k] * (jb[k * nv + i] - ja[k * nv + i]);
+          d->efc_J[e * nv + i] = s2;
+        }
+        FLOP(6 * nv);
+        d->efc_pos[e] = r == 0 ? c->dist : 0;
+        d->efc_margin[e] = r == 0 ? c->margin : 0;
+        d->efc_diagApprox[e] = r < 3 ? tran : rot;
+        d->efc_frictionloss[e] = 0;
+        d->efc_type[e] = EFC_CONTACT_ELL; d->efc_id[e] = ci;
+      }
+      real K, B;
+      sol_kb(m, c->solref, c->solimp, &K, &B);
+      const real imp = impedance(c->solimp, c->dist, c->margin);
+      for (int r = 0; r < dim; r++) {
+        int e = e0 + r;
+        real vel = 0;
+        for (int i = 0; i < nv; i++) vel += d->efc_J[e * nv + i] * d->qvel[i];
+        d->efc_vel[e] = vel;
+        d->efc_aref[e] = -B * vel - (r == 0 ? K * imp * (c->dist - c->margin) : 0);   /* friction dimensions have no position term */
+        FLOP(2 * nv + 4);
+      }
+      real R0 = (1 - imp) * tran / imp;
+      if (R0 < MINVAL) R0 = MINVAL;
+      d->efc_R[e0] = R0;
+      if (dim > 1) {
+        /* friction rows: R = R_normal / impratio, scaled so that R_j mu_j^2 is the same for every friction dimension */
+        const real R1 = R0 / (m->impratio > MINVAL ? m->impratio : MINVAL);
+        d->efc_R[e0 + 1] = R1;
+        for (int r = 2; r < dim; r++) d->efc_R[e0 + r] = R1 * c->friction[0] * c->friction[0] / (c->friction[r - 1] * c->friction[r - 1]);
+        c->mu = c->friction[0] * sqrt(R1 / R0);             /* regularised friction coefficient of the cone */
+      }
+      for (int r = 0; r < dim; r++) { if (d->efc_R[e0 + r] < MINVAL) d->efc_R[e0 + r] = MINVAL; d->efc_D[e0 + r] = 1 / d->efc_R[e0 + r]; }
+    }
+    return;
+  }
   for (int ci = 0; ci < d->ncon; ci++) {
     contact_t* c = d->con + ci;
     c->efc_address = -1;
@@ -1067,6 +1282,8 @@ static void make_constraint(const nmo_model* m, data_t* d) {
       d->efc_pos[e] = c->dist;
       d->efc_margin[e] = c->margin;
       d->efc_diagApprox[e] = tran + c->mu * c->mu * tran;
+      d->efc_frictionloss[e] = 0;
+      d->efc_type[e] = EFC_CONTACT_PYR; d->efc_id[e] = ci;
     }
   }
   /* impedance, R, D, reference acceleration */
@@ -1581,7 +1798,7 @@ int nmo_get_array(const nmo_batch* b, int env, const char* name, double* out, in
   if (!strcmp(name, "time")) { if (cap > 0) out[0] = d->time; return 1; }
   if (!strcmp(name, "solver_niter")) { if (cap > 0) out[0] = d->solver_niter; if (cap > 1) out[1] = d->noslip_niter; if (cap > 2) out[2] = d->warm_used; return 3; }
   if (!strcmp(name, "nwarn")) { if (cap > 0) out[0] = d->nwarn; return 1; }
-  if (!strcmp(name, "nmpr")) { if (cap > 0) out[0] = (double)d->nmpr; return 1; }
+  if (!strcmp(name, "nmpr")) { if (cap > 0) out[0] = (double)d->nmpr; if (cap > 1) out[1] = (double)d->nmpr_hit; if (cap > 2) out[2] = (double)d->nsupp; return 3; }
   if (!strcmp(name, "contact_frame")) {   /* per contact: normal(3) */
     for (int c = 0; c < d->ncon && 3 * c + 2 < cap; c++) { out[3 * c] = d->con[c].frame[0]; out[3 * c + 1] = d->con[c].frame[1]; out[3 * c + 2] = d->con[c].frame[2]; }
     return d->ncon * 3;
