@@ -1116,7 +1116,12 @@ __global__ void __launch_bounds__(BLOCK, MINB) nm_step_kernel(const NmKernelArgs
           if (segseg_dist2(ca, cdir, G.cap_il2, oa, od, Go.cap_il2) < thr * thr) cand |= 1u << idx;
         }
       }
-      if (__any_sync(FULL, cand != 0u)) {          // cold: at least one of the warp's 4 environments has a candidate pair
+#ifdef NM_PAIRS_E3
+      if (A.debug != nullptr && cand != 0u) A.debug[(size_t)env * NM_DBG + 5] = __uint_as_float(cand);   // experiment: broad phase kept alive, nothing else
+      if (false) {
+#else
+      if (__builtin_expect(__any_sync(FULL, cand != 0u), 0)) {          // cold: at least one of the warp's 4 environments has a candidate pair
+#endif
         unsigned oc = cand;
         oc |= __shfl_xor_sync(FULL, oc, 1); oc |= __shfl_xor_sync(FULL, oc, 2); oc |= __shfl_xor_sync(FULL, oc, 4);
         // First step of MPR, here and on scalars only: the hulls are disjoint when they are separated along the line between
@@ -1323,6 +1328,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) nm_step_kernel(const NmKernelArgs
         const float hR = 0.5f * cb.R[c];
         cl += f0 * fmaf(hR, f0, cb.b[c][0]) + f1 * fmaf(hR, f1, cb.b[c][1]) + f2 * fmaf(hR, f2, cb.b[c][2]) + f3 * fmaf(hR, f3, cb.b[c][3]);
       }
+      if (__builtin_expect(npair_max > 0, 0))
       for (int pi = 0; pi < npair; pi++) {                    // pair contacts: Y and the cost terms enter once (lane li), Z on both legs
         const PairBlk& P = pblk[pi];
         const float f0 = P.f[0], f1 = P.f[1], f2 = P.f[2], f3 = P.f[3];
@@ -1348,6 +1354,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) nm_step_kernel(const NmKernelArgs
         for (int c = 0; c < nc; c++)
 #pragma unroll
           for (int rr = 0; rr < 4; rr++) cb.f[c][rr] = 0.f;
+        if (__builtin_expect(npair_max > 0, 0))
         for (int pi = 0; pi < npair; pi++)
           if (l == pblk[pi].li) { pblk[pi].f[0] = 0.f; pblk[pi].f[1] = 0.f; pblk[pi].f[2] = 0.f; pblk[pi].f[3] = 0.f; }
 #pragma unroll
@@ -1355,7 +1362,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) nm_step_kernel(const NmKernelArgs
 #pragma unroll
         for (int j = 0; j < 3; j++) wv[j] = 0.f;
       } else dbg_warm = ncon_env > 0 ? 1 : 0;
-      if (npair_max > 0) __syncwarp();
+      if (__builtin_expect(npair_max > 0, 0)) __syncwarp();
 
       // ---- sweeps: rows in contact order (base geom first, then legs 1..6), Gauss-Seidel through u.
       // sweep 0..iterations-1: PGS on single edges (with R); then noslip on opposing edge pairs (without R, sum fixed).
@@ -1412,6 +1419,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) nm_step_kernel(const NmKernelArgs
         // pair contacts: rows after all plane contacts (MuJoCo orders contacts by body pair; the world body's pairs come first).
         // All eight lanes run the visit on identical (shared-memory) data, so u stays replicated without a broadcast; the
         // two legs' Z.w enter through one octet sum, and each of the two lanes applies its own Z to its w.
+        if (__builtin_expect(npair_max > 0, 0))
         for (int pi = 0; pi < npair_max; pi++) {
           if (active && pi < npair) {
             PairBlk& P = pblk[pi];
@@ -1472,6 +1480,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) nm_step_kernel(const NmKernelArgs
         if (L.site_r[0] >= 0.f && ray_sphere(pg + mul(Xg, ld3(L.site_pos[0])), L.site_r[0], cb.pos[c], ray) >= 0.f) fn_slot0 += fn;
         if (L.site_r[1] >= 0.f && ray_sphere(pg + mul(Xg, ld3(L.site_pos[1])), L.site_r[1], cb.pos[c], ray) >= 0.f) fn_slot1 += fn;
       }
+      if (__builtin_expect(npair_max > 0, 0))
       for (int pi = 0; pi < npair; pi++) {                   // pair contacts load both legs' sensors (ray along +-normal)
         const PairBlk& P = pblk[pi];
         if (l != P.li && l != P.lj) continue;

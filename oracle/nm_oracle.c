@@ -1451,6 +1451,216 @@ static void dual_finish(const nmo_model* m, data_t* d) {
   FLOP(nv);
 }
 
+/* ------------------------------------------------------------------------------------------ P9b Newton solver (primal)
+ * MuJoCo's default solver (models/anymal_c/anymal_c.xml leaves `solver` at Newton, :4 selects elliptic cones): minimise
+ *     cost(qacc) = 1/2 (qacc - qacc_smooth)' M (qacc - qacc_smooth) + sum_i s_i(J qacc - aref)
+ * a convex function with a unique minimiser.  s_i by row type (MuJoCo's constraint update):
+ *   friction loss : quadratic 1/2 D jar^2 inside |jar| < R*floss, linear (force = -+floss) outside;
+ *   limit / frictionless row : 1/2 D jar^2 for jar < 0, else 0;
+ *   elliptic contact (dim rows): with N = mu*jar_0, T = |friction_j * jar_j|: 0 in the top zone (N >= mu T), 1/2 sum D_j jar_j^2
+ *     in the bottom zone (mu N + T <= 0), 1/2 Dm (N - mu T)^2 with Dm = D_0 / (mu^2 (1 + mu^2)) in between.
+ * MuJoCo iterates Newton steps with an approximate line search until the scaled improvement or gradient drops below
+ * opt.tolerance (1e-8); this restatement uses exact Newton steps with an exact line search and iterates to the minimiser itself,
+ * i.e. MuJoCo's result is reproduced up to ITS solver tolerance (parity is stated to that tolerance). */
+static real newton_rows(const nmo_model* m, data_t* d, const real* jar, real* force, real* Hd, real* Hcone /* ncon x 36 */, int* cone_on) {
+  real cost = 0;
+  const int ne = d->nefc;
+  if (Hd) for (int e = 0; e < ne; e++) Hd[e] = 0;
+  for (int e = 0; e < ne; e++) {
+    const real D = d->efc_D[e], R = d->efc_R[e];
+    switch (d->efc_type[e]) {
+      case EFC_FRICTION: {
+        const real fl = d->efc_frictionloss[e], bound = R * fl;
+        if (jar[e] <= -bound) { force[e] = fl; cost += -(real)0.5 * R * fl * fl - fl * jar[e]; }
+        else if (jar[e] >= bound) { force[e] = -fl; cost += -(real)0.5 * R * fl * fl + fl * jar[e]; }
+        else { force[e] = -D * jar[e]; cost += (real)0.5 * D * jar[e] * jar[e]; if (Hd) Hd[e] = D; }
+        FLOP(8);
+        break;
+      }
+      case EFC_LIMIT:
+      case EFC_CONTACT_PYR:
+        if (jar[e] < 0) { force[e] = -D * jar[e]; cost += (real)0.5 * D * jar[e] * jar[e]; if (Hd) Hd[e] = D; }
+        else force[e] = 0;
+        FLOP(4);
+        break;
+      case EFC_CONTACT_ELL: {
+        const int ci = d->efc_id[e];
+        const contact_t* c = d->con + ci;
+        if (c->efc_address != e) break;                       /* handled at the contact's first row */
+        const int dim = c->dim;
+        const real mu = c->mu;
+        real U[6];
+        U[0] = jar[e] * mu;
+        real T2 = 0;
+        for (int j = 1; j < dim; j++) { U[j] = jar[e + j] * c->friction[j - 1]; T2 += U[j] * U[j]; }
+        const real N = U[0], T = sqrt(T2);
+        if (cone_on) cone_on[ci] = 0;
+        FLOP(6 * dim);
+        if (dim == 1) {                                       /* frictionless contact */
+          if (jar[e] < 0) { force[e] = -D * jar[e]; cost += (real)0.5 * D * jar[e] * jar[e]; if (Hd) Hd[e] = D; } else force[e] = 0;
+        } else if (N >= mu * T || (T <= 0 && N >= 0)) {       /* top zone: satisfied */
+          for (int j = 0; j < dim; j++) force[e + j] = 0;
+        } else if (mu * N + T <= 0 || (T <= 0 && N < 0)) {    /* bottom zone: quadratic in every dimension */
+          for (int j = 0; j < dim; j++) {
+            force[e + j] = -d->efc_D[e + j] * jar[e + j];
+            cost += (real)0.5 * d->efc_D[e + j] * jar[e + j] * jar[e + j];
+            if (Hd) Hd[e + j] = d->efc_D[e + j];
+          }
+        } else {                                              /* middle zone: on the cone */
+          const real Dm = D / (mu * mu * (1 + mu * mu)), NmT = N - mu * T;
+          cost += (real)0.5 * Dm * NmT * NmT;
+          force[e] = -Dm * NmT * mu;
+          for (int j = 1; j < dim; j++) force[e + j] = -force[e] / T * U[j] * c->friction[j - 1];
+          if (Hcone) {
+            /* Hessian of 1/2 Dm (N - mu T)^2 in jar: Dm (g g' - mu (N - mu T) d2T),  g = (mu, -mu f_j U_j / T),
+             * d2T_jk = f_j f_k (delta_jk - U_j U_k / T^2) / T */
+            real g[6];
+            g[0] = mu;
+            for (int j = 1; j < dim; j++) g[j] = -mu * c->friction[j - 1] * U[j] / T;
+            real* H = Hcone + 36 * ci;
+            for (int a = 0; a < dim; a++)
+              for (int b = 0; b < dim; b++) {
+                real h = g[a] * g[b];
+                if (a > 0 && b > 0)
+                  h += -mu * NmT * c->friction[a - 1] * c->friction[b - 1] * ((a == b ? 1 : 0) - U[a] * U[b] / T2) / T;
+                H[6 * a + b] = Dm * h;
+              }
+            cone_on[ci] = 1;
+            FLOP(12 * dim * dim);
+          }
+        }
+        break;
+      }
+    }
+  }
+  return cost;
+}
+
+static void solve_newton(const nmo_model* m, data_t* d) {
+  const int nv = m->nv, ne = d->nefc;
+  real* work = d->scratch + 16 * nv + (size_t)MAXEFC * nv + 16 * m->nbody;      /* 4 nv^2 + 8 MAXEFC reals */
+  real *H = work, *LH = work + nv * nv, *tmpM = work + 2 * nv * nv;
+  real *jar = work + 4 * nv * nv, *jv = jar + MAXEFC, *Hd = jv + MAXEFC, *force = d->efc_force;
+  real Hcone[NMO_MAXCON * 36];
+  int cone_on[NMO_MAXCON];
+  real qacc[64], grad[64], dir[64], dq[64], Ma[64], Md[64];
+  (void)tmpM;
+  const real scale = 1.0 / (m->meaninertia * (nv > 1 ? nv : 1));
+  /* cost of a candidate start */
+  #define TOTAL_COST(q_, out_)                                                                            \
+    do {                                                                                                  \
+      real c_ = 0;                                                                                        \
+      for (int i_ = 0; i_ < nv; i_++) dq[i_] = (q_)[i_] - d->qacc_smooth[i_];                             \
+      for (int i_ = 0; i_ < nv; i_++) { real s_ = 0; for (int k_ = 0; k_ < nv; k_++) s_ += d->M[i_ * nv + k_] * dq[k_]; c_ += (real)0.5 * dq[i_] * s_; } \
+      for (int e_ = 0; e_ < ne; e_++) { real s_ = -d->efc_aref[e_]; for (int i_ = 0; i_ < nv; i_++) s_ += d->efc_J[e_ * nv + i_] * (q_)[i_]; jar[e_] = s_; } \
+      c_ += newton_rows(m, d, jar, force, NULL, NULL, NULL);                                              \
+      (out_) = c_;                                                                                        \
+    } while (0)
+  STAGE(ST_WARMSTART);
+  real cw, cs;
+  TOTAL_COST(d->qacc_warmstart, cw);
+  TOTAL_COST(d->qacc_smooth, cs);
+  FLOP(2 * (2 * nv * nv + 2 * ne * nv));
+  if (cw < cs) { memcpy(qacc, d->qacc_warmstart, sizeof(real) * nv); d->warm_used = 1; }
+  else memcpy(qacc, d->qacc_smooth, sizeof(real) * nv);
+  STAGE(ST_PGS);
+  for (int it = 0; it < m->iterations; it++) {
+    /* gradient and Hessian at qacc */
+    for (int i = 0; i < nv; i++) dq[i] = qacc[i] - d->qacc_smooth[i];
+    for (int i = 0; i < nv; i++) { real s2 = 0; for (int k = 0; k < nv; k++) s2 += d->M[i * nv + k] * dq[k]; Ma[i] = s2; }
+    for (int e = 0; e < ne; e++) { real s2 = -d->efc_aref[e]; for (int i = 0; i < nv; i++) s2 += d->efc_J[e * nv + i] * qacc[i]; jar[e] = s2; }
+    newton_rows(m, d, jar, force, Hd, Hcone, cone_on);
+    real gn = 0;
+    for (int i = 0; i < nv; i++) {
+      real s2 = Ma[i];
+      for (int e = 0; e < ne; e++) s2 -= d->efc_J[e * nv + i] * force[e];
+      grad[i] = s2; gn += s2 * s2;
+    }
+    FLOP(2 * nv * nv + 4 * ne * nv);
+    d->solver_niter = it;
+    if (getenv("NMO_NEWTON_TRACE")) fprintf(stderr, "it %d scaled grad %.3e\n", it, (double)(scale * sqrt(gn)));
+    if (scale * sqrt(gn) < m->tolerance * (real)1e-3) break;            /* converged far below MuJoCo's own tolerance */
+    memcpy(H, d->M, sizeof(real) * nv * nv);
+    for (int e = 0; e < ne; e++) {
+      if (Hd[e] == 0) continue;
+      const real* J = d->efc_J + e * nv;
+      for (int i = 0; i < nv; i++) { if (J[i] == 0) continue; const real t = Hd[e] * J[i]; for (int k = 0; k < nv; k++) H[i * nv + k] += t * J[k]; }
+      FLOP(2 * nv * nv);
+    }
+    for (int ci = 0; ci < d->ncon; ci++) {
+      const contact_t* c = d->con + ci;
+      if (c->efc_address < 0 || d->efc_type[c->efc_address] != EFC_CONTACT_ELL || !cone_on[ci]) continue;
+      const real* Jc = d->efc_J + c->efc_address * nv;
+      for (int a = 0; a < c->dim; a++)
+        for (int b = 0; b < c->dim; b++) {
+          const real h = Hcone[36 * ci + 6 * a + b];
+          if (h == 0) continue;
+          for (int i = 0; i < nv; i++) { const real t = h * Jc[a * nv + i]; if (t == 0) continue; for (int k = 0; k < nv; k++) H[i * nv + k] += t * Jc[b * nv + k]; }
+        }
+      FLOP(2 * c->dim * c->dim * nv * nv);
+    }
+    if (cholesky(LH, H, nv) != 0) { d->nwarn++; break; }
+    for (int i = 0; i < nv; i++) dir[i] = -grad[i];
+    chol_solve(LH, nv, dir);
+    /* exact line search: phi'(alpha) = dir' M (dq + alpha dir) - sum force_e(jar + alpha jv) jv_e is increasing in alpha */
+    for (int e = 0; e < ne; e++) { real s2 = 0; for (int i = 0; i < nv; i++) s2 += d->efc_J[e * nv + i] * dir[i]; jv[e] = s2; }
+    real a1 = 0, a2 = 0;
+    for (int i = 0; i < nv; i++) { real s2 = 0; for (int k = 0; k < nv; k++) s2 += d->M[i * nv + k] * dir[k]; Md[i] = s2; a1 += dir[i] * Ma[i]; a2 += dir[i] * s2; }
+    FLOP(2 * ne * nv + 2 * nv * nv);
+    real* jt = Hd;                                                        /* reuse: trial jar */
+    #define DPHI(alpha_, out_)                                                                            \
+      do {                                                                                                \
+        for (int e_ = 0; e_ < ne; e_++) jt[e_] = jar[e_] + (alpha_) * jv[e_];                            \
+        newton_rows(m, d, jt, force, NULL, NULL, NULL);                                                   \
+        real s_ = a1 + (alpha_) * a2;                                                                     \
+        for (int e_ = 0; e_ < ne; e_++) s_ -= force[e_] * jv[e_];                                         \
+        (out_) = s_;                                                                                      \
+      } while (0)
+    real lo = 0, hi = 1, flo, fhi, alpha = 1;
+    DPHI(0, flo);
+    if (!(flo < 0)) break;                                                /* no descent left: at the minimum to rounding */
+    DPHI(hi, fhi);
+    int guard = 0;
+    while (fhi < 0 && guard++ < 40) { lo = hi; flo = fhi; hi *= 2; DPHI(hi, fhi); }
+    if (fhi < 0) alpha = hi;
+    else {
+      /* regula falsi with the Illinois modification on the bracket [lo, hi] */
+      int side = 0;
+      alpha = hi;
+      for (int k = 0; k < 60; k++) {
+        alpha = (lo * fhi - hi * flo) / (fhi - flo);
+        if (!(alpha > lo && alpha < hi)) alpha = (real)0.5 * (lo + hi);
+        real fa;
+        DPHI(alpha, fa);
+        if (fabs(fa) <= (real)1e-13 * fabs(a1) || hi - lo <= (real)1e-15 * hi) break;
+        if (fa < 0) { lo = alpha; flo = fa; if (side == -1) fhi *= (real)0.5; side = -1; }
+        else { hi = alpha; fhi = fa; if (side == 1) flo *= (real)0.5; side = 1; }
+      }
+    }
+    if (getenv("NMO_NEWTON_TRACE")) {
+      fprintf(stderr, "   alpha %.4e lo %.3e hi %.3e a1 %.3e zones:", (double)alpha, (double)lo, (double)hi, (double)a1);
+      for (int ci = 0; ci < d->ncon; ci++) fprintf(stderr, " %d", cone_on[ci]);
+      int nq = 0; for (int e = 0; e < ne; e++) if (d->efc_type[e] == EFC_FRICTION && fabs(jar[e]) < d->efc_R[e] * d->efc_frictionloss[e]) nq++;
+      fprintf(stderr, " fl-quadratic %d\n", nq);
+    }
+    for (int i = 0; i < nv; i++) qacc[i] += alpha * dir[i];
+    #undef DPHI
+  }
+  #undef TOTAL_COST
+  /* forces and accelerations at the solution */
+  STAGE(ST_FINISH);
+  for (int e = 0; e < ne; e++) { real s2 = -d->efc_aref[e]; for (int i = 0; i < nv; i++) s2 += d->efc_J[e * nv + i] * qacc[i]; jar[e] = s2; d->efc_jar[e] = s2; }
+  newton_rows(m, d, jar, force, NULL, NULL, NULL);
+  for (int i = 0; i < nv; i++) {
+    real s2 = 0;
+    for (int e = 0; e < ne; e++) s2 += d->efc_J[e * nv + i] * force[e];
+    d->qfrc_constraint[i] = s2;
+    d->qacc[i] = qacc[i];
+  }
+  FLOP(4 * ne * nv);
+  memcpy(d->qacc_warmstart, d->qacc, sizeof(real) * nv);
+}
+
 static void fwd_constraint(const nmo_model* m, data_t* d) {
   int nv = m->nv, ne = d->nefc;
   d->solver_niter = d->noslip_niter = 0;
@@ -1461,6 +1671,7 @@ static void fwd_constraint(const nmo_model* m, data_t* d) {
     memset(d->qfrc_constraint, 0, sizeof(real) * nv);
     return;
   }
+  if (m->solver == SOL_NEWTON) { solve_newton(m, d); return; }
   const real* AR = d->efc_AR;
   real* f = d->efc_force;
   STAGE(ST_WARMSTART);
@@ -1573,7 +1784,8 @@ static void sensor_touch(const nmo_model* m, data_t* d) {
       const contact_t* c = d->con + ci;
       if (c->efc_address < 0 || (c->body1 != body && c->body2 != body)) continue;
       real fn = 0;
-      for (int r = 0; r < 4; r++) fn += d->efc_force[c->efc_address + r];
+      if (d->efc_type[c->efc_address] == EFC_CONTACT_ELL) fn = d->efc_force[c->efc_address];     /* elliptic: the normal row */
+      else for (int r = 0; r < 4; r++) fn += d->efc_force[c->efc_address + r];
       if (fn <= 0) continue;
       FLOP(3 + 3 + 25);
       real ray[3] = {c->frame[0] * fn, c->frame[1] * fn, c->frame[2] * fn};
@@ -1592,7 +1804,7 @@ static void forward(const nmo_model* m, data_t* d) {
   crb(m, d);
   collision(m, d);
   make_constraint(m, d);
-  project_constraint(m, d);
+  if (m->solver != SOL_NEWTON) project_constraint(m, d);     /* the dual solvers need A = J M^-1 J' + R; Newton works on J itself */
   fwd_velocity_actuation_acceleration(m, d);
   fwd_constraint(m, d);
   sensor_touch(m, d);
