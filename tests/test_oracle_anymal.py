@@ -140,4 +140,4 @@ def test_fp32_build_agrees_on_one_step(cm):
         errs.append((np.abs(va2 - vf2).max(axis=1) / np.maximum(np.abs(va2).max(axis=1), 1e-3))[same])
     e = np.concatenate(errs)
     print(f"\n[anymal f32 vs f64] one-step qvel rel: median {np.median(e):.2e} p99 {np.percentile(e, 99):.2e} max {e.max():.2e} over {e.size} env-substeps")
-    assert np.median(e) < 1e-5 and np.percentile(e, 90) < 1e-4 and np.percentile(e, 99) < 1e-2      # elliptic cones at impratio 100 are stiff: a heavy tail
+    assert np.median(e) < 1e-5 and np.percentile(e, 90) < 5e-4 and np.percentile(e, 99) < 1e-2      # elliptic cones at impratio 100 are stiff: a heavy tail
