@@ -247,6 +247,35 @@ int  nm_ppo_adam(const nm_ppo_adam_args* args, nm_stream stream);
 int  nm_gae(int T, int n, const float* rewards, const uint8_t* dones, const float* values, const float* last_values, float gamma,
             float lam, float* returns, float* advantages, double* moments, nm_stream stream);
 
+/* ---------------------------------------------------------------------------------------------------------------------
+ * Second model family of the reference: models/anymal_c (BASELINE configs[3]) -- MuJoCo's Newton solver with elliptic
+ * cones (anymal_c.xml:4), joint damping + friction loss (:9), condim-6 feet with priority (:20-21), position actuators with
+ * a force range (:26), joint limits, box / cylinder / sphere geoms against the plane, Euler with implicit joint damping.
+ * Same call sites as above (mj.MjModel.from_xml_path, mj.mj_step: envs/nightmare_v3_env.py:37,200; simple_test.py:39).
+ * Scope: a free-floating base plus hinge joints, collisions with ONE static plane (the model's geom-geom self collisions
+ * are not generated).  Models with solver="PGS" go through nm_model_* / nm_step above; each loader names the other one
+ * in its error message. */
+typedef struct nm_gen_model nm_gen_model;
+typedef struct nm_gen_batch nm_gen_batch;
+/* ≙ mj.MjModel.from_xml_path (compiled .nmb buffer, see nm_model_from_buffer) */
+int  nm_gen_model_from_buffer(const void* data, size_t nbytes, nm_gen_model** out);
+void nm_gen_model_destroy(nm_gen_model*);
+/* ≙ model.nq / nv / nu / nbody; "ngeom" = collision geoms kept (plane excluded) */
+int  nm_gen_model_size(const nm_gen_model*, const char* what);
+/* ≙ model.opt.timestep */
+double nm_gen_model_timestep(const nm_gen_model*);
+/* ≙ model.qpos0 */
+int  nm_gen_model_qpos0(const nm_gen_model*, float* out, int cap);
+/* ≙ [mj.MjData(model) for _ in range(num_envs)]: state in caller-owned DEVICE float32 buffers qpos [N,nq], qvel [N,nv],
+ * warm [N,nv] (qacc_warmstart); info: DEVICE int32 [N,4] = {ncon, nefc, Newton iterations, overflow flag} of the last
+ * substep, or NULL. */
+int  nm_gen_batch_create(const nm_gen_model*, int num_envs, int device, float* qpos, float* qvel, float* warm, int32_t* info,
+                         nm_gen_batch** out);
+void nm_gen_batch_destroy(nm_gen_batch*);
+/* ≙ for i: data[i].ctrl = ctrl[i]; mj.mj_step(model, data[i], nstep)      ctrl: DEVICE float32 [N,nu] */
+int  nm_gen_physics_step(nm_gen_batch*, const float* ctrl, int nstep, nm_stream stream);
+int64_t nm_gen_batch_launches(const nm_gen_batch*);
+
 /* number of kernel launches issued by this batch so far (bench.py "gpu_launches") */
 int64_t nm_batch_launches(const nm_batch*);
 

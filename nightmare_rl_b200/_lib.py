@@ -71,6 +71,17 @@ def _load() -> ctypes.CDLL:
     L.nm_policy_tc5_destroy.argtypes = [_vp]
     L.nm_policy_tc5_load_weights.argtypes = [_vp, _vp, _vp, _vp, _vp]
     L.nm_policy_tc5_act.argtypes = [_vp, _vp, _ci, _ci, ctypes.c_uint64, _i64, _i64, _ci, _vp, _vp, _vp, _vp, _vp, _vp, _vp]
+    L.nm_gen_model_from_buffer.argtypes = [_vp, ctypes.c_size_t, ctypes.POINTER(_vp)]
+    L.nm_gen_model_destroy.argtypes = [_vp]
+    L.nm_gen_model_size.argtypes = [_vp, ctypes.c_char_p]
+    L.nm_gen_model_timestep.argtypes = [_vp]
+    L.nm_gen_model_timestep.restype = ctypes.c_double
+    L.nm_gen_model_qpos0.argtypes = [_vp, _vp, _ci]
+    L.nm_gen_batch_create.argtypes = [_vp, _ci, _ci, _vp, _vp, _vp, _vp, ctypes.POINTER(_vp)]
+    L.nm_gen_batch_destroy.argtypes = [_vp]
+    L.nm_gen_physics_step.argtypes = [_vp, _vp, _ci, _vp]
+    L.nm_gen_batch_launches.argtypes = [_vp]
+    L.nm_gen_batch_launches.restype = _i64
     return L
 
 
@@ -82,7 +93,9 @@ EXPORTS = ("nm_last_error", "nm_model_load", "nm_model_from_buffer", "nm_model_d
            "nm_physics_step", "nm_reset_idx", "nm_step_host", "nm_batch_launches", "nm_measure_fp32_peak",
            "nm_policy_create", "nm_policy_destroy", "nm_policy_param_count", "nm_policy_load_weights", "nm_policy_act",
            "nm_policy_act_store", "nm_policy_launches", "nm_rollout_store", "nm_ppo_head", "nm_ppo_grad", "nm_gae", "nm_ppo_adam",
-           "nm_policy_tc5_create", "nm_policy_tc5_destroy", "nm_policy_tc5_load_weights", "nm_policy_tc5_act")
+           "nm_policy_tc5_create", "nm_policy_tc5_destroy", "nm_policy_tc5_load_weights", "nm_policy_tc5_act",
+           "nm_gen_model_from_buffer", "nm_gen_model_destroy", "nm_gen_model_size", "nm_gen_model_timestep", "nm_gen_model_qpos0",
+           "nm_gen_batch_create", "nm_gen_batch_destroy", "nm_gen_physics_step", "nm_gen_batch_launches")
 
 
 def check(rc: int) -> None:
@@ -116,4 +129,30 @@ class Model:
     def __del__(self):
         if getattr(self, "_h", None) and lib is not None:
             lib.nm_model_destroy(self._h)
+            self._h = None
+
+
+class GenModel:
+    """Device-ready compiled model for the Newton / elliptic-cone path (≙ ``mj.MjModel`` of models/anymal_c)."""
+
+    def __init__(self, nmb_bytes: bytes):
+        self._h = _vp()
+        buf = ctypes.create_string_buffer(nmb_bytes, len(nmb_bytes))
+        check(lib.nm_gen_model_from_buffer(buf, len(nmb_bytes), ctypes.byref(self._h)))
+
+    def size(self, what: str) -> int:
+        return lib.nm_gen_model_size(self._h, what.encode())
+
+    @property
+    def timestep(self) -> float:
+        return lib.nm_gen_model_timestep(self._h)
+
+    def qpos0(self):
+        out = (ctypes.c_float * 64)()
+        n = lib.nm_gen_model_qpos0(self._h, out, 64)
+        return list(out[:n])
+
+    def __del__(self):
+        if getattr(self, "_h", None) and lib is not None:
+            lib.nm_gen_model_destroy(self._h)
             self._h = None

@@ -111,3 +111,39 @@ class Batch:
         if getattr(self, "_h", None) and _lib is not None and getattr(_lib, "lib", None) is not None:
             _lib.lib.nm_batch_destroy(self._h)
             self._h = None
+
+
+class GenBatch:
+    """≙ ``[mj.MjData(model) for _ in range(num_envs)]`` for a model on the Newton / elliptic-cone path (models/anymal_c of the
+    reference, BASELINE configs[3]); ``physics_step`` ≙ ``mj.mj_step(model, data[i], nstep)`` for every environment."""
+
+    def __init__(self, model: _lib.GenModel, num_envs: int, device: torch.device):
+        if device.type != "cuda":
+            raise _lib.NightmareLibError("the physics step only runs on CUDA devices (no CPU fallback)")
+        self.model, self.n, self.device = model, num_envs, device
+        self.nq, self.nv, self.nu = model.size("nq"), model.size("nv"), model.size("nu")
+        f32 = dict(dtype=torch.float32, device=device)
+        self.qpos = torch.tensor(model.qpos0(), **f32).repeat(num_envs, 1).contiguous()
+        self.qvel, self.warm = torch.zeros(num_envs, self.nv, **f32), torch.zeros(num_envs, self.nv, **f32)
+        self.info = torch.zeros(num_envs, 4, dtype=torch.int32, device=device)
+        self._h = ctypes.c_void_p()
+        with torch.cuda.device(device):
+            _lib.check(_lib.lib.nm_gen_batch_create(model._h, num_envs, device.index or 0, self.qpos.data_ptr(), self.qvel.data_ptr(),
+                                                    self.warm.data_ptr(), self.info.data_ptr(), ctypes.byref(self._h)))
+
+    def physics_step(self, ctrl: torch.Tensor, nstep: int = 1) -> None:
+        ctrl = ctrl.to(device=self.device, dtype=torch.float32).contiguous()
+        if ctrl.shape != (self.n, self.nu):
+            raise ValueError(f"ctrl must be [num_envs, {self.nu}]")
+        _lib.check(_lib.lib.nm_gen_physics_step(self._h, ctrl.data_ptr(), nstep,
+                                                ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)))
+        self._keep = ctrl
+
+    @property
+    def launches(self) -> int:
+        return int(_lib.lib.nm_gen_batch_launches(self._h))
+
+    def __del__(self):
+        if getattr(self, "_h", None) and _lib is not None and getattr(_lib, "lib", None) is not None:
+            _lib.lib.nm_gen_batch_destroy(self._h)
+            self._h = None

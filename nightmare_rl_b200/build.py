@@ -9,7 +9,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 # NIGHTMARE_B200_LIB lets experiments load an alternative build of the same ABI (tools/quick_bench.py)
 LIB_PATH = os.environ.get("NIGHTMARE_B200_LIB") or os.path.join(PKG, "libnightmare_b200.so")
-SOURCES = ["nm_kernels.cu", "nm_abi.cu", "nm_policy.cu", "nm_policy_tc5.cu", "nm_ppo_grad.cu"]
+SOURCES = ["nm_kernels.cu", "nm_abi.cu", "nm_policy.cu", "nm_policy_tc5.cu", "nm_ppo_grad.cu", "nm_generic.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--use_fast_math=false"]
 

@@ -132,7 +132,7 @@ static int build_device_model(nm_model* m) {
   NEED(sensor_site, "sensor_site", 2, int);
 #undef NEED
   const int integrator = oi[0], solver = oi[1], cone = oi[2];
-  if (solver != 0) return fail(NM_ERR_UNSUPPORTED, "only solver=\"PGS\" is implemented by the step kernels");
+  if (solver != 0) return fail(NM_ERR_UNSUPPORTED, "only solver=\"PGS\" is implemented by nm_step / nm_physics_step; Newton models load through nm_gen_model_from_buffer");
   if (cone != 0) return fail(NM_ERR_UNSUPPORTED, "only cone=\"pyramidal\" is implemented by the step kernels");
   if (integrator != 0 && integrator != 3) return fail(NM_ERR_UNSUPPORTED, "only integrator Euler/implicitfast is implemented");
 

@@ -1,0 +1,1061 @@
+// nm_generic.cu — physics step for general small legged robots whose model needs MuJoCo's Newton solver: models/anymal_c
+// of the reference (BASELINE configs[3]; `anymal_c.xml:4` cone="elliptic" impratio="100", solver left at Newton, `:9` joint
+// damping + friction loss, `:20-21` condim-6 sphere feet with priority, `:26` position actuators with a force range, joint
+// limits, box / cylinder / sphere geoms against the plane, Euler integration with implicit joint damping).
+//
+// Replaces `mj.mj_step(model, data[i], nstep)` (reference call sites envs/nightmare_v3_env.py:200, simple_test.py:39) for
+// such a model.  Scope: a free-floating base plus hinge joints (one joint per body, anchored at the body
+// origin), collisions with ONE static plane; the model's geom-geom self collisions are not generated.
+//
+// Decomposition: ONE WARP PER ENVIRONMENT, four environments per CTA.  Everything of an environment lives in shared memory
+// for the whole launch (state, kinematics, dense M / J / H for nv <= 24, up to 72 constraint rows: ~21 KB); every stage is a
+// loop over bodies / dofs / rows / matrix entries strided over the 32 lanes with __syncwarp() between dependent stages;
+// tree recursions go level by level.  The constraint solve is Newton's method on MuJoCo's convex primal problem with the
+// exact cone Hessian and an exact line search (regula falsi on the directional derivative), dense Cholesky in shared memory.
+#include <cuda_runtime.h>
+#include <math_constants.h>
+
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/nightmare_b200.h"
+
+int nm_fail(int code, const std::string& msg);   // nm_abi.cu
+
+#define GM_MAXB 16     // bodies, world included
+#define GM_MAXV 24
+#define GM_MAXQ 25
+#define GM_MAXU 18
+#define GM_MAXG 48     // collision geoms (plane excluded)
+#define GM_MAXCON 16
+#define GM_MAXROW 72
+#define GM_WARPS 4     // environments per CTA
+
+enum { G_SPHERE = 2, G_CYLINDER = 5, G_BOX = 6 };
+enum { R_FRICTION = 0, R_LIMIT = 1, R_CONTACT = 3 };
+
+struct GenModel {
+  int nq, nv, nu, nbody, ngeom, maxdepth, nfloss, cone, iterations, integrator, eulerdamp, pad0;
+  float timestep, gravity[3], tolerance, impratio, solver_scale, pad1;
+  float qpos0[GM_MAXQ];
+  // bodies (one joint each; body 0 = world, body 1 = the free-floating base)
+  int body_parent[GM_MAXB], body_depth[GM_MAXB], body_dofadr[GM_MAXB], body_qadr[GM_MAXB], body_dofmask[GM_MAXB];
+  float body_pos[GM_MAXB][3], body_quat[GM_MAXB][4], body_ipos[GM_MAXB][3], body_iquat[GM_MAXB][4], body_mass[GM_MAXB], body_inertia[GM_MAXB][3];
+  float body_invw[GM_MAXB][2], jnt_axis[GM_MAXB][3], jnt_range[GM_MAXB][2];
+  int jnt_limited[GM_MAXB];
+  // dofs
+  int dof_body[GM_MAXV], dof_parent[GM_MAXV], dof_flossrow[GM_MAXV];
+  float dof_damping[GM_MAXV], dof_floss[GM_MAXV], dof_armature[GM_MAXV], dof_invw[GM_MAXV];
+  // actuators (affine: force = gain0 * ctrl + bias0 + bias1 * q + bias2 * qvel)
+  int act_dof[GM_MAXU], act_qadr[GM_MAXU], act_ctrllimited[GM_MAXU], act_forcelimited[GM_MAXU];
+  float act_gain0[GM_MAXU], act_bias[GM_MAXU][3], act_gear[GM_MAXU], act_ctrlrange[GM_MAXU][2], act_forcerange[GM_MAXU][2];
+  // collision geoms against the plane, in MuJoCo's geom order
+  int geom_type[GM_MAXG], geom_body[GM_MAXG], geom_dim[GM_MAXG];
+  float geom_pos[GM_MAXG][3], geom_mat[GM_MAXG][9], geom_size[GM_MAXG][3], geom_margin[GM_MAXG];
+  float geom_friction[GM_MAXG][5], geom_K[GM_MAXG], geom_B[GM_MAXG], geom_solimp[GM_MAXG][5];   // already mixed with the plane's parameters
+  float plane_n[3], plane_pos[3], plane_frame[9];
+  float lim_K, lim_B, lim_imp0, lim_solimp[5];        // default solref / solimp of friction-loss and limit rows
+};
+
+struct GenArgs {
+  const GenModel* model;
+  float* qpos; float* qvel; float* warm; const float* ctrl; int* info;   // info[N][4] = ncon, nefc, Newton iterations (last substep), overflow flag
+  int num_envs, nstep;
+};
+
+// ---------------------------------------------------------------------------------------------- small algebra (device)
+__device__ __forceinline__ void g_quat2mat(const float* q, float* m) {
+  const float w = q[0], x = q[1], y = q[2], z = q[3];
+  m[0] = w * w + x * x - y * y - z * z; m[1] = 2.f * (x * y - w * z); m[2] = 2.f * (x * z + w * y);
+  m[3] = 2.f * (x * y + w * z); m[4] = w * w - x * x + y * y - z * z; m[5] = 2.f * (y * z - w * x);
+  m[6] = 2.f * (x * z - w * y); m[7] = 2.f * (y * z + w * x); m[8] = w * w - x * x - y * y + z * z;
+}
+__device__ __forceinline__ void g_mulquat(float* r, const float* a, const float* b) {
+  const float w = a[0] * b[0] - a[1] * b[1] - a[2] * b[2] - a[3] * b[3];
+  const float x = a[0] * b[1] + a[1] * b[0] + a[2] * b[3] - a[3] * b[2];
+  const float y = a[0] * b[2] - a[1] * b[3] + a[2] * b[0] + a[3] * b[1];
+  const float z = a[0] * b[3] + a[1] * b[2] - a[2] * b[1] + a[3] * b[0];
+  r[0] = w; r[1] = x; r[2] = y; r[3] = z;
+}
+__device__ __forceinline__ void g_normquat(float* q) {
+  const float n = sqrtf(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+  if (n < 1e-15f) { q[0] = 1.f; q[1] = q[2] = q[3] = 0.f; return; }
+  const float inv = 1.f / n;
+  q[0] *= inv; q[1] *= inv; q[2] *= inv; q[3] *= inv;
+}
+__device__ __forceinline__ void g_matvec(float* r, const float* m, const float* v) {
+  const float x = m[0] * v[0] + m[1] * v[1] + m[2] * v[2], y = m[3] * v[0] + m[4] * v[1] + m[5] * v[2], z = m[6] * v[0] + m[7] * v[1] + m[8] * v[2];
+  r[0] = x; r[1] = y; r[2] = z;
+}
+__device__ __forceinline__ void g_cross(float* r, const float* a, const float* b) {
+  const float x = a[1] * b[2] - a[2] * b[1], y = a[2] * b[0] - a[0] * b[2], z = a[0] * b[1] - a[1] * b[0];
+  r[0] = x; r[1] = y; r[2] = z;
+}
+__device__ __forceinline__ float g_dot3(const float* a, const float* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+// spatial inertia (Ixx Iyy Izz Ixy Ixz Iyz, m*r(3), m) times motion vector [w; v]
+__device__ __forceinline__ void g_inertvec(float* res, const float* i, const float* v) {
+  res[0] = i[0] * v[0] + i[3] * v[1] + i[4] * v[2] - i[8] * v[4] + i[7] * v[5];
+  res[1] = i[3] * v[0] + i[1] * v[1] + i[5] * v[2] + i[8] * v[3] - i[6] * v[5];
+  res[2] = i[4] * v[0] + i[5] * v[1] + i[2] * v[2] - i[7] * v[3] + i[6] * v[4];
+  res[3] = i[8] * v[1] - i[7] * v[2] + i[9] * v[3];
+  res[4] = i[6] * v[2] - i[8] * v[0] + i[9] * v[4];
+  res[5] = i[7] * v[0] - i[6] * v[1] + i[9] * v[5];
+}
+__device__ __forceinline__ void g_crossmotion(float* r, const float* vel, const float* v) {
+  float a[3], b[3], c[3];
+  g_cross(a, vel, v); g_cross(b, vel, v + 3); g_cross(c, vel + 3, v);
+  r[0] = a[0]; r[1] = a[1]; r[2] = a[2]; r[3] = b[0] + c[0]; r[4] = b[1] + c[1]; r[5] = b[2] + c[2];
+}
+__device__ __forceinline__ void g_crossforce(float* r, const float* vel, const float* f) {
+  float a[3], b[3], c[3];
+  g_cross(a, vel, f); g_cross(b, vel + 3, f + 3); g_cross(c, vel, f + 3);
+  r[0] = a[0] + b[0]; r[1] = a[1] + b[1]; r[2] = a[2] + b[2]; r[3] = c[0]; r[4] = c[1]; r[5] = c[2];
+}
+__device__ __forceinline__ float g_warpsum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float g_impedance(const float* si, float pos) {      // si: dmin dmax width mid power (clamped on the host)
+  if (si[0] == si[1] || si[2] <= 1e-15f) return 0.5f * (si[0] + si[1]);
+  const float x = fabsf(pos / si[2]);
+  if (x >= 1.f) return si[1];
+  if (x <= 0.f) return si[0];
+  float y;
+  if (si[4] == 1.f) y = x;
+  else if (x <= si[3]) y = powf(x, si[4]) / powf(si[3], si[4] - 1.f);
+  else y = 1.f - powf(1.f - x, si[4]) / powf(1.f - si[3], si[4] - 1.f);
+  return si[0] + y * (si[1] - si[0]);
+}
+
+// ---------------------------------------------------------------------------------------------- per-environment shared memory
+struct EnvMem {
+  float qpos[GM_MAXQ + 3], qvel[GM_MAXV], warm[GM_MAXV], ctrl[GM_MAXU + 2];
+  float xpos[GM_MAXB][3], xquat[GM_MAXB][4], xmat[GM_MAXB][9], xipos[GM_MAXB][3], ximat[GM_MAXB][9];
+  float com[4];
+  float cinert[GM_MAXB][10], crb[GM_MAXB][10], cdof[GM_MAXV][6], cdofdot[GM_MAXV][6];
+  float cvel[GM_MAXB][6], cacc[GM_MAXB][6], cfrc[GM_MAXB][6];
+  float M[GM_MAXV][GM_MAXV], L[GM_MAXV][GM_MAXV], H[GM_MAXV][GM_MAXV];
+  float bias[GM_MAXV], smooth[GM_MAXV], qaccs[GM_MAXV], qacc[GM_MAXV], grad[GM_MAXV], dir[GM_MAXV], Ma[GM_MAXV], vec[GM_MAXV], fcon[GM_MAXV];
+  // contacts
+  int ncon, nefc, nlim, overflow;
+  float cpos[GM_MAXCON][3], cdist[GM_MAXCON], cmu[GM_MAXCON];
+  int cgeom[GM_MAXCON], cadr[GM_MAXCON], cdim[GM_MAXCON], czone[GM_MAXCON];
+  float chess[GM_MAXCON][36];
+  // rows
+  float J[GM_MAXROW][GM_MAXV];
+  float aref[GM_MAXROW], D[GM_MAXROW], R[GM_MAXROW], jar[GM_MAXROW], jv[GM_MAXROW], force[GM_MAXROW], Hd[GM_MAXROW], floss[GM_MAXROW];
+  int rtype[GM_MAXROW], rid[GM_MAXROW];
+};
+
+// dense Cholesky of the nv x nv matrix A (lower triangle used) into Lo, by the whole warp; returns false if not positive definite
+__device__ bool g_cholesky(float (*Lo)[GM_MAXV], const float (*A)[GM_MAXV], int n, int lane) {
+  bool ok = true;
+  for (int j = 0; j < n; j++) {
+    float s = 0.f;
+    if (lane == 0) {
+      s = A[j][j];
+      for (int k = 0; k < j; k++) s -= Lo[j][k] * Lo[j][k];
+      if (s < 1e-30f) { s = 1e-30f; ok = false; }
+      Lo[j][j] = sqrtf(s);
+    }
+    __syncwarp();
+    const float inv = 1.f / Lo[j][j];
+    for (int i = j + 1 + lane; i < n; i += 32) {
+      float t = A[i][j];
+      for (int k = 0; k < j; k++) t -= Lo[i][k] * Lo[j][k];
+      Lo[i][j] = t * inv;
+    }
+    __syncwarp();
+  }
+  return __all_sync(0xffffffffu, ok);
+}
+// x <- (L L')^-1 x, x in shared memory; lane-parallel over rows below the pivot
+__device__ void g_cholsolve(const float (*Lo)[GM_MAXV], int n, float* x, int lane) {
+  for (int j = 0; j < n; j++) {
+    if (lane == 0) x[j] /= Lo[j][j];
+    __syncwarp();
+    const float xj = x[j];
+    for (int i = j + 1 + lane; i < n; i += 32) x[i] -= Lo[i][j] * xj;
+    __syncwarp();
+  }
+  for (int j = n - 1; j >= 0; j--) {
+    if (lane == 0) x[j] /= Lo[j][j];
+    __syncwarp();
+    const float xj = x[j];
+    for (int i = lane; i < j; i += 32) x[i] -= Lo[j][i] * xj;
+    __syncwarp();
+  }
+}
+
+// constraint forces, cost and (optionally) curvature at jar: friction-loss / limit rows one per lane, contacts one per lane
+__device__ float g_rows(const GenModel& m, EnvMem& e, const float* jar, bool hess, int lane) {
+  float cost = 0.f;
+  const int nsimple = m.nfloss + e.nlim;
+  for (int r = lane; r < nsimple; r += 32) {
+    const float D = e.D[r], R = e.R[r], j = jar[r];
+    float hd = 0.f;
+    if (e.rtype[r] == R_FRICTION) {
+      const float fl = e.floss[r], bound = R * fl;
+      if (j <= -bound) { e.force[r] = fl; cost += -0.5f * R * fl * fl - fl * j; }
+      else if (j >= bound) { e.force[r] = -fl; cost += -0.5f * R * fl * fl + fl * j; }
+      else { e.force[r] = -D * j; cost += 0.5f * D * j * j; hd = D; }
+    } else {
+      if (j < 0.f) { e.force[r] = -D * j; cost += 0.5f * D * j * j; hd = D; }
+      else e.force[r] = 0.f;
+    }
+    if (hess) e.Hd[r] = hd;
+  }
+  for (int c = lane; c < e.ncon; c += 32) {
+    const int a = e.cadr[c], dim = e.cdim[c];
+    const float mu = e.cmu[c];
+    const float* fri = m.geom_friction[e.cgeom[c]];
+    float U[6];
+    U[0] = jar[a] * mu;
+    float T2 = 0.f;
+    for (int j = 1; j < dim; j++) { U[j] = jar[a + j] * fri[j - 1]; T2 += U[j] * U[j]; }
+    const float N = U[0], T = sqrtf(T2);
+    int zone;
+    if (dim == 1) {
+      zone = jar[a] < 0.f ? 1 : 0;
+    } else if (N >= mu * T || (T <= 0.f && N >= 0.f)) zone = 0;
+    else if (mu * N + T <= 0.f || (T <= 0.f && N < 0.f)) zone = 1;
+    else zone = 2;
+    if (zone == 0) {
+      for (int j = 0; j < dim; j++) { e.force[a + j] = 0.f; if (hess) e.Hd[a + j] = 0.f; }
+    } else if (zone == 1) {
+      for (int j = 0; j < dim; j++) {
+        const float Dj = e.D[a + j], jj = jar[a + j];
+        e.force[a + j] = -Dj * jj;
+        cost += 0.5f * Dj * jj * jj;
+        if (hess) e.Hd[a + j] = Dj;
+      }
+    } else {
+      const float Dm = e.D[a] / (mu * mu * (1.f + mu * mu)), NmT = N - mu * T;
+      cost += 0.5f * Dm * NmT * NmT;
+      const float f0 = -Dm * NmT * mu;
+      e.force[a] = f0;
+      for (int j = 1; j < dim; j++) e.force[a + j] = -f0 / T * U[j] * fri[j - 1];
+      if (hess) {
+        float g[6];
+        g[0] = mu;
+        for (int j = 1; j < dim; j++) g[j] = -mu * fri[j - 1] * U[j] / T;
+        for (int p = 0; p < dim; p++) {
+          e.Hd[a + p] = 0.f;
+          for (int q = 0; q < dim; q++) {
+            float h = g[p] * g[q];
+            if (p > 0 && q > 0) h += -mu * NmT * fri[p - 1] * fri[q - 1] * ((p == q ? 1.f : 0.f) - U[p] * U[q] / T2) / T;
+            e.chess[c][6 * p + q] = Dm * h;
+          }
+        }
+      }
+    }
+    if (hess) e.czone[c] = zone;
+  }
+  return g_warpsum(cost);
+}
+
+// ================================================================================================ the kernel
+__global__ void __launch_bounds__(GM_WARPS * 32) nm_generic_step_kernel(const GenArgs A) {
+  extern __shared__ __align__(16) unsigned char gm_smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int env = blockIdx.x * GM_WARPS + warp;
+  if (env >= A.num_envs) return;                      // whole warps leave together; no CTA-wide barrier is used below
+  EnvMem& e = *reinterpret_cast<EnvMem*>(gm_smem + sizeof(EnvMem) * warp);
+  const GenModel& m = *A.model;
+  const int nv = m.nv, nq = m.nq, nb = m.nbody, nu = m.nu;
+  const float h = m.timestep;
+
+  for (int i = lane; i < nq; i += 32) e.qpos[i] = A.qpos[(size_t)env * nq + i];
+  for (int i = lane; i < nv; i += 32) { e.qvel[i] = A.qvel[(size_t)env * nv + i]; e.warm[i] = A.warm[(size_t)env * nv + i]; }
+  for (int i = lane; i < nu; i += 32) e.ctrl[i] = A.ctrl[(size_t)env * nu + i];
+  int niter_last = 0;
+  __syncwarp();
+
+  for (int sub = 0; sub < A.nstep; sub++) {
+    // ------------------------------------------------------------------ divergence guard (≙ mj_checkPos / mj_checkVel)
+    {
+      bool bad = false;
+      for (int i = lane; i < nq; i += 32) bad |= !(fabsf(e.qpos[i]) < 1e10f);
+      for (int i = lane; i < nv; i += 32) bad |= !(fabsf(e.qvel[i]) < 1e10f);
+      if (__any_sync(0xffffffffu, bad)) {
+        for (int i = lane; i < nq; i += 32) e.qpos[i] = m.qpos0[i];
+        for (int i = lane; i < nv; i += 32) { e.qvel[i] = 0.f; e.warm[i] = 0.f; }
+      }
+      __syncwarp();
+    }
+    // ------------------------------------------------------------------ P1 kinematics, level by level
+    if (lane == 0) {
+      e.xpos[0][0] = e.xpos[0][1] = e.xpos[0][2] = 0.f;
+      e.xquat[0][0] = 1.f; e.xquat[0][1] = e.xquat[0][2] = e.xquat[0][3] = 0.f;
+      g_quat2mat(e.xquat[0], e.xmat[0]);
+    }
+    __syncwarp();
+    for (int lev = 1; lev <= m.maxdepth; lev++) {
+      for (int b = 1 + lane; b < nb; b += 32) {
+        if (m.body_depth[b] != lev) continue;
+        float pos[3], quat[4];
+        if (b == 1) {                                  // free joint
+          pos[0] = e.qpos[0]; pos[1] = e.qpos[1]; pos[2] = e.qpos[2];
+          quat[0] = e.qpos[3]; quat[1] = e.qpos[4]; quat[2] = e.qpos[5]; quat[3] = e.qpos[6];
+          g_normquat(quat);
+        } else {
+          const int p = m.body_parent[b];
+          float t[3];
+          g_matvec(t, e.xmat[p], m.body_pos[b]);
+          pos[0] = e.xpos[p][0] + t[0]; pos[1] = e.xpos[p][1] + t[1]; pos[2] = e.xpos[p][2] + t[2];
+          g_mulquat(quat, e.xquat[p], m.body_quat[b]);
+          const float ang = e.qpos[m.body_qadr[b]] - m.qpos0[m.body_qadr[b]];
+          float s, c;
+          sincosf(0.5f * ang, &s, &c);
+          const float ql[4] = {c, m.jnt_axis[b][0] * s, m.jnt_axis[b][1] * s, m.jnt_axis[b][2] * s};
+          float qn[4];
+          g_mulquat(qn, quat, ql);
+          quat[0] = qn[0]; quat[1] = qn[1]; quat[2] = qn[2]; quat[3] = qn[3];      // (joint anchor at the body origin: no offset correction)
+        }
+        g_normquat(quat);
+        for (int k = 0; k < 3; k++) e.xpos[b][k] = pos[k];
+        for (int k = 0; k < 4; k++) e.xquat[b][k] = quat[k];
+        g_quat2mat(quat, e.xmat[b]);
+        float t[3], qi[4];
+        g_matvec(t, e.xmat[b], m.body_ipos[b]);
+        for (int k = 0; k < 3; k++) e.xipos[b][k] = pos[k] + t[k];
+        g_mulquat(qi, quat, m.body_iquat[b]);
+        g_quat2mat(qi, e.ximat[b]);
+      }
+      __syncwarp();
+    }
+    // ------------------------------------------------------------------ P2 comPos: subtree COM of the root, cinert, cdof
+    {
+      float mx = 0.f, my = 0.f, mz = 0.f, mm = 0.f;
+      for (int b = 1 + lane; b < nb; b += 32) { const float ms = m.body_mass[b]; mx += ms * e.xipos[b][0]; my += ms * e.xipos[b][1]; mz += ms * e.xipos[b][2]; mm += ms; }
+      mx = g_warpsum(mx); my = g_warpsum(my); mz = g_warpsum(mz); mm = g_warpsum(mm);
+      if (lane == 0) { e.com[0] = mx / mm; e.com[1] = my / mm; e.com[2] = mz / mm; }
+      __syncwarp();
+    }
+    for (int b = lane; b < nb; b += 32) {
+      float* ci = e.cinert[b];
+      if (b == 0) { for (int k = 0; k < 10; k++) ci[k] = 0.f; continue; }
+      const float* Rm = e.ximat[b];
+      const float* I = m.body_inertia[b];
+      const float mass = m.body_mass[b];
+      const float r[3] = {e.xipos[b][0] - e.com[0], e.xipos[b][1] - e.com[1], e.xipos[b][2] - e.com[2]};
+      ci[0] = Rm[0] * Rm[0] * I[0] + Rm[1] * Rm[1] * I[1] + Rm[2] * Rm[2] * I[2];
+      ci[1] = Rm[3] * Rm[3] * I[0] + Rm[4] * Rm[4] * I[1] + Rm[5] * Rm[5] * I[2];
+      ci[2] = Rm[6] * Rm[6] * I[0] + Rm[7] * Rm[7] * I[1] + Rm[8] * Rm[8] * I[2];
+      ci[3] = Rm[0] * Rm[3] * I[0] + Rm[1] * Rm[4] * I[1] + Rm[2] * Rm[5] * I[2];
+      ci[4] = Rm[0] * Rm[6] * I[0] + Rm[1] * Rm[7] * I[1] + Rm[2] * Rm[8] * I[2];
+      ci[5] = Rm[3] * Rm[6] * I[0] + Rm[4] * Rm[7] * I[1] + Rm[5] * Rm[8] * I[2];
+      ci[0] += mass * (r[1] * r[1] + r[2] * r[2]);
+      ci[1] += mass * (r[0] * r[0] + r[2] * r[2]);
+      ci[2] += mass * (r[0] * r[0] + r[1] * r[1]);
+      ci[3] -= mass * r[0] * r[1];
+      ci[4] -= mass * r[0] * r[2];
+      ci[5] -= mass * r[1] * r[2];
+      ci[6] = mass * r[0]; ci[7] = mass * r[1]; ci[8] = mass * r[2];
+      ci[9] = mass;
+    }
+    for (int i = lane; i < nv; i += 32) {
+      float* cd = e.cdof[i];
+      const int b = m.dof_body[i];
+      if (b == 1) {
+        if (i < 3) { for (int k = 0; k < 6; k++) cd[k] = 0.f; cd[3 + i] = 1.f; }
+        else {
+          const int k = i - 3;
+          const float ax[3] = {e.xmat[1][k], e.xmat[1][3 + k], e.xmat[1][6 + k]};
+          const float off[3] = {e.com[0] - e.xpos[1][0], e.com[1] - e.xpos[1][1], e.com[2] - e.xpos[1][2]};
+          cd[0] = ax[0]; cd[1] = ax[1]; cd[2] = ax[2];
+          g_cross(cd + 3, ax, off);
+        }
+      } else {
+        float ax[3];
+        g_matvec(ax, e.xmat[b], m.jnt_axis[b]);
+        const float off[3] = {e.com[0] - e.xpos[b][0], e.com[1] - e.xpos[b][1], e.com[2] - e.xpos[b][2]};
+        cd[0] = ax[0]; cd[1] = ax[1]; cd[2] = ax[2];
+        g_cross(cd + 3, ax, off);
+      }
+    }
+    __syncwarp();
+    // ------------------------------------------------------------------ P3 composite inertias (bottom-up), mass matrix, Cholesky
+    for (int b = lane; b < nb; b += 32) for (int k = 0; k < 10; k++) e.crb[b][k] = e.cinert[b][k];
+    __syncwarp();
+    for (int lev = m.maxdepth - 1; lev >= 1; lev--) {
+      for (int b = 1 + lane; b < nb; b += 32) {
+        if (m.body_depth[b] != lev) continue;
+        for (int c = b + 1; c < nb; c++)
+          if (m.body_parent[c] == b) for (int k = 0; k < 10; k++) e.crb[b][k] += e.crb[c][k];
+      }
+      __syncwarp();
+    }
+    for (int i = lane; i < nv * nv; i += 32) (&e.M[0][0])[(i / nv) * GM_MAXV + i % nv] = 0.f;
+    __syncwarp();
+    for (int i = lane; i < nv; i += 32) {
+      float buf[6];
+      g_inertvec(buf, e.crb[m.dof_body[i]], e.cdof[i]);
+      for (int j = i; j >= 0; j = m.dof_parent[j]) {
+        float s = 0.f;
+        for (int k = 0; k < 6; k++) s += e.cdof[j][k] * buf[k];
+        e.M[i][j] = s; e.M[j][i] = s;
+      }
+      e.M[i][i] += m.dof_armature[i];
+    }
+    __syncwarp();
+    g_cholesky(e.L, e.M, nv, lane);
+    // ------------------------------------------------------------------ P7 comVel + RNE
+    if (lane == 0) for (int k = 0; k < 6; k++) { e.cvel[0][k] = 0.f; e.cacc[0][k] = k >= 3 ? -m.gravity[k - 3] : 0.f; }
+    __syncwarp();
+    for (int lev = 1; lev <= m.maxdepth; lev++) {
+      for (int b = 1 + lane; b < nb; b += 32) {
+        if (m.body_depth[b] != lev) continue;
+        float cv[6], ca[6];
+        const int p = m.body_parent[b], da = m.body_dofadr[b];
+        for (int k = 0; k < 6; k++) { cv[k] = e.cvel[p][k]; ca[k] = e.cacc[p][k]; }
+        if (b == 1) {
+          for (int d = 0; d < 3; d++) { for (int k = 0; k < 6; k++) { e.cdofdot[da + d][k] = 0.f; cv[k] += e.cdof[da + d][k] * e.qvel[da + d]; } }
+          for (int d = 3; d < 6; d++) g_crossmotion(e.cdofdot[da + d], cv, e.cdof[da + d]);
+          for (int d = 3; d < 6; d++) for (int k = 0; k < 6; k++) cv[k] += e.cdof[da + d][k] * e.qvel[da + d];
+          for (int d = 0; d < 6; d++) for (int k = 0; k < 6; k++) ca[k] += e.cdofdot[da + d][k] * e.qvel[da + d];
+        } else {
+          g_crossmotion(e.cdofdot[da], cv, e.cdof[da]);
+          for (int k = 0; k < 6; k++) { cv[k] += e.cdof[da][k] * e.qvel[da]; ca[k] += e.cdofdot[da][k] * e.qvel[da]; }
+        }
+        float f[6], t1[6], t2[6];
+        g_inertvec(f, e.cinert[b], ca);
+        g_inertvec(t1, e.cinert[b], cv);
+        g_crossforce(t2, cv, t1);
+        for (int k = 0; k < 6; k++) { e.cvel[b][k] = cv[k]; e.cacc[b][k] = ca[k]; e.cfrc[b][k] = f[k] + t2[k]; }
+      }
+      __syncwarp();
+    }
+    for (int lev = m.maxdepth - 1; lev >= 1; lev--) {
+      for (int b = 1 + lane; b < nb; b += 32) {
+        if (m.body_depth[b] != lev) continue;
+        for (int c = b + 1; c < nb; c++)
+          if (m.body_parent[c] == b) for (int k = 0; k < 6; k++) e.cfrc[b][k] += e.cfrc[c][k];
+      }
+      __syncwarp();
+    }
+    // ------------------------------------------------------------------ P8 passive + actuation + smooth acceleration
+    for (int i = lane; i < nv; i += 32) {
+      float s = 0.f;
+      for (int k = 0; k < 6; k++) s += e.cdof[i][k] * e.cfrc[m.dof_body[i]][k];
+      e.bias[i] = s;
+      e.smooth[i] = -m.dof_damping[i] * e.qvel[i] - s;
+    }
+    __syncwarp();
+    for (int a = lane; a < nu; a += 32) {
+      float c = e.ctrl[a];
+      if (m.act_ctrllimited[a]) c = fminf(fmaxf(c, m.act_ctrlrange[a][0]), m.act_ctrlrange[a][1]);
+      const int dof = m.act_dof[a];
+      const float g = m.act_gear[a];
+      float f = m.act_gain0[a] * c + m.act_bias[a][0] + m.act_bias[a][1] * (e.qpos[m.act_qadr[a]] * g) + m.act_bias[a][2] * (e.qvel[dof] * g);
+      if (m.act_forcelimited[a]) f = fminf(fmaxf(f, m.act_forcerange[a][0]), m.act_forcerange[a][1]);
+      e.smooth[dof] += g * f;                          // (one actuator per dof: checked on the host)
+    }
+    __syncwarp();
+    for (int i = lane; i < nv; i += 32) e.qaccs[i] = e.smooth[i];
+    __syncwarp();
+    g_cholsolve(e.L, nv, e.qaccs, lane);
+    // ------------------------------------------------------------------ P4 collision: sphere / box / cylinder against the plane
+    {
+      int base = 0;
+      if (lane == 0) e.overflow = 0;
+      for (int g0 = 0; g0 < m.ngeom; g0 += 32) {
+        const int g = g0 + lane;
+        int cnt = 0;
+        float cp[4][3], cd[4];
+        if (g < m.ngeom) {
+          const int b = m.geom_body[g];
+          float gc[3], gm[9];
+          g_matvec(gc, e.xmat[b], m.geom_pos[g]);
+          gc[0] += e.xpos[b][0]; gc[1] += e.xpos[b][1]; gc[2] += e.xpos[b][2];
+          const float* n = m.plane_n;
+          const float dif[3] = {gc[0] - m.plane_pos[0], gc[1] - m.plane_pos[1], gc[2] - m.plane_pos[2]};
+          const float dist0 = g_dot3(dif, n), margin = m.geom_margin[g];
+          const float* size = m.geom_size[g];
+          if (m.geom_type[g] == G_SPHERE) {
+            const float dist = dist0 - size[0];
+            if (dist <= margin) { cd[0] = dist; for (int k = 0; k < 3; k++) cp[0][k] = gc[k] - n[k] * (size[0] + 0.5f * dist); cnt = 1; }
+          } else {
+            for (int r = 0; r < 3; r++)
+              for (int c2 = 0; c2 < 3; c2++) gm[3 * r + c2] = e.xmat[b][3 * r] * m.geom_mat[g][c2] + e.xmat[b][3 * r + 1] * m.geom_mat[g][3 + c2] + e.xmat[b][3 * r + 2] * m.geom_mat[g][6 + c2];
+            if (m.geom_type[g] == G_BOX) {
+              for (int i = 0; i < 8 && cnt < 4; i++) {
+                const float v[3] = {(i & 1) ? size[0] : -size[0], (i & 2) ? size[1] : -size[1], (i & 4) ? size[2] : -size[2]};
+                float corner[3];
+                g_matvec(corner, gm, v);
+                const float ld = g_dot3(n, corner);
+                if (dist0 + ld > margin || ld > 0.f) continue;
+                cd[cnt] = dist0 + ld;
+                for (int k = 0; k < 3; k++) cp[cnt][k] = corner[k] - n[k] * cd[cnt] * 0.5f + gc[k];
+                cnt++;
+              }
+            } else {                                   // cylinder (≙ mjc_PlaneCylinder)
+              float axis[3] = {gm[2], gm[5], gm[8]}, vec[3];
+              float prjaxis = g_dot3(n, axis);
+              if (prjaxis > 0.f) { axis[0] = -axis[0]; axis[1] = -axis[1]; axis[2] = -axis[2]; prjaxis = -prjaxis; }
+              for (int k = 0; k < 3; k++) vec[k] = axis[k] * prjaxis - n[k];
+              const float len2 = g_dot3(vec, vec);
+              if (len2 >= 1e-30f) { const float scl = size[0] / sqrtf(len2); vec[0] *= scl; vec[1] *= scl; vec[2] *= scl; }
+              else { vec[0] = gm[0] * size[0]; vec[1] = gm[3] * size[0]; vec[2] = gm[6] * size[0]; }
+              const float prjvec = g_dot3(vec, n);
+              axis[0] *= size[1]; axis[1] *= size[1]; axis[2] *= size[1];
+              prjaxis *= size[1];
+              if (dist0 + prjaxis + prjvec <= margin) {
+                cd[cnt] = dist0 + prjaxis + prjvec;
+                for (int k = 0; k < 3; k++) cp[cnt][k] = gc[k] + vec[k] + axis[k] - n[k] * cd[cnt] * 0.5f;
+                cnt++;
+                if (dist0 - prjaxis + prjvec <= margin) {
+                  cd[cnt] = dist0 - prjaxis + prjvec;
+                  for (int k = 0; k < 3; k++) cp[cnt][k] = gc[k] + vec[k] - axis[k] - n[k] * cd[cnt] * 0.5f;
+                  cnt++;
+                }
+                const float prjvec1 = -prjvec * 0.5f;
+                if (dist0 + prjaxis + prjvec1 <= margin) {
+                  float v1[3];
+                  g_cross(v1, vec, axis);
+                  const float nn = sqrtf(g_dot3(v1, v1));
+                  if (nn < 1e-15f) { v1[0] = 1.f; v1[1] = 0.f; v1[2] = 0.f; } else { v1[0] /= nn; v1[1] /= nn; v1[2] /= nn; }
+                  const float sc = size[0] * 0.8660254037844386f;
+                  for (int sg = 0; sg < 2; sg++) {
+                    cd[cnt] = dist0 + prjaxis + prjvec1;
+                    for (int k = 0; k < 3; k++) cp[cnt][k] = gc[k] + (sg ? -v1[k] : v1[k]) * sc + axis[k] - vec[k] * 0.5f - n[k] * cd[cnt] * 0.5f;
+                    cnt++;
+                  }
+                }
+              }
+            }
+          }
+        }
+        // contacts in geom order: exclusive prefix sum of the counts over the lanes
+        int incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+        const int first = base + incl - cnt;
+        for (int q = 0; q < cnt; q++) {
+          const int c = first + q;
+          if (c < GM_MAXCON) {
+            e.cdist[c] = cd[q]; e.cgeom[c] = g;
+            for (int k = 0; k < 3; k++) e.cpos[c][k] = cp[q][k];
+          } else e.overflow = 1;
+        }
+        base += __shfl_sync(0xffffffffu, incl, 31);
+      }
+      __syncwarp();
+      if (lane == 0) e.ncon = min(base, GM_MAXCON);
+      __syncwarp();
+    }
+    // ------------------------------------------------------------------ P5 constraint rows: friction loss, limits, contacts
+    {
+      // friction-loss rows (host-assigned row per dof)
+      for (int i = lane; i < nv; i += 32) {
+        const int r = m.dof_flossrow[i];
+        if (r < 0) continue;
+        for (int k = 0; k < nv; k++) e.J[r][k] = 0.f;
+        e.J[r][i] = 1.f;
+        const float imp = m.lim_imp0;
+        const float R = fmaxf((1.f - imp) * m.dof_invw[i] / imp, 1e-15f);
+        e.R[r] = R; e.D[r] = 1.f / R; e.floss[r] = m.dof_floss[i];
+        e.aref[r] = -m.lim_B * e.qvel[i];
+        e.rtype[r] = R_FRICTION; e.rid[r] = i;
+      }
+      // joint limits: lower side first, then upper, in joint (= body) order
+      int base = m.nfloss;
+      for (int b0 = 2; b0 < nb; b0 += 32) {
+        const int b = b0 + lane;
+        int cnt = 0;
+        float dist[2], sgn[2];
+        if (b < nb && m.jnt_limited[b]) {
+          const float value = e.qpos[m.body_qadr[b]];
+          const float dlo = value - m.jnt_range[b][0], dhi = m.jnt_range[b][1] - value;
+          if (dlo < 0.f) { dist[cnt] = dlo; sgn[cnt] = 1.f; cnt++; }
+          if (dhi < 0.f) { dist[cnt] = dhi; sgn[cnt] = -1.f; cnt++; }
+        }
+        int incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+        const int first = base + incl - cnt;
+        for (int q = 0; q < cnt; q++) {
+          const int r = first + q, i = m.body_dofadr[b];
+          for (int k = 0; k < nv; k++) e.J[r][k] = 0.f;
+          e.J[r][i] = sgn[q];
+          const float imp = g_impedance(m.lim_solimp, dist[q]);
+          const float R = fmaxf((1.f - imp) * m.dof_invw[i] / imp, 1e-15f);
+          e.R[r] = R; e.D[r] = 1.f / R; e.floss[r] = 0.f;
+          e.aref[r] = -m.lim_B * (sgn[q] * e.qvel[i]) - m.lim_K * imp * dist[q];
+          e.rtype[r] = R_LIMIT; e.rid[r] = b;
+        }
+        base += __shfl_sync(0xffffffffu, incl, 31);
+      }
+      if (lane == 0) e.nlim = base - m.nfloss;
+      __syncwarp();
+      // contacts: row addresses (serial prefix over <= 16 contacts), then the Jacobian entries spread over the lanes
+      if (lane == 0) {
+        int r = m.nfloss + e.nlim, nc = 0;
+        for (int c = 0; c < e.ncon; c++) {
+          const int dim = m.geom_dim[e.cgeom[c]];
+          if (r + dim > GM_MAXROW) { e.overflow = 1; break; }
+          e.cadr[c] = r; e.cdim[c] = dim; r += dim; nc++;
+        }
+        e.ncon = nc; e.nefc = r;
+      }
+      __syncwarp();
+      const int row0 = m.nfloss + e.nlim, nrow = e.nefc - row0;
+      for (int idx = lane; idx < nrow * nv; idx += 32) {
+        const int r = row0 + idx / nv, i = idx % nv;
+        // which contact owns row r
+        int c = 0;
+        while (c + 1 < e.ncon && e.cadr[c + 1] <= r) c++;
+        const int k = r - e.cadr[c];                 // 0 normal, 1-2 tangents, 3 torsion, 4-5 rolling
+        const int g = e.cgeom[c], b = m.geom_body[g];
+        float val = 0.f;
+        if ((m.body_dofmask[b] >> i) & 1) {
+          const float* fr = m.plane_frame + 3 * (k < 3 ? k : k - 3);
+          if (k < 3) {
+            const float off[3] = {e.cpos[c][0] - e.com[0], e.cpos[c][1] - e.com[1], e.cpos[c][2] - e.com[2]};
+            float t[3];
+            g_cross(t, e.cdof[i], off);
+            val = fr[0] * (e.cdof[i][3] + t[0]) + fr[1] * (e.cdof[i][4] + t[1]) + fr[2] * (e.cdof[i][5] + t[2]);
+          } else val = fr[0] * e.cdof[i][0] + fr[1] * e.cdof[i][1] + fr[2] * e.cdof[i][2];
+        }
+        e.J[r][i] = val;
+      }
+      __syncwarp();
+      for (int c = lane; c < e.ncon; c += 32) {
+        const int a = e.cadr[c], dim = e.cdim[c], g = e.cgeom[c], b = m.geom_body[g];
+        const float pos = e.cdist[c] - m.geom_margin[g];
+        const float imp = g_impedance(m.geom_solimp[g], pos);
+        const float tran = m.body_invw[b][0];
+        const float R0 = fmaxf((1.f - imp) * tran / imp, 1e-15f);
+        e.R[a] = R0;
+        if (dim > 1) {
+          const float* fri = m.geom_friction[g];
+          const float R1 = R0 / fmaxf(m.impratio, 1e-15f);
+          e.R[a + 1] = R1;
+          for (int j = 2; j < dim; j++) e.R[a + j] = R1 * fri[0] * fri[0] / (fri[j - 1] * fri[j - 1]);
+          e.cmu[c] = fri[0] * sqrtf(R1 / R0);
+        } else e.cmu[c] = 0.f;
+        for (int j = 0; j < dim; j++) {
+          float vel = 0.f;
+          for (int i = 0; i < nv; i++) vel += e.J[a + j][i] * e.qvel[i];
+          e.R[a + j] = fmaxf(e.R[a + j], 1e-15f);
+          e.D[a + j] = 1.f / e.R[a + j];
+          e.aref[a + j] = -m.geom_B[g] * vel - (j == 0 ? m.geom_K[g] * imp * pos : 0.f);
+          e.floss[a + j] = 0.f; e.rtype[a + j] = R_CONTACT; e.rid[a + j] = c;
+        }
+      }
+      __syncwarp();
+    }
+    // ------------------------------------------------------------------ P9 Newton solver on the primal problem
+    const int ne = e.nefc;
+    int niter = 0;
+    if (ne == 0) {
+      for (int i = lane; i < nv; i += 32) { e.qacc[i] = e.qaccs[i]; e.fcon[i] = 0.f; }
+      __syncwarp();
+    } else {
+      // start from the cheaper of qacc_warmstart and qacc_smooth
+      float cost2[2];
+      for (int s = 0; s < 2; s++) {
+        const float* q = s == 0 ? e.warm : e.qaccs;
+        for (int i = lane; i < nv; i += 32) e.vec[i] = q[i] - e.qaccs[i];
+        __syncwarp();
+        float cg = 0.f;
+        for (int i = lane; i < nv; i += 32) { float t = 0.f; for (int k = 0; k < nv; k++) t += e.M[i][k] * e.vec[k]; cg += 0.5f * e.vec[i] * t; }
+        for (int r = lane; r < ne; r += 32) { float t = -e.aref[r]; for (int i = 0; i < nv; i++) t += e.J[r][i] * q[i]; e.jar[r] = t; }
+        __syncwarp();
+        cost2[s] = g_warpsum(cg) + g_rows(m, e, e.jar, false, lane);
+        __syncwarp();
+      }
+      for (int i = lane; i < nv; i += 32) e.qacc[i] = cost2[0] < cost2[1] ? e.warm[i] : e.qaccs[i];
+      __syncwarp();
+      for (int it = 0; it < min(m.iterations, 30); it++) {          // (fp32: quadratic convergence ends at rounding after 3-8 steps)
+        niter = it;
+        for (int i = lane; i < nv; i += 32) e.vec[i] = e.qacc[i] - e.qaccs[i];
+        for (int r = lane; r < ne; r += 32) { float t = -e.aref[r]; for (int i = 0; i < nv; i++) t += e.J[r][i] * e.qacc[i]; e.jar[r] = t; }
+        __syncwarp();
+        for (int i = lane; i < nv; i += 32) { float t = 0.f; for (int k = 0; k < nv; k++) t += e.M[i][k] * e.vec[k]; e.Ma[i] = t; }
+        g_rows(m, e, e.jar, true, lane);
+        __syncwarp();
+        float gn = 0.f, gref = 0.f;
+        for (int i = lane; i < nv; i += 32) {
+          float jf = 0.f;
+          for (int r = 0; r < ne; r++) jf += e.J[r][i] * e.force[r];
+          const float t = e.Ma[i] - jf;
+          e.grad[i] = t; gn += t * t; gref += e.Ma[i] * e.Ma[i] + jf * jf;
+        }
+        gn = g_warpsum(gn); gref = g_warpsum(gref);
+        // MuJoCo's test (scaled gradient below opt.tolerance), or the gradient has reached fp32 rounding of its two terms
+        if (m.solver_scale * sqrtf(gn) < m.tolerance || gn <= 1e-11f * gref) break;
+        // Hessian (lower triangle): M + sum Hd J'J + cone blocks
+        for (int idx = lane; idx < nv * (nv + 1) / 2; idx += 32) {
+          int i = (int)((sqrtf(8.f * idx + 1.f) - 1.f) * 0.5f);
+          while ((i + 1) * (i + 2) / 2 <= idx) i++;
+          while (i * (i + 1) / 2 > idx) i--;
+          const int k = idx - i * (i + 1) / 2;
+          float s = e.M[i][k];
+          const int nsimple = m.nfloss + e.nlim;
+          for (int r = 0; r < nsimple; r++) s += e.Hd[r] * e.J[r][i] * e.J[r][k];
+          for (int c = 0; c < e.ncon; c++) {
+            const int a = e.cadr[c], dim = e.cdim[c];
+            if (e.czone[c] == 1) { for (int j = 0; j < dim; j++) s += e.Hd[a + j] * e.J[a + j][i] * e.J[a + j][k]; }
+            else if (e.czone[c] == 2) {
+              for (int p = 0; p < dim; p++) {
+                float t = 0.f;
+                for (int q = 0; q < dim; q++) t += e.chess[c][6 * p + q] * e.J[a + q][k];
+                s += e.J[a + p][i] * t;
+              }
+            }
+          }
+          e.H[i][k] = s;
+        }
+        __syncwarp();
+        if (!g_cholesky(e.H, e.H, nv, lane)) break;                 // in place: only the lower triangle is read
+        for (int i = lane; i < nv; i += 32) e.dir[i] = -e.grad[i];
+        __syncwarp();
+        g_cholsolve(e.H, nv, e.dir, lane);
+        // exact line search on phi'(alpha) = a1 + alpha a2 - sum force(jar + alpha jv) jv
+        for (int r = lane; r < ne; r += 32) { float t = 0.f; for (int i = 0; i < nv; i++) t += e.J[r][i] * e.dir[i]; e.jv[r] = t; }
+        float a1 = 0.f, a2 = 0.f;
+        for (int i = lane; i < nv; i += 32) { float t = 0.f; for (int k = 0; k < nv; k++) t += e.M[i][k] * e.dir[k]; a1 += e.dir[i] * e.Ma[i]; a2 += e.dir[i] * t; }
+        a1 = g_warpsum(a1); a2 = g_warpsum(a2);
+        __syncwarp();
+        float* jt = e.Hd;                                             // trial jar (Hd is no longer needed in this iteration)
+        auto dphi = [&](float alpha) -> float {
+          for (int r = lane; r < ne; r += 32) jt[r] = e.jar[r] + alpha * e.jv[r];
+          __syncwarp();
+          g_rows(m, e, jt, false, lane);
+          __syncwarp();
+          float s = 0.f;
+          for (int r = lane; r < ne; r += 32) s += e.force[r] * e.jv[r];
+          return a1 + alpha * a2 - g_warpsum(s);
+        };
+        float lo = 0.f, hi = 1.f, alpha = 1.f;
+        float flo = dphi(0.f);
+        if (!(flo < 0.f)) break;
+        const float d0 = fabsf(flo);
+        float fhi = dphi(hi);
+        int guard = 0;
+        while (fhi < 0.f && guard++ < 30) { lo = hi; flo = fhi; hi *= 2.f; fhi = dphi(hi); }
+        if (fhi < 0.f) alpha = hi;
+        else {
+          int side = 0;
+          alpha = hi;
+          for (int k = 0; k < 40; k++) {
+            alpha = (lo * fhi - hi * flo) / (fhi - flo);
+            if (!(alpha > lo && alpha < hi)) alpha = 0.5f * (lo + hi);
+            const float fa = dphi(alpha);
+            if (fabsf(fa) <= 1e-5f * d0 || hi - lo <= 1e-6f * hi) break;
+            if (fa < 0.f) { lo = alpha; flo = fa; if (side == -1) fhi *= 0.5f; side = -1; }
+            else { hi = alpha; fhi = fa; if (side == 1) flo *= 0.5f; side = 1; }
+          }
+        }
+        for (int i = lane; i < nv; i += 32) e.qacc[i] += alpha * e.dir[i];
+        __syncwarp();
+      }
+      // forces at the solution
+      for (int r = lane; r < ne; r += 32) { float t = -e.aref[r]; for (int i = 0; i < nv; i++) t += e.J[r][i] * e.qacc[i]; e.jar[r] = t; }
+      __syncwarp();
+      g_rows(m, e, e.jar, false, lane);
+      __syncwarp();
+      for (int i = lane; i < nv; i += 32) { float t = 0.f; for (int r = 0; r < ne; r++) t += e.J[r][i] * e.force[r]; e.fcon[i] = t; }
+      __syncwarp();
+    }
+    niter_last = niter;
+    for (int i = lane; i < nv; i += 32) e.warm[i] = e.qacc[i];
+    // ------------------------------------------------------------------ P11 Euler with implicit joint damping, position integration
+    {
+      bool any_damp = false;
+      for (int i = lane; i < nv; i += 32) any_damp |= m.dof_damping[i] > 0.f;
+      any_damp = __any_sync(0xffffffffu, any_damp) && m.eulerdamp;
+      if (any_damp) {
+        for (int idx = lane; idx < nv * nv; idx += 32) { const int i = idx / nv, k = idx % nv; e.H[i][k] = e.M[i][k] + (i == k ? h * m.dof_damping[i] : 0.f); }
+        for (int i = lane; i < nv; i += 32) e.vec[i] = e.smooth[i] + e.fcon[i];
+        __syncwarp();
+        g_cholesky(e.H, e.H, nv, lane);
+        g_cholsolve(e.H, nv, e.vec, lane);
+      } else {
+        for (int i = lane; i < nv; i += 32) e.vec[i] = e.qacc[i];
+        __syncwarp();
+      }
+      for (int i = lane; i < nv; i += 32) e.qvel[i] += h * e.vec[i];
+      __syncwarp();
+      if (lane == 0) {
+        for (int k = 0; k < 3; k++) e.qpos[k] += h * e.qvel[k];
+        float w[3] = {e.qvel[3], e.qvel[4], e.qvel[5]};
+        const float wn = sqrtf(g_dot3(w, w));
+        float quat[4] = {e.qpos[3], e.qpos[4], e.qpos[5], e.qpos[6]};
+        g_normquat(quat);
+        if (wn >= 1e-15f) {
+          float s, c;
+          sincosf(0.5f * h * wn, &s, &c);
+          const float qr[4] = {c, w[0] / wn * s, w[1] / wn * s, w[2] / wn * s};
+          float qn[4];
+          g_mulquat(qn, quat, qr);
+          for (int k = 0; k < 4; k++) quat[k] = qn[k];
+        }
+        for (int k = 0; k < 4; k++) e.qpos[3 + k] = quat[k];
+      }
+      for (int b = 2 + lane; b < nb; b += 32) e.qpos[m.body_qadr[b]] += h * e.qvel[m.body_dofadr[b]];
+      __syncwarp();
+    }
+  }
+  for (int i = lane; i < nq; i += 32) A.qpos[(size_t)env * nq + i] = e.qpos[i];
+  for (int i = lane; i < nv; i += 32) { A.qvel[(size_t)env * nv + i] = e.qvel[i]; A.warm[(size_t)env * nv + i] = e.warm[i]; }
+  if (A.info != nullptr && lane == 0) {
+    A.info[(size_t)env * 4] = e.ncon; A.info[(size_t)env * 4 + 1] = e.nefc; A.info[(size_t)env * 4 + 2] = niter_last; A.info[(size_t)env * 4 + 3] = e.overflow;
+  }
+}
+
+// ================================================================================================ host side
+namespace {
+struct Arr { const unsigned char* data = nullptr; int code = -1; long long count = 0; };
+bool find(const std::vector<unsigned char>& raw, const char* name, Arr& out) {
+  if (raw.size() < 8 || memcmp(raw.data(), "NMB1", 4) != 0) return false;
+  unsigned cnt;
+  memcpy(&cnt, raw.data() + 4, 4);
+  size_t off = 8;
+  for (unsigned i = 0; i < cnt; i++) {
+    if (off + 80 > raw.size()) return false;
+    const char* nm = reinterpret_cast<const char*>(raw.data() + off);
+    unsigned code, nd;
+    long long dims[4], nbytes;
+    memcpy(&code, raw.data() + off + 32, 4);
+    memcpy(&nd, raw.data() + off + 36, 4);
+    memcpy(dims, raw.data() + off + 40, 32);
+    memcpy(&nbytes, raw.data() + off + 72, 8);
+    off += 80;
+    if (off + (size_t)nbytes > raw.size()) return false;
+    if (strncmp(nm, name, 32) == 0) {
+      out.data = raw.data() + off; out.code = (int)code; out.count = 1;
+      for (unsigned k = 0; k < nd; k++) out.count *= dims[k];
+      return true;
+    }
+    off += (size_t)nbytes + (size_t)((8 - nbytes % 8) % 8);
+  }
+  return false;
+}
+void q2m(const double* q, double* mtx) {
+  const double w = q[0], x = q[1], y = q[2], z = q[3];
+  mtx[0] = w * w + x * x - y * y - z * z; mtx[1] = 2 * (x * y - w * z); mtx[2] = 2 * (x * z + w * y);
+  mtx[3] = 2 * (x * y + w * z); mtx[4] = w * w - x * x + y * y - z * z; mtx[5] = 2 * (y * z - w * x);
+  mtx[6] = 2 * (x * z - w * y); mtx[7] = 2 * (y * z + w * x); mtx[8] = w * w - x * x - y * y + z * z;
+}
+double clampd(double x) { return x < 0.0001 ? 0.0001 : (x > 0.9999 ? 0.9999 : x); }
+void kb(double timestep, const double* solref, const double* solimp, double& K, double& B) {
+  double tc = solref[0], dr = solref[1], dmax = clampd(solimp[1]);
+  if (tc > 0) { if (tc < 2 * timestep) tc = 2 * timestep; K = 1.0 / (dmax * dmax * tc * tc * dr * dr); B = 2.0 / (dmax * tc); }
+  else { K = -tc / (dmax * dmax); B = -dr / dmax; }
+}
+}  // namespace
+
+struct nm_gen_model { GenModel host; std::vector<float> qpos0; };
+struct nm_gen_batch { const nm_gen_model* model; GenModel* d_model; int n, device; GenArgs args; int64_t launches; };
+
+extern "C" int nm_gen_model_from_buffer(const void* data, size_t nbytes, nm_gen_model** out) {
+  if (!data || !out || nbytes < 8) return nm_fail(NM_ERR_ARG, "nm_gen_model_from_buffer: bad argument");
+  std::vector<unsigned char> raw((const unsigned char*)data, (const unsigned char*)data + nbytes);
+#define GET(var, name, type, code_)                                                                       \
+  const type* var = nullptr;                                                                             \
+  { Arr a_; if (!find(raw, name, a_) || a_.code != code_) return nm_fail(NM_ERR_FORMAT, std::string("nmb: missing array '") + name + "'"); var = (const type*)a_.data; }
+  GET(sizes, "sizes", int, 2) GET(oi, "opt_int", int, 2) GET(orl, "opt_real", double, 0) GET(qpos0, "qpos0", double, 0)
+  GET(body_parent, "body_parent", int, 2) GET(body_jntadr, "body_jntadr", int, 2) GET(body_jntnum, "body_jntnum", int, 2)
+  GET(body_dofadr, "body_dofadr", int, 2) GET(body_dofnum, "body_dofnum", int, 2)
+  GET(body_pos, "body_pos", double, 0) GET(body_quat, "body_quat", double, 0) GET(body_ipos, "body_ipos", double, 0) GET(body_iquat, "body_iquat", double, 0)
+  GET(body_mass, "body_mass", double, 0) GET(body_inertia, "body_inertia", double, 0) GET(body_invweight0, "body_invweight0", double, 0)
+  GET(jnt_type, "jnt_type", int, 2) GET(jnt_qposadr, "jnt_qposadr", int, 2) GET(jnt_dofadr, "jnt_dofadr", int, 2) GET(jnt_pos, "jnt_pos", double, 0)
+  GET(jnt_axis, "jnt_axis", double, 0) GET(jnt_limited, "jnt_limited", int, 2) GET(jnt_range, "jnt_range", double, 0)
+  GET(dof_body, "dof_body", int, 2) GET(dof_parent, "dof_parent", int, 2) GET(dof_damping, "dof_damping", double, 0)
+  GET(dof_frictionloss, "dof_frictionloss", double, 0) GET(dof_armature, "dof_armature", double, 0) GET(dof_invweight0, "dof_invweight0", double, 0)
+  GET(act_dof, "act_dof", int, 2) GET(act_gain, "act_gain", double, 0) GET(act_bias, "act_bias", double, 0) GET(act_gear, "act_gear", double, 0)
+  GET(act_ctrlrange, "act_ctrlrange", double, 0) GET(act_ctrllimited, "act_ctrllimited", int, 2) GET(act_forcerange, "act_forcerange", double, 0)
+  GET(act_forcelimited, "act_forcelimited", int, 2)
+  GET(geom_type, "geom_type", int, 2) GET(geom_body, "geom_body", int, 2) GET(geom_condim, "geom_condim", int, 2) GET(geom_priority, "geom_priority", int, 2)
+  GET(geom_plane, "geom_plane", int, 2) GET(geom_pos, "geom_pos", double, 0) GET(geom_quat, "geom_quat", double, 0) GET(geom_size, "geom_size", double, 0)
+  GET(geom_friction, "geom_friction", double, 0) GET(geom_solref, "geom_solref", double, 0) GET(geom_solimp, "geom_solimp", double, 0)
+  GET(geom_margin, "geom_margin", double, 0) GET(geom_gap, "geom_gap", double, 0)
+#undef GET
+  nm_gen_model* gm = new nm_gen_model();
+  GenModel& M = gm->host;
+  memset(&M, 0, sizeof(M));
+  const int nq = sizes[0], nv = sizes[1], nu = sizes[2], nbody = sizes[3], njnt = sizes[4], ngeom_all = sizes[5];
+  auto bail = [&](int code, const char* msg) { delete gm; return nm_fail(code, msg); };
+  if (nbody > GM_MAXB || nv > GM_MAXV || nq > GM_MAXQ || nu > GM_MAXU) return bail(NM_ERR_UNSUPPORTED, "generic step: model too large (<= 15 bodies, 24 dofs, 18 actuators)");
+  if (oi[1] != 2) return bail(NM_ERR_UNSUPPORTED, "generic step: this path implements solver=\"Newton\" (PGS models use nm_model_from_buffer / nm_step)");
+  if (oi[0] != 0) return bail(NM_ERR_UNSUPPORTED, "generic step: only integrator=\"Euler\" is implemented");
+  if (oi[2] != 1) return bail(NM_ERR_UNSUPPORTED, "generic step: only cone=\"elliptic\" is implemented with the Newton solver");
+  if (nbody < 2 || body_parent[1] != 0 || body_jntnum[1] != 1 || jnt_type[body_jntadr[1]] != 0) return bail(NM_ERR_UNSUPPORTED, "generic step: body 1 must be a free-floating base");
+  M.nq = nq; M.nv = nv; M.nu = nu; M.nbody = nbody;
+  M.integrator = oi[0]; M.cone = oi[2]; M.iterations = oi[3]; M.eulerdamp = oi[5];
+  M.timestep = (float)orl[0]; for (int k = 0; k < 3; k++) M.gravity[k] = (float)orl[1 + k];
+  M.tolerance = (float)orl[4]; M.impratio = (float)orl[6];
+  M.solver_scale = (float)(1.0 / (orl[7] * (nv > 1 ? nv : 1)));
+  for (int i = 0; i < nq; i++) M.qpos0[i] = (float)qpos0[i];
+  gm->qpos0.assign(M.qpos0, M.qpos0 + nq);
+  M.body_dofadr[0] = -1; M.body_qadr[0] = -1;
+  for (int b = 1; b < nbody; b++) {
+    if (body_jntnum[b] != 1) return bail(NM_ERR_UNSUPPORTED, "generic step: every body needs exactly one joint");
+    const int j = body_jntadr[b];
+    if (b > 1 && jnt_type[j] != 3) return bail(NM_ERR_UNSUPPORTED, "generic step: joints other than the base's free joint must be hinges");
+    if (b > 1 && body_parent[b] >= b) return bail(NM_ERR_UNSUPPORTED, "generic step: bodies must come after their parents");
+    for (int k = 0; k < 3; k++) if (std::fabs(jnt_pos[3 * j + k]) > 1e-12) return bail(NM_ERR_UNSUPPORTED, "generic step: joint anchors must sit at the body origin");
+    M.body_parent[b] = body_parent[b];
+    M.body_depth[b] = M.body_depth[body_parent[b]] + 1;
+    if (M.body_depth[b] > M.maxdepth) M.maxdepth = M.body_depth[b];
+    M.body_dofadr[b] = jnt_dofadr[j]; M.body_qadr[b] = jnt_qposadr[j];
+    for (int k = 0; k < 3; k++) { M.body_pos[b][k] = (float)body_pos[3 * b + k]; M.body_ipos[b][k] = (float)body_ipos[3 * b + k]; M.body_inertia[b][k] = (float)body_inertia[3 * b + k]; M.jnt_axis[b][k] = (float)jnt_axis[3 * j + k]; }
+    for (int k = 0; k < 4; k++) { M.body_quat[b][k] = (float)body_quat[4 * b + k]; M.body_iquat[b][k] = (float)body_iquat[4 * b + k]; }
+    M.body_mass[b] = (float)body_mass[b];
+    M.body_invw[b][0] = (float)body_invweight0[2 * b]; M.body_invw[b][1] = (float)body_invweight0[2 * b + 1];
+    M.jnt_limited[b] = b > 1 ? jnt_limited[j] : 0;
+    M.jnt_range[b][0] = (float)jnt_range[2 * j]; M.jnt_range[b][1] = (float)jnt_range[2 * j + 1];
+  }
+  (void)body_dofnum; (void)njnt;
+  int nfl = 0;
+  for (int i = 0; i < nv; i++) {
+    M.dof_body[i] = dof_body[i]; M.dof_parent[i] = dof_parent[i];
+    M.dof_damping[i] = (float)dof_damping[i]; M.dof_floss[i] = (float)dof_frictionloss[i]; M.dof_armature[i] = (float)dof_armature[i];
+    M.dof_invw[i] = (float)dof_invweight0[i];
+    M.dof_flossrow[i] = dof_frictionloss[i] > 0 ? nfl++ : -1;
+  }
+  M.nfloss = nfl;
+  for (int b = 1; b < nbody; b++) {                    // dofs that move body b: its own chain
+    int mask = 0;
+    for (int i = M.body_dofadr[b] + (b == 1 ? 5 : 0); i >= 0; i = dof_parent[i]) mask |= 1 << i;
+    M.body_dofmask[b] = mask;
+  }
+  std::vector<int> used(nv, 0);
+  for (int a = 0; a < nu; a++) {
+    const int dof = act_dof[a];
+    if (dof < 6 || dof >= nv || used[dof]++) return bail(NM_ERR_UNSUPPORTED, "generic step: one actuator per hinge dof");
+    M.act_dof[a] = dof; M.act_qadr[a] = M.body_qadr[dof_body[dof]];
+    M.act_gain0[a] = (float)act_gain[3 * a];
+    for (int k = 0; k < 3; k++) M.act_bias[a][k] = (float)act_bias[3 * a + k];
+    M.act_gear[a] = (float)act_gear[a];
+    M.act_ctrllimited[a] = act_ctrllimited[a]; M.act_forcelimited[a] = act_forcelimited[a];
+    for (int k = 0; k < 2; k++) { M.act_ctrlrange[a][k] = (float)act_ctrlrange[2 * a + k]; M.act_forcerange[a][k] = (float)act_forcerange[2 * a + k]; }
+  }
+  // plane and the geoms that collide with it
+  int plane = -1;
+  for (int g = 0; g < ngeom_all; g++) if (geom_type[g] == 0) { if (plane >= 0 || geom_body[g] != 0) return bail(NM_ERR_UNSUPPORTED, "generic step: exactly one world-fixed plane"); plane = g; }
+  if (plane < 0) return bail(NM_ERR_UNSUPPORTED, "generic step: the model needs a ground plane");
+  {
+    double R[9];
+    q2m(geom_quat + 4 * plane, R);
+    double n[3] = {R[2], R[5], R[8]}, fr[9] = {n[0], n[1], n[2], 0, 0, 0, 0, 0, 0};
+    if (n[1] < 0.5 && n[1] > -0.5) fr[4] = 1; else fr[5] = 1;
+    const double dd = fr[0] * fr[3] + fr[1] * fr[4] + fr[2] * fr[5];
+    for (int c = 0; c < 3; c++) fr[3 + c] -= dd * fr[c];
+    const double nn = std::sqrt(fr[3] * fr[3] + fr[4] * fr[4] + fr[5] * fr[5]);
+    for (int c = 0; c < 3; c++) fr[3 + c] /= nn;
+    fr[6] = fr[1] * fr[5] - fr[2] * fr[4]; fr[7] = fr[2] * fr[3] - fr[0] * fr[5]; fr[8] = fr[0] * fr[4] - fr[1] * fr[3];
+    for (int c = 0; c < 9; c++) M.plane_frame[c] = (float)fr[c];
+    for (int c = 0; c < 3; c++) { M.plane_n[c] = (float)n[c]; M.plane_pos[c] = (float)geom_pos[3 * plane + c]; }
+  }
+  int ng = 0;
+  for (int g = 0; g < ngeom_all; g++) {
+    if (g == plane || geom_plane[g] < 0) continue;
+    if (geom_type[g] != G_SPHERE && geom_type[g] != G_BOX && geom_type[g] != G_CYLINDER) return bail(NM_ERR_UNSUPPORTED, "generic step: sphere / box / cylinder geoms only");
+    if (ng >= GM_MAXG) return bail(NM_ERR_UNSUPPORTED, "generic step: too many collision geoms");
+    const int p = plane;
+    double fr3[3], solref[2], solimp[5];
+    int dim;
+    if (geom_priority[g] == geom_priority[p]) {
+      for (int k = 0; k < 3; k++) fr3[k] = std::fmax(geom_friction[3 * g + k], geom_friction[3 * p + k]);
+      dim = geom_condim[g] > geom_condim[p] ? geom_condim[g] : geom_condim[p];
+      for (int k = 0; k < 2; k++) solref[k] = 0.5 * (geom_solref[2 * g + k] + geom_solref[2 * p + k]);
+      for (int k = 0; k < 5; k++) solimp[k] = 0.5 * (geom_solimp[5 * g + k] + geom_solimp[5 * p + k]);
+    } else {
+      const int w = geom_priority[g] > geom_priority[p] ? g : p;
+      for (int k = 0; k < 3; k++) fr3[k] = geom_friction[3 * w + k];
+      dim = geom_condim[w];
+      for (int k = 0; k < 2; k++) solref[k] = geom_solref[2 * w + k];
+      for (int k = 0; k < 5; k++) solimp[k] = geom_solimp[5 * w + k];
+    }
+    if (dim != 1 && dim != 3 && dim != 4 && dim != 6) return bail(NM_ERR_UNSUPPORTED, "generic step: condim must be 1, 3, 4 or 6");
+    M.geom_type[ng] = geom_type[g]; M.geom_body[ng] = geom_body[g]; M.geom_dim[ng] = dim;
+    double R[9];
+    q2m(geom_quat + 4 * g, R);
+    for (int k = 0; k < 9; k++) M.geom_mat[ng][k] = (float)R[k];
+    for (int k = 0; k < 3; k++) { M.geom_pos[ng][k] = (float)geom_pos[3 * g + k]; M.geom_size[ng][k] = (float)geom_size[3 * g + k]; }
+    M.geom_margin[ng] = (float)(std::fmax(geom_margin[g], geom_margin[p]) - std::fmax(geom_gap[g], geom_gap[p]));
+    M.geom_friction[ng][0] = M.geom_friction[ng][1] = (float)fr3[0]; M.geom_friction[ng][2] = (float)fr3[1]; M.geom_friction[ng][3] = M.geom_friction[ng][4] = (float)fr3[2];
+    double K, B;
+    kb(orl[0], solref, solimp, K, B);
+    M.geom_K[ng] = (float)K; M.geom_B[ng] = (float)B;
+    M.geom_solimp[ng][0] = (float)clampd(solimp[0]); M.geom_solimp[ng][1] = (float)clampd(solimp[1]); M.geom_solimp[ng][2] = (float)solimp[2];
+    M.geom_solimp[ng][3] = (float)clampd(solimp[3]); M.geom_solimp[ng][4] = (float)(solimp[4] < 1 ? 1 : solimp[4]);
+    ng++;
+  }
+  M.ngeom = ng;
+  {
+    const double dref[2] = {0.02, 1.0}, dimp[5] = {0.9, 0.95, 0.001, 0.5, 2.0};
+    double K, B;
+    kb(orl[0], dref, dimp, K, B);
+    M.lim_K = (float)K; M.lim_B = (float)B; M.lim_imp0 = (float)dimp[0];
+    for (int k = 0; k < 5; k++) M.lim_solimp[k] = (float)dimp[k];
+  }
+  *out = gm;
+  return NM_OK;
+}
+
+extern "C" void nm_gen_model_destroy(nm_gen_model* m) { delete m; }
+extern "C" int nm_gen_model_size(const nm_gen_model* m, const char* what) {
+  if (!m || !what) return -1;
+  const GenModel& M = m->host;
+  if (!strcmp(what, "nq")) return M.nq;
+  if (!strcmp(what, "nv")) return M.nv;
+  if (!strcmp(what, "nu")) return M.nu;
+  if (!strcmp(what, "nbody")) return M.nbody;
+  if (!strcmp(what, "ngeom")) return M.ngeom;
+  return -1;
+}
+extern "C" double nm_gen_model_timestep(const nm_gen_model* m) { return m ? m->host.timestep : 0.0; }
+extern "C" int nm_gen_model_qpos0(const nm_gen_model* m, float* out, int cap) {
+  if (!m || !out) return -1;
+  const int n = (int)m->qpos0.size();
+  for (int i = 0; i < n && i < cap; i++) out[i] = m->qpos0[i];
+  return n;
+}
+
+extern "C" int nm_gen_batch_create(const nm_gen_model* m, int num_envs, int device, float* qpos, float* qvel, float* warm, int32_t* info, nm_gen_batch** out) {
+  if (!m || !out || num_envs <= 0 || !qpos || !qvel || !warm) return nm_fail(NM_ERR_ARG, "nm_gen_batch_create: bad argument");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return nm_fail(NM_ERR_CUDA, "no such CUDA device");
+  nm_gen_batch* b = new nm_gen_batch();
+  memset(b, 0, sizeof(*b));
+  b->model = m; b->n = num_envs; b->device = device;
+  if (cudaSetDevice(device) != cudaSuccess || cudaMalloc(&b->d_model, sizeof(GenModel)) != cudaSuccess ||
+      cudaMemcpy(b->d_model, &m->host, sizeof(GenModel), cudaMemcpyHostToDevice) != cudaSuccess ||
+      cudaFuncSetAttribute(nm_generic_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(EnvMem) * GM_WARPS)) != cudaSuccess) {
+    if (b->d_model) cudaFree(b->d_model);
+    delete b;
+    return nm_fail(NM_ERR_CUDA, "nm_gen_batch_create: CUDA allocation failed");
+  }
+  b->args.model = b->d_model; b->args.qpos = qpos; b->args.qvel = qvel; b->args.warm = warm; b->args.info = info; b->args.num_envs = num_envs;
+  *out = b;
+  return NM_OK;
+}
+extern "C" void nm_gen_batch_destroy(nm_gen_batch* b) {
+  if (!b) return;
+  cudaFree(b->d_model);
+  delete b;
+}
+extern "C" int nm_gen_physics_step(nm_gen_batch* b, const float* ctrl, int nstep, nm_stream stream) {
+  if (!b || !ctrl || nstep < 1) return nm_fail(NM_ERR_ARG, "nm_gen_physics_step: bad argument");
+  int prev = -1;
+  cudaGetDevice(&prev);
+  if (prev != b->device) cudaSetDevice(b->device);
+  GenArgs a = b->args;
+  a.ctrl = ctrl; a.nstep = nstep;
+  const int blocks = (b->n + GM_WARPS - 1) / GM_WARPS;
+  nm_generic_step_kernel<<<blocks, GM_WARPS * 32, sizeof(EnvMem) * GM_WARPS, static_cast<cudaStream_t>(stream)>>>(a);
+  b->launches++;
+  const cudaError_t err = cudaGetLastError();
+  if (prev >= 0 && prev != b->device) cudaSetDevice(prev);
+  if (err != cudaSuccess) return nm_fail(NM_ERR_CUDA, std::string("nm_gen_physics_step: ") + cudaGetErrorString(err));
+  return NM_OK;
+}
+extern "C" int64_t nm_gen_batch_launches(const nm_gen_batch* b) { return b ? b->launches : 0; }

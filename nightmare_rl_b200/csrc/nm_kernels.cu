@@ -995,20 +995,11 @@ __global__ void __launch_bounds__(BLOCK, MINB) nm_step_kernel(const NmKernelArgs
     for (int i = 0; i < 6; i++) rb[i] = -bias_b[i];
     Factor F, FH;
     {
-#ifndef NM_FACTOR_TWICE
-      // ONE copy of the factorisation code, run twice (pass 0 -> F, pass 1 -> FH) instead of two inlined copies: the kernel
-      // is bound by instruction fetch, 600 fewer SASS instructions on the hot path buy 2.2 us per 4096-env step
-#pragma unroll 1
-      for (int pass = 0; pass < 2; pass++) {
-        const float dd[3] = {pass ? hD[0] : 0.f, pass ? hD[1] : 0.f, pass ? hD[2] : 0.f};
-        factor_system(Mk, C, Mbb, dd, FH);
-        if (pass == 0) F = FH;
-      }
-#else
+      // (a single copy of the factorisation run twice in a loop was 2 us faster and produced wrong in-contact results on the
+      // GPU -- gpurun_out/r02_t_default.log vs r02_t_ftwice.log -- so the two factorisations stay inlined)
       const float zero3[3] = {0.f, 0.f, 0.f};
       factor_system(Mk, C, Mbb, zero3, F);
       factor_system(Mk, C, Mbb, hD, FH);      // (M - h*qDeriv) for the implicit velocity update
-#endif
     }
     float xsb[6], xsk[3];                      // qacc_smooth
     solve_system(F, rb, rk, xsb, xsk);

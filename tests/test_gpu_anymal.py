@@ -1,0 +1,153 @@
+"""models/anymal_c of the reference (BASELINE configs[3]) on the CUDA path: `nm_gen_physics_step` (csrc/nm_generic.cu: Newton
+solver, elliptic cones with impratio 100, friction loss, joint limits, condim-6 feet, box / cylinder / sphere against the
+plane, Euler with implicit damping) against the oracle, substep by substep from identical fp32 states.
+
+≙ mj.mj_step(model, data[i], nstep) at envs/nightmare_v3_env.py:200 / simple_test.py:39 with model = models/anymal_c/scene.xml."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT
+from gpu_common import DEV, per_env_rel
+from nightmare_rl_b200 import _lib, mjcf
+from nightmare_rl_b200.batch import GenBatch
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+NMB = os.path.join(ROOT, "models", "anymal_c", "anymal_c.nmb")
+
+
+@pytest.fixture(scope="module")
+def trio():
+    cm = mjcf.CompiledModel.load(NMB)
+    return cm, _lib.GenModel(cm.to_bytes()), O.OracleModel(NMB), O.OracleModel(NMB, variant="f32")
+
+
+def _tumbling(cm, n, seed, low=False):
+    rng = np.random.default_rng(seed)
+    q = np.tile(cm.qpos0, (n, 1))
+    q[:, 2] = rng.uniform(0.25, 0.7, n) if low else rng.uniform(0.3, 0.8, n)
+    q[:, 3:7] = rng.normal(size=(n, 4))
+    q[:, 3:7] /= np.linalg.norm(q[:, 3:7], axis=1, keepdims=True)
+    q[:, 7:] += rng.uniform(-0.6, 0.6, (n, 12))
+    v = rng.normal(size=(n, 18)) * 0.5
+    return q, v, rng
+
+
+def _push(gb, q, v, w):
+    gb.qpos.copy_(torch.from_numpy(np.ascontiguousarray(q, dtype=np.float32)))
+    gb.qvel.copy_(torch.from_numpy(np.ascontiguousarray(v, dtype=np.float32)))
+    gb.warm.copy_(torch.from_numpy(np.ascontiguousarray(w, dtype=np.float32)))
+
+
+def test_model_loaders_name_each_other(trio):
+    cm = trio[0]
+    with pytest.raises(_lib.NightmareLibError, match="nm_gen"):
+        _lib.Model(cm.to_bytes())                                   # the PGS loader refuses the Newton model and says where it goes
+    from conftest import NMB as HEX
+    with pytest.raises(_lib.NightmareLibError, match="Newton"):
+        _lib.GenModel(mjcf.CompiledModel.load(HEX).to_bytes())
+    gm = trio[1]
+    assert (gm.size("nq"), gm.size("nv"), gm.size("nu"), gm.size("nbody")) == (19, 18, 12, 14)
+    assert abs(gm.timestep - 0.002) < 1e-9
+    np.testing.assert_allclose(gm.qpos0(), cm.qpos0.astype(np.float32))
+
+
+def test_stands_on_four_feet(trio):
+    cm, gm, om, _ = trio
+    gb = GenBatch(gm, 4, DEV)
+    ob = O.OracleBatch(om, 1)
+    ctrl = torch.zeros(4, 12, device=DEV)
+    gb.physics_step(ctrl, 1500)
+    ob.physics_step(np.zeros((1, 12)), 1500)
+    q, v = gb.qpos.cpu().numpy(), gb.qvel.cpu().numpy()
+    qo, vo, _ = ob.get_state()
+    info = gb.info.cpu().numpy()
+    assert (info[:, 0] == 4).all() and (info[:, 1] == 12 + 24).all() and (info[:, 3] == 0).all()
+    assert np.abs(v).max() < 5e-3 and np.abs(q - qo).max() < 2e-3, (np.abs(v).max(), np.abs(q - qo).max())
+    assert np.abs(q - q[0]).max() == 0.0                            # identical environments stay bit-identical
+
+
+@pytest.mark.parametrize("seed", [0, 1])
+def test_tumbling_lockstep(trio, seed):
+    """One substep at a time from states both sides share bit for bit (fp32-rounded): constraint counts identical, velocities
+    within the fp32 rounding floor measured with the oracle's own source compiled in float arithmetic."""
+    cm, gm, om, om32 = trio
+    n, rounds = 256, 120
+    q, v, rng = _tumbling(cm, n, seed, low=True)
+    ob, fb, gb = O.OracleBatch(om, n), O.OracleBatch(om32, n), GenBatch(gm, n, DEV)
+    ob.set_state(q, v, np.zeros((n, 18)))
+    ctrl = rng.uniform(-1, 1, (n, 12))
+    ctrl_d = torch.from_numpy(ctrl.astype(np.float32)).to(DEV)
+    ctrl = ctrl.astype(np.float32).astype(np.float64)
+    errs, ferrs, ncon_hist, mism, iters = [], [], [], 0, []
+    for it in range(rounds):
+        q, v, w = ob.get_state()
+        q32, v32, w32 = q.astype(np.float32), v.astype(np.float32), w.astype(np.float32)
+        ob.set_state(q32, v32, w32)
+        fb.set_state(q32, v32, w32)
+        _push(gb, q32, v32, w32)
+        ob.physics_step(ctrl, 1, 8)
+        fb.physics_step(ctrl, 1, 8)
+        gb.physics_step(ctrl_d, 1)
+        qo, vo, wo = ob.get_state()
+        qf, vf, _ = fb.get_state()
+        qg, vg = gb.qpos.cpu().numpy().astype(np.float64), gb.qvel.cpu().numpy().astype(np.float64)
+        info = gb.info.cpu().numpy()
+        assert (info[:, 3] == 0).all()
+        nefc = np.array([int(ob.get(i, "nefc")[0]) for i in range(n)])
+        ncon = np.array([ob.get(i, "contact").reshape(-1, 7).shape[0] for i in range(n)])
+        same = (info[:, 1] == nefc) & (info[:, 0] == ncon)
+        mism += int((~same).sum())                                   # a geom within fp32 rounding of its margin
+        errs.append(per_env_rel(vg, vo)[same]); ferrs.append(per_env_rel(vf, vo)[same])
+        errs.append(per_env_rel(qg, qo)[same])
+        ncon_hist.append(ncon); iters.append(info[:, 2])
+    e, f = np.concatenate(errs), np.concatenate(ferrs)
+    ncon_all = np.concatenate(ncon_hist)
+    print(f"\n[anymal lockstep seed {seed}] env-substeps {n * rounds} in contact {int((ncon_all > 0).sum())} max ncon {ncon_all.max()} "
+          f"count mismatches {mism} | CUDA median {np.median(e):.2e} p99 {np.percentile(e, 99):.2e} max {e.max():.2e} | "
+          f"fp32 oracle median {np.median(f):.2e} p99 {np.percentile(f, 99):.2e} max {f.max():.2e} | Newton iterations mean {np.mean(iters):.2f} max {np.max(iters)}")
+    assert (ncon_all > 0).sum() > 0.3 * n * rounds and ncon_all.max() >= 6
+    assert mism <= 0.002 * n * rounds
+    # north_star: <= 1e-5 relative after one step.  Median and 99th percentile meet it; the worst env-substeps are bounded by the
+    # fp32 floor of the same arithmetic (the oracle's own source in float), as for the hexapod (profiles/r02_fp32_floor.md).
+    assert np.median(e) < 1e-6 and np.percentile(e, 99) < max(1e-5, 2 * np.percentile(f, 99))
+    assert e.max() < max(1e-5, 4 * f.max())
+
+
+def test_free_running_matches_oracle(trio):
+    """200 substeps (0.4 s) of free-running tumbling / landing robots: the trajectories stay together on non-chaotic envs."""
+    cm, gm, om, _ = trio
+    n = 64
+    q, v, rng = _tumbling(cm, n, 5)
+    q[:, 3:7] = [1, 0, 0, 0]
+    q[:, 2] = rng.uniform(0.55, 0.75, n)                              # upright drops onto the feet: well conditioned
+    v *= 0.2
+    ob, gb = O.OracleBatch(om, n), GenBatch(gm, n, DEV)
+    q32, v32 = q.astype(np.float32), v.astype(np.float32)
+    ob.set_state(q32, v32, np.zeros((n, 18)))
+    _push(gb, q32, v32, np.zeros((n, 18)))
+    ctrl = rng.uniform(-0.3, 0.3, (n, 12)).astype(np.float32)
+    ob.physics_step(ctrl.astype(np.float64), 200, 8)
+    gb.physics_step(torch.from_numpy(ctrl).to(DEV), 200)
+    qo, vo, _ = ob.get_state()
+    err = per_env_rel(gb.qpos.cpu().numpy().astype(np.float64), qo)
+    print(f"\n[anymal free run] 200 substeps: qpos rel err median {np.median(err):.2e} max {err.max():.2e}")
+    assert np.median(err) < 1e-4 and np.percentile(err, 90) < 1e-3
+
+
+def test_nstep_equals_repeated_single_steps(trio):
+    cm, gm, _, _ = trio
+    n = 32
+    q, v, rng = _tumbling(cm, n, 9, low=True)
+    a, b = GenBatch(gm, n, DEV), GenBatch(gm, n, DEV)
+    for g in (a, b):
+        _push(g, q, v, np.zeros((n, 18)))
+    ctrl = torch.from_numpy(rng.uniform(-1, 1, (n, 12)).astype(np.float32)).to(DEV)
+    a.physics_step(ctrl, 4)
+    for _ in range(4):
+        b.physics_step(ctrl, 1)
+    assert torch.equal(a.qpos, b.qpos) and torch.equal(a.qvel, b.qvel) and torch.equal(a.warm, b.warm)
+    assert a.launches == 1 and b.launches == 4

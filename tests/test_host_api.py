@@ -134,8 +134,9 @@ def test_second_model_through_compiler_and_loader():
     """BASELINE configs[3] names anymal_c as the model that exercises the generic compiler / loader.  Its MJCF (includes,
     nested default classes, explicit inertials, primitive collision geoms, position actuators; reference
     models/anymal_c/anymal_c.xml) compiles to models/anymal_c/anymal_c.nmb in the same container format as the hexapod's.
-    Its STEP is not implemented (the kernels have no Newton solver / elliptic cones / condim 6 / joint limits /
-    frictionloss): nm_model_from_buffer must say so instead of simulating something else."""
+    Its step needs the Newton solver / elliptic cones / condim 6 / joint limits / frictionloss: the hexapod loader
+    nm_model_from_buffer must refuse it and name the loader that takes it (nm_gen_model_from_buffer, csrc/nm_generic.cu;
+    GPU parity in tests/test_gpu_anymal.py), which validates the model on the host without needing a GPU."""
     from conftest import ROOT
     from nightmare_rl_b200 import _lib, mjcf
     path = os.path.join(ROOT, "models", "anymal_c", "anymal_c.nmb")
@@ -148,7 +149,12 @@ def test_second_model_through_compiler_and_loader():
     # the C ABI validates a model against what the step kernels implement when it builds the device image: refused, with the reason
     with pytest.raises(_lib.NightmareLibError) as ei:
         _lib.Model(cm.to_bytes())
-    assert 'only solver="PGS" is implemented' in str(ei.value)
+    assert 'only solver="PGS" is implemented' in str(ei.value) and "nm_gen_model_from_buffer" in str(ei.value)
+    gm = _lib.GenModel(cm.to_bytes())                              # host-side validation + packing only: no CUDA call
+    assert (gm.size("nq"), gm.size("nv"), gm.size("nu"), gm.size("nbody"), gm.size("ngeom")) == (19, 18, 12, 14, 44)
+    assert abs(gm.timestep - 0.002) < 1e-9 and np.allclose(gm.qpos0(), cm.qpos0)
+    with pytest.raises(_lib.NightmareLibError, match="Newton"):
+        _lib.GenModel(open(os.path.join(ROOT, "models", "nightmare_v3", "mjmodel.nmb"), "rb").read())
     if os.path.isdir("/root/reference/models/anymal_c"):         # the committed file is what the compiler produces from the reference MJCF
         fresh = mjcf.compile_mjcf("/root/reference/models/anymal_c/scene.xml")
         assert set(fresh.arrays) == set(cm.arrays)
