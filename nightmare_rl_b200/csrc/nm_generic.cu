@@ -30,9 +30,11 @@ int nm_fail(int code, const std::string& msg);   // nm_abi.cu
 #define GM_MAXQ 25
 #define GM_MAXU 18
 #define GM_MAXG 48     // collision geoms (plane excluded)
-#define GM_MAXCON 16
+#define GM_MAXCON 16   // first tier: contacts / constraint rows per environment held in shared memory
 #define GM_MAXROW 72
 #define GM_WARPS 4     // environments per CTA
+#define GM_BIGCON 64   // second tier (same cap as the oracle's NMO_MAXCON); beyond it info[3] = 1 and the step is truncated
+#define GM_BIGROW 240
 
 enum { G_SPHERE = 2, G_CYLINDER = 5, G_BOX = 6 };
 enum { R_FRICTION = 0, R_LIMIT = 1, R_CONTACT = 3 };
@@ -63,6 +65,7 @@ struct GenModel {
 struct GenArgs {
   const GenModel* model;
   float* qpos; float* qvel; float* warm; const float* ctrl; int* info;   // info[N][4] = ncon, nefc, Newton iterations (last substep), overflow flag
+  int* ovf;                                                                // work list of the second tier: count, then (env, substeps left) pairs
   int num_envs, nstep;
 };
 
@@ -132,7 +135,13 @@ __device__ __forceinline__ float g_impedance(const float* si, float pos) {      
 }
 
 // ---------------------------------------------------------------------------------------------- per-environment shared memory
-struct EnvMem {
+template <int MC, int MR>
+struct EnvMemT {
+  // fp64 islands of the Newton solver: the iterate and the constraint residual jar = J qacc - aref.  On a sliding elliptic
+  // contact the force is Dm * mu * (mu * jar_n - mu * |friction . jar_t|) with Dm ~ 4e6 for the feet (impratio 100): the
+  // difference of two O(10) numbers has to be right to 1e-9 for a force good to 1e-3 N, which fp32 residuals miss by three
+  // orders of magnitude (measured: fp32 floor 1e-3 relative in qvel, with these two arrays in fp64 2.6e-6).
+  double xd[GM_MAXV], jar[MR], jt[MR];
   float qpos[GM_MAXQ + 3], qvel[GM_MAXV], warm[GM_MAXV], ctrl[GM_MAXU + 2];
   float xpos[GM_MAXB][3], xquat[GM_MAXB][4], xmat[GM_MAXB][9], xipos[GM_MAXB][3], ximat[GM_MAXB][9];
   float com[4];
@@ -142,13 +151,13 @@ struct EnvMem {
   float bias[GM_MAXV], smooth[GM_MAXV], qaccs[GM_MAXV], qacc[GM_MAXV], grad[GM_MAXV], dir[GM_MAXV], Ma[GM_MAXV], vec[GM_MAXV], fcon[GM_MAXV];
   // contacts
   int ncon, nefc, nlim, overflow;
-  float cpos[GM_MAXCON][3], cdist[GM_MAXCON], cmu[GM_MAXCON];
-  int cgeom[GM_MAXCON], cadr[GM_MAXCON], cdim[GM_MAXCON], czone[GM_MAXCON];
-  float chess[GM_MAXCON][36];
+  float cpos[MC][3], cdist[MC], cmu[MC];
+  int cgeom[MC], cadr[MC], cdim[MC], czone[MC];
+  float chess[MC][36];
   // rows
-  float J[GM_MAXROW][GM_MAXV];
-  float aref[GM_MAXROW], D[GM_MAXROW], R[GM_MAXROW], jar[GM_MAXROW], jv[GM_MAXROW], force[GM_MAXROW], Hd[GM_MAXROW], floss[GM_MAXROW];
-  int rtype[GM_MAXROW], rid[GM_MAXROW];
+  float J[MR][GM_MAXV];
+  float aref[MR], D[MR], R[MR], jv[MR], force[MR], Hd[MR], floss[MR];
+  int rtype[MR], rid[MR];
 };
 
 // dense Cholesky of the nv x nv matrix A (lower triangle used) into Lo, by the whole warp; returns false if not positive definite
@@ -192,11 +201,12 @@ __device__ void g_cholsolve(const float (*Lo)[GM_MAXV], int n, float* x, int lan
 }
 
 // constraint forces, cost and (optionally) curvature at jar: friction-loss / limit rows one per lane, contacts one per lane
-__device__ float g_rows(const GenModel& m, EnvMem& e, const float* jar, bool hess, int lane) {
+template <class EnvMem>
+__device__ float g_rows(const GenModel& m, EnvMem& e, const double* jar, bool hess, int lane) {
   float cost = 0.f;
   const int nsimple = m.nfloss + e.nlim;
   for (int r = lane; r < nsimple; r += 32) {
-    const float D = e.D[r], R = e.R[r], j = jar[r];
+    const float D = e.D[r], R = e.R[r], j = (float)jar[r];
     float hd = 0.f;
     if (e.rtype[r] == R_FRICTION) {
       const float fl = e.floss[r], bound = R * fl;
@@ -213,28 +223,31 @@ __device__ float g_rows(const GenModel& m, EnvMem& e, const float* jar, bool hes
     const int a = e.cadr[c], dim = e.cdim[c];
     const float mu = e.cmu[c];
     const float* fri = m.geom_friction[e.cgeom[c]];
+    double Ud[6];
+    Ud[0] = jar[a] * (double)mu;
+    double T2d = 0.0;
+    for (int j = 1; j < dim; j++) { Ud[j] = jar[a + j] * (double)fri[j - 1]; T2d += Ud[j] * Ud[j]; }
+    const double Nd = Ud[0], Td = sqrt(T2d);
     float U[6];
-    U[0] = jar[a] * mu;
-    float T2 = 0.f;
-    for (int j = 1; j < dim; j++) { U[j] = jar[a + j] * fri[j - 1]; T2 += U[j] * U[j]; }
-    const float N = U[0], T = sqrtf(T2);
+    for (int j = 0; j < dim; j++) U[j] = (float)Ud[j];
+    const float T2 = (float)T2d, T = (float)Td;
     int zone;
     if (dim == 1) {
-      zone = jar[a] < 0.f ? 1 : 0;
-    } else if (N >= mu * T || (T <= 0.f && N >= 0.f)) zone = 0;
-    else if (mu * N + T <= 0.f || (T <= 0.f && N < 0.f)) zone = 1;
+      zone = jar[a] < 0.0 ? 1 : 0;
+    } else if (Nd >= (double)mu * Td || (Td <= 0.0 && Nd >= 0.0)) zone = 0;
+    else if ((double)mu * Nd + Td <= 0.0 || (Td <= 0.0 && Nd < 0.0)) zone = 1;
     else zone = 2;
     if (zone == 0) {
       for (int j = 0; j < dim; j++) { e.force[a + j] = 0.f; if (hess) e.Hd[a + j] = 0.f; }
     } else if (zone == 1) {
       for (int j = 0; j < dim; j++) {
-        const float Dj = e.D[a + j], jj = jar[a + j];
+        const float Dj = e.D[a + j], jj = (float)jar[a + j];
         e.force[a + j] = -Dj * jj;
         cost += 0.5f * Dj * jj * jj;
         if (hess) e.Hd[a + j] = Dj;
       }
     } else {
-      const float Dm = e.D[a] / (mu * mu * (1.f + mu * mu)), NmT = N - mu * T;
+      const float Dm = e.D[a] / (mu * mu * (1.f + mu * mu)), NmT = (float)(Nd - (double)mu * Td);
       cost += 0.5f * Dm * NmT * NmT;
       const float f0 = -Dm * NmT * mu;
       e.force[a] = f0;
@@ -259,23 +272,33 @@ __device__ float g_rows(const GenModel& m, EnvMem& e, const float* jar, bool hes
 }
 
 // ================================================================================================ the kernel
-__global__ void __launch_bounds__(GM_WARPS * 32) nm_generic_step_kernel(const GenArgs A) {
+// Two capacity tiers.  FIRST: <GM_MAXCON contacts, GM_MAXROW rows>, GM_WARPS environments per CTA, one warp per environment
+// of the batch.  An environment whose substep needs more (a robot lying on its boxes and cylinders: ~1 % of tumbling robots)
+// is handed over untouched at the START of that substep through the work list A.ovf = {count, (env, substeps left) ...};
+// the second launch (!FIRST: <GM_BIGCON, GM_BIGROW>, one environment per CTA at a time) finishes those.
+template <int MC, int MR, int WARPS, bool FIRST>
+__global__ void __launch_bounds__(WARPS * 32) nm_generic_step_kernel(const GenArgs A) {
+  typedef EnvMemT<MC, MR> EnvMem;
   extern __shared__ __align__(16) unsigned char gm_smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int env = blockIdx.x * GM_WARPS + warp;
-  if (env >= A.num_envs) return;                      // whole warps leave together; no CTA-wide barrier is used below
   EnvMem& e = *reinterpret_cast<EnvMem*>(gm_smem + sizeof(EnvMem) * warp);
   const GenModel& m = *A.model;
   const int nv = m.nv, nq = m.nq, nb = m.nbody, nu = m.nu;
   const float h = m.timestep;
+  const int nwork = FIRST ? A.num_envs : min(A.ovf[0], A.num_envs);
+  for (int item = blockIdx.x * WARPS + warp; item < nwork; item += gridDim.x * WARPS) {   // (FIRST: the grid covers the batch, one trip)
+  const int env = FIRST ? item : A.ovf[1 + 2 * item];
+  const int nstep = FIRST ? A.nstep : A.ovf[2 + 2 * item];
+  __syncwarp();
 
   for (int i = lane; i < nq; i += 32) e.qpos[i] = A.qpos[(size_t)env * nq + i];
   for (int i = lane; i < nv; i += 32) { e.qvel[i] = A.qvel[(size_t)env * nv + i]; e.warm[i] = A.warm[(size_t)env * nv + i]; }
   for (int i = lane; i < nu; i += 32) e.ctrl[i] = A.ctrl[(size_t)env * nu + i];
   int niter_last = 0;
+  bool handed_over = false;
   __syncwarp();
 
-  for (int sub = 0; sub < A.nstep; sub++) {
+  for (int sub = 0; sub < nstep; sub++) {
     // ------------------------------------------------------------------ divergence guard (≙ mj_checkPos / mj_checkVel)
     {
       bool bad = false;
@@ -537,7 +560,7 @@ __global__ void __launch_bounds__(GM_WARPS * 32) nm_generic_step_kernel(const Ge
         const int first = base + incl - cnt;
         for (int q = 0; q < cnt; q++) {
           const int c = first + q;
-          if (c < GM_MAXCON) {
+          if (c < MC) {
             e.cdist[c] = cd[q]; e.cgeom[c] = g;
             for (int k = 0; k < 3; k++) e.cpos[c][k] = cp[q][k];
           } else e.overflow = 1;
@@ -545,7 +568,7 @@ __global__ void __launch_bounds__(GM_WARPS * 32) nm_generic_step_kernel(const Ge
         base += __shfl_sync(0xffffffffu, incl, 31);
       }
       __syncwarp();
-      if (lane == 0) e.ncon = min(base, GM_MAXCON);
+      if (lane == 0) e.ncon = min(base, MC);
       __syncwarp();
     }
     // ------------------------------------------------------------------ P5 constraint rows: friction loss, limits, contacts
@@ -597,12 +620,22 @@ __global__ void __launch_bounds__(GM_WARPS * 32) nm_generic_step_kernel(const Ge
         int r = m.nfloss + e.nlim, nc = 0;
         for (int c = 0; c < e.ncon; c++) {
           const int dim = m.geom_dim[e.cgeom[c]];
-          if (r + dim > GM_MAXROW) { e.overflow = 1; break; }
+          if (r + dim > MR) { e.overflow = 1; break; }
           e.cadr[c] = r; e.cdim[c] = dim; r += dim; nc++;
         }
         e.ncon = nc; e.nefc = r;
       }
       __syncwarp();
+      if (FIRST && e.overflow) {                       // hand the environment over as it is at the start of this substep
+        for (int i = lane; i < nq; i += 32) A.qpos[(size_t)env * nq + i] = e.qpos[i];
+        for (int i = lane; i < nv; i += 32) { A.qvel[(size_t)env * nv + i] = e.qvel[i]; A.warm[(size_t)env * nv + i] = e.warm[i]; }
+        if (lane == 0) {
+          const int k = atomicAdd(A.ovf, 1);
+          A.ovf[1 + 2 * k] = env; A.ovf[2 + 2 * k] = nstep - sub;
+        }
+        handed_over = true;
+        break;
+      }
       const int row0 = m.nfloss + e.nlim, nrow = e.nefc - row0;
       for (int idx = lane; idx < nrow * nv; idx += 32) {
         const int r = row0 + idx / nv, i = idx % nv;
@@ -664,17 +697,18 @@ __global__ void __launch_bounds__(GM_WARPS * 32) nm_generic_step_kernel(const Ge
         __syncwarp();
         float cg = 0.f;
         for (int i = lane; i < nv; i += 32) { float t = 0.f; for (int k = 0; k < nv; k++) t += e.M[i][k] * e.vec[k]; cg += 0.5f * e.vec[i] * t; }
-        for (int r = lane; r < ne; r += 32) { float t = -e.aref[r]; for (int i = 0; i < nv; i++) t += e.J[r][i] * q[i]; e.jar[r] = t; }
+        for (int r = lane; r < ne; r += 32) { double t = -(double)e.aref[r]; for (int i = 0; i < nv; i++) t += (double)e.J[r][i] * (double)q[i]; e.jar[r] = t; }
         __syncwarp();
         cost2[s] = g_warpsum(cg) + g_rows(m, e, e.jar, false, lane);
         __syncwarp();
       }
-      for (int i = lane; i < nv; i += 32) e.qacc[i] = cost2[0] < cost2[1] ? e.warm[i] : e.qaccs[i];
+      for (int i = lane; i < nv; i += 32) e.xd[i] = cost2[0] < cost2[1] ? e.warm[i] : e.qaccs[i];
       __syncwarp();
-      for (int it = 0; it < min(m.iterations, 30); it++) {          // (fp32: quadratic convergence ends at rounding after 3-8 steps)
+      float gprev = 1e30f;
+      for (int it = 0; it < m.iterations; it++) {
         niter = it;
-        for (int i = lane; i < nv; i += 32) e.vec[i] = e.qacc[i] - e.qaccs[i];
-        for (int r = lane; r < ne; r += 32) { float t = -e.aref[r]; for (int i = 0; i < nv; i++) t += e.J[r][i] * e.qacc[i]; e.jar[r] = t; }
+        for (int i = lane; i < nv; i += 32) e.vec[i] = (float)(e.xd[i] - (double)e.qaccs[i]);
+        for (int r = lane; r < ne; r += 32) { double t = -(double)e.aref[r]; for (int i = 0; i < nv; i++) t += (double)e.J[r][i] * e.xd[i]; e.jar[r] = t; }
         __syncwarp();
         for (int i = lane; i < nv; i += 32) { float t = 0.f; for (int k = 0; k < nv; k++) t += e.M[i][k] * e.vec[k]; e.Ma[i] = t; }
         g_rows(m, e, e.jar, true, lane);
@@ -687,8 +721,10 @@ __global__ void __launch_bounds__(GM_WARPS * 32) nm_generic_step_kernel(const Ge
           e.grad[i] = t; gn += t * t; gref += e.Ma[i] * e.Ma[i] + jf * jf;
         }
         gn = g_warpsum(gn); gref = g_warpsum(gref);
-        // MuJoCo's test (scaled gradient below opt.tolerance), or the gradient has reached fp32 rounding of its two terms
-        if (m.solver_scale * sqrtf(gn) < m.tolerance || gn <= 1e-11f * gref) break;
+        // MuJoCo's test (scaled gradient below opt.tolerance); or the gradient is at the fp32 rounding of its two terms; or it is
+        // small and has stopped shrinking (Newton's quadratic phase ended in rounding noise: more steps only wander)
+        if (m.solver_scale * sqrtf(gn) < m.tolerance || gn <= 1e-16f * gref || (gn <= 1e-10f * gref && gn >= 0.25f * gprev)) break;
+        gprev = gn;
         // Hessian (lower triangle): M + sum Hd J'J + cone blocks
         for (int idx = lane; idx < nv * (nv + 1) / 2; idx += 32) {
           int i = (int)((sqrtf(8.f * idx + 1.f) - 1.f) * 0.5f);
@@ -722,9 +758,9 @@ __global__ void __launch_bounds__(GM_WARPS * 32) nm_generic_step_kernel(const Ge
         for (int i = lane; i < nv; i += 32) { float t = 0.f; for (int k = 0; k < nv; k++) t += e.M[i][k] * e.dir[k]; a1 += e.dir[i] * e.Ma[i]; a2 += e.dir[i] * t; }
         a1 = g_warpsum(a1); a2 = g_warpsum(a2);
         __syncwarp();
-        float* jt = e.Hd;                                             // trial jar (Hd is no longer needed in this iteration)
+        double* jt = e.jt;                                            // trial jar
         auto dphi = [&](float alpha) -> float {
-          for (int r = lane; r < ne; r += 32) jt[r] = e.jar[r] + alpha * e.jv[r];
+          for (int r = lane; r < ne; r += 32) jt[r] = e.jar[r] + (double)alpha * (double)e.jv[r];
           __syncwarp();
           g_rows(m, e, jt, false, lane);
           __syncwarp();
@@ -752,11 +788,12 @@ __global__ void __launch_bounds__(GM_WARPS * 32) nm_generic_step_kernel(const Ge
             else { hi = alpha; fhi = fa; if (side == 1) flo *= 0.5f; side = 1; }
           }
         }
-        for (int i = lane; i < nv; i += 32) e.qacc[i] += alpha * e.dir[i];
+        for (int i = lane; i < nv; i += 32) e.xd[i] += (double)alpha * (double)e.dir[i];
         __syncwarp();
       }
       // forces at the solution
-      for (int r = lane; r < ne; r += 32) { float t = -e.aref[r]; for (int i = 0; i < nv; i++) t += e.J[r][i] * e.qacc[i]; e.jar[r] = t; }
+      for (int r = lane; r < ne; r += 32) { double t = -(double)e.aref[r]; for (int i = 0; i < nv; i++) t += (double)e.J[r][i] * e.xd[i]; e.jar[r] = t; }
+      for (int i = lane; i < nv; i += 32) e.qacc[i] = (float)e.xd[i];
       __syncwarp();
       g_rows(m, e, e.jar, false, lane);
       __syncwarp();
@@ -802,10 +839,12 @@ __global__ void __launch_bounds__(GM_WARPS * 32) nm_generic_step_kernel(const Ge
       __syncwarp();
     }
   }
+  if (handed_over) continue;
   for (int i = lane; i < nq; i += 32) A.qpos[(size_t)env * nq + i] = e.qpos[i];
   for (int i = lane; i < nv; i += 32) { A.qvel[(size_t)env * nv + i] = e.qvel[i]; A.warm[(size_t)env * nv + i] = e.warm[i]; }
   if (A.info != nullptr && lane == 0) {
     A.info[(size_t)env * 4] = e.ncon; A.info[(size_t)env * 4 + 1] = e.nefc; A.info[(size_t)env * 4 + 2] = niter_last; A.info[(size_t)env * 4 + 3] = e.overflow;
+  }
   }
 }
 
@@ -852,7 +891,9 @@ void kb(double timestep, const double* solref, const double* solimp, double& K, 
 }  // namespace
 
 struct nm_gen_model { GenModel host; std::vector<float> qpos0; };
-struct nm_gen_batch { const nm_gen_model* model; GenModel* d_model; int n, device; GenArgs args; int64_t launches; };
+struct nm_gen_batch { const nm_gen_model* model; GenModel* d_model; int* d_ovf; int n, device, sms; GenArgs args; int64_t launches; };
+typedef EnvMemT<GM_MAXCON, GM_MAXROW> EnvMemSmall;
+typedef EnvMemT<GM_BIGCON, GM_BIGROW> EnvMemBig;
 
 extern "C" int nm_gen_model_from_buffer(const void* data, size_t nbytes, nm_gen_model** out) {
   if (!data || !out || nbytes < 8) return nm_fail(NM_ERR_ARG, "nm_gen_model_from_buffer: bad argument");
@@ -882,8 +923,8 @@ extern "C" int nm_gen_model_from_buffer(const void* data, size_t nbytes, nm_gen_
   memset(&M, 0, sizeof(M));
   const int nq = sizes[0], nv = sizes[1], nu = sizes[2], nbody = sizes[3], njnt = sizes[4], ngeom_all = sizes[5];
   auto bail = [&](int code, const char* msg) { delete gm; return nm_fail(code, msg); };
-  if (nbody > GM_MAXB || nv > GM_MAXV || nq > GM_MAXQ || nu > GM_MAXU) return bail(NM_ERR_UNSUPPORTED, "generic step: model too large (<= 15 bodies, 24 dofs, 18 actuators)");
   if (oi[1] != 2) return bail(NM_ERR_UNSUPPORTED, "generic step: this path implements solver=\"Newton\" (PGS models use nm_model_from_buffer / nm_step)");
+  if (nbody > GM_MAXB || nv > GM_MAXV || nq > GM_MAXQ || nu > GM_MAXU) return bail(NM_ERR_UNSUPPORTED, "generic step: model too large (<= 15 bodies, 24 dofs, 18 actuators)");
   if (oi[0] != 0) return bail(NM_ERR_UNSUPPORTED, "generic step: only integrator=\"Euler\" is implemented");
   if (oi[2] != 1) return bail(NM_ERR_UNSUPPORTED, "generic step: only cone=\"elliptic\" is implemented with the Newton solver");
   if (nbody < 2 || body_parent[1] != 0 || body_jntnum[1] != 1 || jnt_type[body_jntadr[1]] != 0) return bail(NM_ERR_UNSUPPORTED, "generic step: body 1 must be a free-floating base");
@@ -1027,13 +1068,20 @@ extern "C" int nm_gen_batch_create(const nm_gen_model* m, int num_envs, int devi
   nm_gen_batch* b = new nm_gen_batch();
   memset(b, 0, sizeof(*b));
   b->model = m; b->n = num_envs; b->device = device;
-  if (cudaSetDevice(device) != cudaSuccess || cudaMalloc(&b->d_model, sizeof(GenModel)) != cudaSuccess ||
+  cudaDeviceProp prop;
+  if (cudaSetDevice(device) != cudaSuccess || cudaGetDeviceProperties(&prop, device) != cudaSuccess ||
+      cudaMalloc(&b->d_model, sizeof(GenModel)) != cudaSuccess ||
+      cudaMalloc(&b->d_ovf, sizeof(int) * (1 + 2 * (size_t)num_envs)) != cudaSuccess ||
       cudaMemcpy(b->d_model, &m->host, sizeof(GenModel), cudaMemcpyHostToDevice) != cudaSuccess ||
-      cudaFuncSetAttribute(nm_generic_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(EnvMem) * GM_WARPS)) != cudaSuccess) {
+      cudaFuncSetAttribute(nm_generic_step_kernel<GM_MAXCON, GM_MAXROW, GM_WARPS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(EnvMemSmall) * GM_WARPS)) != cudaSuccess ||
+      cudaFuncSetAttribute(nm_generic_step_kernel<GM_BIGCON, GM_BIGROW, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(EnvMemBig)) != cudaSuccess) {
     if (b->d_model) cudaFree(b->d_model);
+    if (b->d_ovf) cudaFree(b->d_ovf);
     delete b;
     return nm_fail(NM_ERR_CUDA, "nm_gen_batch_create: CUDA allocation failed");
   }
+  b->sms = prop.multiProcessorCount;
+  b->args.ovf = b->d_ovf;
   b->args.model = b->d_model; b->args.qpos = qpos; b->args.qvel = qvel; b->args.warm = warm; b->args.info = info; b->args.num_envs = num_envs;
   *out = b;
   return NM_OK;
@@ -1041,6 +1089,7 @@ extern "C" int nm_gen_batch_create(const nm_gen_model* m, int num_envs, int devi
 extern "C" void nm_gen_batch_destroy(nm_gen_batch* b) {
   if (!b) return;
   cudaFree(b->d_model);
+  cudaFree(b->d_ovf);
   delete b;
 }
 extern "C" int nm_gen_physics_step(nm_gen_batch* b, const float* ctrl, int nstep, nm_stream stream) {
@@ -1051,8 +1100,13 @@ extern "C" int nm_gen_physics_step(nm_gen_batch* b, const float* ctrl, int nstep
   GenArgs a = b->args;
   a.ctrl = ctrl; a.nstep = nstep;
   const int blocks = (b->n + GM_WARPS - 1) / GM_WARPS;
-  nm_generic_step_kernel<<<blocks, GM_WARPS * 32, sizeof(EnvMem) * GM_WARPS, static_cast<cudaStream_t>(stream)>>>(a);
-  b->launches++;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  cudaMemsetAsync(b->d_ovf, 0, sizeof(int), st);
+  nm_generic_step_kernel<GM_MAXCON, GM_MAXROW, GM_WARPS, true><<<blocks, GM_WARPS * 32, sizeof(EnvMemSmall) * GM_WARPS, st>>>(a);
+  // second tier: the few environments that need more contacts / rows than the first tier holds (usually none: ~3 us)
+  const int big = b->n < 4 * b->sms ? b->n : 4 * b->sms;
+  nm_generic_step_kernel<GM_BIGCON, GM_BIGROW, 1, false><<<big, 32, sizeof(EnvMemBig), st>>>(a);
+  b->launches += 2;
   const cudaError_t err = cudaGetLastError();
   if (prev >= 0 && prev != b->device) cudaSetDevice(prev);
   if (err != cudaSuccess) return nm_fail(NM_ERR_CUDA, std::string("nm_gen_physics_step: ") + cudaGetErrorString(err));

@@ -82,7 +82,7 @@ def test_tumbling_lockstep(trio, seed):
     ctrl = rng.uniform(-1, 1, (n, 12))
     ctrl_d = torch.from_numpy(ctrl.astype(np.float32)).to(DEV)
     ctrl = ctrl.astype(np.float32).astype(np.float64)
-    errs, ferrs, ncon_hist, mism, iters = [], [], [], 0, []
+    errs, ferrs, ncon_hist, mism, iters, trunc = [], [], [], 0, [], 0
     for it in range(rounds):
         q, v, w = ob.get_state()
         q32, v32, w32 = q.astype(np.float32), v.astype(np.float32), w.astype(np.float32)
@@ -96,10 +96,10 @@ def test_tumbling_lockstep(trio, seed):
         qf, vf, _ = fb.get_state()
         qg, vg = gb.qpos.cpu().numpy().astype(np.float64), gb.qvel.cpu().numpy().astype(np.float64)
         info = gb.info.cpu().numpy()
-        assert (info[:, 3] == 0).all()
         nefc = np.array([int(ob.get(i, "nefc")[0]) for i in range(n)])
         ncon = np.array([ob.get(i, "contact").reshape(-1, 7).shape[0] for i in range(n)])
-        same = (info[:, 1] == nefc) & (info[:, 0] == ncon)
+        trunc += int((info[:, 3] != 0).sum())                        # beyond the second tier's 64 contacts / 240 rows (the oracle caps at 64 too)
+        same = (info[:, 1] == nefc) & (info[:, 0] == ncon) & (info[:, 3] == 0)
         mism += int((~same).sum())                                   # a geom within fp32 rounding of its margin
         errs.append(per_env_rel(vg, vo)[same]); ferrs.append(per_env_rel(vf, vo)[same])
         errs.append(per_env_rel(qg, qo)[same])
@@ -107,14 +107,16 @@ def test_tumbling_lockstep(trio, seed):
     e, f = np.concatenate(errs), np.concatenate(ferrs)
     ncon_all = np.concatenate(ncon_hist)
     print(f"\n[anymal lockstep seed {seed}] env-substeps {n * rounds} in contact {int((ncon_all > 0).sum())} max ncon {ncon_all.max()} "
-          f"count mismatches {mism} | CUDA median {np.median(e):.2e} p99 {np.percentile(e, 99):.2e} max {e.max():.2e} | "
+          f"second-tier env-substeps {int((ncon_all > 16).sum())} truncated {trunc} count mismatches {mism} | CUDA median {np.median(e):.2e} p99 {np.percentile(e, 99):.2e} max {e.max():.2e} | "
           f"fp32 oracle median {np.median(f):.2e} p99 {np.percentile(f, 99):.2e} max {f.max():.2e} | Newton iterations mean {np.mean(iters):.2f} max {np.max(iters)}")
     assert (ncon_all > 0).sum() > 0.3 * n * rounds and ncon_all.max() >= 6
-    assert mism <= 0.002 * n * rounds
-    # north_star: <= 1e-5 relative after one step.  Median and 99th percentile meet it; the worst env-substeps are bounded by the
-    # fp32 floor of the same arithmetic (the oracle's own source in float), as for the hexapod (profiles/r02_fp32_floor.md).
-    assert np.median(e) < 1e-6 and np.percentile(e, 99) < max(1e-5, 2 * np.percentile(f, 99))
-    assert e.max() < max(1e-5, 4 * f.max())
+    assert mism - trunc <= 0.002 * n * rounds and trunc <= 0.002 * n * rounds and (ncon_all > 16).sum() > 20
+    # north_star: <= 1e-5 relative after one step.  Plain fp32 misses it by two orders of magnitude on this model (the oracle's own
+    # source in float arithmetic: p99 ~ 1e-3, printed above) because a sliding foot's force is Dm * (mu jar_n - mu |jar_t|) with
+    # Dm ~ 4e6; the kernel keeps the Newton iterate and the residual jar in fp64 and meets the bar on all but the hardest env-substeps
+    # (stalled Newton runs of tumbling robots in 20-60 contacts), which are bounded here.
+    assert np.median(e) < 1e-6 and np.percentile(e, 99) < 1e-5 and np.percentile(e, 99.9) < 5e-5
+    assert e.max() < 1e-4
 
 
 def test_free_running_matches_oracle(trio):
@@ -150,4 +152,4 @@ def test_nstep_equals_repeated_single_steps(trio):
     for _ in range(4):
         b.physics_step(ctrl, 1)
     assert torch.equal(a.qpos, b.qpos) and torch.equal(a.qvel, b.qvel) and torch.equal(a.warm, b.warm)
-    assert a.launches == 1 and b.launches == 4
+    assert a.launches == 2 and b.launches == 8                       # first tier + second (overflow) tier per call
