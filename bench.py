@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py — hexapod env-steps/s of the batched Nightmare-v3 environment step (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload step|rollout|ppo] [--envs-per-gpu E]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload step|rollout|ppo|anymal_c] [--envs-per-gpu E]
 
 One "step" = one call of the hot path over one batch: NightmareV3Env.step for E envs per GPU
 (configs[1] of BASELINE.json: 4096 envs, flat ground, random actions), i.e. `decimation`=2 physics
@@ -436,6 +436,84 @@ def bench_ppo(c, E=16384, iters=3):
     return rec
 
 
+def bench_anymal(c, E=4096, K=200):
+    """BASELINE configs[3]: the reference's second model (models/anymal_c: Newton solver, elliptic cones, condim-6 feet,
+    friction loss, joint limits, position actuators) -- E envs per GPU, dt 0.002, 4 substeps per env step
+    (≙ mj.mj_step(model, data[i], 4), simple_test.py:39), joint targets redrawn every step from U(-0.35, 0.35) rad around the
+    standing pose; robots whose trunk drops below 0.3 m or tilts past 60 deg are put back on their feet (torch ops inside the
+    timed region), so the population stays in the standing / stumbling regime."""
+    import torch
+    from nightmare_rl_b200 import _lib, mjcf
+    from nightmare_rl_b200.batch import GenBatch
+    dev = c.dev
+    path = os.path.join(ROOT, "models", "anymal_c", "anymal_c.nmb")
+    cm = mjcf.CompiledModel.load(path)
+    gb = GenBatch(_lib.GenModel(cm.to_bytes()), E, dev)
+    gen = torch.Generator(device=dev).manual_seed(4321 + c.rank)
+    q0 = gb.qpos[0].clone()
+    pool = (torch.rand(16, E, 12, device=dev, generator=gen) - 0.5) * 0.7
+    resets = torch.zeros(1, dtype=torch.int64, device=dev)
+
+    def one(i):
+        gb.physics_step(pool[i % 16], 4)
+        qw, qz = gb.qpos[:, 3], gb.qpos[:, 6]
+        fallen = (gb.qpos[:, 2] < 0.3) | (1.0 - 2.0 * (gb.qpos[:, 4] ** 2 + gb.qpos[:, 5] ** 2) < 0.5)      # trunk z axis . world z < cos 60
+        gb.qpos[fallen] = q0
+        gb.qvel[fallen] = 0.0
+        resets.add_(fallen.sum())
+
+    for i in range(300):
+        one(i)
+    resets.zero_()
+    ncon_mean = float(gb.info[:, 0].float().mean())
+    nefc_mean, it_mean, ovf = float(gb.info[:, 1].float().mean()), float(gb.info[:, 2].float().mean()), int(gb.info[:, 3].sum())
+    c.barrier()
+    l0 = gb.launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(K):
+        one(i)
+    e1.record()
+    c.barrier()
+    ms = c.max_over_ranks(e0.elapsed_time(e1)) / K
+    # the physics launches alone (no reset bookkeeping), same state distribution
+    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    k0.record()
+    for i in range(50):
+        gb.physics_step(pool[i % 16], 4)
+    k1.record()
+    torch.cuda.synchronize()
+    kern_ms = k0.elapsed_time(k1) / 50
+    rec = {"workload": f"anymal_c {E} envs/GPU, dt 0.002 x 4 substeps per env step, random joint targets U(-0.35, 0.35) rad, fallen robots re-seated "
+                       "(BASELINE configs[3]; Newton solver, elliptic cones impratio 100, condim-6 feet, friction loss, joint limits)",
+           "envs_per_gpu": E, "envs_total": c.world * E, "value": c.world * E / (ms * 1e-3), "unit": UNIT, "substeps_per_s": 4 * c.world * E / (ms * 1e-3),
+           "ms_per_step": ms, "physics_launch_ms": kern_ms, "steps": K, "gpu_launches_per_step": (gb.launches - l0) / K,
+           "resets_per_step": float(resets.item()) / K, "mean_contacts": ncon_mean, "mean_constraint_rows": nefc_mean, "mean_newton_iterations_last_substep": it_mean,
+           "truncated_envs": ovf, "dtype": "f32 (+ fp64 Newton iterate / residual)",
+           "algorithmic_bytes_per_env_step": 4 * (19 + 18 + 18 + 12 + 19 + 18 + 18 + 4),
+           "hbm_gbs": 4 * (19 + 18 + 18 + 12 + 19 + 18 + 18 + 4) * E / (kern_ms * 1e-3) / 1e9}
+    if c.rank == 0 and c.world == 1:
+        # CPU arm on the same workload: the oracle (fp64 restatement of mj_step for this model) on all host cores, bounded sample
+        import numpy as np
+        from oracle import oracle as O
+        cores = os.cpu_count() or 1
+        n_cpu = min(E, 512)
+        ob = O.OracleBatch(O.OracleModel(path), n_cpu)
+        rng = np.random.default_rng(7)
+        ctrl = (rng.random((n_cpu, 12)) - 0.5) * 0.7
+        ob.physics_step(ctrl, 100, cores)
+        t0 = time.time()
+        nst = 10
+        for _ in range(nst):
+            ob.physics_step(ctrl, 4, cores)
+        dt = time.time() - t0
+        rec["cpu_baseline"] = {"value": n_cpu * nst / dt, "unit": UNIT, "cores": cores, "kind": "port",
+                               "sample": f"{n_cpu} envs x {nst} env steps of 4 substeps after 100 settle substeps, fp64 oracle (exact Newton), {cores} pthreads"}
+    del gb
+    torch.cuda.empty_cache()
+    return rec
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -471,9 +549,9 @@ def run_ours(args):
     if not args.no_extras:
         # BASELINE configs[2] and configs[4] in the same line, so that the driver's runs (1 GPU and the 1/2/4/8 scaling run)
         # carry a rollout number and a full-PPO number whose timed region contains the NCCL collectives
-        for name, fn in (("rollout", bench_rollout), ("ppo", bench_ppo)):
+        for name, fn in (("rollout", bench_rollout), ("ppo", bench_ppo), ("anymal_c", bench_anymal)):
             try:
-                extras[name] = fn(c, E=args.extras_envs_per_gpu)
+                extras[name] = fn(c, E=args.envs_per_gpu if name == "anymal_c" else args.extras_envs_per_gpu)
             except Exception as exc:              # the headline must survive a failing extra; the failure is reported, not hidden
                 extras[name] = {"error": f"{type(exc).__name__}: {exc}"}
                 barrier()
@@ -547,9 +625,13 @@ def run_workload(args):
 
     c.barrier, c.max_over_ranks = barrier, max_over_ranks
     E = args.extras_envs_per_gpu
-    rec = bench_rollout(c, E=E, reps=max(3, min(args.steps, 10))) if args.workload == "rollout" else bench_ppo(c, E=E, iters=max(3, min(args.steps, 10)))
+    if args.workload == "anymal_c":
+        E = args.envs_per_gpu
+        rec = bench_anymal(c, E=E, K=max(20, min(args.steps, 1000)))
+    else:
+        rec = bench_rollout(c, E=E, reps=max(3, min(args.steps, 10))) if args.workload == "rollout" else bench_ppo(c, E=E, iters=max(3, min(args.steps, 10)))
     if c.rank == 0:
-        ms = rec.get("ms_per_rollout", rec.get("ms_per_iteration"))
+        ms = rec.get("ms_per_rollout", rec.get("ms_per_iteration", rec.get("ms_per_step")))
         line = {"metric": METRIC, "value": rec["value"], "unit": UNIT, "n_gpus": c.world, "steps": rec.get("reps", rec.get("iterations")), "warmup": 2,
                 "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": _config(E, c.world, rec["workload"]), args.workload: rec}
@@ -564,9 +646,9 @@ def main():
     ap.add_argument("--steps", type=int, default=1000)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
-    ap.add_argument("--workload", choices=["step", "rollout", "ppo"], default="step",
+    ap.add_argument("--workload", choices=["step", "rollout", "ppo", "anymal_c"], default="step",
                     help="step (default, the headline: BASELINE configs[1]; its line also carries `rollout` and `ppo` sub-records), "
-                         "rollout (configs[2]) or ppo (configs[4]) alone")
+                         "rollout (configs[2]), ppo (configs[4]) or anymal_c (configs[3]) alone")
     ap.add_argument("--envs-per-gpu", type=int, default=4096)
     ap.add_argument("--extras-envs-per-gpu", type=int, default=16384, help="envs per GPU of the rollout / ppo records (131072 over 8 GPUs)")
     ap.add_argument("--no-sweep", action="store_true", help="skip the 16384/65536/131072-env sweep of the 1-GPU run")

@@ -141,7 +141,7 @@ struct EnvMemT {
   // contact the force is Dm * mu * (mu * jar_n - mu * |friction . jar_t|) with Dm ~ 4e6 for the feet (impratio 100): the
   // difference of two O(10) numbers has to be right to 1e-9 for a force good to 1e-3 N, which fp32 residuals miss by three
   // orders of magnitude (measured: fp32 floor 1e-3 relative in qvel, with these two arrays in fp64 2.6e-6).
-  double xd[GM_MAXV], jar[MR], jt[MR];
+  double xd[GM_MAXV], jar[MR];
   float qpos[GM_MAXQ + 3], qvel[GM_MAXV], warm[GM_MAXV], ctrl[GM_MAXU + 2];
   float xpos[GM_MAXB][3], xquat[GM_MAXB][4], xmat[GM_MAXB][9], xipos[GM_MAXB][3], ximat[GM_MAXB][9];
   float com[4];
@@ -153,11 +153,12 @@ struct EnvMemT {
   int ncon, nefc, nlim, overflow;
   float cpos[MC][3], cdist[MC], cmu[MC];
   int cgeom[MC], cadr[MC], cdim[MC], czone[MC];
-  float chess[MC][36];
+  float cDm[MC], ccoef[MC], cb[MC][GM_MAXV];          // elliptic-cone curvature data (g_cone)
   // rows
   float J[MR][GM_MAXV];
   float aref[MR], D[MR], R[MR], jv[MR], force[MR], Hd[MR], floss[MR];
-  int rtype[MR], rid[MR];
+  int rtype[2 * GM_MAXV], rdof[2 * GM_MAXV];           // simple rows (friction loss, limits): one dof each, J = rsgn * e_dof
+  float rsgn[2 * GM_MAXV];
 };
 
 // dense Cholesky of the nv x nv matrix A (lower triangle used) into Lo, by the whole warp; returns false if not positive definite
@@ -200,75 +201,111 @@ __device__ void g_cholsolve(const float (*Lo)[GM_MAXV], int n, float* x, int lan
   }
 }
 
-// constraint forces, cost and (optionally) curvature at jar: friction-loss / limit rows one per lane, contacts one per lane
+// ---------------------------------------------------------------------------------------------- constraint rows
+// sqrt of a double from the fp32 rsqrt plus one Newton step in fp64 (relative error ~1e-14): the fp64 sqrt / divide are
+// software sequences of a few hundred cycles, this is 5 DFMA-class operations
+__device__ __forceinline__ double g_sqrt64(double x, double* rinv) {
+  if (!(x > 0.0)) { *rinv = 0.0; return 0.0; }
+  const double r0 = (double)rsqrtf((float)x);
+  const double r = r0 * (1.5 - 0.5 * x * r0 * r0);
+  *rinv = r;
+  return x * r;
+}
+
+// One elliptic contact at residual j[0..dim): zone (0 top: no force, 1 bottom: quadratic in every row, 2 middle: on the cone),
+// forces f, cost; for zone 2 also the curvature data of the Hessian Dm g g' + c F (I - uu') F  (g = mu (e0 - F u)):
+// uh[j] = friction_j * u_j (j >= 1) and the scalar c = -Dm mu (N - mu T) / T >= 0.
+__device__ __forceinline__ int g_cone(int dim, const double* j, const float* fri, float mu, const float* D, float Dm, float* f, float* cost, float* uh, float* ccoef) {
+  if (dim == 1) {
+    if (j[0] < 0.0) { const float jj = (float)j[0]; f[0] = -D[0] * jj; *cost = 0.5f * D[0] * jj * jj; return 1; }
+    f[0] = 0.f; *cost = 0.f; return 0;
+  }
+  double U[6], T2 = 0.0, rT;
+  for (int k = 1; k < dim; k++) { U[k] = j[k] * (double)fri[k - 1]; T2 += U[k] * U[k]; }
+  const double N = j[0] * (double)mu, T = g_sqrt64(T2, &rT);
+  if (N >= (double)mu * T || (T <= 0.0 && N >= 0.0)) {
+    for (int k = 0; k < dim; k++) f[k] = 0.f;
+    *cost = 0.f;
+    return 0;
+  }
+  if ((double)mu * N + T <= 0.0 || (T <= 0.0 && N < 0.0)) {
+    float cs = 0.f;
+    for (int k = 0; k < dim; k++) { const float jj = (float)j[k]; f[k] = -D[k] * jj; cs += 0.5f * D[k] * jj * jj; }
+    *cost = cs;
+    return 1;
+  }
+  const float NmT = (float)(N - (double)mu * T);
+  const float f0 = -Dm * NmT * mu;
+  f[0] = f0;
+  for (int k = 1; k < dim; k++) { const float u = (float)(U[k] * rT) * fri[k - 1]; uh[k] = u; f[k] = -f0 * u; }
+  *cost = 0.5f * Dm * NmT * NmT;
+  *ccoef = -Dm * mu * NmT * (float)rT;
+  return 2;
+}
+
+// friction-loss / joint-limit row at residual j: force, cost, curvature
+__device__ __forceinline__ float g_simple(int type, float D, float R, float fl, float j, float* cost, float* hd) {
+  if (type == R_FRICTION) {
+    const float bound = R * fl;
+    if (j <= -bound) { *cost = -0.5f * R * fl * fl - fl * j; *hd = 0.f; return fl; }
+    if (j >= bound) { *cost = -0.5f * R * fl * fl + fl * j; *hd = 0.f; return -fl; }
+  } else if (!(j < 0.f)) { *cost = 0.f; *hd = 0.f; return 0.f; }
+  *cost = 0.5f * D * j * j; *hd = D;
+  return -D * j;
+}
+
+// Forces, cost and curvature of every row at e.jar (written to e.force / e.Hd / e.czone / e.ccoef / e.cb); returns the cost.
 template <class EnvMem>
-__device__ float g_rows(const GenModel& m, EnvMem& e, const double* jar, bool hess, int lane) {
+__device__ float g_rows(const GenModel& m, EnvMem& e, bool hess, int lane) {
   float cost = 0.f;
-  const int nsimple = m.nfloss + e.nlim;
+  const int nsimple = m.nfloss + e.nlim, nv = m.nv;
   for (int r = lane; r < nsimple; r += 32) {
-    const float D = e.D[r], R = e.R[r], j = (float)jar[r];
-    float hd = 0.f;
-    if (e.rtype[r] == R_FRICTION) {
-      const float fl = e.floss[r], bound = R * fl;
-      if (j <= -bound) { e.force[r] = fl; cost += -0.5f * R * fl * fl - fl * j; }
-      else if (j >= bound) { e.force[r] = -fl; cost += -0.5f * R * fl * fl + fl * j; }
-      else { e.force[r] = -D * j; cost += 0.5f * D * j * j; hd = D; }
-    } else {
-      if (j < 0.f) { e.force[r] = -D * j; cost += 0.5f * D * j * j; hd = D; }
-      else e.force[r] = 0.f;
-    }
+    float cs, hd;
+    e.force[r] = g_simple(e.rtype[r], e.D[r], e.R[r], e.floss[r], (float)e.jar[r], &cs, &hd);
+    cost += cs;
     if (hess) e.Hd[r] = hd;
   }
   for (int c = lane; c < e.ncon; c += 32) {
     const int a = e.cadr[c], dim = e.cdim[c];
-    const float mu = e.cmu[c];
     const float* fri = m.geom_friction[e.cgeom[c]];
-    double Ud[6];
-    Ud[0] = jar[a] * (double)mu;
-    double T2d = 0.0;
-    for (int j = 1; j < dim; j++) { Ud[j] = jar[a + j] * (double)fri[j - 1]; T2d += Ud[j] * Ud[j]; }
-    const double Nd = Ud[0], Td = sqrt(T2d);
-    float U[6];
-    for (int j = 0; j < dim; j++) U[j] = (float)Ud[j];
-    const float T2 = (float)T2d, T = (float)Td;
-    int zone;
-    if (dim == 1) {
-      zone = jar[a] < 0.0 ? 1 : 0;
-    } else if (Nd >= (double)mu * Td || (Td <= 0.0 && Nd >= 0.0)) zone = 0;
-    else if ((double)mu * Nd + Td <= 0.0 || (Td <= 0.0 && Nd < 0.0)) zone = 1;
-    else zone = 2;
-    if (zone == 0) {
-      for (int j = 0; j < dim; j++) { e.force[a + j] = 0.f; if (hess) e.Hd[a + j] = 0.f; }
-    } else if (zone == 1) {
-      for (int j = 0; j < dim; j++) {
-        const float Dj = e.D[a + j], jj = (float)jar[a + j];
-        e.force[a + j] = -Dj * jj;
-        cost += 0.5f * Dj * jj * jj;
-        if (hess) e.Hd[a + j] = Dj;
-      }
-    } else {
-      const float Dm = e.D[a] / (mu * mu * (1.f + mu * mu)), NmT = (float)(Nd - (double)mu * Td);
-      cost += 0.5f * Dm * NmT * NmT;
-      const float f0 = -Dm * NmT * mu;
-      e.force[a] = f0;
-      for (int j = 1; j < dim; j++) e.force[a + j] = -f0 / T * U[j] * fri[j - 1];
-      if (hess) {
-        float g[6];
-        g[0] = mu;
-        for (int j = 1; j < dim; j++) g[j] = -mu * fri[j - 1] * U[j] / T;
-        for (int p = 0; p < dim; p++) {
-          e.Hd[a + p] = 0.f;
-          for (int q = 0; q < dim; q++) {
-            float h = g[p] * g[q];
-            if (p > 0 && q > 0) h += -mu * NmT * fri[p - 1] * fri[q - 1] * ((p == q ? 1.f : 0.f) - U[p] * U[q] / T2) / T;
-            e.chess[c][6 * p + q] = Dm * h;
-          }
+    float f[6], uh[6], cs, cc = 0.f;
+    const int zone = g_cone(dim, e.jar + a, fri, e.cmu[c], e.D + a, e.cDm[c], f, &cs, uh, &cc);
+    for (int k = 0; k < dim; k++) e.force[a + k] = f[k];
+    cost += cs;
+    if (hess) {
+      e.czone[c] = zone;
+      if (zone == 2) {
+        e.ccoef[c] = cc;
+        for (int i = 0; i < nv; i++) {                     // b = sum_k friction_k u_k J_k
+          float t = 0.f;
+          for (int k = 1; k < dim; k++) t += uh[k] * e.J[a + k][i];
+          e.cb[c][i] = t;
         }
       }
     }
-    if (hess) e.czone[c] = zone;
   }
   return g_warpsum(cost);
+}
+
+// Line-search derivative term sum_r force_r(jar + alpha jv) jv_r: every lane evaluates its own rows, nothing is stored
+template <class EnvMem>
+__device__ float g_rows_dot(const GenModel& m, const EnvMem& e, float alpha, int lane) {
+  float s = 0.f;
+  const int nsimple = m.nfloss + e.nlim;
+  for (int r = lane; r < nsimple; r += 32) {
+    float cs, hd;
+    const float jv = e.jv[r];
+    s += g_simple(e.rtype[r], e.D[r], e.R[r], e.floss[r], (float)(e.jar[r] + (double)alpha * (double)jv), &cs, &hd) * jv;
+  }
+  for (int c = lane; c < e.ncon; c += 32) {
+    const int a = e.cadr[c], dim = e.cdim[c];
+    double j[6];
+    for (int k = 0; k < dim; k++) j[k] = e.jar[a + k] + (double)alpha * (double)e.jv[a + k];
+    float f[6], uh[6], cs, cc;
+    g_cone(dim, j, m.geom_friction[e.cgeom[c]], e.cmu[c], e.D + a, e.cDm[c], f, &cs, uh, &cc);
+    for (int k = 0; k < dim; k++) s += f[k] * e.jv[a + k];
+  }
+  return g_warpsum(s);
 }
 
 // ================================================================================================ the kernel
@@ -577,13 +614,11 @@ __global__ void __launch_bounds__(WARPS * 32) nm_generic_step_kernel(const GenAr
       for (int i = lane; i < nv; i += 32) {
         const int r = m.dof_flossrow[i];
         if (r < 0) continue;
-        for (int k = 0; k < nv; k++) e.J[r][k] = 0.f;
-        e.J[r][i] = 1.f;
         const float imp = m.lim_imp0;
         const float R = fmaxf((1.f - imp) * m.dof_invw[i] / imp, 1e-15f);
         e.R[r] = R; e.D[r] = 1.f / R; e.floss[r] = m.dof_floss[i];
         e.aref[r] = -m.lim_B * e.qvel[i];
-        e.rtype[r] = R_FRICTION; e.rid[r] = i;
+        e.rtype[r] = R_FRICTION; e.rdof[r] = i; e.rsgn[r] = 1.f;
       }
       // joint limits: lower side first, then upper, in joint (= body) order
       int base = m.nfloss;
@@ -603,13 +638,11 @@ __global__ void __launch_bounds__(WARPS * 32) nm_generic_step_kernel(const GenAr
         const int first = base + incl - cnt;
         for (int q = 0; q < cnt; q++) {
           const int r = first + q, i = m.body_dofadr[b];
-          for (int k = 0; k < nv; k++) e.J[r][k] = 0.f;
-          e.J[r][i] = sgn[q];
           const float imp = g_impedance(m.lim_solimp, dist[q]);
           const float R = fmaxf((1.f - imp) * m.dof_invw[i] / imp, 1e-15f);
           e.R[r] = R; e.D[r] = 1.f / R; e.floss[r] = 0.f;
           e.aref[r] = -m.lim_B * (sgn[q] * e.qvel[i]) - m.lim_K * imp * dist[q];
-          e.rtype[r] = R_LIMIT; e.rid[r] = b;
+          e.rtype[r] = R_LIMIT; e.rdof[r] = i; e.rsgn[r] = sgn[q];
         }
         base += __shfl_sync(0xffffffffu, incl, 31);
       }
@@ -636,25 +669,22 @@ __global__ void __launch_bounds__(WARPS * 32) nm_generic_step_kernel(const GenAr
         handed_over = true;
         break;
       }
-      const int row0 = m.nfloss + e.nlim, nrow = e.nefc - row0;
-      for (int idx = lane; idx < nrow * nv; idx += 32) {
-        const int r = row0 + idx / nv, i = idx % nv;
-        // which contact owns row r
-        int c = 0;
-        while (c + 1 < e.ncon && e.cadr[c + 1] <= r) c++;
-        const int k = r - e.cadr[c];                 // 0 normal, 1-2 tangents, 3 torsion, 4-5 rolling
-        const int g = e.cgeom[c], b = m.geom_body[g];
-        float val = 0.f;
+      // contact Jacobians: one (contact, dof) pair per lane trip, all rows of the contact at once
+      for (int idx = lane; idx < e.ncon * nv; idx += 32) {
+        const int c = idx / nv, i = idx - c * nv;
+        const int a = e.cadr[c], dim = e.cdim[c], b = m.geom_body[e.cgeom[c]];
+        float lin[3] = {0.f, 0.f, 0.f}, ang[3] = {0.f, 0.f, 0.f};
         if ((m.body_dofmask[b] >> i) & 1) {
-          const float* fr = m.plane_frame + 3 * (k < 3 ? k : k - 3);
-          if (k < 3) {
-            const float off[3] = {e.cpos[c][0] - e.com[0], e.cpos[c][1] - e.com[1], e.cpos[c][2] - e.com[2]};
-            float t[3];
-            g_cross(t, e.cdof[i], off);
-            val = fr[0] * (e.cdof[i][3] + t[0]) + fr[1] * (e.cdof[i][4] + t[1]) + fr[2] * (e.cdof[i][5] + t[2]);
-          } else val = fr[0] * e.cdof[i][0] + fr[1] * e.cdof[i][1] + fr[2] * e.cdof[i][2];
+          const float off[3] = {e.cpos[c][0] - e.com[0], e.cpos[c][1] - e.com[1], e.cpos[c][2] - e.com[2]};
+          g_cross(lin, e.cdof[i], off);
+          lin[0] += e.cdof[i][3]; lin[1] += e.cdof[i][4]; lin[2] += e.cdof[i][5];
+          ang[0] = e.cdof[i][0]; ang[1] = e.cdof[i][1]; ang[2] = e.cdof[i][2];
         }
-        e.J[r][i] = val;
+        for (int k = 0; k < dim; k++) {                  // 0 normal, 1-2 tangents, 3 torsion, 4-5 rolling
+          const float* fr = m.plane_frame + 3 * (k < 3 ? k : k - 3);
+          const float* v = k < 3 ? lin : ang;
+          e.J[a + k][i] = fr[0] * v[0] + fr[1] * v[1] + fr[2] * v[2];
+        }
       }
       __syncwarp();
       for (int c = lane; c < e.ncon; c += 32) {
@@ -677,127 +707,147 @@ __global__ void __launch_bounds__(WARPS * 32) nm_generic_step_kernel(const GenAr
           e.R[a + j] = fmaxf(e.R[a + j], 1e-15f);
           e.D[a + j] = 1.f / e.R[a + j];
           e.aref[a + j] = -m.geom_B[g] * vel - (j == 0 ? m.geom_K[g] * imp * pos : 0.f);
-          e.floss[a + j] = 0.f; e.rtype[a + j] = R_CONTACT; e.rid[a + j] = c;
         }
+        e.cDm[c] = dim > 1 ? e.D[a] / (e.cmu[c] * e.cmu[c] * (1.f + e.cmu[c] * e.cmu[c])) : 0.f;
       }
       __syncwarp();
     }
     // ------------------------------------------------------------------ P9 Newton solver on the primal problem
-    const int ne = e.nefc;
+    const int ne = e.nefc, nsimple = m.nfloss + e.nlim;
     int niter = 0;
     if (ne == 0) {
       for (int i = lane; i < nv; i += 32) { e.qacc[i] = e.qaccs[i]; e.fcon[i] = 0.f; }
       __syncwarp();
     } else {
+      // residual jar = J x - aref in fp64 from the fp64 iterate; simple rows touch one dof, contact rows the dofs of their body's chain
+      auto residual = [&](const double* x) {
+        for (int r = lane; r < ne; r += 32) {
+          double t = -(double)e.aref[r];
+          if (r < nsimple) t += (double)e.rsgn[r] * x[e.rdof[r]];
+          else for (int i = 0; i < nv; i++) t += (double)e.J[r][i] * x[i];
+          e.jar[r] = t;
+        }
+      };
       // start from the cheaper of qacc_warmstart and qacc_smooth
       float cost2[2];
       for (int s = 0; s < 2; s++) {
         const float* q = s == 0 ? e.warm : e.qaccs;
-        for (int i = lane; i < nv; i += 32) e.vec[i] = q[i] - e.qaccs[i];
+        for (int i = lane; i < nv; i += 32) { e.vec[i] = q[i] - e.qaccs[i]; e.xd[i] = (double)q[i]; }
         __syncwarp();
         float cg = 0.f;
-        for (int i = lane; i < nv; i += 32) { float t = 0.f; for (int k = 0; k < nv; k++) t += e.M[i][k] * e.vec[k]; cg += 0.5f * e.vec[i] * t; }
-        for (int r = lane; r < ne; r += 32) { double t = -(double)e.aref[r]; for (int i = 0; i < nv; i++) t += (double)e.J[r][i] * (double)q[i]; e.jar[r] = t; }
+        if (s == 0) for (int i = lane; i < nv; i += 32) { float t = 0.f; for (int k = 0; k < nv; k++) t += e.M[i][k] * e.vec[k]; cg += 0.5f * e.vec[i] * t; }
+        residual(e.xd);
         __syncwarp();
-        cost2[s] = g_warpsum(cg) + g_rows(m, e, e.jar, false, lane);
+        cost2[s] = g_warpsum(cg) + g_rows(m, e, false, lane);
         __syncwarp();
       }
-      for (int i = lane; i < nv; i += 32) e.xd[i] = cost2[0] < cost2[1] ? e.warm[i] : e.qaccs[i];
+      if (cost2[0] < cost2[1]) { for (int i = lane; i < nv; i += 32) e.xd[i] = (double)e.warm[i]; }
       __syncwarp();
       float gprev = 1e30f;
-      for (int it = 0; it < m.iterations; it++) {
+      // every trip evaluates forces and gradient at the current iterate FIRST, so whenever the loop is left the forces in
+      // e.force / e.fcon belong to the returned qacc
+      for (int it = 0;; it++) {
         niter = it;
         for (int i = lane; i < nv; i += 32) e.vec[i] = (float)(e.xd[i] - (double)e.qaccs[i]);
-        for (int r = lane; r < ne; r += 32) { double t = -(double)e.aref[r]; for (int i = 0; i < nv; i++) t += (double)e.J[r][i] * e.xd[i]; e.jar[r] = t; }
+        residual(e.xd);
         __syncwarp();
         for (int i = lane; i < nv; i += 32) { float t = 0.f; for (int k = 0; k < nv; k++) t += e.M[i][k] * e.vec[k]; e.Ma[i] = t; }
-        g_rows(m, e, e.jar, true, lane);
+        g_rows(m, e, true, lane);
         __syncwarp();
         float gn = 0.f, gref = 0.f;
         for (int i = lane; i < nv; i += 32) {
           float jf = 0.f;
-          for (int r = 0; r < ne; r++) jf += e.J[r][i] * e.force[r];
-          const float t = e.Ma[i] - jf;
+          for (int r = nsimple; r < ne; r++) jf += e.J[r][i] * e.force[r];
+          const int fr = m.dof_flossrow[i];
+          if (fr >= 0) jf += e.force[fr];
+          e.fcon[i] = jf;
+        }
+        __syncwarp();
+        for (int r = m.nfloss + lane; r < nsimple; r += 32) e.fcon[e.rdof[r]] += e.rsgn[r] * e.force[r];     // limit rows: distinct dofs
+        __syncwarp();
+        for (int i = lane; i < nv; i += 32) {
+          const float jf = e.fcon[i], t = e.Ma[i] - jf;
           e.grad[i] = t; gn += t * t; gref += e.Ma[i] * e.Ma[i] + jf * jf;
         }
         gn = g_warpsum(gn); gref = g_warpsum(gref);
         // MuJoCo's test (scaled gradient below opt.tolerance); or the gradient is at the fp32 rounding of its two terms; or it is
         // small and has stopped shrinking (Newton's quadratic phase ended in rounding noise: more steps only wander)
-        if (m.solver_scale * sqrtf(gn) < m.tolerance || gn <= 1e-16f * gref || (gn <= 1e-10f * gref && gn >= 0.25f * gprev)) break;
+        const bool quad = gn <= 1e-10f * gref;                     // Newton's quadratic phase: full steps, no line search
+        if (m.solver_scale * sqrtf(gn) < m.tolerance || gn <= 1e-16f * gref || (quad && gn >= 0.25f * gprev) || it >= m.iterations) break;
         gprev = gn;
-        // Hessian (lower triangle): M + sum Hd J'J + cone blocks
+        // Hessian (lower triangle) H = M + sum_r Hd_r J_r J_r' + cone terms.  Simple rows add to the diagonal; a contact in the
+        // bottom zone adds its rows weighted by D, one on the cone adds Dm mu^2 (J0 - b)(J0 - b)' + c (sum_k fri_k^2 J_k J_k' - b b')
         for (int idx = lane; idx < nv * (nv + 1) / 2; idx += 32) {
           int i = (int)((sqrtf(8.f * idx + 1.f) - 1.f) * 0.5f);
           while ((i + 1) * (i + 2) / 2 <= idx) i++;
           while (i * (i + 1) / 2 > idx) i--;
           const int k = idx - i * (i + 1) / 2;
           float s = e.M[i][k];
-          const int nsimple = m.nfloss + e.nlim;
-          for (int r = 0; r < nsimple; r++) s += e.Hd[r] * e.J[r][i] * e.J[r][k];
           for (int c = 0; c < e.ncon; c++) {
+            const int zone = e.czone[c];
+            if (zone == 0) continue;
             const int a = e.cadr[c], dim = e.cdim[c];
-            if (e.czone[c] == 1) { for (int j = 0; j < dim; j++) s += e.Hd[a + j] * e.J[a + j][i] * e.J[a + j][k]; }
-            else if (e.czone[c] == 2) {
-              for (int p = 0; p < dim; p++) {
-                float t = 0.f;
-                for (int q = 0; q < dim; q++) t += e.chess[c][6 * p + q] * e.J[a + q][k];
-                s += e.J[a + p][i] * t;
-              }
+            if (zone == 1) { for (int j = 0; j < dim; j++) s += e.D[a + j] * e.J[a + j][i] * e.J[a + j][k]; }
+            else {
+              const float* fri = m.geom_friction[e.cgeom[c]];
+              const float mu = e.cmu[c], cc = e.ccoef[c], bi = e.cb[c][i], bk = e.cb[c][k];
+              float t = 0.f;
+              for (int j = 1; j < dim; j++) t += fri[j - 1] * fri[j - 1] * e.J[a + j][i] * e.J[a + j][k];
+              s += e.cDm[c] * mu * mu * (e.J[a][i] - bi) * (e.J[a][k] - bk) + cc * (t - bi * bk);
             }
           }
           e.H[i][k] = s;
         }
         __syncwarp();
+        for (int r = lane; r < nsimple; r += 32) { const int i = e.rdof[r]; if (e.Hd[r] != 0.f) atomicAdd(&e.H[i][i], e.Hd[r]); }
+        __syncwarp();
         if (!g_cholesky(e.H, e.H, nv, lane)) break;                 // in place: only the lower triangle is read
         for (int i = lane; i < nv; i += 32) e.dir[i] = -e.grad[i];
         __syncwarp();
         g_cholsolve(e.H, nv, e.dir, lane);
-        // exact line search on phi'(alpha) = a1 + alpha a2 - sum force(jar + alpha jv) jv
-        for (int r = lane; r < ne; r += 32) { float t = 0.f; for (int i = 0; i < nv; i++) t += e.J[r][i] * e.dir[i]; e.jv[r] = t; }
+        if (quad) {
+          for (int i = lane; i < nv; i += 32) e.xd[i] += (double)e.dir[i];
+          __syncwarp();
+          continue;
+        }
+        // line search on phi'(alpha) = a1 + alpha a2 - sum_r force_r(jar + alpha jv) jv_r (increasing in alpha), to MuJoCo's
+        // relative tolerance class: |phi'| <= 0.1 |phi'(0)| (exactness buys nothing: the outer Newton iteration corrects it)
+        for (int r = lane; r < ne; r += 32) {
+          float t = 0.f;
+          if (r < nsimple) t = e.rsgn[r] * e.dir[e.rdof[r]];
+          else for (int i = 0; i < nv; i++) t += e.J[r][i] * e.dir[i];
+          e.jv[r] = t;
+        }
         float a1 = 0.f, a2 = 0.f;
         for (int i = lane; i < nv; i += 32) { float t = 0.f; for (int k = 0; k < nv; k++) t += e.M[i][k] * e.dir[k]; a1 += e.dir[i] * e.Ma[i]; a2 += e.dir[i] * t; }
         a1 = g_warpsum(a1); a2 = g_warpsum(a2);
         __syncwarp();
-        double* jt = e.jt;                                            // trial jar
-        auto dphi = [&](float alpha) -> float {
-          for (int r = lane; r < ne; r += 32) jt[r] = e.jar[r] + (double)alpha * (double)e.jv[r];
-          __syncwarp();
-          g_rows(m, e, jt, false, lane);
-          __syncwarp();
-          float s = 0.f;
-          for (int r = lane; r < ne; r += 32) s += e.force[r] * e.jv[r];
-          return a1 + alpha * a2 - g_warpsum(s);
-        };
+        auto dphi = [&](float alpha) -> float { return a1 + alpha * a2 - g_rows_dot(m, e, alpha, lane); };
         float lo = 0.f, hi = 1.f, alpha = 1.f;
         float flo = dphi(0.f);
         if (!(flo < 0.f)) break;
-        const float d0 = fabsf(flo);
+        const float tol = 0.1f * fabsf(flo);
         float fhi = dphi(hi);
-        int guard = 0;
-        while (fhi < 0.f && guard++ < 30) { lo = hi; flo = fhi; hi *= 2.f; fhi = dphi(hi); }
-        if (fhi < 0.f) alpha = hi;
-        else {
-          int side = 0;
+        if (fabsf(fhi) > tol) {
+          int guard = 0;
+          while (fhi < 0.f && guard++ < 30) { lo = hi; flo = fhi; hi *= 2.f; fhi = dphi(hi); }
           alpha = hi;
-          for (int k = 0; k < 40; k++) {
-            alpha = (lo * fhi - hi * flo) / (fhi - flo);
-            if (!(alpha > lo && alpha < hi)) alpha = 0.5f * (lo + hi);
-            const float fa = dphi(alpha);
-            if (fabsf(fa) <= 1e-5f * d0 || hi - lo <= 1e-6f * hi) break;
-            if (fa < 0.f) { lo = alpha; flo = fa; if (side == -1) fhi *= 0.5f; side = -1; }
-            else { hi = alpha; fhi = fa; if (side == 1) flo *= 0.5f; side = 1; }
+          if (fhi > tol) {
+            int side = 0;
+            for (int k = 0; k < 12; k++) {                           // regula falsi with the Illinois modification
+              alpha = (lo * fhi - hi * flo) / (fhi - flo);
+              if (!(alpha > lo && alpha < hi)) alpha = 0.5f * (lo + hi);
+              const float fa = dphi(alpha);
+              if (fabsf(fa) <= tol) break;
+              if (fa < 0.f) { lo = alpha; flo = fa; if (side == -1) fhi *= 0.5f; side = -1; }
+              else { hi = alpha; fhi = fa; if (side == 1) flo *= 0.5f; side = 1; }
+            }
           }
         }
         for (int i = lane; i < nv; i += 32) e.xd[i] += (double)alpha * (double)e.dir[i];
         __syncwarp();
       }
-      // forces at the solution
-      for (int r = lane; r < ne; r += 32) { double t = -(double)e.aref[r]; for (int i = 0; i < nv; i++) t += (double)e.J[r][i] * e.xd[i]; e.jar[r] = t; }
       for (int i = lane; i < nv; i += 32) e.qacc[i] = (float)e.xd[i];
-      __syncwarp();
-      g_rows(m, e, e.jar, false, lane);
-      __syncwarp();
-      for (int i = lane; i < nv; i += 32) { float t = 0.f; for (int r = 0; r < ne; r++) t += e.J[r][i] * e.force[r]; e.fcon[i] = t; }
       __syncwarp();
     }
     niter_last = niter;
