@@ -32,7 +32,10 @@ int nm_fail(int code, const std::string& msg);   // nm_abi.cu
 #define GM_MAXG 48     // collision geoms (plane excluded)
 #define GM_MAXCON 16   // first tier: contacts / constraint rows per environment held in shared memory
 #define GM_MAXROW 72
-#define GM_WARPS 4     // environments per CTA
+#ifndef GM_WARPS
+#define GM_WARPS 8     // environments (warps) per CTA: one CTA per SM, its warps in lockstep (measured 12.4 ms unsynchronised, 9.6 / 6.9 / 5.9 ms with 2 / 4 / 8 warps in lockstep)
+#endif
+#define GM_MAXCHAIN 16  // dofs on the chain from the world to any body
 #define GM_BIGCON 64   // second tier (same cap as the oracle's NMO_MAXCON); beyond it info[3] = 1 and the step is truncated
 #define GM_BIGROW 240
 
@@ -45,6 +48,7 @@ struct GenModel {
   float qpos0[GM_MAXQ];
   // bodies (one joint each; body 0 = world, body 1 = the free-floating base)
   int body_parent[GM_MAXB], body_depth[GM_MAXB], body_dofadr[GM_MAXB], body_qadr[GM_MAXB], body_dofmask[GM_MAXB];
+  int body_ndof[GM_MAXB], body_dofs[GM_MAXB][GM_MAXCHAIN];   // dofs that move the body (its chain), ascending
   float body_pos[GM_MAXB][3], body_quat[GM_MAXB][4], body_ipos[GM_MAXB][3], body_iquat[GM_MAXB][4], body_mass[GM_MAXB], body_inertia[GM_MAXB][3];
   float body_invw[GM_MAXB][2], jnt_axis[GM_MAXB][3], jnt_range[GM_MAXB][2];
   int jnt_limited[GM_MAXB];
@@ -122,6 +126,9 @@ __device__ __forceinline__ float g_warpsum(float v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
+__device__ __noinline__ float g_impedance_pow(float x, float mid, float power) {      // general solimp power: cold, out of line
+  return x <= mid ? powf(x, power) / powf(mid, power - 1.f) : 1.f - powf(1.f - x, power) / powf(1.f - mid, power - 1.f);
+}
 __device__ __forceinline__ float g_impedance(const float* si, float pos) {      // si: dmin dmax width mid power (clamped on the host)
   if (si[0] == si[1] || si[2] <= 1e-15f) return 0.5f * (si[0] + si[1]);
   const float x = fabsf(pos / si[2]);
@@ -129,8 +136,8 @@ __device__ __forceinline__ float g_impedance(const float* si, float pos) {      
   if (x <= 0.f) return si[0];
   float y;
   if (si[4] == 1.f) y = x;
-  else if (x <= si[3]) y = powf(x, si[4]) / powf(si[3], si[4] - 1.f);
-  else y = 1.f - powf(1.f - x, si[4]) / powf(1.f - si[3], si[4] - 1.f);
+  else if (si[4] == 2.f) y = x <= si[3] ? x * x / si[3] : 1.f - (1.f - x) * (1.f - x) / (1.f - si[3]);      // MuJoCo's default power
+  else y = g_impedance_pow(x, si[3], si[4]);
   return si[0] + y * (si[1] - si[0]);
 }
 
@@ -147,12 +154,12 @@ struct EnvMemT {
   float com[4];
   float cinert[GM_MAXB][10], crb[GM_MAXB][10], cdof[GM_MAXV][6], cdofdot[GM_MAXV][6];
   float cvel[GM_MAXB][6], cacc[GM_MAXB][6], cfrc[GM_MAXB][6];
-  float M[GM_MAXV][GM_MAXV], L[GM_MAXV][GM_MAXV], H[GM_MAXV][GM_MAXV];
+  float M[GM_MAXV][GM_MAXV], H[GM_MAXV][GM_MAXV];
   float bias[GM_MAXV], smooth[GM_MAXV], qaccs[GM_MAXV], qacc[GM_MAXV], grad[GM_MAXV], dir[GM_MAXV], Ma[GM_MAXV], vec[GM_MAXV], fcon[GM_MAXV];
   // contacts
   int ncon, nefc, nlim, overflow;
   float cpos[MC][3], cdist[MC], cmu[MC];
-  int cgeom[MC], cadr[MC], cdim[MC], czone[MC];
+  int cgeom[MC], cadr[MC], cdim[MC], czone[MC], crow[MR];   // crow: contact that owns a row
   float cDm[MC], ccoef[MC], cb[MC][GM_MAXV];          // elliptic-cone curvature data (g_cone)
   // rows
   float J[MR][GM_MAXV];
@@ -161,45 +168,53 @@ struct EnvMemT {
   float rsgn[2 * GM_MAXV];
 };
 
-// dense Cholesky of the nv x nv matrix A (lower triangle used) into Lo, by the whole warp; returns false if not positive definite
-__device__ bool g_cholesky(float (*Lo)[GM_MAXV], const float (*A)[GM_MAXV], int n, int lane) {
+// x <- A^-1 x for the symmetric positive definite n x n matrix A (lower triangle read) by the whole warp, entirely in
+// registers: lane i holds row i and its right-hand side, elimination of column j broadcasts pivot row j by shuffles and
+// clears the column in ALL other rows (Gauss-Jordan: no pivoting needed for an SPD matrix, no back substitution, no
+// transposed access).  ~n^2/2 shuffle + FMA pairs and a dependent chain of ~50 cycles per column, against ~4000 instructions
+// and two shared-memory round trips per column of the left-looking Cholesky this replaces.  Returns false if a pivot is <= 0.
+template <int N>
+__device__ __noinline__ bool g_solve_spd_n(const float (*A)[GM_MAXV], float* x, int n, int lane) {
+  float h[N];
+  const int i = lane;
+#pragma unroll
+  for (int k = 0; k < N; k++) h[k] = (k == i) ? 1.f : 0.f;           // rows / columns beyond n: identity
+  if (i < n) {
+#pragma unroll
+    for (int k = 0; k < N; k++) if (k < n) h[k] = k <= i ? A[i][k] : A[k][i];
+  }
+  float b = i < n ? x[i] : 0.f, d = 1.f;
   bool ok = true;
-  for (int j = 0; j < n; j++) {
-    float s = 0.f;
-    if (lane == 0) {
-      s = A[j][j];
-      for (int k = 0; k < j; k++) s -= Lo[j][k] * Lo[j][k];
-      if (s < 1e-30f) { s = 1e-30f; ok = false; }
-      Lo[j][j] = sqrtf(s);
-    }
-    __syncwarp();
-    const float inv = 1.f / Lo[j][j];
-    for (int i = j + 1 + lane; i < n; i += 32) {
-      float t = A[i][j];
-      for (int k = 0; k < j; k++) t -= Lo[i][k] * Lo[j][k];
-      Lo[i][j] = t * inv;
-    }
-    __syncwarp();
+#pragma unroll
+  for (int j = 0; j < N; j++) {
+    float pj = __shfl_sync(0xffffffffu, h[j], j);
+    ok &= pj > 1e-30f;
+    pj = fmaxf(pj, 1e-30f);
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(pj));
+    r = fmaf(r, fmaf(-pj, r, 1.f), r);                       // one Newton step: correctly rounded to within an ulp, no slow path
+    d = i == j ? r : d;                                      // row j is final after its own column: 1 / its pivot
+    const float f = i == j ? 0.f : h[j] * r;
+#pragma unroll
+    for (int k = j + 1; k < N; k++) h[k] = fmaf(-f, __shfl_sync(0xffffffffu, h[k], j), h[k]);
+    b = fmaf(-f, __shfl_sync(0xffffffffu, b, j), b);
   }
-  return __all_sync(0xffffffffu, ok);
+  if (i < n) x[i] = b * d;
+  __syncwarp();
+  return ok;
 }
-// x <- (L L')^-1 x, x in shared memory; lane-parallel over rows below the pivot
-__device__ void g_cholsolve(const float (*Lo)[GM_MAXV], int n, float* x, int lane) {
-  for (int j = 0; j < n; j++) {
-    if (lane == 0) x[j] /= Lo[j][j];
-    __syncwarp();
-    const float xj = x[j];
-    for (int i = j + 1 + lane; i < n; i += 32) x[i] -= Lo[i][j] * xj;
-    __syncwarp();
-  }
-  for (int j = n - 1; j >= 0; j--) {
-    if (lane == 0) x[j] /= Lo[j][j];
-    __syncwarp();
-    const float xj = x[j];
-    for (int i = lane; i < j; i += 32) x[i] -= Lo[j][i] * xj;
-    __syncwarp();
-  }
+// sizes the code is instantiated for: the quadrupeds / hexapods of the reference (nv = 18, 24); anything smaller pads
+__device__ __forceinline__ bool g_solve_spd(const float (*A)[GM_MAXV], float* x, int n, int lane) {
+  return n <= 18 ? g_solve_spd_n<18>(A, x, n, lane) : g_solve_spd_n<GM_MAXV>(A, x, n, lane);
 }
+
+// (row, column) of the p-th entry of a lower triangle, p < 16 * 17 / 2
+__constant__ unsigned char g_tri_r[136] = {0, 1,1, 2,2,2, 3,3,3,3, 4,4,4,4,4, 5,5,5,5,5,5, 6,6,6,6,6,6,6, 7,7,7,7,7,7,7,7, 8,8,8,8,8,8,8,8,8, 9,9,9,9,9,9,9,9,9,9,
+  10,10,10,10,10,10,10,10,10,10,10, 11,11,11,11,11,11,11,11,11,11,11,11, 12,12,12,12,12,12,12,12,12,12,12,12,12, 13,13,13,13,13,13,13,13,13,13,13,13,13,13,
+  14,14,14,14,14,14,14,14,14,14,14,14,14,14,14, 15,15,15,15,15,15,15,15,15,15,15,15,15,15,15,15};
+__constant__ unsigned char g_tri_c[136] = {0, 0,1, 0,1,2, 0,1,2,3, 0,1,2,3,4, 0,1,2,3,4,5, 0,1,2,3,4,5,6, 0,1,2,3,4,5,6,7, 0,1,2,3,4,5,6,7,8, 0,1,2,3,4,5,6,7,8,9,
+  0,1,2,3,4,5,6,7,8,9,10, 0,1,2,3,4,5,6,7,8,9,10,11, 0,1,2,3,4,5,6,7,8,9,10,11,12, 0,1,2,3,4,5,6,7,8,9,10,11,12,13,
+  0,1,2,3,4,5,6,7,8,9,10,11,12,13,14, 0,1,2,3,4,5,6,7,8,9,10,11,12,13,14,15};
 
 // ---------------------------------------------------------------------------------------------- constraint rows
 // sqrt of a double from the fp32 rsqrt plus one Newton step in fp64 (relative error ~1e-14): the fp64 sqrt / divide are
@@ -221,23 +236,27 @@ __device__ __forceinline__ int g_cone(int dim, const double* j, const float* fri
     f[0] = 0.f; *cost = 0.f; return 0;
   }
   double U[6], T2 = 0.0, rT;
-  for (int k = 1; k < dim; k++) { U[k] = j[k] * (double)fri[k - 1]; T2 += U[k] * U[k]; }
+#pragma unroll
+  for (int k = 1; k < 6; k++) if (k < dim) { U[k] = j[k] * (double)fri[k - 1]; T2 += U[k] * U[k]; }
   const double N = j[0] * (double)mu, T = g_sqrt64(T2, &rT);
   if (N >= (double)mu * T || (T <= 0.0 && N >= 0.0)) {
-    for (int k = 0; k < dim; k++) f[k] = 0.f;
+#pragma unroll
+    for (int k = 0; k < 6; k++) f[k] = 0.f;
     *cost = 0.f;
     return 0;
   }
   if ((double)mu * N + T <= 0.0 || (T <= 0.0 && N < 0.0)) {
     float cs = 0.f;
-    for (int k = 0; k < dim; k++) { const float jj = (float)j[k]; f[k] = -D[k] * jj; cs += 0.5f * D[k] * jj * jj; }
+#pragma unroll
+    for (int k = 0; k < 6; k++) if (k < dim) { const float jj = (float)j[k]; f[k] = -D[k] * jj; cs += 0.5f * D[k] * jj * jj; }
     *cost = cs;
     return 1;
   }
   const float NmT = (float)(N - (double)mu * T);
   const float f0 = -Dm * NmT * mu;
   f[0] = f0;
-  for (int k = 1; k < dim; k++) { const float u = (float)(U[k] * rT) * fri[k - 1]; uh[k] = u; f[k] = -f0 * u; }
+#pragma unroll
+  for (int k = 1; k < 6; k++) if (k < dim) { const float u = (float)(U[k] * rT) * fri[k - 1]; uh[k] = u; f[k] = -f0 * u; }
   *cost = 0.5f * Dm * NmT * NmT;
   *ccoef = -Dm * mu * NmT * (float)rT;
   return 2;
@@ -254,58 +273,53 @@ __device__ __forceinline__ float g_simple(int type, float D, float R, float fl, 
   return -D * j;
 }
 
-// Forces, cost and curvature of every row at e.jar (written to e.force / e.Hd / e.czone / e.ccoef / e.cb); returns the cost.
+// Row evaluation at the residual e.jar + alpha * e.jv, one copy of the code for its three uses (the kernel is bound by
+// instruction fetch):  mode 0 = line search: returns sum_r force_r jv_r, stores nothing;  mode 1 = forces into e.force, returns
+// the cost;  mode 2 = mode 1 plus the curvature data (e.Hd / e.czone / e.ccoef / e.cb).  alpha is ignored unless mode == 0.
 template <class EnvMem>
-__device__ float g_rows(const GenModel& m, EnvMem& e, bool hess, int lane) {
-  float cost = 0.f;
-  const int nsimple = m.nfloss + e.nlim, nv = m.nv;
+__device__ __noinline__ float g_rows(const GenModel& m, EnvMem& e, int mode, float alpha, int lane) {
+  float acc = 0.f;
+  const int nsimple = m.nfloss + e.nlim;
   for (int r = lane; r < nsimple; r += 32) {
     float cs, hd;
-    e.force[r] = g_simple(e.rtype[r], e.D[r], e.R[r], e.floss[r], (float)e.jar[r], &cs, &hd);
-    cost += cs;
-    if (hess) e.Hd[r] = hd;
+    const float jv = mode == 0 ? e.jv[r] : 0.f;
+    const float f = g_simple(e.rtype[r], e.D[r], e.R[r], e.floss[r], (float)(mode == 0 ? e.jar[r] + (double)alpha * (double)jv : e.jar[r]), &cs, &hd);
+    if (mode == 0) acc += f * jv;
+    else { e.force[r] = f; acc += cs; if (mode == 2) e.Hd[r] = hd; }
   }
   for (int c = lane; c < e.ncon; c += 32) {
     const int a = e.cadr[c], dim = e.cdim[c];
     const float* fri = m.geom_friction[e.cgeom[c]];
+    double j[6];
+    float jv[6];
+#pragma unroll
+    for (int k = 0; k < 6; k++) if (k < dim) { j[k] = e.jar[a + k]; if (mode == 0) { jv[k] = e.jv[a + k]; j[k] += (double)alpha * (double)jv[k]; } }
     float f[6], uh[6], cs, cc = 0.f;
-    const int zone = g_cone(dim, e.jar + a, fri, e.cmu[c], e.D + a, e.cDm[c], f, &cs, uh, &cc);
-    for (int k = 0; k < dim; k++) e.force[a + k] = f[k];
-    cost += cs;
-    if (hess) {
+    const int zone = g_cone(dim, j, fri, e.cmu[c], e.D + a, e.cDm[c], f, &cs, uh, &cc);
+    if (mode == 0) {
+#pragma unroll
+      for (int k = 0; k < 6; k++) if (k < dim) acc += f[k] * jv[k];
+      continue;
+    }
+#pragma unroll
+    for (int k = 0; k < 6; k++) if (k < dim) e.force[a + k] = f[k];
+    acc += cs;
+    if (mode == 2) {
       e.czone[c] = zone;
       if (zone == 2) {
         e.ccoef[c] = cc;
-        for (int i = 0; i < nv; i++) {                     // b = sum_k friction_k u_k J_k
+        const int body = m.geom_body[e.cgeom[c]], nd = m.body_ndof[body];
+        for (int q = 0; q < nd; q++) {                     // b = sum_k friction_k u_k J_k, on the dofs of the body's chain
+          const int i = m.body_dofs[body][q];
           float t = 0.f;
-          for (int k = 1; k < dim; k++) t += uh[k] * e.J[a + k][i];
+#pragma unroll
+          for (int k = 1; k < 6; k++) if (k < dim) t += uh[k] * e.J[a + k][i];
           e.cb[c][i] = t;
         }
       }
     }
   }
-  return g_warpsum(cost);
-}
-
-// Line-search derivative term sum_r force_r(jar + alpha jv) jv_r: every lane evaluates its own rows, nothing is stored
-template <class EnvMem>
-__device__ float g_rows_dot(const GenModel& m, const EnvMem& e, float alpha, int lane) {
-  float s = 0.f;
-  const int nsimple = m.nfloss + e.nlim;
-  for (int r = lane; r < nsimple; r += 32) {
-    float cs, hd;
-    const float jv = e.jv[r];
-    s += g_simple(e.rtype[r], e.D[r], e.R[r], e.floss[r], (float)(e.jar[r] + (double)alpha * (double)jv), &cs, &hd) * jv;
-  }
-  for (int c = lane; c < e.ncon; c += 32) {
-    const int a = e.cadr[c], dim = e.cdim[c];
-    double j[6];
-    for (int k = 0; k < dim; k++) j[k] = e.jar[a + k] + (double)alpha * (double)e.jv[a + k];
-    float f[6], uh[6], cs, cc;
-    g_cone(dim, j, m.geom_friction[e.cgeom[c]], e.cmu[c], e.D + a, e.cDm[c], f, &cs, uh, &cc);
-    for (int k = 0; k < dim; k++) s += f[k] * e.jv[a + k];
-  }
-  return g_warpsum(s);
+  return g_warpsum(acc);
 }
 
 // ================================================================================================ the kernel
@@ -323,19 +337,27 @@ __global__ void __launch_bounds__(WARPS * 32) nm_generic_step_kernel(const GenAr
   const int nv = m.nv, nq = m.nq, nb = m.nbody, nu = m.nu;
   const float h = m.timestep;
   const int nwork = FIRST ? A.num_envs : min(A.ovf[0], A.num_envs);
-  for (int item = blockIdx.x * WARPS + warp; item < nwork; item += gridDim.x * WARPS) {   // (FIRST: the grid covers the batch, one trip)
-  const int env = FIRST ? item : A.ovf[1 + 2 * item];
-  const int nstep = FIRST ? A.nstep : A.ovf[2 + 2 * item];
+  // The warps of a CTA run in LOCKSTEP through the substeps and the Newton iterations (CTA barriers at the top of every
+  // Newton trip): the kernel is bound by instruction fetch (ncu: 72 % of the stall samples were no_inst with eight warps per SM
+  // each at its own place in ~50 KB of code against a 32 KB instruction cache); warps that walk the code together share the fetches.
+  // `live` = this warp has an environment to work on; warps without one (tail of the batch, handed over) still meet the barriers.
+  for (int base = blockIdx.x * WARPS; base < nwork; base += gridDim.x * WARPS) {        // (FIRST: the grid covers the batch, one trip)
+  const int item = base + warp;
+  bool live = item < nwork;
+  const int env = !live ? 0 : FIRST ? item : A.ovf[1 + 2 * item];
+  const int nstep = FIRST ? A.nstep : (live ? A.ovf[2 + 2 * item] : 0);          // uniform over the CTA (the second tier has one warp per CTA)
   __syncwarp();
 
-  for (int i = lane; i < nq; i += 32) e.qpos[i] = A.qpos[(size_t)env * nq + i];
-  for (int i = lane; i < nv; i += 32) { e.qvel[i] = A.qvel[(size_t)env * nv + i]; e.warm[i] = A.warm[(size_t)env * nv + i]; }
-  for (int i = lane; i < nu; i += 32) e.ctrl[i] = A.ctrl[(size_t)env * nu + i];
+  if (live) {
+    for (int i = lane; i < nq; i += 32) e.qpos[i] = A.qpos[(size_t)env * nq + i];
+    for (int i = lane; i < nv; i += 32) { e.qvel[i] = A.qvel[(size_t)env * nv + i]; e.warm[i] = A.warm[(size_t)env * nv + i]; }
+    for (int i = lane; i < nu; i += 32) e.ctrl[i] = A.ctrl[(size_t)env * nu + i];
+  }
   int niter_last = 0;
-  bool handed_over = false;
   __syncwarp();
 
   for (int sub = 0; sub < nstep; sub++) {
+    if (live) do {
     // ------------------------------------------------------------------ divergence guard (≙ mj_checkPos / mj_checkVel)
     {
       bool bad = false;
@@ -463,7 +485,6 @@ __global__ void __launch_bounds__(WARPS * 32) nm_generic_step_kernel(const GenAr
       e.M[i][i] += m.dof_armature[i];
     }
     __syncwarp();
-    g_cholesky(e.L, e.M, nv, lane);
     // ------------------------------------------------------------------ P7 comVel + RNE
     if (lane == 0) for (int k = 0; k < 6; k++) { e.cvel[0][k] = 0.f; e.cacc[0][k] = k >= 3 ? -m.gravity[k - 3] : 0.f; }
     __syncwarp();
@@ -518,7 +539,7 @@ __global__ void __launch_bounds__(WARPS * 32) nm_generic_step_kernel(const GenAr
     __syncwarp();
     for (int i = lane; i < nv; i += 32) e.qaccs[i] = e.smooth[i];
     __syncwarp();
-    g_cholsolve(e.L, nv, e.qaccs, lane);
+    g_solve_spd(e.M, e.qaccs, nv, lane);
     // ------------------------------------------------------------------ P4 collision: sphere / box / cylinder against the plane
     {
       int base = 0;
@@ -654,7 +675,9 @@ __global__ void __launch_bounds__(WARPS * 32) nm_generic_step_kernel(const GenAr
         for (int c = 0; c < e.ncon; c++) {
           const int dim = m.geom_dim[e.cgeom[c]];
           if (r + dim > MR) { e.overflow = 1; break; }
-          e.cadr[c] = r; e.cdim[c] = dim; r += dim; nc++;
+          e.cadr[c] = r; e.cdim[c] = dim;
+          for (int k = 0; k < dim; k++) e.crow[r + k] = c;
+          r += dim; nc++;
         }
         e.ncon = nc; e.nefc = r;
       }
@@ -666,7 +689,7 @@ __global__ void __launch_bounds__(WARPS * 32) nm_generic_step_kernel(const GenAr
           const int k = atomicAdd(A.ovf, 1);
           A.ovf[1 + 2 * k] = env; A.ovf[2 + 2 * k] = nstep - sub;
         }
-        handed_over = true;
+        live = false;
         break;
       }
       // contact Jacobians: one (contact, dof) pair per lane trip, all rows of the contact at once
@@ -712,25 +735,30 @@ __global__ void __launch_bounds__(WARPS * 32) nm_generic_step_kernel(const GenAr
       }
       __syncwarp();
     }
+    } while (0);
     // ------------------------------------------------------------------ P9 Newton solver on the primal problem
-    const int ne = e.nefc, nsimple = m.nfloss + e.nlim;
+    const int ne = live ? e.nefc : 0, nsimple = live ? m.nfloss + e.nlim : 0;
     int niter = 0;
     if (ne == 0) {
-      for (int i = lane; i < nv; i += 32) { e.qacc[i] = e.qaccs[i]; e.fcon[i] = 0.f; }
+      if (live) for (int i = lane; i < nv; i += 32) { e.qacc[i] = e.qaccs[i]; e.fcon[i] = 0.f; }
       __syncwarp();
-    } else {
+    }
+    {
       // residual jar = J x - aref in fp64 from the fp64 iterate; simple rows touch one dof, contact rows the dofs of their body's chain
       auto residual = [&](const double* x) {
         for (int r = lane; r < ne; r += 32) {
           double t = -(double)e.aref[r];
           if (r < nsimple) t += (double)e.rsgn[r] * x[e.rdof[r]];
-          else for (int i = 0; i < nv; i++) t += (double)e.J[r][i] * x[i];
+          else {
+            const int body = m.geom_body[e.cgeom[e.crow[r]]], nd = m.body_ndof[body];
+            for (int q = 0; q < nd; q++) { const int i = m.body_dofs[body][q]; t += (double)e.J[r][i] * x[i]; }
+          }
           e.jar[r] = t;
         }
       };
       // start from the cheaper of qacc_warmstart and qacc_smooth
-      float cost2[2];
-      for (int s = 0; s < 2; s++) {
+      float cost2[2] = {0.f, 0.f};
+      if (ne > 0) for (int s = 0; s < 2; s++) {
         const float* q = s == 0 ? e.warm : e.qaccs;
         for (int i = lane; i < nv; i += 32) { e.vec[i] = q[i] - e.qaccs[i]; e.xd[i] = (double)q[i]; }
         __syncwarp();
@@ -738,21 +766,24 @@ __global__ void __launch_bounds__(WARPS * 32) nm_generic_step_kernel(const GenAr
         if (s == 0) for (int i = lane; i < nv; i += 32) { float t = 0.f; for (int k = 0; k < nv; k++) t += e.M[i][k] * e.vec[k]; cg += 0.5f * e.vec[i] * t; }
         residual(e.xd);
         __syncwarp();
-        cost2[s] = g_warpsum(cg) + g_rows(m, e, false, lane);
+        cost2[s] = g_warpsum(cg) + g_rows(m, e, 1, 0.f, lane);
         __syncwarp();
       }
-      if (cost2[0] < cost2[1]) { for (int i = lane; i < nv; i += 32) e.xd[i] = (double)e.warm[i]; }
+      if (ne > 0 && cost2[0] < cost2[1]) { for (int i = lane; i < nv; i += 32) e.xd[i] = (double)e.warm[i]; }
       __syncwarp();
       float gprev = 1e30f;
-      // every trip evaluates forces and gradient at the current iterate FIRST, so whenever the loop is left the forces in
+      bool active = ne > 0;                                          // (warp-uniform)
+      // every trip evaluates forces and gradient at the current iterate FIRST, so whenever a warp stops iterating the forces in
       // e.force / e.fcon belong to the returned qacc
       for (int it = 0;; it++) {
+        if (__syncthreads_and(!active)) break;                       // lockstep: all warps of the CTA start a Newton trip together
+        if (active) do {
         niter = it;
         for (int i = lane; i < nv; i += 32) e.vec[i] = (float)(e.xd[i] - (double)e.qaccs[i]);
         residual(e.xd);
         __syncwarp();
         for (int i = lane; i < nv; i += 32) { float t = 0.f; for (int k = 0; k < nv; k++) t += e.M[i][k] * e.vec[k]; e.Ma[i] = t; }
-        g_rows(m, e, true, lane);
+        g_rows(m, e, 2, 0.f, lane);
         __syncwarp();
         float gn = 0.f, gref = 0.f;
         for (int i = lane; i < nv; i += 32) {
@@ -773,59 +804,70 @@ __global__ void __launch_bounds__(WARPS * 32) nm_generic_step_kernel(const GenAr
         // MuJoCo's test (scaled gradient below opt.tolerance); or the gradient is at the fp32 rounding of its two terms; or it is
         // small and has stopped shrinking (Newton's quadratic phase ended in rounding noise: more steps only wander)
         const bool quad = gn <= 1e-10f * gref;                     // Newton's quadratic phase: full steps, no line search
-        if (m.solver_scale * sqrtf(gn) < m.tolerance || gn <= 1e-16f * gref || (quad && gn >= 0.25f * gprev) || it >= m.iterations) break;
+        if (m.solver_scale * sqrtf(gn) < m.tolerance || gn <= 1e-16f * gref || (quad && gn >= 0.25f * gprev) || it >= m.iterations) { active = false; break; }
         gprev = gn;
-        // Hessian (lower triangle) H = M + sum_r Hd_r J_r J_r' + cone terms.  Simple rows add to the diagonal; a contact in the
-        // bottom zone adds its rows weighted by D, one on the cone adds Dm mu^2 (J0 - b)(J0 - b)' + c (sum_k fri_k^2 J_k J_k' - b b')
-        for (int idx = lane; idx < nv * (nv + 1) / 2; idx += 32) {
-          int i = (int)((sqrtf(8.f * idx + 1.f) - 1.f) * 0.5f);
-          while ((i + 1) * (i + 2) / 2 <= idx) i++;
-          while (i * (i + 1) / 2 > idx) i--;
-          const int k = idx - i * (i + 1) / 2;
-          float s = e.M[i][k];
-          for (int c = 0; c < e.ncon; c++) {
-            const int zone = e.czone[c];
-            if (zone == 0) continue;
-            const int a = e.cadr[c], dim = e.cdim[c];
+        // Hessian (lower triangle) H = M + sum_r Hd_r J_r J_r' + cone terms.  Simple rows add to the diagonal; a contact only
+        // touches the dofs of its body's chain (9 of 18 for a leg): a bottom-zone contact adds its rows weighted by D, one on the
+        // cone adds Dm mu^2 (J0 - b)(J0 - b)' + c (sum_k fri_k^2 J_k J_k' - b b').  One contact at a time, its chain pairs over the lanes.
+        for (int idx = lane; idx < nv * nv; idx += 32) { const int i = idx / nv, k = idx - i * nv; if (k <= i) e.H[i][k] = e.M[i][k]; }
+        __syncwarp();
+        for (int i = lane; i < nv; i += 32) { const int fr = m.dof_flossrow[i]; if (fr >= 0) e.H[i][i] += e.Hd[fr]; }
+        __syncwarp();
+        for (int r = m.nfloss + lane; r < nsimple; r += 32) e.H[e.rdof[r]][e.rdof[r]] += e.Hd[r];
+        __syncwarp();
+        for (int c = 0; c < e.ncon; c++) {
+          const int zone = e.czone[c];
+          if (zone == 0) continue;
+          const int a = e.cadr[c], dim = e.cdim[c], body = m.geom_body[e.cgeom[c]], nd = m.body_ndof[body];
+          const float* fri = m.geom_friction[e.cgeom[c]];
+          const float w0 = e.cDm[c] * e.cmu[c] * e.cmu[c], cc = e.ccoef[c];
+          for (int p = lane; p < nd * (nd + 1) / 2; p += 32) {
+            const int i = m.body_dofs[body][g_tri_r[p]], k = m.body_dofs[body][g_tri_c[p]];
+            float s = 0.f;
             if (zone == 1) { for (int j = 0; j < dim; j++) s += e.D[a + j] * e.J[a + j][i] * e.J[a + j][k]; }
             else {
-              const float* fri = m.geom_friction[e.cgeom[c]];
-              const float mu = e.cmu[c], cc = e.ccoef[c], bi = e.cb[c][i], bk = e.cb[c][k];
+              const float bi = e.cb[c][i], bk = e.cb[c][k];
               float t = 0.f;
               for (int j = 1; j < dim; j++) t += fri[j - 1] * fri[j - 1] * e.J[a + j][i] * e.J[a + j][k];
-              s += e.cDm[c] * mu * mu * (e.J[a][i] - bi) * (e.J[a][k] - bk) + cc * (t - bi * bk);
+              s = w0 * (e.J[a][i] - bi) * (e.J[a][k] - bk) + cc * (t - bi * bk);
             }
+            e.H[i][k] += s;
           }
-          e.H[i][k] = s;
+          __syncwarp();
         }
-        __syncwarp();
-        for (int r = lane; r < nsimple; r += 32) { const int i = e.rdof[r]; if (e.Hd[r] != 0.f) atomicAdd(&e.H[i][i], e.Hd[r]); }
-        __syncwarp();
-        if (!g_cholesky(e.H, e.H, nv, lane)) break;                 // in place: only the lower triangle is read
         for (int i = lane; i < nv; i += 32) e.dir[i] = -e.grad[i];
         __syncwarp();
-        g_cholsolve(e.H, nv, e.dir, lane);
+        if (!g_solve_spd(e.H, e.dir, nv, lane)) { active = false; break; }
         if (quad) {
+          // quadratic phase (relative gradient <= 1e-5): full Newton steps without a line search.  At a relative gradient
+          // <= 1e-6 the step lands below the fp32 rounding of the gradient (1e-12 relative in exact arithmetic): it is taken and
+          // the iteration ends without evaluating the rows again -- the integrator below works from qacc alone
           for (int i = lane; i < nv; i += 32) e.xd[i] += (double)e.dir[i];
+          if (gn <= 1e-12f * gref) { niter = it + 1; active = false; }
           __syncwarp();
-          continue;
+          break;
         }
         // line search on phi'(alpha) = a1 + alpha a2 - sum_r force_r(jar + alpha jv) jv_r (increasing in alpha), to MuJoCo's
         // relative tolerance class: |phi'| <= 0.1 |phi'(0)| (exactness buys nothing: the outer Newton iteration corrects it)
         for (int r = lane; r < ne; r += 32) {
           float t = 0.f;
           if (r < nsimple) t = e.rsgn[r] * e.dir[e.rdof[r]];
-          else for (int i = 0; i < nv; i++) t += e.J[r][i] * e.dir[i];
+          else {
+            const int body = m.geom_body[e.cgeom[e.crow[r]]], nd = m.body_ndof[body];
+            for (int q = 0; q < nd; q++) { const int i = m.body_dofs[body][q]; t += e.J[r][i] * e.dir[i]; }
+          }
           e.jv[r] = t;
         }
         float a1 = 0.f, a2 = 0.f;
         for (int i = lane; i < nv; i += 32) { float t = 0.f; for (int k = 0; k < nv; k++) t += e.M[i][k] * e.dir[k]; a1 += e.dir[i] * e.Ma[i]; a2 += e.dir[i] * t; }
         a1 = g_warpsum(a1); a2 = g_warpsum(a2);
         __syncwarp();
-        auto dphi = [&](float alpha) -> float { return a1 + alpha * a2 - g_rows_dot(m, e, alpha, lane); };
+        auto dphi = [&](float alpha) -> float { return a1 + alpha * a2 - g_rows(m, e, 0, alpha, lane); };
         float lo = 0.f, hi = 1.f, alpha = 1.f;
-        float flo = dphi(0.f);
-        if (!(flo < 0.f)) break;
+        float flo = 0.f;                                             // phi'(0) = dir . grad
+        for (int i = lane; i < nv; i += 32) flo += e.dir[i] * e.grad[i];
+        flo = g_warpsum(flo);
+        if (!(flo < 0.f)) { active = false; break; }
         const float tol = 0.1f * fabsf(flo);
         float fhi = dphi(hi);
         if (fabsf(fhi) > tol) {
@@ -846,10 +888,12 @@ __global__ void __launch_bounds__(WARPS * 32) nm_generic_step_kernel(const GenAr
         }
         for (int i = lane; i < nv; i += 32) e.xd[i] += (double)alpha * (double)e.dir[i];
         __syncwarp();
+        } while (0);
       }
-      for (int i = lane; i < nv; i += 32) e.qacc[i] = (float)e.xd[i];
+      if (ne > 0) for (int i = lane; i < nv; i += 32) e.qacc[i] = (float)e.xd[i];
       __syncwarp();
     }
+    if (live) {
     niter_last = niter;
     for (int i = lane; i < nv; i += 32) e.warm[i] = e.qacc[i];
     // ------------------------------------------------------------------ P11 Euler with implicit joint damping, position integration
@@ -858,11 +902,14 @@ __global__ void __launch_bounds__(WARPS * 32) nm_generic_step_kernel(const GenAr
       for (int i = lane; i < nv; i += 32) any_damp |= m.dof_damping[i] > 0.f;
       any_damp = __any_sync(0xffffffffu, any_damp) && m.eulerdamp;
       if (any_damp) {
-        for (int idx = lane; idx < nv * nv; idx += 32) { const int i = idx / nv, k = idx % nv; e.H[i][k] = e.M[i][k] + (i == k ? h * m.dof_damping[i] : 0.f); }
-        for (int i = lane; i < nv; i += 32) e.vec[i] = e.smooth[i] + e.fcon[i];
+        // (M + h D) a = qfrc_smooth + qfrc_constraint = M qacc at the solver's optimum  =>  a = qacc - h (M + h D)^-1 D qacc:
+        // the correction is O(h), so its rounding does not matter, and no constraint force has to be formed
+        for (int idx = lane; idx < nv * nv; idx += 32) { const int i = idx / nv, k = idx - i * nv; e.H[i][k] = e.M[i][k] + (i == k ? h * m.dof_damping[i] : 0.f); }
+        for (int i = lane; i < nv; i += 32) e.vec[i] = m.dof_damping[i] * e.qacc[i];
         __syncwarp();
-        g_cholesky(e.H, e.H, nv, lane);
-        g_cholsolve(e.H, nv, e.vec, lane);
+        g_solve_spd(e.H, e.vec, nv, lane);
+        for (int i = lane; i < nv; i += 32) e.vec[i] = e.qacc[i] - h * e.vec[i];
+        __syncwarp();
       } else {
         for (int i = lane; i < nv; i += 32) e.vec[i] = e.qacc[i];
         __syncwarp();
@@ -888,8 +935,9 @@ __global__ void __launch_bounds__(WARPS * 32) nm_generic_step_kernel(const GenAr
       for (int b = 2 + lane; b < nb; b += 32) e.qpos[m.body_qadr[b]] += h * e.qvel[m.body_dofadr[b]];
       __syncwarp();
     }
+    }
   }
-  if (handed_over) continue;
+  if (!live) continue;
   for (int i = lane; i < nq; i += 32) A.qpos[(size_t)env * nq + i] = e.qpos[i];
   for (int i = lane; i < nv; i += 32) { A.qvel[(size_t)env * nv + i] = e.qvel[i]; A.warm[(size_t)env * nv + i] = e.warm[i]; }
   if (A.info != nullptr && lane == 0) {
@@ -1016,6 +1064,9 @@ extern "C" int nm_gen_model_from_buffer(const void* data, size_t nbytes, nm_gen_
     int mask = 0;
     for (int i = M.body_dofadr[b] + (b == 1 ? 5 : 0); i >= 0; i = dof_parent[i]) mask |= 1 << i;
     M.body_dofmask[b] = mask;
+    int nd = 0;
+    for (int i = 0; i < nv; i++) if ((mask >> i) & 1) { if (nd >= GM_MAXCHAIN) return bail(NM_ERR_UNSUPPORTED, "generic step: kinematic chains of at most 16 dofs"); M.body_dofs[b][nd++] = i; }
+    M.body_ndof[b] = nd;
   }
   std::vector<int> used(nv, 0);
   for (int a = 0; a < nu; a++) {
