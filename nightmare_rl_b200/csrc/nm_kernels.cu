@@ -756,12 +756,14 @@ enum { RW_ACTION_RATE = 0, RW_ANG_VEL_XY, RW_BASE_HEIGHT, RW_BODY_CONTACT_FORCES
        RW_STAND_STILL, RW_TERMINATION, RW_TORQUES, RW_TRACKING_ANG_VEL, RW_TRACKING_LIN_VEL };
 
 // ================================================================================================ the step kernel
-// Two register budgets of the same code: <BLOCK=128, MINB=2> (255 registers, 8 warps/SM) has the shortest single-warp
-// latency and serves batches that fit one wave; <BLOCK=256, MINB=2> (128 registers, 16 warps/SM, some spills) has twice
-// the envs per SM marching through the code together and serves large batches.
+// Two launch shapes of the same code, both on the 255-register budget (8 warps/SM): <BLOCK=128, MINB=2> for batches that fit
+// one wave, <BLOCK=256, MINB=1> (one CTA per SM, its eight warps marching through the code together) for large batches.
+// Measured at 131 072 envs (round 2, gpurun_out/r02_qb13.log): <256,1> 74.7 M env-steps/s, <256,2> (128 registers, 16 warps/SM,
+// spills) 71.3 M, <384,1> 66.8 M, <512,1> 63.2 M; at 4096 envs <64,4>, <128,2> and <256,1> all take 88.8 us -- one wave is
+// as slow as its slowest warp, whatever shares the SM with it.
 #ifndef NM_LARGE_BLOCK
 #define NM_LARGE_BLOCK 256
-#define NM_LARGE_MINB 2
+#define NM_LARGE_MINB 1
 #endif
 #ifndef NM_SMALL_BLOCK
 #define NM_SMALL_BLOCK 128
