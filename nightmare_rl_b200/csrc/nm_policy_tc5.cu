@@ -37,6 +37,7 @@ struct T5Args {
   const float* obs; int obs_stride; int n;
   unsigned long long seed; long long step, env_offset;
   int deterministic, act_dim;
+  int split;               // 1: grid.y = 2, CTA (x, 0) runs the critic and CTA (x, 1) the actor of tile x (small batches: twice the CTAs, half the layer chain)
   float* actions; float* mean; float* value; float* logp; float* obs_copy; float* sigma_out;
 };
 
@@ -65,14 +66,19 @@ __device__ __forceinline__ void t5_mma(unsigned tmem_d, unsigned long long a, un
   asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
                ::"r"(tmem_d), "l"(a), "l"(b), "r"(idesc), "r"(accumulate) : "memory");
 }
-__device__ __forceinline__ void t5_ld8(unsigned taddr, float* v) {
-  unsigned r[8];
+// issue one 8-column accumulator load; the registers are valid only after t5_ld_wait (which names them, so that neither the
+// compiler nor ptxas can schedule a consumer ahead of the wait)
+__device__ __forceinline__ void t5_ld8_issue(unsigned taddr, unsigned* r) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
                : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 8; i++) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void t5_ld_wait(unsigned* r /*[32]*/) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]), "+r"(r[9]), "+r"(r[10]),
+                 "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]),
+                 "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+               :: "memory");
 }
 
 __device__ __noinline__ void t5_philox(unsigned k0, unsigned k1, unsigned c0, unsigned c1, unsigned c2, unsigned c3, unsigned* out) {
@@ -150,15 +156,20 @@ __device__ __forceinline__ void t5_net(const T5Net& net, const float* X_hi, cons
     const int kp_next = L.npad, ncol = L.npad >> 1, cbeg = half * ncol;      // this warp's column range [cbeg, cbeg + ncol)
     const unsigned taddr = tmem + ((unsigned)((warp & 3) * 32) << 16) + (unsigned)cbeg;
     const int rbase = (row >> 3) * (kp_next >> 2) * 32 + (row & 7) * 4;
+    unsigned acc[32];                                          // this thread's half row of the accumulator: all loads in flight, one wait
+#pragma unroll
+    for (int i = 0; i < 32; i++) acc[i] = 0u;
+#pragma unroll
+    for (int cc = 0; cc < T5_TMEM_COLS / 16; cc++)
+      if (cc * 8 < ncol) t5_ld8_issue(taddr + (unsigned)(cc * 8), acc + cc * 8);
+    t5_ld_wait(acc);
 #pragma unroll
     for (int cc = 0; cc < T5_TMEM_COLS / 16; cc++) {           // compile-time column blocks keep out[] in registers
       if (cc * 8 < ncol) {
-        float v[8];
-        t5_ld8(taddr + (unsigned)(cc * 8), v);
 #pragma unroll
         for (int i = 0; i < 8; i++) {
           const int col = cbeg + cc * 8 + i;
-          float x = v[i] + bias[L.b_off + col];
+          float x = __uint_as_float(acc[cc * 8 + i]) + bias[L.b_off + col];
           if (last) { if (cc < 2) out[(cc < 2 ? cc : 0) * 8 + i] = x; }
           else {
             x = (col < L.kout) ? (x > 0.f ? x : __expf(x) - 1.f) : 0.f;      // ELU; padded columns stay exactly zero
@@ -204,29 +215,53 @@ __global__ void __launch_bounds__(T5_THREADS, 1) nm_policy_tc5_kernel(const T5Ar
   const int row0 = blockIdx.x * T5_ROWS;
   unsigned phase = 0;
   const int a_floats = 2 * A.actor.plane_floats + A.actor.bias_floats;
-  if (tid == 0) t5_issue_weights(A.critic, A.packed + a_floats, W, &wbar);     // lands while the observations are staged
-  // observations: staged once (both networks read them), split into TF32 hi/lo planes in the UMMA operand layout
-  for (int idx = tid; idx < T5_ROWS * kp0; idx += T5_THREADS) {
-    const int r = idx / kp0, c = idx - r * kp0;
-    const int e = row0 + r;
-    const float x = (c < kin && e < A.n) ? A.obs[(size_t)e * A.obs_stride + c] : 0.f;
-    const unsigned h = t5_tf32(x);
-    const int j = t5_idx(r, c, kp0);
-    X_hi[j] = __uint_as_float(h);
-    X_lo[j] = __uint_as_float(t5_tf32(x - __uint_as_float(h)));
-    if (A.obs_copy != nullptr && c < kin && e < A.n) A.obs_copy[(size_t)e * kin + c] = x;
+  const bool do_critic = !A.split || blockIdx.y == 0, do_actor = !A.split || blockIdx.y == 1;
+  if (tid == 0) t5_issue_weights(do_critic ? A.critic : A.actor, do_critic ? A.packed + a_floats : A.packed, W, &wbar);     // lands while the observations are staged
+  // observations: split into TF32 hi/lo planes in the UMMA operand layout.  A warp covers 8 rows x 4 columns per trip
+  // (lane = 4 * (row & 7) + (col & 3)): that is exactly one shared-memory bank per lane in the canonical layout, the global
+  // reads are eight 16-byte row segments, and the 18 trips of a row group are independent loads in flight together (the first
+  // version walked a flat index: a division per element, 8-way bank conflicts, one exposed load latency per element --
+  // half of the kernel's time at 4096 observations, profiles/r02_policy_tc5_metrics.txt)
+  {
+    const int nq = kp0 >> 2;                                   // column quads (18 for 66 -> 72 inputs)
+    for (int g = warp; g < T5_ROWS / 8; g += T5_THREADS / 32) {
+      const int r = g * 8 + (lane >> 2), e = row0 + r, cl = lane & 3;
+      const float* src = A.obs + (size_t)(e < A.n ? e : 0) * A.obs_stride;
+      float xv[18];
+#pragma unroll
+      for (int q = 0; q < 18; q++) {
+        const int c = q * 4 + cl;
+        xv[q] = (q < nq && c < kin && e < A.n) ? __ldg(src + c) : 0.f;
+      }
+      const int jb = (r >> 3) * nq * 32 + (r & 7) * 4 + cl;
+#pragma unroll
+      for (int q = 0; q < 18; q++) {
+        if (q < nq) {
+          const float x = xv[q];
+          const unsigned h = t5_tf32(x);
+          X_hi[jb + q * 32] = __uint_as_float(h);
+          X_lo[jb + q * 32] = x - __uint_as_float(h);          // exact in fp32; the tensor core drops lo's own low bits (< 2^-21 |x|)
+          const int c = q * 4 + cl;
+          if (A.obs_copy != nullptr && do_critic && c < kin && e < A.n) A.obs_copy[(size_t)e * kin + c] = x;
+        }
+      }
+    }
   }
   float vout[16], mout[16];
-  t5_net(A.critic, X_hi, X_lo, H_hi, H_lo, W, tmem, &bar, phase, &wbar, 0u, vout);
-  if (tid == 0) t5_issue_weights(A.actor, A.packed, W, &wbar);                 // critic MMAs are complete: reuse the buffer
-  t5_net(A.actor, X_hi, X_lo, H_hi, H_lo, W, tmem, &bar, phase, &wbar, 1u, mout);
+  unsigned wpar = 0u;
+  if (do_critic) {
+    t5_net(A.critic, X_hi, X_lo, H_hi, H_lo, W, tmem, &bar, phase, &wbar, wpar, vout);
+    wpar ^= 1u;
+    if (do_actor && tid == 0) t5_issue_weights(A.actor, A.packed, W, &wbar);   // critic MMAs are complete: reuse the buffer
+  }
+  if (do_actor) t5_net(A.actor, X_hi, X_lo, H_hi, H_lo, W, tmem, &bar, phase, &wbar, wpar, mout);
 
   // ---- epilogue: thread (row, half) = environment row of the tile, action columns [16*half, 16*half + 16)
   const int row = (warp & 3) * 32 + lane, half = warp >> 2;
   const int e = row0 + row;
-  if (e < A.n) {
+  if (e < A.n && do_critic && half == 0) A.value[e] = vout[0];
+  if (e < A.n && do_actor) {
     const float* stdv = A.packed + a_floats + 2 * A.critic.plane_floats + A.critic.bias_floats;
-    if (half == 0) A.value[e] = vout[0];
     float lp = 0.f;
 #pragma unroll
     for (int qq = 0; qq < 4; qq++) {
@@ -263,7 +298,7 @@ __global__ void __launch_bounds__(T5_THREADS, 1) nm_policy_tc5_kernel(const T5Ar
     atomicAdd(lp_s + row, lp);
   }
   __syncthreads();
-  if (tid < T5_ROWS && row0 + tid < A.n) A.logp[row0 + tid] = lp_s[tid];
+  if (do_actor && tid < T5_ROWS && row0 + tid < A.n) A.logp[row0 + tid] = lp_s[tid];
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((unsigned)T5_TMEM_COLS) : "memory");
 }
 
@@ -303,7 +338,7 @@ __global__ void nm_policy_tc5_pack_kernel(T5Net net, const float* src, float* ds
 // ------------------------------------------------------------------------------------------------ host side
 struct nm_policy_tc5 {
   T5Net actor, critic;
-  int act_dim, obs_dim;
+  int act_dim, obs_dim, sms;
   float* d_packed;
   int packed_floats;
   size_t smem_bytes;
@@ -355,6 +390,8 @@ extern "C" int nm_policy_tc5_create(const nm_mlp_shape* actor, const nm_mlp_shap
     delete p;
     return nm_fail(NM_ERR_CUDA, "nm_policy_tc5_create: CUDA allocation failed");
   }
+  cudaDeviceProp prop;
+  p->sms = cudaGetDeviceProperties(&prop, device) == cudaSuccess ? prop.multiProcessorCount : 148;
   *out = p;
   return NM_OK;
 }
@@ -387,7 +424,11 @@ extern "C" int nm_policy_tc5_act(nm_policy_tc5* p, const float* obs, int obs_str
   a.obs = obs; a.obs_stride = obs_stride; a.n = n; a.seed = seed; a.step = step; a.env_offset = env_offset;
   a.deterministic = deterministic; a.act_dim = p->act_dim;
   a.actions = actions; a.mean = mean; a.value = value; a.logp = logp; a.obs_copy = obs_copy; a.sigma_out = sigma_out;
-  nm_policy_tc5_kernel<<<(n + T5_ROWS - 1) / T5_ROWS, T5_THREADS, p->smem_bytes, static_cast<cudaStream_t>(stream)>>>(a);
+  // a batch whose tiles do not fill the SMs twice over runs the two networks of a tile on two CTAs (4096 observations: 64 CTAs
+  // with a 4-layer chain each instead of 32 with 8); larger batches keep one CTA per tile (observations staged once)
+  const int tiles = (n + T5_ROWS - 1) / T5_ROWS;
+  a.split = 2 * tiles <= p->sms ? 1 : 0;
+  nm_policy_tc5_kernel<<<dim3(tiles, a.split ? 2 : 1), T5_THREADS, p->smem_bytes, static_cast<cudaStream_t>(stream)>>>(a);
   if (cudaGetLastError() != cudaSuccess) return nm_fail(NM_ERR_CUDA, "nm_policy_tc5_act: launch failed");
   return NM_OK;
 }
