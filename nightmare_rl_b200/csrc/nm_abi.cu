@@ -103,8 +103,8 @@ static void local_inertia(const double* iquat, const double* diag, float* out) {
 static int build_device_model(nm_model* m) {
   const int *sizes, *oi;
   const double* orl;
-  long long n_oi = 0;
-  if (!get(m, "sizes", 2, sizes) || !get(m, "opt_int", 2, oi, &n_oi) || !get(m, "opt_real", 0, orl))
+  long long n_oi = 0, n_orl = 0;
+  if (!get(m, "sizes", 2, sizes) || !get(m, "opt_int", 2, oi, &n_oi) || !get(m, "opt_real", 0, orl, &n_orl))
     return fail(NM_ERR_FORMAT, "nmb: missing header arrays (sizes/opt_int/opt_real)");
   m->nq = sizes[0]; m->nv = sizes[1]; m->nu = sizes[2]; m->nbody = sizes[3]; m->njnt = sizes[4];
   m->ngeom = sizes[5]; m->nsite = sizes[6]; m->nsensor = sizes[7]; m->nhv = sizes[8]; m->nhn = sizes[9];
@@ -214,6 +214,7 @@ static int build_device_model(nm_model* m) {
       plane = g;
     }
   const double opt_timestep = orl[0], impratio = orl[6], meaninertia = orl[7];
+  const double pyramid_rfac = (n_orl > 10 && orl[10] > 0) ? orl[10] : 2.0;       // model option (opt_real[10]): R of pyramid edges = this * mu_reg^2 * R[first]
   if (plane >= 0) {
     double R[9];
     quat2mat(geom_quat + 4 * plane, R);
@@ -263,7 +264,7 @@ static int build_device_model(nm_model* m) {
     G.mu = (float)mu;
     const double tran = body_invweight0[2 * geom_body[g]] + body_invweight0[2 * geom_body[p]];
     const double mureg = mu / std::sqrt(impratio > 1e-15 ? impratio : 1.0);
-    G.rfac = (float)(2.0 * mureg * mureg * (1.0 + mu * mu) * tran);
+    G.rfac = (float)(pyramid_rfac * mureg * mureg * (1.0 + mu * mu) * tran);
     double tc = solref[0], dr = solref[1], dmax = clampd(solimp[1]);
     if (tc > 0) {
       if (tc < 2 * opt_timestep) tc = 2 * opt_timestep;
@@ -348,7 +349,7 @@ static int build_device_model(nm_model* m) {
       G.cap_il2 = (float)(1.0 / std::fmax((tmax - tmin) * (tmax - tmin), 1e-12));
       G.cap_len = (float)((tmax - tmin) * 1.0001);
       const double mureg = G.mu / std::sqrt(impratio > 1e-15 ? impratio : 1.0);
-      G.rfac_self = (float)(2.0 * mureg * mureg * (1.0 + (double)G.mu * G.mu) * body_invweight0[2 * geom_body[g]]);
+      G.rfac_self = (float)(pyramid_rfac * mureg * mureg * (1.0 + (double)G.mu * G.mu) * body_invweight0[2 * geom_body[g]]);
     }
     long long n_or = 0;
     const double* orl2 = nullptr;
@@ -377,6 +378,10 @@ static int build_device_model(nm_model* m) {
   D.iterations = oi[3];
   D.noslip_iterations = oi[4];
   D.planemesh_maxcon = (n_oi > 7 && oi[7] >= 1 && oi[7] <= NM_MAXC) ? oi[7] : NM_MAXC;
+  D.planemesh_allverts = n_oi > 9 ? oi[9] != 0 : 0;
+  D.planemesh_sepvert = n_oi > 10 ? oi[10] != 0 : 0;
+  D.warm_after_noslip = n_oi > 11 ? oi[11] != 0 : 0;
+  D.planemesh_sep = (n_orl > 9 && orl[9] > 0) ? (float)orl[9] : 0.3f;
   D.integrator = integrator;
   D.imp_act = integrator == 3 ? 1.f : 0.f;
   D.imp_damp = (integrator == 3 || oi[5]) ? 1.f : 0.f;

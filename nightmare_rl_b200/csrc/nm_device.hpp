@@ -61,6 +61,11 @@ struct alignas(16) NmDevModel {
   int planemesh_maxcon;     // contacts per plane-mesh pair (opt_int[7] of the model file, 1..NM_MAXC)
   int pair_mask;            // bit idx(i,j), i<j lexicographic over the leg lanes: the hulls of legs i and j collide
   int mpr_iterations;       // opt.mpr_iterations (50)
+  // recalled-but-unverified MuJoCo details as model data (nightmare_rl_b200/mjcf.py lists them with their defaults):
+  int planemesh_allverts;   // opt_int[9]:  extra plane-mesh contacts from 0 = hull-graph neighbours of the support vertex, 1 = all hull vertices
+  int planemesh_sepvert;    // opt_int[10]: minimum separation measured between 0 = contact points, 1 = hull vertices
+  int warm_after_noslip;    // opt_int[11]: qacc_warmstart saved 0 = before noslip, 1 = after
+  float planemesh_sep;      // opt_real[9]:  separation as a fraction of rbound (0.3)
   float mpr_tolerance;      // opt.mpr_tolerance (1e-6)
   float imp_damp, imp_act;  // which velocity derivatives enter the implicit velocity update (implicitfast: both; Euler+eulerdamp: damping)
   float qpos0[32];

@@ -1046,27 +1046,33 @@ __global__ void __launch_bounds__(BLOCK, MINB) nm_step_kernel(const NmKernelArgs
       float dist = dot(pn, wv) - sm.plane_d;
       if (dist <= G.margin) {
         cdist[0] = dist; cvert[0] = best; cb.pos[0] = fma3(-0.5f * dist, pn, wv); nc = 1;
-        const float thr2 = (0.3f * G.rbound) * (0.3f * G.rbound);
+        const float thr2 = (sm.planemesh_sep * G.rbound) * (sm.planemesh_sep * G.rbound);
         const float dpl = dot(pn, pg) - sm.plane_d;       // cheap pre-test in the geom frame: dist(u) ~= dl.v_u + dpl
-        const int el = e0 + deg - 1;
         const int maxc = sm.planemesh_maxcon;              // model option, <= NM_MAXC (kept out of the loop bounds: they stay compile-time)
-        for (int e = e0; e <= el && nc < NM_MAXC; e += 4) {   // up to maxc - 1 more among the support vertex's neighbours
-          // four neighbours per trip (L1-resident after the walk); almost all fail the cheap depth pre-test
+        // candidates (model option): the support vertex's hull-graph neighbours from the edge table, or every hull vertex in
+        // index order from the vertex table (both tables hold float4 coordinates)
+        const bool allv = sm.planemesh_allverts != 0;
+        const float4* cand = allv ? hv : A.hull_edge;
+        const int ef = allv ? 0 : e0, el = allv ? G.hull_num - 1 : e0 + deg - 1;
+        const float hsep = sm.planemesh_sepvert ? 0.5f : 0.f;   // separation between contact points (0) or hull vertices (point + dist/2 n)
+        for (int e = ef; e <= el && nc < NM_MAXC; e += 4) {   // up to maxc - 1 more
+          // four candidates per trip (L1-resident after the walk); almost all fail the cheap depth pre-test
           float4 ww[4];
 #pragma unroll
-          for (int k = 0; k < 4; k++) ww[k] = __ldg(A.hull_edge + min(e + k, el));
+          for (int k = 0; k < 4; k++) ww[k] = __ldg(cand + min(e + k, el));
 #pragma unroll
           for (int k = 0; k < 4; k++) {
             const float4 w4 = ww[k];
-            if (e + k > el || nc >= NM_MAXC || fmaf(dl.x, w4.x, fmaf(dl.y, w4.y, dl.z * w4.z)) + dpl > G.margin + 1e-4f) continue;
+            const int vid = allv ? e + k : __float_as_int(w4.w);
+            if (e + k > el || nc >= NM_MAXC || (allv && vid == best) || fmaf(dl.x, w4.x, fmaf(dl.y, w4.y, dl.z * w4.z)) + dpl > G.margin + 1e-4f) continue;
             V3 wu = pg + mul(Xg, mk(w4.x, w4.y, w4.z));
             float du = dot(pn, wu) - sm.plane_d;
             if (du > G.margin) continue;
             V3 cp = fma3(-0.5f * du, pn, wu);
             bool close = false;
-            for (int q = 0; q < nc; q++) { V3 d3 = cb.pos[q] - cp; close |= dot(d3, d3) < thr2; }
+            for (int q = 0; q < nc; q++) { V3 d3 = fma3(hsep * (cdist[q] - du), pn, cb.pos[q] - cp); close |= dot(d3, d3) < thr2; }
             if (close || nc >= maxc) continue;
-            cdist[nc] = du; cvert[nc] = __float_as_int(w4.w); cb.pos[nc] = cp; nc++;
+            cdist[nc] = du; cvert[nc] = vid; cb.pos[nc] = cp; nc++;
           }
         }
       }
@@ -1463,6 +1469,11 @@ __global__ void __launch_bounds__(BLOCK, MINB) nm_step_kernel(const NmKernelArgs
           for (int i = 0; i < 6; i++) xb[i] = 0.f;
 #pragma unroll
           for (int i = 0; i < 3; i++) xk[i] = 0.f;
+        } else if (sm.warm_after_noslip && sm.noslip_iterations > 0) {     // model option: the warm start is the acceleration AFTER noslip
+#pragma unroll
+          for (int i = 0; i < 6; i++) wsb[i] = xsb[i] + xb[i];
+#pragma unroll
+          for (int i = 0; i < 3; i++) wsk[i] = xsk[i] + xk[i];
         }
       }
       // ============================================================== P10 touch sensors (sum of pyramid-edge forces)

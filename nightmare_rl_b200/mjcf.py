@@ -766,8 +766,9 @@ def compile_mjcf(path: str) -> CompiledModel:
         # Appendix A.2 as recalled ("up to 3 more"); the entry exists so that a MuJoCo cross-check can correct it to whatever
         # mjc_PlaneConvex really does by re-saving the model, without touching oracle or kernel code
         "opt_int": i32([integrator, solver, cone, o["iterations"], o["noslip_iterations"], int(o["eulerdamp"]), o["ls_iterations"],
-                        PLANEMESH_MAXCON]),
-        "opt_real": f64([o["timestep"], *o["gravity"], o["tolerance"], o["noslip_tolerance"], o["impratio"], meaninertia], -1),
+                        PLANEMESH_MAXCON, MPR_ITERATIONS, PLANEMESH_ALLVERTS, PLANEMESH_SEPVERT, WARM_AFTER_NOSLIP]),
+        "opt_real": f64([o["timestep"], *o["gravity"], o["tolerance"], o["noslip_tolerance"], o["impratio"], meaninertia,
+                         MPR_TOLERANCE, PLANEMESH_SEP, PYRAMID_RFAC], -1),
         "qpos0": qpos0,
         "body_parent": i32([b.parent for b in p.bodies]),
         "body_rootid": i32(body_rootid),
@@ -805,6 +806,16 @@ def compile_mjcf(path: str) -> CompiledModel:
 
 
 PLANEMESH_MAXCON = 4
+# Further details of MuJoCo's engine that SURVEY.md Appendix A marks as recalled, not verified -- stored in the model file so that
+# a cross-check against MuJoCo (tools/mujoco_crosscheck.py) corrects a wrong guess by re-saving the model, not by editing code.
+# Oracle and CUDA kernel honour every one of them (tests/test_oracle_physics.py, tests/test_gpu_physics.py at both values).
+MPR_ITERATIONS = 50        # opt_int[8]   opt.mpr_iterations
+PLANEMESH_ALLVERTS = 0     # opt_int[9]   extra plane-mesh contacts from 0 = hull-graph neighbours of the support vertex, 1 = all hull vertices
+PLANEMESH_SEPVERT = 0      # opt_int[10]  their minimum separation measured between 0 = contact points, 1 = hull vertices
+WARM_AFTER_NOSLIP = 0      # opt_int[11]  qacc_warmstart saved 0 = before the noslip pass, 1 = after
+MPR_TOLERANCE = 1e-6       # opt_real[8]  opt.mpr_tolerance
+PLANEMESH_SEP = 0.3        # opt_real[9]  that separation as a fraction of the geom's rbound
+PYRAMID_RFAC = 2.0         # opt_real[10] R of a pyramidal contact's four edges = this * mu_reg^2 * R[first]
 
 
 def load_model(path: str) -> CompiledModel:

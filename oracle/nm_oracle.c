@@ -73,6 +73,13 @@ struct nmo_model {
   int integrator, solver, cone, iterations, noslip_iterations, eulerdamp;
   int planemesh_maxcon; /* contacts per plane-mesh pair (opt_int[7]; 4 when the model file predates the entry) */
   int mpr_iterations;   /* opt_int[8], MuJoCo default 50 */
+  /* Details of MuJoCo recalled but not verifiable here, kept as MODEL DATA so that a cross-check against
+   * MuJoCo corrects them by re-saving the model file (tools/mujoco_crosscheck.py names the option for each mismatch): */
+  int planemesh_allverts;   /* opt_int[9]:  extra plane-mesh contacts drawn from 0 = the support vertex's hull-graph neighbours, 1 = all hull vertices */
+  int planemesh_sepvert;    /* opt_int[10]: their minimum separation measured between 0 = contact points, 1 = hull vertices */
+  int warm_after_noslip;    /* opt_int[11]: qacc_warmstart saved 0 = before the noslip pass, 1 = after it */
+  real planemesh_sep;       /* opt_real[9]:  that separation as a fraction of rbound (0.3) */
+  real pyramid_rfac;        /* opt_real[10]: R of a pyramidal contact's edges = this * mu_reg^2 * R[first] (2) */
   real mpr_tolerance;   /* opt_real[8], MuJoCo default 1e-6 */
   real timestep, gravity[3], tolerance, noslip_tolerance, impratio, meaninertia;
   const real *qpos0, *body_pos, *body_quat, *body_ipos, *body_iquat, *body_mass, *body_inertia, *body_invweight0;
@@ -171,9 +178,14 @@ nmo_model* nmo_model_load(const char* path, char* err, int errlen) {
   m->noslip_iterations = oi[4]; m->eulerdamp = oi[5];
   m->planemesh_maxcon = (noi > 7 && oi[7] >= 1 && oi[7] <= 4) ? oi[7] : 4;
   m->mpr_iterations = (noi > 8 && oi[8] > 0) ? oi[8] : 50;
+  m->planemesh_allverts = noi > 9 ? oi[9] != 0 : 0;
+  m->planemesh_sepvert = noi > 10 ? oi[10] != 0 : 0;
+  m->warm_after_noslip = noi > 11 ? oi[11] != 0 : 0;
   m->timestep = orl[0]; m->gravity[0] = orl[1]; m->gravity[1] = orl[2]; m->gravity[2] = orl[3];
   m->tolerance = orl[4]; m->noslip_tolerance = orl[5]; m->impratio = orl[6]; m->meaninertia = orl[7];
   m->mpr_tolerance = (norl > 8 && orl[8] > 0) ? (real)orl[8] : (real)1e-6;
+  m->planemesh_sep = (norl > 9 && orl[9] > 0) ? (real)orl[9] : (real)TOLPLANEMESH;
+  m->pyramid_rfac = (norl > 10 && orl[10] > 0) ? (real)orl[10] : (real)2;
   GETR(qpos0); GETR(body_pos); GETR(body_quat); GETR(body_ipos);
   GETR(body_iquat); GETR(body_mass); GETR(body_inertia); GETR(body_invweight0);
   GETP(body_parent, int); GETP(body_rootid, int); GETP(body_jntadr, int); GETP(body_jntnum, int);
@@ -937,11 +949,13 @@ static void collision(const nmo_model* m, data_t* d) {
       if (best < 0 || bestd > margin) continue;
       int first = d->ncon, cnt = 0;
       for (int pass = 0; pass < 2; pass++) {
-        /* pass 0: the support vertex.  pass 1: its hull-graph neighbours (up to 3 more contacts) */
-        int lo = pass == 0 ? 0 : m->hull_nbr_adr[adr + best];
-        int hi = pass == 0 ? 1 : m->hull_nbr_adr[adr + best + 1];
+        /* pass 0: the support vertex.  pass 1: its hull-graph neighbours, or every other hull vertex in index order (model option) */
+        const int allv = pass == 1 && m->planemesh_allverts;
+        int lo = pass == 0 || allv ? 0 : m->hull_nbr_adr[adr + best];
+        int hi = pass == 0 ? 1 : allv ? num : m->hull_nbr_adr[adr + best + 1];
         for (int e = lo; e < hi && cnt < m->planemesh_maxcon && d->ncon < NMO_MAXCON; e++) {
-          int v = pass == 0 ? best : m->hull_nbr[e];
+          int v = pass == 0 ? best : allv ? e : m->hull_nbr[e];
+          if (allv && v == best) continue;
           real w[3], dist;
           if (pass == 0) { memcpy(w, bestw, sizeof(w)); dist = bestd; }
           else {
@@ -957,8 +971,12 @@ static void collision(const nmo_model* m, data_t* d) {
           FLOP(7 + 9 * cnt);
           int tooclose = 0;
           for (int c = first; c < first + cnt; c++) {
-            real dx = d->con[c].pos[0] - cp[0], dy = d->con[c].pos[1] - cp[1], dz = d->con[c].pos[2] - cp[2];
-            if (sqrt(dx * dx + dy * dy + dz * dz) < TOLPLANEMESH * m->geom_rbound[g]) tooclose = 1;
+            /* separation between the contact points, or between the hull vertices they came from (vertex = point + dist/2 n) */
+            const real hv = m->planemesh_sepvert ? (real)0.5 : 0;
+            real dx = (d->con[c].pos[0] + hv * d->con[c].dist * n[0]) - (cp[0] + hv * dist * n[0]);
+            real dy = (d->con[c].pos[1] + hv * d->con[c].dist * n[1]) - (cp[1] + hv * dist * n[1]);
+            real dz = (d->con[c].pos[2] + hv * d->con[c].dist * n[2]) - (cp[2] + hv * dist * n[2]);
+            if (sqrt(dx * dx + dy * dy + dz * dz) < m->planemesh_sep * m->geom_rbound[g]) tooclose = 1;
           }
           if (tooclose) continue;
           contact_t* c = d->con + d->ncon++;
@@ -1316,7 +1334,7 @@ static void make_constraint(const nmo_model* m, data_t* d) {
     }
     /* pyramidal cone: all edges share R = 2 mu^2 R[first]  (mu regularised by impratio) */
     real mureg = c->mu / sqrt(m->impratio > MINVAL ? m->impratio : 1.0);
-    real Rpy = 2 * mureg * mureg * d->efc_R[e0];
+    real Rpy = m->pyramid_rfac * mureg * mureg * d->efc_R[e0];
     if (Rpy < MINVAL) Rpy = MINVAL;
     for (int r = 0; r < 4; r++) { d->efc_R[e0 + r] = Rpy; d->efc_D[e0 + r] = 1.0 / Rpy; }
   }
@@ -1759,6 +1777,7 @@ static void fwd_constraint(const nmo_model* m, data_t* d) {
       if (improvement * scale < m->noslip_tolerance) break;
     }
     dual_finish(m, d);
+    if (m->warm_after_noslip) memcpy(d->qacc_warmstart, d->qacc, sizeof(real) * nv);   /* model option: saved AFTER noslip */
   }
 }
 

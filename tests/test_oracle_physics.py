@@ -326,6 +326,59 @@ def test_plane_mesh_contact_cap_is_a_model_option(compiled_model, tmp_path):
     assert most == {4: 4, 3: 3, 1: 1}, most
 
 
+def test_recalled_details_are_model_options(compiled_model, tmp_path):
+    """The other engine details SURVEY.md Appendix A could only recall -- candidate set of the extra plane-mesh contacts, how
+    their separation is measured and how large it must be, the R factor of pyramidal rows, where qacc_warmstart is saved --
+    are model data too (opt_int[9..11], opt_real[9..10]; nightmare_rl_b200/mjcf.py).  Each default is the recalled value, each
+    alternative changes the simulation in the way its meaning says, and none needs a code change."""
+    oi, orl = compiled_model.arrays["opt_int"], compiled_model.arrays["opt_real"]
+    assert list(oi[8:12]) == [50, 0, 0, 0] and list(orl[8:11]) == [1e-6, 0.3, 2.0]
+    rng = np.random.default_rng(1)
+    n = 96
+    qpos = np.tile(compiled_model.qpos0, (n, 1))
+    qpos[:, 7:] += rng.uniform(-0.6, 0.6, (n, 18))
+    qpos[:, 2] = rng.uniform(0.03, 0.22, n)
+    qpos[:, 3:7] = rng.normal(size=(n, 4))
+    qpos[:, 3:7] /= np.linalg.norm(qpos[:, 3:7], axis=1, keepdims=True)
+
+    def run(name, key=None, idx=None, val=None, steps=30):
+        cm = mjcf.CompiledModel(dict((k, v.copy()) for k, v in compiled_model.arrays.items()), compiled_model.names)
+        if key is not None:
+            cm.arrays[key][idx] = val
+        p = str(tmp_path / f"{name}.nmb")
+        cm.save(p)
+        b = O.OracleBatch(O.OracleModel(p), n)
+        b.set_state(qpos, np.zeros((n, 24)), np.zeros((n, 24)))
+        ncon, first = 0, None
+        for s in range(steps):
+            b.physics_step(np.zeros((n, 18)), 1, 8)
+            cnt = np.array([b.get(i, "ncon")[0] for i in range(n)])
+            ncon += int(cnt.sum())
+            if s == 0:
+                first = dict(ncon=cnt, R=[b.get(i, "efc_R") for i in range(n)], qacc=[b.get(i, "qacc") for i in range(n)], warm=b.get_state()[2].copy())
+        q, v, w = b.get_state()
+        assert np.isfinite(q).all() and np.isfinite(v).all()
+        return dict(q=q, ncon=ncon, first=first)
+
+    base = run("default")
+    allv = run("allverts", "opt_int", 9, 1)
+    # more candidates can only add contacts on the first substep (same state, same support vertices)
+    assert (allv["first"]["ncon"] >= base["first"]["ncon"]).all() and (allv["first"]["ncon"] > base["first"]["ncon"]).any()
+    sepv = run("sepvert", "opt_int", 10, 1)
+    sep = run("sep015", "opt_real", 9, 0.15)
+    assert (sep["first"]["ncon"] >= base["first"]["ncon"]).all() and (sep["first"]["ncon"] > base["first"]["ncon"]).any()   # closer contacts allowed
+    assert np.isfinite(sepv["q"]).all()                                                            # (may coincide with the default on a sample: vertex and point are dist/2 apart)
+    rf = run("rfac1", "opt_real", 10, 1.0)
+    ratios = np.concatenate([a / b for a, b in zip(rf["first"]["R"], base["first"]["R"]) if len(a) and len(a) == len(b)])
+    assert len(ratios) > 100 and np.allclose(ratios, 0.5, rtol=1e-12)                              # R of every pyramid edge halves
+    wa = run("warmafter", "opt_int", 11, 1)
+    inc = [i for i in range(n) if base["first"]["ncon"][i] > 0]
+    # first substep: identical solve, different save point -- after noslip the warm start IS that substep's qacc, before it is not
+    assert all(np.array_equal(wa["first"]["qacc"][i], base["first"]["qacc"][i]) for i in inc)
+    assert all(np.array_equal(wa["first"]["warm"][i], wa["first"]["qacc"][i]) for i in inc)
+    assert any(not np.array_equal(base["first"]["warm"][i], base["first"]["qacc"][i]) for i in inc)
+
+
 def test_passive_contact_never_gains_energy(compiled_model, oracle_model):
     """Zero controls: the velocity servos act as dampers and the soft contacts follow a critically damped reference
     (solref 0.02 / 1), so a robot dropped in any pose must never have more mechanical energy than it started with, and must end
