@@ -14,6 +14,18 @@ sequence (U(-1,1) joint targets from torch seed 0 through the env's PD law) in b
 a time with the oracle re-synchronised to MuJoCo's state before every substep, and reports per-stage maximum deviations
 (xpos, cinert, M, qfrc_bias, qacc_smooth, contact count / geoms / dist, efc_force, sensordata, qpos/qvel after the step).
 Each item marked "❓ recalled" in SURVEY.md Appendix A shows up here as a stage whose deviation is not ~1e-12.
+
+Which MODEL OPTION repairs which mismatch (all are slots of the .nmb file, written by nightmare_rl_b200/mjcf.py and honoured
+by oracle and kernel -- change the constant there or the array in the file, re-save, re-run; no engine code changes):
+
+    stage that deviates                         option to try                                        slot
+    ------------------------------------------  ---------------------------------------------------  ------------
+    ncon: more / fewer contacts on a flat hull  PLANEMESH_MAXCON (contacts per plane-mesh pair)       opt_int[7]
+    ncon / contact vertices: other vertices     PLANEMESH_ALLVERTS (neighbours vs all hull vertices)  opt_int[9]
+    ncon: a close second contact kept/dropped   PLANEMESH_SEP (fraction of rbound), PLANEMESH_SEPVERT opt_real[9], opt_int[10]
+    efc_R / efc_D of contact rows off by const  PYRAMID_RFAC (R = fac * mu_reg^2 * R[first])          opt_real[10]
+    qacc_warmstart after the step               WARM_AFTER_NOSLIP (save point relative to noslip)     opt_int[11]
+    tibia-tibia penetration depth / iterations  MPR_ITERATIONS, MPR_TOLERANCE                         opt_int[8], opt_real[8]
 """
 import argparse
 import os
@@ -139,6 +151,7 @@ def main():
         print(f"per-stage worst deviation over {a.steps} env steps (oracle re-synchronised to MuJoCo before every substep):")
         for k, v in worst.items():
             print(f"  {k:28s} {v:.3e}" if isinstance(v, float) else f"  {k:28s} {v}")
+        print("a stage that is not ~1e-12: see the option table in this file's docstring (model data, not code)")
     return 0
 
 
