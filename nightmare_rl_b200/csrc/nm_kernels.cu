@@ -44,6 +44,24 @@ __device__ long long* nm_timing_buf = nullptr;
 #define TSTAMP(k)
 #endif
 #define NM_MINVAL 1e-15f
+// Loads of the hull tables (read-only, shared by all environments, a few KB of them hot): ask L1 to keep their lines
+// over the streaming local-memory traffic of the contact blocks.
+#ifdef NM_HULL_EVICT_LAST
+__device__ __forceinline__ float4 ld_hull4(const float4* p) {
+  float4 v;
+  asm volatile("ld.global.nc.L1::evict_last.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ int ld_hulli(const int* p) {
+  int v;
+  asm volatile("ld.global.nc.L1::evict_last.s32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+#else
+__device__ __forceinline__ float4 ld_hull4(const float4* p) { return __ldg(p); }
+__device__ __forceinline__ int ld_hulli(const int* p) { return __ldg(p); }
+#endif
+
 #define NM_TINY 1e-30f
 
 // ---------------------------------------------------------------------------------------------- small algebra
@@ -1022,15 +1040,15 @@ __global__ void __launch_bounds__(BLOCK, MINB) nm_step_kernel(const NmKernelArgs
       const float4* hv = A.hull_vert + G.hull_adr;
       const int* nadr = A.hull_nbr_adr + G.hull_adr;
       int best = hint & 0x1ff, deg = (hint >> 9) & 0x3f, e0 = hint >> 15;
-      float4 vb = __ldg(hv + best);
+      float4 vb = ld_hull4(hv + best);
       float bval = fmaf(dl.x, vb.x, fmaf(dl.y, vb.y, dl.z * vb.z));
       for (;;) {
-        if (deg == 0) { e0 = __ldg(nadr + best); deg = __ldg(nadr + best + 1) - e0; }
+        if (deg == 0) { e0 = ld_hulli(nadr + best); deg = ld_hulli(nadr + best + 1) - e0; }
         int nb = best;
         const int el = e0 + deg - 1;
         for (int e = e0; e <= el; e += 4) {              // 4 neighbours per trip: loads issued together, compared in list order
-          const float4 w0 = __ldg(A.hull_edge + e), w1 = __ldg(A.hull_edge + min(e + 1, el)), w2 = __ldg(A.hull_edge + min(e + 2, el)),
-                       w3 = __ldg(A.hull_edge + min(e + 3, el));
+          const float4 w0 = ld_hull4(A.hull_edge + e), w1 = ld_hull4(A.hull_edge + min(e + 1, el)), w2 = ld_hull4(A.hull_edge + min(e + 2, el)),
+                       w3 = ld_hull4(A.hull_edge + min(e + 3, el));
           const float a0 = fmaf(dl.x, w0.x, fmaf(dl.y, w0.y, dl.z * w0.z)), a1 = fmaf(dl.x, w1.x, fmaf(dl.y, w1.y, dl.z * w1.z));
           const float a2 = fmaf(dl.x, w2.x, fmaf(dl.y, w2.y, dl.z * w2.z)), a3 = fmaf(dl.x, w3.x, fmaf(dl.y, w3.y, dl.z * w3.z));
           if (a0 < bval) { bval = a0; nb = __float_as_int(w0.w); vb = w0; }
@@ -1059,7 +1077,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) nm_step_kernel(const NmKernelArgs
           // four candidates per trip (L1-resident after the walk); almost all fail the cheap depth pre-test
           float4 ww[4];
 #pragma unroll
-          for (int k = 0; k < 4; k++) ww[k] = __ldg(cand + min(e + k, el));
+          for (int k = 0; k < 4; k++) ww[k] = ld_hull4(cand + min(e + k, el));
 #pragma unroll
           for (int k = 0; k < 4; k++) {
             const float4 w4 = ww[k];
