@@ -33,7 +33,7 @@ int nm_fail(int code, const std::string& msg);   // nm_abi.cu
 #define GM_MAXCON 16   // first tier: contacts / constraint rows per environment held in shared memory
 #define GM_MAXROW 72
 #ifndef GM_WARPS
-#define GM_WARPS 8     // environments (warps) per CTA: one CTA per SM, its warps in lockstep (measured 12.4 ms unsynchronised, 9.6 / 6.9 / 5.9 ms with 2 / 4 / 8 warps in lockstep)
+#define GM_WARPS 4     // environments (warps) per CTA, in lockstep.  Measured per 4096-env x 4-substep launch: unsynchronised 12.4 ms; in lockstep with the first code 9.6 / 6.9 / 5.9 ms for 2 / 4 / 8 warps; with the final (4x smaller) code 3.53 ms for 2 CTAs x 4 warps, 3.80 for 1 x 8, 4.35 for 1 x 6
 #endif
 #define GM_MAXCHAIN 16  // dofs on the chain from the world to any body
 #define GM_BIGCON 64   // second tier (same cap as the oracle's NMO_MAXCON); beyond it info[3] = 1 and the step is truncated
