@@ -150,23 +150,29 @@ struct EnvMemT {
   // orders of magnitude (measured: fp32 floor 1e-3 relative in qvel, with these two arrays in fp64 2.6e-6).
   double xd[GM_MAXV], jar[MR];
   float qpos[GM_MAXQ + 3], qvel[GM_MAXV], warm[GM_MAXV], ctrl[GM_MAXU + 2];
-  float xpos[GM_MAXB][3], xquat[GM_MAXB][4], xmat[GM_MAXB][9], xipos[GM_MAXB][3], ximat[GM_MAXB][9];
+  float xpos[GM_MAXB][3], xmat[GM_MAXB][9];
   float com[4];
-  float cinert[GM_MAXB][10], crb[GM_MAXB][10], cdof[GM_MAXV][6], cdofdot[GM_MAXV][6];
-  float cvel[GM_MAXB][6], cacc[GM_MAXB][6], cfrc[GM_MAXB][6];
-  float M[GM_MAXV][GM_MAXV], H[GM_MAXV][GM_MAXV];
-  float bias[GM_MAXV], smooth[GM_MAXV], qaccs[GM_MAXV], qacc[GM_MAXV], grad[GM_MAXV], dir[GM_MAXV], Ma[GM_MAXV], vec[GM_MAXV], fcon[GM_MAXV];
+  float cdof[GM_MAXV][6];
+  // Two phases share one block of memory (shared memory per environment decides how many warps an SM holds: 24.1 KB -> 19.1 KB
+  // = 8 -> 12 warps): `k` is dead once the smooth dynamics are done (before collision), `s` is written from the constraint rows on
+  union {
+    struct { float xquat[GM_MAXB][4], xipos[GM_MAXB][3], ximat[GM_MAXB][9], cinert[GM_MAXB][10], crb[GM_MAXB][10], cdofdot[GM_MAXV][6],
+                   cvel[GM_MAXB][6], cacc[GM_MAXB][6], cfrc[GM_MAXB][6]; } k;
+    struct { float H[GM_MAXV][GM_MAXV], aref[MR], D[MR], R[MR], jv[MR], force[MR], Hd[MR], floss[MR]; } s;
+  };
+  float M[GM_MAXV][GM_MAXV];
+  float smooth[GM_MAXV], qaccs[GM_MAXV], qacc[GM_MAXV], grad[GM_MAXV], dir[GM_MAXV], Ma[GM_MAXV], vec[GM_MAXV];
   // contacts
   int ncon, nefc, nlim, overflow;
   float cpos[MC][3], cdist[MC], cmu[MC];
-  int cgeom[MC], cadr[MC], cdim[MC], czone[MC], crow[MR];   // crow: contact that owns a row
+  unsigned char cgeom[MC], cadr[MC], cdim[MC], czone[MC], crow[MR];   // crow: contact that owns a row (row addresses < 256 in both tiers)
   float cDm[MC], ccoef[MC], cb[MC][GM_MAXV];          // elliptic-cone curvature data (g_cone)
   // rows
   float J[MR][GM_MAXV];
-  float aref[MR], D[MR], R[MR], jv[MR], force[MR], Hd[MR], floss[MR];
-  int rtype[2 * GM_MAXV], rdof[2 * GM_MAXV];           // simple rows (friction loss, limits): one dof each, J = rsgn * e_dof
+  unsigned char rtype[2 * GM_MAXV], rdof[2 * GM_MAXV];  // simple rows (friction loss, limits): one dof each, J = rsgn * e_dof
   float rsgn[2 * GM_MAXV];
 };
+
 
 // x <- A^-1 x for the symmetric positive definite n x n matrix A (lower triangle read) by the whole warp, entirely in
 // registers: lane i holds row i and its right-hand side, elimination of column j broadcasts pivot row j by shuffles and
@@ -273,19 +279,19 @@ __device__ __forceinline__ float g_simple(int type, float D, float R, float fl, 
   return -D * j;
 }
 
-// Row evaluation at the residual e.jar + alpha * e.jv, one copy of the code for its three uses (the kernel is bound by
-// instruction fetch):  mode 0 = line search: returns sum_r force_r jv_r, stores nothing;  mode 1 = forces into e.force, returns
-// the cost;  mode 2 = mode 1 plus the curvature data (e.Hd / e.czone / e.ccoef / e.cb).  alpha is ignored unless mode == 0.
+// Row evaluation at the residual e.jar + alpha * e.s.jv, one copy of the code for its three uses (the kernel is bound by
+// instruction fetch):  mode 0 = line search: returns sum_r force_r jv_r, stores nothing;  mode 1 = forces into e.s.force, returns
+// the cost;  mode 2 = mode 1 plus the curvature data (e.s.Hd / e.czone / e.ccoef / e.cb).  alpha is ignored unless mode == 0.
 template <class EnvMem>
 __device__ __noinline__ float g_rows(const GenModel& m, EnvMem& e, int mode, float alpha, int lane) {
   float acc = 0.f;
   const int nsimple = m.nfloss + e.nlim;
   for (int r = lane; r < nsimple; r += 32) {
     float cs, hd;
-    const float jv = mode == 0 ? e.jv[r] : 0.f;
-    const float f = g_simple(e.rtype[r], e.D[r], e.R[r], e.floss[r], (float)(mode == 0 ? e.jar[r] + (double)alpha * (double)jv : e.jar[r]), &cs, &hd);
+    const float jv = mode == 0 ? e.s.jv[r] : 0.f;
+    const float f = g_simple(e.rtype[r], e.s.D[r], e.s.R[r], e.s.floss[r], (float)(mode == 0 ? e.jar[r] + (double)alpha * (double)jv : e.jar[r]), &cs, &hd);
     if (mode == 0) acc += f * jv;
-    else { e.force[r] = f; acc += cs; if (mode == 2) e.Hd[r] = hd; }
+    else { e.s.force[r] = f; acc += cs; if (mode == 2) e.s.Hd[r] = hd; }
   }
   for (int c = lane; c < e.ncon; c += 32) {
     const int a = e.cadr[c], dim = e.cdim[c];
@@ -293,16 +299,16 @@ __device__ __noinline__ float g_rows(const GenModel& m, EnvMem& e, int mode, flo
     double j[6];
     float jv[6];
 #pragma unroll
-    for (int k = 0; k < 6; k++) if (k < dim) { j[k] = e.jar[a + k]; if (mode == 0) { jv[k] = e.jv[a + k]; j[k] += (double)alpha * (double)jv[k]; } }
+    for (int k = 0; k < 6; k++) if (k < dim) { j[k] = e.jar[a + k]; if (mode == 0) { jv[k] = e.s.jv[a + k]; j[k] += (double)alpha * (double)jv[k]; } }
     float f[6], uh[6], cs, cc = 0.f;
-    const int zone = g_cone(dim, j, fri, e.cmu[c], e.D + a, e.cDm[c], f, &cs, uh, &cc);
+    const int zone = g_cone(dim, j, fri, e.cmu[c], e.s.D + a, e.cDm[c], f, &cs, uh, &cc);
     if (mode == 0) {
 #pragma unroll
       for (int k = 0; k < 6; k++) if (k < dim) acc += f[k] * jv[k];
       continue;
     }
 #pragma unroll
-    for (int k = 0; k < 6; k++) if (k < dim) e.force[a + k] = f[k];
+    for (int k = 0; k < 6; k++) if (k < dim) e.s.force[a + k] = f[k];
     acc += cs;
     if (mode == 2) {
       e.czone[c] = zone;
@@ -372,8 +378,8 @@ __global__ void __launch_bounds__(WARPS * 32) nm_generic_step_kernel(const GenAr
     // ------------------------------------------------------------------ P1 kinematics, level by level
     if (lane == 0) {
       e.xpos[0][0] = e.xpos[0][1] = e.xpos[0][2] = 0.f;
-      e.xquat[0][0] = 1.f; e.xquat[0][1] = e.xquat[0][2] = e.xquat[0][3] = 0.f;
-      g_quat2mat(e.xquat[0], e.xmat[0]);
+      e.k.xquat[0][0] = 1.f; e.k.xquat[0][1] = e.k.xquat[0][2] = e.k.xquat[0][3] = 0.f;
+      g_quat2mat(e.k.xquat[0], e.xmat[0]);
     }
     __syncwarp();
     for (int lev = 1; lev <= m.maxdepth; lev++) {
@@ -389,7 +395,7 @@ __global__ void __launch_bounds__(WARPS * 32) nm_generic_step_kernel(const GenAr
           float t[3];
           g_matvec(t, e.xmat[p], m.body_pos[b]);
           pos[0] = e.xpos[p][0] + t[0]; pos[1] = e.xpos[p][1] + t[1]; pos[2] = e.xpos[p][2] + t[2];
-          g_mulquat(quat, e.xquat[p], m.body_quat[b]);
+          g_mulquat(quat, e.k.xquat[p], m.body_quat[b]);
           const float ang = e.qpos[m.body_qadr[b]] - m.qpos0[m.body_qadr[b]];
           float s, c;
           sincosf(0.5f * ang, &s, &c);
@@ -400,31 +406,31 @@ __global__ void __launch_bounds__(WARPS * 32) nm_generic_step_kernel(const GenAr
         }
         g_normquat(quat);
         for (int k = 0; k < 3; k++) e.xpos[b][k] = pos[k];
-        for (int k = 0; k < 4; k++) e.xquat[b][k] = quat[k];
+        for (int k = 0; k < 4; k++) e.k.xquat[b][k] = quat[k];
         g_quat2mat(quat, e.xmat[b]);
         float t[3], qi[4];
         g_matvec(t, e.xmat[b], m.body_ipos[b]);
-        for (int k = 0; k < 3; k++) e.xipos[b][k] = pos[k] + t[k];
+        for (int k = 0; k < 3; k++) e.k.xipos[b][k] = pos[k] + t[k];
         g_mulquat(qi, quat, m.body_iquat[b]);
-        g_quat2mat(qi, e.ximat[b]);
+        g_quat2mat(qi, e.k.ximat[b]);
       }
       __syncwarp();
     }
     // ------------------------------------------------------------------ P2 comPos: subtree COM of the root, cinert, cdof
     {
       float mx = 0.f, my = 0.f, mz = 0.f, mm = 0.f;
-      for (int b = 1 + lane; b < nb; b += 32) { const float ms = m.body_mass[b]; mx += ms * e.xipos[b][0]; my += ms * e.xipos[b][1]; mz += ms * e.xipos[b][2]; mm += ms; }
+      for (int b = 1 + lane; b < nb; b += 32) { const float ms = m.body_mass[b]; mx += ms * e.k.xipos[b][0]; my += ms * e.k.xipos[b][1]; mz += ms * e.k.xipos[b][2]; mm += ms; }
       mx = g_warpsum(mx); my = g_warpsum(my); mz = g_warpsum(mz); mm = g_warpsum(mm);
       if (lane == 0) { e.com[0] = mx / mm; e.com[1] = my / mm; e.com[2] = mz / mm; }
       __syncwarp();
     }
     for (int b = lane; b < nb; b += 32) {
-      float* ci = e.cinert[b];
+      float* ci = e.k.cinert[b];
       if (b == 0) { for (int k = 0; k < 10; k++) ci[k] = 0.f; continue; }
-      const float* Rm = e.ximat[b];
+      const float* Rm = e.k.ximat[b];
       const float* I = m.body_inertia[b];
       const float mass = m.body_mass[b];
-      const float r[3] = {e.xipos[b][0] - e.com[0], e.xipos[b][1] - e.com[1], e.xipos[b][2] - e.com[2]};
+      const float r[3] = {e.k.xipos[b][0] - e.com[0], e.k.xipos[b][1] - e.com[1], e.k.xipos[b][2] - e.com[2]};
       ci[0] = Rm[0] * Rm[0] * I[0] + Rm[1] * Rm[1] * I[1] + Rm[2] * Rm[2] * I[2];
       ci[1] = Rm[3] * Rm[3] * I[0] + Rm[4] * Rm[4] * I[1] + Rm[5] * Rm[5] * I[2];
       ci[2] = Rm[6] * Rm[6] * I[0] + Rm[7] * Rm[7] * I[1] + Rm[8] * Rm[8] * I[2];
@@ -462,13 +468,13 @@ __global__ void __launch_bounds__(WARPS * 32) nm_generic_step_kernel(const GenAr
     }
     __syncwarp();
     // ------------------------------------------------------------------ P3 composite inertias (bottom-up), mass matrix, Cholesky
-    for (int b = lane; b < nb; b += 32) for (int k = 0; k < 10; k++) e.crb[b][k] = e.cinert[b][k];
+    for (int b = lane; b < nb; b += 32) for (int k = 0; k < 10; k++) e.k.crb[b][k] = e.k.cinert[b][k];
     __syncwarp();
     for (int lev = m.maxdepth - 1; lev >= 1; lev--) {
       for (int b = 1 + lane; b < nb; b += 32) {
         if (m.body_depth[b] != lev) continue;
         for (int c = b + 1; c < nb; c++)
-          if (m.body_parent[c] == b) for (int k = 0; k < 10; k++) e.crb[b][k] += e.crb[c][k];
+          if (m.body_parent[c] == b) for (int k = 0; k < 10; k++) e.k.crb[b][k] += e.k.crb[c][k];
       }
       __syncwarp();
     }
@@ -476,7 +482,7 @@ __global__ void __launch_bounds__(WARPS * 32) nm_generic_step_kernel(const GenAr
     __syncwarp();
     for (int i = lane; i < nv; i += 32) {
       float buf[6];
-      g_inertvec(buf, e.crb[m.dof_body[i]], e.cdof[i]);
+      g_inertvec(buf, e.k.crb[m.dof_body[i]], e.cdof[i]);
       for (int j = i; j >= 0; j = m.dof_parent[j]) {
         float s = 0.f;
         for (int k = 0; k < 6; k++) s += e.cdof[j][k] * buf[k];
@@ -486,28 +492,28 @@ __global__ void __launch_bounds__(WARPS * 32) nm_generic_step_kernel(const GenAr
     }
     __syncwarp();
     // ------------------------------------------------------------------ P7 comVel + RNE
-    if (lane == 0) for (int k = 0; k < 6; k++) { e.cvel[0][k] = 0.f; e.cacc[0][k] = k >= 3 ? -m.gravity[k - 3] : 0.f; }
+    if (lane == 0) for (int k = 0; k < 6; k++) { e.k.cvel[0][k] = 0.f; e.k.cacc[0][k] = k >= 3 ? -m.gravity[k - 3] : 0.f; }
     __syncwarp();
     for (int lev = 1; lev <= m.maxdepth; lev++) {
       for (int b = 1 + lane; b < nb; b += 32) {
         if (m.body_depth[b] != lev) continue;
         float cv[6], ca[6];
         const int p = m.body_parent[b], da = m.body_dofadr[b];
-        for (int k = 0; k < 6; k++) { cv[k] = e.cvel[p][k]; ca[k] = e.cacc[p][k]; }
+        for (int k = 0; k < 6; k++) { cv[k] = e.k.cvel[p][k]; ca[k] = e.k.cacc[p][k]; }
         if (b == 1) {
-          for (int d = 0; d < 3; d++) { for (int k = 0; k < 6; k++) { e.cdofdot[da + d][k] = 0.f; cv[k] += e.cdof[da + d][k] * e.qvel[da + d]; } }
-          for (int d = 3; d < 6; d++) g_crossmotion(e.cdofdot[da + d], cv, e.cdof[da + d]);
+          for (int d = 0; d < 3; d++) { for (int k = 0; k < 6; k++) { e.k.cdofdot[da + d][k] = 0.f; cv[k] += e.cdof[da + d][k] * e.qvel[da + d]; } }
+          for (int d = 3; d < 6; d++) g_crossmotion(e.k.cdofdot[da + d], cv, e.cdof[da + d]);
           for (int d = 3; d < 6; d++) for (int k = 0; k < 6; k++) cv[k] += e.cdof[da + d][k] * e.qvel[da + d];
-          for (int d = 0; d < 6; d++) for (int k = 0; k < 6; k++) ca[k] += e.cdofdot[da + d][k] * e.qvel[da + d];
+          for (int d = 0; d < 6; d++) for (int k = 0; k < 6; k++) ca[k] += e.k.cdofdot[da + d][k] * e.qvel[da + d];
         } else {
-          g_crossmotion(e.cdofdot[da], cv, e.cdof[da]);
-          for (int k = 0; k < 6; k++) { cv[k] += e.cdof[da][k] * e.qvel[da]; ca[k] += e.cdofdot[da][k] * e.qvel[da]; }
+          g_crossmotion(e.k.cdofdot[da], cv, e.cdof[da]);
+          for (int k = 0; k < 6; k++) { cv[k] += e.cdof[da][k] * e.qvel[da]; ca[k] += e.k.cdofdot[da][k] * e.qvel[da]; }
         }
         float f[6], t1[6], t2[6];
-        g_inertvec(f, e.cinert[b], ca);
-        g_inertvec(t1, e.cinert[b], cv);
+        g_inertvec(f, e.k.cinert[b], ca);
+        g_inertvec(t1, e.k.cinert[b], cv);
         g_crossforce(t2, cv, t1);
-        for (int k = 0; k < 6; k++) { e.cvel[b][k] = cv[k]; e.cacc[b][k] = ca[k]; e.cfrc[b][k] = f[k] + t2[k]; }
+        for (int k = 0; k < 6; k++) { e.k.cvel[b][k] = cv[k]; e.k.cacc[b][k] = ca[k]; e.k.cfrc[b][k] = f[k] + t2[k]; }
       }
       __syncwarp();
     }
@@ -515,15 +521,14 @@ __global__ void __launch_bounds__(WARPS * 32) nm_generic_step_kernel(const GenAr
       for (int b = 1 + lane; b < nb; b += 32) {
         if (m.body_depth[b] != lev) continue;
         for (int c = b + 1; c < nb; c++)
-          if (m.body_parent[c] == b) for (int k = 0; k < 6; k++) e.cfrc[b][k] += e.cfrc[c][k];
+          if (m.body_parent[c] == b) for (int k = 0; k < 6; k++) e.k.cfrc[b][k] += e.k.cfrc[c][k];
       }
       __syncwarp();
     }
     // ------------------------------------------------------------------ P8 passive + actuation + smooth acceleration
     for (int i = lane; i < nv; i += 32) {
       float s = 0.f;
-      for (int k = 0; k < 6; k++) s += e.cdof[i][k] * e.cfrc[m.dof_body[i]][k];
-      e.bias[i] = s;
+      for (int k = 0; k < 6; k++) s += e.cdof[i][k] * e.k.cfrc[m.dof_body[i]][k];
       e.smooth[i] = -m.dof_damping[i] * e.qvel[i] - s;
     }
     __syncwarp();
@@ -637,8 +642,8 @@ __global__ void __launch_bounds__(WARPS * 32) nm_generic_step_kernel(const GenAr
         if (r < 0) continue;
         const float imp = m.lim_imp0;
         const float R = fmaxf((1.f - imp) * m.dof_invw[i] / imp, 1e-15f);
-        e.R[r] = R; e.D[r] = 1.f / R; e.floss[r] = m.dof_floss[i];
-        e.aref[r] = -m.lim_B * e.qvel[i];
+        e.s.R[r] = R; e.s.D[r] = 1.f / R; e.s.floss[r] = m.dof_floss[i];
+        e.s.aref[r] = -m.lim_B * e.qvel[i];
         e.rtype[r] = R_FRICTION; e.rdof[r] = i; e.rsgn[r] = 1.f;
       }
       // joint limits: lower side first, then upper, in joint (= body) order
@@ -661,8 +666,8 @@ __global__ void __launch_bounds__(WARPS * 32) nm_generic_step_kernel(const GenAr
           const int r = first + q, i = m.body_dofadr[b];
           const float imp = g_impedance(m.lim_solimp, dist[q]);
           const float R = fmaxf((1.f - imp) * m.dof_invw[i] / imp, 1e-15f);
-          e.R[r] = R; e.D[r] = 1.f / R; e.floss[r] = 0.f;
-          e.aref[r] = -m.lim_B * (sgn[q] * e.qvel[i]) - m.lim_K * imp * dist[q];
+          e.s.R[r] = R; e.s.D[r] = 1.f / R; e.s.floss[r] = 0.f;
+          e.s.aref[r] = -m.lim_B * (sgn[q] * e.qvel[i]) - m.lim_K * imp * dist[q];
           e.rtype[r] = R_LIMIT; e.rdof[r] = i; e.rsgn[r] = sgn[q];
         }
         base += __shfl_sync(0xffffffffu, incl, 31);
@@ -716,22 +721,22 @@ __global__ void __launch_bounds__(WARPS * 32) nm_generic_step_kernel(const GenAr
         const float imp = g_impedance(m.geom_solimp[g], pos);
         const float tran = m.body_invw[b][0];
         const float R0 = fmaxf((1.f - imp) * tran / imp, 1e-15f);
-        e.R[a] = R0;
+        e.s.R[a] = R0;
         if (dim > 1) {
           const float* fri = m.geom_friction[g];
           const float R1 = R0 / fmaxf(m.impratio, 1e-15f);
-          e.R[a + 1] = R1;
-          for (int j = 2; j < dim; j++) e.R[a + j] = R1 * fri[0] * fri[0] / (fri[j - 1] * fri[j - 1]);
+          e.s.R[a + 1] = R1;
+          for (int j = 2; j < dim; j++) e.s.R[a + j] = R1 * fri[0] * fri[0] / (fri[j - 1] * fri[j - 1]);
           e.cmu[c] = fri[0] * sqrtf(R1 / R0);
         } else e.cmu[c] = 0.f;
         for (int j = 0; j < dim; j++) {
           float vel = 0.f;
           for (int i = 0; i < nv; i++) vel += e.J[a + j][i] * e.qvel[i];
-          e.R[a + j] = fmaxf(e.R[a + j], 1e-15f);
-          e.D[a + j] = 1.f / e.R[a + j];
-          e.aref[a + j] = -m.geom_B[g] * vel - (j == 0 ? m.geom_K[g] * imp * pos : 0.f);
+          e.s.R[a + j] = fmaxf(e.s.R[a + j], 1e-15f);
+          e.s.D[a + j] = 1.f / e.s.R[a + j];
+          e.s.aref[a + j] = -m.geom_B[g] * vel - (j == 0 ? m.geom_K[g] * imp * pos : 0.f);
         }
-        e.cDm[c] = dim > 1 ? e.D[a] / (e.cmu[c] * e.cmu[c] * (1.f + e.cmu[c] * e.cmu[c])) : 0.f;
+        e.cDm[c] = dim > 1 ? e.s.D[a] / (e.cmu[c] * e.cmu[c] * (1.f + e.cmu[c] * e.cmu[c])) : 0.f;
       }
       __syncwarp();
     }
@@ -740,14 +745,14 @@ __global__ void __launch_bounds__(WARPS * 32) nm_generic_step_kernel(const GenAr
     const int ne = live ? e.nefc : 0, nsimple = live ? m.nfloss + e.nlim : 0;
     int niter = 0;
     if (ne == 0) {
-      if (live) for (int i = lane; i < nv; i += 32) { e.qacc[i] = e.qaccs[i]; e.fcon[i] = 0.f; }
+      if (live) for (int i = lane; i < nv; i += 32) e.qacc[i] = e.qaccs[i];
       __syncwarp();
     }
     {
       // residual jar = J x - aref in fp64 from the fp64 iterate; simple rows touch one dof, contact rows the dofs of their body's chain
       auto residual = [&](const double* x) {
         for (int r = lane; r < ne; r += 32) {
-          double t = -(double)e.aref[r];
+          double t = -(double)e.s.aref[r];
           if (r < nsimple) t += (double)e.rsgn[r] * x[e.rdof[r]];
           else {
             const int body = m.geom_body[e.cgeom[e.crow[r]]], nd = m.body_ndof[body];
@@ -774,9 +779,13 @@ __global__ void __launch_bounds__(WARPS * 32) nm_generic_step_kernel(const GenAr
       float gprev = 1e30f;
       bool active = ne > 0;                                          // (warp-uniform)
       // every trip evaluates forces and gradient at the current iterate FIRST, so whenever a warp stops iterating the forces in
-      // e.force / e.fcon belong to the returned qacc
+      // e.s.force / e.vec belong to the returned qacc
       for (int it = 0;; it++) {
+#ifdef GM_NOLOCKSTEP
+        if (!active) break;                                          // (experiment: every warp on its own)
+#else
         if (__syncthreads_and(!active)) break;                       // lockstep: all warps of the CTA start a Newton trip together
+#endif
         if (active) do {
         niter = it;
         for (int i = lane; i < nv; i += 32) e.vec[i] = (float)(e.xd[i] - (double)e.qaccs[i]);
@@ -788,16 +797,16 @@ __global__ void __launch_bounds__(WARPS * 32) nm_generic_step_kernel(const GenAr
         float gn = 0.f, gref = 0.f;
         for (int i = lane; i < nv; i += 32) {
           float jf = 0.f;
-          for (int r = nsimple; r < ne; r++) jf += e.J[r][i] * e.force[r];
+          for (int r = nsimple; r < ne; r++) jf += e.J[r][i] * e.s.force[r];
           const int fr = m.dof_flossrow[i];
-          if (fr >= 0) jf += e.force[fr];
-          e.fcon[i] = jf;
+          if (fr >= 0) jf += e.s.force[fr];
+          e.vec[i] = jf;
         }
         __syncwarp();
-        for (int r = m.nfloss + lane; r < nsimple; r += 32) e.fcon[e.rdof[r]] += e.rsgn[r] * e.force[r];     // limit rows: distinct dofs
+        for (int r = m.nfloss + lane; r < nsimple; r += 32) e.vec[e.rdof[r]] += e.rsgn[r] * e.s.force[r];     // limit rows: distinct dofs
         __syncwarp();
         for (int i = lane; i < nv; i += 32) {
-          const float jf = e.fcon[i], t = e.Ma[i] - jf;
+          const float jf = e.vec[i], t = e.Ma[i] - jf;
           e.grad[i] = t; gn += t * t; gref += e.Ma[i] * e.Ma[i] + jf * jf;
         }
         gn = g_warpsum(gn); gref = g_warpsum(gref);
@@ -809,11 +818,11 @@ __global__ void __launch_bounds__(WARPS * 32) nm_generic_step_kernel(const GenAr
         // Hessian (lower triangle) H = M + sum_r Hd_r J_r J_r' + cone terms.  Simple rows add to the diagonal; a contact only
         // touches the dofs of its body's chain (9 of 18 for a leg): a bottom-zone contact adds its rows weighted by D, one on the
         // cone adds Dm mu^2 (J0 - b)(J0 - b)' + c (sum_k fri_k^2 J_k J_k' - b b').  One contact at a time, its chain pairs over the lanes.
-        for (int idx = lane; idx < nv * nv; idx += 32) { const int i = idx / nv, k = idx - i * nv; if (k <= i) e.H[i][k] = e.M[i][k]; }
+        for (int idx = lane; idx < nv * nv; idx += 32) { const int i = idx / nv, k = idx - i * nv; if (k <= i) e.s.H[i][k] = e.M[i][k]; }
         __syncwarp();
-        for (int i = lane; i < nv; i += 32) { const int fr = m.dof_flossrow[i]; if (fr >= 0) e.H[i][i] += e.Hd[fr]; }
+        for (int i = lane; i < nv; i += 32) { const int fr = m.dof_flossrow[i]; if (fr >= 0) e.s.H[i][i] += e.s.Hd[fr]; }
         __syncwarp();
-        for (int r = m.nfloss + lane; r < nsimple; r += 32) e.H[e.rdof[r]][e.rdof[r]] += e.Hd[r];
+        for (int r = m.nfloss + lane; r < nsimple; r += 32) e.s.H[e.rdof[r]][e.rdof[r]] += e.s.Hd[r];
         __syncwarp();
         for (int c = 0; c < e.ncon; c++) {
           const int zone = e.czone[c];
@@ -824,20 +833,20 @@ __global__ void __launch_bounds__(WARPS * 32) nm_generic_step_kernel(const GenAr
           for (int p = lane; p < nd * (nd + 1) / 2; p += 32) {
             const int i = m.body_dofs[body][g_tri_r[p]], k = m.body_dofs[body][g_tri_c[p]];
             float s = 0.f;
-            if (zone == 1) { for (int j = 0; j < dim; j++) s += e.D[a + j] * e.J[a + j][i] * e.J[a + j][k]; }
+            if (zone == 1) { for (int j = 0; j < dim; j++) s += e.s.D[a + j] * e.J[a + j][i] * e.J[a + j][k]; }
             else {
               const float bi = e.cb[c][i], bk = e.cb[c][k];
               float t = 0.f;
               for (int j = 1; j < dim; j++) t += fri[j - 1] * fri[j - 1] * e.J[a + j][i] * e.J[a + j][k];
               s = w0 * (e.J[a][i] - bi) * (e.J[a][k] - bk) + cc * (t - bi * bk);
             }
-            e.H[i][k] += s;
+            e.s.H[i][k] += s;
           }
           __syncwarp();
         }
         for (int i = lane; i < nv; i += 32) e.dir[i] = -e.grad[i];
         __syncwarp();
-        if (!g_solve_spd(e.H, e.dir, nv, lane)) { active = false; break; }
+        if (!g_solve_spd(e.s.H, e.dir, nv, lane)) { active = false; break; }
         if (quad) {
           // quadratic phase (relative gradient <= 1e-5): full Newton steps without a line search.  At a relative gradient
           // <= 1e-6 the step lands below the fp32 rounding of the gradient (1e-12 relative in exact arithmetic): it is taken and
@@ -856,7 +865,7 @@ __global__ void __launch_bounds__(WARPS * 32) nm_generic_step_kernel(const GenAr
             const int body = m.geom_body[e.cgeom[e.crow[r]]], nd = m.body_ndof[body];
             for (int q = 0; q < nd; q++) { const int i = m.body_dofs[body][q]; t += e.J[r][i] * e.dir[i]; }
           }
-          e.jv[r] = t;
+          e.s.jv[r] = t;
         }
         float a1 = 0.f, a2 = 0.f;
         for (int i = lane; i < nv; i += 32) { float t = 0.f; for (int k = 0; k < nv; k++) t += e.M[i][k] * e.dir[k]; a1 += e.dir[i] * e.Ma[i]; a2 += e.dir[i] * t; }
@@ -904,10 +913,10 @@ __global__ void __launch_bounds__(WARPS * 32) nm_generic_step_kernel(const GenAr
       if (any_damp) {
         // (M + h D) a = qfrc_smooth + qfrc_constraint = M qacc at the solver's optimum  =>  a = qacc - h (M + h D)^-1 D qacc:
         // the correction is O(h), so its rounding does not matter, and no constraint force has to be formed
-        for (int idx = lane; idx < nv * nv; idx += 32) { const int i = idx / nv, k = idx - i * nv; e.H[i][k] = e.M[i][k] + (i == k ? h * m.dof_damping[i] : 0.f); }
+        for (int idx = lane; idx < nv * nv; idx += 32) { const int i = idx / nv, k = idx - i * nv; e.s.H[i][k] = e.M[i][k] + (i == k ? h * m.dof_damping[i] : 0.f); }
         for (int i = lane; i < nv; i += 32) e.vec[i] = m.dof_damping[i] * e.qacc[i];
         __syncwarp();
-        g_solve_spd(e.H, e.vec, nv, lane);
+        g_solve_spd(e.s.H, e.vec, nv, lane);
         for (int i = lane; i < nv; i += 32) e.vec[i] = e.qacc[i] - h * e.vec[i];
         __syncwarp();
       } else {
