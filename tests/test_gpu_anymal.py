@@ -153,3 +153,24 @@ def test_nstep_equals_repeated_single_steps(trio):
         b.physics_step(ctrl, 1)
     assert torch.equal(a.qpos, b.qpos) and torch.equal(a.qvel, b.qvel) and torch.equal(a.warm, b.warm)
     assert a.launches == 2 and b.launches == 8                       # first tier + second (overflow) tier per call
+
+
+def test_ragged_batches_and_batch_independence(trio):
+    """Environment i does not depend on its neighbours, on the batch size or on how the batch fills the last CTA (5 and 203
+    environments with 4 per CTA), nor on whether a neighbour overflows into the second capacity tier; runs are bit-reproducible."""
+    cm, gm, _, _ = trio
+    n = 203
+    q, v, rng = _tumbling(cm, n, 21, low=True)
+    ctrl = rng.uniform(-1, 1, (n, 12)).astype(np.float32)
+    outs = []
+    for m in (n, n, 5, 64):
+        g = GenBatch(gm, m, DEV)
+        _push(g, q[:m], v[:m], np.zeros((m, 18)))
+        for _ in range(6):
+            g.physics_step(torch.from_numpy(ctrl[:m]).to(DEV), 3)
+        outs.append((g.qpos.cpu().numpy(), g.qvel.cpu().numpy(), g.info.cpu().numpy()))
+    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
+    for k in (2, 3):
+        m = len(outs[k][0])
+        assert np.array_equal(outs[0][0][:m], outs[k][0]) and np.array_equal(outs[0][1][:m], outs[k][1]) and np.array_equal(outs[0][2][:m], outs[k][2])
+    assert np.isfinite(outs[0][0]).all() and (outs[0][2][:, 0] > 16).any()              # some environments went through the second tier
