@@ -463,6 +463,7 @@ struct nm_batch {
   int* d_nbr_adr;
   int* d_nbr;
   float4* d_edge;
+  unsigned short *d_nbr16, *d_nadr16;
   int* d_hint;
   float* d_acc;          // [2][19] double-buffered episode accumulators
   int parity;
@@ -566,6 +567,27 @@ static int batch_create_impl(const nm_model* m, int num_envs, int device, uint64
   a.hull_hint = b->d_hint;
   a.ep_means = bufs->ep_means; a.time_outs_latched = bufs->time_outs_latched;
   a.model = b->d_model; a.cfg = b->d_cfg; a.hull_vert = b->d_hull; a.hull_nbr_adr = b->d_nbr_adr; a.hull_nbr = b->d_nbr; a.hull_edge = b->d_edge;
+  {
+    // compact adjacency (16-bit ids and offsets) for the support-vertex walk.  NM_HULL_SMEM=1 makes every CTA stage the tables
+    // (52 KB for the hexapod) in shared memory: measured (round 2, gpurun_out/r02_qb17.log, r02_phase8*.log) the walk itself
+    // drops from 4630 to 3210 cycles per substep but the step does not get faster (89.1 -> 91.0 us at 4096 envs, equal at
+    // 16 384 / 131 072): with the CTA's warps in lockstep the phase is bound by instruction issue, not by load latency.  Off by default.
+    const size_t ne = m->nbr.size(), nv1 = m->nbr_adr.size();
+    if (ne >= 65536) return fail(NM_ERR_UNSUPPORTED, "hull adjacency with more than 65535 directed edges is not supported");
+    const size_t ne_pad = (ne + 8 + 7) & ~(size_t)7, na_pad = (nv1 + 7) & ~(size_t)7;
+    std::vector<unsigned short> n16(ne_pad, 0), a16(na_pad, 0);
+    for (size_t i = 0; i < ne; i++) n16[i] = (unsigned short)m->nbr[i];
+    for (size_t i = 0; i < nv1; i++) a16[i] = (unsigned short)m->nbr_adr[i];
+    CUDA_OK(cudaMalloc(&b->d_nbr16, 2 * ne_pad));
+    CUDA_OK(cudaMemcpy(b->d_nbr16, n16.data(), 2 * ne_pad, cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMalloc(&b->d_nadr16, 2 * na_pad));
+    CUDA_OK(cudaMemcpy(b->d_nadr16, a16.data(), 2 * na_pad, cudaMemcpyHostToDevice));
+    a.hull_nbr16 = b->d_nbr16; a.hull_nadr16 = b->d_nadr16;
+    a.hull_nv = (int)m->hull4.size(); a.hull_ne_pad = (int)ne_pad; a.hull_na_pad = (int)na_pad;
+    const char* sw = getenv("NM_HULL_SMEM");
+    const size_t bytes = 16 * m->hull4.size() + 2 * ne_pad + 2 * na_pad;
+    a.hull_smem = (bytes <= 96 * 1024 && sw && sw[0] == '1') ? 1 : 0;
+  }
   a.num_envs = num_envs; a.nstep = cfg ? cfg->decimation : 1; a.step_counter = 0; a.env_offset = 0; a.seed = seed;
   a.qpos = bufs->qpos; a.qvel = bufs->qvel; a.warm = bufs->warm; a.actions = bufs->actions; a.dof_pos = bufs->dof_pos;
   a.dof_vel = bufs->dof_vel; a.commands = bufs->commands; a.episode_length = reinterpret_cast<long long*>(bufs->episode_length);
@@ -580,7 +602,7 @@ static int batch_create_impl(const nm_model* m, int num_envs, int device, uint64
 
 extern "C" void nm_batch_destroy(nm_batch* b) {
   if (!b) return;
-  cudaFree(b->d_model); cudaFree(b->d_cfg); cudaFree(b->d_hull); cudaFree(b->d_nbr_adr); cudaFree(b->d_nbr); cudaFree(b->d_edge); cudaFree(b->d_hint); cudaFree(b->d_acc);
+  cudaFree(b->d_model); cudaFree(b->d_cfg); cudaFree(b->d_hull); cudaFree(b->d_nbr_adr); cudaFree(b->d_nbr); cudaFree(b->d_edge); cudaFree(b->d_nbr16); cudaFree(b->d_nadr16); cudaFree(b->d_hint); cudaFree(b->d_acc);
   if (b->d_stage_actions) cudaFree(b->d_stage_actions);
   delete b;
 }

@@ -44,23 +44,17 @@ __device__ long long* nm_timing_buf = nullptr;
 #define TSTAMP(k)
 #endif
 #define NM_MINVAL 1e-15f
-// Loads of the hull tables (read-only, shared by all environments, a few KB of them hot): ask L1 to keep their lines
-// over the streaming local-memory traffic of the contact blocks.
-#ifdef NM_HULL_EVICT_LAST
-__device__ __forceinline__ float4 ld_hull4(const float4* p) {
-  float4 v;
-  asm volatile("ld.global.nc.L1::evict_last.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
-  return v;
+// Directed hull edge e of a geom whose vertex table starts at hv: the neighbour's coordinates (xyz) and its geom-local id (w),
+// through the compact adjacency (16-bit neighbour id -> vertex table).  Generic loads: the tables live in shared memory when the
+// CTA staged them, in global memory otherwise.  (Round 2 also measured a 16-byte-per-edge table with the coordinates inline -- one
+// load level less, 165 KB -- and `ld.global.nc.L1::evict_last` on either layout: no difference to 0.1 us, the walk is bound by
+// the latency of each level, not by hit rates.)
+__device__ __forceinline__ float4 ld_edge(const unsigned short* nbr, const float4* hv, int e) {
+  const int u = nbr[e];
+  float4 q = hv[u];
+  q.w = __int_as_float(u);
+  return q;
 }
-__device__ __forceinline__ int ld_hulli(const int* p) {
-  int v;
-  asm volatile("ld.global.nc.L1::evict_last.s32 %0, [%1];" : "=r"(v) : "l"(p));
-  return v;
-}
-#else
-__device__ __forceinline__ float4 ld_hull4(const float4* p) { return __ldg(p); }
-__device__ __forceinline__ int ld_hulli(const int* p) { return __ldg(p); }
-#endif
 
 #define NM_TINY 1e-30f
 
@@ -811,6 +805,24 @@ __global__ void __launch_bounds__(BLOCK, MINB) nm_step_kernel(const NmKernelArgs
       for (int i = threadIdx.x; i < (int)(sizeof(NmDevCfg) / 16); i += blockDim.x) d2[i] = __ldg(s2 + i);
     }
   }
+  // hull tables of the support-vertex walk, optionally staged once per CTA (experiment switch NM_HULL_SMEM=1, see nm_abi.cu:
+  // measured neutral -- the walk is ~3 rounds of ~120 instructions per substep and issue bound with the warps in lockstep)
+  const float4* hvt = A.hull_vert;
+  const unsigned short* nbt = A.hull_nbr16;
+  const unsigned short* nat = A.hull_nadr16;
+  if (A.hull_smem) {
+    unsigned char* base = dyn_smem + (sizeof(HullPose) * 6 + sizeof(PairBlk) * NM_MAXPAIR + 12 * sizeof(float4)) * (BLOCK / NM_OCT);
+    int4* hs = reinterpret_cast<int4*>(base);
+    int4* ns = hs + A.hull_nv;
+    int4* as = ns + A.hull_ne_pad / 8;
+    const int4 *gv = reinterpret_cast<const int4*>(A.hull_vert), *gn = reinterpret_cast<const int4*>(A.hull_nbr16), *ga = reinterpret_cast<const int4*>(A.hull_nadr16);
+    for (int i = threadIdx.x; i < A.hull_nv; i += BLOCK) hs[i] = __ldg(gv + i);
+    for (int i = threadIdx.x; i < A.hull_ne_pad / 8; i += BLOCK) ns[i] = __ldg(gn + i);
+    for (int i = threadIdx.x; i < A.hull_na_pad / 8; i += BLOCK) as[i] = __ldg(ga + i);
+    hvt = reinterpret_cast<const float4*>(hs);
+    nbt = reinterpret_cast<const unsigned short*>(ns);
+    nat = reinterpret_cast<const unsigned short*>(as);
+  }
   __syncthreads();
 
   const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1026,6 +1038,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) nm_step_kernel(const NmKernelArgs
 
     TSTAMP(5 + 10 * sub);
     PHASE_SYNC();
+    if (sub == 0) TSTAMP(23);
     // ================================================================ P4 collision: convex hull vs plane
     // Support vertex by hill-climbing the hull graph (a local minimum of a linear function on a convex hull is the
     // global one), warm-started from the previous substep's / step's support vertex.  The hint word also remembers
@@ -1037,18 +1050,23 @@ __global__ void __launch_bounds__(BLOCK, MINB) nm_step_kernel(const NmKernelArgs
     int cvert[NM_MAXC];
     if (G.has) {
       const V3 dl = mulT(Xg, pn);                        // plane normal in the geom frame; minimise dl . v
-      const float4* hv = A.hull_vert + G.hull_adr;
-      const int* nadr = A.hull_nbr_adr + G.hull_adr;
+      const float4* hv = hvt + G.hull_adr;
+      const unsigned short* nadr = nat + G.hull_adr;
       int best = hint & 0x1ff, deg = (hint >> 9) & 0x3f, e0 = hint >> 15;
-      float4 vb = ld_hull4(hv + best);
+      float4 vb = hv[best];
       float bval = fmaf(dl.x, vb.x, fmaf(dl.y, vb.y, dl.z * vb.z));
+#ifdef NM_TIMING
+      int dbg_rounds = 0, dbg_trips = 0;
+#endif
       for (;;) {
-        if (deg == 0) { e0 = ld_hulli(nadr + best); deg = ld_hulli(nadr + best + 1) - e0; }
+#ifdef NM_TIMING
+        dbg_rounds++;
+#endif
+        if (deg == 0) { e0 = nadr[best]; deg = nadr[best + 1] - e0; }
         int nb = best;
         const int el = e0 + deg - 1;
         for (int e = e0; e <= el; e += 4) {              // 4 neighbours per trip: loads issued together, compared in list order
-          const float4 w0 = ld_hull4(A.hull_edge + e), w1 = ld_hull4(A.hull_edge + min(e + 1, el)), w2 = ld_hull4(A.hull_edge + min(e + 2, el)),
-                       w3 = ld_hull4(A.hull_edge + min(e + 3, el));
+          const float4 w0 = ld_edge(nbt, hv, e), w1 = ld_edge(nbt, hv, min(e + 1, el)), w2 = ld_edge(nbt, hv, min(e + 2, el)), w3 = ld_edge(nbt, hv, min(e + 3, el));
           const float a0 = fmaf(dl.x, w0.x, fmaf(dl.y, w0.y, dl.z * w0.z)), a1 = fmaf(dl.x, w1.x, fmaf(dl.y, w1.y, dl.z * w1.z));
           const float a2 = fmaf(dl.x, w2.x, fmaf(dl.y, w2.y, dl.z * w2.z)), a3 = fmaf(dl.x, w3.x, fmaf(dl.y, w3.y, dl.z * w3.z));
           if (a0 < bval) { bval = a0; nb = __float_as_int(w0.w); vb = w0; }
@@ -1060,6 +1078,16 @@ __global__ void __launch_bounds__(BLOCK, MINB) nm_step_kernel(const NmKernelArgs
         best = nb; deg = 0;
       }
       hint = best | (deg << 9) | (e0 << 15);
+#ifdef NM_TIMING
+      if (sub == 0 && nm_timing_buf) {
+        const unsigned am = __activemask();
+        int r = dbg_rounds, dg = deg;
+        for (int o = 16; o > 0; o >>= 1) { r = max(r, __shfl_xor_sync(am, r, o)); dg = max(dg, __shfl_xor_sync(am, dg, o)); }
+        if ((threadIdx.x & 31) == __ffs(am) - 1) { nm_timing_buf[(size_t)(gtid >> 5) * 32 + 27] = r; nm_timing_buf[(size_t)(gtid >> 5) * 32 + 28] = dg; }
+        (void)dbg_trips;
+      }
+      if (sub == 0) TSTAMP(24);
+#endif
       V3 wv = pg + mul(Xg, mk(vb.x, vb.y, vb.z));
       float dist = dot(pn, wv) - sm.plane_d;
       if (dist <= G.margin) {
@@ -1070,14 +1098,13 @@ __global__ void __launch_bounds__(BLOCK, MINB) nm_step_kernel(const NmKernelArgs
         // candidates (model option): the support vertex's hull-graph neighbours from the edge table, or every hull vertex in
         // index order from the vertex table (both tables hold float4 coordinates)
         const bool allv = sm.planemesh_allverts != 0;
-        const float4* cand = allv ? hv : A.hull_edge;
         const int ef = allv ? 0 : e0, el = allv ? G.hull_num - 1 : e0 + deg - 1;
         const float hsep = sm.planemesh_sepvert ? 0.5f : 0.f;   // separation between contact points (0) or hull vertices (point + dist/2 n)
         for (int e = ef; e <= el && nc < NM_MAXC; e += 4) {   // up to maxc - 1 more
           // four candidates per trip (L1-resident after the walk); almost all fail the cheap depth pre-test
           float4 ww[4];
 #pragma unroll
-          for (int k = 0; k < 4; k++) ww[k] = ld_hull4(cand + min(e + k, el));
+          for (int k = 0; k < 4; k++) ww[k] = allv ? hv[min(e + k, el)] : ld_edge(nbt, hv, min(e + k, el));
 #pragma unroll
           for (int k = 0; k < 4; k++) {
             const float4 w4 = ww[k];
@@ -1095,6 +1122,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) nm_step_kernel(const NmKernelArgs
         }
       }
     }
+    if (sub == 0) TSTAMP(25);
     // ================================================================ P4b convex-convex pairs between the legs' hulls
     // Broad phase on bounding capsules (hot, ~3 segment-segment tests per lane); MPR + contact block only for overlapping
     // capsules (cold: the whole warp skips it when none of its 4 environments has a candidate).
@@ -1198,6 +1226,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) nm_step_kernel(const NmKernelArgs
     }
     int npair_max = max(npair, __shfl_xor_sync(FULL, npair, 8));
     npair_max = max(npair_max, __shfl_xor_sync(FULL, npair_max, 16));          // warp-uniform
+    if (sub == 0) TSTAMP(26);
     const int ncon_env = oct_sumi(nc) + npair;
     // Sweep order inside an env is MuJoCo's row order: base geom (lane 6) first, then legs 0..5.  Each octet walks ITS
     // OWN list of contact-owning lanes: in slot k of a sweep the k-th owner of every octet works, so a sweep costs
@@ -1911,6 +1940,8 @@ void nm_launch_finalize(const NmKernelArgs& a, void* stream) {
 }
 
 static size_t step_dyn_smem(int block) { return (size_t)(block / NM_OCT) * (6 * sizeof(HullPose) + NM_MAXPAIR * sizeof(PairBlk) + 12 * sizeof(float4)); }
+static size_t hull_smem_bytes(const NmKernelArgs& a) { return a.hull_smem ? 16 * (size_t)a.hull_nv + 2 * (size_t)a.hull_ne_pad + 2 * (size_t)a.hull_na_pad : 0; }
+#define NM_HULL_SMEM_MAX (96 * 1024)      // hull tables larger than this stay in global memory (nm_abi.cu clears hull_smem)
 
 void nm_launch_step(const NmKernelArgs& a, bool env_mode, void* stream) {
   const int threads = a.num_envs * NM_OCT;
@@ -1920,11 +1951,13 @@ void nm_launch_step(const NmKernelArgs& a, bool env_mode, void* stream) {
   cudaGetDevice(&dev);
   int& sms = sms_of[dev & 63];
   if (sms == 0 && (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0)) sms = 148;
-  const bool one_wave = threads <= sms * 8 * 32;           // fits one wave of the 255-register build (8 warps/SM)
+  // with the hull tables staged in shared memory a CTA needs ~120 KB: one 256-thread CTA per SM for every batch size (measured
+  // equal to two 128-thread CTAs at one-wave sizes without the staging)
+  const bool one_wave = threads <= sms * 8 * 32 && !a.hull_smem;
   static bool attr_set[64] = {false};                      // the large-block build needs > 48 KB of shared memory in total
   if (!attr_set[dev & 63]) {
-    cudaFuncSetAttribute(nm_step_kernel<true, NM_LARGE_BLOCK, NM_LARGE_MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)step_dyn_smem(NM_LARGE_BLOCK));
-    cudaFuncSetAttribute(nm_step_kernel<false, NM_LARGE_BLOCK, NM_LARGE_MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)step_dyn_smem(NM_LARGE_BLOCK));
+    cudaFuncSetAttribute(nm_step_kernel<true, NM_LARGE_BLOCK, NM_LARGE_MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(step_dyn_smem(NM_LARGE_BLOCK) + NM_HULL_SMEM_MAX));
+    cudaFuncSetAttribute(nm_step_kernel<false, NM_LARGE_BLOCK, NM_LARGE_MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(step_dyn_smem(NM_LARGE_BLOCK) + NM_HULL_SMEM_MAX));
     cudaFuncSetAttribute(nm_step_kernel<true, NM_SMALL_BLOCK, NM_SMALL_MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)step_dyn_smem(NM_SMALL_BLOCK));
     cudaFuncSetAttribute(nm_step_kernel<false, NM_SMALL_BLOCK, NM_SMALL_MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)step_dyn_smem(NM_SMALL_BLOCK));
     attr_set[dev & 63] = true;
@@ -1935,8 +1968,9 @@ void nm_launch_step(const NmKernelArgs& a, bool env_mode, void* stream) {
     else nm_step_kernel<false, NM_SMALL_BLOCK, NM_SMALL_MINB><<<blocks, NM_SMALL_BLOCK, step_dyn_smem(NM_SMALL_BLOCK), st>>>(a);
   } else {
     const int blocks = (threads + NM_LARGE_BLOCK - 1) / NM_LARGE_BLOCK;
-    if (env_mode) nm_step_kernel<true, NM_LARGE_BLOCK, NM_LARGE_MINB><<<blocks, NM_LARGE_BLOCK, step_dyn_smem(NM_LARGE_BLOCK), st>>>(a);
-    else nm_step_kernel<false, NM_LARGE_BLOCK, NM_LARGE_MINB><<<blocks, NM_LARGE_BLOCK, step_dyn_smem(NM_LARGE_BLOCK), st>>>(a);
+    const size_t smem = step_dyn_smem(NM_LARGE_BLOCK) + hull_smem_bytes(a);
+    if (env_mode) nm_step_kernel<true, NM_LARGE_BLOCK, NM_LARGE_MINB><<<blocks, NM_LARGE_BLOCK, smem, st>>>(a);
+    else nm_step_kernel<false, NM_LARGE_BLOCK, NM_LARGE_MINB><<<blocks, NM_LARGE_BLOCK, smem, st>>>(a);
   }
 }
 

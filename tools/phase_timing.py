@@ -46,6 +46,14 @@ for rep in range(10):
             add(f"sub{sub} {names[k]:28s}", (np.median(d), d.max()))
             prev = cur
     add("P11 of last substep + epilogue", np.median(t[:, 22] - t[:, 19]))
+    if t[:, 23].max() > 0:                                   # finer stamps inside the collision phase of substep 0 (NM_TIMING builds)
+        add("sub0 barrier before P4", (np.median(t[:, 23] - t[:, 5]), (t[:, 23] - t[:, 5]).max()))
+        add("sub0 P4 hull-plane (walk + extra contacts)", (np.median(t[:, 25] - t[:, 23]), (t[:, 25] - t[:, 23]).max()))
+        add("sub0   of which the support-vertex walk", (np.median(t[:, 24] - t[:, 23]), (t[:, 24] - t[:, 23]).max()))
+        add("sub0   walk rounds (max over the warp's hulls)", (np.median(t[:, 27]), t[:, 27].max()))
+        add("sub0   max vertex degree at the support vertex", (np.median(t[:, 28]), t[:, 28].max()))
+        add("sub0 P4b tibia pairs broad phase", (np.median(t[:, 26] - t[:, 25]), (t[:, 26] - t[:, 25]).max()))
+        add("sub0 after P4b -> stamp 6", (np.median(t[:, 6] - t[:, 26]), (t[:, 6] - t[:, 26]).max()))
 print(f"N={N} warps={nw}  (cycles @1.965 GHz; median over 10 steps of [median over warps, max over warps])")
 for k, v in acc.items():
     a = np.array(v)
