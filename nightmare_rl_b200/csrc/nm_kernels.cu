@@ -35,6 +35,22 @@
 #else
 #define PHASE_SYNC() __syncthreads()
 #endif
+// experiment switches: individual phase barriers off (NM_SKIP_SYNC_B: before CRBA, _C: before the factorisations, _E: before the contact build)
+#ifdef NM_SKIP_SYNC_B
+#define PHASE_SYNC_B()
+#else
+#define PHASE_SYNC_B() PHASE_SYNC()
+#endif
+#ifdef NM_SKIP_SYNC_C
+#define PHASE_SYNC_C()
+#else
+#define PHASE_SYNC_C() PHASE_SYNC()
+#endif
+#ifndef NM_KEEP_SYNC_E
+#define PHASE_SYNC_E()       // measured (gpurun_out/r02_qb18.log): without this barrier +2.6 % at 131 072 envs, +3 % at 16 384, equal at 4096
+#else
+#define PHASE_SYNC_E() PHASE_SYNC()
+#endif
 // Experiment builds (-DNM_TIMING): every warp records clock64() at the phase boundaries into a global buffer
 // (tools/phase_timing.py); compiled out of the product library.
 #ifdef NM_TIMING
@@ -974,7 +990,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) nm_step_kernel(const NmKernelArgs
     }
 
     TSTAMP(3 + 10 * sub);
-    PHASE_SYNC();
+    PHASE_SYNC_B();
     // ================================================================ P3 CRBA in block form
     float Mk[6], C[3][6], Mbb[21];
     {
@@ -1011,7 +1027,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) nm_step_kernel(const NmKernelArgs
     }
 
     TSTAMP(4 + 10 * sub);
-    PHASE_SYNC();
+    PHASE_SYNC_C();
     // ================================================================ P8 actuation + smooth acceleration
     float rk[3], rb[6], hD[3];
 #pragma unroll
@@ -1253,7 +1269,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) nm_step_kernel(const NmKernelArgs
     }
 
     TSTAMP(6 + 10 * sub);
-    PHASE_SYNC();
+    PHASE_SYNC_E();
     float xb[6], xk[3];          // constraint-induced acceleration M^-1 J^T f (after noslip)
 #pragma unroll
     for (int i = 0; i < 6; i++) xb[i] = 0.f;
