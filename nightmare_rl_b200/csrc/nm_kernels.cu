@@ -421,30 +421,38 @@ __device__ __forceinline__ void con_sweep(ConRegs& k, float* u, float* wv, float
       if (e == 2) { r[3] = fmaf(de, g23, r[3]); }
     }
   } else {
+    // noslip on the two opposing edge pairs, their sum 2*mid held fixed: f = (mid + x, mid - x).  With o = (mid + s, mid - s) the
+    // stationarity condition of the oracle's pair problem (K0 + K1 x = 0, K0 = mid (a00 - a11) + bc0 - bc1, bc = res - A o)
+    // reduces to x = s - (res0 - res1) / K1, K1 = a00 + a11 - 2 a01, and the cost change to d0 (K1 d0 / 2 + res0 - res1):
+    // half the instructions of evaluating K0, bc and the 2x2 quadratic form literally.
 #pragma unroll
     for (int t = 0; t < 2; t++) {
       const float a00 = t ? g22 : g00, a11 = t ? g33 : g11, a01 = t ? g23 : g01;
-      const float o0 = o[2 * t], o1 = o[2 * t + 1], res0 = r[2 * t], res1 = r[2 * t + 1];
-      const float bc0 = res0 - a00 * o0 - a01 * o1, bc1 = res1 - a01 * o0 - a11 * o1;
+      const float o0 = o[2 * t], o1 = o[2 * t + 1], dr = r[2 * t] - r[2 * t + 1];
       const float mid = 0.5f * (o0 + o1);
-      const float K0 = mid * (a00 - a11) + bc0 - bc1;
-      float f0, f1;
-      if (k.ik[t] == 0.f) { f0 = mid; f1 = mid; }
-      else {
-        float x = -K0 * k.ik[t];
-        if (x < -mid) { f0 = 0.f; f1 = 2.f * mid; }
-        else if (x > mid) { f0 = 2.f * mid; f1 = 0.f; }
-        else { f0 = mid + x; f1 = mid - x; }
-      }
+      const float x = k.ik[t] == 0.f ? 0.f : fmaf(-dr, k.ik[t], 0.5f * (o0 - o1));
+      float f0 = mid + x, f1 = mid - x;
+      if (x < -mid) { f0 = 0.f; f1 = 2.f * mid; }
+      else if (x > mid) { f0 = 2.f * mid; f1 = 0.f; }
       float d0 = f0 - o0, d1 = f1 - o1;
-      float change = 0.5f * (d0 * (a00 * d0 + a01 * d1) + d1 * (a01 * d0 + a11 * d1)) + d0 * res0 + d1 * res1;
+      float change = d0 * fmaf(0.5f * d0, (a00 + a11) - 2.f * a01, dr);
       if (change > 1e-10f) { f0 = o0; f1 = o1; d0 = 0.f; d1 = 0.f; change = 0.f; }
       improvement -= change;
       o[2 * t] = f0; o[2 * t + 1] = f1; d[2 * t] = d0; d[2 * t + 1] = d1;
       if (t == 0) { r[2] = fmaf(d0, g02, fmaf(d1, g12, r[2])); r[3] = fmaf(d0, g03, fmaf(d1, g13, r[3])); }
     }
   }
-  const float c0 = (d[0] + d[1]) + (d[2] + d[3]), c1 = mu * (d[0] - d[1]), c2 = mu * (d[2] - d[3]);
+  const float c1 = mu * (d[0] - d[1]), c2 = mu * (d[2] - d[3]);
+  if (in_noslip) {
+    // the normal component (d0 + d1) + (d2 + d3) is zero by construction (fp32 rounding aside): only the tangential rows move u, w
+    if (cout != nullptr) { cout[0] = 0.f; cout[1] = c1; cout[2] = c2; }
+#pragma unroll
+    for (int a = 0; a < 6; a++) u[a] = fmaf(k.Y[1][a], c1, fmaf(k.Y[2][a], c2, u[a]));
+#pragma unroll
+    for (int j = 0; j < 3; j++) wv[j] = fmaf(k.Z[1][j], c1, fmaf(k.Z[2][j], c2, wv[j]));
+    return;
+  }
+  const float c0 = (d[0] + d[1]) + (d[2] + d[3]);
   if (cout != nullptr) { cout[0] = c0; cout[1] = c1; cout[2] = c2; }
 #pragma unroll
   for (int a = 0; a < 6; a++) u[a] = fmaf(k.Y[0][a], c0, fmaf(k.Y[1][a], c1, fmaf(k.Y[2][a], c2, u[a])));
