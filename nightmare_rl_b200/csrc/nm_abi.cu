@@ -464,6 +464,7 @@ struct nm_batch {
   int* d_nbr;
   float4* d_edge;
   unsigned short *d_nbr16, *d_nadr16;
+  cudaEvent_t host_ev;   // nm_step_host waits for the step kernel's outputs, not for the extras latch launched behind it
   int* d_hint;
   float* d_acc;          // [2][19] double-buffered episode accumulators
   int parity;
@@ -602,7 +603,7 @@ static int batch_create_impl(const nm_model* m, int num_envs, int device, uint64
 
 extern "C" void nm_batch_destroy(nm_batch* b) {
   if (!b) return;
-  cudaFree(b->d_model); cudaFree(b->d_cfg); cudaFree(b->d_hull); cudaFree(b->d_nbr_adr); cudaFree(b->d_nbr); cudaFree(b->d_edge); cudaFree(b->d_nbr16); cudaFree(b->d_nadr16); cudaFree(b->d_hint); cudaFree(b->d_acc);
+  cudaFree(b->d_model); cudaFree(b->d_cfg); cudaFree(b->d_hull); cudaFree(b->d_nbr_adr); cudaFree(b->d_nbr); cudaFree(b->d_edge); cudaFree(b->d_nbr16); cudaFree(b->d_nadr16); if (b->host_ev) cudaEventDestroy(b->host_ev); cudaFree(b->d_hint); cudaFree(b->d_acc);
   if (b->d_stage_actions) cudaFree(b->d_stage_actions);
   delete b;
 }
@@ -701,10 +702,14 @@ extern "C" int nm_step_host(nm_batch* b, const float* h_actions, int act_stride,
     a.acc_next = b->d_acc + (NM_NREW + 1) * (b->parity ^ 1);
     b->parity ^= 1;
     nm_launch_step(a, true, stream);
+    // the host buffers are complete when the step kernel is: wait for an event recorded right behind it and let the extras
+    // latch (device-side state, stream-ordered before anything that reads it) run while the caller already has its outputs
+    if (!b->host_ev) CUDA_OK(cudaEventCreateWithFlags(&b->host_ev, cudaEventDisableTiming));
+    CUDA_OK(cudaEventRecord(b->host_ev, st));
     nm_launch_finalize(a, stream);
     b->launches += 2;
     CUDA_OK(cudaGetLastError());
-    CUDA_OK(cudaStreamSynchronize(st));
+    CUDA_OK(cudaEventSynchronize(b->host_ev));
     return NM_OK;
   }
   // Pageable host memory: staged copies on the same stream
