@@ -253,14 +253,16 @@ def bench_step(c, args):
 
     for i in range(PREROLL_STEPS):
         one_step(i)
-    for i in range(W):
-        one_step(i)
     c.barrier()
     sampler = ClockSampler(c.local)
     if rank == 0:
         sampler.start()
-        time.sleep(0.25)
+        time.sleep(0.25)                           # the sampler thread is up before anything is timed ...
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    c.barrier()
+    for i in range(W):                             # ... and the W warm-up steps run right before the timed ones, with the same
+        flush.zero_()                              # flush in between (a first step after an idle quarter second costs 1.6x)
+        one_step(i)
     l0 = batch.launches
     c.barrier()
     t_wall0 = time.time()
@@ -317,8 +319,9 @@ def bench_step(c, args):
             torch.cuda.empty_cache()
     del flush
     torch.cuda.empty_cache()
+    srt = sorted(step_ms)
     return dict(value=value, total_ms=total_ms, kern_ms=sum(step_ms) / K, clocks=clocks, launches=int(launches), e2e_val=e2e_val, Ke=Ke,
-                sweep=sweep, E=E, K=K, W=W)
+                sweep=sweep, E=E, K=K, W=W, step_ms_stats={"min": srt[0], "median": srt[len(srt) // 2], "max": srt[-1]})
 
 
 def bench_rollout(c, E=16384, T=80, reps=3):
@@ -581,6 +584,7 @@ def run_ours(args):
             "clocks": st["clocks"],
             "e2e": {"value": st["e2e_val"], "unit": UNIT, "h2d_bytes_per_step": E * 18 * 4, "d2h_bytes_per_step": E * (66 * 4 + 4 + 8), "steps": st["Ke"]},
             "gpu_launches": st["launches"],
+            "step_ms_stats": st["step_ms_stats"],
             "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak, "traffic": traffic,
                          "traffic_source": prof.get("file"), "algorithmic_bytes": BYTES_PER_ENV_STEP * E,
                          "peak_source": which, "kernel": "nm_step_kernel<true> (+ the 2 us nm_finalize_kernel inside the same event pair)", "kernel_ms": kern_ms,
