@@ -460,9 +460,6 @@ struct nm_batch {
   NmDevModel* d_model;
   NmDevCfg* d_cfg;
   float4* d_hull;
-  int* d_nbr_adr;
-  int* d_nbr;
-  float4* d_edge;
   unsigned short *d_nbr16, *d_nadr16;
   cudaEvent_t host_ev;   // nm_step_host waits for the step kernel's outputs, not for the extras latch launched behind it
   int* d_hint;
@@ -535,30 +532,13 @@ static int batch_create_impl(const nm_model* m, int num_envs, int device, uint64
   CUDA_OK(cudaMemcpy(b->d_cfg, &hc, sizeof(NmDevCfg), cudaMemcpyHostToDevice));
   CUDA_OK(cudaMalloc(&b->d_hull, sizeof(float4) * (m->hull4.size() + 1)));
   CUDA_OK(cudaMemcpy(b->d_hull, m->hull4.data(), sizeof(float4) * m->hull4.size(), cudaMemcpyHostToDevice));
-  CUDA_OK(cudaMalloc(&b->d_nbr_adr, sizeof(int) * (m->nbr_adr.size() + 1)));
-  CUDA_OK(cudaMemcpy(b->d_nbr_adr, m->nbr_adr.data(), sizeof(int) * m->nbr_adr.size(), cudaMemcpyHostToDevice));
-  CUDA_OK(cudaMalloc(&b->d_nbr, sizeof(int) * (m->nbr.size() + 1)));
-  CUDA_OK(cudaMemcpy(b->d_nbr, m->nbr.data(), sizeof(int) * m->nbr.size(), cudaMemcpyHostToDevice));
-  {
-    // edge table: neighbour coordinates next to the neighbour id (one load level less in the support-vertex walk)
-    if (m->hull4.size() > 0x1ff * 64) { /* vertex ids are geom-local; checked per geom below */ }
-    std::vector<float4> edge(m->nbr.size() + 4);
-    for (int g = 0; g < NM_OCT; g++) {
-      const NmGeom& G = m->dev.leg[g].geom;
-      if (!G.has) continue;
-      if (G.hull_num > 0x1ff) return fail(NM_ERR_UNSUPPORTED, "convex hulls with more than 511 vertices are not supported");
-      for (int v = 0; v < G.hull_num; v++) {
-        if (m->nbr_adr[G.hull_adr + v + 1] - m->nbr_adr[G.hull_adr + v] > 63) return fail(NM_ERR_UNSUPPORTED, "hull vertex with more than 63 neighbours");
-        for (int e = m->nbr_adr[G.hull_adr + v]; e < m->nbr_adr[G.hull_adr + v + 1]; e++) {
-          const int u = m->nbr[e];
-          float4 q = m->hull4[G.hull_adr + u];
-          memcpy(&q.w, &u, 4);
-          edge[e] = q;
-        }
-      }
-    }
-    CUDA_OK(cudaMalloc(&b->d_edge, sizeof(float4) * edge.size()));
-    CUDA_OK(cudaMemcpy(b->d_edge, edge.data(), sizeof(float4) * edge.size(), cudaMemcpyHostToDevice));
+  // limits the packed support-vertex hint (9 bits vertex, 6 bits degree) and the 16-bit adjacency rely on
+  for (int g = 0; g < NM_OCT; g++) {
+    const NmGeom& G = m->dev.leg[g].geom;
+    if (!G.has) continue;
+    if (G.hull_num > 0x1ff) return fail(NM_ERR_UNSUPPORTED, "convex hulls with more than 511 vertices are not supported");
+    for (int v = 0; v < G.hull_num; v++)
+      if (m->nbr_adr[G.hull_adr + v + 1] - m->nbr_adr[G.hull_adr + v] > 63) return fail(NM_ERR_UNSUPPORTED, "hull vertex with more than 63 neighbours");
   }
   CUDA_OK(cudaMalloc(&b->d_hint, sizeof(int) * (size_t)num_envs * NM_OCT));
   CUDA_OK(cudaMemset(b->d_hint, 0, sizeof(int) * (size_t)num_envs * NM_OCT));
@@ -567,7 +547,7 @@ static int batch_create_impl(const nm_model* m, int num_envs, int device, uint64
   NmKernelArgs& a = b->args;
   a.hull_hint = b->d_hint;
   a.ep_means = bufs->ep_means; a.time_outs_latched = bufs->time_outs_latched;
-  a.model = b->d_model; a.cfg = b->d_cfg; a.hull_vert = b->d_hull; a.hull_nbr_adr = b->d_nbr_adr; a.hull_nbr = b->d_nbr; a.hull_edge = b->d_edge;
+  a.model = b->d_model; a.cfg = b->d_cfg; a.hull_vert = b->d_hull;
   {
     // compact adjacency (16-bit ids and offsets) for the support-vertex walk.  NM_HULL_SMEM=1 makes every CTA stage the tables
     // (52 KB for the hexapod) in shared memory: measured (round 2, gpurun_out/r02_qb17.log, r02_phase8*.log) the walk itself
@@ -603,7 +583,7 @@ static int batch_create_impl(const nm_model* m, int num_envs, int device, uint64
 
 extern "C" void nm_batch_destroy(nm_batch* b) {
   if (!b) return;
-  cudaFree(b->d_model); cudaFree(b->d_cfg); cudaFree(b->d_hull); cudaFree(b->d_nbr_adr); cudaFree(b->d_nbr); cudaFree(b->d_edge); cudaFree(b->d_nbr16); cudaFree(b->d_nadr16); if (b->host_ev) cudaEventDestroy(b->host_ev); cudaFree(b->d_hint); cudaFree(b->d_acc);
+  cudaFree(b->d_model); cudaFree(b->d_cfg); cudaFree(b->d_hull); cudaFree(b->d_nbr16); cudaFree(b->d_nadr16); if (b->host_ev) cudaEventDestroy(b->host_ev); cudaFree(b->d_hint); cudaFree(b->d_acc);
   if (b->d_stage_actions) cudaFree(b->d_stage_actions);
   delete b;
 }

@@ -90,9 +90,6 @@ struct NmKernelArgs {
   const NmDevModel* model;
   const NmDevCfg* cfg;
   const float4* hull_vert;
-  const int* hull_nbr_adr;
-  const int* hull_nbr;
-  const float4* hull_edge;    // per directed hull edge: the neighbour's coordinates (xyz) and its geom-local vertex id (w, int bits)
   // compact adjacency for the support-vertex walk: 16-bit neighbour ids and list offsets (+ hull_vert); small enough
   // (52 KB for the hexapod) to be staged in shared memory by every CTA when hull_smem != 0
   const unsigned short* hull_nbr16;   // [hull_ne_pad]
