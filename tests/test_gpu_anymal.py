@@ -174,3 +174,40 @@ def test_ragged_batches_and_batch_independence(trio):
         m = len(outs[k][0])
         assert np.array_equal(outs[0][0][:m], outs[k][0]) and np.array_equal(outs[0][1][:m], outs[k][1]) and np.array_equal(outs[0][2][:m], outs[k][2])
     assert np.isfinite(outs[0][0]).all() and (outs[0][2][:, 0] > 16).any()              # some environments went through the second tier
+
+
+def test_standing_regime_lockstep(trio):
+    """The bench's regime (BASELINE configs[3]): robots on their four condim-6 feet, joint targets redrawn every 4 substeps from
+    U(-0.35, 0.35) rad -- feet stick, slide, roll and lift.  One substep at a time from shared fp32 states: constraint counts
+    identical, velocities within north_star's 1e-5 at the 99th percentile (relative to the robot's largest velocity component,
+    which is ~0.05 m/s for a standing robot: the absolute errors are ~1e-7)."""
+    cm, gm, om, _ = trio
+    n, rounds = 128, 160
+    rng = np.random.default_rng(3)
+    ob, gb = O.OracleBatch(om, n), GenBatch(gm, n, DEV)
+    ob.physics_step(np.zeros((n, 12)), 400, 8)                          # settle onto the feet
+    errs, mism, ncon_hist = [], 0, []
+    ctrl = np.zeros((n, 12), dtype=np.float32)
+    for it in range(rounds):
+        if it % 4 == 0:
+            ctrl = ((rng.random((n, 12)) - 0.5) * 0.7).astype(np.float32)
+        q, v, w = ob.get_state()
+        q32, v32, w32 = q.astype(np.float32), v.astype(np.float32), w.astype(np.float32)
+        ob.set_state(q32, v32, w32)
+        _push(gb, q32, v32, w32)
+        ob.physics_step(ctrl.astype(np.float64), 1, 8)
+        gb.physics_step(torch.from_numpy(ctrl).to(DEV), 1)
+        qo, vo, _ = ob.get_state()
+        vg = gb.qvel.cpu().numpy().astype(np.float64)
+        info = gb.info.cpu().numpy()
+        nefc = np.array([int(ob.get(i, "nefc")[0]) for i in range(n)])
+        same = info[:, 1] == nefc
+        mism += int((~same).sum())
+        errs.append(per_env_rel(vg, vo)[same])
+        ncon_hist.append(info[:, 0])
+    e = np.concatenate(errs)
+    nc = np.concatenate(ncon_hist)
+    print(f"\n[anymal standing regime] env-substeps {n * rounds}, contacts per robot mean {nc.mean():.2f} (min {nc.min()}, max {nc.max()}), count mismatches {mism} | "
+          f"CUDA median {np.median(e):.2e} p99 {np.percentile(e, 99):.2e} p99.9 {np.percentile(e, 99.9):.2e} max {e.max():.2e}")
+    assert nc.mean() > 3 and mism <= 0.002 * n * rounds
+    assert np.median(e) < 3e-6 and np.percentile(e, 99) < 1e-5 and e.max() < 1e-4
