@@ -143,7 +143,7 @@ __device__ __forceinline__ float g_impedance(const float* si, float pos) {      
 
 // ---------------------------------------------------------------------------------------------- per-environment shared memory
 template <int MC, int MR>
-struct EnvMemT {
+struct alignas(16) EnvMemT {
   // fp64 islands of the Newton solver: the iterate and the constraint residual jar = J qacc - aref.  On a sliding elliptic
   // contact the force is Dm * mu * (mu * jar_n - mu * |friction . jar_t|) with Dm ~ 4e6 for the feet (impratio 100): the
   // difference of two O(10) numbers has to be right to 1e-9 for a force good to 1e-3 N, which fp32 residuals miss by three
@@ -155,12 +155,12 @@ struct EnvMemT {
   float cdof[GM_MAXV][6];
   // Two phases share one block of memory (shared memory per environment decides how many warps an SM holds: 24.1 KB -> 19.1 KB
   // = 8 -> 12 warps): `k` is dead once the smooth dynamics are done (before collision), `s` is written from the constraint rows on
-  union {
+  alignas(16) union {
     struct { float xquat[GM_MAXB][4], xipos[GM_MAXB][3], ximat[GM_MAXB][9], cinert[GM_MAXB][10], crb[GM_MAXB][10], cdofdot[GM_MAXV][6],
                    cvel[GM_MAXB][6], cacc[GM_MAXB][6], cfrc[GM_MAXB][6]; } k;
     struct { float H[GM_MAXV][GM_MAXV], aref[MR], D[MR], R[MR], jv[MR], force[MR], Hd[MR], floss[MR]; } s;
   };
-  float M[GM_MAXV][GM_MAXV];
+  alignas(16) float M[GM_MAXV][GM_MAXV];
   float smooth[GM_MAXV], qaccs[GM_MAXV], qacc[GM_MAXV], grad[GM_MAXV], dir[GM_MAXV], Ma[GM_MAXV], vec[GM_MAXV];
   // contacts
   int ncon, nefc, nlim, overflow;
@@ -315,6 +315,7 @@ __device__ __noinline__ float g_rows(const GenModel& m, EnvMem& e, int mode, flo
       if (zone == 2) {
         e.ccoef[c] = cc;
         const int body = m.geom_body[e.cgeom[c]], nd = m.body_ndof[body];
+#pragma unroll 4
         for (int q = 0; q < nd; q++) {                     // b = sum_k friction_k u_k J_k, on the dofs of the body's chain
           const int i = m.body_dofs[body][q];
           float t = 0.f;
@@ -478,7 +479,7 @@ __global__ void __launch_bounds__(WARPS * 32) nm_generic_step_kernel(const GenAr
       }
       __syncwarp();
     }
-    for (int i = lane; i < nv * nv; i += 32) (&e.M[0][0])[(i / nv) * GM_MAXV + i % nv] = 0.f;
+    for (int i = lane; i < GM_MAXV * GM_MAXV / 4; i += 32) reinterpret_cast<float4*>(&e.M[0][0])[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     __syncwarp();
     for (int i = lane; i < nv; i += 32) {
       float buf[6];
@@ -698,8 +699,9 @@ __global__ void __launch_bounds__(WARPS * 32) nm_generic_step_kernel(const GenAr
         break;
       }
       // contact Jacobians: one (contact, dof) pair per lane trip, all rows of the contact at once
-      for (int idx = lane; idx < e.ncon * nv; idx += 32) {
-        const int c = idx / nv, i = idx - c * nv;
+      for (int idx = lane; idx < e.ncon * 32; idx += 32) {   // (contact c, dof lane): no division by nv; nv <= 24 < 32
+        const int c = idx >> 5, i = idx & 31;
+        if (i >= nv) continue;
         const int a = e.cadr[c], dim = e.cdim[c], b = m.geom_body[e.cgeom[c]];
         float lin[3] = {0.f, 0.f, 0.f}, ang[3] = {0.f, 0.f, 0.f};
         if ((m.body_dofmask[b] >> i) & 1) {
@@ -731,7 +733,8 @@ __global__ void __launch_bounds__(WARPS * 32) nm_generic_step_kernel(const GenAr
         } else e.cmu[c] = 0.f;
         for (int j = 0; j < dim; j++) {
           float vel = 0.f;
-          for (int i = 0; i < nv; i++) vel += e.J[a + j][i] * e.qvel[i];
+#pragma unroll
+          for (int i = 0; i < GM_MAXV; i++) if (i < nv) vel = fmaf(e.J[a + j][i], e.qvel[i], vel);
           e.s.R[a + j] = fmaxf(e.s.R[a + j], 1e-15f);
           e.s.D[a + j] = 1.f / e.s.R[a + j];
           e.s.aref[a + j] = -m.geom_B[g] * vel - (j == 0 ? m.geom_K[g] * imp * pos : 0.f);
@@ -756,7 +759,8 @@ __global__ void __launch_bounds__(WARPS * 32) nm_generic_step_kernel(const GenAr
           if (r < nsimple) t += (double)e.rsgn[r] * x[e.rdof[r]];
           else {
             const int body = m.geom_body[e.cgeom[e.crow[r]]], nd = m.body_ndof[body];
-            for (int q = 0; q < nd; q++) { const int i = m.body_dofs[body][q]; t += (double)e.J[r][i] * x[i]; }
+#pragma unroll
+            for (int q = 0; q < GM_MAXCHAIN; q++) if (q < nd) { const int i = m.body_dofs[body][q]; t += (double)e.J[r][i] * x[i]; }
           }
           e.jar[r] = t;
         }
@@ -768,7 +772,12 @@ __global__ void __launch_bounds__(WARPS * 32) nm_generic_step_kernel(const GenAr
         for (int i = lane; i < nv; i += 32) { e.vec[i] = q[i] - e.qaccs[i]; e.xd[i] = (double)q[i]; }
         __syncwarp();
         float cg = 0.f;
-        if (s == 0) for (int i = lane; i < nv; i += 32) { float t = 0.f; for (int k = 0; k < nv; k++) t += e.M[i][k] * e.vec[k]; cg += 0.5f * e.vec[i] * t; }
+        if (s == 0) for (int i = lane; i < nv; i += 32) {
+          float t = 0.f;
+#pragma unroll
+          for (int k = 0; k < GM_MAXV; k++) if (k < nv) t = fmaf(e.M[i][k], e.vec[k], t);
+          cg += 0.5f * e.vec[i] * t;
+        }
         residual(e.xd);
         __syncwarp();
         cost2[s] = g_warpsum(cg) + g_rows(m, e, 1, 0.f, lane);
@@ -791,13 +800,19 @@ __global__ void __launch_bounds__(WARPS * 32) nm_generic_step_kernel(const GenAr
         for (int i = lane; i < nv; i += 32) e.vec[i] = (float)(e.xd[i] - (double)e.qaccs[i]);
         residual(e.xd);
         __syncwarp();
-        for (int i = lane; i < nv; i += 32) { float t = 0.f; for (int k = 0; k < nv; k++) t += e.M[i][k] * e.vec[k]; e.Ma[i] = t; }
+        for (int i = lane; i < nv; i += 32) {
+          float t = 0.f;
+#pragma unroll
+          for (int k = 0; k < GM_MAXV; k++) if (k < nv) t = fmaf(e.M[i][k], e.vec[k], t);
+          e.Ma[i] = t;
+        }
         g_rows(m, e, 2, 0.f, lane);
         __syncwarp();
         float gn = 0.f, gref = 0.f;
         for (int i = lane; i < nv; i += 32) {
           float jf = 0.f;
-          for (int r = nsimple; r < ne; r++) jf += e.J[r][i] * e.s.force[r];
+#pragma unroll 8
+          for (int r = nsimple; r < ne; r++) jf = fmaf(e.J[r][i], e.s.force[r], jf);
           const int fr = m.dof_flossrow[i];
           if (fr >= 0) jf += e.s.force[fr];
           e.vec[i] = jf;
@@ -818,7 +833,7 @@ __global__ void __launch_bounds__(WARPS * 32) nm_generic_step_kernel(const GenAr
         // Hessian (lower triangle) H = M + sum_r Hd_r J_r J_r' + cone terms.  Simple rows add to the diagonal; a contact only
         // touches the dofs of its body's chain (9 of 18 for a leg): a bottom-zone contact adds its rows weighted by D, one on the
         // cone adds Dm mu^2 (J0 - b)(J0 - b)' + c (sum_k fri_k^2 J_k J_k' - b b').  One contact at a time, its chain pairs over the lanes.
-        for (int idx = lane; idx < nv * nv; idx += 32) { const int i = idx / nv, k = idx - i * nv; if (k <= i) e.s.H[i][k] = e.M[i][k]; }
+        for (int i = lane; i < GM_MAXV * GM_MAXV / 4; i += 32) reinterpret_cast<float4*>(&e.s.H[0][0])[i] = reinterpret_cast<const float4*>(&e.M[0][0])[i];
         __syncwarp();
         for (int i = lane; i < nv; i += 32) { const int fr = m.dof_flossrow[i]; if (fr >= 0) e.s.H[i][i] += e.s.Hd[fr]; }
         __syncwarp();
@@ -833,11 +848,15 @@ __global__ void __launch_bounds__(WARPS * 32) nm_generic_step_kernel(const GenAr
           for (int p = lane; p < nd * (nd + 1) / 2; p += 32) {
             const int i = m.body_dofs[body][g_tri_r[p]], k = m.body_dofs[body][g_tri_c[p]];
             float s = 0.f;
-            if (zone == 1) { for (int j = 0; j < dim; j++) s += e.s.D[a + j] * e.J[a + j][i] * e.J[a + j][k]; }
+            if (zone == 1) {
+#pragma unroll
+              for (int j = 0; j < 6; j++) if (j < dim) s += e.s.D[a + j] * e.J[a + j][i] * e.J[a + j][k];
+            }
             else {
               const float bi = e.cb[c][i], bk = e.cb[c][k];
               float t = 0.f;
-              for (int j = 1; j < dim; j++) t += fri[j - 1] * fri[j - 1] * e.J[a + j][i] * e.J[a + j][k];
+#pragma unroll
+              for (int j = 1; j < 6; j++) if (j < dim) t += fri[j - 1] * fri[j - 1] * e.J[a + j][i] * e.J[a + j][k];
               s = w0 * (e.J[a][i] - bi) * (e.J[a][k] - bk) + cc * (t - bi * bk);
             }
             e.s.H[i][k] += s;
@@ -863,12 +882,18 @@ __global__ void __launch_bounds__(WARPS * 32) nm_generic_step_kernel(const GenAr
           if (r < nsimple) t = e.rsgn[r] * e.dir[e.rdof[r]];
           else {
             const int body = m.geom_body[e.cgeom[e.crow[r]]], nd = m.body_ndof[body];
-            for (int q = 0; q < nd; q++) { const int i = m.body_dofs[body][q]; t += e.J[r][i] * e.dir[i]; }
+#pragma unroll
+            for (int q = 0; q < GM_MAXCHAIN; q++) if (q < nd) { const int i = m.body_dofs[body][q]; t = fmaf(e.J[r][i], e.dir[i], t); }
           }
           e.s.jv[r] = t;
         }
         float a1 = 0.f, a2 = 0.f;
-        for (int i = lane; i < nv; i += 32) { float t = 0.f; for (int k = 0; k < nv; k++) t += e.M[i][k] * e.dir[k]; a1 += e.dir[i] * e.Ma[i]; a2 += e.dir[i] * t; }
+        for (int i = lane; i < nv; i += 32) {
+          float t = 0.f;
+#pragma unroll
+          for (int k = 0; k < GM_MAXV; k++) if (k < nv) t = fmaf(e.M[i][k], e.dir[k], t);
+          a1 += e.dir[i] * e.Ma[i]; a2 += e.dir[i] * t;
+        }
         a1 = g_warpsum(a1); a2 = g_warpsum(a2);
         __syncwarp();
         auto dphi = [&](float alpha) -> float { return a1 + alpha * a2 - g_rows(m, e, 0, alpha, lane); };
@@ -913,7 +938,9 @@ __global__ void __launch_bounds__(WARPS * 32) nm_generic_step_kernel(const GenAr
       if (any_damp) {
         // (M + h D) a = qfrc_smooth + qfrc_constraint = M qacc at the solver's optimum  =>  a = qacc - h (M + h D)^-1 D qacc:
         // the correction is O(h), so its rounding does not matter, and no constraint force has to be formed
-        for (int idx = lane; idx < nv * nv; idx += 32) { const int i = idx / nv, k = idx - i * nv; e.s.H[i][k] = e.M[i][k] + (i == k ? h * m.dof_damping[i] : 0.f); }
+        for (int i = lane; i < GM_MAXV * GM_MAXV / 4; i += 32) reinterpret_cast<float4*>(&e.s.H[0][0])[i] = reinterpret_cast<const float4*>(&e.M[0][0])[i];
+        __syncwarp();
+        for (int i = lane; i < nv; i += 32) e.s.H[i][i] += h * m.dof_damping[i];
         for (int i = lane; i < nv; i += 32) e.vec[i] = m.dof_damping[i] * e.qacc[i];
         __syncwarp();
         g_solve_spd(e.s.H, e.vec, nv, lane);
