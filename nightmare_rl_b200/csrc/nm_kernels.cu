@@ -46,6 +46,23 @@
 #else
 #define PHASE_SYNC_C() PHASE_SYNC()
 #endif
+#ifdef NM_SKIP_SYNC_A
+#define PHASE_SYNC_A()
+#else
+#define PHASE_SYNC_A() PHASE_SYNC()
+#endif
+#ifdef NM_SKIP_SYNC_D
+#define PHASE_SYNC_D()
+#else
+// before the collision phase: kept for one-wave launches (87.1 vs 89.0 us at 4096 envs without it), dropped for the 256-thread
+// CTAs of large batches (+1.2 % at 131 072 envs, +1.6 % at 16 384; gpurun_out/r02_qb21.log)
+#define PHASE_SYNC_D() do { if (BLOCK <= 128) __syncthreads(); } while (0)
+#endif
+#ifdef NM_SKIP_SYNC_F
+#define PHASE_SYNC_F()
+#else
+#define PHASE_SYNC_F() PHASE_SYNC()
+#endif
 #ifndef NM_KEEP_SYNC_E
 #define PHASE_SYNC_E()       // measured (gpurun_out/r02_qb18.log): without this barrier +2.6 % at 131 072 envs, +3 % at 16 384, equal at 4096
 #else
@@ -918,7 +935,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) nm_step_kernel(const NmKernelArgs
 #pragma unroll 1
   for (int sub = 0; sub < A.nstep; sub++) {
     TSTAMP(1 + 10 * sub);
-    PHASE_SYNC();
+    PHASE_SYNC_A();
     TSTAMP(2 + 10 * sub);
     // ================================================================ P1 kinematics
     {
@@ -1061,7 +1078,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) nm_step_kernel(const NmKernelArgs
     solve_system(F, rb, rk, xsb, xsk);
 
     TSTAMP(5 + 10 * sub);
-    PHASE_SYNC();
+    PHASE_SYNC_D();
     if (sub == 0) TSTAMP(23);
     // ================================================================ P4 collision: convex hull vs plane
     // Support vertex by hill-climbing the hull graph (a local minimum of a linear function on a convex hull is the
@@ -1568,7 +1585,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) nm_step_kernel(const NmKernelArgs
       }
     }
     TSTAMP(8 + 10 * sub);
-    PHASE_SYNC();
+    PHASE_SYNC_F();
     TSTAMP(9 + 10 * sub);
     sens0 = fn_slot0; sens1 = fn_slot1;
     cvel_b = cvb;
