@@ -36,6 +36,7 @@ struct nm_model {
   double timestep;
   NmDevModel dev;                       // host copy of the constant table
   std::vector<float4> hull4;
+  std::vector<float> smap;       // support maps of the legs' hulls (nm_device.hpp, NM_SMAP_N)
   std::vector<int> nbr_adr, nbr;
   std::vector<std::string> names[6];    // body joint geom site actuator sensor
   std::vector<float> qpos0;
@@ -336,18 +337,71 @@ static int build_device_model(nm_model* m) {
         if (nn < 1e-30) break;
         for (int a = 0; a < 3; a++) u[a] = w[a] / nn;
       }
-      double tmin = 1e30, tmax = -1e30, rmax = 0;
-      for (int v = 0; v < G.hull_num; v++) {
-        double d[3] = {hv[3 * v] - mean[0], hv[3 * v + 1] - mean[1], hv[3 * v + 2] - mean[2]};
-        const double t = d[0] * u[0] + d[1] * u[1] + d[2] * u[2];
-        tmin = std::fmin(tmin, t); tmax = std::fmax(tmax, t);
-        const double pr[3] = {d[0] - t * u[0], d[1] - t * u[1], d[2] - t * u[2]};
-        rmax = std::fmax(rmax, std::sqrt(pr[0] * pr[0] + pr[1] * pr[1] + pr[2] * pr[2]));
+      // ... then tightened: the axis (direction and offset) is moved by a deterministic local search to minimise the largest
+      // distance of a vertex from it (the principal axis of the hexapod's tibia leaves 43 mm because of the bracket at its top;
+      // the best axis 30 mm), and the segment is shortened at both ends by what the spherical caps cover.  A tight capsule
+      // matters: walking robots keep adjacent tibias 20-40 mm apart, and every pair of overlapping capsules costs a
+      // support-function test over both hulls in the step kernel.
+      auto radius_of = [&](const double* ax, const double* c0) {
+        double r = 0;
+        for (int v = 0; v < G.hull_num; v++) {
+          const double d[3] = {hv[3 * v] - c0[0], hv[3 * v + 1] - c0[1], hv[3 * v + 2] - c0[2]};
+          const double t = d[0] * ax[0] + d[1] * ax[1] + d[2] * ax[2];
+          const double pr[3] = {d[0] - t * ax[0], d[1] - t * ax[1], d[2] - t * ax[2]};
+          r = std::fmax(r, pr[0] * pr[0] + pr[1] * pr[1] + pr[2] * pr[2]);
+        }
+        return std::sqrt(r);
+      };
+      {
+        double best = radius_of(u, mean);
+        unsigned long long rs = 0x9E3779B97F4A7C15ull + (unsigned long long)k;
+        auto rnd = [&]() { rs ^= rs << 13; rs ^= rs >> 7; rs ^= rs << 17; return (double)(rs >> 11) * (1.0 / 9007199254740992.0) * 2.0 - 1.0; };
+        double step_u = 0.05, step_c = 0.25 * best;
+        for (int it = 0; it < 6000; it++) {
+          double nu[3] = {u[0] + step_u * rnd(), u[1] + step_u * rnd(), u[2] + step_u * rnd()};
+          const double nn = std::sqrt(nu[0] * nu[0] + nu[1] * nu[1] + nu[2] * nu[2]);
+          for (int a = 0; a < 3; a++) nu[a] /= nn;
+          const double nc[3] = {mean[0] + step_c * rnd(), mean[1] + step_c * rnd(), mean[2] + step_c * rnd()};
+          const double r = radius_of(nu, nc);
+          if (r < best) { best = r; for (int a = 0; a < 3; a++) { u[a] = nu[a]; mean[a] = nc[a]; } }
+          if (it % 1000 == 999) { step_u *= 0.5; step_c *= 0.5; }
+        }
       }
+      double rmax = radius_of(u, mean) * 1.0001 + 1e-6;
+      double t0 = -1e30, t1 = 1e30, tlo = 1e30, thi = -1e30;           // segment [t0, t1]: every vertex within rmax of it
+      for (int v = 0; v < G.hull_num; v++) {
+        const double d[3] = {hv[3 * v] - mean[0], hv[3 * v + 1] - mean[1], hv[3 * v + 2] - mean[2]};
+        const double t = d[0] * u[0] + d[1] * u[1] + d[2] * u[2];
+        const double pr[3] = {d[0] - t * u[0], d[1] - t * u[1], d[2] - t * u[2]};
+        const double reach = std::sqrt(std::fmax(rmax * rmax - (pr[0] * pr[0] + pr[1] * pr[1] + pr[2] * pr[2]), 0.0));
+        t1 = std::fmin(t1, t + reach);        // the lower end may sit as high as this and still cover vertex v with its cap ...
+        t0 = std::fmax(t0, t - reach);        // ... and the upper end as low as this
+        tlo = std::fmin(tlo, t); thi = std::fmax(thi, t);
+      }
+      double tmin = std::fmin(t1, 0.5 * (tlo + thi)), tmax = std::fmax(t0, 0.5 * (tlo + thi));
       for (int a = 0; a < 3; a++) { G.cap_a[a] = (float)(mean[a] + tmin * u[a]); G.cap_b[a] = (float)(mean[a] + tmax * u[a]); }
-      G.cap_r = (float)(rmax * 1.0001 + 1e-6);
+      G.cap_r = (float)rmax;
       G.cap_il2 = (float)(1.0 / std::fmax((tmax - tmin) * (tmax - tmin), 1e-12));
       G.cap_len = (float)((tmax - tmin) * 1.0001);
+      {
+        // support map (nm_device.hpp, NM_SMAP_N): node values in double, rounded up by 2 um so that the fp32 interpolation in
+        // the kernel stays an upper bound
+        G.smap_adr = (int)m->smap.size();
+        m->smap.resize(m->smap.size() + NM_SMAP_FLOATS);
+        float* T = m->smap.data() + G.smap_adr;
+        for (int ax = 0; ax < 3; ax++)
+          for (int sg = 0; sg < 2; sg++)
+            for (int iv = 0; iv <= NM_SMAP_N; iv++)
+              for (int iu = 0; iu <= NM_SMAP_N; iu++) {
+                double cdir[3];
+                cdir[ax] = sg ? -1.0 : 1.0;
+                cdir[(ax + 1) % 3] = -1.0 + 2.0 * iu / NM_SMAP_N;
+                cdir[(ax + 2) % 3] = -1.0 + 2.0 * iv / NM_SMAP_N;
+                double h = -1e300;
+                for (int v = 0; v < G.hull_num; v++) h = std::fmax(h, cdir[0] * hv[3 * v] + cdir[1] * hv[3 * v + 1] + cdir[2] * hv[3 * v + 2]);
+                T[((2 * ax + sg) * (NM_SMAP_N + 1) + iv) * (NM_SMAP_N + 1) + iu] = (float)(h + 2e-6 + 1e-6 * std::fabs(h));
+              }
+      }
       const double mureg = G.mu / std::sqrt(impratio > 1e-15 ? impratio : 1.0);
       G.rfac_self = (float)(pyramid_rfac * mureg * mureg * (1.0 + (double)G.mu * G.mu) * body_invweight0[2 * geom_body[g]]);
     }
@@ -460,6 +514,7 @@ struct nm_batch {
   NmDevModel* d_model;
   NmDevCfg* d_cfg;
   float4* d_hull;
+  float* d_smap;
   unsigned short *d_nbr16, *d_nadr16;
   cudaEvent_t host_ev;   // nm_step_host waits for the step kernel's outputs, not for the extras latch launched behind it
   int* d_hint;
@@ -532,6 +587,8 @@ static int batch_create_impl(const nm_model* m, int num_envs, int device, uint64
   CUDA_OK(cudaMemcpy(b->d_cfg, &hc, sizeof(NmDevCfg), cudaMemcpyHostToDevice));
   CUDA_OK(cudaMalloc(&b->d_hull, sizeof(float4) * (m->hull4.size() + 1)));
   CUDA_OK(cudaMemcpy(b->d_hull, m->hull4.data(), sizeof(float4) * m->hull4.size(), cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMalloc(&b->d_smap, sizeof(float) * (m->smap.size() + 4)));
+  if (!m->smap.empty()) CUDA_OK(cudaMemcpy(b->d_smap, m->smap.data(), sizeof(float) * m->smap.size(), cudaMemcpyHostToDevice));
   // limits the packed support-vertex hint (9 bits vertex, 6 bits degree) and the 16-bit adjacency rely on
   for (int g = 0; g < NM_OCT; g++) {
     const NmGeom& G = m->dev.leg[g].geom;
@@ -547,7 +604,7 @@ static int batch_create_impl(const nm_model* m, int num_envs, int device, uint64
   NmKernelArgs& a = b->args;
   a.hull_hint = b->d_hint;
   a.ep_means = bufs->ep_means; a.time_outs_latched = bufs->time_outs_latched;
-  a.model = b->d_model; a.cfg = b->d_cfg; a.hull_vert = b->d_hull;
+  a.model = b->d_model; a.cfg = b->d_cfg; a.hull_vert = b->d_hull; a.hull_smap = b->d_smap;
   {
     // compact adjacency (16-bit ids and offsets) for the support-vertex walk.  NM_HULL_SMEM=1 makes every CTA stage the tables
     // (52 KB for the hexapod) in shared memory: measured (round 2, gpurun_out/r02_qb17.log, r02_phase8*.log) the walk itself
@@ -583,7 +640,7 @@ static int batch_create_impl(const nm_model* m, int num_envs, int device, uint64
 
 extern "C" void nm_batch_destroy(nm_batch* b) {
   if (!b) return;
-  cudaFree(b->d_model); cudaFree(b->d_cfg); cudaFree(b->d_hull); cudaFree(b->d_nbr16); cudaFree(b->d_nadr16); if (b->host_ev) cudaEventDestroy(b->host_ev); cudaFree(b->d_hint); cudaFree(b->d_acc);
+  cudaFree(b->d_model); cudaFree(b->d_cfg); cudaFree(b->d_hull); cudaFree(b->d_smap); cudaFree(b->d_nbr16); cudaFree(b->d_nadr16); if (b->host_ev) cudaEventDestroy(b->host_ev); cudaFree(b->d_hint); cudaFree(b->d_acc);
   if (b->d_stage_actions) cudaFree(b->d_stage_actions);
   delete b;
 }

@@ -656,6 +656,24 @@ __device__ __noinline__ bool mpr_penetration_oct(const float4* __restrict__ hv, 
     expand_portal(P, v4);
   }
 }
+// Upper bound of the support function max_v d.v of a hull from its support map (nm_device.hpp, NM_SMAP_N); d in the hull frame.
+__device__ __forceinline__ float smap_support(const float* __restrict__ T, V3 d) {
+  const float ax = fabsf(d.x), ay = fabsf(d.y), az = fabsf(d.z);
+  int f; float m, u, v;
+  if (ax >= ay && ax >= az) { f = 0; m = d.x; u = d.y; v = d.z; }
+  else if (ay >= az) { f = 2; m = d.y; u = d.z; v = d.x; }
+  else { f = 4; m = d.z; u = d.x; v = d.y; }
+  const float am = fmaxf(fabsf(m), 1e-30f), s = 1.f / am;
+  f += m < 0.f;
+  const float gu = fminf(fmaxf(fmaf(u, s, 1.f) * (0.5f * NM_SMAP_N), 0.f), (float)NM_SMAP_N);
+  const float gv = fminf(fmaxf(fmaf(v, s, 1.f) * (0.5f * NM_SMAP_N), 0.f), (float)NM_SMAP_N);
+  const int iu = min((int)gu, NM_SMAP_N - 1), iv = min((int)gv, NM_SMAP_N - 1);
+  const float fu = gu - (float)iu, fv = gv - (float)iv;
+  const float* p = T + (f * (NM_SMAP_N + 1) + iv) * (NM_SMAP_N + 1) + iu;
+  const float t00 = __ldg(p), t10 = __ldg(p + 1), t01 = __ldg(p + NM_SMAP_N + 1), t11 = __ldg(p + NM_SMAP_N + 2);
+  const float lo = fmaf(fu, t10 - t00, t00), hi = fmaf(fu, t11 - t01, t01);
+  return fmaf(fv, hi - lo, lo) * am;
+}
 // squared distance between two segments (bounding-capsule broad phase); ia / ie = 1 / squared lengths (model constants).
 // Approximate division: the caller compares against a threshold with 0.1 mm of slack.
 __device__ __forceinline__ float segseg_dist2(V3 p1, V3 d1, float ia, V3 p2, V3 d2, float ie) {
@@ -1210,14 +1228,25 @@ __global__ void __launch_bounds__(BLOCK, MINB) nm_step_kernel(const NmKernelArgs
 #endif
         unsigned oc = cand;
         oc |= __shfl_xor_sync(FULL, oc, 1); oc |= __shfl_xor_sync(FULL, oc, 2); oc |= __shfl_xor_sync(FULL, oc, 4);
-        // First step of MPR, here and on scalars only: the hulls are disjoint when they are separated along the line between
-        // their centres, h_i(dir) + h_j(-dir) <= 0 with h(d) = max over hull vertices of d.x (1/8 of the vertices per lane).
-        // That is how MPR itself answers almost every candidate (pairs that are close but do not touch), at a third of the
-        // cost of entering the cold path; only the pairs that survive go there.
+#ifdef NM_TIMING
+        int dbg_c0 = 0, dbg_c1 = 0;
+        const long long dbg_t0 = clock64();
+#endif
+        // First step of MPR, here and without touching a vertex: the hulls are disjoint when they are separated along the line
+        // between their centres, h_i(dir) + h_j(-dir) <= 0 with h(d) = max over hull vertices of d.x.  That is how MPR itself
+        // answers almost every candidate (pairs that are close but do not touch).  h comes from the hull's support map
+        // (NM_SMAP_N: an upper bound, four loads), so the test is conservative; the pairs it keeps go to MPR, whose own first
+        // step is the exact one.  Code size matters more than arithmetic here: one warp in ~40 enters per substep on a walking
+        // batch, always with cold instruction lines (the exact scan over both hulls' vertices that stood here cost 9.3 us per
+        // visit, `tools/phase_timing.py`, and a one-wave launch lasts as long as its slowest warp).
         if (oc != 0u) {
           const V3 cw = prel + mul(Xg, ld3(G.center));
           unsigned rem = oc;
+#ifdef NM_TIMING
+          dbg_c0 = __popc(oc);
+#endif
           oc = 0u;
+#pragma unroll 1
           while (rem != 0u) {
             const int idx = __ffs(rem) - 1;
             rem &= rem - 1u;
@@ -1230,20 +1259,21 @@ __global__ void __launch_bounds__(BLOCK, MINB) nm_step_kernel(const NmKernelArgs
             const V3 dir = normalized(cj - ci);
             const V3 dloc = mulT(Xg, l == j ? mk(-dir.x, -dir.y, -dir.z) : dir);   // the direction in this lane's hull frame
             const float off = dot_plain(prel, dir);
-            const V3 di = mk(__shfl_sync(omask, dloc.x, si), __shfl_sync(omask, dloc.y, si), __shfl_sync(omask, dloc.z, si));
-            const V3 dj = mk(__shfl_sync(omask, dloc.x, sj), __shfl_sync(omask, dloc.y, sj), __shfl_sync(omask, dloc.z, sj));
+            const float hme = (l == i || l == j) ? smap_support(A.hull_smap + G.smap_adr, dloc) : 0.f;
+            const float hi = __shfl_sync(omask, hme, si), hj = __shfl_sync(omask, hme, sj);
             const float oi = __shfl_sync(omask, off, si), oj = __shfl_sync(omask, off, sj);
-            const NmGeom &Gi = sm.leg[i].geom, &Gj = sm.leg[j].geom;
-            float hi = -CUDART_INF_F, hj = -CUDART_INF_F;
-            const float4* hvi = A.hull_vert + Gi.hull_adr;
-            const float4* hvj = A.hull_vert + Gj.hull_adr;
-            for (int v = l; v < Gi.hull_num; v += 8) { const float4 q = __ldg(hvi + v); hi = fmaxf(hi, di.x * q.x + di.y * q.y + di.z * q.z); }
-            for (int v = l; v < Gj.hull_num; v += 8) { const float4 q = __ldg(hvj + v); hj = fmaxf(hj, dj.x * q.x + dj.y * q.y + dj.z * q.z); }
-#pragma unroll
-            for (int o = 1; o < 8; o <<= 1) { hi = fmaxf(hi, __shfl_xor_sync(omask, hi, o)); hj = fmaxf(hj, __shfl_xor_sync(omask, hj, o)); }
-            if ((hi + oi) + (hj - oj) > -1e-6f) oc |= 1u << idx;                // not clearly separated along this axis: full MPR decides
+            if ((hi + oi) + (hj - oj) > -1e-6f) oc |= 1u << idx;                // not clearly separated along this axis: MPR decides
           }
+#ifdef NM_TIMING
+          dbg_c1 = __popc(oc);
+#endif
         }
+#ifdef NM_TIMING
+        const long long dbg_t1 = clock64();
+        if (sub == 0 && nm_timing_buf && l == 0)     // packed event counts: capsules overlap | survive the support-map test << 20 | handed to MPR << 40
+          atomicAdd((unsigned long long*)&nm_timing_buf[(size_t)(gtid >> 5) * 32 + 29],
+                    (unsigned long long)dbg_c0 | ((unsigned long long)dbg_c1 << 20) | ((unsigned long long)__popc(oc) << 40));
+#endif
         if (oc != 0u) {                             // (uniform within the octet)
           cand = oc;
           PairIn in;
@@ -1263,6 +1293,12 @@ __global__ void __launch_bounds__(BLOCK, MINB) nm_step_kernel(const NmKernelArgs
           npair = pair_contacts_cold(in, G, A.hull_vert, pose_s, pblk, cand, sm.mpr_tolerance, sm.mpr_iterations, l, omask);
         }
         __syncwarp();
+#ifdef NM_TIMING
+        if (sub == 0 && nm_timing_buf && (threadIdx.x & 31) == 0) {      // cycles of the candidate filter and of MPR + contact blocks
+          nm_timing_buf[(size_t)(gtid >> 5) * 32 + 30] = dbg_t1 - dbg_t0;
+          nm_timing_buf[(size_t)(gtid >> 5) * 32 + 31] = clock64() - dbg_t1;
+        }
+#endif
       }
     }
     int npair_max = max(npair, __shfl_xor_sync(FULL, npair, 8));

@@ -16,8 +16,16 @@ cfg = NightmareV3Config(); cfg.env.num_envs = N; cfg.viewer.render = cfg.viewer.
 env = NightmareV3Env(cfg, seed=1, device=dev); env.reset()
 env.episode_length_buf = torch.randint(0, 1250, (N,), device=dev)
 acts = torch.randn(8, N, 18, device=dev)
+GAIT = os.environ.get("NM_GAIT", "0") == "1"
+if GAIT:                                                     # the reference's scripted tripod gait instead of N(0,1) actions
+    from nightmare_rl_b200.envs.scripted_gait import ScriptedGait
+    g = ScriptedGait(os.path.join(ROOT, "tests", "golden", "nikengine_gait_targets.npz"), N, dev, phase_shift=3)
+    seq = [g.actions().contiguous() for _ in range(400)]
+    for i in range(330):
+        env._batch.step(seq[i], 10 + i)
+    acts = seq[330:]                                         # the gait goes on through the sampled steps
 for i in range(40):
-    env._batch.step(acts[i % 8], 10 + i)
+    env._batch.step(acts[i % 8 if not GAIT else i], 10 + i)
 nw = (N * 8 + 31) // 32
 buf = torch.zeros(nw + 8, 32, dtype=torch.int64, device=dev)
 _lib.lib.nm_debug_set_timing_buffer.argtypes = [ctypes.c_void_p]
@@ -27,7 +35,7 @@ names = {1: "prev tail", 2: "wait@top", 3: "P1+P2+P7 kin/RNE", 4: "wait+P3 CRBA"
 acc = {}
 for rep in range(10):
     buf.zero_()
-    env._batch.step(acts[rep % 8], 100 + rep)
+    env._batch.step(acts[rep % 8 if not GAIT else 40 + rep], 100 + rep)
     torch.cuda.synchronize()
     t = buf[:nw].cpu().numpy().astype(np.float64)
     t0 = t[:, 0].min()
@@ -53,11 +61,18 @@ for rep in range(10):
         add("sub0   walk rounds (max over the warp's hulls)", (np.median(t[:, 27]), t[:, 27].max()))
         add("sub0   max vertex degree at the support vertex", (np.median(t[:, 28]), t[:, 28].max()))
         add("sub0 P4b tibia pairs broad phase", (np.median(t[:, 26] - t[:, 25]), (t[:, 26] - t[:, 25]).max()))
+        pk = t[:, 29].astype(np.int64)
+        add("sub0   pair candidates per launch: capsules overlap / survive the support-map axis test", ((pk & 0xfffff).sum(), ((pk >> 20) & 0xfffff).sum()))
+        add("sub0   pairs per launch handed to MPR (sum, max per warp)", ((pk >> 40).sum(), (pk >> 40).max()))
+        add("sub0   candidate filter (support maps)", (np.median(t[:, 30][t[:, 30] > 0]) if (t[:, 30] > 0).any() else 0, t[:, 30].max()))
+        add("sub0   MPR + contact blocks", (np.median(t[:, 31][t[:, 31] > 0]) if (t[:, 31] > 0).any() else 0, t[:, 31].max()))
         add("sub0 after P4b -> stamp 6", (np.median(t[:, 6] - t[:, 26]), (t[:, 6] - t[:, 26]).max()))
 print(f"N={N} warps={nw}  (cycles @1.965 GHz; median over 10 steps of [median over warps, max over warps])")
 for k, v in acc.items():
     a = np.array(v)
-    if a.ndim == 1:
+    if "per launch" in k:                                      # event counters, not cycles
+        print(f"{k:50s} {np.mean(a[:, 0]):10.3f}  {np.mean(a[:, 1]):10.3f}")
+    elif a.ndim == 1:
         print(f"{k:50s} {np.median(a):10.0f} cyc  {np.median(a) / 1965:7.2f} us")
     else:
         print(f"{k:50s} {np.median(a[:, 0]):10.0f} cyc  {np.median(a[:, 0]) / 1965:7.2f} us   max-warp {np.median(a[:, 1]) / 1965:7.2f} us")
