@@ -836,6 +836,10 @@ enum { RW_ACTION_RATE = 0, RW_ANG_VEL_XY, RW_BASE_HEIGHT, RW_BODY_CONTACT_FORCES
 #define NM_LARGE_BLOCK 256
 #define NM_LARGE_MINB 1
 #endif
+#ifndef NM_MID_BLOCK
+#define NM_MID_BLOCK 224      // 7 warps per SM: for batches whose last round of 8-warp CTAs would leave most SMs idle (nm_launch_step)
+#define NM_MID_MINB 1
+#endif
 #ifndef NM_SMALL_BLOCK
 #define NM_SMALL_BLOCK 128
 #define NM_SMALL_MINB 2
@@ -2031,10 +2035,20 @@ void nm_launch_step(const NmKernelArgs& a, bool env_mode, void* stream) {
   // with the hull tables staged in shared memory a CTA needs ~120 KB: one 256-thread CTA per SM for every batch size (measured
   // equal to two 128-thread CTAs at one-wave sizes without the staging)
   const bool one_wave = threads <= sms * 8 * 32 && !a.hull_smem;
+  // Beyond one wave the CTAs run in rounds of one per SM.  A round of 7-warp CTAs is ~5 % shorter than a round of 8-warp CTAs
+  // (56.5 vs 59.5 us per round at 131 072 envs, `gpurun_out/r02_qb22.log`), so when both shapes need the same number of rounds
+  // the smaller one wins (16 384 envs: 3.46 rounds of 8 warps or 3.96 of 7: 261.2 -> 253.9 us); otherwise 8 warps per SM.
+  // Same arithmetic in every instantiation (tests/test_gpu_physics.py::test_large_batch_kernel_variant: bit-identical).
+  static const bool mid_ok = getenv("NM_NO_MID_BLOCK") == nullptr;
+  const int rounds8 = ((threads + NM_LARGE_BLOCK - 1) / NM_LARGE_BLOCK + sms - 1) / sms;
+  const int rounds7 = ((threads + NM_MID_BLOCK - 1) / NM_MID_BLOCK + sms - 1) / sms;
+  const bool mid = mid_ok && !one_wave && rounds7 == rounds8;
   static bool attr_set[64] = {false};                      // the large-block build needs > 48 KB of shared memory in total
   if (!attr_set[dev & 63]) {
     cudaFuncSetAttribute(nm_step_kernel<true, NM_LARGE_BLOCK, NM_LARGE_MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(step_dyn_smem(NM_LARGE_BLOCK) + NM_HULL_SMEM_MAX));
     cudaFuncSetAttribute(nm_step_kernel<false, NM_LARGE_BLOCK, NM_LARGE_MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(step_dyn_smem(NM_LARGE_BLOCK) + NM_HULL_SMEM_MAX));
+    cudaFuncSetAttribute(nm_step_kernel<true, NM_MID_BLOCK, NM_MID_MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(step_dyn_smem(NM_MID_BLOCK) + NM_HULL_SMEM_MAX));
+    cudaFuncSetAttribute(nm_step_kernel<false, NM_MID_BLOCK, NM_MID_MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(step_dyn_smem(NM_MID_BLOCK) + NM_HULL_SMEM_MAX));
     cudaFuncSetAttribute(nm_step_kernel<true, NM_SMALL_BLOCK, NM_SMALL_MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)step_dyn_smem(NM_SMALL_BLOCK));
     cudaFuncSetAttribute(nm_step_kernel<false, NM_SMALL_BLOCK, NM_SMALL_MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)step_dyn_smem(NM_SMALL_BLOCK));
     attr_set[dev & 63] = true;
@@ -2043,6 +2057,11 @@ void nm_launch_step(const NmKernelArgs& a, bool env_mode, void* stream) {
     const int blocks = (threads + NM_SMALL_BLOCK - 1) / NM_SMALL_BLOCK;
     if (env_mode) nm_step_kernel<true, NM_SMALL_BLOCK, NM_SMALL_MINB><<<blocks, NM_SMALL_BLOCK, step_dyn_smem(NM_SMALL_BLOCK), st>>>(a);
     else nm_step_kernel<false, NM_SMALL_BLOCK, NM_SMALL_MINB><<<blocks, NM_SMALL_BLOCK, step_dyn_smem(NM_SMALL_BLOCK), st>>>(a);
+  } else if (mid) {
+    const int blocks = (threads + NM_MID_BLOCK - 1) / NM_MID_BLOCK;
+    const size_t smem = step_dyn_smem(NM_MID_BLOCK) + hull_smem_bytes(a);
+    if (env_mode) nm_step_kernel<true, NM_MID_BLOCK, NM_MID_MINB><<<blocks, NM_MID_BLOCK, smem, st>>>(a);
+    else nm_step_kernel<false, NM_MID_BLOCK, NM_MID_MINB><<<blocks, NM_MID_BLOCK, smem, st>>>(a);
   } else {
     const int blocks = (threads + NM_LARGE_BLOCK - 1) / NM_LARGE_BLOCK;
     const size_t smem = step_dyn_smem(NM_LARGE_BLOCK) + hull_smem_bytes(a);

@@ -530,8 +530,9 @@ def test_divergence_guard_resets_env():
 
 
 def test_large_batch_kernel_variant():
-    """Batches beyond one wave (> 8 warps/SM) run the <256 threads, 128 registers> instantiation of the step kernel.
-    It must (i) agree with the oracle like the one-wave build and (ii) give bit-identical results for the same envs."""
+    """Batches beyond one wave (> 8 warps/SM) run the <224 threads> or the <256 threads> instantiation of the step kernel
+    (nm_launch_step picks by the number of rounds: 6144 envs -> 224, 9472 envs -> 256 on 148 SMs).  Each must (i) agree with the
+    oracle like the one-wave build and (ii) give bit-identical results for the same envs."""
     G = _common()
     cm, dm, om = G.models()
     rng = np.random.default_rng(11)
@@ -542,18 +543,26 @@ def test_large_batch_kernel_variant():
     qpos[:, 3:7] += rng.normal(size=(n_big, 4)) * 0.1
     qpos[:, 3:7] /= np.linalg.norm(qpos[:, 3:7], axis=1, keepdims=True)
     ctrl = rng.uniform(-8, 8, (n_big, 18)).astype(np.float32)
+    n_huge = 9472
     big = G.Batch(dm, n_big, G.DEV)
     small = G.Batch(dm, n_small, G.DEV)
+    huge = G.Batch(dm, n_huge, G.DEV)
     z = np.zeros((n_big, 24))
     G.push_state(big, qpos, z, z)
     G.push_state(small, qpos[:n_small], z[:n_small], z[:n_small])
+    reps = -(-n_huge // n_big)
+    qh, ch = np.tile(qpos, (reps, 1))[:n_huge], np.tile(ctrl, (reps, 1))[:n_huge]
+    G.push_state(huge, qh, np.zeros((n_huge, 24)), np.zeros((n_huge, 24)))
     for _ in range(12):
         big.physics_step(torch.from_numpy(ctrl), 2)
         small.physics_step(torch.from_numpy(ctrl[:n_small]), 2)
+        huge.physics_step(torch.from_numpy(ch), 2)
     torch.cuda.synchronize()
-    for a, b in zip(G.gpu_state(big), G.gpu_state(small)):
-        assert np.array_equal(a[:n_small], b)                       # same arithmetic in both instantiations
+    for a, b, c in zip(G.gpu_state(big), G.gpu_state(small), G.gpu_state(huge)):
+        assert np.array_equal(a[:n_small], b)                       # same arithmetic in all three instantiations
+        assert np.array_equal(a, c[:n_big])
     assert np.array_equal(big.sensordata.cpu().numpy()[:n_small], small.sensordata.cpu().numpy())
+    assert np.array_equal(big.sensordata.cpu().numpy(), huge.sensordata.cpu().numpy()[:n_big])
     # one-step parity of the large build against the oracle, from the settled states
     q, v, w = G.gpu_state(big)
     ob = G.O.OracleBatch(om, n_big)
