@@ -56,7 +56,10 @@
 #else
 // before the collision phase: kept for one-wave launches (87.1 vs 89.0 us at 4096 envs without it), dropped for the 256-thread
 // CTAs of large batches (+1.2 % at 131 072 envs, +1.6 % at 16 384; gpurun_out/r02_qb21.log)
-#define PHASE_SYNC_D() do { if (BLOCK <= 128) __syncthreads(); } while (0)
+#ifndef NM_SYNC_D_MAX
+#define NM_SYNC_D_MAX 128
+#endif
+#define PHASE_SYNC_D() do { if (BLOCK <= NM_SYNC_D_MAX) __syncthreads(); } while (0)
 #endif
 #ifdef NM_SKIP_SYNC_F
 #define PHASE_SYNC_F()
@@ -2042,7 +2045,12 @@ void nm_launch_step(const NmKernelArgs& a, bool env_mode, void* stream) {
   static const bool mid_ok = getenv("NM_NO_MID_BLOCK") == nullptr;
   const int rounds8 = ((threads + NM_LARGE_BLOCK - 1) / NM_LARGE_BLOCK + sms - 1) / sms;
   const int rounds7 = ((threads + NM_MID_BLOCK - 1) / NM_MID_BLOCK + sms - 1) / sms;
-  const bool mid = mid_ok && !one_wave && rounds7 == rounds8;
+  // One-wave batches get one CTA per SM sized to the warps an SM has to take anyway (4096 envs on 148 SMs: 6.9 warps per SM ->
+  // 147 CTAs of 7 warps instead of 256 CTAs of 4, two of them on 108 of the SMs: 87.1 -> 83.0 us, `gpurun_out/r02_qb25.log`);
+  // up to 4 warps per SM the small shape stays.
+  const int warps_per_sm = ((threads + 31) / 32 + sms - 1) / sms;
+  const bool mid = mid_ok && (one_wave ? (warps_per_sm > 4 && warps_per_sm <= NM_MID_BLOCK / 32) : rounds7 == rounds8);
+  const bool small = one_wave && warps_per_sm <= 4;
   static bool attr_set[64] = {false};                      // the large-block build needs > 48 KB of shared memory in total
   if (!attr_set[dev & 63]) {
     cudaFuncSetAttribute(nm_step_kernel<true, NM_LARGE_BLOCK, NM_LARGE_MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(step_dyn_smem(NM_LARGE_BLOCK) + NM_HULL_SMEM_MAX));
@@ -2053,7 +2061,7 @@ void nm_launch_step(const NmKernelArgs& a, bool env_mode, void* stream) {
     cudaFuncSetAttribute(nm_step_kernel<false, NM_SMALL_BLOCK, NM_SMALL_MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)step_dyn_smem(NM_SMALL_BLOCK));
     attr_set[dev & 63] = true;
   }
-  if (one_wave) {
+  if (small || (one_wave && !mid_ok)) {
     const int blocks = (threads + NM_SMALL_BLOCK - 1) / NM_SMALL_BLOCK;
     if (env_mode) nm_step_kernel<true, NM_SMALL_BLOCK, NM_SMALL_MINB><<<blocks, NM_SMALL_BLOCK, step_dyn_smem(NM_SMALL_BLOCK), st>>>(a);
     else nm_step_kernel<false, NM_SMALL_BLOCK, NM_SMALL_MINB><<<blocks, NM_SMALL_BLOCK, step_dyn_smem(NM_SMALL_BLOCK), st>>>(a);
