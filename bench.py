@@ -317,10 +317,34 @@ def bench_step(c, args):
             sweep.append({"envs": En, "ms_per_step": ms, "env_steps_per_s": En / (ms * 1e-3)})
             del e2, acts
             torch.cuda.empty_cache()
+    # ---- the same step on a walking population (the reference's scripted tripod gait, phase-shifted per env): what a trained
+    # policy's rollouts look like -- six feet in contact, adjacent tibias close enough to enter the pair broad phase
+    walking = None
+    if world == 1 and not args.no_sweep:
+        from nightmare_rl_b200.envs.scripted_gait import ScriptedGait
+        e3, _ = _make_env(E, 0, dev)
+        gait = ScriptedGait(os.path.join(ROOT, "tests", "golden", "nikengine_gait_targets.npz"), E, dev, phase_shift=3)
+        settle, Kw = 330, 50
+        seq = [gait.actions().contiguous() for _ in range(settle + Kw)]
+        for i in range(settle):
+            e3._batch.step(seq[i], 100 + i)
+        torch.cuda.synchronize()
+        evw = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(Kw)]
+        for i in range(Kw):
+            flush.zero_()
+            evw[i][0].record()
+            e3._batch.step(seq[settle + i], 1000 + i)
+            evw[i][1].record()
+        torch.cuda.synchronize()
+        msw = sum(a.elapsed_time(b) for a, b in evw) / Kw
+        walking = {"workload": "same batch, actions from the reference's scripted tripod gait (tests/golden/nikengine_gait_targets.npz), "
+                               "330 untimed steps, L2 flushed between timed steps", "envs": E, "steps": Kw, "ms_per_step": msw,
+                   "env_steps_per_s": E / (msw * 1e-3)}
+        del e3, seq
     del flush
     torch.cuda.empty_cache()
     srt = sorted(step_ms)
-    return dict(value=value, total_ms=total_ms, kern_ms=sum(step_ms) / K, clocks=clocks, launches=int(launches), e2e_val=e2e_val, Ke=Ke,
+    return dict(walking=walking, value=value, total_ms=total_ms, kern_ms=sum(step_ms) / K, clocks=clocks, launches=int(launches), e2e_val=e2e_val, Ke=Ke,
                 sweep=sweep, E=E, K=K, W=W, step_ms_stats={"min": srt[0], "median": srt[len(srt) // 2], "max": srt[-1]})
 
 
@@ -597,6 +621,8 @@ def run_ours(args):
             "cpu_baseline": {"value": cpu_val, "unit": UNIT, "cores": cores, "kind": "port",
                              "sample": f"{E} envs x {cpu_steps} env-steps after {PREROLL_STEPS} pre-roll steps, fp64 C restatement (oracle/), {cores} pthreads"},
         }
+        if st.get("walking") is not None:
+            line["walking"] = st["walking"]
         if st["sweep"] is not None:
             line["sweep"] = {"note": "same step at larger batches on 1 GPU, back-to-back launches, no L2 flush", "points": st["sweep"]}
         line.update(extras)
