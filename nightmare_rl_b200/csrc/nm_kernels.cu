@@ -860,6 +860,42 @@ __global__ void __launch_bounds__(BLOCK, MINB) nm_step_kernel(const NmKernelArgs
   PairBlk* const pblk = reinterpret_cast<PairBlk*>(dyn_smem + sizeof(HullPose) * 6 * (BLOCK / NM_OCT)) + (threadIdx.x >> 3) * NM_MAXPAIR;
   // bounding capsules of the six leg hulls (hot): start point and direction, one float4 pair per leg
   float4* const cap_s = reinterpret_cast<float4*>(dyn_smem + (sizeof(HullPose) * 6 + sizeof(PairBlk) * NM_MAXPAIR) * (BLOCK / NM_OCT)) + (threadIdx.x >> 3) * 12;
+  const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int env_raw = gtid >> 3;
+  const bool valid = env_raw < A.num_envs;
+  const int env = valid ? env_raw : A.num_envs - 1;
+  const int l = threadIdx.x & 7;                 // lane inside the octet
+  const int lane = threadIdx.x & 31;
+  const int obase = lane & 24;                   // first warp lane of this octet
+  // ------------------------------------------------------------------ load state (registers for the whole step)
+  // Issued BEFORE the constant tables are copied to shared memory: with the L2 flushed both are DRAM round trips, and the
+  // state rows do not depend on the tables (a leg lane's dof offset is 3 l whatever the model says; lanes that turn out not
+  // to be legs discard what they read).
+  const float* qp = A.qpos + (size_t)env * 25;
+  const float* qv = A.qvel + (size_t)env * 24;
+  const float* qw = A.warm + (size_t)env * 24;
+  V3 p = ld3(qp);
+  float q0 = qp[3], q1 = qp[4], q2 = qp[5], q3 = qp[6];
+  V3 vlin = ld3(qv), wloc = ld3(qv + 3);
+  float awb[6], awk[3], th[3], thd[3], ctrl[3];
+#pragma unroll
+  for (int i = 0; i < 6; i++) awb[i] = qw[i];
+  const int jo6 = l < 6 ? 3 * l : 0;
+#pragma unroll
+  for (int j = 0; j < 3; j++) { th[j] = qp[7 + jo6 + j]; thd[j] = qv[6 + jo6 + j]; awk[j] = qw[6 + jo6 + j]; }
+  float in0[3], in1[3], in2[3], in3[3];          // env mode: previous actions, new actions, previous dof velocities, carried dof positions
+#pragma unroll
+  for (int j = 0; j < 3; j++) {
+    if (ENV) {
+      in0[j] = A.actions[(size_t)env * 18 + jo6 + j];
+      in1[j] = A.in_actions[(size_t)env * A.act_stride + jo6 + j];
+      in2[j] = A.dof_vel[(size_t)env * 18 + jo6 + j];
+      in3[j] = A.dof_pos[(size_t)env * 18 + jo6 + j];
+    } else {
+      in0[j] = A.in_ctrl[(size_t)env * 18 + jo6 + j];
+      in1[j] = in2[j] = in3[j] = 0.f;
+    }
+  }
   {
     static_assert(sizeof(NmDevModel) % 16 == 0 && sizeof(NmDevCfg) % 16 == 0, "constant tables are copied as int4");
     const int4* src = reinterpret_cast<const int4*>(A.model);
@@ -891,36 +927,19 @@ __global__ void __launch_bounds__(BLOCK, MINB) nm_step_kernel(const NmKernelArgs
   }
   __syncthreads();
 
-  const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
   TSTAMP(0);
-  const int env_raw = gtid >> 3;
-  const bool valid = env_raw < A.num_envs;
-  const int env = valid ? env_raw : A.num_envs - 1;
-  const int l = threadIdx.x & 7;                 // lane inside the octet
-  const int lane = threadIdx.x & 31;
-  const int obase = lane & 24;                   // first warp lane of this octet
   const NmLeg& L = sm.leg[l];
   const NmGeom& G = L.geom;
   const float isleg = L.isleg;
   const bool leg = l < sm.nleg;
   const float h = sm.timestep;
 
-  // ------------------------------------------------------------------ load state (registers for the whole step)
-  const float* qp = A.qpos + (size_t)env * 25;
-  const float* qv = A.qvel + (size_t)env * 24;
-  const float* qw = A.warm + (size_t)env * 24;
-  V3 p = ld3(qp);
-  float q0 = qp[3], q1 = qp[4], q2 = qp[5], q3 = qp[6];
-  V3 vlin = ld3(qv), wloc = ld3(qv + 3);
-  float awb[6], awk[3], th[3], thd[3], ctrl[3];
-#pragma unroll
-  for (int i = 0; i < 6; i++) awb[i] = qw[i];
   const int jo = leg ? 3 * l : 0;
 #pragma unroll
   for (int j = 0; j < 3; j++) {
-    th[j] = leg ? qp[7 + jo + j] : 0.f;
-    thd[j] = leg ? qv[6 + jo + j] : 0.f;
-    awk[j] = leg ? qw[6 + jo + j] : 0.f;
+    th[j] = leg ? th[j] : 0.f;
+    thd[j] = leg ? thd[j] : 0.f;
+    awk[j] = leg ? awk[j] : 0.f;
   }
 
   // ------------------------------------------------------------------ E1/E3: actions -> ctrl   (env.py:152-188)
@@ -929,17 +948,17 @@ __global__ void __launch_bounds__(BLOCK, MINB) nm_step_kernel(const NmKernelArgs
 #pragma unroll
     for (int j = 0; j < 3; j++) {
       if (leg) {
-        prev_act[j] = A.actions[(size_t)env * 18 + jo + j];
-        float a = A.in_actions[(size_t)env * A.act_stride + jo + j] * scfg.action_scale;
+        prev_act[j] = in0[j];
+        float a = in1[j] * scfg.action_scale;
         act[j] = fminf(fmaxf(a, -scfg.clip_actions), scfg.clip_actions);
-        prev_dof_vel[j] = A.dof_vel[(size_t)env * 18 + jo + j];
-        float dpos = A.dof_pos[(size_t)env * 18 + jo + j];          // carried buffer, stale after a reset (quirk Q2)
+        prev_dof_vel[j] = in2[j];
+        float dpos = in3[j];                                        // carried buffer, stale after a reset (quirk Q2)
         ctrl[j] = ((act[j] - scfg.default_pos[jo + j]) - dpos) * scfg.p_gain;
       } else ctrl[j] = 0.f;
     }
   } else {
 #pragma unroll
-    for (int j = 0; j < 3; j++) ctrl[j] = leg ? A.in_ctrl[(size_t)env * 18 + jo + j] : 0.f;
+    for (int j = 0; j < 3; j++) ctrl[j] = leg ? in0[j] : 0.f;
   }
 
   // outputs of the LAST substep's forward pass that the env layer reads (stale by one substep, quirk Q4)
