@@ -75,9 +75,16 @@ def _profile_numbers():
     cyc = num("sm__cycles_elapsed.max")
     out = {"file": os.path.relpath(best, ROOT), "envs": int(grid * block / 8) if grid and block else None,
            "dram_bytes": (rd + wr) if rd is not None and wr is not None else None, "executed_flops_per_env_step": None}
+    out["grid"], out["envs_per_cta"] = (int(grid), int(block) // 8) if grid and block else (None, None)
     if None not in (ffma, fadd, fmul, cyc) and out["envs"]:
-        out["executed_flops_per_env_step"] = (2 * ffma + fadd + fmul) * cyc / out["envs"]
+        out["executed_flops_total"] = (2 * ffma + fadd + fmul) * cyc
+        out["executed_flops_per_env_step"] = out["executed_flops_total"] / out["envs"]
     return out
+
+
+def _profile_matches(prof, E):
+    """the captured launch is this batch size: the same number of CTAs (the last CTA may be partly filled)"""
+    return bool(prof.get("grid")) and prof["grid"] == -(-E // prof["envs_per_cta"])
 
 
 def _config(E, world, workload=None):
@@ -599,7 +606,9 @@ def run_ours(args):
         cores = os.cpu_count() or 1
         cpu_steps = 600                                   # ~10 s of CPU work on 16 cores
         cpu_val, _ = cpu_env_steps_per_s(E, cpu_steps, 2, cores)
-        traffic = prof.get("dram_bytes") if prof.get("envs") == E else None
+        traffic = prof.get("dram_bytes") if _profile_matches(prof, E) else None
+        if _profile_matches(prof, E) and prof.get("executed_flops_total"):
+            prof["executed_flops_per_env_step"] = prof["executed_flops_total"] / E
         line = {
             "metric": METRIC, "value": st["value"], "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": st["total_ms"] / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
