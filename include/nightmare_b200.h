@@ -105,6 +105,12 @@ double nm_model_timestep(const nm_model*);
 int  nm_name2id(const nm_model*, int objtype, const char* name);
 /* ≙ model.qpos0                                            envs/nightmare_v3_env.py:349 */
 int  nm_model_qpos0(const nm_model*, float* out, int cap);
+/* Test access to the support map of leg `leg`'s collision hull (the conservative first stage of the tibia-tibia narrow phase that
+ * replaces mj_collision's convex-convex broad phase for models/nightmare_v3/mjmodel.xml:47): copies up to `cap` floats of the
+ * table the step kernel reads -- 6 cube faces x (n+1) x (n+1) nodes, node value >= max over hull vertices of c.v at the cube
+ * point c -- and up to `vcap` xyz triples of the hull's vertices (body frame).  Returns the grid size n (0: the leg has no
+ * hull), *nvert = number of hull vertices.  Host only, no GPU needed. */
+int  nm_model_support_map(const nm_model*, int leg, float* table, int cap, float* verts, int vcap, int* nvert);
 
 /* ≙ [mj.MjData(model) for _ in range(num_envs)]             envs/nightmare_v3_env.py:38 */
 int  nm_batch_create(const nm_model*, int num_envs, int device, uint64_t seed, const nm_envcfg* cfg,

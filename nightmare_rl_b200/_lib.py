@@ -88,7 +88,7 @@ def _load() -> ctypes.CDLL:
 lib = _load()
 
 EXPORTS = ("nm_last_error", "nm_model_load", "nm_model_from_buffer", "nm_model_destroy", "nm_model_size", "nm_model_timestep",
-           "nm_name2id", "nm_model_qpos0", "nm_batch_create", "nm_batch_destroy", "nm_batch_set_env_offset",
+           "nm_name2id", "nm_model_qpos0", "nm_model_support_map", "nm_batch_create", "nm_batch_destroy", "nm_batch_set_env_offset",
            "nm_batch_set_domain_randomization", "nm_batch_set_recorder", "nm_step",
            "nm_physics_step", "nm_reset_idx", "nm_step_host", "nm_batch_launches", "nm_measure_fp32_peak",
            "nm_policy_create", "nm_policy_destroy", "nm_policy_param_count", "nm_policy_load_weights", "nm_policy_act",

@@ -506,6 +506,17 @@ extern "C" int nm_model_qpos0(const nm_model* m, float* out, int cap) {
   return m->nq;
 }
 
+extern "C" int nm_model_support_map(const nm_model* m, int leg, float* table, int cap, float* verts, int vcap, int* nvert) {
+  if (!m || leg < 0 || leg >= m->nleg) return 0;
+  const NmGeom& G = m->dev.leg[leg].geom;
+  if (nvert) *nvert = 0;
+  if (!G.has || G.hull_num <= 0 || (size_t)G.smap_adr + NM_SMAP_FLOATS > m->smap.size()) return 0;
+  if (table) for (int i = 0; i < NM_SMAP_FLOATS && i < cap; i++) table[i] = m->smap[(size_t)G.smap_adr + i];
+  if (verts) for (int v = 0; v < G.hull_num && v < vcap; v++) { verts[3 * v] = m->hull4[G.hull_adr + v].x; verts[3 * v + 1] = m->hull4[G.hull_adr + v].y; verts[3 * v + 2] = m->hull4[G.hull_adr + v].z; }
+  if (nvert) *nvert = G.hull_num;
+  return NM_SMAP_N;
+}
+
 // ------------------------------------------------------------------------------------------------ batch
 struct nm_batch {
   const nm_model* model;

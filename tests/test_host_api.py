@@ -160,3 +160,55 @@ def test_second_model_through_compiler_and_loader():
         assert set(fresh.arrays) == set(cm.arrays)
         for k, v in fresh.arrays.items():
             assert np.array_equal(v, cm.arrays[k]), k
+
+
+def test_support_map_is_a_tight_upper_bound_of_the_hull_support():
+    """The tibia-tibia candidate filter of the step kernel (nm_kernels.cu, `smap_support`) may only reject a pair that MPR's own
+    first step (exact separating-axis test along the line between the hull centres, oracle/nm_oracle.c `mpr_penetration`) would
+    reject too: the interpolated support-map value must never be below max_v d.v, for any direction, on every leg hull of the
+    shipped model -- and it should be tight enough to be useful (mean slack well under a millimetre)."""
+    from nightmare_rl_b200 import _lib
+    h = ctypes.c_void_p()
+    assert _lib.lib.nm_model_load(NMB.encode(), ctypes.byref(h)) == 0
+    fn = _lib.lib.nm_model_support_map
+    fn.restype = ctypes.c_int
+    fn.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_int)]
+    rng = np.random.default_rng(5)
+    D = rng.normal(size=(40000, 3)).astype(np.float32)
+    D[:6] = np.vstack([np.eye(3), -np.eye(3)])                     # face centres
+    D[6:14] = np.array([[sx, sy, sz] for sx in (-1, 1) for sy in (-1, 1) for sz in (-1, 1)])      # cube corners
+    D[14:20] = [[1, 1, 0], [1, 0, 1], [0, 1, 1], [-1, 1, 0], [1, 0, -1], [0, -1, 1]]               # face edges (ties of the face choice)
+    D /= np.linalg.norm(D, axis=1, keepdims=True)
+    assert fn(h, 6, None, 0, None, 0, None) == 0                   # lane 6 is the base hull: no map
+    for leg in range(6):
+        nv = ctypes.c_int(0)
+        n = fn(h, leg, None, 0, None, 0, ctypes.byref(nv))
+        assert n == 16 and 100 < nv.value < 512
+        T = np.zeros(6 * (n + 1) * (n + 1), dtype=np.float32)
+        V = np.zeros((nv.value, 3), dtype=np.float32)
+        assert fn(h, leg, T.ctypes.data, T.size, V.ctypes.data, nv.value, ctypes.byref(nv)) == n
+        T = T.reshape(6, n + 1, n + 1)
+        exact = (D.astype(np.float64) @ V.astype(np.float64).T).max(axis=1)
+        # the kernel's lookup, in fp32 like the kernel
+        a = np.abs(D)
+        f0 = (a[:, 0] >= a[:, 1]) & (a[:, 0] >= a[:, 2])
+        f1 = ~f0 & (a[:, 1] >= a[:, 2])
+        ax = np.where(f0, 0, np.where(f1, 1, 2))
+        idx = np.arange(len(D))
+        m = D[idx, ax]
+        u, v = D[idx, (ax + 1) % 3], D[idx, (ax + 2) % 3]
+        am = np.abs(m)
+        s = (np.float32(1.0) / am).astype(np.float32)
+        face = 2 * ax + (m < 0)
+        gu = np.clip((u * s + np.float32(1)) * np.float32(0.5 * n), 0, n).astype(np.float32)
+        gv = np.clip((v * s + np.float32(1)) * np.float32(0.5 * n), 0, n).astype(np.float32)
+        iu, iv = np.minimum(gu.astype(np.int32), n - 1), np.minimum(gv.astype(np.int32), n - 1)
+        fu, fv = gu - iu, gv - iv
+        t00, t10, t01, t11 = T[face, iv, iu], T[face, iv, iu + 1], T[face, iv + 1, iu], T[face, iv + 1, iu + 1]
+        lo = (fu * (t10 - t00) + t00).astype(np.float32)
+        hi = (fu * (t11 - t01) + t01).astype(np.float32)
+        bound = ((fv * (hi - lo) + lo) * am).astype(np.float32)
+        slack = bound.astype(np.float64) - exact
+        assert slack.min() > 0.0, (leg, slack.min())              # never below the hull's support: conservative
+        assert slack.mean() < 5e-4 and slack.max() < 8e-3, (leg, slack.mean(), slack.max())
+    _lib.lib.nm_model_destroy(h)
