@@ -58,7 +58,12 @@ for rep in range(10):
         add("sub0 barrier before P4", (np.median(t[:, 23] - t[:, 5]), (t[:, 23] - t[:, 5]).max()))
         add("sub0 P4 hull-plane (walk + extra contacts)", (np.median(t[:, 25] - t[:, 23]), (t[:, 25] - t[:, 23]).max()))
         add("sub0   of which the support-vertex walk", (np.median(t[:, 24] - t[:, 23]), (t[:, 24] - t[:, 23]).max()))
-        add("sub0   walk rounds (max over the warp's hulls)", (np.median(t[:, 27]), t[:, 27].max()))
+        add("sub0   walk rounds per launch (max over the warp's hulls: median, max)", (np.median(t[:, 27]), t[:, 27].max()))
+        if rep == 0:
+            wt = (t[:, 24] - t[:, 23]) / 1965.0
+            for r_ in sorted(set(t[:, 27].astype(int).tolist())):
+                m_ = t[:, 27].astype(int) == r_
+                print(f"  walk rounds {r_:2d}: warps {m_.sum():4d}  walk median {np.median(wt[m_]):5.2f} us  max {wt[m_].max():5.2f} us")
         add("sub0   max vertex degree at the support vertex", (np.median(t[:, 28]), t[:, 28].max()))
         add("sub0 P4b tibia pairs broad phase", (np.median(t[:, 26] - t[:, 25]), (t[:, 26] - t[:, 25]).max()))
         pk = t[:, 29].astype(np.int64)
