@@ -1553,6 +1553,9 @@ __global__ void __launch_bounds__(BLOCK, MINB) nm_step_kernel(const NmKernelArgs
         for (int slot = 0; slot < nslot; slot++) {
           // lane of this octet that owns slot `slot` (none: broadcast from lane 0, u is unchanged there)
           const int owner = (owner_tab >> (4 * slot)) & 0xf;
+#ifdef NM_TIMING_VISIT
+          const long long tv0 = clock64();
+#endif
           if (active && nc > 0 && my_slot == slot) {
             if (kCache0) con_sweep(k0, u, wv, mu, in_noslip, improvement);   // first contact of the lane: cached in registers
             for (int c = kCache0 ? 1 : 0; c < nc; c++) {                      // further contacts (rare): through local memory
@@ -1562,8 +1565,19 @@ __global__ void __launch_bounds__(BLOCK, MINB) nm_step_kernel(const NmKernelArgs
               cb.f[c][0] = kc.f[0]; cb.f[c][1] = kc.f[1]; cb.f[c][2] = kc.f[2]; cb.f[c][3] = kc.f[3];
             }
           }
+#ifdef NM_TIMING_VISIT
+          const long long tv1 = clock64();
+#endif
 #pragma unroll
           for (int a = 0; a < 6; a++) u[a] = oct_bcast(u[a], obase | owner);
+#ifdef NM_TIMING_VISIT
+          if (sub == 0 && nm_timing_buf && (threadIdx.x & 31) == 0 && slot == 0 && (sweep == 0 || sweep == npgs)) {
+            // cycles of the visit alone and of the whole slot (visit + broadcast), first PGS sweep -> cols 29/30, first noslip sweep -> col 31 (slot)
+            const long long tv2 = clock64() + (long long)(__float_as_int(u[0]) & 0);      // (after the broadcast has delivered)
+            if (sweep == 0) { nm_timing_buf[(size_t)(gtid >> 5) * 32 + 29] = tv1 - tv0; nm_timing_buf[(size_t)(gtid >> 5) * 32 + 30] = tv2 - tv0; }
+            else nm_timing_buf[(size_t)(gtid >> 5) * 32 + 31] = tv2 - tv0;
+          }
+#endif
         }
         // pair contacts: rows after all plane contacts (MuJoCo orders contacts by body pair; the world body's pairs come first).
         // All eight lanes run the visit on identical (shared-memory) data, so u stays replicated without a broadcast; the

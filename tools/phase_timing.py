@@ -71,6 +71,10 @@ for rep in range(10):
         add("sub0   pairs per launch handed to MPR (sum, max per warp)", ((pk >> 40).sum(), (pk >> 40).max()))
         add("sub0   candidate filter (support maps)", (np.median(t[:, 30][t[:, 30] > 0]) if (t[:, 30] > 0).any() else 0, t[:, 30].max()))
         add("sub0   MPR + contact blocks", (np.median(t[:, 31][t[:, 31] > 0]) if (t[:, 31] > 0).any() else 0, t[:, 31].max()))
+        if os.environ.get("NM_VISIT") == "1":
+            for nm_, col in (("PGS visit alone (slot 0, sweep 0)", 29), ("PGS slot = visit + broadcast", 30), ("noslip slot = visit + broadcast", 31)):
+                v_ = t[:, col][t[:, col] > 0]
+                if len(v_): add("sub0   " + nm_ + " [min over warps, median]", (v_.min(), np.median(v_) * 1965))
         add("sub0 after P4b -> stamp 6", (np.median(t[:, 6] - t[:, 26]), (t[:, 6] - t[:, 26]).max()))
 print(f"N={N} warps={nw}  (cycles @1.965 GHz; median over 10 steps of [median over warps, max over warps])")
 for k, v in acc.items():
