@@ -633,6 +633,7 @@ static int batch_create_impl(const nm_model* m, int num_envs, int device, uint64
     CUDA_OK(cudaMemcpy(b->d_nadr16, a16.data(), 2 * na_pad, cudaMemcpyHostToDevice));
     a.hull_nbr16 = b->d_nbr16; a.hull_nadr16 = b->d_nadr16;
     a.hull_nv = (int)m->hull4.size(); a.hull_ne_pad = (int)ne_pad; a.hull_na_pad = (int)na_pad;
+    { const char* pf = getenv("NM_PAIR_FILTER_OFF"); a.pair_filter_off = (pf && pf[0] == '1') ? 1 : 0; }
     const char* sw = getenv("NM_HULL_SMEM");
     const size_t bytes = 16 * m->hull4.size() + 2 * ne_pad + 2 * na_pad;
     a.hull_smem = (bytes <= 96 * 1024 && sw && sw[0] == '1') ? 1 : 0;

@@ -98,6 +98,7 @@ struct NmKernelArgs {
   const NmDevCfg* cfg;
   const float4* hull_vert;
   const float* hull_smap;    // support maps of the legs' hulls (NM_SMAP_FLOATS each, at NmGeom::smap_adr)
+  int pair_filter_off;       // test switch (NM_PAIR_FILTER_OFF=1 at batch creation): every pair of overlapping capsules goes to MPR
   // compact adjacency for the support-vertex walk: 16-bit neighbour ids and list offsets (+ hull_vert); small enough
   // (52 KB for the hexapod) to be staged in shared memory by every CTA when hull_smem != 0
   const unsigned short* hull_nbr16;   // [hull_ne_pad]

@@ -1265,7 +1265,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) nm_step_kernel(const NmKernelArgs
         // step is the exact one.  Code size matters more than arithmetic here: one warp in ~40 enters per substep on a walking
         // batch, always with cold instruction lines (the exact scan over both hulls' vertices that stood here cost 9.3 us per
         // visit, `tools/phase_timing.py`, and a one-wave launch lasts as long as its slowest warp).
-        if (oc != 0u) {
+        if (oc != 0u && !A.pair_filter_off) {
           const V3 cw = prel + mul(Xg, ld3(G.center));
           unsigned rem = oc;
 #ifdef NM_TIMING

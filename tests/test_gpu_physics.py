@@ -666,3 +666,48 @@ def test_tibia_tibia_contacts_lockstep():
     assert set_mismatch == 0
     assert agree >= 0.9 * stable
     assert ev.size > 300 and np.median(ev) < 1e-5 and np.percentile(ev, 99) < 1e-3
+
+
+@pytest.mark.gpu
+def test_pair_candidate_filter_is_conservative(monkeypatch):
+    """The support-map candidate filter of the tibia-tibia narrow phase (nm_kernels.cu `smap_support`) may only drop pairs that
+    MPR would reject as well: a batch created with the filter switched off (every pair of overlapping bounding capsules goes to
+    MPR, NM_PAIR_FILTER_OFF=1) must produce bit-identical states -- on robots with their legs thrown across each other (many
+    real pair contacts) and on robots walking on the reference's scripted gait (many near misses)."""
+    G = _common()
+    cm, dm, om = G.models()
+    rng = np.random.default_rng(21)
+    n = 1024
+    qpos = np.tile(cm.qpos0, (n, 1)).astype(np.float32)
+    qpos[: n // 2, 7:] += rng.uniform(-1.0, 1.0, (n // 2, 18)).astype(np.float32)
+    qpos[: n // 2, 2] = rng.uniform(0.06, 0.3, n // 2)
+    qpos[: n // 2, 3:7] += rng.normal(size=(n // 2, 4)).astype(np.float32) * 0.15
+    qpos[:, 3:7] /= np.linalg.norm(qpos[:, 3:7], axis=1, keepdims=True)
+    fast = G.Batch(dm, n, G.DEV, debug=True)
+    monkeypatch.setenv("NM_PAIR_FILTER_OFF", "1")
+    exact = G.Batch(dm, n, G.DEV, debug=True)
+    monkeypatch.delenv("NM_PAIR_FILTER_OFF")
+    z = np.zeros((n, 24))
+    G.push_state(fast, qpos, z, z)
+    G.push_state(exact, qpos, z, z)
+    import os
+    from conftest import ROOT
+    T = np.load(os.path.join(ROOT, "tests", "golden", "nikengine_gait_targets.npz"))["targets"]
+    h = n // 2
+    start = 340 + (np.arange(h) * 3) % 380                              # second half: walking, at different phases of the gait
+    pair_steps = 0
+    ctrl = np.zeros((n, 18), dtype=np.float32)
+    for t in range(120):
+        q = G.gpu_state(fast)[0]
+        if t % 4 == 0:
+            ctrl[:h] = rng.uniform(-8, 8, (h, 18)).astype(np.float32)   # first half: legs thrown across each other
+        ctrl[h:] = np.clip((T[start + t] - q[h:, 7:]) * 12.0, -8, 8).astype(np.float32)
+        fast.physics_step(torch.from_numpy(ctrl), 2)
+        exact.physics_step(torch.from_numpy(ctrl), 2)
+        torch.cuda.synchronize()
+        pair_steps += int((fast.debug.cpu().numpy()[:, 4] > 0).sum())
+        for a, b in zip(G.gpu_state(fast), G.gpu_state(exact)):
+            assert np.array_equal(a, b), f"step {t}: the filter changed a result"
+        assert np.array_equal(fast.sensordata.cpu().numpy(), exact.sensordata.cpu().numpy())
+    print(f"\n[pair filter] {pair_steps} env-steps with pair contacts, states bit-identical with and without the filter")
+    assert pair_steps > 500
