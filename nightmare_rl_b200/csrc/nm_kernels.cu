@@ -2041,6 +2041,10 @@ __global__ void nm_reset_kernel(const NmKernelArgs A, const long long* ids, int 
 // mean episode sums / episode_length_s and latches time_outs.  Also clears the accumulator half the NEXT step
 // will add into, so no memset is needed between steps.
 __global__ void nm_finalize_kernel(const NmKernelArgs A) {
+  // Launched with programmatic stream serialization (nm_launch_finalize): its CTAs are placed while the step kernel is still
+  // running and wait here until that grid has completed and its writes are visible -- the launch latency of this second
+  // kernel disappears behind the first.  A no-op when launched the ordinary way.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const float cnt = A.acc_cur[18];
   if (i < 19) {
@@ -2053,6 +2057,17 @@ __global__ void nm_finalize_kernel(const NmKernelArgs A) {
 }
 
 void nm_launch_finalize(const NmKernelArgs& a, void* stream) {
+  static const bool pdl = getenv("NM_NO_PDL") == nullptr;
+  if (pdl) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((a.num_envs + 255) / 256); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = 0; cfg.stream = static_cast<cudaStream_t>(stream);
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    if (cudaLaunchKernelEx(&cfg, nm_finalize_kernel, a) == cudaSuccess) return;
+    cudaGetLastError();                                  // (not supported in this context: fall through to the ordinary launch)
+  }
   nm_finalize_kernel<<<(a.num_envs + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
 }
 
