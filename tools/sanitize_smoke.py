@@ -7,7 +7,7 @@ from envs.nightmare_v3_config import NightmareV3Config
 from envs.nightmare_v3_env import NightmareV3Env
 from nightmare_rl_b200.ppo import PPO, ActorCritic
 dev = torch.device("cuda:0")
-for n in (301, 4800):
+for n in ([int(x) for x in sys.argv[1:]] or (301, 4000, 4800, 9472)):      # small / one-wave 7-warp / multi-round 7-warp / 8-warp launch shapes
     cfg = NightmareV3Config(); cfg.env.num_envs = n; cfg.viewer.render = cfg.viewer.record_states = False
     env = NightmareV3Env(cfg, seed=1)
     env.reset()
