@@ -22,6 +22,8 @@ def main():
     ap.add_argument("--sizes", default="4096,16384,131072")
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--no-flush", action="store_true", help="do not evict L2 between timed steps")
+    ap.add_argument("--clean-flush", action="store_true", help="follow the 256 MiB memset by a 256 MiB read of a second buffer: L2 then holds "
+                    "clean unrelated lines instead of dirty ones (the step's misses do not have to write anything back first)")
     ap.add_argument("--settle", type=int, default=40, help="untimed steps so that robots are on the ground")
     ap.add_argument("--gait", action="store_true", help="drive the robots with the reference's scripted tripod gait (phase-shifted per env, "
                     "tests/golden/nikengine_gait_targets.npz) instead of N(0,1) actions: walking contacts instead of thrashing")
@@ -29,6 +31,8 @@ def main():
     dev = torch.device("cuda:0")
     gen = torch.Generator(device=dev).manual_seed(7)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    flush2 = torch.zeros(256 << 20, dtype=torch.uint8, device=dev)
+    sink = torch.zeros((), dtype=torch.int64, device=dev)
     out = []
     for n in [int(x) for x in a.sizes.split(",")]:
         cfg = NightmareV3Config()
@@ -54,13 +58,15 @@ def main():
         for i in range(a.steps):
             if not a.no_flush:
                 flush.zero_()
+                if a.clean_flush:
+                    sink.add_(flush2.view(torch.int32)[::1].sum())
             ev[i][0].record()
             env._batch.step(seq[a.settle + i], 1000 + i)
             ev[i][1].record()
         torch.cuda.synchronize()
         ms = sorted(x.elapsed_time(y) for x, y in ev)
         med = ms[len(ms) // 2]
-        out.append(f"N={n}: median {med * 1e3:.1f} us/step  {n / med / 1e3:.1f} M env-steps/s (min {ms[0] * 1e3:.1f} us)")
+        out.append(f"N={n}: mean {sum(ms) / len(ms) * 1e3:.1f} median {med * 1e3:.1f} us/step  {n / med / 1e3:.1f} M env-steps/s (min {ms[0] * 1e3:.1f} us)")
         done_frac = float(env.reset_buf.float().mean())
         out[-1] += f" resets/step {done_frac:.4f}"
         del env, acts, seq
